@@ -1,0 +1,156 @@
+/*
+ * lgae_b200.h -- C ABI of the B200-native LGAE hot path (fp64, sm_100a).
+ *
+ * Drop-in boundary: the reference (zichunhao/lgn-autoencoder) is pure Python; its "operator API" for this
+ * path is the lgn/ module surface.  The Python package lgn_autoencoder_b200 mirrors that surface and calls
+ * the entry points below through ctypes.  Every pointer is a DEVICE pointer to float64 unless stated; every
+ * function returns 0 on success or a negative LGAE_E_* code (never throws), and enqueues its work on the
+ * CUDA stream passed as `stream` (a cudaStream_t cast to void*).
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   lgae_encoder_forward / _backward   lgn/models/lgn_encoder.py:255-336  (LGNEncoder.forward) + autograd
+ *   lgae_decoder_forward / _backward   lgn/models/lgn_decoder.py:218-303  (LGNDecoder.forward) + autograd
+ *   lgae_level_forward  / _backward    lgn/models/lgn_levels.py:96-121    (LGNNodeLevel.forward), which wraps
+ *                                      lgn/cg_lib/cg_ops.py:135-298 (cg_product, aggregate and power),
+ *                                      lgn/nn/g_nn.py:260-278 (CatMixReps), lgn/models/lgn_cg.py:167 (edge features),
+ *                                      lgn/nn/position_levels.py:118-209 (RadPolyTrig.forward),
+ *                                      lgn/cg_lib/zonal_functions.py:123-248 (pairwise zonal functions / norms)
+ *   lgae_mlp_forward    / _backward    lgn/models/lgn_levels.py:191-227   (CGMLP.forward)
+ *   lgae_chamfer                       utils/losses/chamfer_loss/chamfer_loss.py:16-31 + distance_sq.py:263-304
+ *   lgae_cg_product_*, lgae_mix_*      lgn/cg_lib/cg_ops.py:135-218, lgn/nn/g_nn.py:95-117 (generic layer API)
+ *
+ * Internal activation layout ("node layout"): complex numbers are interleaved (re, im) pairs.
+ *   scalars S : (B, N, C, 2)         vectors V : (B, N, C, 4, 2)   (canonical basis of the (1,1) irrep)
+ * The reference's planar layout (2, B, N, C, d) only appears at the module boundary (latent, output).
+ */
+#ifndef LGAE_B200_H
+#define LGAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGAE_MAX_LEVELS 8
+#define LGAE_MAX_LINEAR 12
+#define LGAE_MAX_CHANNELS 8
+
+#define LGAE_OK 0
+#define LGAE_E_BADARG (-1)      /* null pointer / negative size / inconsistent descriptor              */
+#define LGAE_E_UNSUPPORTED (-2) /* configuration outside what the fused path implements                  */
+#define LGAE_E_CUDA (-3)        /* a CUDA runtime call or kernel launch failed (see lgae_last_cuda_error) */
+#define LGAE_E_NODEVICE (-4)
+
+/* latent aggregation modes (lgn/models/lgn_encoder.py:419-496) */
+#define LGAE_LATENT_MEAN 0
+#define LGAE_LATENT_MINMAX 1 /* "min&max": tau doubles                                                    */
+#define LGAE_LATENT_MIN 2
+#define LGAE_LATENT_MAX 3
+#define LGAE_LATENT_SUM 4
+#define LGAE_LATENT_MIX 5    /* nodes x channels mixed by the latent MixReps; no pooling                  */
+
+/* Model descriptor: geometry + offsets (in doubles) of every parameter inside one flat fp64 buffer `theta`.
+ * Gradients are written to a buffer `gtheta` with the same offsets.  Parameter shapes are the reference's
+ * state-dict shapes; complex weights are planar (2, C_out, C_in). */
+typedef struct LgaeModelDesc {
+    int32_t is_decoder;
+    int32_t n_levels;                       /* number of LGN message-passing levels                         */
+    int32_t n_particles;                    /* N                                                            */
+    int32_t n_basis;                        /* K = 2*num_basis_fn radial basis functions (encoder only)     */
+    int32_t channels[LGAE_MAX_LEVELS + 1];  /* C_0 .. C_L                                                   */
+    int32_t has_mlp;                        /* CGMLP after each level                                       */
+    int32_t mlp_hidden;                     /* number of hidden layers (mlp_depth); linears = hidden + 1    */
+    int32_t mlp_width[LGAE_MAX_LEVELS];     /* hidden width of level l = mlp_width_mul * 2 * C_{l+1}        */
+    int32_t latent_mode;                    /* encoder: LGAE_LATENT_*                                       */
+    int32_t tau_s, tau_v;                   /* encoder: latent MixReps outputs; decoder: latent inputs      */
+    int32_t reserved;
+    int64_t n_params;                       /* length of theta                                              */
+    int64_t off_in00, off_in11;             /* input_func_node.weights.(0, 0) / (1, 1): (2, C_0, 1)         */
+    int64_t off_rad_a[LGAE_MAX_LEVELS], off_rad_b[LGAE_MAX_LEVELS], off_rad_c[LGAE_MAX_LEVELS];
+    int64_t off_rad_w0[LGAE_MAX_LEVELS], off_rad_b0[LGAE_MAX_LEVELS];   /* linear.0: (2C|C, K), (2C|C)      */
+    int64_t off_rad_w1[LGAE_MAX_LEVELS], off_rad_b1[LGAE_MAX_LEVELS];   /* linear.1                          */
+    int64_t off_mix00[LGAE_MAX_LEVELS], off_mix11[LGAE_MAX_LEVELS];     /* cat_mix weights (2, C', 5C)       */
+    int64_t off_mlp_w[LGAE_MAX_LEVELS][LGAE_MAX_LINEAR];
+    int64_t off_mlp_b[LGAE_MAX_LEVELS][LGAE_MAX_LINEAR];
+    int64_t off_lat00, off_lat11;           /* encoder mix_reps: (2, tau_s, C_L) / (2, tau_v, C_L) [x N: mix] */
+    int64_t off_graph00, off_graph11;       /* decoder latent_to_graph: (2, N, tau_s) / (2, N, tau_v)        */
+    int64_t off_out00, off_out11;           /* decoder mix_to_output: (2, 1, C_L)                            */
+} LgaeModelDesc;
+
+/* ---- library / device ---------------------------------------------------------------------------- */
+int lgae_version(void);
+const char* lgae_error_string(int code);
+const char* lgae_last_cuda_error(void);
+int lgae_device_sm_count(void);
+/* Number of kernels launched by this library since load (all entry points); bench.py reports the delta. */
+int64_t lgae_launch_count(void);
+
+/* ---- workspace geometry -------------------------------------------------------------------------- */
+/* Doubles of per-batch workspace holding what the backward pass keeps (level inputs, neighbour sums,
+ * pre-MLP scalars, MLP activations).  Allocated by the caller (torch.empty), never by the library. */
+int64_t lgae_workspace_doubles(const LgaeModelDesc* d, int32_t batch);
+/* Offset (doubles) of one saved tensor inside the workspace, or -1.  kind: 0 = S_in[level] (B,N,C,2),
+ * 1 = V_in[level] (B,N,C,4,2) (level == n_levels gives the final features), 2 = pre-MLP scalars of level,
+ * 3 = canonical momenta y (B,N,4,2), 4 = neighbour sums of level (B,N,C,10,2), 5 = masses (B,N) (encoder). */
+int64_t lgae_workspace_offset(const LgaeModelDesc* d, int32_t batch, int32_t kind, int32_t level);
+/* Doubles of scratch for per-CTA partial parameter gradients used by the backward entry points. */
+int64_t lgae_partials_doubles(const LgaeModelDesc* d);
+
+/* ---- whole-model entry points -------------------------------------------------------------------- */
+/* LGNEncoder.forward.  p4 (B,N,4) Cartesian (E,px,py,pz); node_mask (B,N) uint8 or NULL (=> p4[...,0] != 0).
+ * Outputs, planar like the reference: lat00 (2,B,1,T_s,1), lat11 (2,B,1,T_v,4) with T = tau (x2 for min&max);
+ * sel (int32, device) receives the selected particle indices for min/max modes: (4, 2, B, tau_max) laid out as
+ * [kind: smin, smax, vmin, vmax][re/im][b][t]; may be NULL for mean/sum/mix. */
+int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask,
+                         int32_t batch, double* workspace, double* lat00, double* lat11, int32_t* sel, void* stream);
+/* Adjoint.  g_lat00 / g_lat11 may be NULL (treated as zero).  gtheta (n_params) is OVERWRITTEN with the
+ * parameter gradient.  partials: scratch of lgae_partials_doubles(d). */
+int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask,
+                          int32_t batch, double* workspace, const int32_t* sel, const double* g_lat00,
+                          const double* g_lat11, double* gtheta, double* partials, void* stream);
+/* LGNDecoder.forward.  lat11 (2,B,1,tau_v,4) planar complex Cartesian.  recon (2,B,N,4); gen00 (2,B,N,1,1) or NULL. */
+int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch,
+                         double* workspace, double* recon, double* gen00, void* stream);
+/* g_recon (2,B,N,4); g_gen00 (2,B,N,1,1) or NULL.  g_lat11 (2,B,1,tau_v,4) receives the latent gradient. */
+int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch,
+                          double* workspace, const double* g_recon, const double* g_gen00, double* g_lat11,
+                          double* gtheta, double* partials, void* stream);
+
+/* ---- caller-side ops on the hot path ------------------------------------------------------------- */
+/* ChamferLoss (sum over the batch) of x = re(recon) + im(recon) against target (B,M,4).
+ * loss (1 double) is overwritten.  If g_recon != NULL it receives d loss / d recon (2,B,N,4), scaled by
+ * *g_loss (device scalar) when g_loss != NULL.  jet_loss (B) optional per-jet loss (anomaly score). */
+int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss,
+                 double* jet_loss, const double* g_loss, double* g_recon, void* stream);
+/* normalize_p4(..., 'overall_max') (utils/normalize_p4.py:39-52): out = p4 / (max|p4| + 1e-16) per jet. */
+int lgae_normalize_p4(const double* p4, int32_t batch, int32_t n, double* out, double* factor, void* stream);
+/* L1 regulariser: out[0] (+)= lambda * sum |theta| ; gtheta += lambda * sign(theta)  (lgn_encoder.py:249-250). */
+int lgae_l1(const double* theta, int64_t n, double lambda, double* out_accumulate, double* gtheta_accumulate,
+            void* stream);
+
+/* ---- stage-level entry points (LGNNodeLevel / CGMLP), node layout --------------------------------- */
+/* One LGN level at maxdim 2: radial functions -> edge features -> CG aggregation -> CG self product ->
+ * concat -> complex channel mix.  Encoder flavour: p (B,N,4) real Cartesian + node_mask, radial parameters
+ * from theta at level `level`.  Decoder flavour: y (B,N,4,2) complex canonical, constant radial weights.
+ * s_in (B,N,C,2), v_in (B,N,C,4,2) -> s_pre (B,N,C',2), v_out (B,N,C',4,2), sums (B,N,C,10,2). */
+int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
+                       const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
+                       double* sums, double* s_pre, double* v_out, void* stream);
+int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
+                        const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
+                        const double* sums, const double* g_s_pre, const double* g_v_out, double* g_s_in,
+                        double* g_v_in, double* g_y_accumulate, double* partials, void* stream);
+/* CGMLP on rows = batch*N interleaved scalars x (rows, 2C').  acts: (n_hidden, rows, width_padded) saved
+ * activations.  y (rows, 2C'). */
+int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows,
+                     double* acts, double* y, void* stream);
+int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows,
+                      const double* acts, const double* g_y, double* g_x, double* partials, void* stream);
+/* Sum the per-CTA partial gradients into gtheta (overwrite). */
+int lgae_reduce_partials(const LgaeModelDesc* d, const double* partials, double* gtheta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGAE_B200_H */

@@ -1,0 +1,319 @@
+// extern "C" entry points of liblgae_b200.so (declared in include/lgae_b200.h): argument checks, workspace
+// geometry, and the launch sequences of the whole-model forward / backward passes.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "lgae_common.cuh"
+
+namespace lgae {
+
+// ---- implemented in the other translation units -------------------------------------------------------------
+int run_level(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
+              const double* s_in, const double* v_in, double* sums, double* s_pre, double* v_out, const double* g_s_pre,
+              const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y, double* partials, bool bwd, cudaStream_t st);
+int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* x, int64_t rows, double* acts, double* y,
+            const double* g_y, double* g_x, double* partials, bool bwd, cudaStream_t st);
+int mlp_padded_width(const LgaeModelDesc* d, int level);
+int run_enc_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* mass, double* S, double* V, cudaStream_t st);
+int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* mass, int B, const double* gS, const double* gV, double* partials, cudaStream_t st);
+int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* lat00, double* lat11, int32_t* sel, cudaStream_t st);
+int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const int32_t* sel,
+                       const double* g_lat00, const double* g_lat11, double* gS, double* gV, double* partials, cudaStream_t st);
+int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, double* S, double* V, cudaStream_t st);
+int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, const double* gS, const double* gV,
+                      const double* gy, double* g_lat11, double* partials, cudaStream_t st);
+int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st);
+int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const double* g_recon,
+                       const double* g_gen00, double* gS, double* gV, double* partials, cudaStream_t st);
+int run_reduce_partials(const double* partials, int rows, int64_t n, double* gtheta, cudaStream_t st);
+int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
+                double* g_recon, cudaStream_t st);
+int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st);
+int run_l1(const double* theta, int64_t n, double lambda, double* out, double* gtheta, cudaStream_t st);
+
+// ---- bookkeeping ------------------------------------------------------------------------------------------------
+static std::atomic<int64_t> g_launches{0};
+static char g_cuda_error[512] = "";
+static int g_sm_count = 0;
+
+void count_launch(int n) { g_launches += n; }
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return LGAE_OK;
+    snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s", what, cudaGetErrorString(e));
+    return LGAE_E_CUDA;
+}
+int sm_count() {
+    if (g_sm_count > 0) return g_sm_count;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 148;
+    }
+    g_sm_count = n;
+    return n;
+}
+
+// ---- workspace layout -----------------------------------------------------------------------------------------------
+struct Layout {
+    int64_t S[LGAE_MAX_LEVELS + 1], V[LGAE_MAX_LEVELS + 1];
+    int64_t sums[LGAE_MAX_LEVELS], spre[LGAE_MAX_LEVELS], acts[LGAE_MAX_LEVELS];
+    int64_t y, mass, gS[2], gV[2], gSpre, gy, total;
+};
+static int max_channels(const LgaeModelDesc* d) {
+    int m = 1;
+    for (int l = 0; l <= d->n_levels; ++l) m = d->channels[l] > m ? d->channels[l] : m;
+    return m;
+}
+static Layout layout(const LgaeModelDesc* d, int64_t B) {
+    Layout L;
+    const int64_t nodes = B * d->n_particles;
+    int64_t o = 0;
+    auto take = [&](int64_t n) { const int64_t r = o; o += (n + 1) & ~int64_t(1); return r; };
+    L.y = take(nodes * 8);
+    L.mass = take(nodes);
+    for (int l = 0; l <= d->n_levels; ++l) {
+        L.S[l] = take(nodes * d->channels[l] * 2);
+        L.V[l] = take(nodes * d->channels[l] * 8);
+    }
+    for (int l = 0; l < d->n_levels; ++l) {
+        L.sums[l] = take(nodes * d->channels[l] * 20);
+        L.spre[l] = d->has_mlp ? take(nodes * d->channels[l + 1] * 2) : L.S[l + 1];
+        L.acts[l] = d->has_mlp ? take((int64_t)d->mlp_hidden * nodes * mlp_padded_width(d, l)) : 0;
+    }
+    const int cm = max_channels(d);
+    for (int k = 0; k < 2; ++k) { L.gS[k] = take(nodes * cm * 2); L.gV[k] = take(nodes * cm * 8); }
+    L.gSpre = take(nodes * cm * 2);
+    L.gy = take(nodes * 8);
+    L.total = o;
+    return L;
+}
+
+static int check_desc(const LgaeModelDesc* d) {
+    if (!d) return LGAE_E_BADARG;
+    if (d->n_levels < 1 || d->n_levels > LGAE_MAX_LEVELS || d->n_particles < 1 || d->n_params <= 0) return LGAE_E_BADARG;
+    for (int l = 0; l <= d->n_levels; ++l)
+        if (d->channels[l] < 1 || d->channels[l] > LGAE_MAX_CHANNELS) return LGAE_E_UNSUPPORTED;
+    if (d->has_mlp && (d->mlp_hidden < 1 || d->mlp_hidden + 1 > LGAE_MAX_LINEAR)) return LGAE_E_UNSUPPORTED;
+    return LGAE_OK;
+}
+
+#define LGAE_TRY(expr)            \
+    do {                          \
+        const int rc_ = (expr);   \
+        if (rc_ != LGAE_OK) return rc_; \
+    } while (0)
+
+}  // namespace lgae
+
+using namespace lgae;
+
+extern "C" {
+
+int lgae_version(void) { return 100; }
+
+const char* lgae_error_string(int code) {
+    switch (code) {
+        case LGAE_OK: return "ok";
+        case LGAE_E_BADARG: return "bad argument (null pointer, negative size or inconsistent descriptor)";
+        case LGAE_E_UNSUPPORTED: return "configuration not supported by the fused sm_100a path";
+        case LGAE_E_CUDA: return "CUDA error (see lgae_last_cuda_error)";
+        case LGAE_E_NODEVICE: return "no CUDA device";
+        default: return "unknown error";
+    }
+}
+const char* lgae_last_cuda_error(void) { return g_cuda_error; }
+int lgae_device_sm_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return LGAE_E_NODEVICE; }
+    return sm_count();
+}
+int64_t lgae_launch_count(void) { return g_launches.load(); }
+
+int64_t lgae_workspace_doubles(const LgaeModelDesc* d, int32_t batch) {
+    if (check_desc(d) != LGAE_OK || batch < 0) return -1;
+    return layout(d, batch).total;
+}
+int64_t lgae_workspace_offset(const LgaeModelDesc* d, int32_t batch, int32_t kind, int32_t level) {
+    if (check_desc(d) != LGAE_OK || batch < 0 || level < 0 || level > d->n_levels) return -1;
+    const Layout L = layout(d, batch);
+    switch (kind) {
+        case 0: return L.S[level];
+        case 1: return L.V[level];
+        case 2: return level < d->n_levels ? L.spre[level] : -1;
+        case 3: return L.y;
+        case 4: return level < d->n_levels ? L.sums[level] : -1;
+        case 5: return L.mass;
+        case 6: return level < d->n_levels ? L.acts[level] : -1;
+        default: return -1;
+    }
+}
+int64_t lgae_partials_doubles(const LgaeModelDesc* d) {
+    if (check_desc(d) != LGAE_OK) return -1;
+    return (int64_t)sm_count() * d->n_params;
+}
+
+int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
+                         double* ws, double* lat00, double* lat11, int32_t* sel, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (d->is_decoder || !theta || !p4 || !ws || !lat00 || !lat11 || batch < 0) return LGAE_E_BADARG;
+    if (batch == 0) return LGAE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout L = layout(d, batch);
+    const int64_t rows = (int64_t)batch * d->n_particles;
+    LGAE_TRY(run_enc_input(d, theta, p4, batch, ws + L.mass, ws + L.S[0], ws + L.V[0], st));
+    for (int l = 0; l < d->n_levels; ++l) {
+        LGAE_TRY(run_level(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], ws + L.spre[l], ws + L.V[l + 1],
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, st));
+        if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
+    }
+    return run_enc_latent(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], lat00, lat11, sel, st);
+}
+
+int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
+                          double* ws, const int32_t* sel, const double* g_lat00, const double* g_lat11, double* gtheta,
+                          double* partials, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (d->is_decoder || !theta || !p4 || !ws || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = sm_count();
+    if (cudaMemsetAsync(partials, 0, (size_t)G * d->n_params * sizeof(double), st) != cudaSuccess) return check_launch("memset partials");
+    if (batch > 0) {
+        const Layout L = layout(d, batch);
+        const int64_t rows = (int64_t)batch * d->n_particles;
+        const int nl = d->n_levels;
+        int cur = 0;
+        LGAE_TRY(run_enc_latent_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], sel, g_lat00, g_lat11, ws + L.gS[cur], ws + L.gV[cur], partials, st));
+        // The scalar features of the last level only reach the latent scalars: without a gradient on those the
+        // whole last-level MLP is dead in the backward pass ("dead-in-training sub-paths").
+        bool gs_zero = g_lat00 == nullptr;
+        for (int l = nl - 1; l >= 0; --l) {
+            const double* g_spre = nullptr;
+            if (!gs_zero) {
+                if (d->has_mlp) {
+                    LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, partials, true, st));
+                    g_spre = ws + L.gSpre;
+                } else {
+                    g_spre = ws + L.gS[cur];
+                }
+            }
+            LGAE_TRY(run_level(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, nullptr, g_spre,
+                               ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], nullptr, partials, true, st));
+            cur ^= 1;
+            gs_zero = false;
+        }
+        LGAE_TRY(run_enc_input_bwd(d, p4, ws + L.mass, batch, ws + L.gS[cur], ws + L.gV[cur], partials, st));
+    }
+    return run_reduce_partials(partials, G, d->n_params, gtheta, st);
+}
+
+int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
+                         double* gen00, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!d->is_decoder || !theta || !lat11 || !ws || !recon || batch < 0) return LGAE_E_BADARG;
+    if (batch == 0) return LGAE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const Layout L = layout(d, batch);
+    const int64_t rows = (int64_t)batch * d->n_particles;
+    LGAE_TRY(run_dec_input(d, theta, batch, lat11, ws + L.y, ws + L.S[0], ws + L.V[0], st));
+    for (int l = 0; l < d->n_levels; ++l) {
+        LGAE_TRY(run_level(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], ws + L.spre[l], ws + L.V[l + 1],
+                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, st));
+        if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
+    }
+    return run_dec_output(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], recon, gen00, st);
+}
+
+int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws,
+                          const double* g_recon, const double* g_gen00, double* g_lat11, double* gtheta, double* partials, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!d->is_decoder || !theta || !lat11 || !ws || !g_recon || !g_lat11 || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = sm_count();
+    if (cudaMemsetAsync(partials, 0, (size_t)G * d->n_params * sizeof(double), st) != cudaSuccess) return check_launch("memset partials");
+    if (batch > 0) {
+        const Layout L = layout(d, batch);
+        const int64_t rows = (int64_t)batch * d->n_particles;
+        const int nl = d->n_levels;
+        if (cudaMemsetAsync(ws + L.gy, 0, (size_t)rows * 8 * sizeof(double), st) != cudaSuccess) return check_launch("memset gy");
+        int cur = 0;
+        LGAE_TRY(run_dec_output_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], g_recon, g_gen00, ws + L.gS[cur], ws + L.gV[cur], partials, st));
+        bool gs_zero = g_gen00 == nullptr;
+        for (int l = nl - 1; l >= 0; --l) {
+            const double* g_spre = nullptr;
+            if (!gs_zero) {
+                if (d->has_mlp) {
+                    LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, partials, true, st));
+                    g_spre = ws + L.gSpre;
+                } else {
+                    g_spre = ws + L.gS[cur];
+                }
+            }
+            LGAE_TRY(run_level(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, nullptr, g_spre,
+                               ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], ws + L.gy, partials, true, st));
+            cur ^= 1;
+            gs_zero = false;
+        }
+        LGAE_TRY(run_dec_input_bwd(d, theta, batch, lat11, ws + L.y, ws + L.gS[cur], ws + L.gV[cur], ws + L.gy, g_lat11, partials, st));
+    }
+    return run_reduce_partials(partials, G, d->n_params, gtheta, st);
+}
+
+int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,
+                 const double* g_loss, double* g_recon, void* stream) {
+    if (!recon || !target || !jet_loss || batch < 0 || n < 1 || m < 1) return LGAE_E_BADARG;
+    if (batch == 0) {
+        if (loss && cudaMemsetAsync(loss, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) return check_launch("memset loss");
+        return LGAE_OK;
+    }
+    return run_chamfer(recon, target, batch, n, m, loss, jet_loss, g_loss, g_recon, (cudaStream_t)stream);
+}
+
+int lgae_normalize_p4(const double* p4, int32_t batch, int32_t n, double* out, double* factor, void* stream) {
+    if (!p4 || !out || batch < 0 || n < 1) return LGAE_E_BADARG;
+    if (batch == 0) return LGAE_OK;
+    return run_normalize(p4, batch, n, out, factor, (cudaStream_t)stream);
+}
+
+int lgae_l1(const double* theta, int64_t n, double lambda, double* out_accumulate, double* gtheta_accumulate, void* stream) {
+    if (!theta || n < 0) return LGAE_E_BADARG;
+    if (n == 0) return LGAE_OK;
+    return run_l1(theta, n, lambda, out_accumulate, gtheta_accumulate, (cudaStream_t)stream);
+}
+
+int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y, const uint8_t* node_mask,
+                       int32_t batch, const double* s_in, const double* v_in, double* sums, double* s_pre, double* v_out, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!theta || !p_or_y || !s_in || !v_in || !sums || !s_pre || !v_out || batch < 0) return LGAE_E_BADARG;
+    return run_level(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, s_pre, v_out, nullptr, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, false, (cudaStream_t)stream);
+}
+int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y, const uint8_t* node_mask,
+                        int32_t batch, const double* s_in, const double* v_in, const double* sums, const double* g_s_pre,
+                        const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y_accumulate, double* partials, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!theta || !p_or_y || !s_in || !v_in || !sums || !g_v_out || !g_s_in || !g_v_in || !partials || batch < 0) return LGAE_E_BADARG;
+    if (d->is_decoder && !g_y_accumulate) return LGAE_E_BADARG;
+    return run_level(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, const_cast<double*>(sums), nullptr, nullptr, g_s_pre, g_v_out,
+                     g_s_in, g_v_in, g_y_accumulate, partials, true, (cudaStream_t)stream);
+}
+int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, double* acts, double* y,
+                     void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!theta || !x || !acts || !y || rows < 0) return LGAE_E_BADARG;
+    return run_mlp(d, level, theta, x, rows, acts, y, nullptr, nullptr, nullptr, false, (cudaStream_t)stream);
+}
+int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, const double* acts,
+                      const double* g_y, double* g_x, double* partials, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!theta || !x || !acts || !g_y || !partials || rows < 0) return LGAE_E_BADARG;
+    return run_mlp(d, level, theta, x, rows, const_cast<double*>(acts), nullptr, g_y, g_x, partials, true, (cudaStream_t)stream);
+}
+int lgae_reduce_partials(const LgaeModelDesc* d, const double* partials, double* gtheta, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!partials || !gtheta) return LGAE_E_BADARG;
+    return run_reduce_partials(partials, sm_count(), d->n_params, gtheta, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Shared device helpers for the LGAE sm_100a kernels: interleaved-complex arithmetic, the fp64 tensor-core
+// instruction (DMMA m8n8k4), warp/block reductions and the host-side launch bookkeeping.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/lgae_b200.h"
+
+namespace lgae {
+
+typedef double2 cplx;  // x = re, y = im
+
+#define LGAE_DEV __device__ __forceinline__
+
+LGAE_DEV cplx cmake(double re, double im) { return make_double2(re, im); }
+LGAE_DEV cplx czero() { return make_double2(0.0, 0.0); }
+LGAE_DEV cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+LGAE_DEV cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+LGAE_DEV cplx cneg(cplx a) { return make_double2(-a.x, -a.y); }
+LGAE_DEV cplx cconj(cplx a) { return make_double2(a.x, -a.y); }
+LGAE_DEV cplx cscale(cplx a, double s) { return make_double2(a.x * s, a.y * s); }
+LGAE_DEV cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// conj(a) * b
+LGAE_DEV cplx cmulc(cplx a, cplx b) { return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+// acc += a * b
+LGAE_DEV void cfma(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a) * b
+LGAE_DEV void cfmac(cplx& acc, cplx a, cplx b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(-a.y, b.x, acc.y);
+}
+// acc += a * s  (s real)
+LGAE_DEV void cfmar(cplx& acc, cplx a, double s) {
+    acc.x = fma(a.x, s, acc.x);
+    acc.y = fma(a.y, s, acc.y);
+}
+// (1+i) * a   and   (1-i) * a
+LGAE_DEV cplx cmul_1pi(cplx a) { return make_double2(a.x - a.y, a.x + a.y); }
+LGAE_DEV cplx cmul_1mi(cplx a) { return make_double2(a.x + a.y, a.y - a.x); }
+
+// Canonical-basis metric of the (1,1) irrep: eta(a,b) = a0 b0 + a1 b3 - a2 b2 + a3 b1 (complex bilinear,
+// lgn/cg_lib/zonal_functions.py:396-438; equals the Minkowski product of the Cartesian components).
+LGAE_DEV cplx ceta(const cplx* a, const cplx* b) {
+    cplx r = cmul(a[0], b[0]);
+    cfma(r, a[1], b[3]);
+    cfma(r, cneg(a[2]), b[2]);
+    cfma(r, a[3], b[1]);
+    return r;
+}
+// ghat(a)_mu: eta(a,b) = sum_mu ghat(a)_mu b_mu
+LGAE_DEV void cghat(const cplx* a, cplx* out) {
+    out[0] = a[0];
+    out[1] = a[3];
+    out[2] = cneg(a[2]);
+    out[3] = a[1];
+}
+
+#define LGAE_RSQRT2 0.70710678118654752440
+
+// Real Cartesian (t,x,y,z) -> canonical complex components, with the reference's rounding
+// (a matrix product with entries 1 and +-1/sqrt(2), lgn/cg_lib/zonal_functions.py:251-289).
+LGAE_DEV void canon_from_real(const double* p, cplx* y) {
+    const double a = __dmul_rn(LGAE_RSQRT2, p[1]);
+    const double b = __dmul_rn(LGAE_RSQRT2, p[2]);
+    y[0] = cmake(p[0], 0.0);
+    y[1] = cmake(a, -b);
+    y[2] = cmake(p[3], 0.0);
+    y[3] = cmake(-a, -b);
+}
+// Complex Cartesian -> canonical (p_cplx_to_rep, zonal_functions.py:292-341)
+LGAE_DEV void canon_from_cplx(const cplx* p, cplx* y) {
+    y[0] = p[0];
+    y[1] = cmake(LGAE_RSQRT2 * (p[1].x + p[2].y), LGAE_RSQRT2 * (p[1].y - p[2].x));    // (x - i y)/sqrt2
+    y[2] = p[3];
+    y[3] = cmake(-LGAE_RSQRT2 * (p[1].x - p[2].y), -LGAE_RSQRT2 * (p[1].y + p[2].x));  // -(x + i y)/sqrt2
+}
+// Adjoint of canon_from_cplx == rep_to_p (zonal_functions.py:344-381): canonical -> complex Cartesian
+LGAE_DEV void cart_from_canon(const cplx* v, cplx* p) {
+    p[0] = v[0];
+    p[1] = cmake(LGAE_RSQRT2 * (v[1].x - v[3].x), LGAE_RSQRT2 * (v[1].y - v[3].y));
+    // i * (v1 + v3) / sqrt2
+    p[2] = cmake(-LGAE_RSQRT2 * (v[1].y + v[3].y), LGAE_RSQRT2 * (v[1].x + v[3].x));
+    p[3] = v[2];
+}
+
+// Minkowski square of a real 4-vector with the reference's exact rounding sequence
+// (zonal_functions.py:201-218: psq = p**2 ; 2*psq[0] - psq.sum(-1), torch sums the 4 terms left to right).
+LGAE_DEV double minkowski_sq(double p0, double p1, double p2, double p3) {
+    const double q0 = __dmul_rn(p0, p0), q1 = __dmul_rn(p1, p1), q2 = __dmul_rn(p2, p2), q3 = __dmul_rn(p3, p3);
+    const double s = __dadd_rn(__dadd_rn(__dadd_rn(q0, q1), q2), q3);
+    return __dsub_rn(__dmul_rn(2.0, q0), s);
+}
+
+// D(8x8) += A(8x4) * B(4x8), fp64 tensor-core MMA.  Fragment layout (g = lane>>2, q = lane&3):
+//   a = A[g][q], b = B[q][g], c0/c1 = C[g][2q], C[g][2q+1].
+LGAE_DEV void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+LGAE_DEV double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in thread 0.  `scratch` must hold >= 32 doubles.
+LGAE_DEV double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        r = lane < nw ? scratch[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+LGAE_DEV double leaky(double x, double slope) { return x > 0.0 ? x : x * slope; }
+
+// ---- host side ------------------------------------------------------------------------------------
+void count_launch(int n = 1);
+int check_launch(const char* what);
+int sm_count();
+
+}  // namespace lgae

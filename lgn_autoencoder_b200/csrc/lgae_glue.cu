@@ -1,0 +1,741 @@
+// Encoder / decoder glue around the LGN levels, and the caller-side ops of the training step:
+//   enc_input   : LGNEncoder._prepare_input + input MixReps      (lgn/models/lgn_encoder.py:338-412, 290-296)
+//   enc_latent  : latent MixReps + rep_to_p + pooling             (lgn_encoder.py:313-336, 419-583)
+//   dec_input   : latent_to_graph + p_cplx_to_rep + input MixReps (lgn/models/lgn_decoder.py:305-345, 259-262)
+//   dec_output  : mix_to_output + rep_to_p                        (lgn_decoder.py:286-296)
+//   chamfer     : ChamferLoss over cdist                          (utils/losses/chamfer_loss/chamfer_loss.py:16-31)
+//   normalize_p4, L1 regulariser, partial-gradient reduction.
+// All of these are O(B*N*C) memory-trivial kernels; they exist so that a training step never leaves the
+// library's node layout and launches ~35 kernels instead of the reference's several thousand ATen calls.
+#include "lgae_common.cuh"
+
+namespace lgae {
+
+constexpr int MAXC = LGAE_MAX_CHANNELS;
+
+// planar complex weight (2, R, Cc) at theta+off -> element [r][cc]
+LGAE_DEV cplx wget(const double* theta, int64_t off, int rows, int cols, int r, int cc) {
+    const int64_t idx = off + (int64_t)r * cols + cc;
+    return cmake(theta[idx], theta[idx + (int64_t)rows * cols]);
+}
+LGAE_DEV void padd(double* part, int64_t off, int rows, int cols, int r, int cc, cplx v) {
+    const int64_t idx = off + (int64_t)r * cols + cc;
+    part[idx] += v.x;
+    part[idx + (int64_t)rows * cols] += v.y;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// encoder input
+// ------------------------------------------------------------------------------------------------------------
+__global__ void enc_input_kernel(const double* theta, int64_t off00, int64_t off11, const double* p4, int64_t nodes, int C,
+                                 double* mass, double* S, double* V) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nodes) return;
+    const double* p = p4 + 4 * t;
+    const double m = __dsqrt_rn(fabs(minkowski_sq(p[0], p[1], p[2], p[3])));   // lgn_encoder.py:376
+    mass[t] = m;
+    cplx y[4];
+    canon_from_real(p, y);
+    for (int c = 0; c < C; ++c) {
+        const cplx w0 = wget(theta, off00, C, 1, c, 0), w1 = wget(theta, off11, C, 1, c, 0);
+        reinterpret_cast<cplx*>(S)[t * C + c] = cscale(w0, m);
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(V)[(t * C + c) * 4 + mu] = cmul(w1, y[mu]);
+    }
+}
+
+__global__ void __launch_bounds__(256) enc_input_bwd_kernel(int64_t off00, int64_t off11, const double* p4, const double* mass, int64_t nodes,
+                                                            int C, const double* gS, const double* gV, double* partials, int64_t n_params) {
+    __shared__ double scratch[32];
+    double acc[MAXC][4];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nodes; t += (int64_t)gridDim.x * blockDim.x) {
+        const double m = mass[t];
+        cplx y[4];
+        canon_from_real(p4 + 4 * t, y);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            if (c < C) {
+                if (gS) {
+                    const cplx g = reinterpret_cast<const cplx*>(gS)[t * C + c];
+                    acc[c][0] = fma(m, g.x, acc[c][0]);
+                    acc[c][1] = fma(m, g.y, acc[c][1]);
+                }
+                cplx s = czero();
+#pragma unroll
+                for (int mu = 0; mu < 4; ++mu) cfmac(s, y[mu], reinterpret_cast<const cplx*>(gV)[(t * C + c) * 4 + mu]);
+                acc[c][2] += s.x;
+                acc[c][3] += s.y;
+            }
+        }
+    }
+    double* part = partials + (int64_t)blockIdx.x * n_params;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const double v = block_sum(acc[c][x], scratch);
+                if (threadIdx.x == 0) {
+                    const int64_t off = x < 2 ? off00 : off11;
+                    part[off + (x & 1) * C + c] += v;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// encoder latent map
+// ------------------------------------------------------------------------------------------------------------
+struct LatentArgs {
+    const double* theta;
+    int64_t off00, off11;
+    int B, N, C, tau_s, tau_v, mode;
+    const double* S;   // (B,N,C,2)
+    const double* V;   // (B,N,C,4,2)
+    double* lat00;     // (2,B,1,Ts,1)
+    double* lat11;     // (2,B,1,Tv,4)
+    int32_t* sel;      // (4,2,B,tau_max)
+    const double* g_lat00;
+    const double* g_lat11;
+    double* gS;
+    double* gV;
+    double* partials;
+    int64_t n_params;
+};
+
+LGAE_DEV double msq_of(const double* v) {   // get_msq, lgn_encoder.py:499-505 (sqrt, then square)
+    const double nrm = __dsqrt_rn(v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+    return v[0] * v[0] - nrm * nrm;
+}
+
+// One CTA per jet.  Shared: L00 (N*tau_s complex), L11 Cartesian (N*tau_v*4 complex).
+__global__ void __launch_bounds__(256) enc_latent_kernel(const LatentArgs a) {
+    extern __shared__ __align__(128) double smem[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int N = a.N, C = a.C, ts = a.tau_s, tv = a.tau_v;
+    const bool mix = a.mode == LGAE_LATENT_MIX;
+    const int rows = mix ? 1 : N;        // 'mix' contracts particles and channels together
+    const int cin = mix ? N * C : C;
+    cplx* L00 = reinterpret_cast<cplx*>(smem);
+    cplx* L11 = L00 + rows * ts;
+    const cplx* S = reinterpret_cast<const cplx*>(a.S) + (int64_t)b * N * C;
+    const cplx* V = reinterpret_cast<const cplx*>(a.V) + (int64_t)b * N * C * 4;
+    for (int it = tid; it < rows * ts; it += blockDim.x) {
+        const int i = it / ts, t = it % ts;
+        cplx acc = czero();
+        for (int k = 0; k < cin; ++k) cfma(acc, wget(a.theta, a.off00, ts, cin, t, k), S[i * cin + k]);
+        L00[it] = acc;
+    }
+    for (int it = tid; it < rows * tv; it += blockDim.x) {
+        const int i = it / tv, t = it % tv;
+        cplx acc[4] = {czero(), czero(), czero(), czero()};
+        for (int k = 0; k < cin; ++k) {
+            const cplx w = wget(a.theta, a.off11, tv, cin, t, k);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cfma(acc[mu], w, V[(i * cin + k) * 4 + mu]);
+        }
+        cplx cart[4];
+        cart_from_canon(acc, cart);
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) L11[it * 4 + mu] = cart[mu];
+    }
+    __syncthreads();
+    const int B = a.B;
+    const int mode = a.mode;
+    if (mode == LGAE_LATENT_MEAN || mode == LGAE_LATENT_SUM || mix) {
+        const double scale = mode == LGAE_LATENT_MEAN ? 1.0 / N : 1.0;
+        for (int it = tid; it < ts; it += blockDim.x) {
+            cplx acc = czero();
+            for (int i = 0; i < rows; ++i) acc = cadd(acc, L00[i * ts + it]);
+            a.lat00[(int64_t)(0 * B + b) * ts + it] = acc.x * scale;
+            a.lat00[(int64_t)(1 * B + b) * ts + it] = acc.y * scale;
+        }
+        for (int it = tid; it < tv * 4; it += blockDim.x) {
+            cplx acc = czero();
+            for (int i = 0; i < rows; ++i) acc = cadd(acc, L11[i * tv * 4 + it]);
+            a.lat11[(int64_t)(0 * B + b) * tv * 4 + it] = acc.x * scale;
+            a.lat11[(int64_t)(1 * B + b) * tv * 4 + it] = acc.y * scale;
+        }
+        return;
+    }
+    // min / max / min&max: arg-select per (re|im, tau), re and im parts independently (lgn_encoder.py:540-583)
+    const bool both = mode == LGAE_LATENT_MINMAX;
+    const int Ts = both ? 2 * ts : ts, Tv = both ? 2 * tv : tv;
+    const int tmax = ts > tv ? ts : tv;
+    for (int it = tid; it < 2 * 2 * ts; it += blockDim.x) {          // scalars: [kind][part][t]
+        const int t = it % ts, part = (it / ts) & 1, kind = it / (2 * ts);   // kind 0 = min, 1 = max
+        if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
+        int best = 0;
+        double bv = 0.0;
+        for (int i = 0; i < N; ++i) {
+            const cplx z = L00[i * ts + t];
+            const double s = part ? z.y : z.x;
+            const double key = kind ? s * s : s;                     // max selects on s^2 (get_msq of a scalar)
+            if (i == 0 || (kind ? key > bv : key < bv)) { bv = key; best = i; }
+        }
+        const cplx z = L00[best * ts + t];
+        const int T = (both && kind) ? ts + t : t;
+        a.lat00[(int64_t)(part * B + b) * Ts + T] = part ? z.y : z.x;
+        if (a.sel) a.sel[((int64_t)((kind)*2 + part) * B + b) * tmax + t] = best;
+    }
+    for (int it = tid; it < 2 * 2 * tv; it += blockDim.x) {          // vectors
+        const int t = it % tv, part = (it / tv) & 1, kind = it / (2 * tv);
+        if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
+        int best = 0;
+        double bv = 0.0;
+        for (int i = 0; i < N; ++i) {
+            double v[4];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) { const cplx z = L11[(i * tv + t) * 4 + mu]; v[mu] = part ? z.y : z.x; }
+            const double key = msq_of(v);
+            if (i == 0 || (kind ? key > bv : key < bv)) { bv = key; best = i; }
+        }
+        const int T = (both && kind) ? tv + t : t;
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) {
+            const cplx z = L11[(best * tv + t) * 4 + mu];
+            a.lat11[((int64_t)(part * B + b) * Tv + T) * 4 + mu] = part ? z.y : z.x;
+        }
+        if (a.sel) a.sel[((int64_t)((2 + kind) * 2 + part) * B + b) * tmax + t] = best;
+    }
+}
+
+// Adjoint of enc_latent.  Persistent CTAs over jets; latent-weight gradients accumulate in shared memory.
+__global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a) {
+    extern __shared__ __align__(128) double smem[];
+    const int tid = threadIdx.x;
+    const int N = a.N, C = a.C, ts = a.tau_s, tv = a.tau_v, B = a.B, mode = a.mode;
+    const bool mix = mode == LGAE_LATENT_MIX;
+    const int rows = mix ? 1 : N, cin = mix ? N * C : C;
+    cplx* gL00 = reinterpret_cast<cplx*>(smem);       // rows*ts
+    cplx* gL11 = gL00 + rows * ts;                    // rows*tv*4 (canonical after the basis change)
+    cplx* gw00 = gL11 + rows * tv * 4;                // ts*cin
+    cplx* gw11 = gw00 + ts * cin;                     // tv*cin
+    for (int t = tid; t < (ts + tv) * cin; t += blockDim.x) gw00[t] = czero();
+    const bool both = mode == LGAE_LATENT_MINMAX;
+    const int Ts = both ? 2 * ts : ts, Tv = both ? 2 * tv : tv;
+    const int tmax = ts > tv ? ts : tv;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int t = tid; t < rows * (ts + 4 * tv); t += blockDim.x) gL00[t] = czero();
+        __syncthreads();
+        if (mode == LGAE_LATENT_MEAN || mode == LGAE_LATENT_SUM || mix) {
+            const double scale = mode == LGAE_LATENT_MEAN ? 1.0 / N : 1.0;
+            for (int it = tid; it < rows * ts; it += blockDim.x) {
+                const int t = it % ts;
+                if (a.g_lat00) gL00[it] = cmake(a.g_lat00[(int64_t)(0 * B + b) * ts + t] * scale, a.g_lat00[(int64_t)(1 * B + b) * ts + t] * scale);
+            }
+            for (int it = tid; it < rows * tv * 4; it += blockDim.x) {
+                const int r = it % (tv * 4);
+                if (a.g_lat11) gL11[it] = cmake(a.g_lat11[(int64_t)(0 * B + b) * tv * 4 + r] * scale, a.g_lat11[(int64_t)(1 * B + b) * tv * 4 + r] * scale);
+            }
+        } else {
+            // scatter: one thread per (tau) handles its 2 kinds x 2 parts sequentially => no write conflicts
+            for (int t = tid; t < ts; t += blockDim.x) {
+                if (!a.g_lat00) break;
+                for (int kind = 0; kind < 2; ++kind) {
+                    if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
+                    const int T = (both && kind) ? ts + t : t;
+                    for (int part = 0; part < 2; ++part) {
+                        const int i = a.sel[((int64_t)(kind * 2 + part) * B + b) * tmax + t];
+                        const double gv = a.g_lat00[(int64_t)(part * B + b) * Ts + T];
+                        if (part) gL00[i * ts + t].y += gv; else gL00[i * ts + t].x += gv;
+                    }
+                }
+            }
+            for (int t = tid; t < tv; t += blockDim.x) {
+                if (!a.g_lat11) break;
+                for (int kind = 0; kind < 2; ++kind) {
+                    if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
+                    const int T = (both && kind) ? tv + t : t;
+                    for (int part = 0; part < 2; ++part) {
+                        const int i = a.sel[((int64_t)((2 + kind) * 2 + part) * B + b) * tmax + t];
+                        for (int mu = 0; mu < 4; ++mu) {
+                            const double gv = a.g_lat11[((int64_t)(part * B + b) * Tv + T) * 4 + mu];
+                            if (part) gL11[(i * tv + t) * 4 + mu].y += gv; else gL11[(i * tv + t) * 4 + mu].x += gv;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // adjoint of rep_to_p: Cartesian gradient -> canonical
+        for (int it = tid; it < rows * tv; it += blockDim.x) {
+            cplx gc[4], gy[4];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) gc[mu] = gL11[it * 4 + mu];
+            canon_from_cplx(gc, gy);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) gL11[it * 4 + mu] = gy[mu];
+        }
+        __syncthreads();
+        const cplx* S = reinterpret_cast<const cplx*>(a.S) + (int64_t)b * N * C;
+        const cplx* V = reinterpret_cast<const cplx*>(a.V) + (int64_t)b * N * C * 4;
+        // feature gradients
+        for (int it = tid; it < rows * cin; it += blockDim.x) {
+            const int i = it / cin, k = it % cin;
+            cplx gs = czero(), gv[4] = {czero(), czero(), czero(), czero()};
+            for (int t = 0; t < ts; ++t) cfmac(gs, wget(a.theta, a.off00, ts, cin, t, k), gL00[i * ts + t]);
+            for (int t = 0; t < tv; ++t) {
+                const cplx w = wget(a.theta, a.off11, tv, cin, t, k);
+#pragma unroll
+                for (int mu = 0; mu < 4; ++mu) cfmac(gv[mu], w, gL11[(i * tv + t) * 4 + mu]);
+            }
+            reinterpret_cast<cplx*>(a.gS)[(int64_t)b * N * C + it] = gs;
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(a.gV)[((int64_t)b * N * C + it) * 4 + mu] = gv[mu];
+        }
+        // weight gradients: one thread per (t, k)
+        for (int it = tid; it < ts * cin; it += blockDim.x) {
+            const int t = it / cin, k = it % cin;
+            cplx acc = czero();
+            for (int i = 0; i < rows; ++i) cfmac(acc, S[i * cin + k], gL00[i * ts + t]);
+            gw00[it] = cadd(gw00[it], acc);
+        }
+        for (int it = tid; it < tv * cin; it += blockDim.x) {
+            const int t = it / cin, k = it % cin;
+            cplx acc = czero();
+            for (int i = 0; i < rows; ++i)
+#pragma unroll
+                for (int mu = 0; mu < 4; ++mu) cfmac(acc, V[(i * cin + k) * 4 + mu], gL11[(i * tv + t) * 4 + mu]);
+            gw11[it] = cadd(gw11[it], acc);
+        }
+    }
+    __syncthreads();
+    double* part = a.partials + (int64_t)blockIdx.x * a.n_params;
+    for (int it = tid; it < ts * cin; it += blockDim.x) padd(part, a.off00, ts, cin, it / cin, it % cin, gw00[it]);
+    for (int it = tid; it < tv * cin; it += blockDim.x) padd(part, a.off11, tv, cin, it / cin, it % cin, gw11[it]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// decoder input
+// ------------------------------------------------------------------------------------------------------------
+struct DecInArgs {
+    const double* theta;
+    int64_t off_g11, off_in00, off_in11;
+    int B, N, C, tau;
+    const double* lat11;   // (2,B,1,tau,4)
+    double* y;             // (B,N,4,2)
+    double* S;
+    double* V;
+    const double* gS;
+    const double* gV;
+    const double* gy;      // accumulated by the level adjoints
+    double* g_lat11;
+    double* partials;
+    int64_t n_params;
+};
+
+__global__ void __launch_bounds__(128) dec_input_kernel(const DecInArgs a) {
+    extern __shared__ __align__(128) double smem[];
+    cplx* lat = reinterpret_cast<cplx*>(smem);   // tau*4
+    const int b = blockIdx.x, tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau, B = a.B;
+    for (int t = tid; t < tau * 4; t += blockDim.x)
+        lat[t] = cmake(a.lat11[(int64_t)(0 * B + b) * tau * 4 + t], a.lat11[(int64_t)(1 * B + b) * tau * 4 + t]);
+    __syncthreads();
+    for (int i = tid; i < N; i += blockDim.x) {
+        cplx P[4] = {czero(), czero(), czero(), czero()};
+        for (int t = 0; t < tau; ++t) {
+            const cplx w = wget(a.theta, a.off_g11, N, tau, i, t);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cfma(P[mu], w, lat[t * 4 + mu]);
+        }
+        cplx y[4];
+        canon_from_cplx(P, y);
+        const int64_t node = (int64_t)b * N + i;
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(a.y)[node * 4 + mu] = y[mu];
+        for (int c = 0; c < C; ++c) {
+            const cplx w0 = wget(a.theta, a.off_in00, C, 1, c, 0), w1 = wget(a.theta, a.off_in11, C, 1, c, 0);
+            reinterpret_cast<cplx*>(a.S)[node * C + c] = cmul_1pi(w0);     // zonal (0,0) = 1 + 1j (zonal_functions.py:150-154)
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(a.V)[(node * C + c) * 4 + mu] = cmul(w1, y[mu]);
+        }
+    }
+}
+
+// Persistent over jets, one thread per particle (N <= blockDim.x required).
+__global__ void __launch_bounds__(128) dec_input_bwd_kernel(const DecInArgs a) {
+    extern __shared__ __align__(128) double smem[];
+    const int tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau, B = a.B;
+    cplx* lat = reinterpret_cast<cplx*>(smem);   // tau*4
+    cplx* gP_s = lat + tau * 4;                  // N*4
+    cplx* gwg = gP_s + N * 4;                    // N*tau   accumulators
+    cplx* gin = gwg + N * tau;                   // 2*C     accumulators (in00, in11)
+    for (int t = tid; t < N * tau + 2 * C; t += blockDim.x) gwg[t] = czero();
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        for (int t = tid; t < tau * 4; t += blockDim.x)
+            lat[t] = cmake(a.lat11[(int64_t)(0 * B + b) * tau * 4 + t], a.lat11[(int64_t)(1 * B + b) * tau * 4 + t]);
+        if (tid < N) {
+            const int i = tid;
+            const int64_t node = (int64_t)b * N + i;
+            cplx gy[4], y[4];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) {
+                gy[mu] = reinterpret_cast<const cplx*>(a.gy)[node * 4 + mu];
+                y[mu] = reinterpret_cast<const cplx*>(a.y)[node * 4 + mu];
+            }
+            for (int c = 0; c < C; ++c) {
+                const cplx w1 = wget(a.theta, a.off_in11, C, 1, c, 0);
+#pragma unroll
+                for (int mu = 0; mu < 4; ++mu) cfmac(gy[mu], w1, reinterpret_cast<const cplx*>(a.gV)[(node * C + c) * 4 + mu]);
+            }
+            cplx gP[4];
+            cart_from_canon(gy, gP);   // adjoint of p_cplx_to_rep
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) gP_s[i * 4 + mu] = gP[mu];
+        }
+        __syncthreads();
+        // input-mix weight gradients (reduce over particles with shared-memory atomics: N*C*2 adds per jet)
+        for (int it = tid; it < N * C; it += blockDim.x) {
+            const int i = it / C, c = it % C;
+            const int64_t node = (int64_t)b * N + i;
+            cplx g11 = czero();
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu)
+                cfmac(g11, reinterpret_cast<const cplx*>(a.y)[node * 4 + mu], reinterpret_cast<const cplx*>(a.gV)[(node * C + c) * 4 + mu]);
+            atomicAdd(&gin[C + c].x, g11.x);
+            atomicAdd(&gin[C + c].y, g11.y);
+            if (a.gS) {
+                const cplx g00 = cmul_1mi(reinterpret_cast<const cplx*>(a.gS)[node * C + c]);
+                atomicAdd(&gin[c].x, g00.x);
+                atomicAdd(&gin[c].y, g00.y);
+            }
+        }
+        // latent_to_graph weight gradient and latent gradient
+        for (int it = tid; it < N * tau; it += blockDim.x) {
+            const int i = it / tau, t = it % tau;
+            cplx acc = czero();
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cfmac(acc, lat[t * 4 + mu], gP_s[i * 4 + mu]);
+            gwg[it] = cadd(gwg[it], acc);
+        }
+        for (int it = tid; it < tau * 4; it += blockDim.x) {
+            const int t = it / 4, mu = it % 4;
+            cplx acc = czero();
+            for (int i = 0; i < N; ++i) cfmac(acc, wget(a.theta, a.off_g11, N, tau, i, t), gP_s[i * 4 + mu]);
+            a.g_lat11[(int64_t)(0 * B + b) * tau * 4 + it] = acc.x;
+            a.g_lat11[(int64_t)(1 * B + b) * tau * 4 + it] = acc.y;
+        }
+    }
+    __syncthreads();
+    double* part = a.partials + (int64_t)blockIdx.x * a.n_params;
+    for (int it = tid; it < N * tau; it += blockDim.x) padd(part, a.off_g11, N, tau, it / tau, it % tau, gwg[it]);
+    for (int c = tid; c < C; c += blockDim.x) {
+        padd(part, a.off_in00, C, 1, c, 0, gin[c]);
+        padd(part, a.off_in11, C, 1, c, 0, gin[C + c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// decoder output
+// ------------------------------------------------------------------------------------------------------------
+__global__ void dec_output_kernel(const double* theta, int64_t off00, int64_t off11, int B, int N, int C, const double* S,
+                                  const double* V, double* recon, double* gen00) {
+    const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= (int64_t)B * N) return;
+    cplx gen[4] = {czero(), czero(), czero(), czero()}, g0 = czero();
+    for (int c = 0; c < C; ++c) {
+        const cplx w1 = wget(theta, off11, 1, C, 0, c);
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) cfma(gen[mu], w1, reinterpret_cast<const cplx*>(V)[(node * C + c) * 4 + mu]);
+        if (gen00) cfma(g0, wget(theta, off00, 1, C, 0, c), reinterpret_cast<const cplx*>(S)[node * C + c]);
+    }
+    cplx p[4];
+    cart_from_canon(gen, p);
+#pragma unroll
+    for (int mu = 0; mu < 4; ++mu) {
+        recon[node * 4 + mu] = p[mu].x;
+        recon[((int64_t)B * N + node) * 4 + mu] = p[mu].y;
+    }
+    if (gen00) {
+        gen00[node] = g0.x;
+        gen00[(int64_t)B * N + node] = g0.y;
+    }
+}
+
+__global__ void __launch_bounds__(256) dec_output_bwd_kernel(const double* theta, int64_t off00, int64_t off11, int B, int N, int C,
+                                                             const double* S, const double* V, const double* g_recon, const double* g_gen00,
+                                                             double* gS, double* gV, double* partials, int64_t n_params) {
+    __shared__ double scratch[32];
+    double acc[MAXC][4];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.0;
+    const int64_t nodes = (int64_t)B * N;
+    for (int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; node < nodes; node += (int64_t)gridDim.x * blockDim.x) {
+        cplx gp[4], gg[4];
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) gp[mu] = cmake(g_recon[node * 4 + mu], g_recon[(nodes + node) * 4 + mu]);
+        canon_from_cplx(gp, gg);    // adjoint of rep_to_p
+        const cplx g0 = g_gen00 ? cmake(g_gen00[node], g_gen00[nodes + node]) : czero();
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            if (c < C) {
+                const cplx w1 = wget(theta, off11, 1, C, 0, c);
+                cplx gw = czero();
+#pragma unroll
+                for (int mu = 0; mu < 4; ++mu) {
+                    reinterpret_cast<cplx*>(gV)[(node * C + c) * 4 + mu] = cmulc(w1, gg[mu]);
+                    cfmac(gw, reinterpret_cast<const cplx*>(V)[(node * C + c) * 4 + mu], gg[mu]);
+                }
+                acc[c][2] += gw.x;
+                acc[c][3] += gw.y;
+                if (g_gen00) {
+                    reinterpret_cast<cplx*>(gS)[node * C + c] = cmulc(wget(theta, off00, 1, C, 0, c), g0);
+                    const cplx gw0 = cmulc(reinterpret_cast<const cplx*>(S)[node * C + c], g0);
+                    acc[c][0] += gw0.x;
+                    acc[c][1] += gw0.y;
+                }
+            }
+        }
+    }
+    double* part = partials + (int64_t)blockIdx.x * n_params;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const double v = block_sum(acc[c][x], scratch);
+                if (threadIdx.x == 0) part[(x < 2 ? off00 : off11) + (x & 1) * C + c] += v;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// chamfer loss (+ gradient), normalisation, L1, reductions
+// ------------------------------------------------------------------------------------------------------------
+// One CTA per jet.  x_i = re(recon_i) + im(recon_i)  (get_real 'sum', utils/utils.py:201-202).
+__global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const double* target, int B, int N, int M, double* jet_loss,
+                                                      const double* g_loss, double* g_recon) {
+    extern __shared__ __align__(128) double smem[];
+    double* x = smem;            // N*4
+    double* t = x + 4 * N;       // M*4
+    double* m1 = t + 4 * M;      // N
+    double* m2 = m1 + N;         // M
+    int* j1 = reinterpret_cast<int*>(m2 + M);   // N
+    int* i2 = j1 + N;                            // M
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int64_t plane = (int64_t)B * N * 4;
+    for (int k = tid; k < 4 * N; k += blockDim.x) x[k] = recon[(int64_t)b * N * 4 + k] + recon[plane + (int64_t)b * N * 4 + k];
+    for (int k = tid; k < 4 * M; k += blockDim.x) t[k] = target[(int64_t)b * M * 4 + k];
+    __syncthreads();
+    auto dist = [&](int i, int j) {
+        double s = 0.0;
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) { const double d = x[4 * i + mu] - t[4 * j + mu]; s += d * d; }
+        return s;
+    };
+    for (int i = tid; i < N; i += blockDim.x) {
+        double best = dist(i, 0);
+        int bj = 0;
+        for (int j = 1; j < M; ++j) { const double d = dist(i, j); if (d < best) { best = d; bj = j; } }
+        m1[i] = best; j1[i] = bj;
+    }
+    for (int j = tid; j < M; j += blockDim.x) {
+        double best = dist(0, j);
+        int bi = 0;
+        for (int i = 1; i < N; ++i) { const double d = dist(i, j); if (d < best) { best = d; bi = i; } }
+        m2[j] = best; i2[j] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = 0; i < N; ++i) s += m1[i];
+        for (int j = 0; j < M; ++j) s += m2[j];
+        jet_loss[b] = 0.5 * s;
+    }
+    if (g_recon) {
+        const double scale = g_loss ? *g_loss : 1.0;
+        for (int i = tid; i < N; i += blockDim.x) {
+            double g[4];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) g[mu] = x[4 * i + mu] - t[4 * j1[i] + mu];
+            for (int j = 0; j < M; ++j)
+                if (i2[j] == i) {
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) g[mu] += x[4 * i + mu] - t[4 * j + mu];
+                }
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) {
+                const double v = g[mu] * scale;
+                g_recon[((int64_t)b * N + i) * 4 + mu] = v;
+                g_recon[plane + ((int64_t)b * N + i) * 4 + mu] = v;
+            }
+        }
+    }
+}
+
+// Deterministic single-block sum of n values: out[0] = sum (or += when accumulate).
+__global__ void __launch_bounds__(1024) sum_kernel(const double* v, int64_t n, double scale, double* out, int accumulate) {
+    __shared__ double scratch[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.0) + scale * s;
+}
+
+__global__ void __launch_bounds__(128) normalize_kernel(const double* p4, int N, double* out, double* factor) {
+    __shared__ double scratch[32];
+    const int b = blockIdx.x;
+    double m = 0.0;
+    for (int k = threadIdx.x; k < 4 * N; k += blockDim.x) m = fmax(m, fabs(p4[(int64_t)b * N * 4 + k]));
+    // block max via the sum helper's scratch
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = m;
+    __syncthreads();
+    double f = 0.0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) f = fmax(f, scratch[w]);
+    f = f + 1e-16;
+    if (threadIdx.x == 0 && factor) factor[b] = f;
+    for (int k = threadIdx.x; k < 4 * N; k += blockDim.x) out[(int64_t)b * N * 4 + k] = p4[(int64_t)b * N * 4 + k] / f;
+}
+
+// Single block: the parameter vector has ~3e4..3e5 entries.  out[0] += lambda * sum|theta| ; gtheta += lambda * sign(theta).
+__global__ void __launch_bounds__(1024) l1_kernel(const double* theta, int64_t n, double lambda, double* out, double* gtheta) {
+    __shared__ double scratch[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = theta[i];
+        s += fabs(v);
+        if (gtheta) gtheta[i] += lambda * (v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0));
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0 && out) out[0] += lambda * s;
+}
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* partials, int rows, int64_t n, double* gtheta) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double s = 0.0;
+    for (int r = 0; r < rows; ++r) s += partials[(int64_t)r * n + p];
+    gtheta[p] = s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host wrappers used by lgae_api.cu
+// ------------------------------------------------------------------------------------------------------------
+int run_enc_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* mass, double* S, double* V, cudaStream_t st) {
+    const int64_t nodes = (int64_t)B * d->n_particles;
+    enc_input_kernel<<<(unsigned)((nodes + 127) / 128), 128, 0, st>>>(theta, d->off_in00, d->off_in11, p4, nodes, d->channels[0], mass, S, V);
+    count_launch();
+    return check_launch("enc_input");
+}
+int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* mass, int B, const double* gS, const double* gV,
+                      double* partials, cudaStream_t st) {
+    const int64_t nodes = (int64_t)B * d->n_particles;
+    enc_input_bwd_kernel<<<sm_count(), 256, 0, st>>>(d->off_in00, d->off_in11, p4, mass, nodes, d->channels[0], gS, gV, partials, d->n_params);
+    count_launch();
+    return check_launch("enc_input_bwd");
+}
+
+static LatentArgs latent_args(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V) {
+    LatentArgs a;
+    a.theta = theta; a.off00 = d->off_lat00; a.off11 = d->off_lat11;
+    a.B = B; a.N = d->n_particles; a.C = d->channels[d->n_levels]; a.tau_s = d->tau_s; a.tau_v = d->tau_v; a.mode = d->latent_mode;
+    a.S = S; a.V = V; a.lat00 = nullptr; a.lat11 = nullptr; a.sel = nullptr; a.g_lat00 = nullptr; a.g_lat11 = nullptr;
+    a.gS = nullptr; a.gV = nullptr; a.partials = nullptr; a.n_params = d->n_params;
+    return a;
+}
+int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* lat00, double* lat11,
+                   int32_t* sel, cudaStream_t st) {
+    LatentArgs a = latent_args(d, theta, B, S, V);
+    a.lat00 = lat00; a.lat11 = lat11; a.sel = sel;
+    const int rows = a.mode == LGAE_LATENT_MIX ? 1 : a.N;
+    const size_t bytes = (size_t)rows * (a.tau_s + 4 * a.tau_v) * sizeof(cplx);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    if (cudaFuncSetAttribute(enc_latent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("enc_latent attr");
+    enc_latent_kernel<<<B, 256, bytes, st>>>(a);
+    count_launch();
+    return check_launch("enc_latent");
+}
+int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const int32_t* sel,
+                       const double* g_lat00, const double* g_lat11, double* gS, double* gV, double* partials, cudaStream_t st) {
+    LatentArgs a = latent_args(d, theta, B, S, V);
+    a.sel = const_cast<int32_t*>(sel); a.g_lat00 = g_lat00; a.g_lat11 = g_lat11; a.gS = gS; a.gV = gV; a.partials = partials;
+    const int mix = a.mode == LGAE_LATENT_MIX;
+    const int rows = mix ? 1 : a.N, cin = mix ? a.N * a.C : a.C;
+    const size_t bytes = ((size_t)rows * (a.tau_s + 4 * a.tau_v) + (size_t)(a.tau_s + a.tau_v) * cin) * sizeof(cplx);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    if (cudaFuncSetAttribute(enc_latent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("enc_latent_bwd attr");
+    enc_latent_bwd_kernel<<<sm_count(), 256, bytes, st>>>(a);
+    count_launch();
+    return check_launch("enc_latent_bwd");
+}
+
+static DecInArgs dec_in_args(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, double* S, double* V) {
+    DecInArgs a;
+    a.theta = theta; a.off_g11 = d->off_graph11; a.off_in00 = d->off_in00; a.off_in11 = d->off_in11;
+    a.B = B; a.N = d->n_particles; a.C = d->channels[0]; a.tau = d->tau_v; a.lat11 = lat11; a.y = y; a.S = S; a.V = V;
+    a.gS = nullptr; a.gV = nullptr; a.gy = nullptr; a.g_lat11 = nullptr; a.partials = nullptr; a.n_params = d->n_params;
+    return a;
+}
+int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, double* S, double* V, cudaStream_t st) {
+    DecInArgs a = dec_in_args(d, theta, B, lat11, y, S, V);
+    const size_t bytes = (size_t)a.tau * 4 * sizeof(cplx);
+    dec_input_kernel<<<B, 128, bytes, st>>>(a);
+    count_launch();
+    return check_launch("dec_input");
+}
+int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, const double* gS, const double* gV,
+                      const double* gy, double* g_lat11, double* partials, cudaStream_t st) {
+    DecInArgs a = dec_in_args(d, theta, B, lat11, y, nullptr, nullptr);
+    a.gS = gS; a.gV = gV; a.gy = gy; a.g_lat11 = g_lat11; a.partials = partials;
+    if (a.N > 128) return LGAE_E_UNSUPPORTED;
+    const size_t bytes = ((size_t)a.tau * 4 + (size_t)a.N * 4 + (size_t)a.N * a.tau + 2 * a.C) * sizeof(cplx);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    if (cudaFuncSetAttribute(dec_input_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("dec_input_bwd attr");
+    dec_input_bwd_kernel<<<sm_count(), 128, bytes, st>>>(a);
+    count_launch();
+    return check_launch("dec_input_bwd");
+}
+int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st) {
+    const int64_t nodes = (int64_t)B * d->n_particles;
+    dec_output_kernel<<<(unsigned)((nodes + 127) / 128), 128, 0, st>>>(theta, d->off_out00, d->off_out11, B, d->n_particles, d->channels[d->n_levels], S, V, recon, gen00);
+    count_launch();
+    return check_launch("dec_output");
+}
+int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const double* g_recon,
+                       const double* g_gen00, double* gS, double* gV, double* partials, cudaStream_t st) {
+    dec_output_bwd_kernel<<<sm_count(), 256, 0, st>>>(theta, d->off_out00, d->off_out11, B, d->n_particles, d->channels[d->n_levels], S, V, g_recon,
+                                                       g_gen00, gS, gV, partials, d->n_params);
+    count_launch();
+    return check_launch("dec_output_bwd");
+}
+int run_reduce_partials(const double* partials, int rows, int64_t n, double* gtheta, cudaStream_t st) {
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partials, rows, n, gtheta);
+    count_launch();
+    return check_launch("reduce_partials");
+}
+int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
+                double* g_recon, cudaStream_t st) {
+    const size_t bytes = (size_t)(4 * N + 4 * M + N + M) * sizeof(double) + (size_t)(N + M) * sizeof(int);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    if (cudaFuncSetAttribute(chamfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("chamfer attr");
+    chamfer_kernel<<<B, 128, bytes, st>>>(recon, target, B, N, M, jet_loss, g_loss, g_recon);
+    count_launch();
+    int rc = check_launch("chamfer");
+    if (rc) return rc;
+    if (loss) {
+        sum_kernel<<<1, 1024, 0, st>>>(jet_loss, B, 1.0, loss, 0);
+        count_launch();
+        rc = check_launch("chamfer_sum");
+    }
+    return rc;
+}
+int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st) {
+    normalize_kernel<<<B, 128, 0, st>>>(p4, N, out, factor);
+    count_launch();
+    return check_launch("normalize_p4");
+}
+int run_l1(const double* theta, int64_t n, double lambda, double* out, double* gtheta, cudaStream_t st) {
+    l1_kernel<<<1, 1024, 0, st>>>(theta, n, lambda, out, gtheta);
+    count_launch();
+    return check_launch("l1");
+}
+
+}  // namespace lgae
