@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- jets/s of one LGAE training step (encoder fwd + decoder fwd + chamfer + L1 + full backward) on the
+configuration BASELINE.json quotes: 30-particle jets, batch 512 per GPU, maxdim 2, enc 3 3 4 4 / dec 4 4 3 3,
+'min&max' latent, chamfer loss, fp64 (cfg-1/cfg-2; cfg-3 is the same step sharded over 2/4/8 GPUs, weak scaling).
+
+    python bench.py --gpus N --steps K --warmup W            # one process per GPU (torchrun for N > 1)
+    python bench.py --impl reference ...                     # the reference algorithm on the host CPU cores
+
+Prints ONE JSON line (rank 0).  `value` = whole-job jets/s with the inputs resident in HBM; `e2e` = the same step
+through the public module API with the jets starting in pinned HOST memory and the loss read back every step;
+`roofline` = the dominant kernel against the measured fp64 peak; `cpu_baseline` = the CPU oracle (a restatement of
+the reference's algorithm in plain torch, oracle/lgae_oracle.py) on a bounded sample, all host cores."""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(n=30, batch=512, maxdim=2, enc_channels=[3, 3, 4, 4], dec_channels=[4, 4, 3, 3], tau_s=1, tau_v=8, map_to_latent="min&max",
+           num_basis_fn=10, mlp_depth=6, mlp_width=6, l1_lambda=1e-8)
+WORKLOAD = "cfg1: LGAE train step, 30p jets, bs 512/GPU, maxdim 2, enc 3-3-4-4 / dec 4-4-3-3, min&max latent, chamfer + 1e-8 L1, fp64"
+FP64_PEAK_TFLOPS = 37.1   # measured on this pool's B200 with tools/fp64_peak.cu (DMMA m8n8k4 37.1, DFMA 33.7): profiles/fp64_peak_r01.json
+
+
+def synthetic_jets(batch, n, seed):
+    """near-massless QCD-like jets."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    u = lambda *s: torch.rand(*s, generator=g, dtype=torch.float64)
+    pt = 0.2 * u(batch, n) ** 3 + 1e-3
+    eta, phi, m = 0.8 * u(batch, n) - 0.4, 0.8 * u(batch, n) - 0.4, 1e-6 * u(batch, n)
+    e = torch.sqrt((pt * torch.cosh(eta)) ** 2 + m ** 2)
+    return torch.stack([e, pt * torch.cos(phi), pt * torch.sin(phi), pt * torch.sinh(eta)], -1)
+
+
+def build_models(device, seed=0):
+    import torch
+    from lgn_autoencoder_b200.models import LGNDecoder, LGNEncoder
+    torch.manual_seed(seed)
+    common = dict(maxdim=[CFG["maxdim"]], num_basis_fn=CFG["num_basis_fn"], max_zf=[1], weight_init="randn", level_gain=[1.0],
+                  activation="leakyrelu", mlp=True, mlp_depth=CFG["mlp_depth"], mlp_width=CFG["mlp_width"], device=torch.device("cpu"),
+                  dtype=torch.float64)
+    enc = LGNEncoder(num_input_particles=CFG["n"], tau_input_scalars=1, tau_input_vectors=1, tau_latent_scalars=CFG["tau_s"],
+                     tau_latent_vectors=CFG["tau_v"], num_channels=CFG["enc_channels"], jet_features=False,
+                     map_to_latent=CFG["map_to_latent"], **common)
+    dec = LGNDecoder(tau_latent_scalars=2 * CFG["tau_s"], tau_latent_vectors=2 * CFG["tau_v"], num_output_particles=CFG["n"],
+                     tau_output_scalars=1, tau_output_vectors=1, num_channels=CFG["dec_channels"], cg_dict=enc.cg_dict, **common)
+    return enc.to(device), dec.to(device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+            out, _ = self.p.communicate()
+        sm, smax, reasons = [], 0, set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            sm.append(int(f[0]))
+            smax = max(smax, int(f[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(sample_batch, steps, warmup):
+    """jets/s of the CPU oracle (the reference's algorithm restated in torch, all host threads) on a bounded sample."""
+    import torch
+    from oracle import lgae_oracle as orc
+    from lgn_autoencoder_b200.models import LGNDecoder, LGNEncoder  # only to draw reference-shaped random weights
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    common = dict(maxdim=[2], num_basis_fn=10, max_zf=[1], weight_init="randn", level_gain=[1.0], activation="leakyrelu", mlp=True,
+                  mlp_depth=6, mlp_width=6, device=torch.device("cpu"), dtype=torch.float64)
+    enc = LGNEncoder(num_input_particles=30, tau_input_scalars=1, tau_input_vectors=1, tau_latent_scalars=1, tau_latent_vectors=8,
+                     num_channels=CFG["enc_channels"], jet_features=False, map_to_latent="min&max", **common)
+    dec = LGNDecoder(tau_latent_scalars=2, tau_latent_vectors=16, num_output_particles=30, tau_output_scalars=1, tau_output_vectors=1,
+                     num_channels=CFG["dec_channels"], cg_dict=enc.cg_dict, **common)
+    enc_sd = {k: v.detach().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+    dec_sd = {k: v.detach().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    ecfg = dict(num_channels=CFG["enc_channels"], maxdim=[2], max_zf=[1], map_to_latent="min&max")
+    dcfg = dict(num_channels=CFG["dec_channels"], maxdim=[2], max_zf=[1])
+    p4 = synthetic_jets(sample_batch, CFG["n"], seed=1)
+    p4, _ = orc.normalize_p4_overall_max(p4)
+    times = []
+    for it in range(warmup + steps):
+        for sd in (enc_sd, dec_sd):
+            for v in sd.values():
+                v.grad = None
+        t0 = time.perf_counter()
+        loss, _, _ = orc.training_step(enc_sd, dec_sd, ecfg, dcfg, {"p4": p4}, l1_lambda=CFG["l1_lambda"])
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sample_batch / statistics.median(times), statistics.median(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 32
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    rate, sec = cpu_oracle_rate(sample, steps, warmup)
+    cores = os.cpu_count()
+    line = {"impl": "reference", "metric": "jets/sec LGAE fwd+bwd (30p, maxdim 2)", "value": rate, "unit": "jets/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{sample} jets per step on the host CPU"},
+            "cpu_baseline": {"value": rate, "unit": "jets/s", "cores": cores, "kind": "port",
+                             "sample": f"{steps} steps of {sample} jets, fwd+bwd, torch fp64 on {cores} threads (oracle/lgae_oracle.py)"},
+            "e2e": {"value": rate, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=CFG["batch"], help="jets per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from lgn_autoencoder_b200 import _lib, fused
+    from lgn_autoencoder_b200.flop_model import level_flops, step_flops_per_jet
+    from lgn_autoencoder_b200.train import allreduce_gradients, training_step
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K, B, N = max(args.warmup, 3), args.steps, args.batch, CFG["n"]
+
+    enc, dec = build_models(dev)
+    host_p4 = synthetic_jets(B, N, seed=100 + rank).pin_memory()
+    dev_p4 = host_p4.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
+
+    def step(p4):
+        for m in (enc, dec):
+            for p in m.parameters():
+                p.grad = None
+        loss, _, _ = training_step(enc, dec, p4, l1_lambda=CFG["l1_lambda"], l1_scale=1.0 / world)
+        loss.backward()
+        allreduce_gradients(enc, dec)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        """n steps, each timed with CUDA events on the launching stream; L2 flushed (untimed) between steps."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        barrier()
+        t0 = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            fn()
+            b.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t[0].item() / n, t[1].item() / n
+
+    for _ in range(W):
+        step(dev_p4)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    ms_step, _ = timed(lambda: step(dev_p4), K)
+    launches = (_lib.launch_count() - n0) / K
+
+    # end to end: pinned host jets -> device, loss back to the host, every step
+    def e2e_step():
+        p4 = host_p4.to(dev, non_blocking=True)
+        return step(p4).item()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e, _ = timed(e2e_step, K)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- roofline of the dominant kernel: the encoder level adjoint (level 2: C=4 -> C'=4), timed alone ----
+    roofline = None
+    if rank == 0:
+        plan = enc._plan
+        theta, _ = enc._flat_params()
+        p4n, _ = fused.normalize_p4(dev_p4)
+        lat00, lat11, ws, sel = fused.encoder_forward_raw(plan, theta, p4n, None)
+        lvl = plan.n_levels - 1
+        C, Co = plan.channels[lvl], plan.channels[lvl + 1]
+        import ctypes as Ct
+        lib = _lib.load()
+        s_in = plan.ws_tensor(ws, B, 0, lvl, (B, N, C, 2))
+        v_in = plan.ws_tensor(ws, B, 1, lvl, (B, N, C, 4, 2))
+        sums = plan.ws_tensor(ws, B, 4, lvl, (B, N, C, 10, 2))
+        g_v = torch.randn(B, N, Co, 4, 2, dtype=torch.float64, device=dev)
+        g_s = torch.randn(B, N, Co, 2, dtype=torch.float64, device=dev)
+        gs_in, gv_in = torch.empty_like(s_in), torch.empty_like(v_in)
+        part = plan.partials(dev)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def kern():
+            _lib.check(lib.lgae_level_backward(Ct.byref(plan.desc), lvl, theta.data_ptr(), p4n.data_ptr(), None, B, s_in.data_ptr(),
+                                               v_in.data_ptr(), sums.data_ptr(), g_s.data_ptr(), g_v.data_ptr(), gs_in.data_ptr(),
+                                               gv_in.data_ptr(), None, part.data_ptr(), st), "level_backward")
+        for _ in range(3):
+            kern()
+        reps = 10
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
+            flush.zero_()
+            a.record()
+            kern()
+            b.record()
+        torch.cuda.synchronize()
+        k_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
+        lf = level_flops(N, C, Co, 2 * CFG["num_basis_fn"], True, 0, 0)
+        flops = 2.0 * B * (lf["radial"] + lf["edge"] + lf["aggregate"] + lf["power"] + lf["mix"])   # adjoint = 2 x forward
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "level_bwd_kernel<enc> (level 2, C=4)", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                    "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None, "kernel_ms": k_ms,
+                    "peak_source": "fp64 pipe: DMMA m8n8k4 37.1 TFLOP/s / DFMA 33.7 TFLOP/s measured with tools/fp64_peak.cu on this pool "
+                                   "(MEASURED_PEAKS.json holds no fp64 figure)",
+                    "flops_per_launch": flops}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, sec = cpu_oracle_rate(32, 3, 1)
+        cpu = {"value": rate, "unit": "jets/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"3 steps of 32 jets (median {sec:.2f} s/step), fwd+bwd, torch fp64 on {os.cpu_count()} threads, oracle/lgae_oracle.py"}
+
+    if rank == 0:
+        jets = B * world
+        fl = step_flops_per_jet(N, CFG["enc_channels"], CFG["dec_channels"])
+        line = {
+            "metric": "jets/sec LGAE fwd+bwd (30p, maxdim 2)", "value": jets / (ms_step * 1e-3), "unit": "jets/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": jets, "parallelism": f"dp{world}", "l2": "flushed (256 MB write) between timed steps",
+                       "step_tflops": jets * fl / (ms_step * 1e-3) / 1e12, "step_frac_of_fp64_peak": jets * fl / (ms_step * 1e-3) / 1e12 / (FP64_PEAK_TFLOPS * world),
+                       "mflop_per_jet": fl / 1e6},
+            "e2e": {"value": jets / (ms_e2e * 1e-3), "unit": "jets/s", "h2d_bytes_per_step": host_p4.numel() * 8, "d2h_bytes_per_step": 8,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
