@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 #include "lgae_common.cuh"
 
@@ -43,6 +45,16 @@ int check_launch(const char* what) {
     if (e == cudaSuccess) return LGAE_OK;
     snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s", what, cudaGetErrorString(e));
     return LGAE_E_CUDA;
+}
+int ensure_smem(const void* kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, size_t> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = seen.find(kernel);
+    if (it != seen.end() && it->second >= bytes) return LGAE_OK;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("cudaFuncSetAttribute");
+    seen[kernel] = bytes;
+    return LGAE_OK;
 }
 int sm_count() {
     if (g_sm_count > 0) return g_sm_count;

@@ -132,6 +132,8 @@ LGAE_DEV double leaky(double x, double slope) { return x > 0.0 ? x : x * slope; 
 
 // ---- host side ------------------------------------------------------------------------------------
 void count_launch(int n = 1);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (and again only if a larger size is needed).
+int ensure_smem(const void* kernel, size_t bytes);
 int check_launch(const char* what);
 int sm_count();
 

@@ -648,7 +648,7 @@ int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const dou
     const int rows = a.mode == LGAE_LATENT_MIX ? 1 : a.N;
     const size_t bytes = (size_t)rows * (a.tau_s + 4 * a.tau_v) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
-    if (cudaFuncSetAttribute(enc_latent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("enc_latent attr");
+    if (int rc = ensure_smem((const void*)enc_latent_kernel, bytes)) return rc;
     enc_latent_kernel<<<B, 256, bytes, st>>>(a);
     count_launch();
     return check_launch("enc_latent");
@@ -661,7 +661,7 @@ int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const
     const int rows = mix ? 1 : a.N, cin = mix ? a.N * a.C : a.C;
     const size_t bytes = ((size_t)rows * (a.tau_s + 4 * a.tau_v) + (size_t)(a.tau_s + a.tau_v) * cin) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
-    if (cudaFuncSetAttribute(enc_latent_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("enc_latent_bwd attr");
+    if (int rc = ensure_smem((const void*)enc_latent_bwd_kernel, bytes)) return rc;
     enc_latent_bwd_kernel<<<sm_count(), 256, bytes, st>>>(a);
     count_launch();
     return check_launch("enc_latent_bwd");
@@ -688,7 +688,7 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
     if (a.N > 128) return LGAE_E_UNSUPPORTED;
     const size_t bytes = ((size_t)a.tau * 4 + (size_t)a.N * 4 + (size_t)a.N * a.tau + 2 * a.C) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
-    if (cudaFuncSetAttribute(dec_input_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("dec_input_bwd attr");
+    if (int rc = ensure_smem((const void*)dec_input_bwd_kernel, bytes)) return rc;
     dec_input_bwd_kernel<<<sm_count(), 128, bytes, st>>>(a);
     count_launch();
     return check_launch("dec_input_bwd");
@@ -715,7 +715,7 @@ int run_chamfer(const double* recon, const double* target, int B, int N, int M, 
                 double* g_recon, cudaStream_t st) {
     const size_t bytes = (size_t)(4 * N + 4 * M + N + M) * sizeof(double) + (size_t)(N + M) * sizeof(int);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
-    if (cudaFuncSetAttribute(chamfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("chamfer attr");
+    if (int rc = ensure_smem((const void*)chamfer_kernel, bytes)) return rc;
     chamfer_kernel<<<B, 128, bytes, st>>>(recon, target, B, N, M, jet_loss, g_loss, g_recon);
     count_launch();
     int rc = check_launch("chamfer");

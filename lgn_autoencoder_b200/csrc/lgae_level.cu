@@ -786,13 +786,13 @@ static int launch_level(const LevelArgs& a, bool bwd, cudaStream_t st) {
     const int threads = 32 * a.C;
     if (!bwd) {
         auto kern = level_fwd_kernel<ENC, NT, KS>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("level_fwd attr");
+        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
         const int nib = (a.N + 31) / 32;
         kern<<<a.B * nib, threads, bytes, st>>>(a);
     } else {
         if (a.N > 32) return LGAE_E_UNSUPPORTED;
         auto kern = level_bwd_kernel<ENC, NT, KS>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("level_bwd attr");
+        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
         kern<<<sm_count(), threads, bytes, st>>>(a);
     }
     count_launch();

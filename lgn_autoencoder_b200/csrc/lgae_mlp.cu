@@ -282,7 +282,7 @@ static int launch_mlp(const MlpArgs& a, bool bwd, cudaStream_t st) {
     if (!bwd) {
         const size_t bytes = (size_t)(NTW * NTW * 64 + 8 * NTW) * sizeof(double);
         auto kern = mlp_fwd_kernel<NTW, NTI, MT>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("mlp_fwd attr");
+        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
         int64_t chunks = (a.rows + RW - 1) / RW;
         int grid = (int)(chunks < (int64_t)2 * sm_count() ? chunks : (int64_t)2 * sm_count());
         kern<<<grid, threads, bytes, st>>>(a);
@@ -292,7 +292,7 @@ static int launch_mlp(const MlpArgs& a, bool bwd, cudaStream_t st) {
     const size_t bytes = (size_t)(NTW * NTW * 64 + 2 * RW * (8 * NTW + 4)) * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
     auto kern = mlp_bwd_kernel<NTW, NTI, MT>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("mlp_bwd attr");
+    if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
     kern<<<sm_count(), threads, bytes, st>>>(a);
     count_launch();
     return check_launch("mlp_bwd");
