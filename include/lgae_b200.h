@@ -92,10 +92,12 @@ int64_t lgae_launch_count(void);
 int64_t lgae_workspace_doubles(const LgaeModelDesc* d, int32_t batch);
 /* Offset (doubles) of one saved tensor inside the workspace, or -1.  kind: 0 = S_in[level] (B,N,C,2),
  * 1 = V_in[level] (B,N,C,4,2) (level == n_levels gives the final features), 2 = pre-MLP scalars of level,
- * 3 = canonical momenta y (B,N,4,2), 4 = neighbour sums of level (B,N,C,10,2), 5 = masses (B,N) (encoder). */
+ * 3 = canonical momenta y (B,N,4,2), 4 = neighbour sums of level (B,N,C,10,2), 5 = masses (B,N) (encoder),
+ * 6 = MLP activations of level (hidden, B*N, padded width), 7 = radial weights of level (B,N,C,32,4) (encoder, N <= 32). */
 int64_t lgae_workspace_offset(const LgaeModelDesc* d, int32_t batch, int32_t kind, int32_t level);
-/* Doubles of scratch for per-CTA partial parameter gradients used by the backward entry points. */
-int64_t lgae_partials_doubles(const LgaeModelDesc* d);
+/* Doubles of scratch for the per-CTA rows of parameter-gradient partials the backward entry points write (every
+ * backward kernel owns a block of compact rows; one reduce launch sums them into gtheta, in a fixed order). */
+int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch);
 
 /* ---- whole-model entry points -------------------------------------------------------------------- */
 /* LGNEncoder.forward.  p4 (B,N,4) Cartesian (E,px,py,pz); node_mask (B,N) uint8 or NULL (=> p4[...,0] != 0).
@@ -105,7 +107,7 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d);
 int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask,
                          int32_t batch, double* workspace, double* lat00, double* lat11, int32_t* sel, void* stream);
 /* Adjoint.  g_lat00 / g_lat11 may be NULL (treated as zero).  gtheta (n_params) is OVERWRITTEN with the
- * parameter gradient.  partials: scratch of lgae_partials_doubles(d). */
+ * parameter gradient.  partials: scratch of lgae_partials_doubles(d, batch).  Needs N <= 32. */
 int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask,
                           int32_t batch, double* workspace, const int32_t* sel, const double* g_lat00,
                           const double* g_lat11, double* gtheta, double* partials, void* stream);
@@ -133,22 +135,24 @@ int lgae_l1(const double* theta, int64_t n, double lambda, double* out_accumulat
 /* One LGN level at maxdim 2: radial functions -> edge features -> CG aggregation -> CG self product ->
  * concat -> complex channel mix.  Encoder flavour: p (B,N,4) real Cartesian + node_mask, radial parameters
  * from theta at level `level`.  Decoder flavour: y (B,N,4,2) complex canonical, constant radial weights.
- * s_in (B,N,C,2), v_in (B,N,C,4,2) -> s_pre (B,N,C',2), v_out (B,N,C',4,2), sums (B,N,C,10,2). */
+ * s_in (B,N,C,2), v_in (B,N,C,4,2) -> s_pre (B,N,C',2), v_out (B,N,C',4,2), sums (B,N,C,10,2).
+ * r_save (encoder, N <= 32, may be NULL): (B,N,C,32,4) copy of the radial weights, required by the adjoint. */
 int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
                        const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
-                       double* sums, double* s_pre, double* v_out, void* stream);
+                       double* sums, double* r_save, double* s_pre, double* v_out, void* stream);
+/* gtheta (n_params) is overwritten: zero except for the parameters of this level. */
 int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
                         const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
-                        const double* sums, const double* g_s_pre, const double* g_v_out, double* g_s_in,
-                        double* g_v_in, double* g_y_accumulate, double* partials, void* stream);
+                        const double* sums, const double* r_save, const double* g_s_pre, const double* g_v_out,
+                        double* g_s_in, double* g_v_in, double* g_y_accumulate, double* gtheta, double* partials,
+                        void* stream);
 /* CGMLP on rows = batch*N interleaved scalars x (rows, 2C').  acts: (n_hidden, rows, width_padded) saved
  * activations.  y (rows, 2C'). */
 int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows,
                      double* acts, double* y, void* stream);
 int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows,
-                      const double* acts, const double* g_y, double* g_x, double* partials, void* stream);
-/* Sum the per-CTA partial gradients into gtheta (overwrite). */
-int lgae_reduce_partials(const LgaeModelDesc* d, const double* partials, double* gtheta, void* stream);
+                      const double* acts, const double* g_y, double* g_x, double* gtheta, double* partials,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,24 +11,31 @@
 namespace lgae {
 
 // ---- implemented in the other translation units -------------------------------------------------------------
-int run_level(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
-              const double* s_in, const double* v_in, double* sums, double* s_pre, double* v_out, const double* g_s_pre,
-              const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y, double* partials, bool bwd, cudaStream_t st);
+int run_level_fwd(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
+                  const double* s_in, const double* v_in, double* sums, double* r_save, double* s_pre, double* v_out, cudaStream_t st);
+int run_level_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
+                  const double* s_in, const double* v_in, const double* sums, const double* r_save, const double* g_s_pre,
+                  const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y, PartPlan* plan, cudaStream_t st);
+int level_bwd_grid(int batch);
+int64_t level_part_width(const LgaeModelDesc* d, int level);
 int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* x, int64_t rows, double* acts, double* y,
-            const double* g_y, double* g_x, double* partials, bool bwd, cudaStream_t st);
+            const double* g_y, double* g_x, PartPlan* plan, bool bwd, cudaStream_t st);
 int mlp_padded_width(const LgaeModelDesc* d, int level);
+int64_t mlp_part_width(const LgaeModelDesc* d, int level);
+int mlp_bwd_grid();
 int run_enc_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* mass, double* S, double* V, cudaStream_t st);
-int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* mass, int B, const double* gS, const double* gV, double* partials, cudaStream_t st);
+int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* mass, int B, const double* gS, const double* gV, PartPlan* plan, cudaStream_t st);
 int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* lat00, double* lat11, int32_t* sel, cudaStream_t st);
 int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const int32_t* sel,
-                       const double* g_lat00, const double* g_lat11, double* gS, double* gV, double* partials, cudaStream_t st);
+                       const double* g_lat00, const double* g_lat11, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
 int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, double* S, double* V, cudaStream_t st);
 int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, const double* gS, const double* gV,
-                      const double* gy, double* g_lat11, double* partials, cudaStream_t st);
+                      const double* gy, double* g_lat11, PartPlan* plan, cudaStream_t st);
 int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st);
 int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const double* g_recon,
-                       const double* g_gen00, double* gS, double* gV, double* partials, cudaStream_t st);
-int run_reduce_partials(const double* partials, int rows, int64_t n, double* gtheta, cudaStream_t st);
+                       const double* g_gen00, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
+int run_reduce_plan(const PartPlan* plan, int64_t n_params, double* gtheta, cudaStream_t st);
+int64_t glue_part_doubles(const LgaeModelDesc* d);
 int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
                 double* g_recon, cudaStream_t st);
 int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st);
@@ -70,7 +77,7 @@ int sm_count() {
 // ---- workspace layout -----------------------------------------------------------------------------------------------
 struct Layout {
     int64_t S[LGAE_MAX_LEVELS + 1], V[LGAE_MAX_LEVELS + 1];
-    int64_t sums[LGAE_MAX_LEVELS], spre[LGAE_MAX_LEVELS], acts[LGAE_MAX_LEVELS];
+    int64_t sums[LGAE_MAX_LEVELS], spre[LGAE_MAX_LEVELS], acts[LGAE_MAX_LEVELS], rsave[LGAE_MAX_LEVELS];
     int64_t y, mass, gS[2], gV[2], gSpre, gy, total;
 };
 static int max_channels(const LgaeModelDesc* d) {
@@ -93,6 +100,8 @@ static Layout layout(const LgaeModelDesc* d, int64_t B) {
         L.sums[l] = take(nodes * d->channels[l] * 20);
         L.spre[l] = d->has_mlp ? take(nodes * d->channels[l + 1] * 2) : L.S[l + 1];
         L.acts[l] = d->has_mlp ? take((int64_t)d->mlp_hidden * nodes * mlp_padded_width(d, l)) : 0;
+        // encoder, N <= 32: the radial weights R_ij[c] of every level, kept for the adjoint
+        L.rsave[l] = (!d->is_decoder && d->n_particles <= 32) ? take(nodes * d->channels[l] * 128) : -1;
     }
     const int cm = max_channels(d);
     for (int k = 0; k < 2; ++k) { L.gS[k] = take(nodes * cm * 2); L.gV[k] = take(nodes * cm * 8); }
@@ -158,12 +167,18 @@ int64_t lgae_workspace_offset(const LgaeModelDesc* d, int32_t batch, int32_t kin
         case 4: return level < d->n_levels ? L.sums[level] : -1;
         case 5: return L.mass;
         case 6: return level < d->n_levels ? L.acts[level] : -1;
+        case 7: return level < d->n_levels ? L.rsave[level] : -1;
         default: return -1;
     }
 }
-int64_t lgae_partials_doubles(const LgaeModelDesc* d) {
-    if (check_desc(d) != LGAE_OK) return -1;
-    return (int64_t)sm_count() * d->n_params;
+int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
+    if (check_desc(d) != LGAE_OK || batch < 0) return -1;
+    int64_t n = glue_part_doubles(d);
+    for (int l = 0; l < d->n_levels; ++l) {
+        n += (int64_t)level_bwd_grid(batch) * level_part_width(d, l);
+        if (d->has_mlp) n += (int64_t)mlp_bwd_grid() * mlp_part_width(d, l);
+    }
+    return n;
 }
 
 int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
@@ -176,8 +191,8 @@ int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     const int64_t rows = (int64_t)batch * d->n_particles;
     LGAE_TRY(run_enc_input(d, theta, p4, batch, ws + L.mass, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
-        LGAE_TRY(run_level(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], ws + L.spre[l], ws + L.V[l + 1],
-                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, st));
+        LGAE_TRY(run_level_fwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l],
+                               L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, ws + L.spre[l], ws + L.V[l + 1], st));
         if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
     return run_enc_latent(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], lat00, lat11, sel, st);
@@ -189,14 +204,14 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
     LGAE_TRY(check_desc(d));
     if (d->is_decoder || !theta || !p4 || !ws || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int G = sm_count();
-    if (cudaMemsetAsync(partials, 0, (size_t)G * d->n_params * sizeof(double), st) != cudaSuccess) return check_launch("memset partials");
+    PartPlan plan;
+    plan.base = partials;
     if (batch > 0) {
         const Layout L = layout(d, batch);
         const int64_t rows = (int64_t)batch * d->n_particles;
         const int nl = d->n_levels;
         int cur = 0;
-        LGAE_TRY(run_enc_latent_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], sel, g_lat00, g_lat11, ws + L.gS[cur], ws + L.gV[cur], partials, st));
+        LGAE_TRY(run_enc_latent_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], sel, g_lat00, g_lat11, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
         // The scalar features of the last level only reach the latent scalars: without a gradient on those the
         // whole last-level MLP is dead in the backward pass ("dead-in-training sub-paths").
         bool gs_zero = g_lat00 == nullptr;
@@ -204,20 +219,21 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
             const double* g_spre = nullptr;
             if (!gs_zero) {
                 if (d->has_mlp) {
-                    LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, partials, true, st));
+                    LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, &plan, true, st));
                     g_spre = ws + L.gSpre;
                 } else {
                     g_spre = ws + L.gS[cur];
                 }
             }
-            LGAE_TRY(run_level(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, nullptr, g_spre,
-                               ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], nullptr, partials, true, st));
+            LGAE_TRY(run_level_bwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l],
+                                   L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, g_spre, ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1],
+                                   nullptr, &plan, st));
             cur ^= 1;
             gs_zero = false;
         }
-        LGAE_TRY(run_enc_input_bwd(d, p4, ws + L.mass, batch, ws + L.gS[cur], ws + L.gV[cur], partials, st));
+        LGAE_TRY(run_enc_input_bwd(d, p4, ws + L.mass, batch, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
     }
-    return run_reduce_partials(partials, G, d->n_params, gtheta, st);
+    return run_reduce_plan(&plan, d->n_params, gtheta, st);
 }
 
 int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
@@ -230,8 +246,8 @@ int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     const int64_t rows = (int64_t)batch * d->n_particles;
     LGAE_TRY(run_dec_input(d, theta, batch, lat11, ws + L.y, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
-        LGAE_TRY(run_level(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], ws + L.spre[l], ws + L.V[l + 1],
-                           nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, false, st));
+        LGAE_TRY(run_level_fwd(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, ws + L.spre[l],
+                               ws + L.V[l + 1], st));
         if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
     return run_dec_output(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], recon, gen00, st);
@@ -242,34 +258,34 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
     LGAE_TRY(check_desc(d));
     if (!d->is_decoder || !theta || !lat11 || !ws || !g_recon || !g_lat11 || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int G = sm_count();
-    if (cudaMemsetAsync(partials, 0, (size_t)G * d->n_params * sizeof(double), st) != cudaSuccess) return check_launch("memset partials");
+    PartPlan plan;
+    plan.base = partials;
     if (batch > 0) {
         const Layout L = layout(d, batch);
         const int64_t rows = (int64_t)batch * d->n_particles;
         const int nl = d->n_levels;
         if (cudaMemsetAsync(ws + L.gy, 0, (size_t)rows * 8 * sizeof(double), st) != cudaSuccess) return check_launch("memset gy");
         int cur = 0;
-        LGAE_TRY(run_dec_output_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], g_recon, g_gen00, ws + L.gS[cur], ws + L.gV[cur], partials, st));
+        LGAE_TRY(run_dec_output_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], g_recon, g_gen00, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
         bool gs_zero = g_gen00 == nullptr;
         for (int l = nl - 1; l >= 0; --l) {
             const double* g_spre = nullptr;
             if (!gs_zero) {
                 if (d->has_mlp) {
-                    LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, partials, true, st));
+                    LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, &plan, true, st));
                     g_spre = ws + L.gSpre;
                 } else {
                     g_spre = ws + L.gS[cur];
                 }
             }
-            LGAE_TRY(run_level(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, nullptr, g_spre,
-                               ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], ws + L.gy, partials, true, st));
+            LGAE_TRY(run_level_bwd(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, g_spre,
+                                   ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], ws + L.gy, &plan, st));
             cur ^= 1;
             gs_zero = false;
         }
-        LGAE_TRY(run_dec_input_bwd(d, theta, batch, lat11, ws + L.y, ws + L.gS[cur], ws + L.gV[cur], ws + L.gy, g_lat11, partials, st));
+        LGAE_TRY(run_dec_input_bwd(d, theta, batch, lat11, ws + L.y, ws + L.gS[cur], ws + L.gV[cur], ws + L.gy, g_lat11, &plan, st));
     }
-    return run_reduce_partials(partials, G, d->n_params, gtheta, st);
+    return run_reduce_plan(&plan, d->n_params, gtheta, st);
 }
 
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,
@@ -295,20 +311,25 @@ int lgae_l1(const double* theta, int64_t n, double lambda, double* out_accumulat
 }
 
 int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y, const uint8_t* node_mask,
-                       int32_t batch, const double* s_in, const double* v_in, double* sums, double* s_pre, double* v_out, void* stream) {
+                       int32_t batch, const double* s_in, const double* v_in, double* sums, double* r_save, double* s_pre, double* v_out,
+                       void* stream) {
     LGAE_TRY(check_desc(d));
     if (!theta || !p_or_y || !s_in || !v_in || !sums || !s_pre || !v_out || batch < 0) return LGAE_E_BADARG;
-    return run_level(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, s_pre, v_out, nullptr, nullptr, nullptr, nullptr, nullptr,
-                     nullptr, false, (cudaStream_t)stream);
+    return run_level_fwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, s_pre, v_out, (cudaStream_t)stream);
 }
 int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y, const uint8_t* node_mask,
-                        int32_t batch, const double* s_in, const double* v_in, const double* sums, const double* g_s_pre,
-                        const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y_accumulate, double* partials, void* stream) {
+                        int32_t batch, const double* s_in, const double* v_in, const double* sums, const double* r_save,
+                        const double* g_s_pre, const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y_accumulate,
+                        double* gtheta, double* partials, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (!theta || !p_or_y || !s_in || !v_in || !sums || !g_v_out || !g_s_in || !g_v_in || !partials || batch < 0) return LGAE_E_BADARG;
+    if (!theta || !p_or_y || !s_in || !v_in || !sums || !g_v_out || !g_s_in || !g_v_in || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
     if (d->is_decoder && !g_y_accumulate) return LGAE_E_BADARG;
-    return run_level(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, const_cast<double*>(sums), nullptr, nullptr, g_s_pre, g_v_out,
-                     g_s_in, g_v_in, g_y_accumulate, partials, true, (cudaStream_t)stream);
+    if (!d->is_decoder && !r_save) return LGAE_E_BADARG;
+    PartPlan plan;
+    plan.base = partials;
+    LGAE_TRY(run_level_bwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, g_s_pre, g_v_out, g_s_in, g_v_in,
+                           g_y_accumulate, &plan, (cudaStream_t)stream));
+    return run_reduce_plan(&plan, d->n_params, gtheta, (cudaStream_t)stream);
 }
 int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, double* acts, double* y,
                      void* stream) {
@@ -317,15 +338,13 @@ int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta,
     return run_mlp(d, level, theta, x, rows, acts, y, nullptr, nullptr, nullptr, false, (cudaStream_t)stream);
 }
 int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, const double* acts,
-                      const double* g_y, double* g_x, double* partials, void* stream) {
+                      const double* g_y, double* g_x, double* gtheta, double* partials, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (!theta || !x || !acts || !g_y || !partials || rows < 0) return LGAE_E_BADARG;
-    return run_mlp(d, level, theta, x, rows, const_cast<double*>(acts), nullptr, g_y, g_x, partials, true, (cudaStream_t)stream);
-}
-int lgae_reduce_partials(const LgaeModelDesc* d, const double* partials, double* gtheta, void* stream) {
-    LGAE_TRY(check_desc(d));
-    if (!partials || !gtheta) return LGAE_E_BADARG;
-    return run_reduce_partials(partials, sm_count(), d->n_params, gtheta, (cudaStream_t)stream);
+    if (!theta || !x || !acts || !g_y || !gtheta || !partials || rows < 0) return LGAE_E_BADARG;
+    PartPlan plan;
+    plan.base = partials;
+    LGAE_TRY(run_mlp(d, level, theta, x, rows, const_cast<double*>(acts), nullptr, g_y, g_x, &plan, true, (cudaStream_t)stream));
+    return run_reduce_plan(&plan, d->n_params, gtheta, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -130,6 +130,90 @@ LGAE_DEV double block_sum(double v, double* scratch) {
 
 LGAE_DEV double leaky(double x, double slope) { return x > 0.0 ? x : x * slope; }
 
+// Sums of 16 per-lane values over the 32 lanes of a warp with 8+4+2+1+1 = 16 shuffles instead of 5*16: a
+// butterfly that halves the number of live values at every stage.  On return lane l holds the total of value
+// number l >> 1 (each total is replicated in two neighbouring lanes).
+LGAE_DEV double warp_sum16(const double (&v)[16]) {
+    const int lane = threadIdx.x & 31;
+    double a[8], b[4], c[2], d;
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double send = up ? v[j] : v[j + 8], keep = up ? v[j + 8] : v[j];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double send = up ? a[j] : a[j + 4], keep = up ? a[j + 4] : a[j];
+            b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double send = up ? b[j] : b[j + 2], keep = up ? b[j + 2] : b[j];
+            c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+        const double send = up ? c[0] : c[1], keep = up ? c[1] : c[0];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
+// ---- parameter-gradient partials ------------------------------------------------------------------------
+// Every backward kernel writes one compact row of parameter-gradient partials per CTA into its own block of the
+// scratch buffer `partials`; one reduce launch then sums the rows of every block into gtheta.  A segment maps a
+// contiguous range of theta to a column range of a block.
+#define LGAE_MAX_SEGS 320
+struct Seg {
+    int64_t theta_off;  // first parameter (offset in theta / gtheta)
+    int64_t part_off;   // offset (doubles) of row 0, column 0 of this segment inside `partials`
+    int64_t stride;     // row stride (doubles) of the block
+    int32_t len;        // number of parameters
+    int32_t rows;       // number of rows (CTAs of the producing kernel)
+};
+struct SegTable {
+    int32_t n;
+    int32_t pad;
+    Seg s[LGAE_MAX_SEGS];
+};
+// Host-side allocator of blocks inside `partials`.
+struct PartPlan {
+    double* base = nullptr;
+    int64_t used = 0;
+    SegTable table;
+    PartPlan() { table.n = 0; table.pad = 0; }
+    // reserve rows x width doubles; returns the block's offset
+    int64_t block(int rows, int64_t width) {
+        const int64_t off = used;
+        used += (int64_t)rows * width;
+        return off;
+    }
+    // declare that columns [col, col+len) of the block at `off` hold the gradient of theta[theta_off ...]
+    int seg(int64_t theta_off, int64_t off, int64_t stride, int64_t col, int64_t len, int rows) {
+        if (len <= 0) return LGAE_OK;
+        if (table.n > 0) {   // merge with the previous segment when both ranges continue it
+            Seg& p = table.s[table.n - 1];
+            if (p.rows == rows && p.stride == stride && p.theta_off + p.len == theta_off && p.part_off + p.len == off + col) {
+                p.len += (int32_t)len;
+                return LGAE_OK;
+            }
+        }
+        if (table.n >= LGAE_MAX_SEGS) return LGAE_E_UNSUPPORTED;
+        Seg& s = table.s[table.n++];
+        s.theta_off = theta_off; s.part_off = off + col; s.stride = stride; s.len = (int32_t)len; s.rows = rows;
+        return LGAE_OK;
+    }
+};
+
 // ---- host side ------------------------------------------------------------------------------------
 void count_launch(int n = 1);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (and again only if a larger size is needed).

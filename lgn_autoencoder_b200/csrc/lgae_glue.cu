@@ -18,10 +18,11 @@ LGAE_DEV cplx wget(const double* theta, int64_t off, int rows, int cols, int r, 
     const int64_t idx = off + (int64_t)r * cols + cc;
     return cmake(theta[idx], theta[idx + (int64_t)rows * cols]);
 }
-LGAE_DEV void padd(double* part, int64_t off, int rows, int cols, int r, int cc, cplx v) {
+// store element [r][cc] of a planar complex weight gradient into a row of partials (column offset `off`)
+LGAE_DEV void pput(double* part, int64_t off, int rows, int cols, int r, int cc, cplx v) {
     const int64_t idx = off + (int64_t)r * cols + cc;
-    part[idx] += v.x;
-    part[idx + (int64_t)rows * cols] += v.y;
+    part[idx] = v.x;
+    part[idx + (int64_t)rows * cols] = v.y;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -45,7 +46,7 @@ __global__ void enc_input_kernel(const double* theta, int64_t off00, int64_t off
 }
 
 __global__ void __launch_bounds__(256) enc_input_bwd_kernel(int64_t off00, int64_t off11, const double* p4, const double* mass, int64_t nodes,
-                                                            int C, const double* gS, const double* gV, double* partials, int64_t n_params) {
+                                                            int C, const double* gS, const double* gV, double* partials, int64_t part_stride) {
     __shared__ double scratch[32];
     double acc[MAXC][4];
 #pragma unroll
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(256) enc_input_bwd_kernel(int64_t off00, int64
             }
         }
     }
-    double* part = partials + (int64_t)blockIdx.x * n_params;
+    double* part = partials + (int64_t)blockIdx.x * part_stride;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
         if (c < C) {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(256) enc_input_bwd_kernel(int64_t off00, int64
                 const double v = block_sum(acc[c][x], scratch);
                 if (threadIdx.x == 0) {
                     const int64_t off = x < 2 ? off00 : off11;
-                    part[off + (x & 1) * C + c] += v;
+                    part[off + (x & 1) * C + c] = v;
                 }
             }
         }
@@ -102,8 +103,8 @@ struct LatentArgs {
     const double* g_lat11;
     double* gS;
     double* gV;
-    double* partials;
-    int64_t n_params;
+    double* partials;       // (gridDim.x, part_stride) rows; columns [po00 ...), [po11 ...)
+    int64_t part_stride, po00, po11;
 };
 
 LGAE_DEV double msq_of(const double* v) {   // get_msq, lgn_encoder.py:499-505 (sqrt, then square)
@@ -305,9 +306,9 @@ __global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a)
         }
     }
     __syncthreads();
-    double* part = a.partials + (int64_t)blockIdx.x * a.n_params;
-    for (int it = tid; it < ts * cin; it += blockDim.x) padd(part, a.off00, ts, cin, it / cin, it % cin, gw00[it]);
-    for (int it = tid; it < tv * cin; it += blockDim.x) padd(part, a.off11, tv, cin, it / cin, it % cin, gw11[it]);
+    double* part = a.partials + (int64_t)blockIdx.x * a.part_stride;
+    for (int it = tid; it < ts * cin; it += blockDim.x) pput(part, a.po00, ts, cin, it / cin, it % cin, gw00[it]);
+    for (int it = tid; it < tv * cin; it += blockDim.x) pput(part, a.po11, tv, cin, it / cin, it % cin, gw11[it]);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -325,8 +326,8 @@ struct DecInArgs {
     const double* gV;
     const double* gy;      // accumulated by the level adjoints
     double* g_lat11;
-    double* partials;
-    int64_t n_params;
+    double* partials;       // (gridDim.x, part_stride) rows
+    int64_t part_stride, po_g11, po_in00, po_in11;
 };
 
 __global__ void __launch_bounds__(128) dec_input_kernel(const DecInArgs a) {
@@ -423,11 +424,11 @@ __global__ void __launch_bounds__(128) dec_input_bwd_kernel(const DecInArgs a) {
         }
     }
     __syncthreads();
-    double* part = a.partials + (int64_t)blockIdx.x * a.n_params;
-    for (int it = tid; it < N * tau; it += blockDim.x) padd(part, a.off_g11, N, tau, it / tau, it % tau, gwg[it]);
+    double* part = a.partials + (int64_t)blockIdx.x * a.part_stride;
+    for (int it = tid; it < N * tau; it += blockDim.x) pput(part, a.po_g11, N, tau, it / tau, it % tau, gwg[it]);
     for (int c = tid; c < C; c += blockDim.x) {
-        padd(part, a.off_in00, C, 1, c, 0, gin[c]);
-        padd(part, a.off_in11, C, 1, c, 0, gin[C + c]);
+        pput(part, a.po_in00, C, 1, c, 0, gin[c]);
+        pput(part, a.po_in11, C, 1, c, 0, gin[C + c]);
     }
 }
 
@@ -460,7 +461,7 @@ __global__ void dec_output_kernel(const double* theta, int64_t off00, int64_t of
 
 __global__ void __launch_bounds__(256) dec_output_bwd_kernel(const double* theta, int64_t off00, int64_t off11, int B, int N, int C,
                                                              const double* S, const double* V, const double* g_recon, const double* g_gen00,
-                                                             double* gS, double* gV, double* partials, int64_t n_params) {
+                                                             double* gS, double* gV, double* partials, int64_t part_stride) {
     __shared__ double scratch[32];
     double acc[MAXC][4];
 #pragma unroll
@@ -493,14 +494,15 @@ __global__ void __launch_bounds__(256) dec_output_bwd_kernel(const double* theta
             }
         }
     }
-    double* part = partials + (int64_t)blockIdx.x * n_params;
+    // row of partials: [out00 (2C) | out11 (2C)]
+    double* part = partials + (int64_t)blockIdx.x * part_stride;
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
         if (c < C) {
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
                 const double v = block_sum(acc[c][x], scratch);
-                if (threadIdx.x == 0) part[(x < 2 ? off00 : off11) + (x & 1) * C + c] += v;
+                if (threadIdx.x == 0) part[(x < 2 ? 0 : 2 * C) + (x & 1) * C + c] = v;
             }
         }
     }
@@ -608,12 +610,28 @@ __global__ void __launch_bounds__(1024) l1_kernel(const double* theta, int64_t n
     if (threadIdx.x == 0 && out) out[0] += lambda * s;
 }
 
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* partials, int rows, int64_t n, double* gtheta) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    double s = 0.0;
-    for (int r = 0; r < rows; ++r) s += partials[(int64_t)r * n + p];
-    gtheta[p] = s;
+// gtheta[seg] = sum over the rows of the segment's block.  blockIdx.y = segment, blockDim = (32 columns, 8 row groups);
+// fixed summation order => deterministic gradients.
+__global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, const double* partials, double* gtheta) {
+    __shared__ double sm[8][33];
+    const Seg sg = t.s[blockIdx.y];
+    for (int x0 = blockIdx.x * 32; x0 < sg.len; x0 += gridDim.x * 32) {
+        const int x = x0 + threadIdx.x;
+        double acc = 0.0;
+        if (x < sg.len) {
+            const double* src = partials + sg.part_off + x;
+            for (int r = threadIdx.y; r < sg.rows; r += 8) acc += src[(int64_t)r * sg.stride];
+        }
+        sm[threadIdx.y][threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.y == 0 && x < sg.len) {
+            double v = 0.0;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) v += sm[y][threadIdx.x];
+            gtheta[sg.theta_off + x] = v;
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -626,9 +644,13 @@ int run_enc_input(const LgaeModelDesc* d, const double* theta, const double* p4,
     return check_launch("enc_input");
 }
 int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* mass, int B, const double* gS, const double* gV,
-                      double* partials, cudaStream_t st) {
+                      PartPlan* plan, cudaStream_t st) {
     const int64_t nodes = (int64_t)B * d->n_particles;
-    enc_input_bwd_kernel<<<sm_count(), 256, 0, st>>>(d->off_in00, d->off_in11, p4, mass, nodes, d->channels[0], gS, gV, partials, d->n_params);
+    const int C = d->channels[0], grid = sm_count();
+    const int64_t w = 4 * C, off = plan->block(grid, w);   // row: [in00 (2C) | in11 (2C)]
+    if (int rc = plan->seg(d->off_in00, off, w, 0, 2 * C, grid)) return rc;
+    if (int rc = plan->seg(d->off_in11, off, w, 2 * C, 2 * C, grid)) return rc;
+    enc_input_bwd_kernel<<<grid, 256, 0, st>>>(0, 2 * C, p4, mass, nodes, C, gS, gV, plan->base + off, w);
     count_launch();
     return check_launch("enc_input_bwd");
 }
@@ -638,7 +660,7 @@ static LatentArgs latent_args(const LgaeModelDesc* d, const double* theta, int B
     a.theta = theta; a.off00 = d->off_lat00; a.off11 = d->off_lat11;
     a.B = B; a.N = d->n_particles; a.C = d->channels[d->n_levels]; a.tau_s = d->tau_s; a.tau_v = d->tau_v; a.mode = d->latent_mode;
     a.S = S; a.V = V; a.lat00 = nullptr; a.lat11 = nullptr; a.sel = nullptr; a.g_lat00 = nullptr; a.g_lat11 = nullptr;
-    a.gS = nullptr; a.gV = nullptr; a.partials = nullptr; a.n_params = d->n_params;
+    a.gS = nullptr; a.gV = nullptr; a.partials = nullptr; a.part_stride = 0; a.po00 = 0; a.po11 = 0;
     return a;
 }
 int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* lat00, double* lat11,
@@ -654,11 +676,18 @@ int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const dou
     return check_launch("enc_latent");
 }
 int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const int32_t* sel,
-                       const double* g_lat00, const double* g_lat11, double* gS, double* gV, double* partials, cudaStream_t st) {
+                       const double* g_lat00, const double* g_lat11, double* gS, double* gV, PartPlan* plan, cudaStream_t st) {
     LatentArgs a = latent_args(d, theta, B, S, V);
-    a.sel = const_cast<int32_t*>(sel); a.g_lat00 = g_lat00; a.g_lat11 = g_lat11; a.gS = gS; a.gV = gV; a.partials = partials;
+    a.sel = const_cast<int32_t*>(sel); a.g_lat00 = g_lat00; a.g_lat11 = g_lat11; a.gS = gS; a.gV = gV;
     const int mix = a.mode == LGAE_LATENT_MIX;
     const int rows = mix ? 1 : a.N, cin = mix ? a.N * a.C : a.C;
+    {
+        const int grid = sm_count();
+        const int64_t n00 = (int64_t)2 * a.tau_s * cin, n11 = (int64_t)2 * a.tau_v * cin, w = n00 + n11, off = plan->block(grid, w);
+        if (int rc = plan->seg(a.off00, off, w, 0, n00, grid)) return rc;
+        if (int rc = plan->seg(a.off11, off, w, n00, n11, grid)) return rc;
+        a.partials = plan->base + off; a.part_stride = w; a.po00 = 0; a.po11 = n00;
+    }
     const size_t bytes = ((size_t)rows * (a.tau_s + 4 * a.tau_v) + (size_t)(a.tau_s + a.tau_v) * cin) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)enc_latent_bwd_kernel, bytes)) return rc;
@@ -671,7 +700,7 @@ static DecInArgs dec_in_args(const LgaeModelDesc* d, const double* theta, int B,
     DecInArgs a;
     a.theta = theta; a.off_g11 = d->off_graph11; a.off_in00 = d->off_in00; a.off_in11 = d->off_in11;
     a.B = B; a.N = d->n_particles; a.C = d->channels[0]; a.tau = d->tau_v; a.lat11 = lat11; a.y = y; a.S = S; a.V = V;
-    a.gS = nullptr; a.gV = nullptr; a.gy = nullptr; a.g_lat11 = nullptr; a.partials = nullptr; a.n_params = d->n_params;
+    a.gS = nullptr; a.gV = nullptr; a.gy = nullptr; a.g_lat11 = nullptr; a.partials = nullptr; a.part_stride = 0; a.po_g11 = a.po_in00 = a.po_in11 = 0;
     return a;
 }
 int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, double* S, double* V, cudaStream_t st) {
@@ -682,10 +711,18 @@ int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const doub
     return check_launch("dec_input");
 }
 int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, const double* gS, const double* gV,
-                      const double* gy, double* g_lat11, double* partials, cudaStream_t st) {
+                      const double* gy, double* g_lat11, PartPlan* plan, cudaStream_t st) {
     DecInArgs a = dec_in_args(d, theta, B, lat11, y, nullptr, nullptr);
-    a.gS = gS; a.gV = gV; a.gy = gy; a.g_lat11 = g_lat11; a.partials = partials;
+    a.gS = gS; a.gV = gV; a.gy = gy; a.g_lat11 = g_lat11;
     if (a.N > 128) return LGAE_E_UNSUPPORTED;
+    {
+        const int grid = sm_count();
+        const int64_t ng = (int64_t)2 * a.N * a.tau, w = ng + 4 * a.C, off = plan->block(grid, w);
+        if (int rc = plan->seg(a.off_g11, off, w, 0, ng, grid)) return rc;
+        if (int rc = plan->seg(a.off_in00, off, w, ng, 2 * a.C, grid)) return rc;
+        if (int rc = plan->seg(a.off_in11, off, w, ng + 2 * a.C, 2 * a.C, grid)) return rc;
+        a.partials = plan->base + off; a.part_stride = w; a.po_g11 = 0; a.po_in00 = ng; a.po_in11 = ng + 2 * a.C;
+    }
     const size_t bytes = ((size_t)a.tau * 4 + (size_t)a.N * 4 + (size_t)a.N * a.tau + 2 * a.C) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)dec_input_bwd_kernel, bytes)) return rc;
@@ -700,16 +737,35 @@ int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const dou
     return check_launch("dec_output");
 }
 int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const double* g_recon,
-                       const double* g_gen00, double* gS, double* gV, double* partials, cudaStream_t st) {
-    dec_output_bwd_kernel<<<sm_count(), 256, 0, st>>>(theta, d->off_out00, d->off_out11, B, d->n_particles, d->channels[d->n_levels], S, V, g_recon,
-                                                       g_gen00, gS, gV, partials, d->n_params);
+                       const double* g_gen00, double* gS, double* gV, PartPlan* plan, cudaStream_t st) {
+    const int C = d->channels[d->n_levels], grid = sm_count();
+    const int64_t w = 4 * C, off = plan->block(grid, w);
+    if (int rc = plan->seg(d->off_out00, off, w, 0, 2 * C, grid)) return rc;
+    if (int rc = plan->seg(d->off_out11, off, w, 2 * C, 2 * C, grid)) return rc;
+    dec_output_bwd_kernel<<<grid, 256, 0, st>>>(theta, d->off_out00, d->off_out11, B, d->n_particles, C, S, V, g_recon,
+                                                 g_gen00, gS, gV, plan->base + off, w);
     count_launch();
     return check_launch("dec_output_bwd");
 }
-int run_reduce_partials(const double* partials, int rows, int64_t n, double* gtheta, cudaStream_t st) {
-    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partials, rows, n, gtheta);
+// gtheta = 0, then every segment of the plan is reduced over its rows.
+int run_reduce_plan(const PartPlan* plan, int64_t n_params, double* gtheta, cudaStream_t st) {
+    if (cudaMemsetAsync(gtheta, 0, (size_t)n_params * sizeof(double), st) != cudaSuccess) return check_launch("memset gtheta");
+    if (plan->table.n == 0) return LGAE_OK;
+    int maxlen = 1;
+    for (int i = 0; i < plan->table.n; ++i) maxlen = plan->table.s[i].len > maxlen ? plan->table.s[i].len : maxlen;
+    int gx = (maxlen + 31) / 32;
+    if (gx > 64) gx = 64;
+    reduce_segs_kernel<<<dim3(gx, plan->table.n), dim3(32, 8), 0, st>>>(plan->table, plan->base, gtheta);
     count_launch();
     return check_launch("reduce_partials");
+}
+// Doubles of partial rows used by the glue adjoints of a model.
+int64_t glue_part_doubles(const LgaeModelDesc* d) {
+    const int64_t g = sm_count();
+    if (d->is_decoder) return g * ((int64_t)2 * d->n_particles * d->tau_v + 4 * d->channels[0]) + g * 4 * d->channels[d->n_levels];
+    const int mix = d->latent_mode == LGAE_LATENT_MIX;
+    const int64_t cin = mix ? (int64_t)d->n_particles * d->channels[d->n_levels] : d->channels[d->n_levels];
+    return g * 4 * d->channels[0] + g * 2 * (d->tau_s + d->tau_v) * cin;
 }
 int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
                 double* g_recon, cudaStream_t st) {

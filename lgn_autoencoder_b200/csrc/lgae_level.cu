@@ -9,7 +9,10 @@
 // Thread mapping: lane = particle i (one warp covers a block of 32 particles), warp = channel c.  The radial
 // weights R^l_ij[c] = Linear_l(phi(n_ij)) of a tile of neighbours j are produced with the fp64 tensor-core
 // MMA (phi (pairs x K) times W^T (K x 4C)) into shared memory and consumed by the (i, c) threads; the neighbour
-// sums stay in registers.  Nothing of size O(N^2) ever goes to HBM.
+// sums stay in registers.  The only O(N^2) tensor that goes to HBM is the optional copy of the radial weights
+// R_ij[c] (r_save) that the training forward keeps for the adjoint, which then does not re-evaluate them.
+#include <cstring>
+
 #include "lgae_common.cuh"
 
 namespace lgae {
@@ -24,14 +27,17 @@ struct LevelArgs {
     double* sums;              // (B,N,C,10,2)   [A0V(4), A0S, A1Y(4), A1E]
     double* s_pre;             // (B,N,C',2)
     double* v_out;             // (B,N,C',4,2)
+    double* r_save;            // encoder, N <= 32: (B,N_j,C,32_i,4) radial weights (R0.re, R0.im, R1.re, R1.im); fwd: optional
+                               // output, bwd: input
     // backward only
     const double* g_s_pre;
     const double* g_v_out;
     double* g_s_in;
     double* g_v_in;
     double* g_y;               // decoder: (B,N,4,2), accumulated
-    double* partials;          // (gridDim.x, n_params)
-    int64_t n_params;
+    double* part;              // (gridDim.x, part_stride) per-CTA rows of parameter-gradient partials
+    int64_t part_stride;
+    int64_t po_w0, po_b0, po_w1, po_b1, po_a, po_b, po_c, po_m00, po_m11;   // column offsets inside a row
     int B, N, C, Cout, K;
 };
 
@@ -118,12 +124,12 @@ LGAE_DEV void load_radial_frags(const LevelArgs& a, double (&wf)[KS][NT], double
     }
 }
 
-// Shared-memory carve-up (in doubles) common to forward and backward.
+// Shared-memory carve-up (in doubles) of the forward kernel.
 struct LevelSmem {
     int p, msk, S, V, abc, m00, m11, big;  // offsets
     int total;
 };
-__host__ __device__ inline LevelSmem level_smem(bool enc, int N, int C, int Cout, int KS, bool bwd) {
+__host__ __device__ inline LevelSmem level_smem(bool enc, int N, int C, int Cout, int KS) {
     LevelSmem s;
     int o = 0;
     s.p = o; o += enc ? 4 * N : 8 * N;
@@ -135,15 +141,9 @@ __host__ __device__ inline LevelSmem level_smem(bool enc, int N, int C, int Cout
     s.m11 = o; o += 2 * Cout * 5 * C;
     o = (o + 3) & ~3;
     s.big = o;
-    const int cat = 2 * 25 * C * 32;                       // cat / gcat: [(k*5+comp)][32] complex
-    const int tile = (enc ? (bwd ? 2 : 1) : 0) * TJ * C * 32 * 4;  // Rs (+ gRs)
+    const int cat = 2 * 25 * C * 32;                // cat: [(k*5+comp)][32] complex
+    const int tile = enc ? TJ * C * 32 * 4 : 0;     // Rs
     o += cat > tile ? cat : tile;
-    if (bwd) {
-        o += 2 * Cout * 5 * 32;      // gout_s
-        o += 2 * C * 10 * 32;        // gA_s
-        o += 2 * 2 * Cout * 5 * C;   // gm_s (m00, m11 gradient accumulators)
-        o += 2 * 4 * 32;             // gy_s
-    }
     s.total = o;
     return s;
 }
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
     const int nib = (N + 31) / 32;
     const int b = blockIdx.x / nib, i0 = (blockIdx.x % nib) * 32;
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;
-    const LevelSmem L = level_smem(ENC, N, C, Cout, KS, false);
+    const LevelSmem L = level_smem(ENC, N, C, Cout, KS);
     double* p_s = smem + L.p;
     uint8_t* msk_s = reinterpret_cast<uint8_t*>(smem + L.msk);
     cplx* S_s = reinterpret_cast<cplx*>(smem + L.S);
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
                 const double4 r = *reinterpret_cast<const double4*>(Rs + ((size_t)((jj * C + c) * 32 + lane)) * 4);
                 R0 = cmake(r.x, r.y);
                 R1 = cmake(r.z, r.w);
+                if (a.r_save) reinterpret_cast<double4*>(a.r_save)[((int64_t)(b * N + j) * C + c) * 32 + lane] = r;
             }
             const cplx Sj = S_s[j * C + c];
             cplx Vj[4];
@@ -396,15 +397,90 @@ LGAE_DEV void radial_tile_bwd(const double* p_s, const uint8_t* msk_s, int N, in
     }
 }
 
-template <bool ENC, int NT, int KS>
-__global__ void __launch_bounds__(256) level_bwd_kernel(const LevelArgs a) {
+// Shared-memory carve-up (in doubles) of the backward kernel.
+struct LevelBwdSmem {
+    int p, msk, S, V, abc, m00, m11, gm, gA, gy, un;
+    int total;
+};
+__host__ __device__ inline LevelBwdSmem level_bwd_smem(bool enc, int N, int C, int Cout, int NT, int KS) {
+    LevelBwdSmem s;
+    const int NT2 = KS / 2 + 1;
+    int o = 0;
+    s.p = o; o += enc ? 4 * N : 8 * N;
+    s.msk = o; o += ((N + 7) / 8 + 2) & ~1;
+    s.S = o; o += 2 * N * C;
+    s.V = o; o += 8 * N * C;
+    s.abc = o; o += (3 * 4 * KS + 1) & ~1;
+    s.m00 = o; o += 2 * Cout * 5 * C;
+    s.m11 = o; o += 2 * Cout * 5 * C;
+    s.gm = o; o += 2 * 2 * Cout * 5 * C;     // [irrep][c'][k] complex accumulators, live for the whole CTA
+    s.gA = o; o += 2 * C * 10 * 32;          // [(c*10+e)][32] complex: adjoints of the neighbour sums
+    s.gy = o; o += enc ? 0 : 2 * 4 * 32;
+    o = (o + 3) & ~3;
+    s.un = o;
+    // union: incoming gradients gout [(c'*5+comp)][32] complex (mix adjoint) | gRs tile (pair loop, encoder) |
+    //        reduction scratch of the final flush
+    int u = 2 * Cout * 5 * 32;
+    const int tile = enc ? TJ * C * 32 * 4 : 0;
+    const int red = enc ? (8 * NT) * (8 * NT2) + 3 * 8 * NT2 : 0;
+    u = u > tile ? u : tile;
+    u = u > red ? u : red;
+    o += u;
+    s.total = o;
+    return s;
+}
+
+// Adjoint of "cat -> mix" for one block of the concatenation (k = blk*C + c), thread = (particle lane, channel c):
+//   gm[irrep][c'][k] += sum_lanes conj(cat[comp]) gout[c'][comp]      (mix-weight gradient; lgn/nn/g_nn.py:95-117)
+//   gc[comp]          = sum_c'   conj(W[c'][k])  gout[c'][comp]       (gradient wrt this thread's cat entries)
+LGAE_DEV void mix_adjoint_block(int k, int Cout, int C5, int nm, int lane, const cplx (&cat5)[5], const cplx* gout_s,
+                                const cplx* m00_s, const cplx* m11_s, double* gm_d, cplx (&gc)[5]) {
+#pragma unroll
+    for (int comp = 0; comp < 5; ++comp) gc[comp] = czero();
+    for (int cb = 0; cb < Cout; cb += 4) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int co = cb + u;
+            cplx a0 = czero(), a1 = czero();
+            if (co < Cout) {
+                const cplx* gp = gout_s + (co * 5) * 32 + lane;
+                const cplx g0 = gp[0];
+                a0 = cmulc(cat5[0], g0);
+                cfmac(gc[0], m00_s[co * C5 + k], g0);
+                const cplx w1 = m11_s[co * C5 + k];
+#pragma unroll
+                for (int comp = 1; comp < 5; ++comp) {
+                    const cplx gv = gp[comp * 32];
+                    cfmac(a1, cat5[comp], gv);
+                    cfmac(gc[comp], w1, gv);
+                }
+            }
+            v[4 * u] = a0.x; v[4 * u + 1] = a0.y; v[4 * u + 2] = a1.x; v[4 * u + 3] = a1.y;
+        }
+        const double tot = warp_sum16(v);
+        const int idx = lane >> 1, co = cb + (idx >> 2), irr = (idx >> 1) & 1, ri = idx & 1;
+        if (!(lane & 1) && co < Cout) gm_d[((size_t)(irr * nm + co * C5 + k)) * 2 + ri] += tot;
+    }
+}
+
+// One CTA works on one jet at a time (persistent over jets); warp = channel c, lane = particle.
+//   1. stage the jet, rebuild this thread's 25 cat entries from the saved neighbour sums, push the incoming gradients
+//      through the adjoint of the channel mix (registers + warp butterflies, no cat buffer in shared memory);
+//   2. pair loop over tiles of TJ partners o: role 1 (own = receiving node) yields dL/dR_{lane,o} -> shared tile;
+//      role 2 (own = neighbour) accumulates dL/dS_lane, dL/dV_lane in registers.  Encoder: R_{lane,o} comes from the
+//      copy the forward kept (r_save), prefetched one partner ahead;
+//   3. encoder: adjoint of the radial functions of the tile on the fp64 tensor-core MMA (radial_tile_bwd);
+//   4. when the CTA runs out of jets: one compact row of parameter-gradient partials.
+template <bool ENC, int NT, int KS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a) {
     extern __shared__ __align__(128) double smem[];
     constexpr int NT2 = KS / 2 + 1;
     constexpr int KP = 4 * KS;
     const int N = a.N, C = a.C, Cout = a.Cout, K = a.K;
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const LevelSmem L = level_smem(ENC, N, C, Cout, KS, true);
+    const LevelBwdSmem L = level_bwd_smem(ENC, N, C, Cout, NT, KS);
     double* p_s = smem + L.p;
     uint8_t* msk_s = reinterpret_cast<uint8_t*>(smem + L.msk);
     cplx* S_s = reinterpret_cast<cplx*>(smem + L.S);
@@ -412,28 +488,28 @@ __global__ void __launch_bounds__(256) level_bwd_kernel(const LevelArgs a) {
     double* abc_s = smem + L.abc;
     cplx* m00_s = reinterpret_cast<cplx*>(smem + L.m00);
     cplx* m11_s = reinterpret_cast<cplx*>(smem + L.m11);
-    double* Rs = smem + L.big;
-    double* gRs = Rs + TJ * C * 32 * 4;
-    cplx* cat_s = reinterpret_cast<cplx*>(smem + L.big);
-    const int cat_d = 2 * 25 * C * 32, tile_d = (ENC ? 2 : 0) * TJ * C * 32 * 4;
-    double* after = smem + L.big + (cat_d > tile_d ? cat_d : tile_d);
-    cplx* gout_s = reinterpret_cast<cplx*>(after);                 // [(c'*5+comp)][32]
-    cplx* gA_s = gout_s + Cout * 5 * 32;                            // [(c*10+e)][32]
-    cplx* gm_s = gA_s + C * 10 * 32;                                // [2][Cout*5C]
-    cplx* gy_s = gm_s + 2 * Cout * 5 * C;                           // [4][32]
-    const int nm = Cout * 5 * C;
+    double* gm_d = smem + L.gm;
+    cplx* gA_s = reinterpret_cast<cplx*>(smem + L.gA);
+    cplx* gy_s = reinterpret_cast<cplx*>(smem + L.gy);
+    cplx* gout_s = reinterpret_cast<cplx*>(smem + L.un);
+    double* gRs = smem + L.un;
+    const int nm = Cout * 5 * C, C5 = 5 * C;
 
     for (int t = tid; t < nm; t += blockDim.x) {
         m00_s[t] = cmake(a.theta[a.off_m00 + t], a.theta[a.off_m00 + nm + t]);
         m11_s[t] = cmake(a.theta[a.off_m11 + t], a.theta[a.off_m11 + nm + t]);
     }
-    for (int t = tid; t < 2 * nm; t += blockDim.x) gm_s[t] = czero();
+    for (int t = tid; t < 4 * nm; t += blockDim.x) gm_d[t] = 0.0;
 
-    double wf[KS][NT], bf[NT][2], w2[2 * NT][NT2];
+    double w2[2 * NT][NT2];
     double gw[NT][NT2][2], gabc[3][NT2][2];
     cplx R0c = czero(), R1c = czero(), gR0c = czero(), gR1c = czero();
     if (ENC) {
-        load_radial_frags<NT, KS>(a, wf, bf, abc_s);
+        for (int k = tid; k < KP; k += blockDim.x) {
+            abc_s[k] = k < K ? a.theta[a.off_a + k] : 0.0;
+            abc_s[KP + k] = k < K ? a.theta[a.off_b + k] : 0.0;
+            abc_s[2 * KP + k] = k < K ? a.theta[a.off_c + k] : 0.0;
+        }
 #pragma unroll
         for (int s = 0; s < 2 * NT; ++s)
 #pragma unroll
@@ -452,9 +528,11 @@ __global__ void __launch_bounds__(256) level_bwd_kernel(const LevelArgs a) {
         R1c = cmake(b1, b1);
     }
 
+    const int i = lane;
+    const bool live = i < N;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
-        // ---- stage the jet and the incoming gradients ----
+        // ---- 1a. stage the jet and the incoming gradients ----
         {
             const int np = ENC ? 4 * N : 8 * N;
             const double* src = a.p + (int64_t)b * np;
@@ -482,133 +560,102 @@ __global__ void __launch_bounds__(256) level_bwd_kernel(const LevelArgs a) {
                 for (int t = tid; t < 4 * 32; t += blockDim.x) gy_s[t] = czero();
         }
         __syncthreads();
-        const int i = lane;
-        const bool live = i < N;
-        // ---- rebuild cat from the saved neighbour sums ----
+        // ---- 1b. adjoint of cat -> mix, block by block, in registers ----
+        cplx gS = czero(), gV[4] = {czero(), czero(), czero(), czero()};
         {
-            cplx A0V[4], A0S = czero(), A1Y[4], A1E = czero();
-#pragma unroll
-            for (int mu = 0; mu < 4; ++mu) { A0V[mu] = czero(); A1Y[mu] = czero(); }
-            if (live) {
-                const cplx* src = reinterpret_cast<const cplx*>(a.sums) + ((int64_t)(b * N + i) * C + c) * 10;
-#pragma unroll
-                for (int mu = 0; mu < 4; ++mu) { A0V[mu] = src[mu]; A1Y[mu] = src[5 + mu]; }
-                A0S = src[4];
-                A1E = src[9];
-            }
             const cplx Si = live ? S_s[i * C + c] : czero();
             cplx Vi[4];
 #pragma unroll
             for (int mu = 0; mu < 4; ++mu) Vi[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
-            auto put = [&](int k, int comp, cplx v) { cat_s[(k * 5 + comp) * 32 + lane] = v; };
-            put(c, 0, cscale(A1E, 0.5));
-            put(C + c, 0, cmul_1pi(A0S));
-            put(2 * C + c, 0, Si);
-            put(3 * C + c, 0, cscale(ceta(Vi, Vi), 0.5));
-            put(4 * C + c, 0, cmul(Si, Si));
+            cplx A[10];
+#pragma unroll
+            for (int e = 0; e < 10; ++e) A[e] = czero();
+            if (live) {
+                const cplx* src = reinterpret_cast<const cplx*>(a.sums) + ((int64_t)(b * N + i) * C + c) * 10;
+#pragma unroll
+                for (int e = 0; e < 10; ++e) A[e] = src[e];
+            }
+            cplx cat5[5], gc[5];
+            // block 0: [ (1/2) A1E | (1+i) A0V ]   -> adjoints of A1E, A0V
+            cat5[0] = cscale(A[9], 0.5);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cat5[1 + mu] = cmul_1pi(A[mu]);
+            mix_adjoint_block(c, Cout, C5, nm, lane, cat5, gout_s, m00_s, m11_s, gm_d, gc);
+            gA_s[(c * 10 + 9) * 32 + lane] = cscale(gc[0], 0.5);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) gA_s[(c * 10 + mu) * 32 + lane] = cmul_1mi(gc[1 + mu]);
+            // block 1: [ (1+i) A0S | A1Y ]
+            cat5[0] = cmul_1pi(A[4]);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cat5[1 + mu] = A[5 + mu];
+            mix_adjoint_block(C + c, Cout, C5, nm, lane, cat5, gout_s, m00_s, m11_s, gm_d, gc);
+            gA_s[(c * 10 + 4) * 32 + lane] = cmul_1mi(gc[0]);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) gA_s[(c * 10 + 5 + mu) * 32 + lane] = gc[1 + mu];
+            // block 2: the node itself
+            cat5[0] = Si;
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cat5[1 + mu] = Vi[mu];
+            mix_adjoint_block(2 * C + c, Cout, C5, nm, lane, cat5, gout_s, m00_s, m11_s, gm_d, gc);
+            gS = gc[0];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) gV[mu] = gc[1 + mu];
+            // block 3: self product, [ (1/2) eta(V,V) | V S ]
+            cplx gh[4];
+            cghat(Vi, gh);
+            cat5[0] = cscale(ceta(Vi, Vi), 0.5);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cat5[1 + mu] = cmul(Vi[mu], Si);
+            mix_adjoint_block(3 * C + c, Cout, C5, nm, lane, cat5, gout_s, m00_s, m11_s, gm_d, gc);
 #pragma unroll
             for (int mu = 0; mu < 4; ++mu) {
-                put(c, 1 + mu, cmul_1pi(A0V[mu]));
-                put(C + c, 1 + mu, A1Y[mu]);
-                put(2 * C + c, 1 + mu, Vi[mu]);
-                const cplx sv = cmul(Vi[mu], Si);
-                put(3 * C + c, 1 + mu, sv);
-                put(4 * C + c, 1 + mu, sv);
+                cfmac(gV[mu], gh[mu], gc[0]);
+                cfmac(gV[mu], Si, gc[1 + mu]);
+                cfmac(gS, Vi[mu], gc[1 + mu]);
+            }
+            // block 4: self product, [ S^2 | S V ]
+            cat5[0] = cmul(Si, Si);
+            mix_adjoint_block(4 * C + c, Cout, C5, nm, lane, cat5, gout_s, m00_s, m11_s, gm_d, gc);
+            cfmac(gS, Si, cscale(gc[0], 2.0));
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) {
+                cfmac(gV[mu], Si, gc[1 + mu]);
+                cfmac(gS, Vi[mu], gc[1 + mu]);
             }
         }
-        __syncthreads();
-        // ---- mix-weight gradients: g_m[c'][k] += sum_{i,comp} gout[c'][comp][i] conj(cat[k][comp][i]) ----
+        __syncthreads();  // gout consumed (the gRs tile may overwrite it); gA_s visible
+        // ---- 2./3. pair loop over tiles of partners ----
+        cplx gy[4] = {czero(), czero(), czero(), czero()};
         {
-            const int nw = blockDim.x >> 5;
-            for (int item = c; item < 2 * nm; item += nw) {
-                const int irr = item / nm, r = item % nm, co = r / (5 * C), k = r % (5 * C);
-                cplx acc = czero();
-                if (irr == 0) {
-                    cfmac(acc, cat_s[(k * 5) * 32 + lane], gout_s[(co * 5) * 32 + lane]);
+            double pa[4] = {0, 0, 0, 0};
+            cplx ya[4] = {czero(), czero(), czero(), czero()};
+            if (live) {
+                if (ENC) {
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) pa[mu] = p_s[4 * i + mu];
                 } else {
 #pragma unroll
-                    for (int comp = 1; comp < 5; ++comp)
-                        cfmac(acc, cat_s[(k * 5 + comp) * 32 + lane], gout_s[(co * 5 + comp) * 32 + lane]);
+                    for (int mu = 0; mu < 4; ++mu) ya[mu] = reinterpret_cast<const cplx*>(p_s)[4 * i + mu];
                 }
-                acc.x = warp_sum(acc.x);
-                acc.y = warp_sum(acc.y);
-                if (lane == 0) gm_s[item] = cadd(gm_s[item], acc);
             }
-        }
-        __syncthreads();
-        // ---- gcat = W^H gout, overwriting cat ----
-        for (int it = tid; it < 32 * 25 * C; it += blockDim.x) {
-            const int il = it & 31, r = it >> 5, k = r / 5, comp = r % 5;
-            const cplx* w = (comp == 0 ? m00_s : m11_s) + k;
-            cplx acc = czero();
-            for (int co = 0; co < Cout; ++co) cfmac(acc, w[co * 5 * C], gout_s[(co * 5 + comp) * 32 + il]);
-            cat_s[r * 32 + il] = acc;
-        }
-        __syncthreads();
-        // ---- adjoint of the cat assembly: direct gS/gV, and the adjoints of the four neighbour sums ----
-        cplx gS = czero(), gV[4];
-        {
-            const cplx Si = live ? S_s[i * C + c] : czero();
-            cplx Vi[4], gh[4];
+            const cplx Sa = live ? S_s[i * C + c] : czero();
+            cplx Va[4], gAa[10];
 #pragma unroll
-            for (int mu = 0; mu < 4; ++mu) Vi[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
-            cghat(Vi, gh);
-            auto get = [&](int k, int comp) { return cat_s[(k * 5 + comp) * 32 + lane]; };
-            const cplx g_sq00a = get(3 * C + c, 0), g_sq00b = get(4 * C + c, 0);
-            gS = get(2 * C + c, 0);
-            cfmac(gS, Si, cscale(g_sq00b, 2.0));
+            for (int mu = 0; mu < 4; ++mu) Va[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
 #pragma unroll
-            for (int mu = 0; mu < 4; ++mu) {
-                const cplx g_sq11 = cadd(get(3 * C + c, 1 + mu), get(4 * C + c, 1 + mu));
-                gV[mu] = get(2 * C + c, 1 + mu);
-                cfmac(gV[mu], Si, g_sq11);
-                cfmac(gV[mu], gh[mu], g_sq00a);
-                cfmac(gS, Vi[mu], g_sq11);
-            }
-            // gA: [0..3] A0V, [4] A0S, [5..8] A1Y, [9] A1E
-#pragma unroll
-            for (int mu = 0; mu < 4; ++mu) {
-                gA_s[(c * 10 + mu) * 32 + lane] = cmul_1mi(get(c, 1 + mu));
-                gA_s[(c * 10 + 5 + mu) * 32 + lane] = get(C + c, 1 + mu);
-            }
-            gA_s[(c * 10 + 4) * 32 + lane] = cmul_1mi(get(C + c, 0));
-            gA_s[(c * 10 + 9) * 32 + lane] = cscale(get(c, 0), 0.5);
-        }
-        __syncthreads();  // gcat consumed; Rs/gRs may now overwrite it; gA_s visible
-        cplx gy[4] = {czero(), czero(), czero(), czero()};
-        // ---- pair loop: own index = lane, other index o runs over tiles ----
-        for (int o0 = 0; o0 < N; o0 += TJ) {
-            const int to = min(TJ, N - o0);
-            if (ENC) {
-                radial_tile<NT, KS>(p_s, msk_s, N, C, 0, o0, to, abc_s, wf, bf, Rs);
-                __syncthreads();
-            }
-            {
-                // own quantities, reloaded per tile so that they are dead during the radial adjoint
-                double pa[4] = {0, 0, 0, 0};
-                cplx ya[4] = {czero(), czero(), czero(), czero()};
-                if (live) {
-                    if (ENC) {
-#pragma unroll
-                        for (int mu = 0; mu < 4; ++mu) pa[mu] = p_s[4 * i + mu];
-                    } else {
-#pragma unroll
-                        for (int mu = 0; mu < 4; ++mu) ya[mu] = reinterpret_cast<const cplx*>(p_s)[4 * i + mu];
-                    }
-                }
-                const cplx Sa = live ? S_s[i * C + c] : czero();
-                cplx Va[4], gAa[10];
-#pragma unroll
-                for (int mu = 0; mu < 4; ++mu) Va[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
-#pragma unroll
-                for (int e = 0; e < 10; ++e) gAa[e] = gA_s[(c * 10 + e) * 32 + lane];
+            for (int e = 0; e < 10; ++e) gAa[e] = gA_s[(c * 10 + e) * 32 + lane];
+            const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
+            double4 rnext = make_double4(0.0, 0.0, 0.0, 0.0);
+            if (ENC) rnext = rsv[0];
+            for (int o0 = 0; o0 < N; o0 += TJ) {
+                const int to = min(TJ, N - o0);
                 for (int oo = 0; oo < to; ++oo) {
                     const int o = o0 + oo;
                     cplx R0 = R0c, R1 = R1c;
                     if (ENC) {
-                        const double4 r = *reinterpret_cast<const double4*>(Rs + ((size_t)((oo * C + c) * 32 + lane)) * 4);
-                        R0 = cmake(r.x, r.y);
-                        R1 = cmake(r.z, r.w);
+                        R0 = cmake(rnext.x, rnext.y);
+                        R1 = cmake(rnext.z, rnext.w);
+                        if (o + 1 < N) rnext = rsv[(int64_t)(o + 1) * C * 32];
                     }
                     const cplx So = S_s[o * C + c];
                     cplx Vo[4], Y[4];
@@ -686,11 +733,11 @@ __global__ void __launch_bounds__(256) level_bwd_kernel(const LevelArgs a) {
                         }
                     }
                 }
-            }
-            if (ENC) {
-                __syncthreads();
-                radial_tile_bwd<NT, KS, NT2>(p_s, msk_s, N, C, K, 0, o0, to, abc_s, w2, gRs, gw, gabc);
-                __syncthreads();
+                if (ENC) {
+                    __syncthreads();
+                    radial_tile_bwd<NT, KS, NT2>(p_s, msk_s, N, C, K, 0, o0, to, abc_s, w2, gRs, gw, gabc);
+                    __syncthreads();
+                }
             }
         }
         // ---- results for this jet ----
@@ -716,17 +763,17 @@ __global__ void __launch_bounds__(256) level_bwd_kernel(const LevelArgs a) {
         }
     }
 
-    // ---- per-CTA partial parameter gradients ----
+    // ---- 4. this CTA's row of parameter-gradient partials ----
     __syncthreads();
-    double* part = a.partials + (int64_t)blockIdx.x * a.n_params;
+    double* row = a.part + (int64_t)blockIdx.x * a.part_stride;
     for (int t = tid; t < nm; t += blockDim.x) {
-        part[a.off_m00 + t] = gm_s[t].x;
-        part[a.off_m00 + nm + t] = gm_s[t].y;
-        part[a.off_m11 + t] = gm_s[nm + t].x;
-        part[a.off_m11 + nm + t] = gm_s[nm + t].y;
+        row[a.po_m00 + t] = gm_d[2 * t];
+        row[a.po_m00 + nm + t] = gm_d[2 * t + 1];
+        row[a.po_m11 + t] = gm_d[2 * (nm + t)];
+        row[a.po_m11 + nm + t] = gm_d[2 * (nm + t) + 1];
     }
-    double* red = smem + L.big;  // reuse: [8*NT cols][8*NT2 + 1 ...] accumulators
     if (ENC) {
+        double* red = smem + L.un;  // [8*NT cols][8*NT2] + [3][8*NT2]
         constexpr int NK = 8 * NT2;
         const int ncol = 8 * NT;
         for (int t = tid; t < ncol * NK + 3 * NK; t += blockDim.x) red[t] = 0.0;
@@ -755,20 +802,20 @@ __global__ void __launch_bounds__(256) level_bwd_kernel(const LevelArgs a) {
             const double v = red[col * NK + k];
             const int l = col >= 2 * C ? 1 : 0, o = col - l * 2 * C;
             if (k < K)
-                part[(l ? a.off_w1 : a.off_w0) + (int64_t)o * K + k] = v;
+                row[(l ? a.po_w1 : a.po_w0) + (int64_t)o * K + k] = v;
             else
-                part[(l ? a.off_b1 : a.off_b0) + o] = v;
+                row[(l ? a.po_b1 : a.po_b0) + o] = v;
         }
         for (int t = tid; t < 3 * K; t += blockDim.x) {
             const int x = t / K, k = t % K;
-            part[(x == 0 ? a.off_a : x == 1 ? a.off_b : a.off_c) + k] = red[ncol * NK + x * NK + k];
+            row[(x == 0 ? a.po_a : x == 1 ? a.po_b : a.po_c) + k] = red[ncol * NK + x * NK + k];
         }
     } else {
         // decoder: only the biases learn; R^l[c] = bias (1+i)  =>  g_bias = Re(gR) + Im(gR)
         double v0 = warp_sum(gR0c.x + gR0c.y), v1 = warp_sum(gR1c.x + gR1c.y);
         if (lane == 0) {
-            part[a.off_b0 + c] = v0;
-            part[a.off_b1 + c] = v1;
+            row[a.po_b0 + c] = v0;
+            row[a.po_b1 + c] = v1;
         }
     }
 }
@@ -779,34 +826,52 @@ __global__ void __launch_bounds__(256) level_bwd_kernel(const LevelArgs a) {
 static int pick_ks(int K) { return K <= 12 ? 3 : (K <= 20 ? 5 : (K <= 32 ? 8 : -1)); }
 
 template <bool ENC, int NT, int KS>
-static int launch_level(const LevelArgs& a, bool bwd, cudaStream_t st) {
-    const LevelSmem L = level_smem(ENC, a.N, a.C, a.Cout, KS, bwd);
+static int launch_level_fwd(const LevelArgs& a, cudaStream_t st) {
+    const LevelSmem L = level_smem(ENC, a.N, a.C, a.Cout, KS);
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
-    const int threads = 32 * a.C;
-    if (!bwd) {
-        auto kern = level_fwd_kernel<ENC, NT, KS>;
-        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
-        const int nib = (a.N + 31) / 32;
-        kern<<<a.B * nib, threads, bytes, st>>>(a);
-    } else {
-        if (a.N > 32) return LGAE_E_UNSUPPORTED;
-        auto kern = level_bwd_kernel<ENC, NT, KS>;
-        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
-        kern<<<sm_count(), threads, bytes, st>>>(a);
-    }
+    auto kern = level_fwd_kernel<ENC, NT, KS>;
+    if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
+    const int nib = (a.N + 31) / 32;
+    kern<<<a.B * nib, 32 * a.C, bytes, st>>>(a);
     count_launch();
-    return check_launch(bwd ? "level_bwd" : "level_fwd");
+    return check_launch("level_fwd");
+}
+
+template <bool ENC, int NT, int KS>
+static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
+    if (a.N > 32) return LGAE_E_UNSUPPORTED;
+    const LevelBwdSmem L = level_bwd_smem(ENC, a.N, a.C, a.Cout, NT, KS);
+    const size_t bytes = (size_t)L.total * sizeof(double);
+    if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
+    constexpr int MAXT = NT <= 2 ? 128 : 256;
+    constexpr int MINB = NT <= 2 ? 3 : 1;
+    if (32 * a.C > MAXT) return LGAE_E_UNSUPPORTED;
+    auto kern = level_bwd_kernel<ENC, NT, KS, MAXT, MINB>;
+    if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
+    kern<<<grid, 32 * a.C, bytes, st>>>(a);
+    count_launch();
+    return check_launch("level_bwd");
+}
+
+// Number of CTAs (= rows of partials) the level adjoint uses for a batch.
+int level_bwd_grid(int batch) {
+    const int cap = 4 * sm_count();
+    return batch < cap ? (batch > 0 ? batch : 1) : cap;
 }
 
 template <bool ENC>
-static int dispatch_level(const LevelArgs& a, bool bwd, cudaStream_t st) {
+static int dispatch_level(const LevelArgs& a, bool bwd, int grid, cudaStream_t st) {
     if (a.C < 1 || a.C > LGAE_MAX_CHANNELS || a.Cout < 1 || a.Cout > LGAE_MAX_CHANNELS) return LGAE_E_UNSUPPORTED;
-    if (!ENC) return launch_level<false, 1, 3>(a, bwd, st);
+    if (!ENC) {
+        if (!bwd) return launch_level_fwd<false, 1, 3>(a, st);
+        return a.C <= 4 ? launch_level_bwd<false, 1, 3>(a, grid, st) : launch_level_bwd<false, 3, 3>(a, grid, st);
+    }
     const int nt = (4 * a.C + 7) / 8, ks = pick_ks(a.K);
     if (ks < 0) return LGAE_E_UNSUPPORTED;
-#define LGAE_CASE(NTV, KSV) \
-    if (nt == NTV && ks == KSV) return launch_level<true, NTV, KSV>(a, bwd, st);
+#define LGAE_CASE(NTV, KSV)                                                   \
+    if (nt == NTV && ks == KSV)                                               \
+        return bwd ? launch_level_bwd<true, NTV, KSV>(a, grid, st) : launch_level_fwd<true, NTV, KSV>(a, st);
     LGAE_CASE(1, 3) LGAE_CASE(2, 3) LGAE_CASE(3, 3) LGAE_CASE(4, 3)
     LGAE_CASE(1, 5) LGAE_CASE(2, 5) LGAE_CASE(3, 5) LGAE_CASE(4, 5)
     LGAE_CASE(1, 8) LGAE_CASE(2, 8) LGAE_CASE(3, 8) LGAE_CASE(4, 8)
@@ -814,23 +879,79 @@ static int dispatch_level(const LevelArgs& a, bool bwd, cudaStream_t st) {
     return LGAE_E_UNSUPPORTED;
 }
 
-int run_level(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask,
-              int batch, const double* s_in, const double* v_in, double* sums, double* s_pre, double* v_out,
-              const double* g_s_pre, const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y,
-              double* partials, bool bwd, cudaStream_t st) {
-    if (!d || level < 0 || level >= d->n_levels) return LGAE_E_BADARG;
-    LevelArgs a;
+static void fill_level_args(LevelArgs& a, const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y,
+                            const uint8_t* node_mask, int batch, const double* s_in, const double* v_in, double* sums, double* r_save) {
+    memset(&a, 0, sizeof(a));
     a.theta = theta;
     a.off_a = d->off_rad_a[level]; a.off_b = d->off_rad_b[level]; a.off_c = d->off_rad_c[level];
     a.off_w0 = d->off_rad_w0[level]; a.off_b0 = d->off_rad_b0[level];
     a.off_w1 = d->off_rad_w1[level]; a.off_b1 = d->off_rad_b1[level];
     a.off_m00 = d->off_mix00[level]; a.off_m11 = d->off_mix11[level];
-    a.p = p_or_y; a.node_mask = node_mask; a.s_in = s_in; a.v_in = v_in; a.sums = sums; a.s_pre = s_pre; a.v_out = v_out;
-    a.g_s_pre = g_s_pre; a.g_v_out = g_v_out; a.g_s_in = g_s_in; a.g_v_in = g_v_in; a.g_y = g_y;
-    a.partials = partials; a.n_params = d->n_params;
+    a.p = p_or_y; a.node_mask = node_mask; a.s_in = s_in; a.v_in = v_in; a.sums = sums;
+    a.r_save = (!d->is_decoder && d->n_particles <= 32) ? r_save : nullptr;
     a.B = batch; a.N = d->n_particles; a.C = d->channels[level]; a.Cout = d->channels[level + 1]; a.K = d->n_basis;
+}
+
+int run_level_fwd(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
+                  const double* s_in, const double* v_in, double* sums, double* r_save, double* s_pre, double* v_out, cudaStream_t st) {
+    if (!d || level < 0 || level >= d->n_levels) return LGAE_E_BADARG;
     if (batch <= 0) return LGAE_OK;
-    return d->is_decoder ? dispatch_level<false>(a, bwd, st) : dispatch_level<true>(a, bwd, st);
+    LevelArgs a;
+    fill_level_args(a, d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save);
+    a.s_pre = s_pre; a.v_out = v_out;
+    return d->is_decoder ? dispatch_level<false>(a, false, 0, st) : dispatch_level<true>(a, false, 0, st);
+}
+
+// Adjoint of one level.  Reserves a block of `plan` for the per-CTA partial rows and declares its segments.
+int run_level_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
+                  const double* s_in, const double* v_in, const double* sums, const double* r_save, const double* g_s_pre,
+                  const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y, PartPlan* plan, cudaStream_t st) {
+    if (!d || level < 0 || level >= d->n_levels || !plan) return LGAE_E_BADARG;
+    if (batch <= 0) return LGAE_OK;
+    LevelArgs a;
+    fill_level_args(a, d, level, theta, p_or_y, node_mask, batch, s_in, v_in, const_cast<double*>(sums), const_cast<double*>(r_save));
+    if (!d->is_decoder && !a.r_save) return LGAE_E_UNSUPPORTED;   // the encoder adjoint needs the saved radial weights (N <= 32)
+    a.g_s_pre = g_s_pre; a.g_v_out = g_v_out; a.g_s_in = g_s_in; a.g_v_in = g_v_in; a.g_y = g_y;
+    const int grid = level_bwd_grid(batch);
+    const int C = a.C, K = a.K, nm2 = 2 * a.Cout * 5 * C;
+    int64_t w = 0;
+    const bool enc = !d->is_decoder;
+    if (enc) {
+        a.po_w0 = w; w += (int64_t)2 * C * K;
+        a.po_b0 = w; w += 2 * C;
+        a.po_w1 = w; w += (int64_t)2 * C * K;
+        a.po_b1 = w; w += 2 * C;
+        a.po_a = w; w += K;
+        a.po_b = w; w += K;
+        a.po_c = w; w += K;
+    } else {
+        a.po_b0 = w; w += C;
+        a.po_b1 = w; w += C;
+    }
+    a.po_m00 = w; w += nm2;
+    a.po_m11 = w; w += nm2;
+    const int64_t off = plan->block(grid, w);
+    a.part = plan->base + off;
+    a.part_stride = w;
+    int rc = LGAE_OK;
+    auto seg = [&](int64_t theta_off, int64_t col, int64_t len) { if (rc == LGAE_OK) rc = plan->seg(theta_off, off, w, col, len, grid); };
+    if (enc) {
+        seg(a.off_w0, a.po_w0, (int64_t)2 * C * K); seg(a.off_b0, a.po_b0, 2 * C);
+        seg(a.off_w1, a.po_w1, (int64_t)2 * C * K); seg(a.off_b1, a.po_b1, 2 * C);
+        seg(a.off_a, a.po_a, K); seg(a.off_b, a.po_b, K); seg(a.off_c, a.po_c, K);
+    } else {
+        seg(a.off_b0, a.po_b0, C); seg(a.off_b1, a.po_b1, C);
+    }
+    seg(a.off_m00, a.po_m00, nm2); seg(a.off_m11, a.po_m11, nm2);
+    if (rc != LGAE_OK) return rc;
+    return enc ? dispatch_level<true>(a, true, grid, st) : dispatch_level<false>(a, true, grid, st);
+}
+
+// Width (doubles) of one row of partials of the level adjoint.
+int64_t level_part_width(const LgaeModelDesc* d, int level) {
+    const int C = d->channels[level], Cout = d->channels[level + 1], K = d->n_basis;
+    const int64_t mix = (int64_t)4 * Cout * 5 * C;
+    return d->is_decoder ? 2 * C + mix : (int64_t)4 * C * (K + 1) + 3 * K + mix;
 }
 
 }  // namespace lgae

@@ -10,6 +10,8 @@
 // no shuffles or shared-memory round trips are needed between layers.
 // Backward: per layer, the data gradient uses the same trick with the transposed weights; the weight gradient
 // dW = dZ^T H is a second DMMA GEMM over the chunk's rows with dZ and H staged in shared memory.
+#include <cstring>
+
 #include "lgae_common.cuh"
 
 namespace lgae {
@@ -26,8 +28,9 @@ struct MlpArgs {
     int64_t rows;
     const double* g_y;
     double* g_x;
-    double* partials;
-    int64_t n_params;
+    double* part;          // (gridDim.x, part_stride) per-CTA rows of parameter-gradient partials (zeroed by the host)
+    int64_t part_stride;
+    int64_t po_w[LGAE_MAX_LINEAR], po_b[LGAE_MAX_LINEAR];   // column offsets inside a row
     double slope;
 };
 
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_kernel(const MlpArgs a) {
     double* dz_s = Wq + NTW * NTW * 64;       // RW * WS
     double* h_s = dz_s + RW * WS;             // RW * WS
     const int last = a.n_lin - 1;
-    double* part = a.partials + (int64_t)blockIdx.x * a.n_params;
+    double* part = a.part + (int64_t)blockIdx.x * a.part_stride;
 
     for (int64_t r0 = (int64_t)blockIdx.x * RW; r0 < a.rows; r0 += (int64_t)gridDim.x * RW) {
         const int rl0 = warp * 8 * MT;          // first local row of this warp
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(256) mlp_bwd_kernel(const MlpArgs a) {
             for (int n = tid; n < nout; n += blockDim.x) {
                 double s = 0.0;
                 for (int r = 0; r < RW; ++r) s += dz_s[r * WS + n];
-                part[a.off_b[l] + n] += s;
+                part[a.po_b[l] + n] += s;
             }
             // ---- weight gradient: dW[n][k] += sum_rows dZ[row][n] H[row][k] ----
             for (int t = warp; t < NOt * KIt; t += nwarps) {
@@ -226,8 +229,8 @@ __global__ void __launch_bounds__(256) mlp_bwd_kernel(const MlpArgs a) {
                 }
                 const int n = 8 * mt + g, k = 8 * nt + 2 * q;
                 if (n < nout) {
-                    if (k < nink) part[a.off_w[l] + (int64_t)n * nink + k] += c0;
-                    if (k + 1 < nink) part[a.off_w[l] + (int64_t)n * nink + k + 1] += c1;
+                    if (k < nink) part[a.po_w[l] + (int64_t)n * nink + k] += c0;
+                    if (k + 1 < nink) part[a.po_w[l] + (int64_t)n * nink + k + 1] += c1;
                 }
             }
             // ---- data gradient: Gin[row][k] = sum_n dZ[row][n] W[n][k], then through the LeakyReLU of layer l-1 ----
@@ -299,19 +302,38 @@ static int launch_mlp(const MlpArgs& a, bool bwd, cudaStream_t st) {
 }
 
 int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* x, int64_t rows, double* acts,
-            double* y, const double* g_y, double* g_x, double* partials, bool bwd, cudaStream_t st) {
+            double* y, const double* g_y, double* g_x, PartPlan* plan, bool bwd, cudaStream_t st) {
     if (!d || level < 0 || level >= d->n_levels || !d->has_mlp) return LGAE_E_BADARG;
     MlpArgs a;
+    memset(&a, 0, sizeof(a));
     a.theta = theta;
     a.n_lin = d->mlp_hidden + 1;
     if (a.n_lin < 2 || a.n_lin > LGAE_MAX_LINEAR) return LGAE_E_UNSUPPORTED;
     for (int i = 0; i < a.n_lin; ++i) { a.off_w[i] = d->off_mlp_w[level][i]; a.off_b[i] = d->off_mlp_b[level][i]; }
     a.nin = 2 * d->channels[level + 1];
     a.width = d->mlp_width[level];
-    a.x = x; a.acts = acts; a.y = y; a.rows = rows; a.g_y = g_y; a.g_x = g_x; a.partials = partials;
-    a.n_params = d->n_params;
+    a.x = x; a.acts = acts; a.y = y; a.rows = rows; a.g_y = g_y; a.g_x = g_x;
     a.slope = 0.01;
     if (rows <= 0) return LGAE_OK;
+    if (bwd) {
+        if (!plan) return LGAE_E_BADARG;
+        const int grid = sm_count();
+        int64_t w = 0;
+        for (int i = 0; i < a.n_lin; ++i) {
+            const int nout = i == a.n_lin - 1 ? a.nin : a.width, nink = i == 0 ? a.nin : a.width;
+            a.po_w[i] = w; w += (int64_t)nout * nink;
+            a.po_b[i] = w; w += nout;
+        }
+        const int64_t off = plan->block(grid, w);
+        a.part = plan->base + off;
+        a.part_stride = w;
+        for (int i = 0; i < a.n_lin; ++i) {
+            const int nout = i == a.n_lin - 1 ? a.nin : a.width, nink = i == 0 ? a.nin : a.width;
+            if (int rc = plan->seg(a.off_w[i], off, w, a.po_w[i], (int64_t)nout * nink, grid)) return rc;
+            if (int rc = plan->seg(a.off_b[i], off, w, a.po_b[i], nout, grid)) return rc;
+        }
+        if (cudaMemsetAsync(a.part, 0, (size_t)grid * w * sizeof(double), st) != cudaSuccess) return check_launch("memset mlp partials");
+    }
     const int ntw = (a.width + 7) / 8, nti = (a.nin + 7) / 8;
 #define LGAE_MLP_CASE(W, I, M) \
     if (ntw == W && nti == I) return launch_mlp<W, I, M>(a, bwd, st);
@@ -321,6 +343,18 @@ int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double
 #undef LGAE_MLP_CASE
     return LGAE_E_UNSUPPORTED;
 }
+
+// Width (doubles) of one row of partials of the MLP adjoint.
+int64_t mlp_part_width(const LgaeModelDesc* d, int level) {
+    const int n_lin = d->mlp_hidden + 1, nin = 2 * d->channels[level + 1], width = d->mlp_width[level];
+    int64_t w = 0;
+    for (int i = 0; i < n_lin; ++i) {
+        const int nout = i == n_lin - 1 ? nin : width, nink = i == 0 ? nin : width;
+        w += (int64_t)nout * nink + nout;
+    }
+    return w;
+}
+int mlp_bwd_grid() { return sm_count(); }
 
 int mlp_padded_width(const LgaeModelDesc* d, int level) { return 8 * ((d->mlp_width[level] + 7) / 8); }
 

@@ -108,8 +108,8 @@ class FusedPlan:
             raise NotImplementedError("configuration not supported by the fused B200 path")
         return torch.empty(max(int(n), 1), dtype=torch.float64, device=device)
 
-    def partials(self, device) -> torch.Tensor:
-        n = self._lib.lgae_partials_doubles(C.byref(self.desc))
+    def partials(self, batch: int, device) -> torch.Tensor:
+        n = self._lib.lgae_partials_doubles(C.byref(self.desc), batch)
         return torch.empty(max(int(n), 1), dtype=torch.float64, device=device)
 
     def ws_tensor(self, ws: torch.Tensor, batch: int, kind: int, level: int, shape) -> torch.Tensor:
@@ -152,7 +152,7 @@ def encoder_backward_raw(plan: FusedPlan, theta, p4, node_mask, ws, sel, g00, g1
     lib = plan._lib
     dev = p4.device
     gtheta = torch.empty(plan.n_params, dtype=torch.float64, device=dev)
-    part = plan.partials(dev)
+    part = plan.partials(p4.shape[0], dev)
     check(lib.lgae_encoder_backward(C.byref(plan.desc), ptr(theta), ptr(p4), ptr(node_mask), p4.shape[0], ptr(ws), ptr(sel),
                                     ptr(g00), ptr(g11), ptr(gtheta), ptr(part), _stream()), "encoder_backward")
     return gtheta
@@ -176,7 +176,7 @@ def decoder_backward_raw(plan: FusedPlan, theta, lat11, ws, g_recon, g_gen00):
     b = lat11.shape[1]
     gtheta = torch.empty(plan.n_params, dtype=torch.float64, device=dev)
     g_lat11 = torch.empty_like(lat11)
-    part = plan.partials(dev)
+    part = plan.partials(b, dev)
     check(lib.lgae_decoder_backward(C.byref(plan.desc), ptr(theta), ptr(lat11), b, ptr(ws), ptr(g_recon), ptr(g_gen00), ptr(g_lat11),
                                     ptr(gtheta), ptr(part), _stream()), "decoder_backward")
     return g_lat11, gtheta
