@@ -238,6 +238,7 @@ def main():
         g_v = torch.randn(B, N, Co, 4, 2, dtype=torch.float64, device=dev)
         g_s = torch.randn(B, N, Co, 2, dtype=torch.float64, device=dev)
         rsv = plan.ws_tensor(ws, B, 7, lvl, (B, N, C, 32, 4))
+        grs = torch.empty_like(rsv)
         gs_in, gv_in = torch.empty_like(s_in), torch.empty_like(v_in)
         part = plan.partials(B, dev)
         gth = torch.empty(plan.n_params, dtype=torch.float64, device=dev)
@@ -245,7 +246,7 @@ def main():
 
         def kern():
             _lib.check(lib.lgae_level_backward(Ct.byref(plan.desc), lvl, theta.data_ptr(), p4n.data_ptr(), None, B, s_in.data_ptr(),
-                                               v_in.data_ptr(), sums.data_ptr(), rsv.data_ptr(), g_s.data_ptr(), g_v.data_ptr(),
+                                               v_in.data_ptr(), sums.data_ptr(), rsv.data_ptr(), grs.data_ptr(), g_s.data_ptr(), g_v.data_ptr(),
                                                gs_in.data_ptr(), gv_in.data_ptr(), None, gth.data_ptr(), part.data_ptr(), st), "level_backward")
         for _ in range(3):
             kern()

@@ -93,7 +93,8 @@ int64_t lgae_workspace_doubles(const LgaeModelDesc* d, int32_t batch);
 /* Offset (doubles) of one saved tensor inside the workspace, or -1.  kind: 0 = S_in[level] (B,N,C,2),
  * 1 = V_in[level] (B,N,C,4,2) (level == n_levels gives the final features), 2 = pre-MLP scalars of level,
  * 3 = canonical momenta y (B,N,4,2), 4 = neighbour sums of level (B,N,C,10,2), 5 = masses (B,N) (encoder),
- * 6 = MLP activations of level (hidden, B*N, padded width), 7 = radial weights of level (B,N,C,32,4) (encoder, N <= 32). */
+ * 6 = MLP activations of level (hidden, B*N, padded width), 7 = radial weights of level (B,N,C,32,4) (encoder, N <= 32),
+ * 8 = scratch for dL/dR of one level (B,N,max C,32,4) (encoder, N <= 32). */
 int64_t lgae_workspace_offset(const LgaeModelDesc* d, int32_t batch, int32_t kind, int32_t level);
 /* Doubles of scratch for the per-CTA rows of parameter-gradient partials the backward entry points write (every
  * backward kernel owns a block of compact rows; one reduce launch sums them into gtheta, in a fixed order). */
@@ -140,12 +141,13 @@ int lgae_l1(const double* theta, int64_t n, double lambda, double* out_accumulat
 int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
                        const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
                        double* sums, double* r_save, double* s_pre, double* v_out, void* stream);
-/* gtheta (n_params) is overwritten: zero except for the parameters of this level. */
+/* gtheta (n_params) is overwritten: zero except for the parameters of this level.  g_r_scratch (encoder):
+ * (B,N,C,32,4) scratch for dL/dR of the ordered pairs (workspace kind 8). */
 int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
                         const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
-                        const double* sums, const double* r_save, const double* g_s_pre, const double* g_v_out,
-                        double* g_s_in, double* g_v_in, double* g_y_accumulate, double* gtheta, double* partials,
-                        void* stream);
+                        const double* sums, const double* r_save, double* g_r_scratch, const double* g_s_pre,
+                        const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y_accumulate, double* gtheta,
+                        double* partials, void* stream);
 /* CGMLP on rows = batch*N interleaved scalars x (rows, 2C').  acts: (n_hidden, rows, width_padded) saved
  * activations.  y (rows, 2C'). */
 int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows,

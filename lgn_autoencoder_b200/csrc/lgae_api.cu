@@ -14,8 +14,14 @@ namespace lgae {
 int run_level_fwd(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
                   const double* s_in, const double* v_in, double* sums, double* r_save, double* s_pre, double* v_out, cudaStream_t st);
 int run_level_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
-                  const double* s_in, const double* v_in, const double* sums, const double* r_save, const double* g_s_pre,
+                  const double* s_in, const double* v_in, const double* sums, const double* r_save, double* g_r, const double* g_s_pre,
                   const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y, PartPlan* plan, cudaStream_t st);
+int run_radial_fwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
+                   double* r, cudaStream_t st);
+int run_radial_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
+                   const double* g_r, PartPlan* plan, cudaStream_t st);
+int radial_grid();
+int64_t radial_part_width(const LgaeModelDesc* d, int level);
 int level_bwd_grid(int batch);
 int64_t level_part_width(const LgaeModelDesc* d, int level);
 int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* x, int64_t rows, double* acts, double* y,
@@ -78,7 +84,7 @@ int sm_count() {
 struct Layout {
     int64_t S[LGAE_MAX_LEVELS + 1], V[LGAE_MAX_LEVELS + 1];
     int64_t sums[LGAE_MAX_LEVELS], spre[LGAE_MAX_LEVELS], acts[LGAE_MAX_LEVELS], rsave[LGAE_MAX_LEVELS];
-    int64_t y, mass, gS[2], gV[2], gSpre, gy, total;
+    int64_t y, mass, gS[2], gV[2], gSpre, gy, gr, total;
 };
 static int max_channels(const LgaeModelDesc* d) {
     int m = 1;
@@ -107,6 +113,8 @@ static Layout layout(const LgaeModelDesc* d, int64_t B) {
     for (int k = 0; k < 2; ++k) { L.gS[k] = take(nodes * cm * 2); L.gV[k] = take(nodes * cm * 8); }
     L.gSpre = take(nodes * cm * 2);
     L.gy = take(nodes * 8);
+    // encoder, N <= 32: dL/dR of the ordered pairs of the level being differentiated (reused by every level)
+    L.gr = (!d->is_decoder && d->n_particles <= 32) ? take(nodes * cm * 128) : -1;
     L.total = o;
     return L;
 }
@@ -168,6 +176,7 @@ int64_t lgae_workspace_offset(const LgaeModelDesc* d, int32_t batch, int32_t kin
         case 5: return L.mass;
         case 6: return level < d->n_levels ? L.acts[level] : -1;
         case 7: return level < d->n_levels ? L.rsave[level] : -1;
+        case 8: return L.gr;
         default: return -1;
     }
 }
@@ -176,6 +185,7 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
     int64_t n = glue_part_doubles(d);
     for (int l = 0; l < d->n_levels; ++l) {
         n += (int64_t)level_bwd_grid(batch) * level_part_width(d, l);
+        if (!d->is_decoder) n += (int64_t)radial_grid() * radial_part_width(d, l);
         if (d->has_mlp) n += (int64_t)mlp_bwd_grid() * mlp_part_width(d, l);
     }
     return n;
@@ -191,6 +201,7 @@ int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     const int64_t rows = (int64_t)batch * d->n_particles;
     LGAE_TRY(run_enc_input(d, theta, p4, batch, ws + L.mass, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
+        if (L.rsave[l] >= 0) LGAE_TRY(run_radial_fwd(d, l, theta, p4, node_mask, batch, ws + L.rsave[l], st));
         LGAE_TRY(run_level_fwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l],
                                L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, ws + L.spre[l], ws + L.V[l + 1], st));
         if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
@@ -225,9 +236,10 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
                     g_spre = ws + L.gS[cur];
                 }
             }
-            LGAE_TRY(run_level_bwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l],
-                                   L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, g_spre, ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1],
-                                   nullptr, &plan, st));
+            if (L.rsave[l] < 0 || L.gr < 0) return LGAE_E_UNSUPPORTED;
+            LGAE_TRY(run_level_bwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], ws + L.rsave[l], ws + L.gr,
+                                   g_spre, ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], nullptr, &plan, st));
+            LGAE_TRY(run_radial_bwd(d, l, theta, p4, node_mask, batch, ws + L.gr, &plan, st));
             cur ^= 1;
             gs_zero = false;
         }
@@ -278,7 +290,7 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
                     g_spre = ws + L.gS[cur];
                 }
             }
-            LGAE_TRY(run_level_bwd(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, g_spre,
+            LGAE_TRY(run_level_bwd(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, nullptr, g_spre,
                                    ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], ws + L.gy, &plan, st));
             cur ^= 1;
             gs_zero = false;
@@ -315,20 +327,23 @@ int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* thet
                        void* stream) {
     LGAE_TRY(check_desc(d));
     if (!theta || !p_or_y || !s_in || !v_in || !sums || !s_pre || !v_out || batch < 0) return LGAE_E_BADARG;
+    if (!d->is_decoder && d->n_particles <= 32 && r_save)
+        LGAE_TRY(run_radial_fwd(d, level, theta, p_or_y, node_mask, batch, r_save, (cudaStream_t)stream));
     return run_level_fwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, s_pre, v_out, (cudaStream_t)stream);
 }
 int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y, const uint8_t* node_mask,
                         int32_t batch, const double* s_in, const double* v_in, const double* sums, const double* r_save,
-                        const double* g_s_pre, const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y_accumulate,
-                        double* gtheta, double* partials, void* stream) {
+                        double* g_r_scratch, const double* g_s_pre, const double* g_v_out, double* g_s_in, double* g_v_in,
+                        double* g_y_accumulate, double* gtheta, double* partials, void* stream) {
     LGAE_TRY(check_desc(d));
     if (!theta || !p_or_y || !s_in || !v_in || !sums || !g_v_out || !g_s_in || !g_v_in || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
     if (d->is_decoder && !g_y_accumulate) return LGAE_E_BADARG;
-    if (!d->is_decoder && !r_save) return LGAE_E_BADARG;
+    if (!d->is_decoder && (!r_save || !g_r_scratch)) return LGAE_E_BADARG;
     PartPlan plan;
     plan.base = partials;
-    LGAE_TRY(run_level_bwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, g_s_pre, g_v_out, g_s_in, g_v_in,
-                           g_y_accumulate, &plan, (cudaStream_t)stream));
+    LGAE_TRY(run_level_bwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, g_r_scratch, g_s_pre, g_v_out, g_s_in,
+                           g_v_in, g_y_accumulate, &plan, (cudaStream_t)stream));
+    if (!d->is_decoder) LGAE_TRY(run_radial_bwd(d, level, theta, p_or_y, node_mask, batch, g_r_scratch, &plan, (cudaStream_t)stream));
     return run_reduce_plan(&plan, d->n_params, gtheta, (cudaStream_t)stream);
 }
 int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, double* acts, double* y,

@@ -27,8 +27,9 @@ struct LevelArgs {
     double* sums;              // (B,N,C,10,2)   [A0V(4), A0S, A1Y(4), A1E]
     double* s_pre;             // (B,N,C',2)
     double* v_out;             // (B,N,C',4,2)
-    double* r_save;            // encoder, N <= 32: (B,N_j,C,32_i,4) radial weights (R0.re, R0.im, R1.re, R1.im); fwd: optional
-                               // output, bwd: input
+    double* r_save;            // encoder, N <= 32: (B,N_j,C,32_i,4) radial weights (R0.re, R0.im, R1.re, R1.im), produced by
+                               // radial_fwd_kernel (lgae_radial.cu); input of the PRE forward and of the adjoint
+    double* g_r;               // encoder adjoint out: dL/dR of the ordered pairs, same layout as r_save
     // backward only
     const double* g_s_pre;
     const double* g_v_out;
@@ -129,7 +130,7 @@ struct LevelSmem {
     int p, msk, S, V, abc, m00, m11, big;  // offsets
     int total;
 };
-__host__ __device__ inline LevelSmem level_smem(bool enc, int N, int C, int Cout, int KS) {
+__host__ __device__ inline LevelSmem level_smem(bool enc, bool tiles, int N, int C, int Cout, int KS) {
     LevelSmem s;
     int o = 0;
     s.p = o; o += enc ? 4 * N : 8 * N;
@@ -142,7 +143,7 @@ __host__ __device__ inline LevelSmem level_smem(bool enc, int N, int C, int Cout
     o = (o + 3) & ~3;
     s.big = o;
     const int cat = 2 * 25 * C * 32;                // cat: [(k*5+comp)][32] complex
-    const int tile = enc ? TJ * C * 32 * 4 : 0;     // Rs
+    const int tile = tiles ? TJ * C * 32 * 4 : 0;   // Rs (radial weights evaluated in the kernel)
     o += cat > tile ? cat : tile;
     s.total = o;
     return s;
@@ -151,14 +152,16 @@ __host__ __device__ inline LevelSmem level_smem(bool enc, int N, int C, int Cout
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
-template <bool ENC, int NT, int KS>
+// PRE (encoder, N <= 32): the radial weights were computed by radial_fwd_kernel and are streamed from r_save (one
+// double4 per partner, prefetched one partner ahead); no radial tiles, no barriers inside the neighbour loop.
+template <bool ENC, int NT, int KS, bool PRE>
 __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
     extern __shared__ __align__(128) double smem[];
     const int N = a.N, C = a.C, Cout = a.Cout;
     const int nib = (N + 31) / 32;
     const int b = blockIdx.x / nib, i0 = (blockIdx.x % nib) * 32;
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;
-    const LevelSmem L = level_smem(ENC, N, C, Cout, KS);
+    const LevelSmem L = level_smem(ENC, ENC && !PRE, N, C, Cout, KS);
     double* p_s = smem + L.p;
     uint8_t* msk_s = reinterpret_cast<uint8_t*>(smem + L.msk);
     cplx* S_s = reinterpret_cast<cplx*>(smem + L.S);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
     double wf[KS][NT], bf[NT][2];
     cplx R0c = czero(), R1c = czero();
     if (ENC) {
-        load_radial_frags<NT, KS>(a, wf, bf, abc_s);
+        if (!PRE) load_radial_frags<NT, KS>(a, wf, bf, abc_s);
     } else {
         // decoder: all-zero edge mask => R^l[c] = bias_l[c] * (1+i)   
         const double b0 = a.theta[a.off_b0 + c], b1 = a.theta[a.off_b1 + c];
@@ -216,20 +219,26 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
 #pragma unroll
     for (int mu = 0; mu < 4; ++mu) { A0V[mu] = czero(); A1Y[mu] = czero(); }
 
+    const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
+    double4 rnext = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (ENC && PRE) rnext = rsv[0];
     for (int j0 = 0; j0 < N; j0 += TJ) {
         const int tj = min(TJ, N - j0);
-        if (ENC) {
+        if (ENC && !PRE) {
             radial_tile<NT, KS>(p_s, msk_s, N, C, i0, j0, tj, abc_s, wf, bf, Rs);
             __syncthreads();
         }
         for (int jj = 0; jj < tj; ++jj) {
             const int j = j0 + jj;
             cplx R0 = R0c, R1 = R1c;
-            if (ENC) {
+            if (ENC && PRE) {
+                R0 = cmake(rnext.x, rnext.y);
+                R1 = cmake(rnext.z, rnext.w);
+                if (j + 1 < N) rnext = rsv[(int64_t)(j + 1) * C * 32];
+            } else if (ENC) {
                 const double4 r = *reinterpret_cast<const double4*>(Rs + ((size_t)((jj * C + c) * 32 + lane)) * 4);
                 R0 = cmake(r.x, r.y);
                 R1 = cmake(r.z, r.w);
-                if (a.r_save) reinterpret_cast<double4*>(a.r_save)[((int64_t)(b * N + j) * C + c) * 32 + lane] = r;
             }
             const cplx Sj = S_s[j * C + c];
             cplx Vj[4];
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
             }
             cfma(A1E, R1, e);
         }
-        if (ENC) __syncthreads();
+        if (ENC && !PRE) __syncthreads();
     }
 
     // ---- keep the neighbour sums for the backward pass; build cat = [ag | node | sq] in shared memory ----
@@ -319,113 +328,24 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
-// Adjoint of the radial functions for one tile: consumes gRs (same layout as Rs), accumulates
-//   gw[mt][nt2] : d/dW[col][k] (+ bias in column k == K), as MMA accumulators (col = 8mt+g, k = 8nt2+2q+e)
-//   gabc[3][nt2][2] : d/da_k, d/db_k, d/dc_k for k = 8nt2+2q+e, partial over this lane's pairs
-template <int NT, int KS, int NT2>
-LGAE_DEV void radial_tile_bwd(const double* p_s, const uint8_t* msk_s, int N, int C, int K, int i0, int j0, int tj,
-                              const double* abc_s, const double (&w2)[2 * NT][NT2], const double* gRs,
-                              double (&gw)[NT][NT2][2], double (&gabc)[3][NT2][2]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int g = lane >> 2, q = lane & 3;
-    constexpr int KP = 4 * KS;
-    auto gr_at = [&](int jj, int il, int col) -> double {
-        if (col >= 4 * C) return 0.0;
-        const int l = col >= 2 * C ? 1 : 0, rem = col - l * 2 * C;
-        return gRs[((size_t)((jj * C + (rem >> 1)) * 32 + il)) * 4 + 2 * l + (rem & 1)];
-    };
-    for (int grp = warp; grp < 4 * tj; grp += nwarps) {
-        const int jj = grp >> 2, ib8 = (grp & 3) * 8, il = ib8 + g, i = i0 + il, j = j0 + jj;
-        double n = 0.0;
-        bool m = false;
-        if (i < N) {
-            n = pair_norm(p_s + 4 * i, p_s + 4 * j);
-            m = msk_s[i] && msk_s[j] && n != 0.0;
-        }
-        const bool valid = i < N;
-        // d/dphi[pair g][k] = sum_col gR[pair][col] W[col][k]
-        double gphi[NT2][2];
-#pragma unroll
-        for (int nt = 0; nt < NT2; ++nt) gphi[nt][0] = gphi[nt][1] = 0.0;
-#pragma unroll
-        for (int s = 0; s < 2 * NT; ++s) {
-            const double av = valid ? gr_at(jj, il, 4 * s + q) : 0.0;
-#pragma unroll
-            for (int nt = 0; nt < NT2; ++nt) dmma(gphi[nt][0], gphi[nt][1], av, w2[s][nt]);
-        }
-        if (m) {
-            const double nn = n * n;
-#pragma unroll
-            for (int nt = 0; nt < NT2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int k = 8 * nt + 2 * q + e;
-                    if (k < K) {
-                        const double ck = abc_s[2 * KP + k], bk = abc_s[KP + k];
-                        const double cn = ck * n;
-                        const double rd = 1.0 / (1.0 + cn * cn + 1e-16);
-                        const double gp = gphi[nt][e];
-                        gabc[0][nt][e] += gp;
-                        gabc[1][nt][e] = fma(gp, rd, gabc[1][nt][e]);
-                        gabc[2][nt][e] = fma(gp, -2.0 * bk * rd * rd * ck * nn, gabc[2][nt][e]);
-                    }
-                }
-        }
-        // d/dW[col][k] += sum_pairs gR[pair][col] phi[pair][k]   (k == K: the bias column, phi == 1)
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const int pp = q + 4 * ks;
-            const double n2 = __shfl_sync(0xffffffffu, n, pp * 4);
-            const int m2 = __shfl_sync(0xffffffffu, (int)m, pp * 4);
-            const bool valid2 = (i0 + ib8 + pp) < N;
-            double a3[NT];
-#pragma unroll
-            for (int mt = 0; mt < NT; ++mt) a3[mt] = valid2 ? gr_at(jj, ib8 + pp, 8 * mt + g) : 0.0;
-#pragma unroll
-            for (int nt = 0; nt < NT2; ++nt) {
-                const int k = 8 * nt + g;
-                double phi = 0.0;
-                if (k < K) {
-                    if (m2) phi = bell(abc_s[k], abc_s[KP + k], abc_s[2 * KP + k], n2);
-                } else if (k == K) {
-                    phi = 1.0;
-                }
-#pragma unroll
-                for (int mt = 0; mt < NT; ++mt) dmma(gw[mt][nt][0], gw[mt][nt][1], a3[mt], phi);
-            }
-        }
-    }
-}
-
 // Shared-memory carve-up (in doubles) of the backward kernel.
 struct LevelBwdSmem {
-    int p, msk, S, V, abc, m00, m11, gm, gA, gy, un;
+    int p, S, V, m00, m11, gm, gA, gy, gout;
     int total;
 };
-__host__ __device__ inline LevelBwdSmem level_bwd_smem(bool enc, int N, int C, int Cout, int NT, int KS) {
+__host__ __device__ inline LevelBwdSmem level_bwd_smem(bool enc, int N, int C, int Cout) {
     LevelBwdSmem s;
-    const int NT2 = KS / 2 + 1;
     int o = 0;
     s.p = o; o += enc ? 4 * N : 8 * N;
-    s.msk = o; o += ((N + 7) / 8 + 2) & ~1;
     s.S = o; o += 2 * N * C;
     s.V = o; o += 8 * N * C;
-    s.abc = o; o += (3 * 4 * KS + 1) & ~1;
     s.m00 = o; o += 2 * Cout * 5 * C;
     s.m11 = o; o += 2 * Cout * 5 * C;
     s.gm = o; o += 2 * 2 * Cout * 5 * C;     // [irrep][c'][k] complex accumulators, live for the whole CTA
     s.gA = o; o += 2 * C * 10 * 32;          // [(c*10+e)][32] complex: adjoints of the neighbour sums
     s.gy = o; o += enc ? 0 : 2 * 4 * 32;
     o = (o + 3) & ~3;
-    s.un = o;
-    // union: incoming gradients gout [(c'*5+comp)][32] complex (mix adjoint) | gRs tile (pair loop, encoder) |
-    //        reduction scratch of the final flush
-    int u = 2 * Cout * 5 * 32;
-    const int tile = enc ? TJ * C * 32 * 4 : 0;
-    const int red = enc ? (8 * NT) * (8 * NT2) + 3 * 8 * NT2 : 0;
-    u = u > tile ? u : tile;
-    u = u > red ? u : red;
-    o += u;
+    s.gout = o; o += 2 * Cout * 5 * 32;      // incoming gradients [(c'*5+comp)][32] complex
     s.total = o;
     return s;
 }
@@ -467,32 +387,25 @@ LGAE_DEV void mix_adjoint_block(int k, int Cout, int C5, int nm, int lane, const
 // One CTA works on one jet at a time (persistent over jets); warp = channel c, lane = particle.
 //   1. stage the jet, rebuild this thread's 25 cat entries from the saved neighbour sums, push the incoming gradients
 //      through the adjoint of the channel mix (registers + warp butterflies, no cat buffer in shared memory);
-//   2. pair loop over tiles of TJ partners o: role 1 (own = receiving node) yields dL/dR_{lane,o} -> shared tile;
-//      role 2 (own = neighbour) accumulates dL/dS_lane, dL/dV_lane in registers.  Encoder: R_{lane,o} comes from the
-//      copy the forward kept (r_save), prefetched one partner ahead;
-//   3. encoder: adjoint of the radial functions of the tile on the fp64 tensor-core MMA (radial_tile_bwd);
-//   4. when the CTA runs out of jets: one compact row of parameter-gradient partials.
-template <bool ENC, int NT, int KS, int MAXT, int MINB>
+//   2. neighbour loop over partners o, no barriers: role 1 (own = receiving node) yields dL/dR_{lane,o}, streamed to
+//      g_r for radial_bwd_kernel (encoder) or summed (decoder: constant radial weights); role 2 (own = neighbour)
+//      accumulates dL/dS_lane, dL/dV_lane in registers.  Encoder: R_{lane,o} is streamed from r_save, prefetched;
+//   3. when the CTA runs out of jets: one compact row of parameter-gradient partials (mix weights, decoder biases).
+template <bool ENC, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a) {
     extern __shared__ __align__(128) double smem[];
-    constexpr int NT2 = KS / 2 + 1;
-    constexpr int KP = 4 * KS;
-    const int N = a.N, C = a.C, Cout = a.Cout, K = a.K;
+    const int N = a.N, C = a.C, Cout = a.Cout;
     const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;
-    const int g = lane >> 2, q = lane & 3;
-    const LevelBwdSmem L = level_bwd_smem(ENC, N, C, Cout, NT, KS);
+    const LevelBwdSmem L = level_bwd_smem(ENC, N, C, Cout);
     double* p_s = smem + L.p;
-    uint8_t* msk_s = reinterpret_cast<uint8_t*>(smem + L.msk);
     cplx* S_s = reinterpret_cast<cplx*>(smem + L.S);
     cplx* V_s = reinterpret_cast<cplx*>(smem + L.V);
-    double* abc_s = smem + L.abc;
     cplx* m00_s = reinterpret_cast<cplx*>(smem + L.m00);
     cplx* m11_s = reinterpret_cast<cplx*>(smem + L.m11);
     double* gm_d = smem + L.gm;
     cplx* gA_s = reinterpret_cast<cplx*>(smem + L.gA);
     cplx* gy_s = reinterpret_cast<cplx*>(smem + L.gy);
-    cplx* gout_s = reinterpret_cast<cplx*>(smem + L.un);
-    double* gRs = smem + L.un;
+    cplx* gout_s = reinterpret_cast<cplx*>(smem + L.gout);
     const int nm = Cout * 5 * C, C5 = 5 * C;
 
     for (int t = tid; t < nm; t += blockDim.x) {
@@ -501,28 +414,8 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
     }
     for (int t = tid; t < 4 * nm; t += blockDim.x) gm_d[t] = 0.0;
 
-    double w2[2 * NT][NT2];
-    double gw[NT][NT2][2], gabc[3][NT2][2];
     cplx R0c = czero(), R1c = czero(), gR0c = czero(), gR1c = czero();
-    if (ENC) {
-        for (int k = tid; k < KP; k += blockDim.x) {
-            abc_s[k] = k < K ? a.theta[a.off_a + k] : 0.0;
-            abc_s[KP + k] = k < K ? a.theta[a.off_b + k] : 0.0;
-            abc_s[2 * KP + k] = k < K ? a.theta[a.off_c + k] : 0.0;
-        }
-#pragma unroll
-        for (int s = 0; s < 2 * NT; ++s)
-#pragma unroll
-            for (int nt = 0; nt < NT2; ++nt) w2[s][nt] = radial_w(a, 4 * s + q, 8 * nt + g);
-#pragma unroll
-        for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NT2; ++nt) gw[mt][nt][0] = gw[mt][nt][1] = 0.0;
-#pragma unroll
-        for (int x = 0; x < 3; ++x)
-#pragma unroll
-            for (int nt = 0; nt < NT2; ++nt) gabc[x][nt][0] = gabc[x][nt][1] = 0.0;
-    } else {
+    if (!ENC) {
         const double b0 = a.theta[a.off_b0 + c], b1 = a.theta[a.off_b1 + c];
         R0c = cmake(b0, b0);
         R1c = cmake(b1, b1);
@@ -537,9 +430,6 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
             const int np = ENC ? 4 * N : 8 * N;
             const double* src = a.p + (int64_t)b * np;
             for (int t = tid; t < np; t += blockDim.x) p_s[t] = src[t];
-            if (ENC)
-                for (int t = tid; t < N; t += blockDim.x)
-                    msk_s[t] = a.node_mask ? a.node_mask[(int64_t)b * N + t] : (src[4 * t] != 0.0);
             const double* ss = a.s_in + (int64_t)b * N * C * 2;
             for (int t = tid; t < 2 * N * C; t += blockDim.x) (smem + L.S)[t] = ss[t];
             const double* vs = a.v_in + (int64_t)b * N * C * 8;
@@ -558,6 +448,13 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
             }
             if (!ENC)
                 for (int t = tid; t < 4 * 32; t += blockDim.x) gy_s[t] = czero();
+        }
+        // encoder: first radial weights of this jet, in flight while the mix adjoint runs
+        const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
+        double4 rnext = make_double4(0.0, 0.0, 0.0, 0.0), rnext2 = rnext;
+        if (ENC) {
+            rnext = rsv[0];
+            if (N > 1) rnext2 = rsv[(int64_t)C * 32];
         }
         __syncthreads();
         // ---- 1b. adjoint of cat -> mix, block by block, in registers ----
@@ -623,8 +520,8 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
                 cfmac(gS, Vi[mu], gc[1 + mu]);
             }
         }
-        __syncthreads();  // gout consumed (the gRs tile may overwrite it); gA_s visible
-        // ---- 2./3. pair loop over tiles of partners ----
+        __syncthreads();  // gA_s of every channel is complete (role 2 reads other lanes' entries)
+        // ---- 2. neighbour loop ----
         cplx gy[4] = {czero(), czero(), czero(), czero()};
         {
             double pa[4] = {0, 0, 0, 0};
@@ -644,99 +541,88 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
             for (int mu = 0; mu < 4; ++mu) Va[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
 #pragma unroll
             for (int e = 0; e < 10; ++e) gAa[e] = gA_s[(c * 10 + e) * 32 + lane];
-            const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
-            double4 rnext = make_double4(0.0, 0.0, 0.0, 0.0);
-            if (ENC) rnext = rsv[0];
-            for (int o0 = 0; o0 < N; o0 += TJ) {
-                const int to = min(TJ, N - o0);
-                for (int oo = 0; oo < to; ++oo) {
-                    const int o = o0 + oo;
-                    cplx R0 = R0c, R1 = R1c;
-                    if (ENC) {
-                        R0 = cmake(rnext.x, rnext.y);
-                        R1 = cmake(rnext.z, rnext.w);
-                        if (o + 1 < N) rnext = rsv[(int64_t)(o + 1) * C * 32];
+            double4* grv = reinterpret_cast<double4*>(a.g_r) + ((int64_t)b * N * C + c) * 32 + lane;
+            for (int o = 0; o < N; ++o) {
+                cplx R0 = R0c, R1 = R1c;
+                if (ENC) {
+                    R0 = cmake(rnext.x, rnext.y);
+                    R1 = cmake(rnext.z, rnext.w);
+                    rnext = rnext2;
+                    if (o + 2 < N) rnext2 = rsv[(int64_t)(o + 2) * C * 32];
+                }
+                const cplx So = S_s[o * C + c];
+                cplx Vo[4], Y[4];
+#pragma unroll
+                for (int mu = 0; mu < 4; ++mu) Vo[mu] = V_s[(o * C + c) * 4 + mu];
+                if (ENC) {
+                    double d[4];
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) d[mu] = pa[mu] - p_s[4 * o + mu];
+                    canon_from_real(d, Y);
+                } else {
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) Y[mu] = csub(ya[mu], reinterpret_cast<const cplx*>(p_s)[4 * o + mu]);
+                }
+                // role 1: own = receiving node i, other = neighbour j.  Y = Y_ij.
+                {
+                    cplx w = czero(), gR0 = czero();
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) {
+                        cfmac(w, Y[mu], gAa[5 + mu]);
+                        cfmac(gR0, Vo[mu], gAa[mu]);
                     }
-                    const cplx So = S_s[o * C + c];
-                    cplx Vo[4], Y[4];
-#pragma unroll
-                    for (int mu = 0; mu < 4; ++mu) Vo[mu] = V_s[(o * C + c) * 4 + mu];
+                    cfmac(gR0, So, gAa[4]);
+                    const cplx e = ceta(Vo, Y);
+                    cplx gR1 = cmulc(So, w);
+                    cfmac(gR1, e, gAa[9]);
                     if (ENC) {
-                        double d[4];
-#pragma unroll
-                        for (int mu = 0; mu < 4; ++mu) d[mu] = pa[mu] - p_s[4 * o + mu];
-                        canon_from_real(d, Y);
+                        grv[(int64_t)o * C * 32] = make_double4(gR0.x, gR0.y, gR1.x, gR1.y);
                     } else {
-#pragma unroll
-                        for (int mu = 0; mu < 4; ++mu) Y[mu] = csub(ya[mu], reinterpret_cast<const cplx*>(p_s)[4 * o + mu]);
-                    }
-                    // role 1: own = receiving node i, other = neighbour j.  Y = Y_ij.
-                    {
-                        cplx w = czero(), gR0 = czero();
-#pragma unroll
-                        for (int mu = 0; mu < 4; ++mu) {
-                            cfmac(w, Y[mu], gAa[5 + mu]);
-                            cfmac(gR0, Vo[mu], gAa[mu]);
-                        }
-                        cfmac(gR0, So, gAa[4]);
-                        const cplx e = ceta(Vo, Y);
-                        cplx gR1 = cmulc(So, w);
-                        cfmac(gR1, e, gAa[9]);
-                        if (ENC) {
-                            *reinterpret_cast<double4*>(gRs + ((size_t)((oo * C + c) * 32 + lane)) * 4) =
-                                make_double4(gR0.x, gR0.y, gR1.x, gR1.y);
-                        } else {
-                            gR0c = cadd(gR0c, live ? gR0 : czero());
-                            gR1c = cadd(gR1c, live ? gR1 : czero());
-                            // gy_i += conj(R1 S_j) gA1Y_i + conj(R1 ghat(V_j)) gA1E_i
-                            const cplx rs = cmul(R1, So);
-                            cplx gh[4];
-                            cghat(Vo, gh);
-#pragma unroll
-                            for (int mu = 0; mu < 4; ++mu) {
-                                cfmac(gy[mu], rs, gAa[5 + mu]);
-                                cfmac(gy[mu], cmul(R1, gh[mu]), gAa[9]);
-                            }
-                        }
-                    }
-                    // role 2: own = neighbour j, other = receiving node i.  Y_ij = -Y ; R_ij = R_ji (encoder).
-                    {
-                        cplx gAo[10];
-#pragma unroll
-                        for (int e = 0; e < 10; ++e) gAo[e] = gA_s[(c * 10 + e) * 32 + o];
-                        cplx Yn[4], gh[4];
-#pragma unroll
-                        for (int mu = 0; mu < 4; ++mu) Yn[mu] = cneg(Y[mu]);
-                        cghat(Yn, gh);
-                        cplx w = czero();
-#pragma unroll
-                        for (int mu = 0; mu < 4; ++mu) cfmac(w, Yn[mu], gAo[5 + mu]);
-                        const cplx r1g = cmulc(R1, gAo[9]);   // conj(R1) gA1E_i
+                        gR0c = cadd(gR0c, live ? gR0 : czero());
+                        gR1c = cadd(gR1c, live ? gR1 : czero());
+                        // gy_i += conj(R1 S_j) gA1Y_i + conj(R1 ghat(V_j)) gA1E_i
+                        const cplx rs = cmul(R1, So);
+                        cplx gh[4];
+                        cghat(Vo, gh);
 #pragma unroll
                         for (int mu = 0; mu < 4; ++mu) {
-                            cfmac(gV[mu], R0, gAo[mu]);
-                            cfmac(gV[mu], gh[mu], r1g);
-                        }
-                        cfmac(gS, R0, gAo[4]);
-                        cfmac(gS, R1, w);
-                        if (!ENC) {
-                            // gy_j -= conj(R1 S_j) gA1Y_i + conj(R1 ghat(V_j)) gA1E_i
-                            const cplx rs = cmul(R1, Sa);
-                            cplx gha[4];
-                            cghat(Va, gha);
-#pragma unroll
-                            for (int mu = 0; mu < 4; ++mu) {
-                                cplx t = cmulc(rs, gAo[5 + mu]);
-                                cfmac(t, cmul(R1, gha[mu]), gAo[9]);
-                                gy[mu] = csub(gy[mu], t);
-                            }
+                            cfmac(gy[mu], rs, gAa[5 + mu]);
+                            cfmac(gy[mu], cmul(R1, gh[mu]), gAa[9]);
                         }
                     }
                 }
-                if (ENC) {
-                    __syncthreads();
-                    radial_tile_bwd<NT, KS, NT2>(p_s, msk_s, N, C, K, 0, o0, to, abc_s, w2, gRs, gw, gabc);
-                    __syncthreads();
+                // role 2: own = neighbour j, other = receiving node i.  Y_ij = -Y ; R_ij = R_ji (encoder).
+                {
+                    cplx gAo[10];
+#pragma unroll
+                    for (int e = 0; e < 10; ++e) gAo[e] = gA_s[(c * 10 + e) * 32 + o];
+                    cplx Yn[4], gh[4];
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) Yn[mu] = cneg(Y[mu]);
+                    cghat(Yn, gh);
+                    cplx w = czero();
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) cfmac(w, Yn[mu], gAo[5 + mu]);
+                    const cplx r1g = cmulc(R1, gAo[9]);   // conj(R1) gA1E_i
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) {
+                        cfmac(gV[mu], R0, gAo[mu]);
+                        cfmac(gV[mu], gh[mu], r1g);
+                    }
+                    cfmac(gS, R0, gAo[4]);
+                    cfmac(gS, R1, w);
+                    if (!ENC) {
+                        // gy_j -= conj(R1 S_j) gA1Y_i + conj(R1 ghat(V_j)) gA1E_i
+                        const cplx rs = cmul(R1, Sa);
+                        cplx gha[4];
+                        cghat(Va, gha);
+#pragma unroll
+                        for (int mu = 0; mu < 4; ++mu) {
+                            cplx t = cmulc(rs, gAo[5 + mu]);
+                            cfmac(t, cmul(R1, gha[mu]), gAo[9]);
+                            gy[mu] = csub(gy[mu], t);
+                        }
+                    }
                 }
             }
         }
@@ -763,7 +649,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
         }
     }
 
-    // ---- 4. this CTA's row of parameter-gradient partials ----
+    // ---- 3. this CTA's row of parameter-gradient partials ----
     __syncthreads();
     double* row = a.part + (int64_t)blockIdx.x * a.part_stride;
     for (int t = tid; t < nm; t += blockDim.x) {
@@ -772,45 +658,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
         row[a.po_m11 + t] = gm_d[2 * (nm + t)];
         row[a.po_m11 + nm + t] = gm_d[2 * (nm + t) + 1];
     }
-    if (ENC) {
-        double* red = smem + L.un;  // [8*NT cols][8*NT2] + [3][8*NT2]
-        constexpr int NK = 8 * NT2;
-        const int ncol = 8 * NT;
-        for (int t = tid; t < ncol * NK + 3 * NK; t += blockDim.x) red[t] = 0.0;
-        __syncthreads();
-#pragma unroll
-        for (int mt = 0; mt < NT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NT2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) atomicAdd(&red[(8 * mt + g) * NK + 8 * nt + 2 * q + e], gw[mt][nt][e]);
-#pragma unroll
-        for (int x = 0; x < 3; ++x)
-#pragma unroll
-            for (int nt = 0; nt < NT2; ++nt)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    double v = gabc[x][nt][e];
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    if (g == 0) atomicAdd(&red[ncol * NK + x * NK + 8 * nt + 2 * q + e], v);
-                }
-        __syncthreads();
-        for (int t = tid; t < 4 * C * (K + 1); t += blockDim.x) {
-            const int col = t / (K + 1), k = t % (K + 1);
-            const double v = red[col * NK + k];
-            const int l = col >= 2 * C ? 1 : 0, o = col - l * 2 * C;
-            if (k < K)
-                row[(l ? a.po_w1 : a.po_w0) + (int64_t)o * K + k] = v;
-            else
-                row[(l ? a.po_b1 : a.po_b0) + o] = v;
-        }
-        for (int t = tid; t < 3 * K; t += blockDim.x) {
-            const int x = t / K, k = t % K;
-            row[(x == 0 ? a.po_a : x == 1 ? a.po_b : a.po_c) + k] = red[ncol * NK + x * NK + k];
-        }
-    } else {
+    if (!ENC) {
         // decoder: only the biases learn; R^l[c] = bias (1+i)  =>  g_bias = Re(gR) + Im(gR)
         double v0 = warp_sum(gR0c.x + gR0c.y), v1 = warp_sum(gR1c.x + gR1c.y);
         if (lane == 0) {
@@ -825,12 +673,12 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
 // ------------------------------------------------------------------------------------------------------------
 static int pick_ks(int K) { return K <= 12 ? 3 : (K <= 20 ? 5 : (K <= 32 ? 8 : -1)); }
 
-template <bool ENC, int NT, int KS>
+template <bool ENC, int NT, int KS, bool PRE>
 static int launch_level_fwd(const LevelArgs& a, cudaStream_t st) {
-    const LevelSmem L = level_smem(ENC, a.N, a.C, a.Cout, KS);
+    const LevelSmem L = level_smem(ENC, ENC && !PRE, a.N, a.C, a.Cout, KS);
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
-    auto kern = level_fwd_kernel<ENC, NT, KS>;
+    auto kern = level_fwd_kernel<ENC, NT, KS, PRE>;
     if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
     const int nib = (a.N + 31) / 32;
     kern<<<a.B * nib, 32 * a.C, bytes, st>>>(a);
@@ -838,18 +686,21 @@ static int launch_level_fwd(const LevelArgs& a, cudaStream_t st) {
     return check_launch("level_fwd");
 }
 
-template <bool ENC, int NT, int KS>
+template <bool ENC>
 static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
     if (a.N > 32) return LGAE_E_UNSUPPORTED;
-    const LevelBwdSmem L = level_bwd_smem(ENC, a.N, a.C, a.Cout, NT, KS);
+    const LevelBwdSmem L = level_bwd_smem(ENC, a.N, a.C, a.Cout);
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
-    constexpr int MAXT = NT <= 2 ? 128 : 256;
-    constexpr int MINB = NT <= 2 ? 3 : 1;
-    if (32 * a.C > MAXT) return LGAE_E_UNSUPPORTED;
-    auto kern = level_bwd_kernel<ENC, NT, KS, MAXT, MINB>;
-    if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
-    kern<<<grid, 32 * a.C, bytes, st>>>(a);
+    if (a.C <= 4) {
+        auto kern = level_bwd_kernel<ENC, 128, 3>;
+        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
+        kern<<<grid, 32 * a.C, bytes, st>>>(a);
+    } else {
+        auto kern = level_bwd_kernel<ENC, 256, 1>;
+        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
+        kern<<<grid, 32 * a.C, bytes, st>>>(a);
+    }
     count_launch();
     return check_launch("level_bwd");
 }
@@ -860,18 +711,14 @@ int level_bwd_grid(int batch) {
     return batch < cap ? (batch > 0 ? batch : 1) : cap;
 }
 
-template <bool ENC>
-static int dispatch_level(const LevelArgs& a, bool bwd, int grid, cudaStream_t st) {
+static int dispatch_level_fwd(const LevelArgs& a, bool enc, cudaStream_t st) {
     if (a.C < 1 || a.C > LGAE_MAX_CHANNELS || a.Cout < 1 || a.Cout > LGAE_MAX_CHANNELS) return LGAE_E_UNSUPPORTED;
-    if (!ENC) {
-        if (!bwd) return launch_level_fwd<false, 1, 3>(a, st);
-        return a.C <= 4 ? launch_level_bwd<false, 1, 3>(a, grid, st) : launch_level_bwd<false, 3, 3>(a, grid, st);
-    }
+    if (!enc) return launch_level_fwd<false, 1, 3, false>(a, st);
+    if (a.r_save) return launch_level_fwd<true, 1, 3, true>(a, st);   // radial weights precomputed (N <= 32)
     const int nt = (4 * a.C + 7) / 8, ks = pick_ks(a.K);
     if (ks < 0) return LGAE_E_UNSUPPORTED;
-#define LGAE_CASE(NTV, KSV)                                                   \
-    if (nt == NTV && ks == KSV)                                               \
-        return bwd ? launch_level_bwd<true, NTV, KSV>(a, grid, st) : launch_level_fwd<true, NTV, KSV>(a, st);
+#define LGAE_CASE(NTV, KSV) \
+    if (nt == NTV && ks == KSV) return launch_level_fwd<true, NTV, KSV, false>(a, st);
     LGAE_CASE(1, 3) LGAE_CASE(2, 3) LGAE_CASE(3, 3) LGAE_CASE(4, 3)
     LGAE_CASE(1, 5) LGAE_CASE(2, 5) LGAE_CASE(3, 5) LGAE_CASE(4, 5)
     LGAE_CASE(1, 8) LGAE_CASE(2, 8) LGAE_CASE(3, 8) LGAE_CASE(4, 8)
@@ -892,6 +739,8 @@ static void fill_level_args(LevelArgs& a, const LgaeModelDesc* d, int level, con
     a.B = batch; a.N = d->n_particles; a.C = d->channels[level]; a.Cout = d->channels[level + 1]; a.K = d->n_basis;
 }
 
+// Forward of one level.  Encoder with r_save != NULL (N <= 32): r_save must already hold the radial weights
+// (run_radial_fwd); otherwise the radial functions are evaluated inside the kernel, tile by tile.
 int run_level_fwd(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
                   const double* s_in, const double* v_in, double* sums, double* r_save, double* s_pre, double* v_out, cudaStream_t st) {
     if (!d || level < 0 || level >= d->n_levels) return LGAE_E_BADARG;
@@ -899,32 +748,26 @@ int run_level_fwd(const LgaeModelDesc* d, int level, const double* theta, const 
     LevelArgs a;
     fill_level_args(a, d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save);
     a.s_pre = s_pre; a.v_out = v_out;
-    return d->is_decoder ? dispatch_level<false>(a, false, 0, st) : dispatch_level<true>(a, false, 0, st);
+    return dispatch_level_fwd(a, !d->is_decoder, st);
 }
 
-// Adjoint of one level.  Reserves a block of `plan` for the per-CTA partial rows and declares its segments.
+// Adjoint of one level (without the adjoint of the radial functions: the encoder streams dL/dR to g_r for
+// run_radial_bwd).  Reserves a block of `plan` for the per-CTA partial rows and declares its segments.
 int run_level_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p_or_y, const uint8_t* node_mask, int batch,
-                  const double* s_in, const double* v_in, const double* sums, const double* r_save, const double* g_s_pre,
+                  const double* s_in, const double* v_in, const double* sums, const double* r_save, double* g_r, const double* g_s_pre,
                   const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y, PartPlan* plan, cudaStream_t st) {
     if (!d || level < 0 || level >= d->n_levels || !plan) return LGAE_E_BADARG;
     if (batch <= 0) return LGAE_OK;
     LevelArgs a;
     fill_level_args(a, d, level, theta, p_or_y, node_mask, batch, s_in, v_in, const_cast<double*>(sums), const_cast<double*>(r_save));
-    if (!d->is_decoder && !a.r_save) return LGAE_E_UNSUPPORTED;   // the encoder adjoint needs the saved radial weights (N <= 32)
+    const bool enc = !d->is_decoder;
+    if (enc && (!a.r_save || !g_r)) return LGAE_E_UNSUPPORTED;   // the encoder adjoint needs the saved radial weights (N <= 32)
+    a.g_r = g_r;
     a.g_s_pre = g_s_pre; a.g_v_out = g_v_out; a.g_s_in = g_s_in; a.g_v_in = g_v_in; a.g_y = g_y;
     const int grid = level_bwd_grid(batch);
-    const int C = a.C, K = a.K, nm2 = 2 * a.Cout * 5 * C;
+    const int C = a.C, nm2 = 2 * a.Cout * 5 * C;
     int64_t w = 0;
-    const bool enc = !d->is_decoder;
-    if (enc) {
-        a.po_w0 = w; w += (int64_t)2 * C * K;
-        a.po_b0 = w; w += 2 * C;
-        a.po_w1 = w; w += (int64_t)2 * C * K;
-        a.po_b1 = w; w += 2 * C;
-        a.po_a = w; w += K;
-        a.po_b = w; w += K;
-        a.po_c = w; w += K;
-    } else {
+    if (!enc) {
         a.po_b0 = w; w += C;
         a.po_b1 = w; w += C;
     }
@@ -935,23 +778,18 @@ int run_level_bwd(const LgaeModelDesc* d, int level, const double* theta, const 
     a.part_stride = w;
     int rc = LGAE_OK;
     auto seg = [&](int64_t theta_off, int64_t col, int64_t len) { if (rc == LGAE_OK) rc = plan->seg(theta_off, off, w, col, len, grid); };
-    if (enc) {
-        seg(a.off_w0, a.po_w0, (int64_t)2 * C * K); seg(a.off_b0, a.po_b0, 2 * C);
-        seg(a.off_w1, a.po_w1, (int64_t)2 * C * K); seg(a.off_b1, a.po_b1, 2 * C);
-        seg(a.off_a, a.po_a, K); seg(a.off_b, a.po_b, K); seg(a.off_c, a.po_c, K);
-    } else {
-        seg(a.off_b0, a.po_b0, C); seg(a.off_b1, a.po_b1, C);
-    }
+    if (!enc) { seg(a.off_b0, a.po_b0, C); seg(a.off_b1, a.po_b1, C); }
     seg(a.off_m00, a.po_m00, nm2); seg(a.off_m11, a.po_m11, nm2);
     if (rc != LGAE_OK) return rc;
-    return enc ? dispatch_level<true>(a, true, grid, st) : dispatch_level<false>(a, true, grid, st);
+    if (a.C < 1 || a.C > LGAE_MAX_CHANNELS || a.Cout < 1 || a.Cout > LGAE_MAX_CHANNELS) return LGAE_E_UNSUPPORTED;
+    return enc ? launch_level_bwd<true>(a, grid, st) : launch_level_bwd<false>(a, grid, st);
 }
 
 // Width (doubles) of one row of partials of the level adjoint.
 int64_t level_part_width(const LgaeModelDesc* d, int level) {
-    const int C = d->channels[level], Cout = d->channels[level + 1], K = d->n_basis;
+    const int C = d->channels[level], Cout = d->channels[level + 1];
     const int64_t mix = (int64_t)4 * Cout * 5 * C;
-    return d->is_decoder ? 2 * C + mix : (int64_t)4 * C * (K + 1) + 3 * K + mix;
+    return d->is_decoder ? 2 * C + mix : mix;
 }
 
 }  // namespace lgae

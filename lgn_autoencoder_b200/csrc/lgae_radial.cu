@@ -1,0 +1,375 @@
+// Radial functions of the encoder levels (N <= 32 path), forward and adjoint, as stand-alone kernels on the fp64
+// tensor-core MMA (DMMA m8n8k4).  Replaces RadPolyTrig.forward / RadialFilters (lgn/nn/position_levels.py:118-209,
+// 292-310) applied to the pair norms of zonal_functions_rel (lgn/cg_lib/zonal_functions.py:221-248):
+//   n_ij   = s / sqrt|s|,  s = (p_i - p_j)^2 + 1e-16                          (Minkowski square, symmetric in i <-> j)
+//   phi_k  = m_ij * ( b_k / (1 + (c_k n_ij)^2 + 1e-16) + a_k )                m_ij = mask_i mask_j [n_ij != 0]
+//   R_ij   = W phi + bias   (4C outputs: level-0/1 radial weights, re/im interleaved per channel)
+// Because n_ij == n_ji bit for bit, only the N(N+1)/2 unordered pairs are evaluated; the forward writes both
+// (i,j) and (j,i) entries of the (B, N_j, C, 32_i, 4) tensor the level kernels stream through, and the adjoint first
+// adds the two incoming gradients of a pair.
+//
+// Work decomposition: a warp owns groups of 8 pairs (the M / K dimension of the MMA tiles); warps stride over all
+// groups of all jets, so the grid is sized by the machine (CTAs per SM x 148), not by the batch.
+#include <cstring>
+
+#include "lgae_common.cuh"
+
+namespace lgae {
+
+struct RadialArgs {
+    const double* theta;
+    int64_t off_a, off_b, off_c, off_w0, off_b0, off_w1, off_b1;
+    const double* p4;          // (B,N,4) real Cartesian
+    const uint8_t* node_mask;  // (B,N) or nullptr (=> p4[...,0] != 0)
+    double* r;                 // forward out: (B,N_j,C,32_i,4) = (R0.re, R0.im, R1.re, R1.im)
+    const double* g_r;         // adjoint in: same layout, dL/dR of the ORDERED pairs
+    double* part;              // adjoint out: (gridDim.x, part_stride) rows of parameter-gradient partials
+    int64_t part_stride;
+    int64_t po_w0, po_b0, po_w1, po_b1, po_a, po_b, po_c;
+    int B, N, C, K;
+};
+
+constexpr int RAD_MAXN = 32;
+constexpr int RAD_MAXP = RAD_MAXN * (RAD_MAXN + 1) / 2;
+
+LGAE_DEV double rad_pair_norm(const double* pi, const double* pj) {
+    const double d0 = pi[0] - pj[0], d1 = pi[1] - pj[1], d2 = pi[2] - pj[2], d3 = pi[3] - pj[3];
+    const double s = __dadd_rn(minkowski_sq(d0, d1, d2, d3), 1e-16);
+    return s != 0.0 ? __ddiv_rn(s, __dsqrt_rn(fabs(s))) : s;
+}
+LGAE_DEV double rad_w(const RadialArgs& a, int col, int k) {
+    if (k >= a.K || col >= 4 * a.C) return 0.0;
+    return col < 2 * a.C ? a.theta[a.off_w0 + (int64_t)col * a.K + k] : a.theta[a.off_w1 + (int64_t)(col - 2 * a.C) * a.K + k];
+}
+LGAE_DEV double rad_bias(const RadialArgs& a, int col) {
+    if (col >= 4 * a.C) return 0.0;
+    return col < 2 * a.C ? a.theta[a.off_b0 + col] : a.theta[a.off_b1 + col - 2 * a.C];
+}
+// unordered pairs (i <= j) of one jet in the order p = j (j + 1) / 2 + i
+LGAE_DEV void build_pair_table(int N, unsigned char* ti, unsigned char* tj) {
+    for (int j = threadIdx.x; j < N; j += blockDim.x)
+        for (int i = 0; i <= j; ++i) {
+            ti[j * (j + 1) / 2 + i] = (unsigned char)i;
+            tj[j * (j + 1) / 2 + i] = (unsigned char)j;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+template <int NT, int KS>
+__global__ void __launch_bounds__(256, 2) radial_fwd_kernel(const RadialArgs a) {
+    constexpr int KP = 4 * KS;
+    constexpr int U = 2;   // groups in flight per warp (independent MMA chains)
+    __shared__ unsigned char ti[RAD_MAXP], tj[RAD_MAXP];
+    __shared__ double abc_s[3 * KP];
+    const int N = a.N, C = a.C, K = a.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    build_pair_table(N, ti, tj);
+    for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+        abc_s[k] = k < K ? a.theta[a.off_a + k] : 0.0;
+        abc_s[KP + k] = k < K ? a.theta[a.off_b + k] : 0.0;
+        abc_s[2 * KP + k] = k < K ? a.theta[a.off_c + k] : 0.0;
+    }
+    double wf[KS][NT], bf[NT][2];
+#pragma unroll
+    for (int s = 0; s < KS; ++s)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) wf[s][nt] = rad_w(a, 8 * nt + g, 4 * s + q);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        bf[nt][0] = rad_bias(a, 8 * nt + 2 * q);
+        bf[nt][1] = rad_bias(a, 8 * nt + 2 * q + 1);
+    }
+    __syncthreads();
+    const int NP = N * (N + 1) / 2, NG = (NP + 7) / 8;
+    const int64_t total = (int64_t)a.B * NG;
+    const int64_t stride = (int64_t)gridDim.x * nwarps * U;
+    for (int64_t grp0 = ((int64_t)blockIdx.x * nwarps + warp) * U; grp0 < total; grp0 += stride) {
+        double acc[U][NT][2], n[U];
+        bool m[U], valid[U];
+        int bi[U], ii[U], jj[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t grp = grp0 + u;
+            const int b = (int)(grp / NG), pid = (int)(grp % NG) * 8 + g;
+            valid[u] = grp < total && pid < NP;
+            bi[u] = b;
+            ii[u] = valid[u] ? ti[pid] : 0;
+            jj[u] = valid[u] ? tj[pid] : 0;
+            n[u] = 0.0;
+            m[u] = false;
+            if (valid[u]) {
+                const double* pb = a.p4 + (int64_t)b * N * 4;
+                const double4 pi = *reinterpret_cast<const double4*>(pb + 4 * ii[u]);
+                const double4 pj = *reinterpret_cast<const double4*>(pb + 4 * jj[u]);
+                const double vi[4] = {pi.x, pi.y, pi.z, pi.w}, vj[4] = {pj.x, pj.y, pj.z, pj.w};
+                n[u] = rad_pair_norm(vi, vj);
+                const bool mi = a.node_mask ? a.node_mask[(int64_t)b * N + ii[u]] != 0 : pi.x != 0.0;
+                const bool mj = a.node_mask ? a.node_mask[(int64_t)b * N + jj[u]] != 0 : pj.x != 0.0;
+                m[u] = mi && mj && n[u] != 0.0;
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { acc[u][nt][0] = bf[nt][0]; acc[u][nt][1] = bf[nt][1]; }
+        }
+#pragma unroll
+        for (int s = 0; s < KS; ++s) {
+            const int k = 4 * s + q;
+            const double ak = abc_s[k], bk = abc_s[KP + k], ck = abc_s[2 * KP + k];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double cn = ck * n[u];
+                const double phi = m[u] ? fma(bk, 1.0 / (1.0 + cn * cn + 1e-16), ak) : 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma(acc[u][nt][0], acc[u][nt][1], phi, wf[s][nt]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u]) continue;
+            double* rb = a.r + (int64_t)bi[u] * N * C * 128;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = 8 * nt + 2 * q;
+                if (col < 4 * C) {
+                    const int l = col >= 2 * C ? 1 : 0, cc = (col - l * 2 * C) >> 1;
+                    const double2 v = make_double2(acc[u][nt][0], acc[u][nt][1]);
+                    *reinterpret_cast<double2*>(rb + ((int64_t)(jj[u] * C + cc) * 32 + ii[u]) * 4 + 2 * l) = v;
+                    if (ii[u] != jj[u]) *reinterpret_cast<double2*>(rb + ((int64_t)(ii[u] * C + cc) * 32 + jj[u]) * 4 + 2 * l) = v;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// adjoint
+// ------------------------------------------------------------------------------------------------------------
+// With G[col] the symmetrised incoming gradient of a pair (4C values), rd_k = 1 / (1 + (c_k n)^2 + 1e-16):
+//   G1[col][k]   = sum_pairs G[col] * m rd_k          k < K ;   G1[col][K] = sum_pairs G[col] ;  G1[col][K+1] = sum_pairs G[col] m
+//   G2[col][k]   = sum_pairs G[col] * m n^2 rd_k^2
+// are two MMA-shaped contractions over the pairs; the parameter gradients are linear in them:
+//   dW[col][k] = b_k G1[col][k] + a_k G1[col][K+1]      dbias[col] = G1[col][K]
+//   da_k = sum_col W[col][k] G1[col][K+1]     db_k = sum_col W[col][k] G1[col][k]     dc_k = -2 b_k c_k sum_col W[col][k] G2[col][k]
+// so every CTA applies that map to its own partial G1 / G2 and writes one row of partials.
+template <int NT, int KS>
+__global__ void __launch_bounds__(256, 2) radial_bwd_kernel(const RadialArgs a) {
+    constexpr int KP = 4 * KS;
+    constexpr int NT2 = KS / 2 + 1;
+    constexpr int NK = 8 * NT2, NCOL = 8 * NT;
+    __shared__ unsigned char ti[RAD_MAXP], tj[RAD_MAXP];
+    __shared__ double abc_s[3 * KP];
+    __shared__ double red[2 * NCOL * NK];
+    const int N = a.N, C = a.C, K = a.K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    build_pair_table(N, ti, tj);
+    for (int k = threadIdx.x; k < KP; k += blockDim.x) {
+        abc_s[k] = k < K ? a.theta[a.off_a + k] : 0.0;
+        abc_s[KP + k] = k < K ? a.theta[a.off_b + k] : 0.0;
+        abc_s[2 * KP + k] = k < K ? a.theta[a.off_c + k] : 0.0;
+    }
+    for (int t = threadIdx.x; t < 2 * NCOL * NK; t += blockDim.x) red[t] = 0.0;
+    __syncthreads();
+    double G1[NT][NT2][2], G2[NT][NT2][2];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT2; ++nt) G1[mt][nt][0] = G1[mt][nt][1] = G2[mt][nt][0] = G2[mt][nt][1] = 0.0;
+    // column (8 mt + g) of this lane's A fragments -> (channel, component) inside a (32_i, 4) record
+    int col_cc[NT], col_x[NT];
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt) {
+        const int col = 8 * mt + g;
+        const int l = col >= 2 * C ? 1 : 0, rem = col - l * 2 * C;
+        col_cc[mt] = col < 4 * C ? (rem >> 1) : -1;
+        col_x[mt] = 2 * l + (rem & 1);
+    }
+    // c_k of this lane's B-fragment columns k = 8 nt + g
+    double ck[NT2];
+#pragma unroll
+    for (int nt = 0; nt < NT2; ++nt) ck[nt] = (8 * nt + g) < K ? abc_s[2 * KP + 8 * nt + g] : 0.0;
+
+    const int NP = N * (N + 1) / 2, NG = (NP + 7) / 8;
+    const int64_t total = (int64_t)a.B * NG;
+    for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < total; grp += (int64_t)gridDim.x * nwarps) {
+        const int b = (int)(grp / NG), p0 = (int)(grp % NG) * 8;
+        const double* pb = a.p4 + (int64_t)b * N * 4;
+        const double* gb = a.g_r + (int64_t)b * N * C * 128;
+        // norm and mask of pair g of the group (every q-lane of a g computes the same pair)
+        double n = 0.0;
+        int m = 0;
+        {
+            const int pid = p0 + g;
+            if (pid < NP) {
+                const int i = ti[pid], j = tj[pid];
+                const double4 pi = *reinterpret_cast<const double4*>(pb + 4 * i);
+                const double4 pj = *reinterpret_cast<const double4*>(pb + 4 * j);
+                const double vi[4] = {pi.x, pi.y, pi.z, pi.w}, vj[4] = {pj.x, pj.y, pj.z, pj.w};
+                n = rad_pair_norm(vi, vj);
+                const bool mi = a.node_mask ? a.node_mask[(int64_t)b * N + i] != 0 : pi.x != 0.0;
+                const bool mj = a.node_mask ? a.node_mask[(int64_t)b * N + j] != 0 : pj.x != 0.0;
+                m = (mi && mj && n != 0.0) ? 1 : 0;
+            }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int pp = q + 4 * ks, pid = p0 + pp;
+            const double n2 = __shfl_sync(0xffffffffu, n, pp * 4);
+            const int m2 = __shfl_sync(0xffffffffu, m, pp * 4);
+            const bool valid = pid < NP;
+            const int i = valid ? ti[pid] : 0, j = valid ? tj[pid] : 0;
+            double a3[NT];
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) {
+                double v = 0.0;
+                if (valid && col_cc[mt] >= 0) {
+                    v = gb[((int64_t)(j * C + col_cc[mt]) * 32 + i) * 4 + col_x[mt]];
+                    if (i != j) v += gb[((int64_t)(i * C + col_cc[mt]) * 32 + j) * 4 + col_x[mt]];
+                }
+                a3[mt] = v;
+            }
+            const double nn = n2 * n2;
+#pragma unroll
+            for (int nt = 0; nt < NT2; ++nt) {
+                const int k = 8 * nt + g;
+                double b1 = 0.0, b2 = 0.0;
+                if (k < K) {
+                    if (m2) {
+                        const double cn = ck[nt] * n2;
+                        const double rd = 1.0 / (1.0 + cn * cn + 1e-16);
+                        b1 = rd;
+                        b2 = nn * rd * rd;
+                    }
+                } else if (k == K) {
+                    b1 = 1.0;
+                } else if (k == K + 1) {
+                    b1 = m2 ? 1.0 : 0.0;
+                }
+#pragma unroll
+                for (int mt = 0; mt < NT; ++mt) {
+                    dmma(G1[mt][nt][0], G1[mt][nt][1], a3[mt], b1);
+                    dmma(G2[mt][nt][0], G2[mt][nt][1], a3[mt], b2);
+                }
+            }
+        }
+    }
+    // ---- cross-warp reduction, then this CTA's row of partials ----
+#pragma unroll
+    for (int mt = 0; mt < NT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                atomicAdd(&red[(8 * mt + g) * NK + 8 * nt + 2 * q + e], G1[mt][nt][e]);
+                atomicAdd(&red[NCOL * NK + (8 * mt + g) * NK + 8 * nt + 2 * q + e], G2[mt][nt][e]);
+            }
+    __syncthreads();
+    double* row = a.part + (int64_t)blockIdx.x * a.part_stride;
+    const double* g1 = red;
+    const double* g2 = red + NCOL * NK;
+    for (int t = threadIdx.x; t < 4 * C * (K + 1); t += blockDim.x) {
+        const int col = t / (K + 1), k = t % (K + 1);
+        const int l = col >= 2 * C ? 1 : 0, o = col - l * 2 * C;
+        if (k < K)
+            row[(l ? a.po_w1 : a.po_w0) + (int64_t)o * K + k] = abc_s[KP + k] * g1[col * NK + k] + abc_s[k] * g1[col * NK + K + 1];
+        else
+            row[(l ? a.po_b1 : a.po_b0) + o] = g1[col * NK + K];
+    }
+    for (int t = threadIdx.x; t < 3 * K; t += blockDim.x) {
+        const int x = t / K, k = t % K;
+        double s = 0.0;
+        for (int col = 0; col < 4 * C; ++col) {
+            const double w = rad_w(a, col, k);
+            s += w * (x == 0 ? g1[col * NK + K + 1] : x == 1 ? g1[col * NK + k] : g2[col * NK + k]);
+        }
+        if (x == 2) s *= -2.0 * abc_s[KP + k] * abc_s[2 * KP + k];
+        row[(x == 0 ? a.po_a : x == 1 ? a.po_b : a.po_c) + k] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static int pick_ks(int K) { return K <= 12 ? 3 : (K <= 20 ? 5 : (K <= 32 ? 8 : -1)); }
+
+int radial_grid() { return 2 * sm_count(); }
+
+static void fill(RadialArgs& a, const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch) {
+    memset(&a, 0, sizeof(a));
+    a.theta = theta;
+    a.off_a = d->off_rad_a[level]; a.off_b = d->off_rad_b[level]; a.off_c = d->off_rad_c[level];
+    a.off_w0 = d->off_rad_w0[level]; a.off_b0 = d->off_rad_b0[level];
+    a.off_w1 = d->off_rad_w1[level]; a.off_b1 = d->off_rad_b1[level];
+    a.p4 = p4; a.node_mask = node_mask;
+    a.B = batch; a.N = d->n_particles; a.C = d->channels[level]; a.K = d->n_basis;
+}
+
+template <int NT, int KS>
+static int launch_radial(const RadialArgs& a, bool bwd, cudaStream_t st) {
+    const int grid = radial_grid();
+    if (bwd)
+        radial_bwd_kernel<NT, KS><<<grid, 256, 0, st>>>(a);
+    else
+        radial_fwd_kernel<NT, KS><<<grid, 256, 0, st>>>(a);
+    count_launch();
+    return check_launch(bwd ? "radial_bwd" : "radial_fwd");
+}
+
+static int dispatch_radial(const RadialArgs& a, bool bwd, cudaStream_t st) {
+    if (a.N > RAD_MAXN || a.C < 1 || a.C > LGAE_MAX_CHANNELS) return LGAE_E_UNSUPPORTED;
+    const int nt = (4 * a.C + 7) / 8, ks = pick_ks(a.K);
+    if (ks < 0) return LGAE_E_UNSUPPORTED;
+#define LGAE_CASE(NTV, KSV) \
+    if (nt == NTV && ks == KSV) return launch_radial<NTV, KSV>(a, bwd, st);
+    LGAE_CASE(1, 3) LGAE_CASE(2, 3) LGAE_CASE(3, 3) LGAE_CASE(4, 3)
+    LGAE_CASE(1, 5) LGAE_CASE(2, 5) LGAE_CASE(3, 5) LGAE_CASE(4, 5)
+    LGAE_CASE(1, 8) LGAE_CASE(2, 8) LGAE_CASE(3, 8) LGAE_CASE(4, 8)
+#undef LGAE_CASE
+    return LGAE_E_UNSUPPORTED;
+}
+
+// R (B,N,C,32,4) of encoder level `level`.
+int run_radial_fwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
+                   double* r, cudaStream_t st) {
+    if (!d || d->is_decoder || level < 0 || level >= d->n_levels || !r) return LGAE_E_BADARG;
+    if (batch <= 0) return LGAE_OK;
+    RadialArgs a;
+    fill(a, d, level, theta, p4, node_mask, batch);
+    a.r = r;
+    return dispatch_radial(a, false, st);
+}
+
+int64_t radial_part_width(const LgaeModelDesc* d, int level) { return (int64_t)4 * d->channels[level] * (d->n_basis + 1) + 3 * d->n_basis; }
+
+// Adjoint: g_r (B,N,C,32,4) -> partial rows for a, b, c, linear.{0,1}.{weight,bias} of the level.
+int run_radial_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
+                   const double* g_r, PartPlan* plan, cudaStream_t st) {
+    if (!d || d->is_decoder || level < 0 || level >= d->n_levels || !g_r || !plan) return LGAE_E_BADARG;
+    if (batch <= 0) return LGAE_OK;
+    RadialArgs a;
+    fill(a, d, level, theta, p4, node_mask, batch);
+    a.g_r = g_r;
+    const int C = a.C, K = a.K, grid = radial_grid();
+    int64_t w = 0;
+    a.po_w0 = w; w += (int64_t)2 * C * K;
+    a.po_b0 = w; w += 2 * C;
+    a.po_w1 = w; w += (int64_t)2 * C * K;
+    a.po_b1 = w; w += 2 * C;
+    a.po_a = w; w += K;
+    a.po_b = w; w += K;
+    a.po_c = w; w += K;
+    const int64_t off = plan->block(grid, w);
+    a.part = plan->base + off;
+    a.part_stride = w;
+    int rc = LGAE_OK;
+    auto seg = [&](int64_t theta_off, int64_t col, int64_t len) { if (rc == LGAE_OK) rc = plan->seg(theta_off, off, w, col, len, grid); };
+    seg(a.off_w0, a.po_w0, (int64_t)2 * C * K); seg(a.off_b0, a.po_b0, 2 * C);
+    seg(a.off_w1, a.po_w1, (int64_t)2 * C * K); seg(a.off_b1, a.po_b1, 2 * C);
+    seg(a.off_a, a.po_a, K); seg(a.off_b, a.po_b, K); seg(a.off_c, a.po_c, K);
+    if (rc != LGAE_OK) return rc;
+    return dispatch_radial(a, true, st);
+}
+
+}  // namespace lgae
