@@ -149,12 +149,14 @@ int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* the
                         const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y_accumulate, double* gtheta,
                         double* partials, void* stream);
 /* CGMLP on rows = batch*N interleaved scalars x (rows, 2C').  acts: (n_hidden, rows, width_padded) saved
- * activations.  y (rows, 2C'). */
+ * activations.  y (rows, 2C').  wpack: lgae_mlp_pack_doubles(d, level) doubles (32-byte aligned) that the forward
+ * fills with the level's weights in MMA-fragment order and the backward reads. */
+int64_t lgae_mlp_pack_doubles(const LgaeModelDesc* d, int32_t level);
 int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows,
-                     double* acts, double* y, void* stream);
+                     double* wpack, double* acts, double* y, void* stream);
 int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows,
-                      const double* acts, const double* g_y, double* g_x, double* gtheta, double* partials,
-                      void* stream);
+                      const double* wpack, const double* acts, const double* g_y, double* g_x, double* gtheta,
+                      double* partials, void* stream);
 
 #ifdef __cplusplus
 }

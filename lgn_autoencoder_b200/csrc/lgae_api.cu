@@ -24,8 +24,10 @@ int radial_grid();
 int64_t radial_part_width(const LgaeModelDesc* d, int level);
 int level_bwd_grid(int batch);
 int64_t level_part_width(const LgaeModelDesc* d, int level);
-int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* x, int64_t rows, double* acts, double* y,
-            const double* g_y, double* g_x, PartPlan* plan, bool bwd, cudaStream_t st);
+int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* wpack, const double* x, int64_t rows, double* acts,
+            double* y, const double* g_y, double* g_x, PartPlan* plan, bool bwd, cudaStream_t st);
+int64_t mlp_pack_doubles(const LgaeModelDesc* d, int level);
+int run_mlp_pack(const LgaeModelDesc* d, const double* theta, double* out, const int64_t* out_off, cudaStream_t st);
 int mlp_padded_width(const LgaeModelDesc* d, int level);
 int64_t mlp_part_width(const LgaeModelDesc* d, int level);
 int mlp_bwd_grid();
@@ -83,7 +85,7 @@ int sm_count() {
 // ---- workspace layout -----------------------------------------------------------------------------------------------
 struct Layout {
     int64_t S[LGAE_MAX_LEVELS + 1], V[LGAE_MAX_LEVELS + 1];
-    int64_t sums[LGAE_MAX_LEVELS], spre[LGAE_MAX_LEVELS], acts[LGAE_MAX_LEVELS], rsave[LGAE_MAX_LEVELS];
+    int64_t sums[LGAE_MAX_LEVELS], spre[LGAE_MAX_LEVELS], acts[LGAE_MAX_LEVELS], rsave[LGAE_MAX_LEVELS], wpack[LGAE_MAX_LEVELS];
     int64_t y, mass, gS[2], gV[2], gSpre, gy, gr, total;
 };
 static int max_channels(const LgaeModelDesc* d) {
@@ -95,7 +97,7 @@ static Layout layout(const LgaeModelDesc* d, int64_t B) {
     Layout L;
     const int64_t nodes = B * d->n_particles;
     int64_t o = 0;
-    auto take = [&](int64_t n) { const int64_t r = o; o += (n + 1) & ~int64_t(1); return r; };
+    auto take = [&](int64_t n) { const int64_t r = o; o += (n + 3) & ~int64_t(3); return r; };   // 32-byte granules
     L.y = take(nodes * 8);
     L.mass = take(nodes);
     for (int l = 0; l <= d->n_levels; ++l) {
@@ -106,6 +108,7 @@ static Layout layout(const LgaeModelDesc* d, int64_t B) {
         L.sums[l] = take(nodes * d->channels[l] * 20);
         L.spre[l] = d->has_mlp ? take(nodes * d->channels[l + 1] * 2) : L.S[l + 1];
         L.acts[l] = d->has_mlp ? take((int64_t)d->mlp_hidden * nodes * mlp_padded_width(d, l)) : 0;
+        L.wpack[l] = take(mlp_pack_doubles(d, l));
         // encoder, N <= 32: the radial weights R_ij[c] of every level, kept for the adjoint
         L.rsave[l] = (!d->is_decoder && d->n_particles <= 32) ? take(nodes * d->channels[l] * 128) : -1;
     }
@@ -199,12 +202,13 @@ int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     cudaStream_t st = (cudaStream_t)stream;
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
+    LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
     LGAE_TRY(run_enc_input(d, theta, p4, batch, ws + L.mass, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
         if (L.rsave[l] >= 0) LGAE_TRY(run_radial_fwd(d, l, theta, p4, node_mask, batch, ws + L.rsave[l], st));
         LGAE_TRY(run_level_fwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l],
                                L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, ws + L.spre[l], ws + L.V[l + 1], st));
-        if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
+        if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
     return run_enc_latent(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], lat00, lat11, sel, st);
 }
@@ -230,7 +234,7 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
             const double* g_spre = nullptr;
             if (!gs_zero) {
                 if (d->has_mlp) {
-                    LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, &plan, true, st));
+                    LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, &plan, true, st));
                     g_spre = ws + L.gSpre;
                 } else {
                     g_spre = ws + L.gS[cur];
@@ -256,11 +260,12 @@ int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     cudaStream_t st = (cudaStream_t)stream;
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
+    LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
     LGAE_TRY(run_dec_input(d, theta, batch, lat11, ws + L.y, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
         LGAE_TRY(run_level_fwd(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, ws + L.spre[l],
                                ws + L.V[l + 1], st));
-        if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
+        if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
     return run_dec_output(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], recon, gen00, st);
 }
@@ -284,7 +289,7 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
             const double* g_spre = nullptr;
             if (!gs_zero) {
                 if (d->has_mlp) {
-                    LGAE_TRY(run_mlp(d, l, theta, ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, &plan, true, st));
+                    LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], nullptr, ws + L.gS[cur], ws + L.gSpre, &plan, true, st));
                     g_spre = ws + L.gSpre;
                 } else {
                     g_spre = ws + L.gS[cur];
@@ -346,19 +351,34 @@ int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* the
     if (!d->is_decoder) LGAE_TRY(run_radial_bwd(d, level, theta, p_or_y, node_mask, batch, g_r_scratch, &plan, (cudaStream_t)stream));
     return run_reduce_plan(&plan, d->n_params, gtheta, (cudaStream_t)stream);
 }
-int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, double* acts, double* y,
-                     void* stream) {
-    LGAE_TRY(check_desc(d));
-    if (!theta || !x || !acts || !y || rows < 0) return LGAE_E_BADARG;
-    return run_mlp(d, level, theta, x, rows, acts, y, nullptr, nullptr, nullptr, false, (cudaStream_t)stream);
+int64_t lgae_mlp_pack_doubles(const LgaeModelDesc* d, int32_t level) {
+    if (check_desc(d) != LGAE_OK || level < 0 || level >= d->n_levels) return -1;
+    return mlp_pack_doubles(d, level);
 }
-int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, const double* acts,
-                      const double* g_y, double* g_x, double* gtheta, double* partials, void* stream) {
+static int pack_one_level(const LgaeModelDesc* d, int level, const double* theta, double* wpack, cudaStream_t st) {
+    // pack every level's weights contiguously starting at `wpack` would need more room than one level: pack only `level`
+    LgaeModelDesc one = *d;
+    one.n_levels = 1;
+    one.channels[0] = d->channels[level]; one.channels[1] = d->channels[level + 1];
+    one.mlp_width[0] = d->mlp_width[level];
+    for (int i = 0; i < LGAE_MAX_LINEAR; ++i) { one.off_mlp_w[0][i] = d->off_mlp_w[level][i]; one.off_mlp_b[0][i] = d->off_mlp_b[level][i]; }
+    const int64_t off0 = 0;
+    return run_mlp_pack(&one, theta, wpack, &off0, st);
+}
+int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, double* wpack,
+                     double* acts, double* y, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (!theta || !x || !acts || !g_y || !gtheta || !partials || rows < 0) return LGAE_E_BADARG;
+    if (!theta || !x || !wpack || !acts || !y || rows < 0 || level < 0 || level >= d->n_levels) return LGAE_E_BADARG;
+    LGAE_TRY(pack_one_level(d, level, theta, wpack, (cudaStream_t)stream));
+    return run_mlp(d, level, theta, wpack, x, rows, acts, y, nullptr, nullptr, nullptr, false, (cudaStream_t)stream);
+}
+int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, const double* wpack,
+                      const double* acts, const double* g_y, double* g_x, double* gtheta, double* partials, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!theta || !x || !wpack || !acts || !g_y || !gtheta || !partials || rows < 0) return LGAE_E_BADARG;
     PartPlan plan;
     plan.base = partials;
-    LGAE_TRY(run_mlp(d, level, theta, x, rows, const_cast<double*>(acts), nullptr, g_y, g_x, &plan, true, (cudaStream_t)stream));
+    LGAE_TRY(run_mlp(d, level, theta, wpack, x, rows, const_cast<double*>(acts), nullptr, g_y, g_x, &plan, true, (cudaStream_t)stream));
     return run_reduce_plan(&plan, d->n_params, gtheta, (cudaStream_t)stream);
 }
 

@@ -620,7 +620,16 @@ __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, cons
         double acc = 0.0;
         if (x < sg.len) {
             const double* src = partials + sg.part_off + x;
-            for (int r = threadIdx.y; r < sg.rows; r += 8) acc += src[(int64_t)r * sg.stride];
+            int r = threadIdx.y;
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (; r + 24 < sg.rows; r += 32) {   // four independent loads in flight
+                acc += src[(int64_t)r * sg.stride];
+                a1 += src[(int64_t)(r + 8) * sg.stride];
+                a2 += src[(int64_t)(r + 16) * sg.stride];
+                a3 += src[(int64_t)(r + 24) * sg.stride];
+            }
+            for (; r < sg.rows; r += 8) acc += src[(int64_t)r * sg.stride];
+            acc = (acc + a1) + (a2 + a3);
         }
         sm[threadIdx.y][threadIdx.x] = acc;
         __syncthreads();
@@ -754,7 +763,7 @@ int run_reduce_plan(const PartPlan* plan, int64_t n_params, double* gtheta, cuda
     int maxlen = 1;
     for (int i = 0; i < plan->table.n; ++i) maxlen = plan->table.s[i].len > maxlen ? plan->table.s[i].len : maxlen;
     int gx = (maxlen + 31) / 32;
-    if (gx > 64) gx = 64;
+    if (gx > 1024) gx = 1024;
     reduce_segs_kernel<<<dim3(gx, plan->table.n), dim3(32, 8), 0, st>>>(plan->table, plan->base, gtheta);
     count_launch();
     return check_launch("reduce_partials");

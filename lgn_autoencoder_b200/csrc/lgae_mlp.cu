@@ -3,13 +3,17 @@
 // LeakyReLU(0.01) after all but the last.  This is the one genuinely dense GEMM chain of the LGAE
 // ((B*N) x w x w, fp64), so it runs on the fp64 tensor-core MMA (DMMA m8n8k4).
 //
-// Forward: a warp owns 8*MT rows and keeps them in registers through the whole chain.  The accumulator
+// Both kernels keep the weights of ALL layers resident in shared memory (<= 98 KB at w = 48), staged once per CTA in
+// MMA-fragment order, so the layer chain of a row group runs without any block-wide barrier.
+//
+// Forward: a warp owns 8 rows at a time and keeps them in registers through the whole chain.  The accumulator
 // fragment of layer l (row g, columns 2q,2q+1 of every 8-column tile) is reused directly as the A operand of
 // layer l+1 by enumerating the reduction index in the order the fragments already have (k-step (tile, e) <->
-// column 8*tile + 2q + e); the weights are staged in shared memory pre-permuted into that fragment order, so
-// no shuffles or shared-memory round trips are needed between layers.
-// Backward: per layer, the data gradient uses the same trick with the transposed weights; the weight gradient
-// dW = dZ^T H is a second DMMA GEMM over the chunk's rows with dZ and H staged in shared memory.
+// column 8*tile + 2q + e), so no shuffles or shared-memory round trips are needed between layers.
+// Backward: a CTA owns a contiguous slab of rows.  Per layer, the data gradient uses the same register trick with
+// the transposed weights; the weight gradient dW = dZ^T H is a second MMA contraction over the slab's rows with dZ
+// and H staged in shared memory, its tiles dealt to the warps, and the result goes straight to the CTA's row of
+// parameter-gradient partials.
 #include <cstring>
 
 #include "lgae_common.cuh"
@@ -18,6 +22,7 @@ namespace lgae {
 
 struct MlpArgs {
     const double* theta;
+    const double* wpack;   // fragment-ordered weights of all layers (mlp_pack_kernel): [forward order | transposed order]
     int64_t off_w[LGAE_MAX_LINEAR], off_b[LGAE_MAX_LINEAR];
     int n_lin;   // number of Linear layers (hidden + 1)
     int nin;     // 2C'
@@ -26,13 +31,23 @@ struct MlpArgs {
     double* acts;     // (n_lin-1, rows, 8*NTW)
     double* y;        // (rows, nin)
     int64_t rows;
+    int64_t rows_per_cta;  // backward: slab of rows owned by a CTA (multiple of 8)
     const double* g_y;
     double* g_x;
-    double* part;          // (gridDim.x, part_stride) per-CTA rows of parameter-gradient partials (zeroed by the host)
+    double* part;          // (gridDim.x, part_stride) per-CTA rows of parameter-gradient partials
     int64_t part_stride;
     int64_t po_w[LGAE_MAX_LINEAR], po_b[LGAE_MAX_LINEAR];   // column offsets inside a row
     double slope;
 };
+
+constexpr int MLP_THREADS = 256;
+constexpr int MLP_BWD_ROWS = 128;   // rows of a slab processed at once by the backward kernel (16 row groups)
+
+// Doubles of fragment-ordered weights of layer l (tiles padded to 8).
+__host__ __device__ inline int mlp_layer_frag(int l, int n_lin, int NTW, int NTI) {
+    const int kt = l == 0 ? NTI : NTW, no = l == n_lin - 1 ? NTI : NTW;
+    return kt * 2 * no * 32;
+}
 
 // Stage W (out x in, row-major, from theta) into fragment order for  D[row][n] += A[row][k] W[n][k]:
 //   Wp[((kt*2+e)*NO + nt)*32 + q*8 + g] = W[8nt+g][8kt+2q+e]
@@ -55,259 +70,378 @@ LGAE_DEV void stage_w_bwd(const double* w, int nout, int nink, int NO, int KI, d
     }
 }
 
-template <int MT, int KT, int NO>
-LGAE_DEV void layer_mma(const double (&act)[MT][KT][2], double (&acc)[MT][NO][2], const double* Wp, int q, int g) {
+// Straight copy of pre-packed fragments global -> shared (n is a multiple of 64 doubles).
+LGAE_DEV void copy_frags(const double* src, double* dst, int n) {
+    const double4* s4 = reinterpret_cast<const double4*>(src);
+    double4* d4 = reinterpret_cast<double4*>(dst);
+    const int n4 = n >> 2;
+    int t = threadIdx.x;
+    for (; t + 3 * (int)blockDim.x < n4; t += 4 * blockDim.x) {
+        const double4 v0 = s4[t], v1 = s4[t + blockDim.x], v2 = s4[t + 2 * blockDim.x], v3 = s4[t + 3 * blockDim.x];
+        d4[t] = v0; d4[t + blockDim.x] = v1; d4[t + 2 * blockDim.x] = v2; d4[t + 3 * blockDim.x] = v3;
+    }
+    for (; t < n4; t += blockDim.x) d4[t] = s4[t];
+}
+
+template <int KT, int NO>
+LGAE_DEV void layer_mma(const double (&act)[KT][2], double (&acc)[NO][2], const double* Wp, int q, int g) {
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt)
 #pragma unroll
         for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int nt = 0; nt < NO; ++nt) {
-                const double bv = Wp[((kt * 2 + e) * NO + nt) * 32 + q * 8 + g];
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], act[mt][kt][e], bv);
-            }
+            for (int nt = 0; nt < NO; ++nt) dmma(acc[nt][0], acc[nt][1], act[kt][e], Wp[((kt * 2 + e) * NO + nt) * 32 + q * 8 + g]);
 }
 
-template <int NTW, int NTI, int MT>
-__global__ void __launch_bounds__(256) mlp_fwd_kernel(const MlpArgs a) {
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+template <int NTW, int NTI>
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpArgs a) {
     extern __shared__ __align__(128) double smem[];
-    double* Wp = smem;                                   // NTW*NTW*64
-    double* bias_s = smem + NTW * NTW * 64;              // 8*NTW
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int RW = nwarps * 8 * MT, WP = 8 * NTW;
+    constexpr int WP = 8 * NTW;
     const int last = a.n_lin - 1;
-    for (int64_t r0 = (int64_t)blockIdx.x * RW; r0 < a.rows; r0 += (int64_t)gridDim.x * RW) {
-        const int64_t rbase = r0 + warp * 8 * MT;
-        double in0[MT][NTI][2];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NTI; ++nt) {
-                const int64_t row = rbase + mt * 8 + g;
-                const int col = 8 * nt + 2 * q;
-                double2 v = make_double2(0.0, 0.0);
-                if (row < a.rows && col < a.nin) v = *reinterpret_cast<const double2*>(a.x + row * a.nin + col);
-                in0[mt][nt][0] = v.x;
-                in0[mt][nt][1] = v.y;
-            }
-        double act[MT][NTW][2], acc[MT][NTW][2];
-        auto init_bias = [&](int nout, int off) {
-            __syncthreads();
-            for (int t = tid; t < WP; t += blockDim.x) bias_s[t] = t < nout ? a.theta[off + t] : 0.0;
-        };
-        auto finish_hidden = [&](int l) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NTW; ++nt) {
-                    act[mt][nt][0] = leaky(acc[mt][nt][0], a.slope);
-                    act[mt][nt][1] = leaky(acc[mt][nt][1], a.slope);
-                    const int64_t row = rbase + mt * 8 + g;
-                    if (row < a.rows)
-                        *reinterpret_cast<double2*>(a.acts + ((int64_t)l * a.rows + row) * WP + 8 * nt + 2 * q) =
-                            make_double2(act[mt][nt][0], act[mt][nt][1]);
-                }
-        };
-        // ---- first layer: nin -> w ----
-        init_bias(a.width, a.off_b[0]);
-        stage_w_fwd(a.theta + a.off_w[0], a.width, a.nin, NTI, NTW, Wp);
-        __syncthreads();
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) { acc[mt][nt][0] = bias_s[8 * nt + 2 * q]; acc[mt][nt][1] = bias_s[8 * nt + 2 * q + 1]; }
-        layer_mma<MT, NTI, NTW>(in0, acc, Wp, q, g);
-        finish_hidden(0);
-        // ---- hidden layers: w -> w ----
-        for (int l = 1; l < last; ++l) {
-            init_bias(a.width, a.off_b[l]);
-            stage_w_fwd(a.theta + a.off_w[l], a.width, a.width, NTW, NTW, Wp);
-            __syncthreads();
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NTW; ++nt) { acc[mt][nt][0] = bias_s[8 * nt + 2 * q]; acc[mt][nt][1] = bias_s[8 * nt + 2 * q + 1]; }
-            layer_mma<MT, NTW, NTW>(act, acc, Wp, q, g);
-            finish_hidden(l);
+    // ---- all layers' weights and biases, once per CTA ----
+    double* bias_s = smem;                 // n_lin * WP
+    double* w_s = smem + a.n_lin * WP;
+    {
+        int wtotal = 0;
+        for (int l = 0; l <= last; ++l) {
+            const int nout = l == last ? a.nin : a.width;
+            wtotal += mlp_layer_frag(l, a.n_lin, NTW, NTI);
+            for (int t = tid; t < WP; t += blockDim.x) bias_s[l * WP + t] = t < nout ? a.theta[a.off_b[l] + t] : 0.0;
         }
-        // ---- last layer: w -> nin, no activation ----
-        init_bias(a.nin, a.off_b[last]);
-        stage_w_fwd(a.theta + a.off_w[last], a.nin, a.width, NTW, NTI, Wp);
-        __syncthreads();
-        double out[MT][NTI][2];
+        copy_frags(a.wpack, w_s, wtotal);
+    }
+    __syncthreads();
+    // ---- row groups of 8, a contiguous range per CTA dealt round-robin to its warps ----
+    const int64_t ngroups = (a.rows + 7) / 8;
+    const int64_t per_cta = (ngroups + gridDim.x - 1) / gridDim.x;
+    const int64_t g_begin = (int64_t)blockIdx.x * per_cta, g_end = g_begin + per_cta < ngroups ? g_begin + per_cta : ngroups;
+    for (int64_t grp = g_begin + warp; grp < g_end; grp += nwarps) {
+        const int64_t row = grp * 8 + g;
+        const bool ok = row < a.rows;
+        double in0[NTI][2];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int nt = 0; nt < NTI; ++nt) {
+            const int col = 8 * nt + 2 * q;
+            double2 v = make_double2(0.0, 0.0);
+            if (ok && col < a.nin) v = *reinterpret_cast<const double2*>(a.x + row * a.nin + col);
+            in0[nt][0] = v.x;
+            in0[nt][1] = v.y;
+        }
+        double act[NTW][2], acc[NTW][2];
+        const double* wl = w_s;
+        // first layer: nin -> w
 #pragma unroll
-            for (int nt = 0; nt < NTI; ++nt) { out[mt][nt][0] = bias_s[8 * nt + 2 * q]; out[mt][nt][1] = bias_s[8 * nt + 2 * q + 1]; }
-        layer_mma<MT, NTW, NTI>(act, out, Wp, q, g);
+        for (int nt = 0; nt < NTW; ++nt) { acc[nt][0] = bias_s[8 * nt + 2 * q]; acc[nt][1] = bias_s[8 * nt + 2 * q + 1]; }
+        layer_mma<NTI, NTW>(in0, acc, wl, q, g);
+        wl += NTI * 2 * NTW * 32;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int nt = 0; nt < NTW; ++nt) {
+            act[nt][0] = leaky(acc[nt][0], a.slope);
+            act[nt][1] = leaky(acc[nt][1], a.slope);
+            if (ok) *reinterpret_cast<double2*>(a.acts + row * WP + 8 * nt + 2 * q) = make_double2(act[nt][0], act[nt][1]);
+        }
+        // hidden layers: w -> w
+        for (int l = 1; l < last; ++l) {
+            const double* bl = bias_s + l * WP;
 #pragma unroll
-            for (int nt = 0; nt < NTI; ++nt) {
-                const int64_t row = rbase + mt * 8 + g;
-                const int col = 8 * nt + 2 * q;
-                if (row < a.rows && col < a.nin)
-                    *reinterpret_cast<double2*>(a.y + row * a.nin + col) = make_double2(out[mt][nt][0], out[mt][nt][1]);
+            for (int nt = 0; nt < NTW; ++nt) { acc[nt][0] = bl[8 * nt + 2 * q]; acc[nt][1] = bl[8 * nt + 2 * q + 1]; }
+            layer_mma<NTW, NTW>(act, acc, wl, q, g);
+            wl += NTW * 2 * NTW * 32;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                act[nt][0] = leaky(acc[nt][0], a.slope);
+                act[nt][1] = leaky(acc[nt][1], a.slope);
+                if (ok)
+                    *reinterpret_cast<double2*>(a.acts + ((int64_t)l * a.rows + row) * WP + 8 * nt + 2 * q) = make_double2(act[nt][0], act[nt][1]);
             }
+        }
+        // last layer: w -> nin, no activation
+        double out[NTI][2];
+        const double* bl = bias_s + last * WP;
+#pragma unroll
+        for (int nt = 0; nt < NTI; ++nt) { out[nt][0] = bl[8 * nt + 2 * q]; out[nt][1] = bl[8 * nt + 2 * q + 1]; }
+        layer_mma<NTW, NTI>(act, out, wl, q, g);
+#pragma unroll
+        for (int nt = 0; nt < NTI; ++nt) {
+            const int col = 8 * nt + 2 * q;
+            if (ok && col < a.nin) *reinterpret_cast<double2*>(a.y + row * a.nin + col) = make_double2(out[nt][0], out[nt][1]);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
-template <int NTW, int NTI, int MT>
-__global__ void __launch_bounds__(256) mlp_bwd_kernel(const MlpArgs a) {
+template <int NTW, int NTI>
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a) {
     extern __shared__ __align__(128) double smem[];
-    constexpr int WS = 8 * NTW + 4;  // padded row stride of the staged tiles (bank-conflict-free fragment loads)
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    constexpr int WS = 8 * NTW + 4;                 // padded row stride of the staged tiles (conflict-free fragment loads)
+    constexpr int WP = 8 * NTW;
+    constexpr int NWARP = MLP_THREADS / 32;
+    constexpr int TU = MLP_BWD_ROWS / 8 / NWARP;    // row groups per warp per chunk
+    constexpr int MAXT = (NTW * NTW + NWARP - 1) / NWARP;   // dW tiles per warp
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int RW = nwarps * 8 * MT, WP = 8 * NTW;
-    double* Wq = smem;                        // NTW*NTW*64
-    double* dz_s = Wq + NTW * NTW * 64;       // RW * WS
-    double* h_s = dz_s + RW * WS;             // RW * WS
     const int last = a.n_lin - 1;
+    double* w_s = smem;
+    int wtotal = 0;
+    for (int l = 0; l <= last; ++l) wtotal += mlp_layer_frag(l, a.n_lin, NTW, NTI);
+    double* dz_s = w_s + wtotal;                    // MLP_BWD_ROWS * WS
+    double* h_s = dz_s + MLP_BWD_ROWS * WS;         // MLP_BWD_ROWS * WS
+    double* bred = h_s + MLP_BWD_ROWS * WS;         // NWARP * WP : per-warp column sums of dZ
+    copy_frags(a.wpack + wtotal, w_s, wtotal);
     double* part = a.part + (int64_t)blockIdx.x * a.part_stride;
-
-    for (int64_t r0 = (int64_t)blockIdx.x * RW; r0 < a.rows; r0 += (int64_t)gridDim.x * RW) {
-        const int rl0 = warp * 8 * MT;          // first local row of this warp
-        const int64_t rbase = r0 + rl0;
-        // gradient wrt the output of the last layer, accumulator-fragment layout
-        double dz[MT][NTW][2];
+    const int64_t slab0 = (int64_t)blockIdx.x * a.rows_per_cta;
+    const int64_t slab1 = slab0 + a.rows_per_cta < a.rows ? slab0 + a.rows_per_cta : a.rows;
+    bool first = true;   // first chunk of the slab: partials are stored, later chunks accumulate
+    for (int64_t r0 = slab0;; r0 += MLP_BWD_ROWS) {
+        const int crows = (int)(slab1 - r0 < MLP_BWD_ROWS ? (slab1 > r0 ? slab1 - r0 : 0) : MLP_BWD_ROWS);
+        const int ksteps = ((crows + 7) / 8) * 2;   // MMA k-steps (4 rows each) covering the chunk
+        // gradient wrt the output of the last layer, accumulator-fragment layout, for this warp's row groups
+        double dz[TU][NTW][2];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
+        for (int u = 0; u < TU; ++u) {
+            const int64_t row = r0 + (warp + NWARP * u) * 8 + g;
 #pragma unroll
             for (int nt = 0; nt < NTW; ++nt) {
-                dz[mt][nt][0] = dz[mt][nt][1] = 0.0;
+                dz[u][nt][0] = dz[u][nt][1] = 0.0;
                 if (nt < NTI) {
-                    const int64_t row = rbase + mt * 8 + g;
                     const int col = 8 * nt + 2 * q;
-                    if (row < a.rows && col < a.nin) {
+                    if (row < slab1 && col < a.nin) {
                         const double2 v = *reinterpret_cast<const double2*>(a.g_y + row * a.nin + col);
-                        dz[mt][nt][0] = v.x;
-                        dz[mt][nt][1] = v.y;
+                        dz[u][nt][0] = v.x;
+                        dz[u][nt][1] = v.y;
                     }
                 }
             }
+        }
+        const double* wl = w_s + wtotal;
         for (int l = last; l >= 0; --l) {
             const int nout = l == last ? a.nin : a.width, nink = l == 0 ? a.nin : a.width;
             const int NOt = l == last ? NTI : NTW, KIt = l == 0 ? NTI : NTW;
+            wl -= mlp_layer_frag(l, a.n_lin, NTW, NTI);
+            __syncthreads();   // previous layer's readers of dz_s / h_s / bred are done (also orders the weight staging)
+            // ---- stage dZ_l and the layer input H_l of this warp's row groups ----
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                const int rl = (warp + NWARP * u) * 8;
+                if (rl < ksteps * 4) {
+#pragma unroll
+                    for (int nt = 0; nt < NTW; ++nt)
+                        if (nt < NOt)
+                            *reinterpret_cast<double2*>(dz_s + (rl + g) * WS + 8 * nt + 2 * q) = make_double2(dz[u][nt][0], dz[u][nt][1]);
+                    if (l > 0) {
+                        // 8 consecutive rows of the saved activations are one contiguous run of 8*WP doubles
+                        const double4* src = reinterpret_cast<const double4*>(a.acts + ((int64_t)(l - 1) * a.rows + r0 + rl) * WP);
+                        constexpr int PER = (8 * WP / 4 + 31) / 32;
+                        double4 v[PER];
+#pragma unroll
+                        for (int j = 0; j < PER; ++j) {
+                            const int idx = lane + 32 * j, rr = idx / (WP / 4);
+                            v[j] = make_double4(0.0, 0.0, 0.0, 0.0);
+                            if (idx < 8 * WP / 4 && r0 + rl + rr < slab1) v[j] = src[idx];
+                        }
+#pragma unroll
+                        for (int j = 0; j < PER; ++j) {
+                            const int idx = lane + 32 * j, rr = idx / (WP / 4), c4 = idx % (WP / 4);
+                            if (idx < 8 * WP / 4) *reinterpret_cast<double4*>(h_s + (rl + rr) * WS + 4 * c4) = v[j];
+                        }
+                    } else {
+                        for (int idx = lane; idx < 8 * 8 * NTI; idx += 32) {
+                            const int rr = idx / (8 * NTI), cc = idx % (8 * NTI);
+                            const int64_t row = r0 + rl + rr;
+                            h_s[(rl + rr) * WS + cc] = (row < slab1 && cc < a.nin) ? a.x[row * a.nin + cc] : 0.0;
+                        }
+                    }
+                }
+            }
             __syncthreads();
-            // ---- stage dZ_l, the layer input H_l and the transposed weights ----
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < NTW; ++nt)
-                    if (nt < NOt)
-                        *reinterpret_cast<double2*>(dz_s + (rl0 + mt * 8 + g) * WS + 8 * nt + 2 * q) = make_double2(dz[mt][nt][0], dz[mt][nt][1]);
+            // ---- bias gradient: column sums of dZ (each warp sums a slice of rows, then the slices are added) ----
             {
-                const double* src = l == 0 ? a.x : a.acts + (int64_t)(l - 1) * a.rows * WP;
-                const int ld = l == 0 ? a.nin : WP, ncols = 8 * KIt;
-                for (int t = tid; t < RW * ncols; t += blockDim.x) {
-                    const int r = t / ncols, cc = t % ncols;
-                    const int64_t row = r0 + r;
-                    h_s[r * WS + cc] = (row < a.rows && cc < (l == 0 ? a.nin : WP)) ? src[row * ld + cc] : 0.0;
+                const int per = (ksteps * 4 + NWARP - 1) / NWARP;
+                const int ra = warp * per, rb = ra + per < ksteps * 4 ? ra + per : ksteps * 4;
+                for (int n = lane; n < 8 * NOt; n += 32) {
+                    double s = 0.0;
+                    for (int r = ra; r < rb; ++r) s += dz_s[r * WS + n];
+                    bred[warp * WP + n] = s;
                 }
             }
-            stage_w_bwd(a.theta + a.off_w[l], nout, nink, NOt, KIt, Wq);
-            __syncthreads();
-            // ---- bias gradient: column sums of dZ ----
-            for (int n = tid; n < nout; n += blockDim.x) {
-                double s = 0.0;
-                for (int r = 0; r < RW; ++r) s += dz_s[r * WS + n];
-                part[a.po_b[l] + n] += s;
-            }
-            // ---- weight gradient: dW[n][k] += sum_rows dZ[row][n] H[row][k] ----
-            for (int t = warp; t < NOt * KIt; t += nwarps) {
-                const int mt = t / KIt, nt = t % KIt;
-                double c0 = 0.0, c1 = 0.0;
-                for (int ks = 0; ks < RW / 4; ++ks) {
-                    const double av = dz_s[(4 * ks + q) * WS + 8 * mt + g];
-                    const double bv = h_s[(4 * ks + q) * WS + 8 * nt + g];
-                    dmma(c0, c1, av, bv);
+            // ---- weight gradient: dW[n][k] = sum_rows dZ[row][n] H[row][k]; this warp's tiles, all in flight ----
+            {
+                double cw[MAXT][2];
+                int tm[MAXT], tn[MAXT];
+#pragma unroll
+                for (int j = 0; j < MAXT; ++j) {
+                    const int t = warp + NWARP * j;
+                    const bool on = t < NOt * KIt;
+                    tm[j] = on ? t / KIt : -1;
+                    tn[j] = on ? t % KIt : 0;
+                    cw[j][0] = cw[j][1] = 0.0;
                 }
-                const int n = 8 * mt + g, k = 8 * nt + 2 * q;
-                if (n < nout) {
-                    if (k < nink) part[a.po_w[l] + (int64_t)n * nink + k] += c0;
-                    if (k + 1 < nink) part[a.po_w[l] + (int64_t)n * nink + k + 1] += c1;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const double* dr = dz_s + (4 * ks + q) * WS + g;
+                    const double* hr = h_s + (4 * ks + q) * WS + g;
+#pragma unroll
+                    for (int j = 0; j < MAXT; ++j)
+                        if (tm[j] >= 0) dmma(cw[j][0], cw[j][1], dr[8 * tm[j]], hr[8 * tn[j]]);
+                }
+#pragma unroll
+                for (int j = 0; j < MAXT; ++j) {
+                    if (tm[j] < 0) continue;
+                    const int n = 8 * tm[j] + g, k = 8 * tn[j] + 2 * q;
+                    if (n < nout) {
+                        double* dst = part + a.po_w[l] + (int64_t)n * nink + k;
+                        if (k < nink) dst[0] = first ? cw[j][0] : dst[0] + cw[j][0];
+                        if (k + 1 < nink) dst[1] = first ? cw[j][1] : dst[1] + cw[j][1];
+                    }
                 }
             }
             // ---- data gradient: Gin[row][k] = sum_n dZ[row][n] W[n][k], then through the LeakyReLU of layer l-1 ----
-            double gin[MT][NTW][2];
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
+            for (int u = 0; u < TU; ++u) {
+                const int rl = (warp + NWARP * u) * 8;
+                if (rl >= ksteps * 4) continue;
+                double gin[NTW][2];
 #pragma unroll
-                for (int kt = 0; kt < NTW; ++kt) gin[mt][kt][0] = gin[mt][kt][1] = 0.0;
+                for (int kt = 0; kt < NTW; ++kt) gin[kt][0] = gin[kt][1] = 0.0;
 #pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) {
-                if (nt < NOt) {
+                for (int nt = 0; nt < NTW; ++nt) {
+                    if (nt < NOt) {
 #pragma unroll
-                    for (int e = 0; e < 2; ++e)
+                        for (int e = 0; e < 2; ++e)
 #pragma unroll
-                        for (int kt = 0; kt < NTW; ++kt) {
-                            if (kt < KIt) {
-                                const double bv = Wq[((nt * 2 + e) * KIt + kt) * 32 + q * 8 + g];
-#pragma unroll
-                                for (int mt = 0; mt < MT; ++mt) dmma(gin[mt][kt][0], gin[mt][kt][1], dz[mt][nt][e], bv);
-                            }
-                        }
+                            for (int kt = 0; kt < NTW; ++kt)
+                                if (kt < KIt) dmma(gin[kt][0], gin[kt][1], dz[u][nt][e], wl[((nt * 2 + e) * KIt + kt) * 32 + q * 8 + g]);
+                    }
                 }
-            }
-            if (l > 0) {
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
+                if (l > 0) {
 #pragma unroll
                     for (int kt = 0; kt < NTW; ++kt) {
-                        const double2 h = *reinterpret_cast<const double2*>(h_s + (rl0 + mt * 8 + g) * WS + 8 * kt + 2 * q);
-                        dz[mt][kt][0] = gin[mt][kt][0] * (h.x > 0.0 ? 1.0 : a.slope);
-                        dz[mt][kt][1] = gin[mt][kt][1] * (h.y > 0.0 ? 1.0 : a.slope);
+                        const double2 h = *reinterpret_cast<const double2*>(h_s + (rl + g) * WS + 8 * kt + 2 * q);
+                        dz[u][kt][0] = gin[kt][0] * (h.x > 0.0 ? 1.0 : a.slope);
+                        dz[u][kt][1] = gin[kt][1] * (h.y > 0.0 ? 1.0 : a.slope);
                     }
-            } else if (a.g_x) {
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt)
+                } else if (a.g_x) {
+                    const int64_t row = r0 + rl + g;
 #pragma unroll
                     for (int kt = 0; kt < NTI; ++kt) {
-                        const int64_t row = rbase + mt * 8 + g;
                         const int col = 8 * kt + 2 * q;
-                        if (row < a.rows && col < a.nin)
-                            *reinterpret_cast<double2*>(a.g_x + row * a.nin + col) = make_double2(gin[mt][kt][0], gin[mt][kt][1]);
+                        if (row < slab1 && col < a.nin) *reinterpret_cast<double2*>(a.g_x + row * a.nin + col) = make_double2(gin[kt][0], gin[kt][1]);
                     }
+                }
+            }
+            __syncthreads();   // bred complete
+            for (int n = tid; n < nout; n += blockDim.x) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) s += bred[w * WP + n];
+                double* dst = part + a.po_b[l] + n;
+                dst[0] = first ? s : dst[0] + s;
             }
         }
+        first = false;
+        if (r0 + MLP_BWD_ROWS >= slab1) break;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int NTW, int NTI, int MT>
-static int launch_mlp(const MlpArgs& a, bool bwd, cudaStream_t st) {
-    const int threads = 256, RW = (threads / 32) * 8 * MT;
+// Weight pre-packing: one launch per model forward writes every level's weights in both fragment orders, so the
+// MLP kernels stage them with straight vector copies.  blockIdx = (layer, direction, level).
+struct MlpPackArgs {
+    const double* theta;
+    double* out;
+    int n_lin;
+    int nin[LGAE_MAX_LEVELS], width[LGAE_MAX_LEVELS];
+    int64_t off_w[LGAE_MAX_LEVELS][LGAE_MAX_LINEAR];
+    int64_t out_off[LGAE_MAX_LEVELS];
+};
+__global__ void __launch_bounds__(256) mlp_pack_kernel(const MlpPackArgs p) {
+    const int l = blockIdx.x, dir = blockIdx.y, lev = blockIdx.z;
+    const int nin = p.nin[lev], width = p.width[lev], NTW = (width + 7) / 8, NTI = (nin + 7) / 8, last = p.n_lin - 1;
+    int off = 0, wtotal = 0;
+    for (int i = 0; i <= last; ++i) {
+        if (i < l) off += mlp_layer_frag(i, p.n_lin, NTW, NTI);
+        wtotal += mlp_layer_frag(i, p.n_lin, NTW, NTI);
+    }
+    const int nout = l == last ? nin : width, nink = l == 0 ? nin : width;
+    const double* w = p.theta + p.off_w[lev][l];
+    double* dst = p.out + p.out_off[lev] + (dir ? wtotal : 0) + off;
+    if (dir == 0)
+        stage_w_fwd(w, nout, nink, l == 0 ? NTI : NTW, l == last ? NTI : NTW, dst);
+    else
+        stage_w_bwd(w, nout, nink, l == last ? NTI : NTW, l == 0 ? NTI : NTW, dst);
+}
+
+static int mlp_frag_total(int n_lin, int NTW, int NTI) {
+    int t = 0;
+    for (int l = 0; l < n_lin; ++l) t += mlp_layer_frag(l, n_lin, NTW, NTI);
+    return t;
+}
+
+int mlp_bwd_grid() { return sm_count(); }
+
+template <int NTW, int NTI>
+static int launch_mlp(MlpArgs& a, bool bwd, cudaStream_t st) {
+    const int wtotal = mlp_frag_total(a.n_lin, NTW, NTI);
     if (!bwd) {
-        const size_t bytes = (size_t)(NTW * NTW * 64 + 8 * NTW) * sizeof(double);
-        auto kern = mlp_fwd_kernel<NTW, NTI, MT>;
+        const size_t bytes = (size_t)(wtotal + a.n_lin * 8 * NTW) * sizeof(double);
+        if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
+        auto kern = mlp_fwd_kernel<NTW, NTI>;
         if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
-        int64_t chunks = (a.rows + RW - 1) / RW;
-        int grid = (int)(chunks < (int64_t)2 * sm_count() ? chunks : (int64_t)2 * sm_count());
-        kern<<<grid, threads, bytes, st>>>(a);
+        const int64_t ngroups = (a.rows + 7) / 8;
+        const int grid = (int)(ngroups < sm_count() ? ngroups : sm_count());
+        kern<<<grid, MLP_THREADS, bytes, st>>>(a);
         count_launch();
         return check_launch("mlp_fwd");
     }
-    const size_t bytes = (size_t)(NTW * NTW * 64 + 2 * RW * (8 * NTW + 4)) * sizeof(double);
+    const size_t bytes = (size_t)(wtotal + 2 * MLP_BWD_ROWS * (8 * NTW + 4) + (MLP_THREADS / 32) * 8 * NTW) * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
-    auto kern = mlp_bwd_kernel<NTW, NTI, MT>;
+    auto kern = mlp_bwd_kernel<NTW, NTI>;
     if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
-    kern<<<sm_count(), threads, bytes, st>>>(a);
+    const int grid = mlp_bwd_grid();
+    const int64_t per = (a.rows + grid - 1) / grid;
+    a.rows_per_cta = ((per + 7) / 8) * 8;
+    kern<<<grid, MLP_THREADS, bytes, st>>>(a);
     count_launch();
     return check_launch("mlp_bwd");
 }
 
-int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* x, int64_t rows, double* acts,
+// Doubles of packed weights (both orders) of one level.
+int64_t mlp_pack_doubles(const LgaeModelDesc* d, int level) {
+    if (!d->has_mlp) return 0;
+    return 2 * (int64_t)mlp_frag_total(d->mlp_hidden + 1, (d->mlp_width[level] + 7) / 8, (2 * d->channels[level + 1] + 7) / 8);
+}
+// Pack the MLP weights of every level: out + out_off[level] receives mlp_pack_doubles(d, level) doubles.
+int run_mlp_pack(const LgaeModelDesc* d, const double* theta, double* out, const int64_t* out_off, cudaStream_t st) {
+    if (!d->has_mlp) return LGAE_OK;
+    MlpPackArgs p;
+    memset(&p, 0, sizeof(p));
+    p.theta = theta; p.out = out; p.n_lin = d->mlp_hidden + 1;
+    for (int l = 0; l < d->n_levels; ++l) {
+        p.nin[l] = 2 * d->channels[l + 1];
+        p.width[l] = d->mlp_width[l];
+        p.out_off[l] = out_off[l];
+        for (int i = 0; i < p.n_lin; ++i) p.off_w[l][i] = d->off_mlp_w[l][i];
+    }
+    mlp_pack_kernel<<<dim3(p.n_lin, 2, d->n_levels), 256, 0, st>>>(p);
+    count_launch();
+    return check_launch("mlp_pack");
+}
+
+int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* wpack, const double* x, int64_t rows, double* acts,
             double* y, const double* g_y, double* g_x, PartPlan* plan, bool bwd, cudaStream_t st) {
     if (!d || level < 0 || level >= d->n_levels || !d->has_mlp) return LGAE_E_BADARG;
     MlpArgs a;
     memset(&a, 0, sizeof(a));
     a.theta = theta;
+    a.wpack = wpack;
     a.n_lin = d->mlp_hidden + 1;
+    if (!wpack) return LGAE_E_BADARG;
     if (a.n_lin < 2 || a.n_lin > LGAE_MAX_LINEAR) return LGAE_E_UNSUPPORTED;
     for (int i = 0; i < a.n_lin; ++i) { a.off_w[i] = d->off_mlp_w[level][i]; a.off_b[i] = d->off_mlp_b[level][i]; }
     a.nin = 2 * d->channels[level + 1];
@@ -317,7 +451,7 @@ int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double
     if (rows <= 0) return LGAE_OK;
     if (bwd) {
         if (!plan) return LGAE_E_BADARG;
-        const int grid = sm_count();
+        const int grid = mlp_bwd_grid();
         int64_t w = 0;
         for (int i = 0; i < a.n_lin; ++i) {
             const int nout = i == a.n_lin - 1 ? a.nin : a.width, nink = i == 0 ? a.nin : a.width;
@@ -332,14 +466,13 @@ int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double
             if (int rc = plan->seg(a.off_w[i], off, w, a.po_w[i], (int64_t)nout * nink, grid)) return rc;
             if (int rc = plan->seg(a.off_b[i], off, w, a.po_b[i], nout, grid)) return rc;
         }
-        if (cudaMemsetAsync(a.part, 0, (size_t)grid * w * sizeof(double), st) != cudaSuccess) return check_launch("memset mlp partials");
     }
     const int ntw = (a.width + 7) / 8, nti = (a.nin + 7) / 8;
-#define LGAE_MLP_CASE(W, I, M) \
-    if (ntw == W && nti == I) return launch_mlp<W, I, M>(a, bwd, st);
-    LGAE_MLP_CASE(1, 1, 2) LGAE_MLP_CASE(2, 1, 2) LGAE_MLP_CASE(3, 1, 2) LGAE_MLP_CASE(4, 1, 2)
-    LGAE_MLP_CASE(5, 1, 2) LGAE_MLP_CASE(6, 1, 2)
-    LGAE_MLP_CASE(8, 2, 1) LGAE_MLP_CASE(9, 2, 1) LGAE_MLP_CASE(11, 2, 1) LGAE_MLP_CASE(12, 2, 1)
+#define LGAE_MLP_CASE(W, I) \
+    if (ntw == W && nti == I) return launch_mlp<W, I>(a, bwd, st);
+    LGAE_MLP_CASE(1, 1) LGAE_MLP_CASE(2, 1) LGAE_MLP_CASE(3, 1) LGAE_MLP_CASE(4, 1)
+    LGAE_MLP_CASE(5, 1) LGAE_MLP_CASE(6, 1)
+    LGAE_MLP_CASE(8, 2) LGAE_MLP_CASE(9, 2)
 #undef LGAE_MLP_CASE
     return LGAE_E_UNSUPPORTED;
 }
@@ -354,7 +487,6 @@ int64_t mlp_part_width(const LgaeModelDesc* d, int level) {
     }
     return w;
 }
-int mlp_bwd_grid() { return sm_count(); }
 
 int mlp_padded_width(const LgaeModelDesc* d, int level) { return 8 * ((d->mlp_width[level] + 7) / 8); }
 
