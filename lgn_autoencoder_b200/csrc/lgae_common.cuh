@@ -112,6 +112,9 @@ LGAE_DEV double warp_sum(double v) {
     return v;
 }
 
+// Sum over the warp, result in every lane (the xor butterfly of warp_sum already has that property).
+LGAE_DEV double warp_allsum(double v) { return warp_sum(v); }
+
 // Block-wide sum; result valid in thread 0.  `scratch` must hold >= 32 doubles.
 LGAE_DEV double block_sum(double v, double* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -11,6 +11,7 @@
 // MMA (phi (pairs x K) times W^T (K x 4C)) into shared memory and consumed by the (i, c) threads; the neighbour
 // sums stay in registers.  The only O(N^2) tensor that goes to HBM is the optional copy of the radial weights
 // R_ij[c] (r_save) that the training forward keeps for the adjoint, which then does not re-evaluate them.
+#include <cstdlib>
 #include <cstring>
 
 #include "lgae_common.cuh"
@@ -219,6 +220,44 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
 #pragma unroll
     for (int mu = 0; mu < 4; ++mu) { A0V[mu] = czero(); A1Y[mu] = czero(); }
 
+    if (!ENC && PRE) {
+        // Decoder, closed form: the radial weights are the constants R^l[c] = bias_l[c] (1+i), so
+        // the neighbour sums factor through four jet-level moments of the node features, O(N) instead of O(N^2):
+        //   SS = sum_j S_j   SV = sum_j V_j   SSY = sum_j S_j y_j   SVY = sum_j eta(V_j, y_j)
+        //   A0V_i = R0 SV   A0S_i = R0 SS   A1Y_i = R1 (y_i SS - SSY)   A1E_i = R1 (eta(SV, y_i) - SVY)
+        const cplx* y_s = reinterpret_cast<const cplx*>(p_s);
+        double m[20];
+#pragma unroll
+        for (int t = 0; t < 20; ++t) m[t] = 0.0;
+        for (int j = lane; j < N; j += 32) {
+            const cplx Sj = S_s[j * C + c];
+            cplx Vj[4], yj[4];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) { Vj[mu] = V_s[(j * C + c) * 4 + mu]; yj[mu] = y_s[4 * j + mu]; }
+            m[0] += Sj.x; m[1] += Sj.y;
+            const cplx e = ceta(Vj, yj);
+            m[18] += e.x; m[19] += e.y;
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) {
+                m[2 + 2 * mu] += Vj[mu].x; m[3 + 2 * mu] += Vj[mu].y;
+                const cplx sy = cmul(Sj, yj[mu]);
+                m[10 + 2 * mu] += sy.x; m[11 + 2 * mu] += sy.y;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 20; ++t) m[t] = warp_allsum(m[t]);
+        const cplx SS = cmake(m[0], m[1]), SVY = cmake(m[18], m[19]);
+        cplx SV[4], SSY[4];
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) { SV[mu] = cmake(m[2 + 2 * mu], m[3 + 2 * mu]); SSY[mu] = cmake(m[10 + 2 * mu], m[11 + 2 * mu]); }
+        A0S = cmul(R0c, SS);
+        A1E = cmul(R1c, csub(ceta(SV, yi), SVY));
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) {
+            A0V[mu] = cmul(R0c, SV[mu]);
+            A1Y[mu] = cmul(R1c, csub(cmul(yi[mu], SS), SSY[mu]));
+        }
+    } else {
     const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
     double4 rnext = make_double4(0.0, 0.0, 0.0, 0.0);
     if (ENC && PRE) rnext = rsv[0];
@@ -277,6 +316,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
             cfma(A1E, R1, e);
         }
         if (ENC && !PRE) __syncthreads();
+    }
     }
 
     // ---- keep the neighbour sums for the backward pass; build cat = [ag | node | sq] in shared memory ----
@@ -391,7 +431,7 @@ LGAE_DEV void mix_adjoint_block(int k, int Cout, int C5, int nm, int lane, const
 //      g_r for radial_bwd_kernel (encoder) or summed (decoder: constant radial weights); role 2 (own = neighbour)
 //      accumulates dL/dS_lane, dL/dV_lane in registers.  Encoder: R_{lane,o} is streamed from r_save, prefetched;
 //   3. when the CTA runs out of jets: one compact row of parameter-gradient partials (mix weights, decoder biases).
-template <bool ENC, int MAXT, int MINB>
+template <bool ENC, int MAXT, int MINB, bool CF>
 __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a) {
     extern __shared__ __align__(128) double smem[];
     const int N = a.N, C = a.C, Cout = a.Cout;
@@ -523,7 +563,92 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
         __syncthreads();  // gA_s of every channel is complete (role 2 reads other lanes' entries)
         // ---- 2. neighbour loop ----
         cplx gy[4] = {czero(), czero(), czero(), czero()};
-        {
+        if (!ENC && CF) {
+            // Decoder, closed form: adjoint of  A0V_i = R0 SV, A0S_i = R0 SS, A1Y_i = R1 (y_i SS - SSY), A1E_i = R1 (eta(SV, y_i) - SVY)
+            // with the jet-level moments SS, SV, SSY, SVY of the forward (recomputed here), all O(N).
+            const cplx* y_s = reinterpret_cast<const cplx*>(p_s);
+            cplx ya[4], Va[4], gAa[10];
+            const cplx Sa = live ? S_s[i * C + c] : czero();
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) {
+                ya[mu] = live ? y_s[4 * i + mu] : czero();
+                Va[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
+            }
+#pragma unroll
+            for (int e = 0; e < 10; ++e) gAa[e] = live ? gA_s[(c * 10 + e) * 32 + lane] : czero();
+            // moments (this lane's particle only: N <= 32 in the adjoint)
+            double m[20];
+            {
+                const cplx e = ceta(Va, ya);
+                m[0] = Sa.x; m[1] = Sa.y; m[18] = e.x; m[19] = e.y;
+#pragma unroll
+                for (int mu = 0; mu < 4; ++mu) {
+                    m[2 + 2 * mu] = Va[mu].x; m[3 + 2 * mu] = Va[mu].y;
+                    const cplx sy = cmul(Sa, ya[mu]);
+                    m[10 + 2 * mu] = sy.x; m[11 + 2 * mu] = sy.y;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 20; ++t) m[t] = warp_allsum(m[t]);
+            const cplx SS = cmake(m[0], m[1]), SVY = cmake(m[18], m[19]);
+            cplx SV[4], SSY[4];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) { SV[mu] = cmake(m[2 + 2 * mu], m[3 + 2 * mu]); SSY[mu] = cmake(m[10 + 2 * mu], m[11 + 2 * mu]); }
+            // per-particle pieces
+            cplx gT[4], gU = cmulc(R1c, gAa[9]);          // conj(R1) gA1E_i
+            cplx gr0 = cmulc(SS, gAa[4]);                 // conj(SS) gA0S_i
+            const cplx U = csub(ceta(SV, ya), SVY);
+            cplx gr1 = cmulc(U, gAa[9]);
+            cplx yt = czero();                            // sum_mu conj(y_i) gT_i
+            cplx ghy[4], ghsv[4], ghv[4];
+            cghat(ya, ghy);
+            cghat(SV, ghsv);
+            cghat(Va, ghv);
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) {
+                gT[mu] = cmulc(R1c, gAa[5 + mu]);
+                cfmac(gr0, SV[mu], gAa[mu]);
+                const cplx T = csub(cmul(ya[mu], SS), SSY[mu]);
+                cfmac(gr1, T, gAa[5 + mu]);
+                cfmac(yt, ya[mu], gT[mu]);
+            }
+            gR0c = cadd(gR0c, gr0);
+            gR1c = cadd(gR1c, gr1);
+            // jet-level sums: [sum gA0V (4) | sum gA0S | sum gT (4) | sum gU | sum conj(y) gT | sum conj(ghat(y)) gU (4)]
+            double r[30];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) {
+                r[2 * mu] = gAa[mu].x; r[2 * mu + 1] = gAa[mu].y;
+                r[10 + 2 * mu] = gT[mu].x; r[11 + 2 * mu] = gT[mu].y;
+                const cplx t = cmulc(ghy[mu], gU);
+                r[22 + 2 * mu] = t.x; r[23 + 2 * mu] = t.y;
+            }
+            r[8] = gAa[4].x; r[9] = gAa[4].y;
+            r[18] = gU.x; r[19] = gU.y;
+            r[20] = yt.x; r[21] = yt.y;
+#pragma unroll
+            for (int t = 0; t < 30; ++t) r[t] = warp_allsum(r[t]);
+            cplx gSS = cmulc(R0c, cmake(r[8], r[9]));
+            gSS = cadd(gSS, cmake(r[20], r[21]));
+            const cplx gSVY = cneg(cmake(r[18], r[19]));
+            cplx gSa = gSS;
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) {
+                cplx gSVm = cmulc(R0c, cmake(r[2 * mu], r[2 * mu + 1]));
+                gSVm = cadd(gSVm, cmake(r[22 + 2 * mu], r[23 + 2 * mu]));
+                const cplx gSSYm = cneg(cmake(r[10 + 2 * mu], r[11 + 2 * mu]));
+                cfmac(gSa, ya[mu], gSSYm);
+                cplx gv = gSVm;
+                cfmac(gv, ghy[mu], gSVY);
+                gV[mu] = cadd(gV[mu], gv);
+                cplx g = cmulc(SS, gT[mu]);
+                cfmac(g, ghsv[mu], gU);
+                cfmac(g, Sa, gSSYm);
+                cfmac(g, ghv[mu], gSVY);
+                gy[mu] = g;
+            }
+            gS = cadd(gS, gSa);
+        } else {
             double pa[4] = {0, 0, 0, 0};
             cplx ya[4] = {czero(), czero(), czero(), czero()};
             if (live) {
@@ -673,6 +798,13 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
 // ------------------------------------------------------------------------------------------------------------
 static int pick_ks(int K) { return K <= 12 ? 3 : (K <= 20 ? 5 : (K <= 32 ? 8 : -1)); }
 
+// The decoder levels use the O(N) closed form unless LGAE_DEC_PAIRLOOP=1 asks for the reference-shaped O(N^2) neighbour
+// loop (kept for A/B checks of the closed form).
+static bool dec_pair_loop() {
+    static const bool v = [] { const char* e = getenv("LGAE_DEC_PAIRLOOP"); return e && e[0] == '1'; }();
+    return v;
+}
+
 template <bool ENC, int NT, int KS, bool PRE>
 static int launch_level_fwd(const LevelArgs& a, cudaStream_t st) {
     const LevelSmem L = level_smem(ENC, ENC && !PRE, a.N, a.C, a.Cout, KS);
@@ -692,15 +824,19 @@ static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
     const LevelBwdSmem L = level_bwd_smem(ENC, a.N, a.C, a.Cout);
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
-    if (a.C <= 4) {
-        auto kern = level_bwd_kernel<ENC, 128, 3>;
-        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
-        kern<<<grid, 32 * a.C, bytes, st>>>(a);
-    } else {
-        auto kern = level_bwd_kernel<ENC, 256, 1>;
-        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
-        kern<<<grid, 32 * a.C, bytes, st>>>(a);
+    const bool cf = !ENC && !dec_pair_loop();
+#define LGAE_LAUNCH(MAXT, MINB, CFV)                                          \
+    {                                                                         \
+        auto kern = level_bwd_kernel<ENC, MAXT, MINB, CFV>;                   \
+        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;        \
+        kern<<<grid, 32 * a.C, bytes, st>>>(a);                               \
     }
+    if (a.C <= 4) {
+        if (cf) LGAE_LAUNCH(128, 3, true) else LGAE_LAUNCH(128, 3, false)
+    } else {
+        if (cf) LGAE_LAUNCH(256, 1, true) else LGAE_LAUNCH(256, 1, false)
+    }
+#undef LGAE_LAUNCH
     count_launch();
     return check_launch("level_bwd");
 }
@@ -713,7 +849,7 @@ int level_bwd_grid(int batch) {
 
 static int dispatch_level_fwd(const LevelArgs& a, bool enc, cudaStream_t st) {
     if (a.C < 1 || a.C > LGAE_MAX_CHANNELS || a.Cout < 1 || a.Cout > LGAE_MAX_CHANNELS) return LGAE_E_UNSUPPORTED;
-    if (!enc) return launch_level_fwd<false, 1, 3, false>(a, st);
+    if (!enc) return dec_pair_loop() ? launch_level_fwd<false, 1, 3, false>(a, st) : launch_level_fwd<false, 1, 3, true>(a, st);
     if (a.r_save) return launch_level_fwd<true, 1, 3, true>(a, st);   // radial weights precomputed (N <= 32)
     const int nt = (4 * a.C + 7) / 8, ks = pick_ks(a.K);
     if (ks < 0) return LGAE_E_UNSUPPORTED;
