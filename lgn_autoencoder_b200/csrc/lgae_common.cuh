@@ -106,6 +106,36 @@ LGAE_DEV void dmma(double& c0, double& c1, double a, double b) {
                  : "d"(a), "d"(b));
 }
 
+// ---- TMA 1-D bulk copies global -> shared, completion signalled on an mbarrier -------------------------------------
+// (cp.async.bulk: one elected thread issues the copy of a whole contiguous record -- a jet's node features --, every
+// thread then waits on the barrier's phase parity; addresses and sizes must be multiples of 16 bytes.)
+LGAE_DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+LGAE_DEV void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+LGAE_DEV void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+LGAE_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+LGAE_DEV void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LGAE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LGAE_DONE;\n"
+        "bra LGAE_WAIT;\n"
+        "LGAE_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 LGAE_DEV double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -173,18 +173,22 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
     double* Rs = smem + L.big;
     cplx* cat_s = reinterpret_cast<cplx*>(smem + L.big);
 
-    // ---- stage the jet ----
+    // ---- stage the jet: momenta and node features by TMA bulk copies, weights by the threads meanwhile ----
+    __shared__ uint64_t mbar;
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
     {
         const int np = ENC ? 4 * N : 8 * N;
         const double* src = a.p + (int64_t)b * np;
-        for (int t = tid; t < np; t += blockDim.x) p_s[t] = src[t];
-        if (ENC)
+        if (tid == 0) {
+            mbar_expect_tx(&mbar, (unsigned)((np + 10 * N * C) * sizeof(double)));
+            bulk_g2s(p_s, src, np * sizeof(double), &mbar);
+            bulk_g2s(smem + L.S, a.s_in + (int64_t)b * N * C * 2, 2 * N * C * sizeof(double), &mbar);
+            bulk_g2s(smem + L.V, a.v_in + (int64_t)b * N * C * 8, 8 * N * C * sizeof(double), &mbar);
+        }
+        if (ENC && !PRE)
             for (int t = tid; t < N; t += blockDim.x)
                 msk_s[t] = a.node_mask ? a.node_mask[(int64_t)b * N + t] : (src[4 * t] != 0.0);
-        const double* ss = a.s_in + (int64_t)b * N * C * 2;
-        for (int t = tid; t < 2 * N * C; t += blockDim.x) (smem + L.S)[t] = ss[t];
-        const double* vs = a.v_in + (int64_t)b * N * C * 8;
-        for (int t = tid; t < 8 * N * C; t += blockDim.x) (smem + L.V)[t] = vs[t];
         const int nm = Cout * 5 * C;
         for (int t = tid; t < nm; t += blockDim.x) {
             m00_s[t] = cmake(a.theta[a.off_m00 + t], a.theta[a.off_m00 + nm + t]);
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
         R0c = cmake(b0, b0);
         R1c = cmake(b1, b1);
     }
+    mbar_wait(&mbar, 0);
     __syncthreads();
 
     const int i = i0 + lane;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
 // ------------------------------------------------------------------------------------------------------------
 // Shared-memory carve-up (in doubles) of the backward kernel.
 struct LevelBwdSmem {
-    int p, S, V, m00, m11, gm, gA, gy, gout;
+    int p, S, V, m00, m11, gm, gA, gy, gout, graw;
     int total;
 };
 __host__ __device__ inline LevelBwdSmem level_bwd_smem(bool enc, int N, int C, int Cout) {
@@ -386,6 +391,7 @@ __host__ __device__ inline LevelBwdSmem level_bwd_smem(bool enc, int N, int C, i
     s.gy = o; o += enc ? 0 : 2 * 4 * 32;
     o = (o + 3) & ~3;
     s.gout = o; o += 2 * Cout * 5 * 32;      // incoming gradients [(c'*5+comp)][32] complex
+    s.graw = o; o += 2 * N * Cout * 5;       // the same as they lie in HBM: g_s_pre (N,C') | g_v_out (N,C',4), bulk-copied
     s.total = o;
     return s;
 }
@@ -463,28 +469,22 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
 
     const int i = lane;
     const bool live = i < N;
+    __shared__ uint64_t mbar;
+    if (tid == 0) mbar_init(&mbar, 1);
+    unsigned phase = 0;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
-        // ---- 1a. stage the jet and the incoming gradients ----
+        // ---- 1a. stage the jet (TMA bulk copies) and the incoming gradients ----
         {
             const int np = ENC ? 4 * N : 8 * N;
-            const double* src = a.p + (int64_t)b * np;
-            for (int t = tid; t < np; t += blockDim.x) p_s[t] = src[t];
-            const double* ss = a.s_in + (int64_t)b * N * C * 2;
-            for (int t = tid; t < 2 * N * C; t += blockDim.x) (smem + L.S)[t] = ss[t];
-            const double* vs = a.v_in + (int64_t)b * N * C * 8;
-            for (int t = tid; t < 8 * N * C; t += blockDim.x) (smem + L.V)[t] = vs[t];
-            for (int it = tid; it < 32 * Cout * 5; it += blockDim.x) {
-                const int il = it & 31, r = it >> 5, co = r / 5, comp = r % 5;
-                cplx v = czero();
-                if (il < N) {
-                    if (comp == 0) {
-                        if (a.g_s_pre) v = reinterpret_cast<const cplx*>(a.g_s_pre)[(int64_t)(b * N + il) * Cout + co];
-                    } else {
-                        v = reinterpret_cast<const cplx*>(a.g_v_out)[((int64_t)(b * N + il) * Cout + co) * 4 + comp - 1];
-                    }
-                }
-                gout_s[r * 32 + il] = v;
+            if (tid == 0) {
+                const unsigned gs_bytes = a.g_s_pre ? 2 * N * Cout * sizeof(double) : 0u;
+                mbar_expect_tx(&mbar, (unsigned)((np + 10 * N * C + 8 * N * Cout) * sizeof(double)) + gs_bytes);
+                bulk_g2s(p_s, a.p + (int64_t)b * np, np * sizeof(double), &mbar);
+                bulk_g2s(smem + L.S, a.s_in + (int64_t)b * N * C * 2, 2 * N * C * sizeof(double), &mbar);
+                bulk_g2s(smem + L.V, a.v_in + (int64_t)b * N * C * 8, 8 * N * C * sizeof(double), &mbar);
+                if (a.g_s_pre) bulk_g2s(smem + L.graw, a.g_s_pre + (int64_t)b * N * Cout * 2, gs_bytes, &mbar);
+                bulk_g2s(smem + L.graw + 2 * N * Cout, a.g_v_out + (int64_t)b * N * Cout * 8, 8 * N * Cout * sizeof(double), &mbar);
             }
             if (!ENC)
                 for (int t = tid; t < 4 * 32; t += blockDim.x) gy_s[t] = czero();
@@ -495,6 +495,24 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
         if (ENC) {
             rnext = rsv[0];
             if (N > 1) rnext2 = rsv[(int64_t)C * 32];
+        }
+        mbar_wait(&mbar, phase);
+        phase ^= 1;
+        {   // incoming gradients -> [(c'*5+comp)][lane] (conflict-free for the per-lane reads of the mix adjoint)
+            const cplx* gs_raw = reinterpret_cast<const cplx*>(smem + L.graw);
+            const cplx* gv_raw = gs_raw + N * Cout;
+            for (int it = tid; it < 32 * Cout * 5; it += blockDim.x) {
+                const int il = it & 31, r = it >> 5, co = r / 5, comp = r % 5;
+                cplx v = czero();
+                if (il < N) {
+                    if (comp == 0) {
+                        if (a.g_s_pre) v = gs_raw[il * Cout + co];
+                    } else {
+                        v = gv_raw[(il * Cout + co) * 4 + comp - 1];
+                    }
+                }
+                gout_s[r * 32 + il] = v;
+            }
         }
         __syncthreads();
         // ---- 1b. adjoint of cat -> mix, block by block, in registers ----
