@@ -146,15 +146,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"], help="jets per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from lgn_autoencoder_b200 import _lib, fused
+    from lgn_autoencoder_b200 import _lib
     from lgn_autoencoder_b200.flop_model import level_flops, step_flops_per_jet
-    from lgn_autoencoder_b200.train import allreduce_gradients, training_step
+    from lgn_autoencoder_b200.train import FusedTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -169,17 +170,9 @@ def main():
 
     enc, dec = build_models(dev)
     host_p4 = synthetic_jets(B, N, seed=100 + rank).pin_memory()
-    dev_p4 = host_p4.to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
-
-    def step(p4):
-        for m in (enc, dec):
-            for p in m.parameters():
-                p.grad = None
-        loss, _, _ = training_step(enc, dec, p4, l1_lambda=CFG["l1_lambda"], l1_scale=1.0 / world)
-        loss.backward()
-        allreduce_gradients(enc, dec)
-        return loss
+    # The public training-step API: static buffers + one CUDA graph per step (lgn_autoencoder_b200/train.py)
+    fstep = FusedTrainStep(enc, dec, B, l1_lambda=CFG["l1_lambda"], l1_scale=1.0 / world, normalize=True, use_graph=not args.no_graph)
 
     def barrier():
         if world > 1:
@@ -204,69 +197,75 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t[0].item() / n, t[1].item() / n
 
-    for _ in range(W):
-        step(dev_p4)
-    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- per-kernel durations of one eager step (CUDA events around every launch of the library), rank 0 ----
+    fstep.load(host_p4)
     n0 = _lib.launch_count()
-    ms_step, _ = timed(lambda: step(dev_p4), K)
-    launches = (_lib.launch_count() - n0) / K
+    fstep._launch()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - n0          # kernels of one step (the CUDA graph replays exactly these)
+    kern = None
+    if rank == 0:
+        def eager():
+            flush.zero_()
+            fstep._launch()
+        eager()
+        kern = _lib.kernel_timings(eager, reps=5)
 
-    # end to end: pinned host jets -> device, loss back to the host, every step
+    # ---- value: jets resident in HBM ----
+    for _ in range(W):
+        fstep.run()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, _ = timed(fstep.run, K)
+
+    # ---- end to end: pinned host jets -> device, loss back to the host, every step ----
     def e2e_step():
-        p4 = host_p4.to(dev, non_blocking=True)
-        return step(p4).item()
+        return fstep.step(host_p4).item()
 
     for _ in range(2):
         e2e_step()
     ms_e2e, _ = timed(e2e_step, K)
     clocks = sampler.stop() if sampler else None
 
-    # ---- roofline of the dominant kernel: the encoder level adjoint (level 2: C=4 -> C'=4), timed alone ----
-    roofline = None
-    if rank == 0:
-        plan = enc._plan
-        theta, _ = enc._flat_params()
-        p4n, _ = fused.normalize_p4(dev_p4)
-        lat00, lat11, ws, sel = fused.encoder_forward_raw(plan, theta, p4n, None)
-        lvl = plan.n_levels - 1
-        C, Co = plan.channels[lvl], plan.channels[lvl + 1]
-        import ctypes as Ct
-        lib = _lib.load()
-        s_in = plan.ws_tensor(ws, B, 0, lvl, (B, N, C, 2))
-        v_in = plan.ws_tensor(ws, B, 1, lvl, (B, N, C, 4, 2))
-        sums = plan.ws_tensor(ws, B, 4, lvl, (B, N, C, 10, 2))
-        g_v = torch.randn(B, N, Co, 4, 2, dtype=torch.float64, device=dev)
-        g_s = torch.randn(B, N, Co, 2, dtype=torch.float64, device=dev)
-        rsv = plan.ws_tensor(ws, B, 7, lvl, (B, N, C, 32, 4))
-        grs = torch.empty_like(rsv)
-        gs_in, gv_in = torch.empty_like(s_in), torch.empty_like(v_in)
-        part = plan.partials(B, dev)
-        gth = torch.empty(plan.n_params, dtype=torch.float64, device=dev)
-        st = torch.cuda.current_stream().cuda_stream
+    # ---- roofline of the dominant kernel (largest share of the step), against the measured fp64 peak ----
+    roofline, table = None, None
+    if rank == 0 and kern:
+        Kb = 2 * CFG["num_basis_fn"]
+        ech, dch = CFG["enc_channels"], CFG["dec_channels"]
 
-        def kern():
-            _lib.check(lib.lgae_level_backward(Ct.byref(plan.desc), lvl, theta.data_ptr(), p4n.data_ptr(), None, B, s_in.data_ptr(),
-                                               v_in.data_ptr(), sums.data_ptr(), rsv.data_ptr(), grs.data_ptr(), g_s.data_ptr(), g_v.data_ptr(),
-                                               gs_in.data_ptr(), gv_in.data_ptr(), None, gth.data_ptr(), part.data_ptr(), st), "level_backward")
-        for _ in range(3):
-            kern()
-        reps = 10
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, b in evs:
-            flush.zero_()
-            a.record()
-            kern()
-            b.record()
-        torch.cuda.synchronize()
-        k_ms = sum(a.elapsed_time(b) for a, b in evs) / reps
-        lf = level_flops(N, C, Co, 2 * CFG["num_basis_fn"], True, 0, 0)
-        flops = 2.0 * B * (lf["radial"] + lf["edge"] + lf["aggregate"] + lf["power"] + lf["mix"])   # adjoint = 2 x forward
-        achieved = flops / (k_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "level_bwd_kernel<enc> (level 2, C=4)", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
-                    "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None, "kernel_ms": k_ms,
+        def lvl(chs, enc_side, l):
+            return level_flops(N, chs[l], chs[l + 1], Kb, enc_side, CFG["mlp_width"] * 2 * chs[l + 1], CFG["mlp_depth"])
+        # algorithmic flops per step of each kernel family (reference-faithful counts; adjoint = 2 x forward;
+        # the last level's MLP is dead in the backward pass)
+        fam = {k: 0.0 for k in ("level_fwd", "level_bwd", "radial_fwd", "radial_bwd", "mlp_fwd", "mlp_bwd")}
+        for chs, enc_side in ((ech, True), (dch, False)):
+            for l in range(len(chs) - 1):
+                f = lvl(chs, enc_side, l)
+                cg = f["edge"] + f["aggregate"] + f["power"] + f["mix"]
+                fam["level_fwd"] += B * cg
+                fam["level_bwd"] += 2 * B * cg
+                fam["radial_fwd"] += B * f["radial"]
+                fam["radial_bwd"] += 2 * B * f["radial"]
+                fam["mlp_fwd"] += B * f["mlp"]
+                if l < len(chs) - 2:
+                    fam["mlp_bwd"] += 2 * B * f["mlp"]
+        total_ms = sum(n * ms for n, ms in kern.values()) / 5.0
+        table = {}
+        for name, (n, ms) in sorted(kern.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+            per_step = n / 5.0
+            ent = {"launches_per_step": per_step, "ms_per_launch": ms, "share": per_step * ms / total_ms}
+            if name in fam:
+                ent["tflops"] = fam[name] / (per_step * ms * 1e-3) / 1e12
+                ent["frac_of_fp64_peak"] = ent["tflops"] / FP64_PEAK_TFLOPS
+            table[name] = ent
+        top = max((k for k in table if k in fam), key=lambda k: table[k]["share"])
+        t = table[top]
+        roofline = {"bound": "tensor", "kernel": top, "achieved": t["tflops"], "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": t["frac_of_fp64_peak"], "traffic": None, "kernel_ms": t["ms_per_launch"], "launches_per_step": t["launches_per_step"],
+                    "flops_per_launch": fam[top] / t["launches_per_step"],
                     "peak_source": "fp64 pipe: DMMA m8n8k4 37.1 TFLOP/s / DFMA 33.7 TFLOP/s measured with tools/fp64_peak.cu on this pool "
-                                   "(MEASURED_PEAKS.json holds no fp64 figure)",
-                    "flops_per_launch": flops}
+                                   "(profiles/fp64_peak_r01.json; MEASURED_PEAKS.json holds no fp64 figure)",
+                    "note": "achieved = reference-faithful algorithmic flops of this kernel family per step / its measured time per step "
+                            "(CUDA events around every launch, eager step, L2 flushed); `kernels` lists every kernel of the step"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -282,11 +281,13 @@ def main():
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": jets, "parallelism": f"dp{world}", "l2": "flushed (256 MB write) between timed steps",
+                       "step": "FusedTrainStep: one CUDA graph per step (normalize, encoder, decoder, chamfer, both adjoints, L1, grad all-reduce)"
+                               if not args.no_graph else "FusedTrainStep, eager launches",
                        "step_tflops": jets * fl / (ms_step * 1e-3) / 1e12, "step_frac_of_fp64_peak": jets * fl / (ms_step * 1e-3) / 1e12 / (FP64_PEAK_TFLOPS * world),
                        "mflop_per_jet": fl / 1e6},
             "e2e": {"value": jets / (ms_e2e * 1e-3), "unit": "jets/s", "h2d_bytes_per_step": host_p4.numel() * 8, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernels": table,
         }
         print(json.dumps(line))
     if world > 1:

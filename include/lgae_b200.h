@@ -85,6 +85,11 @@ const char* lgae_last_cuda_error(void);
 int lgae_device_sm_count(void);
 /* Number of kernels launched by this library since load (all entry points); bench.py reports the delta. */
 int64_t lgae_launch_count(void);
+/* Per-kernel timing for bench.py: while enabled every kernel launch of the library is bracketed by CUDA events on its
+ * stream (do not enable during CUDA-graph capture).  lgae_timing_report synchronises the device and writes one line
+ * "name launches total_ms" per kernel into buf; returns the number of lines or a negative error code. */
+void lgae_timing_enable(int32_t on);
+int lgae_timing_report(char* buf, int32_t cap);
 
 /* ---- workspace geometry -------------------------------------------------------------------------- */
 /* Doubles of per-batch workspace holding what the backward pass keeps (level inputs, neighbour sums,
@@ -141,8 +146,8 @@ int lgae_l1(const double* theta, int64_t n, double lambda, double* out_accumulat
 int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
                        const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
                        double* sums, double* r_save, double* s_pre, double* v_out, void* stream);
-/* gtheta (n_params) is overwritten: zero except for the parameters of this level.  g_r_scratch (encoder):
- * (B,N,C,32,4) scratch for dL/dR of the ordered pairs (workspace kind 8). */
+/* gtheta (n_params) is overwritten: zero except for the parameters of this level.  g_r_scratch (encoder): scratch of
+ * B*N*C*128 + B*16*ceil(N(N+1)/32) doubles: dL/dR of the ordered pairs, then the norms of the unordered pairs. */
 int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
                         const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
                         const double* sums, const double* r_save, double* g_r_scratch, const double* g_s_pre,

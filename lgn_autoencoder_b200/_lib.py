@@ -61,6 +61,8 @@ _PROTOS = {
     "lgae_last_cuda_error": (C.c_char_p, []),
     "lgae_device_sm_count": (C.c_int, []),
     "lgae_launch_count": (C.c_int64, []),
+    "lgae_timing_enable": (None, [C.c_int32]),
+    "lgae_timing_report": (C.c_int, [C.c_char_p, C.c_int32]),
     "lgae_workspace_doubles": (C.c_int64, [_D, C.c_int32]),
     "lgae_workspace_offset": (C.c_int64, [_D, C.c_int32, C.c_int32, C.c_int32]),
     "lgae_partials_doubles": (C.c_int64, [_D, C.c_int32]),
@@ -116,6 +118,26 @@ def check(rc: int, what: str = ""):
 def ptr(t):
     """Device pointer of a (contiguous) tensor, or NULL."""
     return None if t is None else t.data_ptr()
+
+
+def kernel_timings(fn, reps: int = 1):
+    """Run fn() `reps` times with per-kernel event timing on; returns {kernel name: (launches, mean ms per launch)}."""
+    lib = load()
+    lib.lgae_timing_enable(1)
+    try:
+        for _ in range(reps):
+            fn()
+        buf = C.create_string_buffer(1 << 16)
+        n = lib.lgae_timing_report(buf, len(buf))
+        if n < 0:
+            check(n, "timing_report")
+    finally:
+        lib.lgae_timing_enable(0)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(" ", 2)
+        out[name] = (int(n), float(ms) / int(n))
+    return out
 
 
 def launch_count() -> int:

@@ -4,7 +4,9 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <unordered_map>
+#include <vector>
 
 #include "lgae_common.cuh"
 
@@ -17,9 +19,10 @@ int run_level_bwd(const LgaeModelDesc* d, int level, const double* theta, const 
                   const double* s_in, const double* v_in, const double* sums, const double* r_save, double* g_r, const double* g_s_pre,
                   const double* g_v_out, double* g_s_in, double* g_v_in, double* g_y, PartPlan* plan, cudaStream_t st);
 int run_radial_fwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
-                   double* r, cudaStream_t st);
+                   double* r, double* nrm, cudaStream_t st);
 int run_radial_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
-                   const double* g_r, PartPlan* plan, cudaStream_t st);
+                   const double* g_r, const double* nrm, PartPlan* plan, cudaStream_t st);
+int64_t radial_nrm_stride(int n);
 int radial_grid();
 int64_t radial_part_width(const LgaeModelDesc* d, int level);
 int level_bwd_grid(int batch);
@@ -55,6 +58,29 @@ static char g_cuda_error[512] = "";
 static int g_sm_count = 0;
 
 void count_launch(int n) { g_launches += n; }
+
+// ---- optional per-kernel timing ---------------------------------------------------------------------------------
+struct TimedLaunch { const char* name; cudaEvent_t a, b; };
+static std::mutex g_timing_mu;
+static bool g_timing_on = false;
+static std::vector<TimedLaunch> g_timed;
+
+LaunchScope::LaunchScope(const char* name_, cudaStream_t st_) : name(name_), st(st_), ev0(nullptr) {
+    if (!g_timing_on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaEventRecord(e, st);
+    ev0 = (void*)e;
+}
+LaunchScope::~LaunchScope() {
+    g_launches += 1;
+    if (!ev0) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); cudaEventDestroy((cudaEvent_t)ev0); return; }
+    cudaEventRecord(e, st);
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    g_timed.push_back({name, (cudaEvent_t)ev0, e});
+}
 int check_launch(const char* what) {
     const cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) return LGAE_OK;
@@ -86,7 +112,7 @@ int sm_count() {
 struct Layout {
     int64_t S[LGAE_MAX_LEVELS + 1], V[LGAE_MAX_LEVELS + 1];
     int64_t sums[LGAE_MAX_LEVELS], spre[LGAE_MAX_LEVELS], acts[LGAE_MAX_LEVELS], rsave[LGAE_MAX_LEVELS], wpack[LGAE_MAX_LEVELS];
-    int64_t y, mass, gS[2], gV[2], gSpre, gy, gr, total;
+    int64_t y, mass, gS[2], gV[2], gSpre, gy, gr, nrm, total;
 };
 static int max_channels(const LgaeModelDesc* d) {
     int m = 1;
@@ -118,6 +144,8 @@ static Layout layout(const LgaeModelDesc* d, int64_t B) {
     L.gy = take(nodes * 8);
     // encoder, N <= 32: dL/dR of the ordered pairs of the level being differentiated (reused by every level)
     L.gr = (!d->is_decoder && d->n_particles <= 32) ? take(nodes * cm * 128) : -1;
+    // encoder, N <= 32: norms of the unordered pairs (NaN = masked), written by the radial forward
+    L.nrm = (!d->is_decoder && d->n_particles <= 32) ? take(B * radial_nrm_stride(d->n_particles)) : -1;
     L.total = o;
     return L;
 }
@@ -163,6 +191,39 @@ int lgae_device_sm_count(void) {
 }
 int64_t lgae_launch_count(void) { return g_launches.load(); }
 
+void lgae_timing_enable(int32_t on) {
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    g_timing_on = on != 0;
+}
+// Synchronises the device, then writes one line per kernel name "name count total_ms\n" into buf (NUL-terminated, at most
+// cap bytes) and clears the records.  Returns the number of distinct names, or a negative error code.
+int lgae_timing_report(char* buf, int32_t cap) {
+    if (!buf || cap < 1) return LGAE_E_BADARG;
+    if (cudaDeviceSynchronize() != cudaSuccess) return check_launch("timing sync");
+    std::lock_guard<std::mutex> lock(g_timing_mu);
+    std::vector<std::string> order;
+    std::unordered_map<std::string, std::pair<int, double>> agg;
+    for (auto& t : g_timed) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+        auto it = agg.find(t.name);
+        if (it == agg.end()) { order.push_back(t.name); agg[t.name] = {1, (double)ms}; }
+        else { it->second.first += 1; it->second.second += ms; }
+    }
+    g_timed.clear();
+    std::string out;
+    for (auto& n : order) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        out += line;
+    }
+    if ((int)out.size() + 1 > cap) return LGAE_E_BADARG;
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)order.size();
+}
+
 int64_t lgae_workspace_doubles(const LgaeModelDesc* d, int32_t batch) {
     if (check_desc(d) != LGAE_OK || batch < 0) return -1;
     return layout(d, batch).total;
@@ -205,7 +266,7 @@ int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
     LGAE_TRY(run_enc_input(d, theta, p4, batch, ws + L.mass, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
-        if (L.rsave[l] >= 0) LGAE_TRY(run_radial_fwd(d, l, theta, p4, node_mask, batch, ws + L.rsave[l], st));
+        if (L.rsave[l] >= 0) LGAE_TRY(run_radial_fwd(d, l, theta, p4, node_mask, batch, ws + L.rsave[l], ws + L.nrm, st));
         LGAE_TRY(run_level_fwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l],
                                L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, ws + L.spre[l], ws + L.V[l + 1], st));
         if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
@@ -243,7 +304,7 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
             if (L.rsave[l] < 0 || L.gr < 0) return LGAE_E_UNSUPPORTED;
             LGAE_TRY(run_level_bwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], ws + L.rsave[l], ws + L.gr,
                                    g_spre, ws + L.gV[cur], ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], nullptr, &plan, st));
-            LGAE_TRY(run_radial_bwd(d, l, theta, p4, node_mask, batch, ws + L.gr, &plan, st));
+            LGAE_TRY(run_radial_bwd(d, l, theta, p4, node_mask, batch, ws + L.gr, ws + L.nrm, &plan, st));
             cur ^= 1;
             gs_zero = false;
         }
@@ -333,7 +394,7 @@ int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* thet
     LGAE_TRY(check_desc(d));
     if (!theta || !p_or_y || !s_in || !v_in || !sums || !s_pre || !v_out || batch < 0) return LGAE_E_BADARG;
     if (!d->is_decoder && d->n_particles <= 32 && r_save)
-        LGAE_TRY(run_radial_fwd(d, level, theta, p_or_y, node_mask, batch, r_save, (cudaStream_t)stream));
+        LGAE_TRY(run_radial_fwd(d, level, theta, p_or_y, node_mask, batch, r_save, nullptr, (cudaStream_t)stream));
     return run_level_fwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, s_pre, v_out, (cudaStream_t)stream);
 }
 int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y, const uint8_t* node_mask,
@@ -348,7 +409,13 @@ int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* the
     plan.base = partials;
     LGAE_TRY(run_level_bwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, g_r_scratch, g_s_pre, g_v_out, g_s_in,
                            g_v_in, g_y_accumulate, &plan, (cudaStream_t)stream));
-    if (!d->is_decoder) LGAE_TRY(run_radial_bwd(d, level, theta, p_or_y, node_mask, batch, g_r_scratch, &plan, (cudaStream_t)stream));
+    if (!d->is_decoder) {
+        // the pair norms live behind the dL/dR scratch: g_r_scratch holds B*N*C*128 + B*nrm_stride doubles
+        double* nrm = g_r_scratch + (int64_t)batch * d->n_particles * d->channels[level] * 128;
+        double* r_tmp = const_cast<double*>(r_save);
+        LGAE_TRY(run_radial_fwd(d, level, theta, p_or_y, node_mask, batch, r_tmp, nrm, (cudaStream_t)stream));   // refreshes R, writes the norms
+        LGAE_TRY(run_radial_bwd(d, level, theta, p_or_y, node_mask, batch, g_r_scratch, nrm, &plan, (cudaStream_t)stream));
+    }
     return run_reduce_plan(&plan, d->n_params, gtheta, (cudaStream_t)stream);
 }
 int64_t lgae_mlp_pack_doubles(const LgaeModelDesc* d, int32_t level) {

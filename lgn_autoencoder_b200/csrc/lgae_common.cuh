@@ -249,6 +249,15 @@ struct PartPlan {
 
 // ---- host side ------------------------------------------------------------------------------------
 void count_launch(int n = 1);
+// Scope around one kernel launch: counts it and, when per-kernel timing is enabled (lgae_timing_enable), brackets it with
+// CUDA events on the launch stream so that bench.py can report measured per-kernel durations without a profiler.
+struct LaunchScope {
+    const char* name;
+    cudaStream_t st;
+    void* ev0;
+    LaunchScope(const char* name_, cudaStream_t st_);
+    ~LaunchScope();
+};
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel (and again only if a larger size is needed).
 int ensure_smem(const void* kernel, size_t bytes);
 int check_launch(const char* what);

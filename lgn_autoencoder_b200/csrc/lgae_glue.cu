@@ -648,8 +648,8 @@ __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, cons
 // ------------------------------------------------------------------------------------------------------------
 int run_enc_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* mass, double* S, double* V, cudaStream_t st) {
     const int64_t nodes = (int64_t)B * d->n_particles;
+    LaunchScope ls_("enc_input", st);
     enc_input_kernel<<<(unsigned)((nodes + 127) / 128), 128, 0, st>>>(theta, d->off_in00, d->off_in11, p4, nodes, d->channels[0], mass, S, V);
-    count_launch();
     return check_launch("enc_input");
 }
 int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* mass, int B, const double* gS, const double* gV,
@@ -659,8 +659,8 @@ int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* ma
     const int64_t w = 4 * C, off = plan->block(grid, w);   // row: [in00 (2C) | in11 (2C)]
     if (int rc = plan->seg(d->off_in00, off, w, 0, 2 * C, grid)) return rc;
     if (int rc = plan->seg(d->off_in11, off, w, 2 * C, 2 * C, grid)) return rc;
+    LaunchScope ls_("enc_input_bwd", st);
     enc_input_bwd_kernel<<<grid, 256, 0, st>>>(0, 2 * C, p4, mass, nodes, C, gS, gV, plan->base + off, w);
-    count_launch();
     return check_launch("enc_input_bwd");
 }
 
@@ -680,8 +680,8 @@ int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const dou
     const size_t bytes = (size_t)rows * (a.tau_s + 4 * a.tau_v) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)enc_latent_kernel, bytes)) return rc;
+    LaunchScope ls_("enc_latent", st);
     enc_latent_kernel<<<B, 256, bytes, st>>>(a);
-    count_launch();
     return check_launch("enc_latent");
 }
 int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const int32_t* sel,
@@ -700,8 +700,8 @@ int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const
     const size_t bytes = ((size_t)rows * (a.tau_s + 4 * a.tau_v) + (size_t)(a.tau_s + a.tau_v) * cin) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)enc_latent_bwd_kernel, bytes)) return rc;
+    LaunchScope ls_("enc_latent_bwd", st);
     enc_latent_bwd_kernel<<<sm_count(), 256, bytes, st>>>(a);
-    count_launch();
     return check_launch("enc_latent_bwd");
 }
 
@@ -715,8 +715,8 @@ static DecInArgs dec_in_args(const LgaeModelDesc* d, const double* theta, int B,
 int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, double* S, double* V, cudaStream_t st) {
     DecInArgs a = dec_in_args(d, theta, B, lat11, y, S, V);
     const size_t bytes = (size_t)a.tau * 4 * sizeof(cplx);
+    LaunchScope ls_("dec_input", st);
     dec_input_kernel<<<B, 128, bytes, st>>>(a);
-    count_launch();
     return check_launch("dec_input");
 }
 int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, const double* gS, const double* gV,
@@ -735,14 +735,14 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
     const size_t bytes = ((size_t)a.tau * 4 + (size_t)a.N * 4 + (size_t)a.N * a.tau + 2 * a.C) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)dec_input_bwd_kernel, bytes)) return rc;
+    LaunchScope ls_("dec_input_bwd", st);
     dec_input_bwd_kernel<<<sm_count(), 128, bytes, st>>>(a);
-    count_launch();
     return check_launch("dec_input_bwd");
 }
 int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st) {
     const int64_t nodes = (int64_t)B * d->n_particles;
+    LaunchScope ls_("dec_output", st);
     dec_output_kernel<<<(unsigned)((nodes + 127) / 128), 128, 0, st>>>(theta, d->off_out00, d->off_out11, B, d->n_particles, d->channels[d->n_levels], S, V, recon, gen00);
-    count_launch();
     return check_launch("dec_output");
 }
 int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const double* g_recon,
@@ -751,9 +751,9 @@ int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const
     const int64_t w = 4 * C, off = plan->block(grid, w);
     if (int rc = plan->seg(d->off_out00, off, w, 0, 2 * C, grid)) return rc;
     if (int rc = plan->seg(d->off_out11, off, w, 2 * C, 2 * C, grid)) return rc;
+    LaunchScope ls_("dec_output_bwd", st);
     dec_output_bwd_kernel<<<grid, 256, 0, st>>>(theta, d->off_out00, d->off_out11, B, d->n_particles, C, S, V, g_recon,
                                                  g_gen00, gS, gV, plan->base + off, w);
-    count_launch();
     return check_launch("dec_output_bwd");
 }
 // gtheta = 0, then every segment of the plan is reduced over its rows.
@@ -764,8 +764,8 @@ int run_reduce_plan(const PartPlan* plan, int64_t n_params, double* gtheta, cuda
     for (int i = 0; i < plan->table.n; ++i) maxlen = plan->table.s[i].len > maxlen ? plan->table.s[i].len : maxlen;
     int gx = (maxlen + 31) / 32;
     if (gx > 1024) gx = 1024;
+    LaunchScope ls_("reduce_partials", st);
     reduce_segs_kernel<<<dim3(gx, plan->table.n), dim3(32, 8), 0, st>>>(plan->table, plan->base, gtheta);
-    count_launch();
     return check_launch("reduce_partials");
 }
 // Doubles of partial rows used by the glue adjoints of a model.
@@ -781,25 +781,25 @@ int run_chamfer(const double* recon, const double* target, int B, int N, int M, 
     const size_t bytes = (size_t)(4 * N + 4 * M + N + M) * sizeof(double) + (size_t)(N + M) * sizeof(int);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)chamfer_kernel, bytes)) return rc;
+    LaunchScope ls_("chamfer", st);
     chamfer_kernel<<<B, 128, bytes, st>>>(recon, target, B, N, M, jet_loss, g_loss, g_recon);
-    count_launch();
     int rc = check_launch("chamfer");
     if (rc) return rc;
     if (loss) {
+        LaunchScope ls_("chamfer_sum", st);
         sum_kernel<<<1, 1024, 0, st>>>(jet_loss, B, 1.0, loss, 0);
-        count_launch();
         rc = check_launch("chamfer_sum");
     }
     return rc;
 }
 int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st) {
+    LaunchScope ls_("normalize_p4", st);
     normalize_kernel<<<B, 128, 0, st>>>(p4, N, out, factor);
-    count_launch();
     return check_launch("normalize_p4");
 }
 int run_l1(const double* theta, int64_t n, double lambda, double* out, double* gtheta, cudaStream_t st) {
+    LaunchScope ls_("l1", st);
     l1_kernel<<<1, 1024, 0, st>>>(theta, n, lambda, out, gtheta);
-    count_launch();
     return check_launch("l1");
 }
 

@@ -831,8 +831,8 @@ static int launch_level_fwd(const LevelArgs& a, cudaStream_t st) {
     auto kern = level_fwd_kernel<ENC, NT, KS, PRE>;
     if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
     const int nib = (a.N + 31) / 32;
+    LaunchScope ls_("level_fwd", st);
     kern<<<a.B * nib, 32 * a.C, bytes, st>>>(a);
-    count_launch();
     return check_launch("level_fwd");
 }
 
@@ -843,6 +843,7 @@ static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
     const size_t bytes = (size_t)L.total * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
     const bool cf = !ENC && !dec_pair_loop();
+    LaunchScope ls_("level_bwd", st);
 #define LGAE_LAUNCH(MAXT, MINB, CFV)                                          \
     {                                                                         \
         auto kern = level_bwd_kernel<ENC, MAXT, MINB, CFV>;                   \
@@ -855,7 +856,6 @@ static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
         if (cf) LGAE_LAUNCH(256, 1, true) else LGAE_LAUNCH(256, 1, false)
     }
 #undef LGAE_LAUNCH
-    count_launch();
     return check_launch("level_bwd");
 }
 

@@ -395,8 +395,8 @@ static int launch_mlp(MlpArgs& a, bool bwd, cudaStream_t st) {
         if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
         const int64_t ngroups = (a.rows + 7) / 8;
         const int grid = (int)(ngroups < sm_count() ? ngroups : sm_count());
+        LaunchScope ls_("mlp_fwd", st);
         kern<<<grid, MLP_THREADS, bytes, st>>>(a);
-        count_launch();
         return check_launch("mlp_fwd");
     }
     const size_t bytes = (size_t)(wtotal + 2 * MLP_BWD_ROWS * (8 * NTW + 4) + (MLP_THREADS / 32) * 8 * NTW) * sizeof(double);
@@ -406,8 +406,8 @@ static int launch_mlp(MlpArgs& a, bool bwd, cudaStream_t st) {
     const int grid = mlp_bwd_grid();
     const int64_t per = (a.rows + grid - 1) / grid;
     a.rows_per_cta = ((per + 7) / 8) * 8;
+    LaunchScope ls_("mlp_bwd", st);
     kern<<<grid, MLP_THREADS, bytes, st>>>(a);
-    count_launch();
     return check_launch("mlp_bwd");
 }
 
@@ -428,8 +428,8 @@ int run_mlp_pack(const LgaeModelDesc* d, const double* theta, double* out, const
         p.out_off[l] = out_off[l];
         for (int i = 0; i < p.n_lin; ++i) p.off_w[l][i] = d->off_mlp_w[l][i];
     }
+    LaunchScope ls_("mlp_pack", st);
     mlp_pack_kernel<<<dim3(p.n_lin, 2, d->n_levels), 256, 0, st>>>(p);
-    count_launch();
     return check_launch("mlp_pack");
 }
 

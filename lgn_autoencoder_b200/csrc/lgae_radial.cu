@@ -8,8 +8,8 @@
 // (i,j) and (j,i) entries of the (B, N_j, C, 32_i, 4) tensor the level kernels stream through, and the adjoint first
 // adds the two incoming gradients of a pair.
 //
-// Work decomposition: a warp owns groups of 8 pairs (the M / K dimension of the MMA tiles); warps stride over all
-// groups of all jets, so the grid is sized by the machine (CTAs per SM x 148), not by the batch.
+// Work decomposition: a warp owns a contiguous range of 16-pair units (two groups of 8 pairs = the M / K dimension of
+// the MMA tiles) of the whole batch, so the grid is sized by the machine (CTAs per SM x 148), not by the batch.
 #include <cstring>
 
 #include "lgae_common.cuh"
@@ -22,6 +22,7 @@ struct RadialArgs {
     const double* p4;          // (B,N,4) real Cartesian
     const uint8_t* node_mask;  // (B,N) or nullptr (=> p4[...,0] != 0)
     double* r;                 // forward out: (B,N_j,C,32_i,4) = (R0.re, R0.im, R1.re, R1.im)
+    double* nrm;               // forward out (optional) / adjoint in: (B, NPS) pair norms, NaN = masked edge or padding
     const double* g_r;         // adjoint in: same layout, dL/dR of the ORDERED pairs
     double* part;              // adjoint out: (gridDim.x, part_stride) rows of parameter-gradient partials
     int64_t part_stride;
@@ -54,14 +55,29 @@ LGAE_DEV void build_pair_table(int N, unsigned char* ti, unsigned char* tj) {
         }
 }
 
+// Reciprocal of x in [1, inf) to ~1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps, no special cases (the argument
+// 1 + (c n)^2 + 1e-16 is always finite and >= 1 for finite inputs).
+LGAE_DEV double rcp_ge1(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+constexpr int RAD_UNIT = 16;   // pairs per work unit (two MMA groups of 8)
+
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
+// A warp owns a contiguous range of units; lanes 0..15 evaluate the norm of one pair each (no redundancy), the two
+// MMA groups of the unit pick theirs up by shuffle.  Also writes nrm (B, NPS): n_ij, or NaN where the edge is masked,
+// which is all the adjoint needs to re-evaluate the basis functions.
 template <int NT, int KS>
-__global__ void __launch_bounds__(256, 2) radial_fwd_kernel(const RadialArgs a) {
+__global__ void __launch_bounds__(128, 4) radial_fwd_kernel(const RadialArgs a) {
     constexpr int KP = 4 * KS;
-    constexpr int U = 2;   // groups in flight per warp (independent MMA chains)
-    __shared__ unsigned char ti[RAD_MAXP], tj[RAD_MAXP];
+    __shared__ unsigned char ti[RAD_MAXP + RAD_UNIT], tj[RAD_MAXP + RAD_UNIT];
     __shared__ double abc_s[3 * KP];
     const int N = a.N, C = a.C, K = a.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -83,33 +99,35 @@ __global__ void __launch_bounds__(256, 2) radial_fwd_kernel(const RadialArgs a) 
         bf[nt][1] = rad_bias(a, 8 * nt + 2 * q + 1);
     }
     __syncthreads();
-    const int NP = N * (N + 1) / 2, NG = (NP + 7) / 8;
-    const int64_t total = (int64_t)a.B * NG;
-    const int64_t stride = (int64_t)gridDim.x * nwarps * U;
-    for (int64_t grp0 = ((int64_t)blockIdx.x * nwarps + warp) * U; grp0 < total; grp0 += stride) {
-        double acc[U][NT][2], n[U];
-        bool m[U], valid[U];
-        int bi[U], ii[U], jj[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t grp = grp0 + u;
-            const int b = (int)(grp / NG), pid = (int)(grp % NG) * 8 + g;
-            valid[u] = grp < total && pid < NP;
-            bi[u] = b;
-            ii[u] = valid[u] ? ti[pid] : 0;
-            jj[u] = valid[u] ? tj[pid] : 0;
-            n[u] = 0.0;
-            m[u] = false;
-            if (valid[u]) {
-                const double* pb = a.p4 + (int64_t)b * N * 4;
-                const double4 pi = *reinterpret_cast<const double4*>(pb + 4 * ii[u]);
-                const double4 pj = *reinterpret_cast<const double4*>(pb + 4 * jj[u]);
+    const int NP = N * (N + 1) / 2, NU = (NP + RAD_UNIT - 1) / RAD_UNIT, NPS = NU * RAD_UNIT;
+    const int total = a.B * NU, twarps = gridDim.x * nwarps;
+    const int per = (total + twarps - 1) / twarps;
+    const int u_begin = (blockIdx.x * nwarps + warp) * per, u_end = u_begin + per < total ? u_begin + per : total;
+    for (int unit = u_begin; unit < u_end; ++unit) {
+        const int b = unit / NU, p0 = (unit - b * NU) * RAD_UNIT;
+        const double* pb = a.p4 + (int64_t)b * N * 4;
+        double n = 0.0;
+        int m = 0;
+        {
+            const int pid = p0 + (lane & 15);
+            if (pid < NP) {
+                const int i = ti[pid], j = tj[pid];
+                const double4 pi = *reinterpret_cast<const double4*>(pb + 4 * i);
+                const double4 pj = *reinterpret_cast<const double4*>(pb + 4 * j);
                 const double vi[4] = {pi.x, pi.y, pi.z, pi.w}, vj[4] = {pj.x, pj.y, pj.z, pj.w};
-                n[u] = rad_pair_norm(vi, vj);
-                const bool mi = a.node_mask ? a.node_mask[(int64_t)b * N + ii[u]] != 0 : pi.x != 0.0;
-                const bool mj = a.node_mask ? a.node_mask[(int64_t)b * N + jj[u]] != 0 : pj.x != 0.0;
-                m[u] = mi && mj && n[u] != 0.0;
+                n = rad_pair_norm(vi, vj);
+                const bool mi = a.node_mask ? a.node_mask[(int64_t)b * N + i] != 0 : pi.x != 0.0;
+                const bool mj = a.node_mask ? a.node_mask[(int64_t)b * N + j] != 0 : pj.x != 0.0;
+                m = (mi && mj && n != 0.0) ? 1 : 0;
             }
+            if (lane < 16 && a.nrm) a.nrm[(int64_t)b * NPS + pid] = m ? n : __longlong_as_double(0x7ff8000000000000LL);
+        }
+        double acc[2][NT][2], nu[2];
+        int mu[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            nu[u] = __shfl_sync(0xffffffffu, n, 8 * u + g);
+            mu[u] = __shfl_sync(0xffffffffu, m, 8 * u + g);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) { acc[u][nt][0] = bf[nt][0]; acc[u][nt][1] = bf[nt][1]; }
         }
@@ -118,25 +136,27 @@ __global__ void __launch_bounds__(256, 2) radial_fwd_kernel(const RadialArgs a) 
             const int k = 4 * s + q;
             const double ak = abc_s[k], bk = abc_s[KP + k], ck = abc_s[2 * KP + k];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double cn = ck * n[u];
-                const double phi = m[u] ? fma(bk, 1.0 / (1.0 + cn * cn + 1e-16), ak) : 0.0;
+            for (int u = 0; u < 2; ++u) {
+                const double cn = ck * nu[u];
+                const double phi = mu[u] ? fma(bk, rcp_ge1(1.0 + cn * cn + 1e-16), ak) : 0.0;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) dmma(acc[u][nt][0], acc[u][nt][1], phi, wf[s][nt]);
             }
         }
+        double* rb = a.r + (int64_t)b * N * C * 128;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (!valid[u]) continue;
-            double* rb = a.r + (int64_t)bi[u] * N * C * 128;
+        for (int u = 0; u < 2; ++u) {
+            const int pid = p0 + 8 * u + g;
+            if (pid >= NP) continue;
+            const int i = ti[pid], j = tj[pid];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
                 const int col = 8 * nt + 2 * q;
                 if (col < 4 * C) {
                     const int l = col >= 2 * C ? 1 : 0, cc = (col - l * 2 * C) >> 1;
                     const double2 v = make_double2(acc[u][nt][0], acc[u][nt][1]);
-                    *reinterpret_cast<double2*>(rb + ((int64_t)(jj[u] * C + cc) * 32 + ii[u]) * 4 + 2 * l) = v;
-                    if (ii[u] != jj[u]) *reinterpret_cast<double2*>(rb + ((int64_t)(ii[u] * C + cc) * 32 + jj[u]) * 4 + 2 * l) = v;
+                    *reinterpret_cast<double2*>(rb + ((int64_t)(j * C + cc) * 32 + i) * 4 + 2 * l) = v;
+                    if (i != j) *reinterpret_cast<double2*>(rb + ((int64_t)(i * C + cc) * 32 + j) * 4 + 2 * l) = v;
                 }
             }
         }
@@ -153,13 +173,49 @@ __global__ void __launch_bounds__(256, 2) radial_fwd_kernel(const RadialArgs a) 
 //   dW[col][k] = b_k G1[col][k] + a_k G1[col][K+1]      dbias[col] = G1[col][K]
 //   da_k = sum_col W[col][k] G1[col][K+1]     db_k = sum_col W[col][k] G1[col][k]     dc_k = -2 b_k c_k sum_col W[col][k] G2[col][k]
 // so every CTA applies that map to its own partial G1 / G2 and writes one row of partials.
+// The operands of a unit (16 pairs: the two gradient entries of every pair, its norm) are fetched one unit ahead into
+// registers, so the L2 latency of the scattered 8-byte reads overlaps the MMA work of the current unit.
+template <int NT>
+struct RadOperands {
+    double g[2][2][NT][2];   // [group][k-step][m-tile][(i,j) | (j,i)]
+    double n;                // norm of pair (lane & 15) of the unit, NaN = masked / invalid
+};
+
+template <int NT>
+LGAE_DEV void rad_fetch(const RadialArgs& a, const unsigned char* ti, const unsigned char* tj, int unit, int NU, int NP, int NPS,
+                        const int (&col_cc)[NT], const int (&col_x)[NT], int lane, RadOperands<NT>& op) {
+    const int N = a.N, C = a.C, q = lane & 3;
+    const int b = unit / NU, p0 = (unit - b * NU) * RAD_UNIT;
+    const double* gb = a.g_r + (int64_t)b * N * C * 128;
+    op.n = a.nrm[(int64_t)b * NPS + p0 + (lane & 15)];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int pid = p0 + 8 * u + q + 4 * ks;
+            const bool valid = pid < NP;
+            const int i = valid ? ti[pid] : 0, j = valid ? tj[pid] : 0;
+#pragma unroll
+            for (int mt = 0; mt < NT; ++mt) {
+                double v0 = 0.0, v1 = 0.0;
+                if (valid && col_cc[mt] >= 0) {
+                    v0 = gb[((int64_t)(j * C + col_cc[mt]) * 32 + i) * 4 + col_x[mt]];
+                    if (i != j) v1 = gb[((int64_t)(i * C + col_cc[mt]) * 32 + j) * 4 + col_x[mt]];
+                }
+                op.g[u][ks][mt][0] = v0;
+                op.g[u][ks][mt][1] = v1;
+            }
+        }
+}
+
 template <int NT, int KS>
-__global__ void __launch_bounds__(256, 2) radial_bwd_kernel(const RadialArgs a) {
+__global__ void __launch_bounds__(128, 3) radial_bwd_kernel(const RadialArgs a) {
     constexpr int KP = 4 * KS;
     constexpr int NT2 = KS / 2 + 1;
     constexpr int NK = 8 * NT2, NCOL = 8 * NT;
-    __shared__ unsigned char ti[RAD_MAXP], tj[RAD_MAXP];
+    __shared__ unsigned char ti[RAD_MAXP + RAD_UNIT], tj[RAD_MAXP + RAD_UNIT];
     __shared__ double abc_s[3 * KP];
+    __shared__ double w_s[NCOL * KP];
     __shared__ double red[2 * NCOL * NK];
     const int N = a.N, C = a.C, K = a.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -170,7 +226,7 @@ __global__ void __launch_bounds__(256, 2) radial_bwd_kernel(const RadialArgs a) 
         abc_s[KP + k] = k < K ? a.theta[a.off_b + k] : 0.0;
         abc_s[2 * KP + k] = k < K ? a.theta[a.off_c + k] : 0.0;
     }
-    for (int t = threadIdx.x; t < 2 * NCOL * NK; t += blockDim.x) red[t] = 0.0;
+    for (int t = threadIdx.x; t < NCOL * KP; t += blockDim.x) w_s[t] = rad_w(a, t / KP, t % KP);
     __syncthreads();
     double G1[NT][NT2][2], G2[NT][NT2][2];
 #pragma unroll
@@ -191,81 +247,65 @@ __global__ void __launch_bounds__(256, 2) radial_bwd_kernel(const RadialArgs a) 
 #pragma unroll
     for (int nt = 0; nt < NT2; ++nt) ck[nt] = (8 * nt + g) < K ? abc_s[2 * KP + 8 * nt + g] : 0.0;
 
-    const int NP = N * (N + 1) / 2, NG = (NP + 7) / 8;
-    const int64_t total = (int64_t)a.B * NG;
-    for (int64_t grp = (int64_t)blockIdx.x * nwarps + warp; grp < total; grp += (int64_t)gridDim.x * nwarps) {
-        const int b = (int)(grp / NG), p0 = (int)(grp % NG) * 8;
-        const double* pb = a.p4 + (int64_t)b * N * 4;
-        const double* gb = a.g_r + (int64_t)b * N * C * 128;
-        // norm and mask of pair g of the group (every q-lane of a g computes the same pair)
-        double n = 0.0;
-        int m = 0;
-        {
-            const int pid = p0 + g;
-            if (pid < NP) {
-                const int i = ti[pid], j = tj[pid];
-                const double4 pi = *reinterpret_cast<const double4*>(pb + 4 * i);
-                const double4 pj = *reinterpret_cast<const double4*>(pb + 4 * j);
-                const double vi[4] = {pi.x, pi.y, pi.z, pi.w}, vj[4] = {pj.x, pj.y, pj.z, pj.w};
-                n = rad_pair_norm(vi, vj);
-                const bool mi = a.node_mask ? a.node_mask[(int64_t)b * N + i] != 0 : pi.x != 0.0;
-                const bool mj = a.node_mask ? a.node_mask[(int64_t)b * N + j] != 0 : pj.x != 0.0;
-                m = (mi && mj && n != 0.0) ? 1 : 0;
-            }
-        }
+    const int NP = N * (N + 1) / 2, NU = (NP + RAD_UNIT - 1) / RAD_UNIT, NPS = NU * RAD_UNIT;
+    const int total = a.B * NU, twarps = gridDim.x * nwarps;
+    const int per = (total + twarps - 1) / twarps;
+    const int u_begin = (blockIdx.x * nwarps + warp) * per, u_end = u_begin + per < total ? u_begin + per : total;
+    RadOperands<NT> cur, nxt;
+    if (u_begin < u_end) rad_fetch<NT>(a, ti, tj, u_begin, NU, NP, NPS, col_cc, col_x, lane, cur);
+    for (int unit = u_begin; unit < u_end; ++unit) {
+        if (unit + 1 < u_end) rad_fetch<NT>(a, ti, tj, unit + 1, NU, NP, NPS, col_cc, col_x, lane, nxt);
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const int pp = q + 4 * ks, pid = p0 + pp;
-            const double n2 = __shfl_sync(0xffffffffu, n, pp * 4);
-            const int m2 = __shfl_sync(0xffffffffu, m, pp * 4);
-            const bool valid = pid < NP;
-            const int i = valid ? ti[pid] : 0, j = valid ? tj[pid] : 0;
-            double a3[NT];
+        for (int u = 0; u < 2; ++u) {
 #pragma unroll
-            for (int mt = 0; mt < NT; ++mt) {
-                double v = 0.0;
-                if (valid && col_cc[mt] >= 0) {
-                    v = gb[((int64_t)(j * C + col_cc[mt]) * 32 + i) * 4 + col_x[mt]];
-                    if (i != j) v += gb[((int64_t)(i * C + col_cc[mt]) * 32 + j) * 4 + col_x[mt]];
-                }
-                a3[mt] = v;
-            }
-            const double nn = n2 * n2;
+            for (int ks = 0; ks < 2; ++ks) {
+                const double n2 = __shfl_sync(0xffffffffu, cur.n, 8 * u + q + 4 * ks);
+                const bool m2 = n2 == n2;   // NaN marks a masked (or padding) pair
+                double a3[NT];
 #pragma unroll
-            for (int nt = 0; nt < NT2; ++nt) {
-                const int k = 8 * nt + g;
-                double b1 = 0.0, b2 = 0.0;
-                if (k < K) {
-                    if (m2) {
+                for (int mt = 0; mt < NT; ++mt) a3[mt] = cur.g[u][ks][mt][0] + cur.g[u][ks][mt][1];
+                const double nn = n2 * n2;
+#pragma unroll
+                for (int nt = 0; nt < NT2; ++nt) {
+                    const int k = 8 * nt + g;
+                    double b1 = 0.0, b2 = 0.0;
+                    if (k < K) {
                         const double cn = ck[nt] * n2;
-                        const double rd = 1.0 / (1.0 + cn * cn + 1e-16);
-                        b1 = rd;
-                        b2 = nn * rd * rd;
+                        const double rd = rcp_ge1(1.0 + cn * cn + 1e-16);
+                        b1 = m2 ? rd : 0.0;
+                        b2 = m2 ? nn * rd * rd : 0.0;
+                    } else if (k == K) {
+                        b1 = 1.0;
+                    } else if (k == K + 1) {
+                        b1 = m2 ? 1.0 : 0.0;
                     }
-                } else if (k == K) {
-                    b1 = 1.0;
-                } else if (k == K + 1) {
-                    b1 = m2 ? 1.0 : 0.0;
-                }
 #pragma unroll
-                for (int mt = 0; mt < NT; ++mt) {
-                    dmma(G1[mt][nt][0], G1[mt][nt][1], a3[mt], b1);
-                    dmma(G2[mt][nt][0], G2[mt][nt][1], a3[mt], b2);
+                    for (int mt = 0; mt < NT; ++mt) {
+                        dmma(G1[mt][nt][0], G1[mt][nt][1], a3[mt], b1);
+                        dmma(G2[mt][nt][0], G2[mt][nt][1], a3[mt], b2);
+                    }
                 }
             }
         }
+        cur = nxt;
     }
-    // ---- cross-warp reduction, then this CTA's row of partials ----
+    // ---- cross-warp reduction (warp after warp: fixed order), then this CTA's row of partials ----
+    for (int w = 0; w < nwarps; ++w) {
+        if (warp == w) {
 #pragma unroll
-    for (int mt = 0; mt < NT; ++mt)
+            for (int mt = 0; mt < NT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NT2; ++nt)
+                for (int nt = 0; nt < NT2; ++nt)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                atomicAdd(&red[(8 * mt + g) * NK + 8 * nt + 2 * q + e], G1[mt][nt][e]);
-                atomicAdd(&red[NCOL * NK + (8 * mt + g) * NK + 8 * nt + 2 * q + e], G2[mt][nt][e]);
-            }
-    __syncthreads();
+                    for (int e = 0; e < 2; ++e) {
+                        double* d1 = &red[(8 * mt + g) * NK + 8 * nt + 2 * q + e];
+                        double* d2 = d1 + NCOL * NK;
+                        *d1 = w == 0 ? G1[mt][nt][e] : *d1 + G1[mt][nt][e];
+                        *d2 = w == 0 ? G2[mt][nt][e] : *d2 + G2[mt][nt][e];
+                    }
+        }
+        __syncthreads();
+    }
     double* row = a.part + (int64_t)blockIdx.x * a.part_stride;
     const double* g1 = red;
     const double* g2 = red + NCOL * NK;
@@ -280,10 +320,8 @@ __global__ void __launch_bounds__(256, 2) radial_bwd_kernel(const RadialArgs a) 
     for (int t = threadIdx.x; t < 3 * K; t += blockDim.x) {
         const int x = t / K, k = t % K;
         double s = 0.0;
-        for (int col = 0; col < 4 * C; ++col) {
-            const double w = rad_w(a, col, k);
-            s += w * (x == 0 ? g1[col * NK + K + 1] : x == 1 ? g1[col * NK + k] : g2[col * NK + k]);
-        }
+        for (int col = 0; col < 4 * C; ++col)
+            s += w_s[col * KP + k] * (x == 0 ? g1[col * NK + K + 1] : x == 1 ? g1[col * NK + k] : g2[col * NK + k]);
         if (x == 2) s *= -2.0 * abc_s[KP + k] * abc_s[2 * KP + k];
         row[(x == 0 ? a.po_a : x == 1 ? a.po_b : a.po_c) + k] = s;
     }
@@ -294,7 +332,10 @@ __global__ void __launch_bounds__(256, 2) radial_bwd_kernel(const RadialArgs a) 
 // ------------------------------------------------------------------------------------------------------------
 static int pick_ks(int K) { return K <= 12 ? 3 : (K <= 20 ? 5 : (K <= 32 ? 8 : -1)); }
 
-int radial_grid() { return 2 * sm_count(); }
+int radial_fwd_grid() { return 4 * sm_count(); }
+int radial_grid() { return 3 * sm_count(); }   // adjoint: CTAs = rows of partials
+// doubles per jet of the pair-norm record (unordered pairs padded to whole units)
+int64_t radial_nrm_stride(int n) { const int np = n * (n + 1) / 2; return (int64_t)((np + RAD_UNIT - 1) / RAD_UNIT) * RAD_UNIT; }
 
 static void fill(RadialArgs& a, const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch) {
     memset(&a, 0, sizeof(a));
@@ -308,12 +349,11 @@ static void fill(RadialArgs& a, const LgaeModelDesc* d, int level, const double*
 
 template <int NT, int KS>
 static int launch_radial(const RadialArgs& a, bool bwd, cudaStream_t st) {
-    const int grid = radial_grid();
+    LaunchScope ls_(bwd ? "radial_bwd" : "radial_fwd", st);
     if (bwd)
-        radial_bwd_kernel<NT, KS><<<grid, 256, 0, st>>>(a);
+        radial_bwd_kernel<NT, KS><<<radial_grid(), 128, 0, st>>>(a);
     else
-        radial_fwd_kernel<NT, KS><<<grid, 256, 0, st>>>(a);
-    count_launch();
+        radial_fwd_kernel<NT, KS><<<radial_fwd_grid(), 128, 0, st>>>(a);
     return check_launch(bwd ? "radial_bwd" : "radial_fwd");
 }
 
@@ -332,12 +372,13 @@ static int dispatch_radial(const RadialArgs& a, bool bwd, cudaStream_t st) {
 
 // R (B,N,C,32,4) of encoder level `level`.
 int run_radial_fwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
-                   double* r, cudaStream_t st) {
+                   double* r, double* nrm, cudaStream_t st) {
     if (!d || d->is_decoder || level < 0 || level >= d->n_levels || !r) return LGAE_E_BADARG;
     if (batch <= 0) return LGAE_OK;
     RadialArgs a;
     fill(a, d, level, theta, p4, node_mask, batch);
     a.r = r;
+    a.nrm = nrm;
     return dispatch_radial(a, false, st);
 }
 
@@ -345,12 +386,13 @@ int64_t radial_part_width(const LgaeModelDesc* d, int level) { return (int64_t)4
 
 // Adjoint: g_r (B,N,C,32,4) -> partial rows for a, b, c, linear.{0,1}.{weight,bias} of the level.
 int run_radial_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
-                   const double* g_r, PartPlan* plan, cudaStream_t st) {
-    if (!d || d->is_decoder || level < 0 || level >= d->n_levels || !g_r || !plan) return LGAE_E_BADARG;
+                   const double* g_r, const double* nrm, PartPlan* plan, cudaStream_t st) {
+    if (!d || d->is_decoder || level < 0 || level >= d->n_levels || !g_r || !nrm || !plan) return LGAE_E_BADARG;
     if (batch <= 0) return LGAE_OK;
     RadialArgs a;
     fill(a, d, level, theta, p4, node_mask, batch);
     a.g_r = g_r;
+    a.nrm = const_cast<double*>(nrm);
     const int C = a.C, K = a.K, grid = radial_grid();
     int64_t w = 0;
     a.po_w0 = w; w += (int64_t)2 * C * K;

@@ -1,12 +1,26 @@
 """The training step of utils/train.py:283-327 (the reference's hot loop body) on the fused path, plus the
 data-parallel gradient exchange: jets are independent, so the batch is sharded over ranks
-with no data-path collective; the only exchange is one NCCL all-reduce(SUM) of the flat gradient per model."""
+with no data-path collective; the only exchange is one NCCL all-reduce(SUM) of the flat gradient per model.
+
+Two entry points:
+
+* ``training_step`` -- the step written with the module API (``LGNEncoder`` / ``LGNDecoder`` forward + autograd), what a
+  caller of the reference's ``lgn/`` modules gets unchanged;
+* ``FusedTrainStep`` -- the same arithmetic as ONE launch sequence of the C library on static buffers (no autograd
+  graph, no per-step allocation), captured in a CUDA graph: normalize -> encoder -> decoder -> chamfer (+ gradient) ->
+  decoder adjoint -> encoder adjoint -> L1.  The parameter gradients land in one flat fp64 buffer per model of which
+  every ``param.grad`` is a view, so optimizers work unchanged and the all-reduce needs no packing.
+"""
 from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
 
 import torch
 import torch.distributed as dist
 
-from . import fused
+from . import _lib, fused
+from ._lib import check, ptr
 
 
 def training_step(encoder, decoder, p4, labels=None, l1_lambda: float = 1e-8, normalize: bool = True, l1_scale: float = 1.0):
@@ -41,3 +55,119 @@ def allreduce_gradients(*models, group=None):
             n = g.numel()
             g.copy_(flat[off:off + n].view_as(g))
             off += n
+
+
+class FusedTrainStep:
+    """One LGAE training step (forward + loss + full backward) for a fixed batch size, on static device buffers.
+
+    ``step(p4, labels=None)`` copies the jets into the static input buffer (host or device source), runs the step and
+    returns the loss as a 0-d device tensor; afterwards ``param.grad`` of every encoder / decoder parameter holds the
+    gradient of  chamfer_sum + l1_lambda * l1_scale * |theta|_1  (summed over ranks if a process group is active).
+    ``recon`` (2,B,N,4), ``latent00/11``, ``norm_factor`` (B,) expose the step's other results.
+    """
+
+    def __init__(self, encoder, decoder, batch: int, l1_lambda: float = 1e-8, l1_scale: float = 1.0, normalize: bool = True,
+                 use_labels: bool = False, use_graph: bool = True, group=None):
+        if not (getattr(encoder, "fused", False) and getattr(decoder, "fused", False)):
+            raise NotImplementedError("FusedTrainStep needs the fused (maxdim 2) encoder and decoder")
+        self.enc, self.dec, self.B = encoder, decoder, int(batch)
+        self.pe, self.pd = encoder._plan, decoder._plan
+        if self.pe.n_particles > 32:
+            raise NotImplementedError("the adjoint kernels hold one particle per lane: at most 32 particles per jet")
+        self.l1 = float(l1_lambda) * float(l1_scale)
+        self.normalize = normalize
+        self.group = group
+        self.lib = _lib.load()
+        dev = next(encoder.parameters()).device
+        self.dev = dev
+        f64 = dict(dtype=torch.float64, device=dev)
+        B, N = self.B, self.pe.n_particles
+        ts, tv = self.pe.latent_taus()
+        self.p4_in = torch.zeros((B, N, 4), **f64)
+        self.p4 = torch.empty((B, N, 4), **f64) if normalize else self.p4_in
+        self.norm_factor = torch.ones(B, **f64)
+        self.mask = torch.ones((B, N), dtype=torch.uint8, device=dev) if use_labels else None
+        self.ws_e, self.ws_d = self.pe.workspace(B, dev), self.pd.workspace(B, dev)
+        self.part_e, self.part_d = self.pe.partials(B, dev), self.pd.partials(B, dev)
+        self.latent00 = torch.empty((2, B, 1, ts, 1), **f64)
+        self.latent11 = torch.empty((2, B, 1, tv, 4), **f64)
+        self.sel = torch.empty((4, 2, B, max(self.pe.tau_s, self.pe.tau_v)), dtype=torch.int32, device=dev)
+        self.recon = torch.empty((2, B, N, 4), **f64)
+        self.g_recon = torch.empty((2, B, N, 4), **f64)
+        self.g_lat11 = torch.empty_like(self.latent11)
+        self.jet_loss = torch.empty(B, **f64)
+        self.loss = torch.zeros((), **f64)
+        # flat gradient buckets; every param.grad is a view of them
+        self.g_e = torch.zeros(self.pe.n_params, **f64)
+        self.g_d = torch.zeros(self.pd.n_params, **f64)
+        self._bind_grads()
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = use_graph
+        self._thetas = None
+
+    def _bind_grads(self):
+        for model, plan, flat in ((self.enc, self.pe, self.g_e), (self.dec, self.pd, self.g_d)):
+            views = plan.views(flat)
+            for name, p in model.named_parameters():
+                p.grad = views[name]
+
+    def _launch(self):
+        lib, pe, pd, B = self.lib, self.pe, self.pd, self.B
+        st = torch.cuda.current_stream().cuda_stream
+        th_e, _ = self.enc._flat_params()
+        th_d, _ = self.dec._flat_params()
+        self._thetas = (th_e.data_ptr(), th_d.data_ptr())
+        if self.normalize:
+            check(lib.lgae_normalize_p4(ptr(self.p4_in), B, pe.n_particles, ptr(self.p4), ptr(self.norm_factor), st), "normalize_p4")
+        check(lib.lgae_encoder_forward(C.byref(pe.desc), ptr(th_e), ptr(self.p4), ptr(self.mask), B, ptr(self.ws_e), ptr(self.latent00),
+                                       ptr(self.latent11), ptr(self.sel), st), "encoder_forward")
+        check(lib.lgae_decoder_forward(C.byref(pd.desc), ptr(th_d), ptr(self.latent11), B, ptr(self.ws_d), ptr(self.recon), None, st),
+              "decoder_forward")
+        check(lib.lgae_chamfer(ptr(self.recon), ptr(self.p4), B, pd.n_particles, pe.n_particles, ptr(self.loss), ptr(self.jet_loss), None,
+                               ptr(self.g_recon), st), "chamfer")
+        check(lib.lgae_decoder_backward(C.byref(pd.desc), ptr(th_d), ptr(self.latent11), B, ptr(self.ws_d), ptr(self.g_recon), None,
+                                        ptr(self.g_lat11), ptr(self.g_d), ptr(self.part_d), st), "decoder_backward")
+        check(lib.lgae_encoder_backward(C.byref(pe.desc), ptr(th_e), ptr(self.p4), ptr(self.mask), B, ptr(self.ws_e), ptr(self.sel), None,
+                                        ptr(self.g_lat11), ptr(self.g_e), ptr(self.part_e), st), "encoder_backward")
+        if self.l1:
+            check(lib.lgae_l1(ptr(th_e), pe.n_params, self.l1, ptr(self.loss), ptr(self.g_e), st), "l1")
+            check(lib.lgae_l1(ptr(th_d), pd.n_params, self.l1, ptr(self.loss), ptr(self.g_d), st), "l1")
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size (SURVEY.md section 8(e))
+            dist.all_reduce(self.g_e, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.g_d, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _params_moved(self) -> bool:
+        th_e, _ = self.enc._flat_params()
+        th_d, _ = self.dec._flat_params()
+        return self._thetas != (th_e.data_ptr(), th_d.data_ptr())
+
+    def load(self, p4, labels=None):
+        """Copy one batch of jets (host or device tensor, (B,N,4)) into the static input buffer."""
+        self.p4_in.copy_(p4, non_blocking=True)
+        if self.mask is not None and labels is not None:
+            self.mask.copy_((labels != 0).to(torch.uint8), non_blocking=True)
+
+    def run(self):
+        """Run the step on the jets already in the static input buffer."""
+        if not self.use_graph:
+            self._launch()
+            return self.loss
+        if self.graph is None or self._params_moved():
+            # warm-up on a side stream (caches kernel attributes, NCCL communicators), then capture
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._launch()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+            self._bind_grads()
+        self.graph.replay()
+        return self.loss
+
+    def step(self, p4, labels=None):
+        self.load(p4, labels)
+        return self.run()
