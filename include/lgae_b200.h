@@ -113,17 +113,20 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch);
 int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask,
                          int32_t batch, double* workspace, double* lat00, double* lat11, int32_t* sel, void* stream);
 /* Adjoint.  g_lat00 / g_lat11 may be NULL (treated as zero).  gtheta (n_params) is OVERWRITTEN with the
- * parameter gradient.  partials: scratch of lgae_partials_doubles(d, batch).  Needs N <= 32. */
+ * parameter gradient.  partials: scratch of lgae_partials_doubles(d, batch).  Needs N <= 32.
+ * l1_lambda != 0 folds the L1 regulariser (lgn_encoder.py:249-250, utils/train.py:483-492) into the same launches:
+ * gtheta += l1_lambda sign(theta) and, when loss_accumulate != NULL, loss_accumulate[0] += l1_lambda |theta|_1. */
 int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask,
                           int32_t batch, double* workspace, const int32_t* sel, const double* g_lat00,
-                          const double* g_lat11, double* gtheta, double* partials, void* stream);
+                          const double* g_lat11, double* gtheta, double* partials, double l1_lambda,
+                          double* loss_accumulate, void* stream);
 /* LGNDecoder.forward.  lat11 (2,B,1,tau_v,4) planar complex Cartesian.  recon (2,B,N,4); gen00 (2,B,N,1,1) or NULL. */
 int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch,
                          double* workspace, double* recon, double* gen00, void* stream);
 /* g_recon (2,B,N,4); g_gen00 (2,B,N,1,1) or NULL.  g_lat11 (2,B,1,tau_v,4) receives the latent gradient. */
 int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch,
                           double* workspace, const double* g_recon, const double* g_gen00, double* g_lat11,
-                          double* gtheta, double* partials, void* stream);
+                          double* gtheta, double* partials, double l1_lambda, double* loss_accumulate, void* stream);
 
 /* ---- caller-side ops on the hot path ------------------------------------------------------------- */
 /* ChamferLoss (sum over the batch) of x = re(recon) + im(recon) against target (B,M,4).

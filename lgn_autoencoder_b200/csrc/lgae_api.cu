@@ -45,8 +45,9 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
 int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st);
 int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const double* g_recon,
                        const double* g_gen00, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
-int run_reduce_plan(const PartPlan* plan, int64_t n_params, double* gtheta, cudaStream_t st);
-int64_t glue_part_doubles(const LgaeModelDesc* d);
+int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const double* theta, double lambda, double* loss, cudaStream_t st);
+int reduce_scratch_doubles();
+int64_t glue_part_doubles(const LgaeModelDesc* d, int batch);
 int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
                 double* g_recon, cudaStream_t st);
 int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st);
@@ -246,7 +247,7 @@ int64_t lgae_workspace_offset(const LgaeModelDesc* d, int32_t batch, int32_t kin
 }
 int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
     if (check_desc(d) != LGAE_OK || batch < 0) return -1;
-    int64_t n = glue_part_doubles(d);
+    int64_t n = glue_part_doubles(d, batch) + reduce_scratch_doubles();
     for (int l = 0; l < d->n_levels; ++l) {
         n += (int64_t)level_bwd_grid(batch) * level_part_width(d, l);
         if (!d->is_decoder) n += (int64_t)radial_grid() * radial_part_width(d, l);
@@ -276,7 +277,7 @@ int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const doub
 
 int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
                           double* ws, const int32_t* sel, const double* g_lat00, const double* g_lat11, double* gtheta,
-                          double* partials, void* stream) {
+                          double* partials, double l1_lambda, double* loss_accumulate, void* stream) {
     LGAE_TRY(check_desc(d));
     if (d->is_decoder || !theta || !p4 || !ws || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -310,7 +311,7 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
         }
         LGAE_TRY(run_enc_input_bwd(d, p4, ws + L.mass, batch, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
     }
-    return run_reduce_plan(&plan, d->n_params, gtheta, st);
+    return run_reduce_plan(&plan, d->n_params, gtheta, theta, l1_lambda, loss_accumulate, st);
 }
 
 int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
@@ -332,7 +333,8 @@ int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const doub
 }
 
 int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws,
-                          const double* g_recon, const double* g_gen00, double* g_lat11, double* gtheta, double* partials, void* stream) {
+                          const double* g_recon, const double* g_gen00, double* g_lat11, double* gtheta, double* partials,
+                          double l1_lambda, double* loss_accumulate, void* stream) {
     LGAE_TRY(check_desc(d));
     if (!d->is_decoder || !theta || !lat11 || !ws || !g_recon || !g_lat11 || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -363,7 +365,7 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
         }
         LGAE_TRY(run_dec_input_bwd(d, theta, batch, lat11, ws + L.y, ws + L.gS[cur], ws + L.gV[cur], ws + L.gy, g_lat11, &plan, st));
     }
-    return run_reduce_plan(&plan, d->n_params, gtheta, st);
+    return run_reduce_plan(&plan, d->n_params, gtheta, theta, l1_lambda, loss_accumulate, st);
 }
 
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,
@@ -416,7 +418,7 @@ int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* the
         LGAE_TRY(run_radial_fwd(d, level, theta, p_or_y, node_mask, batch, r_tmp, nrm, (cudaStream_t)stream));   // refreshes R, writes the norms
         LGAE_TRY(run_radial_bwd(d, level, theta, p_or_y, node_mask, batch, g_r_scratch, nrm, &plan, (cudaStream_t)stream));
     }
-    return run_reduce_plan(&plan, d->n_params, gtheta, (cudaStream_t)stream);
+    return run_reduce_plan(&plan, d->n_params, gtheta, nullptr, 0.0, nullptr, (cudaStream_t)stream);
 }
 int64_t lgae_mlp_pack_doubles(const LgaeModelDesc* d, int32_t level) {
     if (check_desc(d) != LGAE_OK || level < 0 || level >= d->n_levels) return -1;
@@ -446,7 +448,7 @@ int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta
     PartPlan plan;
     plan.base = partials;
     LGAE_TRY(run_mlp(d, level, theta, wpack, x, rows, const_cast<double*>(acts), nullptr, g_y, g_x, &plan, true, (cudaStream_t)stream));
-    return run_reduce_plan(&plan, d->n_params, gtheta, (cudaStream_t)stream);
+    return run_reduce_plan(&plan, d->n_params, gtheta, nullptr, 0.0, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

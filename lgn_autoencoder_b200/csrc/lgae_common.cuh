@@ -122,6 +122,10 @@ LGAE_DEV void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// TMA bulk prefetch of a contiguous global range into L2 (no shared-memory destination, no completion to wait for).
+LGAE_DEV void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 LGAE_DEV void mbar_wait(uint64_t* bar, unsigned parity) {
     asm volatile(
         "{\n"

@@ -610,10 +610,37 @@ __global__ void __launch_bounds__(1024) l1_kernel(const double* theta, int64_t n
     if (threadIdx.x == 0 && out) out[0] += lambda * s;
 }
 
-// gtheta[seg] = sum over the rows of the segment's block.  blockIdx.y = segment, blockDim = (32 columns, 8 row groups);
-// fixed summation order => deterministic gradients.
-__global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, const double* partials, double* gtheta) {
+// gtheta = lambda * sign(theta) (the L1 regulariser's gradient; zero when lambda == 0); psum[block] = sum |theta| of the block.
+constexpr int L1_BLOCKS_MAX = 256;
+__global__ void __launch_bounds__(256) grad_init_kernel(const double* theta, int64_t n, double lambda, double* gtheta, double* psum) {
+    __shared__ double scratch[32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double g = 0.0;
+        if (lambda != 0.0) {
+            const double v = theta[i];
+            s += fabs(v);
+            g = lambda * (v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0));
+        }
+        gtheta[i] = g;
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0 && psum) psum[blockIdx.x] = s;
+}
+
+// gtheta[seg] += sum over the rows of the segment's block.  blockIdx.y = segment, blockDim = (32 columns, 8 row groups);
+// fixed summation order => deterministic gradients.  The extra y-block (blockIdx.y == t.n) adds the L1 term to the loss.
+__global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, const double* partials, double* gtheta, const double* psum,
+                                                          int npsum, double lambda, double* loss) {
     __shared__ double sm[8][33];
+    if ((int)blockIdx.y == t.n) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && loss) {
+            double s = 0.0;
+            for (int i = 0; i < npsum; ++i) s += psum[i];
+            loss[0] += lambda * s;
+        }
+        return;
+    }
     const Seg sg = t.s[blockIdx.y];
     for (int x0 = blockIdx.x * 32; x0 < sg.len; x0 += gridDim.x * 32) {
         const int x = x0 + threadIdx.x;
@@ -637,7 +664,7 @@ __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, cons
             double v = 0.0;
 #pragma unroll
             for (int y = 0; y < 8; ++y) v += sm[y][threadIdx.x];
-            gtheta[sg.theta_off + x] = v;
+            gtheta[sg.theta_off + x] += v;
         }
         __syncthreads();
     }
@@ -662,6 +689,12 @@ int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* ma
     LaunchScope ls_("enc_input_bwd", st);
     enc_input_bwd_kernel<<<grid, 256, 0, st>>>(0, 2 * C, p4, mass, nodes, C, gS, gV, plan->base + off, w);
     return check_launch("enc_input_bwd");
+}
+
+// CTAs (= rows of partials) of the per-jet glue adjoints: one jet per CTA up to four CTAs per SM.
+int glue_grid(int B) {
+    const int cap = 4 * sm_count();
+    return B < cap ? (B > 0 ? B : 1) : cap;
 }
 
 static LatentArgs latent_args(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V) {
@@ -690,8 +723,8 @@ int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const
     a.sel = const_cast<int32_t*>(sel); a.g_lat00 = g_lat00; a.g_lat11 = g_lat11; a.gS = gS; a.gV = gV;
     const int mix = a.mode == LGAE_LATENT_MIX;
     const int rows = mix ? 1 : a.N, cin = mix ? a.N * a.C : a.C;
+    const int grid = glue_grid(B);
     {
-        const int grid = sm_count();
         const int64_t n00 = (int64_t)2 * a.tau_s * cin, n11 = (int64_t)2 * a.tau_v * cin, w = n00 + n11, off = plan->block(grid, w);
         if (int rc = plan->seg(a.off00, off, w, 0, n00, grid)) return rc;
         if (int rc = plan->seg(a.off11, off, w, n00, n11, grid)) return rc;
@@ -701,7 +734,7 @@ int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)enc_latent_bwd_kernel, bytes)) return rc;
     LaunchScope ls_("enc_latent_bwd", st);
-    enc_latent_bwd_kernel<<<sm_count(), 256, bytes, st>>>(a);
+    enc_latent_bwd_kernel<<<grid, 256, bytes, st>>>(a);
     return check_launch("enc_latent_bwd");
 }
 
@@ -724,8 +757,8 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
     DecInArgs a = dec_in_args(d, theta, B, lat11, y, nullptr, nullptr);
     a.gS = gS; a.gV = gV; a.gy = gy; a.g_lat11 = g_lat11;
     if (a.N > 128) return LGAE_E_UNSUPPORTED;
+    const int grid = glue_grid(B);
     {
-        const int grid = sm_count();
         const int64_t ng = (int64_t)2 * a.N * a.tau, w = ng + 4 * a.C, off = plan->block(grid, w);
         if (int rc = plan->seg(a.off_g11, off, w, 0, ng, grid)) return rc;
         if (int rc = plan->seg(a.off_in00, off, w, ng, 2 * a.C, grid)) return rc;
@@ -736,7 +769,7 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)dec_input_bwd_kernel, bytes)) return rc;
     LaunchScope ls_("dec_input_bwd", st);
-    dec_input_bwd_kernel<<<sm_count(), 128, bytes, st>>>(a);
+    dec_input_bwd_kernel<<<grid, 128, bytes, st>>>(a);
     return check_launch("dec_input_bwd");
 }
 int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st) {
@@ -756,25 +789,35 @@ int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const
                                                  g_gen00, gS, gV, plan->base + off, w);
     return check_launch("dec_output_bwd");
 }
-// gtheta = 0, then every segment of the plan is reduced over its rows.
-int run_reduce_plan(const PartPlan* plan, int64_t n_params, double* gtheta, cudaStream_t st) {
-    if (cudaMemsetAsync(gtheta, 0, (size_t)n_params * sizeof(double), st) != cudaSuccess) return check_launch("memset gtheta");
-    if (plan->table.n == 0) return LGAE_OK;
+// gtheta = lambda sign(theta) (0 when lambda == 0), then every segment of the plan is reduced over its rows and added;
+// loss[0] += lambda |theta|_1 when loss != NULL.  Uses L1_BLOCKS_MAX doubles of scratch behind the plan's blocks.
+int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const double* theta, double lambda, double* loss, cudaStream_t st) {
+    const bool l1 = lambda != 0.0 && theta;
+    int nb = (int)((n_params + 1023) / 1024);
+    nb = nb < 1 ? 1 : (nb > L1_BLOCKS_MAX ? L1_BLOCKS_MAX : nb);
+    double* psum = plan->base + plan->used;
+    {
+        LaunchScope ls_("grad_init", st);
+        grad_init_kernel<<<nb, 256, 0, st>>>(theta, n_params, l1 ? lambda : 0.0, gtheta, l1 ? psum : nullptr);
+        if (int rc = check_launch("grad_init")) return rc;
+    }
+    if (plan->table.n == 0 && !l1) return LGAE_OK;
     int maxlen = 1;
     for (int i = 0; i < plan->table.n; ++i) maxlen = plan->table.s[i].len > maxlen ? plan->table.s[i].len : maxlen;
     int gx = (maxlen + 31) / 32;
     if (gx > 1024) gx = 1024;
     LaunchScope ls_("reduce_partials", st);
-    reduce_segs_kernel<<<dim3(gx, plan->table.n), dim3(32, 8), 0, st>>>(plan->table, plan->base, gtheta);
+    reduce_segs_kernel<<<dim3(gx, plan->table.n + 1), dim3(32, 8), 0, st>>>(plan->table, plan->base, gtheta, psum, nb, lambda, l1 ? loss : nullptr);
     return check_launch("reduce_partials");
 }
+int reduce_scratch_doubles() { return L1_BLOCKS_MAX; }
 // Doubles of partial rows used by the glue adjoints of a model.
-int64_t glue_part_doubles(const LgaeModelDesc* d) {
-    const int64_t g = sm_count();
-    if (d->is_decoder) return g * ((int64_t)2 * d->n_particles * d->tau_v + 4 * d->channels[0]) + g * 4 * d->channels[d->n_levels];
+int64_t glue_part_doubles(const LgaeModelDesc* d, int batch) {
+    const int64_t g = sm_count(), gj = glue_grid(batch);
+    if (d->is_decoder) return gj * ((int64_t)2 * d->n_particles * d->tau_v + 4 * d->channels[0]) + g * 4 * d->channels[d->n_levels];
     const int mix = d->latent_mode == LGAE_LATENT_MIX;
     const int64_t cin = mix ? (int64_t)d->n_particles * d->channels[d->n_levels] : d->channels[d->n_levels];
-    return g * 4 * d->channels[0] + g * 2 * (d->tau_s + d->tau_v) * cin;
+    return g * 4 * d->channels[0] + gj * 2 * (d->tau_s + d->tau_v) * cin;
 }
 int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
                 double* g_recon, cudaStream_t st) {

@@ -43,7 +43,11 @@ struct LevelArgs {
     int B, N, C, Cout, K;
 };
 
+#ifndef LGAE_LBWD_MINB
+#define LGAE_LBWD_MINB 3   // resident CTAs per SM the level adjoint is compiled for (register cap 168; 4 => 128 registers spills and is slower)
+#endif
 constexpr int TJ = 8;  // neighbours per shared-memory tile of radial weights
+constexpr int CAT_E = 21;  // entries per (channel, particle) of the concatenation staged for the channel mix
 
 // Pair norm n_ij = s / sqrt|s|, s = (p_i - p_j)^2 + 1e-16, with the reference's rounding sequence
 // (zonal_functions.py:142-144, 201-248).
@@ -143,7 +147,7 @@ __host__ __device__ inline LevelSmem level_smem(bool enc, bool tiles, int N, int
     s.m11 = o; o += 2 * Cout * 5 * C;
     o = (o + 3) & ~3;
     s.big = o;
-    const int cat = 2 * 25 * C * 32;                // cat: [(k*5+comp)][32] complex
+    const int cat = 2 * CAT_E * C * (N < 32 ? N : 32);   // cat: [(c*21+e)][min(N,32)] complex
     const int tile = tiles ? TJ * C * 32 * 4 : 0;   // Rs (radial weights evaluated in the kernel)
     o += cat > tile ? cat : tile;
     s.total = o;
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
     cplx* m11_s = reinterpret_cast<cplx*>(smem + L.m11);
     double* Rs = smem + L.big;
     cplx* cat_s = reinterpret_cast<cplx*>(smem + L.big);
+    const int NS = N < 32 ? N : 32;   // particle stride of cat_s
 
     // ---- stage the jet: momenta and node features by TMA bulk copies, weights by the threads meanwhile ----
     __shared__ uint64_t mbar;
@@ -338,20 +343,23 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
         cplx Vi[4];
 #pragma unroll
         for (int mu = 0; mu < 4; ++mu) Vi[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
-        auto put = [&](int k, int comp, cplx v) { cat_s[(k * 5 + comp) * 32 + lane] = v; };
-        put(c, 0, cscale(A1E, 0.5));
-        put(C + c, 0, cmul_1pi(A0S));
-        put(2 * C + c, 0, Si);
-        put(3 * C + c, 0, cscale(ceta(Vi, Vi), 0.5));
-        put(4 * C + c, 0, cmul(Si, Si));
+        // 21 entries per (channel, particle): the five (0,0) blocks [ag_a, ag_b, node, sq_a, sq_b], then the (1,1) components
+        // of [ag_a, ag_b, node, sq]; the two self-product blocks share their (1,1) part V S, so it is stored once and
+        // mixed with the sum of their weights.
+        auto put = [&](int e, cplx v) { cat_s[(c * CAT_E + e) * NS + lane] = v; };
+        if (lane < NS) {
+            put(0, cscale(A1E, 0.5));
+            put(1, cmul_1pi(A0S));
+            put(2, Si);
+            put(3, cscale(ceta(Vi, Vi), 0.5));
+            put(4, cmul(Si, Si));
 #pragma unroll
-        for (int mu = 0; mu < 4; ++mu) {
-            put(c, 1 + mu, cmul_1pi(A0V[mu]));
-            put(C + c, 1 + mu, A1Y[mu]);
-            put(2 * C + c, 1 + mu, Vi[mu]);
-            const cplx sv = cmul(Vi[mu], Si);
-            put(3 * C + c, 1 + mu, sv);
-            put(4 * C + c, 1 + mu, sv);
+            for (int mu = 0; mu < 4; ++mu) {
+                put(5 + mu, cmul_1pi(A0V[mu]));
+                put(9 + mu, A1Y[mu]);
+                put(13 + mu, Vi[mu]);
+                put(17 + mu, cmul(Vi[mu], Si));
+            }
         }
     }
     __syncthreads();
@@ -360,13 +368,22 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
         const int il = it & 31, r = it >> 5, co = r / 5, comp = r % 5;
         const int ii = i0 + il;
         if (ii >= N) continue;
-        const cplx* w = (comp == 0 ? m00_s : m11_s) + co * 5 * C;
         cplx acc = czero();
-        for (int k = 0; k < 5 * C; ++k) cfma(acc, w[k], cat_s[(k * 5 + comp) * 32 + il]);
-        if (comp == 0)
+        if (comp == 0) {
+            const cplx* w = m00_s + co * 5 * C;
+            for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) cfma(acc, w[j * C + cc], cat_s[(cc * CAT_E + j) * NS + il]);
             reinterpret_cast<cplx*>(a.s_pre)[(int64_t)(b * N + ii) * Cout + co] = acc;
-        else
+        } else {
+            const cplx* w = m11_s + co * 5 * C;
+            for (int cc = 0; cc < C; ++cc) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) cfma(acc, w[j * C + cc], cat_s[(cc * CAT_E + 5 + 4 * j + comp - 1) * NS + il]);
+                cfma(acc, cadd(w[3 * C + cc], w[4 * C + cc]), cat_s[(cc * CAT_E + 17 + comp - 1) * NS + il]);
+            }
             reinterpret_cast<cplx*>(a.v_out)[((int64_t)(b * N + ii) * Cout + co) * 4 + comp - 1] = acc;
+        }
     }
 }
 
@@ -478,8 +495,13 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
         {
             const int np = ENC ? 4 * N : 8 * N;
             if (tid == 0) {
+                // encoder: pull this jet's radial weights (written by the forward pass long ago) towards L2 while the mix
+                // adjoint runs; the neighbour loop then streams them with a two-partner register prefetch
+                if (ENC) bulk_prefetch_l2(a.r_save + (int64_t)b * N * C * 128, (unsigned)(N * C * 128 * sizeof(double)));
                 const unsigned gs_bytes = a.g_s_pre ? 2 * N * Cout * sizeof(double) : 0u;
-                mbar_expect_tx(&mbar, (unsigned)((np + 10 * N * C + 8 * N * Cout) * sizeof(double)) + gs_bytes);
+                mbar_expect_tx(&mbar, (unsigned)((np + 10 * N * C + 8 * N * Cout + 20 * N * C) * sizeof(double)) + gs_bytes);
+                // saved neighbour sums (N,C,10) complex land in the gA buffer, which is only written after they are consumed
+                bulk_g2s(smem + L.gA, a.sums + (int64_t)b * N * C * 20, 20 * N * C * sizeof(double), &mbar);
                 bulk_g2s(p_s, a.p + (int64_t)b * np, np * sizeof(double), &mbar);
                 bulk_g2s(smem + L.S, a.s_in + (int64_t)b * N * C * 2, 2 * N * C * sizeof(double), &mbar);
                 bulk_g2s(smem + L.V, a.v_in + (int64_t)b * N * C * 8, 8 * N * C * sizeof(double), &mbar);
@@ -498,6 +520,9 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
         }
         mbar_wait(&mbar, phase);
         phase ^= 1;
+        cplx A[10];
+#pragma unroll
+        for (int e = 0; e < 10; ++e) A[e] = live ? reinterpret_cast<const cplx*>(smem + L.gA)[(i * C + c) * 10 + e] : czero();
         {   // incoming gradients -> [(c'*5+comp)][lane] (conflict-free for the per-lane reads of the mix adjoint)
             const cplx* gs_raw = reinterpret_cast<const cplx*>(smem + L.graw);
             const cplx* gv_raw = gs_raw + N * Cout;
@@ -522,14 +547,6 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
             cplx Vi[4];
 #pragma unroll
             for (int mu = 0; mu < 4; ++mu) Vi[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
-            cplx A[10];
-#pragma unroll
-            for (int e = 0; e < 10; ++e) A[e] = czero();
-            if (live) {
-                const cplx* src = reinterpret_cast<const cplx*>(a.sums) + ((int64_t)(b * N + i) * C + c) * 10;
-#pragma unroll
-                for (int e = 0; e < 10; ++e) A[e] = src[e];
-            }
             cplx cat5[5], gc[5];
             // block 0: [ (1/2) A1E | (1+i) A0V ]   -> adjoints of A1E, A0V
             cat5[0] = cscale(A[9], 0.5);
@@ -691,7 +708,9 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
                     R0 = cmake(rnext.x, rnext.y);
                     R1 = cmake(rnext.z, rnext.w);
                     rnext = rnext2;
+#ifndef LGAE_EXP_NOR
                     if (o + 2 < N) rnext2 = rsv[(int64_t)(o + 2) * C * 32];
+#endif
                 }
                 const cplx So = S_s[o * C + c];
                 cplx Vo[4], Y[4];
@@ -719,7 +738,11 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
                     cplx gR1 = cmulc(So, w);
                     cfmac(gR1, e, gAa[9]);
                     if (ENC) {
+#ifdef LGAE_EXP_NOGR
+                        if (gR0.x == 1.2345e300) grv[0] = make_double4(gR0.x, gR0.y, gR1.x, gR1.y);
+#else
                         grv[(int64_t)o * C * 32] = make_double4(gR0.x, gR0.y, gR1.x, gR1.y);
+#endif
                     } else {
                         gR0c = cadd(gR0c, live ? gR0 : czero());
                         gR1c = cadd(gR1c, live ? gR1 : czero());
@@ -851,7 +874,7 @@ static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
         kern<<<grid, 32 * a.C, bytes, st>>>(a);                               \
     }
     if (a.C <= 4) {
-        if (cf) LGAE_LAUNCH(128, 3, true) else LGAE_LAUNCH(128, 3, false)
+        if (cf) LGAE_LAUNCH(128, LGAE_LBWD_MINB, true) else LGAE_LAUNCH(128, LGAE_LBWD_MINB, false)
     } else {
         if (cf) LGAE_LAUNCH(256, 1, true) else LGAE_LAUNCH(256, 1, false)
     }

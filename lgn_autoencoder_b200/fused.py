@@ -154,7 +154,7 @@ def encoder_backward_raw(plan: FusedPlan, theta, p4, node_mask, ws, sel, g00, g1
     gtheta = torch.empty(plan.n_params, dtype=torch.float64, device=dev)
     part = plan.partials(p4.shape[0], dev)
     check(lib.lgae_encoder_backward(C.byref(plan.desc), ptr(theta), ptr(p4), ptr(node_mask), p4.shape[0], ptr(ws), ptr(sel),
-                                    ptr(g00), ptr(g11), ptr(gtheta), ptr(part), _stream()), "encoder_backward")
+                                    ptr(g00), ptr(g11), ptr(gtheta), ptr(part), 0.0, None, _stream()), "encoder_backward")
     return gtheta
 
 
@@ -178,7 +178,7 @@ def decoder_backward_raw(plan: FusedPlan, theta, lat11, ws, g_recon, g_gen00):
     g_lat11 = torch.empty_like(lat11)
     part = plan.partials(b, dev)
     check(lib.lgae_decoder_backward(C.byref(plan.desc), ptr(theta), ptr(lat11), b, ptr(ws), ptr(g_recon), ptr(g_gen00), ptr(g_lat11),
-                                    ptr(gtheta), ptr(part), _stream()), "decoder_backward")
+                                    ptr(gtheta), ptr(part), 0.0, None, _stream()), "decoder_backward")
     return g_lat11, gtheta
 
 

@@ -126,12 +126,9 @@ class FusedTrainStep:
         check(lib.lgae_chamfer(ptr(self.recon), ptr(self.p4), B, pd.n_particles, pe.n_particles, ptr(self.loss), ptr(self.jet_loss), None,
                                ptr(self.g_recon), st), "chamfer")
         check(lib.lgae_decoder_backward(C.byref(pd.desc), ptr(th_d), ptr(self.latent11), B, ptr(self.ws_d), ptr(self.g_recon), None,
-                                        ptr(self.g_lat11), ptr(self.g_d), ptr(self.part_d), st), "decoder_backward")
+                                        ptr(self.g_lat11), ptr(self.g_d), ptr(self.part_d), self.l1, ptr(self.loss), st), "decoder_backward")
         check(lib.lgae_encoder_backward(C.byref(pe.desc), ptr(th_e), ptr(self.p4), ptr(self.mask), B, ptr(self.ws_e), ptr(self.sel), None,
-                                        ptr(self.g_lat11), ptr(self.g_e), ptr(self.part_e), st), "encoder_backward")
-        if self.l1:
-            check(lib.lgae_l1(ptr(th_e), pe.n_params, self.l1, ptr(self.loss), ptr(self.g_e), st), "l1")
-            check(lib.lgae_l1(ptr(th_d), pd.n_params, self.l1, ptr(self.loss), ptr(self.g_d), st), "l1")
+                                        ptr(self.g_lat11), ptr(self.g_e), ptr(self.part_e), self.l1, ptr(self.loss), st), "encoder_backward")
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size
             dist.all_reduce(self.g_e, op=dist.ReduceOp.SUM, group=self.group)
