@@ -203,13 +203,12 @@ def main():
     fstep._launch()
     torch.cuda.synchronize()
     launches = _lib.launch_count() - n0          # kernels of one step (the CUDA graph replays exactly these)
-    kern = None
-    if rank == 0:
-        def eager():
-            flush.zero_()
-            fstep._launch()
-        eager()
-        kern = _lib.kernel_timings(eager, reps=5)
+    # (every rank runs it: the step contains the gradient all-reduce, so the launch sequences must match across ranks)
+    def eager():
+        flush.zero_()
+        fstep._launch()
+    eager()
+    kern = _lib.kernel_timings(eager, reps=5)
 
     # ---- value: jets resident in HBM ----
     for _ in range(W):
@@ -291,7 +290,17 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        # the captured step holds NCCL kernels: drop the graph before tearing the communicator down, and never let a slow
+        # teardown keep the job alive after the result line is out
+        import gc
+        import threading
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        fstep.graph = None
+        gc.collect()
+        barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":
