@@ -99,13 +99,16 @@ int64_t lgae_workspace_doubles(const LgaeModelDesc* d, int32_t batch);
  * 1 = V_in[level] (B,N,C,4,2) (level == n_levels gives the final features), 2 = pre-MLP scalars of level,
  * 3 = canonical momenta y (B,N,4,2), 4 = neighbour sums of level (B,N,C,10,2), 5 = masses (B,N) (encoder),
  * 6 = MLP activations of level (hidden, B*N, padded width), 7 = radial weights of level (B,N,C,32,4) (encoder, N <= 32),
- * 8 = scratch for dL/dR of one level (B,N,max C,32,4) (encoder, N <= 32). */
+ * 8 = dL/dR of level (B,N,C,32,4) (encoder, N <= 32; one buffer per level: the radial adjoint of a level overlaps the next one). */
 int64_t lgae_workspace_offset(const LgaeModelDesc* d, int32_t batch, int32_t kind, int32_t level);
 /* Doubles of scratch for the per-CTA rows of parameter-gradient partials the backward entry points write (every
  * backward kernel owns a block of compact rows; one reduce launch sums them into gtheta, in a fixed order). */
 int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch);
 
 /* ---- whole-model entry points -------------------------------------------------------------------- */
+/* With LGAE_OVERLAP=1 (environment; off by default, no measured gain at batch 512) the encoder entry points run the
+ * radial-function kernels on a library-owned side stream, forked from and joined back into `stream` with events (a CUDA-graph
+ * capture of `stream` records them as a parallel branch); all work is complete in `stream` order when the call returns. */
 /* LGNEncoder.forward.  p4 (B,N,4) Cartesian (E,px,py,pz); node_mask (B,N) uint8 or NULL (=> p4[...,0] != 0).
  * Outputs, planar like the reference: lat00 (2,B,1,T_s,1), lat11 (2,B,1,T_v,4) with T = tau (x2 for min&max);
  * sel (int32, device) receives the selected particle indices for min/max modes: (4, 2, B, tau_max) laid out as

@@ -83,14 +83,20 @@ LGAE_DEV void copy_frags(const double* src, double* dst, int n) {
     for (; t < n4; t += blockDim.x) d4[t] = s4[t];
 }
 
-template <int KT, int NO>
-LGAE_DEV void layer_mma(const double (&act)[KT][2], double (&acc)[NO][2], const double* Wp, int q, int g) {
+// MT row groups advance together so that MT * NO independent accumulator chains are in flight (the fp64 MMA has a long
+// dependent-issue latency; a single group's NO chains leave the pipe idle).
+template <int MT, int KT, int NO>
+LGAE_DEV void layer_mma(const double (&act)[MT][KT][2], double (&acc)[MT][NO][2], const double* Wp, int q, int g) {
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt)
 #pragma unroll
         for (int e = 0; e < 2; ++e)
 #pragma unroll
-            for (int nt = 0; nt < NO; ++nt) dmma(acc[nt][0], acc[nt][1], act[kt][e], Wp[((kt * 2 + e) * NO + nt) * 32 + q * 8 + g]);
+            for (int nt = 0; nt < NO; ++nt) {
+                const double bv = Wp[((kt * 2 + e) * NO + nt) * 32 + q * 8 + g];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], act[mt][kt][e], bv);
+            }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -116,61 +122,80 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpArgs a
         copy_frags(a.wpack, w_s, wtotal);
     }
     __syncthreads();
-    // ---- row groups of 8, a contiguous range per CTA dealt round-robin to its warps ----
+    // ---- row groups of 8: a contiguous range per CTA, each warp takes MT = 2 consecutive groups at a time ----
+    constexpr int MT = 2;
     const int64_t ngroups = (a.rows + 7) / 8;
     const int64_t per_cta = (ngroups + gridDim.x - 1) / gridDim.x;
     const int64_t g_begin = (int64_t)blockIdx.x * per_cta, g_end = g_begin + per_cta < ngroups ? g_begin + per_cta : ngroups;
-    for (int64_t grp = g_begin + warp; grp < g_end; grp += nwarps) {
-        const int64_t row = grp * 8 + g;
-        const bool ok = row < a.rows;
-        double in0[NTI][2];
+    for (int64_t grp = g_begin + MT * warp; grp < g_end; grp += MT * nwarps) {
+        int64_t row[MT];
+        bool ok[MT];
+        double in0[MT][NTI][2];
 #pragma unroll
-        for (int nt = 0; nt < NTI; ++nt) {
-            const int col = 8 * nt + 2 * q;
-            double2 v = make_double2(0.0, 0.0);
-            if (ok && col < a.nin) v = *reinterpret_cast<const double2*>(a.x + row * a.nin + col);
-            in0[nt][0] = v.x;
-            in0[nt][1] = v.y;
+        for (int mt = 0; mt < MT; ++mt) {
+            row[mt] = (grp + mt) * 8 + g;
+            ok[mt] = grp + mt < g_end && row[mt] < a.rows;
+#pragma unroll
+            for (int nt = 0; nt < NTI; ++nt) {
+                const int col = 8 * nt + 2 * q;
+                double2 v = make_double2(0.0, 0.0);
+                if (ok[mt] && col < a.nin) v = *reinterpret_cast<const double2*>(a.x + row[mt] * a.nin + col);
+                in0[mt][nt][0] = v.x;
+                in0[mt][nt][1] = v.y;
+            }
         }
-        double act[NTW][2], acc[NTW][2];
+        double act[MT][NTW][2], acc[MT][NTW][2];
         const double* wl = w_s;
         // first layer: nin -> w
 #pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) { acc[nt][0] = bias_s[8 * nt + 2 * q]; acc[nt][1] = bias_s[8 * nt + 2 * q + 1]; }
-        layer_mma<NTI, NTW>(in0, acc, wl, q, g);
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) { acc[mt][nt][0] = bias_s[8 * nt + 2 * q]; acc[mt][nt][1] = bias_s[8 * nt + 2 * q + 1]; }
+        layer_mma<MT, NTI, NTW>(in0, acc, wl, q, g);
         wl += NTI * 2 * NTW * 32;
 #pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) {
-            act[nt][0] = leaky(acc[nt][0], a.slope);
-            act[nt][1] = leaky(acc[nt][1], a.slope);
-            if (ok) *reinterpret_cast<double2*>(a.acts + row * WP + 8 * nt + 2 * q) = make_double2(act[nt][0], act[nt][1]);
-        }
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                act[mt][nt][0] = leaky(acc[mt][nt][0], a.slope);
+                act[mt][nt][1] = leaky(acc[mt][nt][1], a.slope);
+                if (ok[mt]) *reinterpret_cast<double2*>(a.acts + row[mt] * WP + 8 * nt + 2 * q) = make_double2(act[mt][nt][0], act[mt][nt][1]);
+            }
         // hidden layers: w -> w
         for (int l = 1; l < last; ++l) {
             const double* bl = bias_s + l * WP;
 #pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) { acc[nt][0] = bl[8 * nt + 2 * q]; acc[nt][1] = bl[8 * nt + 2 * q + 1]; }
-            layer_mma<NTW, NTW>(act, acc, wl, q, g);
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) { acc[mt][nt][0] = bl[8 * nt + 2 * q]; acc[mt][nt][1] = bl[8 * nt + 2 * q + 1]; }
+            layer_mma<MT, NTW, NTW>(act, acc, wl, q, g);
             wl += NTW * 2 * NTW * 32;
 #pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) {
-                act[nt][0] = leaky(acc[nt][0], a.slope);
-                act[nt][1] = leaky(acc[nt][1], a.slope);
-                if (ok)
-                    *reinterpret_cast<double2*>(a.acts + ((int64_t)l * a.rows + row) * WP + 8 * nt + 2 * q) = make_double2(act[nt][0], act[nt][1]);
-            }
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) {
+                    act[mt][nt][0] = leaky(acc[mt][nt][0], a.slope);
+                    act[mt][nt][1] = leaky(acc[mt][nt][1], a.slope);
+                    if (ok[mt])
+                        *reinterpret_cast<double2*>(a.acts + ((int64_t)l * a.rows + row[mt]) * WP + 8 * nt + 2 * q) =
+                            make_double2(act[mt][nt][0], act[mt][nt][1]);
+                }
         }
         // last layer: w -> nin, no activation
-        double out[NTI][2];
+        double out[MT][NTI][2];
         const double* bl = bias_s + last * WP;
 #pragma unroll
-        for (int nt = 0; nt < NTI; ++nt) { out[nt][0] = bl[8 * nt + 2 * q]; out[nt][1] = bl[8 * nt + 2 * q + 1]; }
-        layer_mma<NTW, NTI>(act, out, wl, q, g);
+        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < NTI; ++nt) {
-            const int col = 8 * nt + 2 * q;
-            if (ok && col < a.nin) *reinterpret_cast<double2*>(a.y + row * a.nin + col) = make_double2(out[nt][0], out[nt][1]);
-        }
+            for (int nt = 0; nt < NTI; ++nt) { out[mt][nt][0] = bl[8 * nt + 2 * q]; out[mt][nt][1] = bl[8 * nt + 2 * q + 1]; }
+        layer_mma<MT, NTW, NTI>(act, out, wl, q, g);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NTI; ++nt) {
+                const int col = 8 * nt + 2 * q;
+                if (ok[mt] && col < a.nin) *reinterpret_cast<double2*>(a.y + row[mt] * a.nin + col) = make_double2(out[mt][nt][0], out[mt][nt][1]);
+            }
     }
 }
 
@@ -273,7 +298,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
             }
             // ---- weight gradient: dW[n][k] = sum_rows dZ[row][n] H[row][k]; this warp's tiles, all in flight ----
             {
-                double cw[MAXT][2];
+                double cw[MAXT][2], cw2[MAXT][2];   // even / odd k-steps: twice the independent MMA chains
                 int tm[MAXT], tn[MAXT];
 #pragma unroll
                 for (int j = 0; j < MAXT; ++j) {
@@ -281,15 +306,20 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
                     const bool on = t < NOt * KIt;
                     tm[j] = on ? t / KIt : -1;
                     tn[j] = on ? t % KIt : 0;
-                    cw[j][0] = cw[j][1] = 0.0;
+                    cw[j][0] = cw[j][1] = cw2[j][0] = cw2[j][1] = 0.0;
                 }
-                for (int ks = 0; ks < ksteps; ++ks) {
+                for (int ks = 0; ks < ksteps; ks += 2) {   // ksteps is even
                     const double* dr = dz_s + (4 * ks + q) * WS + g;
                     const double* hr = h_s + (4 * ks + q) * WS + g;
 #pragma unroll
                     for (int j = 0; j < MAXT; ++j)
-                        if (tm[j] >= 0) dmma(cw[j][0], cw[j][1], dr[8 * tm[j]], hr[8 * tn[j]]);
+                        if (tm[j] >= 0) {
+                            dmma(cw[j][0], cw[j][1], dr[8 * tm[j]], hr[8 * tn[j]]);
+                            dmma(cw2[j][0], cw2[j][1], dr[4 * WS + 8 * tm[j]], hr[4 * WS + 8 * tn[j]]);
+                        }
                 }
+#pragma unroll
+                for (int j = 0; j < MAXT; ++j) { cw[j][0] += cw2[j][0]; cw[j][1] += cw2[j][1]; }
 #pragma unroll
                 for (int j = 0; j < MAXT; ++j) {
                     if (tm[j] < 0) continue;
@@ -302,23 +332,30 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
                 }
             }
             // ---- data gradient: Gin[row][k] = sum_n dZ[row][n] W[n][k], then through the LeakyReLU of layer l-1 ----
+            double ging[TU][NTW][2];
+#pragma unroll
+            for (int u = 0; u < TU; ++u)
+#pragma unroll
+                for (int kt = 0; kt < NTW; ++kt) ging[u][kt][0] = ging[u][kt][1] = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NTW; ++nt) {
+                if (nt < NOt) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int kt = 0; kt < NTW; ++kt)
+                            if (kt < KIt) {
+                                const double bv = wl[((nt * 2 + e) * KIt + kt) * 32 + q * 8 + g];
+#pragma unroll
+                                for (int u = 0; u < TU; ++u) dmma(ging[u][kt][0], ging[u][kt][1], dz[u][nt][e], bv);   // padding groups carry zeros
+                            }
+                }
+            }
 #pragma unroll
             for (int u = 0; u < TU; ++u) {
                 const int rl = (warp + NWARP * u) * 8;
                 if (rl >= ksteps * 4) continue;
-                double gin[NTW][2];
-#pragma unroll
-                for (int kt = 0; kt < NTW; ++kt) gin[kt][0] = gin[kt][1] = 0.0;
-#pragma unroll
-                for (int nt = 0; nt < NTW; ++nt) {
-                    if (nt < NOt) {
-#pragma unroll
-                        for (int e = 0; e < 2; ++e)
-#pragma unroll
-                            for (int kt = 0; kt < NTW; ++kt)
-                                if (kt < KIt) dmma(gin[kt][0], gin[kt][1], dz[u][nt][e], wl[((nt * 2 + e) * KIt + kt) * 32 + q * 8 + g]);
-                    }
-                }
+                double (&gin)[NTW][2] = ging[u];
                 if (l > 0) {
 #pragma unroll
                     for (int kt = 0; kt < NTW; ++kt) {
