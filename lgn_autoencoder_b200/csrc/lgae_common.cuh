@@ -146,6 +146,57 @@ LGAE_DEV double warp_sum(double v) {
     return v;
 }
 
+// Sums of 32 per-lane values over the warp with 16+8+4+2+1 = 31 shuffles: on return lane l holds the total of value l.
+LGAE_DEV double warp_sum32(const double (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+    double a[16], b[8], c[4], d[2];
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const double send = up ? v[j] : v[j + 16], keep = up ? v[j + 16] : v[j];
+            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double send = up ? a[j] : a[j + 8], keep = up ? a[j + 8] : a[j];
+            b[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double send = up ? b[j] : b[j + 4], keep = up ? b[j + 4] : b[j];
+            c[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double send = up ? c[j] : c[j + 2], keep = up ? c[j + 2] : c[j];
+            d[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+    }
+    const bool up = lane & 1;
+    const double send = up ? d[0] : d[1], keep = up ? d[1] : d[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+// All-reduce of NV <= 32 per-lane values: v[t] becomes the warp total of value t in every lane (31 + NV shuffles).
+template <int NV>
+LGAE_DEV void warp_allsum_n(double (&v)[NV]) {
+    double w[32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) w[t] = t < NV ? v[t] : 0.0;
+    const double tot = warp_sum32(w);
+#pragma unroll
+    for (int t = 0; t < NV; ++t) v[t] = __shfl_sync(0xffffffffu, tot, t);
+}
+
 // Sum over the warp, result in every lane (the xor butterfly of warp_sum already has that property).
 LGAE_DEV double warp_allsum(double v) { return warp_sum(v); }
 

@@ -254,8 +254,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
                 m[10 + 2 * mu] += sy.x; m[11 + 2 * mu] += sy.y;
             }
         }
-#pragma unroll
-        for (int t = 0; t < 20; ++t) m[t] = warp_allsum(m[t]);
+        warp_allsum_n<20>(m);
         const cplx SS = cmake(m[0], m[1]), SVY = cmake(m[18], m[19]);
         cplx SV[4], SSY[4];
 #pragma unroll
@@ -623,8 +622,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
                     m[10 + 2 * mu] = sy.x; m[11 + 2 * mu] = sy.y;
                 }
             }
-#pragma unroll
-            for (int t = 0; t < 20; ++t) m[t] = warp_allsum(m[t]);
+            warp_allsum_n<20>(m);
             const cplx SS = cmake(m[0], m[1]), SVY = cmake(m[18], m[19]);
             cplx SV[4], SSY[4];
 #pragma unroll
@@ -661,8 +659,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
             r[8] = gAa[4].x; r[9] = gAa[4].y;
             r[18] = gU.x; r[19] = gU.y;
             r[20] = yt.x; r[21] = yt.y;
-#pragma unroll
-            for (int t = 0; t < 30; ++t) r[t] = warp_allsum(r[t]);
+            warp_allsum_n<30>(r);
             cplx gSS = cmulc(R0c, cmake(r[8], r[9]));
             gSS = cadd(gSS, cmake(r[20], r[21]));
             const cplx gSVY = cneg(cmake(r[18], r[19]));
@@ -716,25 +713,47 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
                 cplx Vo[4], Y[4];
 #pragma unroll
                 for (int mu = 0; mu < 4; ++mu) Vo[mu] = V_s[(o * C + c) * 4 + mu];
+                // encoder: Y = canon(p_i - p_o) = (d0, (ya, -yb), d3, (-ya, -yb)) with real d0, d3, ya, yb -- the contractions
+                // with Y below use that structure (12 instead of 16 multiply-adds each)
+                double d0 = 0.0, d3 = 0.0, ya_ = 0.0, yb_ = 0.0;
                 if (ENC) {
                     double d[4];
 #pragma unroll
                     for (int mu = 0; mu < 4; ++mu) d[mu] = pa[mu] - p_s[4 * o + mu];
                     canon_from_real(d, Y);
+                    d0 = Y[0].x; d3 = Y[2].x; ya_ = Y[1].x; yb_ = -Y[1].y;
                 } else {
 #pragma unroll
                     for (int mu = 0; mu < 4; ++mu) Y[mu] = csub(ya[mu], reinterpret_cast<const cplx*>(p_s)[4 * o + mu]);
                 }
+                // sum_mu conj(Y_mu) g_mu  and  eta(v, Y)
+                auto ydot = [&](const cplx* gq) {
+                    if (ENC) {
+                        const cplx dm = csub(gq[1], gq[3]), sp = cadd(gq[1], gq[3]);
+                        return cmake(fma(d0, gq[0].x, fma(d3, gq[2].x, fma(ya_, dm.x, -yb_ * sp.y))),
+                                     fma(d0, gq[0].y, fma(d3, gq[2].y, fma(ya_, dm.y, yb_ * sp.x))));
+                    }
+                    cplx w = czero();
+#pragma unroll
+                    for (int mu = 0; mu < 4; ++mu) cfmac(w, Y[mu], gq[mu]);
+                    return w;
+                };
+                auto yeta = [&](const cplx* v) {
+                    if (ENC) {
+                        const cplx vm = csub(v[3], v[1]), vp = cadd(v[1], v[3]);
+                        return cmake(fma(d0, v[0].x, fma(-d3, v[2].x, fma(ya_, vm.x, yb_ * vp.y))),
+                                     fma(d0, v[0].y, fma(-d3, v[2].y, fma(ya_, vm.y, -yb_ * vp.x))));
+                    }
+                    return ceta(v, Y);
+                };
                 // role 1: own = receiving node i, other = neighbour j.  Y = Y_ij.
                 {
-                    cplx w = czero(), gR0 = czero();
+                    cplx gR0 = czero();
 #pragma unroll
-                    for (int mu = 0; mu < 4; ++mu) {
-                        cfmac(w, Y[mu], gAa[5 + mu]);
-                        cfmac(gR0, Vo[mu], gAa[mu]);
-                    }
+                    for (int mu = 0; mu < 4; ++mu) cfmac(gR0, Vo[mu], gAa[mu]);
+                    const cplx w = ydot(gAa + 5);
                     cfmac(gR0, So, gAa[4]);
-                    const cplx e = ceta(Vo, Y);
+                    const cplx e = yeta(Vo);
                     cplx gR1 = cmulc(So, w);
                     cfmac(gR1, e, gAa[9]);
                     if (ENC) {
@@ -766,9 +785,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
 #pragma unroll
                     for (int mu = 0; mu < 4; ++mu) Yn[mu] = cneg(Y[mu]);
                     cghat(Yn, gh);
-                    cplx w = czero();
-#pragma unroll
-                    for (int mu = 0; mu < 4; ++mu) cfmac(w, Yn[mu], gAo[5 + mu]);
+                    const cplx w = cneg(ydot(gAo + 5));   // sum_mu conj(-Y_mu) gA1Y_o
                     const cplx r1g = cmulc(R1, gAo[9]);   // conj(R1) gA1E_i
 #pragma unroll
                     for (int mu = 0; mu < 4; ++mu) {

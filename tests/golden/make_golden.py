@@ -125,15 +125,23 @@ CONFIGS = {
     # wide family: maxdim 3 + 'mix' latent map
     "md3_mix_n5": dict(seed=7, batch=2, n=5, maxdim=3, enc_channels=[2, 2, 3, 3], dec_channels=[3, 3, 2, 2], tau_s=1, tau_v=2,
                        map_to_latent="mix", mass_scale=0.1, pad=False, mlp_depth=2, mlp_width=2),
+    # more than 32 particles per jet (two particle blocks per CTA in the forward kernels; cfg-5 has 150): forward parity
+    "n40_b2": dict(seed=9, batch=2, n=40, maxdim=2, enc_channels=[2, 2, 3, 3], dec_channels=[3, 3, 2, 2], tau_s=1, tau_v=4,
+                   map_to_latent="min&max", mass_scale=1e-6, pad=True, mlp_depth=2, mlp_width=2),
 }
 
 
 def main():
+    only = sys.argv[1:]
     for name, cfg in CONFIGS.items():
+        if only and name not in only:
+            continue
         out = run(cfg)
         path = os.path.join(HERE, f"{name}.pt")
         torch.save(out, path)
         print(name, "loss", float(out["loss"]), os.path.getsize(path) // 1024, "KiB")
+    if only:
+        return
     cg = CGDict(maxdim=3, dtype=torch.float64)
     torch.save({str(k): {str(kk): vv.clone() for kk, vv in v.items()} for k, v in cg.items()}, os.path.join(HERE, "cg_maxdim3.pt"))
     # scalar KATs on the basis changes

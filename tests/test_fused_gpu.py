@@ -39,7 +39,7 @@ def _run(g, dev):
                 recon=recon, gen00=gen00, ws_d=ws_d)
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + ["n40_b2"])
 def test_forward_matches_reference(name):
     dev = torch.device("cuda:0")
     g = load_golden(name)

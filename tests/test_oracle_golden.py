@@ -7,7 +7,7 @@ from oracle import lgae_oracle as orc
 from tests.helpers import dec_cfg, enc_cfg, load_golden, rel_err
 
 TOL = 1e-12  # fp64, identical operation order up to BLAS/summation details
-CASES = ["cfg1_b3", "pad_n8", "mean_n6", "md3_mix_n5"]
+CASES = ["cfg1_b3", "pad_n8", "mean_n6", "md3_mix_n5", "n40_b2"]
 
 
 def test_cg_coefficients_match_reference():
