@@ -258,8 +258,15 @@ def main():
             table[name] = ent
         top = max((k for k in table if k in fam), key=lambda k: table[k]["share"])
         t = table[top]
+        # DRAM bytes per launch of that kernel from this round's `ncu --set full` capture (profiles/r01_traffic.json)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"][top]
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except (OSError, KeyError, ValueError):
+            pass
         roofline = {"bound": "tensor", "kernel": top, "achieved": t["tflops"], "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                    "frac": t["frac_of_fp64_peak"], "traffic": None, "kernel_ms": t["ms_per_launch"], "launches_per_step": t["launches_per_step"],
+                    "frac": t["frac_of_fp64_peak"], "traffic": traffic, "kernel_ms": t["ms_per_launch"], "launches_per_step": t["launches_per_step"],
                     "flops_per_launch": fam[top] / t["launches_per_step"],
                     "peak_source": "fp64 pipe: DMMA m8n8k4 37.1 TFLOP/s / DFMA 33.7 TFLOP/s measured with tools/fp64_peak.cu on this pool "
                                    "(profiles/fp64_peak_r01.json; MEASURED_PEAKS.json holds no fp64 figure)",
