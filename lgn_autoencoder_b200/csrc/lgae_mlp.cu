@@ -245,6 +245,24 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
                 }
             }
         }
+        // the saved activations feeding layer l (its input H_l) are fetched into registers one layer ahead, so their L2 / HBM
+        // latency overlaps the MMA work of layer l + 1
+        constexpr int PER = (8 * WP / 4 + 31) / 32;
+        double4 hv[TU][PER];
+        auto fetch_h = [&](int layer) {
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                const int rl = (warp + NWARP * u) * 8;
+                const double4* src = reinterpret_cast<const double4*>(a.acts + ((int64_t)(layer - 1) * a.rows + r0 + rl) * WP);
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const int idx = lane + 32 * j, rr = idx / (WP / 4);
+                    hv[u][j] = make_double4(0.0, 0.0, 0.0, 0.0);
+                    if (rl < ksteps * 4 && idx < 8 * WP / 4 && r0 + rl + rr < slab1) hv[u][j] = src[idx];
+                }
+            }
+        };
+        if (last > 0) fetch_h(last);
         const double* wl = w_s + wtotal;
         for (int l = last; l >= 0; --l) {
             const int nout = l == last ? a.nin : a.width, nink = l == 0 ? a.nin : a.width;
@@ -261,20 +279,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
                         if (nt < NOt)
                             *reinterpret_cast<double2*>(dz_s + (rl + g) * WS + 8 * nt + 2 * q) = make_double2(dz[u][nt][0], dz[u][nt][1]);
                     if (l > 0) {
-                        // 8 consecutive rows of the saved activations are one contiguous run of 8*WP doubles
-                        const double4* src = reinterpret_cast<const double4*>(a.acts + ((int64_t)(l - 1) * a.rows + r0 + rl) * WP);
-                        constexpr int PER = (8 * WP / 4 + 31) / 32;
-                        double4 v[PER];
-#pragma unroll
-                        for (int j = 0; j < PER; ++j) {
-                            const int idx = lane + 32 * j, rr = idx / (WP / 4);
-                            v[j] = make_double4(0.0, 0.0, 0.0, 0.0);
-                            if (idx < 8 * WP / 4 && r0 + rl + rr < slab1) v[j] = src[idx];
-                        }
+                        // 8 consecutive rows of the saved activations are one contiguous run of 8*WP doubles (prefetched above)
 #pragma unroll
                         for (int j = 0; j < PER; ++j) {
                             const int idx = lane + 32 * j, rr = idx / (WP / 4), c4 = idx % (WP / 4);
-                            if (idx < 8 * WP / 4) *reinterpret_cast<double4*>(h_s + (rl + rr) * WS + 4 * c4) = v[j];
+                            if (idx < 8 * WP / 4) *reinterpret_cast<double4*>(h_s + (rl + rr) * WS + 4 * c4) = hv[u][j];
                         }
                     } else {
                         for (int idx = lane; idx < 8 * 8 * NTI; idx += 32) {
@@ -285,6 +294,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
                     }
                 }
             }
+            if (l > 1) fetch_h(l - 1);
             __syncthreads();
             // ---- bias gradient: column sums of dZ (each warp sums a slice of rows, then the slices are added) ----
             {
