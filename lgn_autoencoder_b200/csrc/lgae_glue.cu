@@ -215,13 +215,25 @@ __global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a)
     cplx* gL11 = gL00 + rows * ts;                    // rows*tv*4 (canonical after the basis change)
     cplx* gw00 = gL11 + rows * tv * 4;                // ts*cin
     cplx* gw11 = gw00 + ts * cin;                     // tv*cin
+    cplx* w00_s = gw11 + tv * cin;                    // ts*cin   latent weights, interleaved
+    cplx* w11_s = w00_s + ts * cin;                   // tv*cin
+    cplx* S_s = w11_s + tv * cin;                     // N*C      this jet's node features
+    cplx* V_s = S_s + N * C;                          // N*C*4
     for (int t = tid; t < (ts + tv) * cin; t += blockDim.x) gw00[t] = czero();
+    for (int t = tid; t < ts * cin; t += blockDim.x) w00_s[t] = wget(a.theta, a.off00, ts, cin, t / cin, t % cin);
+    for (int t = tid; t < tv * cin; t += blockDim.x) w11_s[t] = wget(a.theta, a.off11, tv, cin, t / cin, t % cin);
     const bool both = mode == LGAE_LATENT_MINMAX;
     const int Ts = both ? 2 * ts : ts, Tv = both ? 2 * tv : tv;
     const int tmax = ts > tv ? ts : tv;
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
         for (int t = tid; t < rows * (ts + 4 * tv); t += blockDim.x) gL00[t] = czero();
+        {   // node features of the jet -> shared memory (16-byte vector loads, all in flight)
+            const double2* gs = reinterpret_cast<const double2*>(a.S) + (int64_t)b * N * C;
+            const double2* gv = reinterpret_cast<const double2*>(a.V) + (int64_t)b * N * C * 4;
+            for (int t = tid; t < N * C; t += blockDim.x) S_s[t] = gs[t];
+            for (int t = tid; t < N * C * 4; t += blockDim.x) V_s[t] = gv[t];
+        }
         __syncthreads();
         if (mode == LGAE_LATENT_MEAN || mode == LGAE_LATENT_SUM || mix) {
             const double scale = mode == LGAE_LATENT_MEAN ? 1.0 / N : 1.0;
@@ -273,15 +285,15 @@ __global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a)
             for (int mu = 0; mu < 4; ++mu) gL11[it * 4 + mu] = gy[mu];
         }
         __syncthreads();
-        const cplx* S = reinterpret_cast<const cplx*>(a.S) + (int64_t)b * N * C;
-        const cplx* V = reinterpret_cast<const cplx*>(a.V) + (int64_t)b * N * C * 4;
+        const cplx* S = S_s;
+        const cplx* V = V_s;
         // feature gradients
         for (int it = tid; it < rows * cin; it += blockDim.x) {
             const int i = it / cin, k = it % cin;
             cplx gs = czero(), gv[4] = {czero(), czero(), czero(), czero()};
-            for (int t = 0; t < ts; ++t) cfmac(gs, wget(a.theta, a.off00, ts, cin, t, k), gL00[i * ts + t]);
+            for (int t = 0; t < ts; ++t) cfmac(gs, w00_s[t * cin + k], gL00[i * ts + t]);
             for (int t = 0; t < tv; ++t) {
-                const cplx w = wget(a.theta, a.off11, tv, cin, t, k);
+                const cplx w = w11_s[t * cin + k];
 #pragma unroll
                 for (int mu = 0; mu < 4; ++mu) cfmac(gv[mu], w, gL11[(i * tv + t) * 4 + mu]);
             }
@@ -730,7 +742,7 @@ int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const
         if (int rc = plan->seg(a.off11, off, w, n00, n11, grid)) return rc;
         a.partials = plan->base + off; a.part_stride = w; a.po00 = 0; a.po11 = n00;
     }
-    const size_t bytes = ((size_t)rows * (a.tau_s + 4 * a.tau_v) + (size_t)(a.tau_s + a.tau_v) * cin) * sizeof(cplx);
+    const size_t bytes = ((size_t)rows * (a.tau_s + 4 * a.tau_v) + (size_t)2 * (a.tau_s + a.tau_v) * cin + (size_t)5 * a.N * a.C) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)enc_latent_bwd_kernel, bytes)) return rc;
     LaunchScope ls_("enc_latent_bwd", st);

@@ -104,6 +104,12 @@ class FusedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
         self._thetas = None
+        # pinned host staging: with `step_host` the host->device copy of the jets and the device->host copy of the loss are
+        # nodes of the same CUDA graph, so an end-to-end step is one graph launch + one stream synchronisation
+        self.host_p4 = torch.zeros((B, N, 4), dtype=torch.float64).pin_memory()
+        self.host_mask = torch.ones((B, N), dtype=torch.uint8).pin_memory() if use_labels else None
+        self.host_loss = torch.zeros((), dtype=torch.float64).pin_memory()
+        self.graph_host: Optional[torch.cuda.CUDAGraph] = None
 
     def _bind_grads(self):
         for model, plan, flat in ((self.enc, self.pe, self.g_e), (self.dec, self.pd, self.g_d)):
@@ -168,3 +174,35 @@ class FusedTrainStep:
     def step(self, p4, labels=None):
         self.load(p4, labels)
         return self.run()
+
+    def _launch_host(self):
+        self.p4_in.copy_(self.host_p4, non_blocking=True)
+        if self.mask is not None:
+            self.mask.copy_(self.host_mask, non_blocking=True)
+        self._launch()
+        self.host_loss.copy_(self.loss, non_blocking=True)
+
+    def step_host(self, p4=None, labels=None) -> float:
+        """End-to-end step from host memory: jets (B,N,4) are staged in the pinned buffer ``host_p4`` (pass ``p4=None`` if the
+        data loader already wrote them there), copied to the device, the step runs, and the loss comes back as a float."""
+        if p4 is not None and p4.data_ptr() != self.host_p4.data_ptr():
+            self.host_p4.copy_(p4)
+        if self.host_mask is not None and labels is not None:
+            self.host_mask.copy_((labels != 0).to(torch.uint8))
+        if not self.use_graph:
+            self._launch_host()
+        else:
+            if self.graph_host is None or self._params_moved():
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._launch_host()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                self.graph_host = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph_host):
+                    self._launch_host()
+                self._bind_grads()
+            self.graph_host.replay()
+        torch.cuda.current_stream().synchronize()
+        return float(self.host_loss)

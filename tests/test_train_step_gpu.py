@@ -50,3 +50,18 @@ def test_fused_train_step_padded_jets_and_optimizer():
     opt.step()
     l2 = step.step(batch["p4"], batch["labels"]).item()
     assert l2 != l0
+
+
+def test_step_host_matches_step():
+    """End-to-end entry (pinned staging + in-graph copies) gives the same loss and gradients as the device-resident step."""
+    from lgn_autoencoder_b200.train import FusedTrainStep
+    dev = torch.device("cuda:0")
+    g, enc, dec, batch = load("cfg1_b3", dev)
+    step = FusedTrainStep(enc, dec, batch["p4"].shape[0], l1_lambda=1e-8, normalize=False, use_graph=True)
+    l_dev = step.step(batch["p4"]).item()
+    g_dev = step.g_e.clone()
+    for _ in range(2):
+        l_host = step.step_host(batch["p4"].cpu())
+    assert l_host == l_dev
+    assert torch.equal(step.g_e, g_dev)
+    assert abs(l_host - g["loss"].item()) < 1e-10 * abs(g["loss"].item())
