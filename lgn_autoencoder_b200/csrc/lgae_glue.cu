@@ -403,21 +403,23 @@ __global__ void __launch_bounds__(128) dec_input_bwd_kernel(const DecInArgs a) {
             for (int mu = 0; mu < 4; ++mu) gP_s[i * 4 + mu] = gP[mu];
         }
         __syncthreads();
-        // input-mix weight gradients (reduce over particles with shared-memory atomics: N*C*2 adds per jet)
-        for (int it = tid; it < N * C; it += blockDim.x) {
-            const int i = it / C, c = it % C;
-            const int64_t node = (int64_t)b * N + i;
-            cplx g11 = czero();
+        // input-mix weight gradients: one warp per (which, c), lanes over the particles, butterfly sum (fixed order)
+        for (int it = tid >> 5; it < 2 * C; it += blockDim.x >> 5) {
+            const int which = it / C, c = it % C, lane = tid & 31;
+            cplx acc = czero();
+            for (int i = lane; i < N; i += 32) {
+                const int64_t node = (int64_t)b * N + i;
+                if (which) {
 #pragma unroll
-            for (int mu = 0; mu < 4; ++mu)
-                cfmac(g11, reinterpret_cast<const cplx*>(a.y)[node * 4 + mu], reinterpret_cast<const cplx*>(a.gV)[(node * C + c) * 4 + mu]);
-            atomicAdd(&gin[C + c].x, g11.x);
-            atomicAdd(&gin[C + c].y, g11.y);
-            if (a.gS) {
-                const cplx g00 = cmul_1mi(reinterpret_cast<const cplx*>(a.gS)[node * C + c]);
-                atomicAdd(&gin[c].x, g00.x);
-                atomicAdd(&gin[c].y, g00.y);
+                    for (int mu = 0; mu < 4; ++mu)
+                        cfmac(acc, reinterpret_cast<const cplx*>(a.y)[node * 4 + mu], reinterpret_cast<const cplx*>(a.gV)[(node * C + c) * 4 + mu]);
+                } else if (a.gS) {
+                    acc = cadd(acc, cmul_1mi(reinterpret_cast<const cplx*>(a.gS)[node * C + c]));
+                }
             }
+            acc.x = warp_sum(acc.x);
+            acc.y = warp_sum(acc.y);
+            if (lane == 0) gin[which * C + c] = cadd(gin[which * C + c], acc);
         }
         // latent_to_graph weight gradient and latent gradient
         for (int it = tid; it < N * tau; it += blockDim.x) {

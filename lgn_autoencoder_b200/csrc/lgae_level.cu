@@ -404,7 +404,7 @@ __host__ __device__ inline LevelBwdSmem level_bwd_smem(bool enc, int N, int C, i
     s.m11 = o; o += 2 * Cout * 5 * C;
     s.gm = o; o += 2 * 2 * Cout * 5 * C;     // [irrep][c'][k] complex accumulators, live for the whole CTA
     s.gA = o; o += 2 * C * 10 * 32;          // [(c*10+e)][32] complex: adjoints of the neighbour sums
-    s.gy = o; o += enc ? 0 : 2 * 4 * 32;
+    s.gy = o; o += enc ? 0 : 2 * 4 * 32 * C;   // decoder: per-channel dL/dy, summed over channels in a fixed order
     o = (o + 3) & ~3;
     s.gout = o; o += 2 * Cout * 5 * 32;      // incoming gradients [(c'*5+comp)][32] complex
     s.graw = o; o += 2 * N * Cout * 5;       // the same as they lie in HBM: g_s_pre (N,C') | g_v_out (N,C',4), bulk-copied
@@ -507,8 +507,6 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
                 if (a.g_s_pre) bulk_g2s(smem + L.graw, a.g_s_pre + (int64_t)b * N * Cout * 2, gs_bytes, &mbar);
                 bulk_g2s(smem + L.graw + 2 * N * Cout, a.g_v_out + (int64_t)b * N * Cout * 8, 8 * N * Cout * sizeof(double), &mbar);
             }
-            if (!ENC)
-                for (int t = tid; t < 4 * 32; t += blockDim.x) gy_s[t] = czero();
         }
         // encoder: first radial weights of this jet, in flight while the mix adjoint runs
         const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
@@ -816,18 +814,15 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
             for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(a.g_v_in)[((int64_t)(b * N + i) * C + c) * 4 + mu] = gV[mu];
         }
         if (!ENC) {
-            if (live) {
 #pragma unroll
-                for (int mu = 0; mu < 4; ++mu) {
-                    atomicAdd(&gy_s[mu * 32 + lane].x, gy[mu].x);
-                    atomicAdd(&gy_s[mu * 32 + lane].y, gy[mu].y);
-                }
-            }
+            for (int mu = 0; mu < 4; ++mu) gy_s[(c * 4 + mu) * 32 + lane] = live ? gy[mu] : czero();
             __syncthreads();
             for (int t = tid; t < 4 * N; t += blockDim.x) {
                 const int ii = t >> 2, mu = t & 3;
                 cplx* dst = reinterpret_cast<cplx*>(a.g_y) + (int64_t)(b * N + ii) * 4 + mu;
-                *dst = cadd(*dst, gy_s[mu * 32 + ii]);
+                cplx acc = *dst;
+                for (int cc = 0; cc < C; ++cc) acc = cadd(acc, gy_s[(cc * 4 + mu) * 32 + ii]);   // fixed order: deterministic
+                *dst = acc;
             }
         }
     }

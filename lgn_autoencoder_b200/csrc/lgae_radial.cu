@@ -38,13 +38,18 @@ LGAE_DEV double rad_pair_norm(const double* pi, const double* pj) {
     const double s = __dadd_rn(minkowski_sq(d0, d1, d2, d3), 1e-16);
     return s != 0.0 ? __ddiv_rn(s, __dsqrt_rn(fabs(s))) : s;
 }
+// The MMA columns are ordered channel-major, col = 4 c + 2 l + (re|im), i.e. exactly the (R0.re, R0.im, R1.re, R1.im) record
+// of a channel: neighbouring lanes of a fragment then touch the same 32-byte sector of r / g_r.  Row 2c + (re|im) of
+// linear.l (position_levels.py:171-176) is column col.
 LGAE_DEV double rad_w(const RadialArgs& a, int col, int k) {
     if (k >= a.K || col >= 4 * a.C) return 0.0;
-    return col < 2 * a.C ? a.theta[a.off_w0 + (int64_t)col * a.K + k] : a.theta[a.off_w1 + (int64_t)(col - 2 * a.C) * a.K + k];
+    const int o = 2 * (col >> 2) + (col & 1);
+    return a.theta[(((col >> 1) & 1) ? a.off_w1 : a.off_w0) + (int64_t)o * a.K + k];
 }
 LGAE_DEV double rad_bias(const RadialArgs& a, int col) {
     if (col >= 4 * a.C) return 0.0;
-    return col < 2 * a.C ? a.theta[a.off_b0 + col] : a.theta[a.off_b1 + col - 2 * a.C];
+    const int o = 2 * (col >> 2) + (col & 1);
+    return a.theta[(((col >> 1) & 1) ? a.off_b1 : a.off_b0) + o];
 }
 // unordered pairs (i <= j) of one jet in the order p = j (j + 1) / 2 + i
 LGAE_DEV void build_pair_table(int N, unsigned char* ti, unsigned char* tj) {
@@ -67,6 +72,12 @@ LGAE_DEV double rcp_ge1(double x) {
 }
 
 constexpr int RAD_UNIT = 16;   // pairs per work unit (two MMA groups of 8)
+#ifndef LGAE_RFWD_CTAS
+#define LGAE_RFWD_CTAS 4       // resident CTAs per SM the radial forward is launched with
+#endif
+#ifndef LGAE_RBWD_CTAS
+#define LGAE_RBWD_CTAS 3       // ... and the radial adjoint (also its register cap: 3 -> 168, 4 -> 128)
+#endif
 
 // ------------------------------------------------------------------------------------------------------------
 // forward
@@ -75,7 +86,7 @@ constexpr int RAD_UNIT = 16;   // pairs per work unit (two MMA groups of 8)
 // MMA groups of the unit pick theirs up by shuffle.  Also writes nrm (B, NPS): n_ij, or NaN where the edge is masked,
 // which is all the adjoint needs to re-evaluate the basis functions.
 template <int NT, int KS>
-__global__ void __launch_bounds__(128, 4) radial_fwd_kernel(const RadialArgs a) {
+__global__ void __launch_bounds__(128, LGAE_RFWD_CTAS) radial_fwd_kernel(const RadialArgs a) {
     constexpr int KP = 4 * KS;
     __shared__ unsigned char ti[RAD_MAXP + RAD_UNIT], tj[RAD_MAXP + RAD_UNIT];
     __shared__ double abc_s[3 * KP];
@@ -153,7 +164,7 @@ __global__ void __launch_bounds__(128, 4) radial_fwd_kernel(const RadialArgs a) 
             for (int nt = 0; nt < NT; ++nt) {
                 const int col = 8 * nt + 2 * q;
                 if (col < 4 * C) {
-                    const int l = col >= 2 * C ? 1 : 0, cc = (col - l * 2 * C) >> 1;
+                    const int l = (col >> 1) & 1, cc = col >> 2;
                     const double2 v = make_double2(acc[u][nt][0], acc[u][nt][1]);
                     *reinterpret_cast<double2*>(rb + ((int64_t)(j * C + cc) * 32 + i) * 4 + 2 * l) = v;
                     if (i != j) *reinterpret_cast<double2*>(rb + ((int64_t)(i * C + cc) * 32 + j) * 4 + 2 * l) = v;
@@ -209,7 +220,7 @@ LGAE_DEV void rad_fetch(const RadialArgs& a, const unsigned char* ti, const unsi
 }
 
 template <int NT, int KS>
-__global__ void __launch_bounds__(128, 3) radial_bwd_kernel(const RadialArgs a) {
+__global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_kernel(const RadialArgs a) {
     constexpr int KP = 4 * KS;
     constexpr int NT2 = KS / 2 + 1;
     constexpr int NK = 8 * NT2, NCOL = 8 * NT;
@@ -238,9 +249,8 @@ __global__ void __launch_bounds__(128, 3) radial_bwd_kernel(const RadialArgs a) 
 #pragma unroll
     for (int mt = 0; mt < NT; ++mt) {
         const int col = 8 * mt + g;
-        const int l = col >= 2 * C ? 1 : 0, rem = col - l * 2 * C;
-        col_cc[mt] = col < 4 * C ? (rem >> 1) : -1;
-        col_x[mt] = 2 * l + (rem & 1);
+        col_cc[mt] = col < 4 * C ? (col >> 2) : -1;
+        col_x[mt] = col & 3;
     }
     // c_k of this lane's B-fragment columns k = 8 nt + g
     double ck[NT2];
@@ -311,7 +321,7 @@ __global__ void __launch_bounds__(128, 3) radial_bwd_kernel(const RadialArgs a) 
     const double* g2 = red + NCOL * NK;
     for (int t = threadIdx.x; t < 4 * C * (K + 1); t += blockDim.x) {
         const int col = t / (K + 1), k = t % (K + 1);
-        const int l = col >= 2 * C ? 1 : 0, o = col - l * 2 * C;
+        const int l = (col >> 1) & 1, o = 2 * (col >> 2) + (col & 1);
         if (k < K)
             row[(l ? a.po_w1 : a.po_w0) + (int64_t)o * K + k] = abc_s[KP + k] * g1[col * NK + k] + abc_s[k] * g1[col * NK + K + 1];
         else
@@ -332,8 +342,8 @@ __global__ void __launch_bounds__(128, 3) radial_bwd_kernel(const RadialArgs a) 
 // ------------------------------------------------------------------------------------------------------------
 static int pick_ks(int K) { return K <= 12 ? 3 : (K <= 20 ? 5 : (K <= 32 ? 8 : -1)); }
 
-int radial_fwd_grid() { return 4 * sm_count(); }
-int radial_grid() { return 3 * sm_count(); }   // adjoint: CTAs = rows of partials
+int radial_fwd_grid() { return LGAE_RFWD_CTAS * sm_count(); }
+int radial_grid() { return LGAE_RBWD_CTAS * sm_count(); }   // adjoint: CTAs = rows of partials
 // doubles per jet of the pair-norm record (unordered pairs padded to whole units)
 int64_t radial_nrm_stride(int n) { const int np = n * (n + 1) / 2; return (int64_t)((np + RAD_UNIT - 1) / RAD_UNIT) * RAD_UNIT; }
 
