@@ -43,6 +43,9 @@ struct LevelArgs {
     int B, N, C, Cout, K;
 };
 
+#ifndef LGAE_LBWD_CF_MINB
+#define LGAE_LBWD_CF_MINB 3   // the same for the decoder's closed-form adjoint
+#endif
 #ifndef LGAE_LBWD_MINB
 #define LGAE_LBWD_MINB 3   // resident CTAs per SM the level adjoint is compiled for (register cap 168; 4 => 128 registers spills and is slower)
 #endif
@@ -886,7 +889,7 @@ static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
         kern<<<grid, 32 * a.C, bytes, st>>>(a);                               \
     }
     if (a.C <= 4) {
-        if (cf) LGAE_LAUNCH(128, LGAE_LBWD_MINB, true) else LGAE_LAUNCH(128, LGAE_LBWD_MINB, false)
+        if (cf) LGAE_LAUNCH(128, LGAE_LBWD_CF_MINB, true) else LGAE_LAUNCH(128, LGAE_LBWD_MINB, false)
     } else {
         if (cf) LGAE_LAUNCH(256, 1, true) else LGAE_LAUNCH(256, 1, false)
     }

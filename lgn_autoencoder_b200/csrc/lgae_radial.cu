@@ -253,9 +253,17 @@ __global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_kernel(const R
         col_x[mt] = col & 3;
     }
     // c_k of this lane's B-fragment columns k = 8 nt + g
-    double ck[NT2];
+    // and what that column is: a basis function (k < K), the bias column (k == K: 1), the mask column (k == K + 1: m)
+    double ck[NT2], c_one[NT2], c_msk[NT2];
+    bool isb[NT2];
 #pragma unroll
-    for (int nt = 0; nt < NT2; ++nt) ck[nt] = (8 * nt + g) < K ? abc_s[2 * KP + 8 * nt + g] : 0.0;
+    for (int nt = 0; nt < NT2; ++nt) {
+        const int k = 8 * nt + g;
+        isb[nt] = k < K;
+        ck[nt] = isb[nt] ? abc_s[2 * KP + k] : 0.0;
+        c_one[nt] = k == K ? 1.0 : 0.0;
+        c_msk[nt] = k == K + 1 ? 1.0 : 0.0;
+    }
 
     const int NP = N * (N + 1) / 2, NU = (NP + RAD_UNIT - 1) / RAD_UNIT, NPS = NU * RAD_UNIT;
     const int total = a.B * NU, twarps = gridDim.x * nwarps;
@@ -274,27 +282,22 @@ __global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_kernel(const R
                 double a3[NT];
 #pragma unroll
                 for (int mt = 0; mt < NT; ++mt) a3[mt] = cur.g[u][ks][mt][0] + cur.g[u][ks][mt][1];
-                const double nn = n2 * n2;
+                const double ns = m2 ? n2 : 0.0, nn = ns * ns;   // masked pair: every basis column is zero
+                double b1[NT2], b2[NT2];
 #pragma unroll
-                for (int nt = 0; nt < NT2; ++nt) {
-                    const int k = 8 * nt + g;
-                    double b1 = 0.0, b2 = 0.0;
-                    if (k < K) {
-                        const double cn = ck[nt] * n2;
-                        const double rd = rcp_ge1(1.0 + cn * cn + 1e-16);
-                        b1 = m2 ? rd : 0.0;
-                        b2 = m2 ? nn * rd * rd : 0.0;
-                    } else if (k == K) {
-                        b1 = 1.0;
-                    } else if (k == K + 1) {
-                        b1 = m2 ? 1.0 : 0.0;
-                    }
+                for (int nt = 0; nt < NT2; ++nt) {   // branch-free: all reciprocal chains of the k-step in flight
+                    const double cn = ck[nt] * ns;
+                    const double rd = rcp_ge1(1.0 + cn * cn + 1e-16);
+                    b1[nt] = isb[nt] ? (m2 ? rd : 0.0) : c_one[nt] + (m2 ? c_msk[nt] : 0.0);
+                    b2[nt] = isb[nt] ? nn * rd * rd : 0.0;
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT2; ++nt)
 #pragma unroll
                     for (int mt = 0; mt < NT; ++mt) {
-                        dmma(G1[mt][nt][0], G1[mt][nt][1], a3[mt], b1);
-                        dmma(G2[mt][nt][0], G2[mt][nt][1], a3[mt], b2);
+                        dmma(G1[mt][nt][0], G1[mt][nt][1], a3[mt], b1[nt]);
+                        dmma(G2[mt][nt][0], G2[mt][nt][1], a3[mt], b2[nt]);
                     }
-                }
             }
         }
         cur = nxt;
