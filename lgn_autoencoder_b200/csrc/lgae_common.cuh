@@ -260,7 +260,7 @@ LGAE_DEV double warp_sum16(const double (&v)[16]) {
 // Every backward kernel writes one compact row of parameter-gradient partials per CTA into its own block of the
 // scratch buffer `partials`; one reduce launch then sums the rows of every block into gtheta.  A segment maps a
 // contiguous range of theta to a column range of a block.
-#define LGAE_MAX_SEGS 320
+#define LGAE_MAX_SEGS 64
 struct Seg {
     int64_t theta_off;  // first parameter (offset in theta / gtheta)
     int64_t part_off;   // offset (doubles) of row 0, column 0 of this segment inside `partials`

@@ -141,9 +141,19 @@ class FusedTrainStep:
             dist.all_reduce(self.g_d, op=dist.ReduceOp.SUM, group=self.group)
 
     def _params_moved(self) -> bool:
-        th_e, _ = self.enc._flat_params()
-        th_d, _ = self.dec._flat_params()
-        return self._thetas != (th_e.data_ptr(), th_d.data_ptr())
+        """Cheap per-step check (a few attribute reads): the flat buffers the captured kernels read are still the models'.
+        In-place updates (optimizer steps, load_state_dict) keep them; after ``model.to(...)`` or a manual ``param.data = ...``
+        call ``refresh()``."""
+        te, td = self.enc._theta, self.dec._theta
+        return te is None or td is None or self._thetas != (te.data_ptr(), td.data_ptr())
+
+    def refresh(self):
+        """Re-validate the parameter aliasing (full check) and drop the captured graphs so that the next step re-captures."""
+        self.enc._flat_params()
+        self.dec._flat_params()
+        self.graph = None
+        self.graph_host = None
+        self._bind_grads()
 
     def load(self, p4, labels=None):
         """Copy one batch of jets (host or device tensor, (B,N,4)) into the static input buffer."""
