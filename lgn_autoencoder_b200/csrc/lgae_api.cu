@@ -60,6 +60,10 @@ static char g_cuda_error[512] = "";
 static int g_sm_count = 0;
 
 void count_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("LGAE_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
 
 // ---- optional per-kernel timing ---------------------------------------------------------------------------------
 struct TimedLaunch { const char* name; cudaEvent_t a, b; };

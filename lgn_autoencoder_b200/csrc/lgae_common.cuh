@@ -302,7 +302,32 @@ struct PartPlan {
     }
 };
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialisation attribute and starts with
+// pdl_launch(): the next kernel in the stream may then be scheduled while this one is still running, runs the part of its
+// prologue that only touches step-constant data (weights in theta, index tables, barrier setup) and blocks in pdl_wait()
+// until all earlier kernels have completed and flushed their writes.  Every read of a predecessor's output and every global
+// write comes after pdl_wait().  The launch latency and the prologues of the ~45 kernels of a step overlap the previous
+// kernel's tail; captured in a CUDA graph the edges become programmatic dependencies.  LGAE_NO_PDL=1 disables it.
+LGAE_DEV void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+LGAE_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- host side ------------------------------------------------------------------------------------
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 void count_launch(int n = 1);
 // Scope around one kernel launch: counts it and, when per-kernel timing is enabled (lgae_timing_enable), brackets it with
 // CUDA events on the launch stream so that bench.py can report measured per-kernel durations without a profiler.

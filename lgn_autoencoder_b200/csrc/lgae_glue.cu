@@ -30,6 +30,8 @@ LGAE_DEV void pput(double* part, int64_t off, int rows, int cols, int r, int cc,
 // ------------------------------------------------------------------------------------------------------------
 __global__ void enc_input_kernel(const double* theta, int64_t off00, int64_t off11, const double* p4, int64_t nodes, int C,
                                  double* mass, double* S, double* V) {
+    pdl_launch();
+    pdl_wait();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nodes) return;
     const double* p = p4 + 4 * t;
@@ -47,6 +49,8 @@ __global__ void enc_input_kernel(const double* theta, int64_t off00, int64_t off
 
 __global__ void __launch_bounds__(256) enc_input_bwd_kernel(int64_t off00, int64_t off11, const double* p4, const double* mass, int64_t nodes,
                                                             int C, const double* gS, const double* gV, double* partials, int64_t part_stride) {
+    pdl_launch();
+    pdl_wait();
     __shared__ double scratch[32];
     double acc[MAXC][4];
 #pragma unroll
@@ -114,6 +118,8 @@ LGAE_DEV double msq_of(const double* v) {   // get_msq, lgn_encoder.py:499-505 (
 
 // One CTA per jet.  Shared: L00 (N*tau_s complex), L11 Cartesian (N*tau_v*4 complex).
 __global__ void __launch_bounds__(256) enc_latent_kernel(const LatentArgs a) {
+    pdl_launch();
+    pdl_wait();
     extern __shared__ __align__(128) double smem[];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int N = a.N, C = a.C, ts = a.tau_s, tv = a.tau_v;
@@ -206,6 +212,8 @@ __global__ void __launch_bounds__(256) enc_latent_kernel(const LatentArgs a) {
 
 // Adjoint of enc_latent.  Persistent CTAs over jets; latent-weight gradients accumulate in shared memory.
 __global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a) {
+    pdl_launch();
+    pdl_wait();
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x;
     const int N = a.N, C = a.C, ts = a.tau_s, tv = a.tau_v, B = a.B, mode = a.mode;
@@ -343,6 +351,8 @@ struct DecInArgs {
 };
 
 __global__ void __launch_bounds__(128) dec_input_kernel(const DecInArgs a) {
+    pdl_launch();
+    pdl_wait();
     extern __shared__ __align__(128) double smem[];
     cplx* lat = reinterpret_cast<cplx*>(smem);   // tau*4
     const int b = blockIdx.x, tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau, B = a.B;
@@ -372,6 +382,8 @@ __global__ void __launch_bounds__(128) dec_input_kernel(const DecInArgs a) {
 
 // Persistent over jets, one thread per particle (N <= blockDim.x required).
 __global__ void __launch_bounds__(128) dec_input_bwd_kernel(const DecInArgs a) {
+    pdl_launch();
+    pdl_wait();
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau, B = a.B;
     cplx* lat = reinterpret_cast<cplx*>(smem);   // tau*4
@@ -451,6 +463,8 @@ __global__ void __launch_bounds__(128) dec_input_bwd_kernel(const DecInArgs a) {
 // ------------------------------------------------------------------------------------------------------------
 __global__ void dec_output_kernel(const double* theta, int64_t off00, int64_t off11, int B, int N, int C, const double* S,
                                   const double* V, double* recon, double* gen00) {
+    pdl_launch();
+    pdl_wait();
     const int64_t node = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (node >= (int64_t)B * N) return;
     cplx gen[4] = {czero(), czero(), czero(), czero()}, g0 = czero();
@@ -476,6 +490,8 @@ __global__ void dec_output_kernel(const double* theta, int64_t off00, int64_t of
 __global__ void __launch_bounds__(256) dec_output_bwd_kernel(const double* theta, int64_t off00, int64_t off11, int B, int N, int C,
                                                              const double* S, const double* V, const double* g_recon, const double* g_gen00,
                                                              double* gS, double* gV, double* partials, int64_t part_stride) {
+    pdl_launch();
+    pdl_wait();
     __shared__ double scratch[32];
     double acc[MAXC][4];
 #pragma unroll
@@ -528,6 +544,8 @@ __global__ void __launch_bounds__(256) dec_output_bwd_kernel(const double* theta
 // One CTA per jet.  x_i = re(recon_i) + im(recon_i)  (get_real 'sum', utils/utils.py:201-202).
 __global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const double* target, int B, int N, int M, double* jet_loss,
                                                       const double* g_loss, double* g_recon) {
+    pdl_launch();
+    pdl_wait();
     extern __shared__ __align__(128) double smem[];
     double* x = smem;            // N*4
     double* t = x + 4 * N;       // M*4
@@ -588,6 +606,8 @@ __global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const
 
 // Deterministic single-block sum of n values: out[0] = sum (or += when accumulate).
 __global__ void __launch_bounds__(1024) sum_kernel(const double* v, int64_t n, double scale, double* out, int accumulate) {
+    pdl_launch();
+    pdl_wait();
     __shared__ double scratch[32];
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
@@ -596,6 +616,8 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* v, int64_t n, d
 }
 
 __global__ void __launch_bounds__(128) normalize_kernel(const double* p4, int N, double* out, double* factor) {
+    pdl_launch();
+    pdl_wait();
     __shared__ double scratch[32];
     const int b = blockIdx.x;
     double m = 0.0;
@@ -613,6 +635,8 @@ __global__ void __launch_bounds__(128) normalize_kernel(const double* p4, int N,
 
 // Single block: the parameter vector has ~3e4..3e5 entries.  out[0] += lambda * sum|theta| ; gtheta += lambda * sign(theta).
 __global__ void __launch_bounds__(1024) l1_kernel(const double* theta, int64_t n, double lambda, double* out, double* gtheta) {
+    pdl_launch();
+    pdl_wait();
     __shared__ double scratch[32];
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
@@ -627,6 +651,8 @@ __global__ void __launch_bounds__(1024) l1_kernel(const double* theta, int64_t n
 // gtheta = lambda * sign(theta) (the L1 regulariser's gradient; zero when lambda == 0); psum[block] = sum |theta| of the block.
 constexpr int L1_BLOCKS_MAX = 256;
 __global__ void __launch_bounds__(256) grad_init_kernel(const double* theta, int64_t n, double lambda, double* gtheta, double* psum) {
+    pdl_launch();
+    pdl_wait();
     __shared__ double scratch[32];
     double s = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -646,6 +672,8 @@ __global__ void __launch_bounds__(256) grad_init_kernel(const double* theta, int
 // fixed summation order => deterministic gradients.  The extra y-block (blockIdx.y == t.n) adds the L1 term to the loss.
 __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, const double* partials, double* gtheta, const double* psum,
                                                           int npsum, double lambda, double* loss) {
+    pdl_launch();
+    pdl_wait();
     __shared__ double sm[8][33];
     if ((int)blockIdx.y == t.n) {
         if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && loss) {
@@ -690,7 +718,7 @@ __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, cons
 int run_enc_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* mass, double* S, double* V, cudaStream_t st) {
     const int64_t nodes = (int64_t)B * d->n_particles;
     LaunchScope ls_("enc_input", st);
-    enc_input_kernel<<<(unsigned)((nodes + 127) / 128), 128, 0, st>>>(theta, d->off_in00, d->off_in11, p4, nodes, d->channels[0], mass, S, V);
+    launch_k(enc_input_kernel, dim3((unsigned)((nodes + 127) / 128)), dim3(128), 0, st, theta, d->off_in00, d->off_in11, p4, nodes, d->channels[0], mass, S, V);
     return check_launch("enc_input");
 }
 int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* mass, int B, const double* gS, const double* gV,
@@ -701,7 +729,7 @@ int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* ma
     if (int rc = plan->seg(d->off_in00, off, w, 0, 2 * C, grid)) return rc;
     if (int rc = plan->seg(d->off_in11, off, w, 2 * C, 2 * C, grid)) return rc;
     LaunchScope ls_("enc_input_bwd", st);
-    enc_input_bwd_kernel<<<grid, 256, 0, st>>>(0, 2 * C, p4, mass, nodes, C, gS, gV, plan->base + off, w);
+    launch_k(enc_input_bwd_kernel, dim3(grid), dim3(256), 0, st, 0, 2 * C, p4, mass, nodes, C, gS, gV, plan->base + off, w);
     return check_launch("enc_input_bwd");
 }
 
@@ -728,7 +756,7 @@ int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const dou
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)enc_latent_kernel, bytes)) return rc;
     LaunchScope ls_("enc_latent", st);
-    enc_latent_kernel<<<B, 256, bytes, st>>>(a);
+    launch_k(enc_latent_kernel, dim3(B), dim3(256), bytes, st, a);
     return check_launch("enc_latent");
 }
 int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const int32_t* sel,
@@ -748,7 +776,7 @@ int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)enc_latent_bwd_kernel, bytes)) return rc;
     LaunchScope ls_("enc_latent_bwd", st);
-    enc_latent_bwd_kernel<<<grid, 256, bytes, st>>>(a);
+    launch_k(enc_latent_bwd_kernel, dim3(grid), dim3(256), bytes, st, a);
     return check_launch("enc_latent_bwd");
 }
 
@@ -763,7 +791,7 @@ int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const doub
     DecInArgs a = dec_in_args(d, theta, B, lat11, y, S, V);
     const size_t bytes = (size_t)a.tau * 4 * sizeof(cplx);
     LaunchScope ls_("dec_input", st);
-    dec_input_kernel<<<B, 128, bytes, st>>>(a);
+    launch_k(dec_input_kernel, dim3(B), dim3(128), bytes, st, a);
     return check_launch("dec_input");
 }
 int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, const double* gS, const double* gV,
@@ -783,13 +811,13 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)dec_input_bwd_kernel, bytes)) return rc;
     LaunchScope ls_("dec_input_bwd", st);
-    dec_input_bwd_kernel<<<grid, 128, bytes, st>>>(a);
+    launch_k(dec_input_bwd_kernel, dim3(grid), dim3(128), bytes, st, a);
     return check_launch("dec_input_bwd");
 }
 int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st) {
     const int64_t nodes = (int64_t)B * d->n_particles;
     LaunchScope ls_("dec_output", st);
-    dec_output_kernel<<<(unsigned)((nodes + 127) / 128), 128, 0, st>>>(theta, d->off_out00, d->off_out11, B, d->n_particles, d->channels[d->n_levels], S, V, recon, gen00);
+    launch_k(dec_output_kernel, dim3((unsigned)((nodes + 127) / 128)), dim3(128), 0, st, theta, d->off_out00, d->off_out11, B, d->n_particles, d->channels[d->n_levels], S, V, recon, gen00);
     return check_launch("dec_output");
 }
 int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const double* g_recon,
@@ -799,8 +827,7 @@ int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const
     if (int rc = plan->seg(d->off_out00, off, w, 0, 2 * C, grid)) return rc;
     if (int rc = plan->seg(d->off_out11, off, w, 2 * C, 2 * C, grid)) return rc;
     LaunchScope ls_("dec_output_bwd", st);
-    dec_output_bwd_kernel<<<grid, 256, 0, st>>>(theta, d->off_out00, d->off_out11, B, d->n_particles, C, S, V, g_recon,
-                                                 g_gen00, gS, gV, plan->base + off, w);
+    launch_k(dec_output_bwd_kernel, dim3(grid), dim3(256), 0, st, theta, d->off_out00, d->off_out11, B, d->n_particles, C, S, V, g_recon, g_gen00, gS, gV, plan->base + off, w);
     return check_launch("dec_output_bwd");
 }
 // gtheta = lambda sign(theta) (0 when lambda == 0), then every segment of the plan is reduced over its rows and added;
@@ -812,7 +839,7 @@ int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const doub
     double* psum = plan->base + plan->used;
     {
         LaunchScope ls_("grad_init", st);
-        grad_init_kernel<<<nb, 256, 0, st>>>(theta, n_params, l1 ? lambda : 0.0, gtheta, l1 ? psum : nullptr);
+        launch_k(grad_init_kernel, dim3(nb), dim3(256), 0, st, theta, n_params, l1 ? lambda : 0.0, gtheta, l1 ? psum : nullptr);
         if (int rc = check_launch("grad_init")) return rc;
     }
     if (plan->table.n == 0 && !l1) return LGAE_OK;
@@ -821,7 +848,7 @@ int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const doub
     int gx = (maxlen + 31) / 32;
     if (gx > 1024) gx = 1024;
     LaunchScope ls_("reduce_partials", st);
-    reduce_segs_kernel<<<dim3(gx, plan->table.n + 1), dim3(32, 8), 0, st>>>(plan->table, plan->base, gtheta, psum, nb, lambda, l1 ? loss : nullptr);
+    launch_k(reduce_segs_kernel, dim3(gx, plan->table.n + 1), dim3(32, 8), 0, st, plan->table, plan->base, gtheta, psum, nb, lambda, l1 ? loss : nullptr);
     return check_launch("reduce_partials");
 }
 int reduce_scratch_doubles() { return L1_BLOCKS_MAX; }
@@ -839,24 +866,24 @@ int run_chamfer(const double* recon, const double* target, int B, int N, int M, 
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)chamfer_kernel, bytes)) return rc;
     LaunchScope ls_("chamfer", st);
-    chamfer_kernel<<<B, 128, bytes, st>>>(recon, target, B, N, M, jet_loss, g_loss, g_recon);
+    launch_k(chamfer_kernel, dim3(B), dim3(128), bytes, st, recon, target, B, N, M, jet_loss, g_loss, g_recon);
     int rc = check_launch("chamfer");
     if (rc) return rc;
     if (loss) {
         LaunchScope ls_("chamfer_sum", st);
-        sum_kernel<<<1, 1024, 0, st>>>(jet_loss, B, 1.0, loss, 0);
+        launch_k(sum_kernel, dim3(1), dim3(1024), 0, st, jet_loss, B, 1.0, loss, 0);
         rc = check_launch("chamfer_sum");
     }
     return rc;
 }
 int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st) {
     LaunchScope ls_("normalize_p4", st);
-    normalize_kernel<<<B, 128, 0, st>>>(p4, N, out, factor);
+    launch_k(normalize_kernel, dim3(B), dim3(128), 0, st, p4, N, out, factor);
     return check_launch("normalize_p4");
 }
 int run_l1(const double* theta, int64_t n, double lambda, double* out, double* gtheta, cudaStream_t st) {
     LaunchScope ls_("l1", st);
-    l1_kernel<<<1, 1024, 0, st>>>(theta, n, lambda, out, gtheta);
+    launch_k(l1_kernel, dim3(1), dim3(1024), 0, st, theta, n, lambda, out, gtheta);
     return check_launch("l1");
 }
 

@@ -182,8 +182,10 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
     const int NS = N < 32 ? N : 32;   // particle stride of cat_s
 
     // ---- stage the jet: momenta and node features by TMA bulk copies, weights by the threads meanwhile ----
+    pdl_launch();
     __shared__ uint64_t mbar;
     if (tid == 0) mbar_init(&mbar, 1);
+    pdl_wait();   // everything below reads what earlier kernels of the step produced
     __syncthreads();
     {
         const int np = ENC ? 4 * N : 8 * N;
@@ -473,6 +475,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
     cplx* gout_s = reinterpret_cast<cplx*>(smem + L.gout);
     const int nm = Cout * 5 * C, C5 = 5 * C;
 
+    pdl_launch();
     for (int t = tid; t < nm; t += blockDim.x) {
         m00_s[t] = cmake(a.theta[a.off_m00 + t], a.theta[a.off_m00 + nm + t]);
         m11_s[t] = cmake(a.theta[a.off_m11 + t], a.theta[a.off_m11 + nm + t]);
@@ -491,6 +494,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
     __shared__ uint64_t mbar;
     if (tid == 0) mbar_init(&mbar, 1);
     unsigned phase = 0;
+    pdl_wait();   // the weights above come from theta (constant during the step); everything below from earlier kernels
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
         __syncthreads();
         // ---- 1a. stage the jet (TMA bulk copies) and the incoming gradients ----
@@ -870,7 +874,7 @@ static int launch_level_fwd(const LevelArgs& a, cudaStream_t st) {
     if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
     const int nib = (a.N + 31) / 32;
     LaunchScope ls_("level_fwd", st);
-    kern<<<a.B * nib, 32 * a.C, bytes, st>>>(a);
+    launch_k(kern, dim3(a.B * nib), dim3(32 * a.C), bytes, st, a);
     return check_launch("level_fwd");
 }
 
@@ -886,7 +890,7 @@ static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
     {                                                                         \
         auto kern = level_bwd_kernel<ENC, MAXT, MINB, CFV>;                   \
         if (int rc = ensure_smem((const void*)kern, bytes)) return rc;        \
-        kern<<<grid, 32 * a.C, bytes, st>>>(a);                               \
+        launch_k(kern, dim3(grid), dim3(32 * a.C), bytes, st, a);                               \
     }
     if (a.C <= 4) {
         if (cf) LGAE_LAUNCH(128, LGAE_LBWD_CF_MINB, true) else LGAE_LAUNCH(128, LGAE_LBWD_MINB, false)

@@ -110,6 +110,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpArgs a
     constexpr int WP = 8 * NTW;
     const int last = a.n_lin - 1;
     // ---- all layers' weights and biases, once per CTA ----
+    pdl_launch();
     double* bias_s = smem;                 // n_lin * WP
     double* w_s = smem + a.n_lin * WP;
     {
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpArgs a
             wtotal += mlp_layer_frag(l, a.n_lin, NTW, NTI);
             for (int t = tid; t < WP; t += blockDim.x) bias_s[l * WP + t] = t < nout ? a.theta[a.off_b[l] + t] : 0.0;
         }
+        pdl_wait();   // the packed weights and the rows come from earlier kernels of the step
         copy_frags(a.wpack, w_s, wtotal);
     }
     __syncthreads();
@@ -219,6 +221,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
     double* dz_s = w_s + wtotal;                    // MLP_BWD_ROWS * WS
     double* h_s = dz_s + MLP_BWD_ROWS * WS;         // MLP_BWD_ROWS * WS
     double* bred = h_s + MLP_BWD_ROWS * WS;         // NWARP * WP : per-warp column sums of dZ
+    pdl_launch();
+    pdl_wait();
     copy_frags(a.wpack + wtotal, w_s, wtotal);
     double* part = a.part + (int64_t)blockIdx.x * a.part_stride;
     const int64_t slab0 = (int64_t)blockIdx.x * a.rows_per_cta;
@@ -408,6 +412,8 @@ struct MlpPackArgs {
     int64_t out_off[LGAE_MAX_LEVELS];
 };
 __global__ void __launch_bounds__(256) mlp_pack_kernel(const MlpPackArgs p) {
+    pdl_launch();
+    pdl_wait();   // (writes the packed weights that earlier kernels of a previous pass may still be reading)
     const int l = blockIdx.x, dir = blockIdx.y, lev = blockIdx.z;
     const int nin = p.nin[lev], width = p.width[lev], NTW = (width + 7) / 8, NTI = (nin + 7) / 8, last = p.n_lin - 1;
     int off = 0, wtotal = 0;
@@ -443,7 +449,7 @@ static int launch_mlp(MlpArgs& a, bool bwd, cudaStream_t st) {
         const int64_t ngroups = (a.rows + 7) / 8;
         const int grid = (int)(ngroups < sm_count() ? ngroups : sm_count());
         LaunchScope ls_("mlp_fwd", st);
-        kern<<<grid, MLP_THREADS, bytes, st>>>(a);
+        launch_k(kern, dim3(grid), dim3(MLP_THREADS), bytes, st, a);
         return check_launch("mlp_fwd");
     }
     const size_t bytes = (size_t)(wtotal + 2 * MLP_BWD_ROWS * (8 * NTW + 4) + (MLP_THREADS / 32) * 8 * NTW) * sizeof(double);
@@ -454,7 +460,7 @@ static int launch_mlp(MlpArgs& a, bool bwd, cudaStream_t st) {
     const int64_t per = (a.rows + grid - 1) / grid;
     a.rows_per_cta = ((per + 7) / 8) * 8;
     LaunchScope ls_("mlp_bwd", st);
-    kern<<<grid, MLP_THREADS, bytes, st>>>(a);
+    launch_k(kern, dim3(grid), dim3(MLP_THREADS), bytes, st, a);
     return check_launch("mlp_bwd");
 }
 
@@ -476,7 +482,7 @@ int run_mlp_pack(const LgaeModelDesc* d, const double* theta, double* out, const
         for (int i = 0; i < p.n_lin; ++i) p.off_w[l][i] = d->off_mlp_w[l][i];
     }
     LaunchScope ls_("mlp_pack", st);
-    mlp_pack_kernel<<<dim3(p.n_lin, 2, d->n_levels), 256, 0, st>>>(p);
+    launch_k(mlp_pack_kernel, dim3(p.n_lin, 2, d->n_levels), dim3(256), 0, st, p);
     return check_launch("mlp_pack");
 }
 

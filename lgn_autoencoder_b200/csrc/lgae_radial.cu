@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(128, LGAE_RFWD_CTAS) radial_fwd_kernel(const R
     const int N = a.N, C = a.C, K = a.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
+    pdl_launch();
     build_pair_table(N, ti, tj);
     for (int k = threadIdx.x; k < KP; k += blockDim.x) {
         abc_s[k] = k < K ? a.theta[a.off_a + k] : 0.0;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(128, LGAE_RFWD_CTAS) radial_fwd_kernel(const R
         bf[nt][0] = rad_bias(a, 8 * nt + 2 * q);
         bf[nt][1] = rad_bias(a, 8 * nt + 2 * q + 1);
     }
+    pdl_wait();   // p4 (normalised by an earlier kernel) is read below; r / nrm are written
     __syncthreads();
     const int NP = N * (N + 1) / 2, NU = (NP + RAD_UNIT - 1) / RAD_UNIT, NPS = NU * RAD_UNIT;
     const int total = a.B * NU, twarps = gridDim.x * nwarps;
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_kernel(const R
     const int N = a.N, C = a.C, K = a.K;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
+    pdl_launch();
     build_pair_table(N, ti, tj);
     for (int k = threadIdx.x; k < KP; k += blockDim.x) {
         abc_s[k] = k < K ? a.theta[a.off_a + k] : 0.0;
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_kernel(const R
         abc_s[2 * KP + k] = k < K ? a.theta[a.off_c + k] : 0.0;
     }
     for (int t = threadIdx.x; t < NCOL * KP; t += blockDim.x) w_s[t] = rad_w(a, t / KP, t % KP);
+    pdl_wait();   // g_r / nrm come from earlier kernels
     __syncthreads();
     double G1[NT][NT2][2], G2[NT][NT2][2];
 #pragma unroll
@@ -364,9 +368,9 @@ template <int NT, int KS>
 static int launch_radial(const RadialArgs& a, bool bwd, cudaStream_t st) {
     LaunchScope ls_(bwd ? "radial_bwd" : "radial_fwd", st);
     if (bwd)
-        radial_bwd_kernel<NT, KS><<<radial_grid(), 128, 0, st>>>(a);
+        launch_k(radial_bwd_kernel<NT, KS>, dim3(radial_grid()), dim3(128), 0, st, a);
     else
-        radial_fwd_kernel<NT, KS><<<radial_fwd_grid(), 128, 0, st>>>(a);
+        launch_k(radial_fwd_kernel<NT, KS>, dim3(radial_fwd_grid()), dim3(128), 0, st, a);
     return check_launch(bwd ? "radial_bwd" : "radial_fwd");
 }
 
