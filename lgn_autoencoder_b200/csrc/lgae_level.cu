@@ -43,6 +43,12 @@ struct LevelArgs {
     int B, N, C, Cout, K;
 };
 
+#ifndef LGAE_RPD_FWD
+#define LGAE_RPD_FWD 2   // partners of radial weights in flight per thread in the forward neighbour loop
+#endif
+#ifndef LGAE_RPD_BWD
+#define LGAE_RPD_BWD 2   // ... and in the adjoint
+#endif
 #ifndef LGAE_LBWD_CF_MINB
 #define LGAE_LBWD_CF_MINB 3   // the same for the decoder's closed-form adjoint
 #endif
@@ -273,8 +279,13 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
         }
     } else {
     const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
-    double4 rnext = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (ENC && PRE) rnext = rsv[0];
+    constexpr int PDF = LGAE_RPD_FWD;
+    double4 rq[PDF];
+#pragma unroll
+    for (int d = 0; d < PDF; ++d) {
+        rq[d] = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (ENC && PRE && d < N) rq[d] = rsv[(int64_t)d * C * 32];
+    }
     for (int j0 = 0; j0 < N; j0 += TJ) {
         const int tj = min(TJ, N - j0);
         if (ENC && !PRE) {
@@ -285,9 +296,11 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
             const int j = j0 + jj;
             cplx R0 = R0c, R1 = R1c;
             if (ENC && PRE) {
-                R0 = cmake(rnext.x, rnext.y);
-                R1 = cmake(rnext.z, rnext.w);
-                if (j + 1 < N) rnext = rsv[(int64_t)(j + 1) * C * 32];
+                R0 = cmake(rq[0].x, rq[0].y);
+                R1 = cmake(rq[0].z, rq[0].w);
+#pragma unroll
+                for (int d = 0; d + 1 < PDF; ++d) rq[d] = rq[d + 1];
+                if (j + PDF < N) rq[PDF - 1] = rsv[(int64_t)(j + PDF) * C * 32];
             } else if (ENC) {
                 const double4 r = *reinterpret_cast<const double4*>(Rs + ((size_t)((jj * C + c) * 32 + lane)) * 4);
                 R0 = cmake(r.x, r.y);
@@ -517,10 +530,12 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
         }
         // encoder: first radial weights of this jet, in flight while the mix adjoint runs
         const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
-        double4 rnext = make_double4(0.0, 0.0, 0.0, 0.0), rnext2 = rnext;
-        if (ENC) {
-            rnext = rsv[0];
-            if (N > 1) rnext2 = rsv[(int64_t)C * 32];
+        constexpr int PDB = LGAE_RPD_BWD;
+        double4 rq[PDB];
+#pragma unroll
+        for (int d = 0; d < PDB; ++d) {
+            rq[d] = make_double4(0.0, 0.0, 0.0, 0.0);
+            if (ENC && d < N) rq[d] = rsv[(int64_t)d * C * 32];
         }
         mbar_wait(&mbar, phase);
         phase ^= 1;
@@ -701,18 +716,19 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
             cplx Va[4], gAa[10];
 #pragma unroll
             for (int mu = 0; mu < 4; ++mu) Va[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
+#ifndef LGAE_GAA_SMEM
 #pragma unroll
             for (int e = 0; e < 10; ++e) gAa[e] = gA_s[(c * 10 + e) * 32 + lane];
+#endif
             double4* grv = reinterpret_cast<double4*>(a.g_r) + ((int64_t)b * N * C + c) * 32 + lane;
             for (int o = 0; o < N; ++o) {
                 cplx R0 = R0c, R1 = R1c;
                 if (ENC) {
-                    R0 = cmake(rnext.x, rnext.y);
-                    R1 = cmake(rnext.z, rnext.w);
-                    rnext = rnext2;
-#ifndef LGAE_EXP_NOR
-                    if (o + 2 < N) rnext2 = rsv[(int64_t)(o + 2) * C * 32];
-#endif
+                    R0 = cmake(rq[0].x, rq[0].y);
+                    R1 = cmake(rq[0].z, rq[0].w);
+#pragma unroll
+                    for (int d = 0; d + 1 < PDB; ++d) rq[d] = rq[d + 1];
+                    if (o + PDB < N) rq[PDB - 1] = rsv[(int64_t)(o + PDB) * C * 32];
                 }
                 const cplx So = S_s[o * C + c];
                 cplx Vo[4], Y[4];
@@ -753,6 +769,10 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
                 };
                 // role 1: own = receiving node i, other = neighbour j.  Y = Y_ij.
                 {
+#ifdef LGAE_GAA_SMEM
+#pragma unroll
+                    for (int e = 0; e < 10; ++e) gAa[e] = gA_s[(c * 10 + e) * 32 + lane];
+#endif
                     cplx gR0 = czero();
 #pragma unroll
                     for (int mu = 0; mu < 4; ++mu) cfmac(gR0, Vo[mu], gAa[mu]);
@@ -762,11 +782,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
                     cplx gR1 = cmulc(So, w);
                     cfmac(gR1, e, gAa[9]);
                     if (ENC) {
-#ifdef LGAE_EXP_NOGR
-                        if (gR0.x == 1.2345e300) grv[0] = make_double4(gR0.x, gR0.y, gR1.x, gR1.y);
-#else
                         grv[(int64_t)o * C * 32] = make_double4(gR0.x, gR0.y, gR1.x, gR1.y);
-#endif
                     } else {
                         gR0c = cadd(gR0c, live ? gR0 : czero());
                         gR1c = cadd(gR1c, live ? gR1 : czero());
