@@ -564,25 +564,35 @@ __global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const
         for (int mu = 0; mu < 4; ++mu) { const double d = x[4 * i + mu] - t[4 * j + mu]; s += d * d; }
         return s;
     };
-    for (int i = tid; i < N; i += blockDim.x) {
-        double best = dist(i, 0);
-        int bj = 0;
-        for (int j = 1; j < M; ++j) { const double d = dist(i, j); if (d < best) { best = d; bj = j; } }
-        m1[i] = best; j1[i] = bj;
-    }
-    for (int j = tid; j < M; j += blockDim.x) {
-        double best = dist(0, j);
-        int bi = 0;
-        for (int i = 1; i < N; ++i) { const double d = dist(i, j); if (d < best) { best = d; bi = i; } }
-        m2[j] = best; i2[j] = bi;
+    // the two directions run side by side: even warps take the reconstructed particles, odd warps the targets
+    __shared__ double dir_sum[2];
+    const int lane = tid & 31, warp = tid >> 5, nw2 = (blockDim.x >> 5) >> 1;   // blockDim is a multiple of 64
+    if ((warp & 1) == 0) {
+        for (int i = (warp >> 1) * 32 + lane; i < N; i += nw2 * 32) {
+            double best = dist(i, 0);
+            int bj = 0;
+            for (int j = 1; j < M; ++j) { const double d = dist(i, j); if (d < best) { best = d; bj = j; } }
+            m1[i] = best; j1[i] = bj;
+        }
+    } else {
+        for (int j = (warp >> 1) * 32 + lane; j < M; j += nw2 * 32) {
+            double best = dist(0, j);
+            int bi = 0;
+            for (int i = 1; i < N; ++i) { const double d = dist(i, j); if (d < best) { best = d; bi = i; } }
+            m2[j] = best; i2[j] = bi;
+        }
     }
     __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int i = 0; i < N; ++i) s += m1[i];
-        for (int j = 0; j < M; ++j) s += m2[j];
-        jet_loss[b] = 0.5 * s;
+    if (warp < 2) {   // per-direction sums: lanes stride the particles, then a butterfly (fixed order)
+        const double* mm = warp == 0 ? m1 : m2;
+        const int n = warp == 0 ? N : M;
+        double acc = 0.0;
+        for (int k = lane; k < n; k += 32) acc += mm[k];
+        acc = warp_sum(acc);
+        if (lane == 0) dir_sum[warp] = acc;
     }
+    __syncthreads();
+    if (tid == 0) jet_loss[b] = 0.5 * (dir_sum[0] + dir_sum[1]);
     if (g_recon) {
         const double scale = g_loss ? *g_loss : 1.0;
         for (int i = tid; i < N; i += blockDim.x) {

@@ -70,19 +70,6 @@ LGAE_DEV void stage_w_bwd(const double* w, int nout, int nink, int NO, int KI, d
     }
 }
 
-// Straight copy of pre-packed fragments global -> shared (n is a multiple of 64 doubles).
-LGAE_DEV void copy_frags(const double* src, double* dst, int n) {
-    const double4* s4 = reinterpret_cast<const double4*>(src);
-    double4* d4 = reinterpret_cast<double4*>(dst);
-    const int n4 = n >> 2;
-    int t = threadIdx.x;
-    for (; t + 3 * (int)blockDim.x < n4; t += 4 * blockDim.x) {
-        const double4 v0 = s4[t], v1 = s4[t + blockDim.x], v2 = s4[t + 2 * blockDim.x], v3 = s4[t + 3 * blockDim.x];
-        d4[t] = v0; d4[t + blockDim.x] = v1; d4[t + 2 * blockDim.x] = v2; d4[t + 3 * blockDim.x] = v3;
-    }
-    for (; t < n4; t += blockDim.x) d4[t] = s4[t];
-}
-
 // MT row groups advance together so that MT * NO independent accumulator chains are in flight (the fp64 MMA has a long
 // dependent-issue latency; a single group's NO chains leave the pipe idle).
 template <int MT, int KT, int NO>
@@ -121,7 +108,15 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpArgs a
             for (int t = tid; t < WP; t += blockDim.x) bias_s[l * WP + t] = t < nout ? a.theta[a.off_b[l] + t] : 0.0;
         }
         pdl_wait();   // the packed weights and the rows come from earlier kernels of the step
-        copy_frags(a.wpack, w_s, wtotal);
+        // one TMA bulk copy brings all layers' fragments (<= 98 KB) into shared memory
+        __shared__ uint64_t mbar;
+        if (tid == 0) mbar_init(&mbar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&mbar, (unsigned)(wtotal * sizeof(double)));
+            bulk_g2s(w_s, a.wpack, (unsigned)(wtotal * sizeof(double)), &mbar);
+        }
+        mbar_wait(&mbar, 0);
     }
     __syncthreads();
     // ---- row groups of 8: a contiguous range per CTA, each warp takes MT = 2 consecutive groups at a time ----
@@ -223,7 +218,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
     double* bred = h_s + MLP_BWD_ROWS * WS;         // NWARP * WP : per-warp column sums of dZ
     pdl_launch();
     pdl_wait();
-    copy_frags(a.wpack + wtotal, w_s, wtotal);
+    {
+        __shared__ uint64_t mbar;
+        if (tid == 0) mbar_init(&mbar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&mbar, (unsigned)(wtotal * sizeof(double)));
+            bulk_g2s(w_s, a.wpack + wtotal, (unsigned)(wtotal * sizeof(double)), &mbar);
+        }
+        mbar_wait(&mbar, 0);
+    }
     double* part = a.part + (int64_t)blockIdx.x * a.part_stride;
     const int64_t slab0 = (int64_t)blockIdx.x * a.rows_per_cta;
     const int64_t slab1 = slab0 + a.rows_per_cta < a.rows ? slab0 + a.rows_per_cta : a.rows;
