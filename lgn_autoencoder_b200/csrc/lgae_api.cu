@@ -297,8 +297,9 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
 int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
                          double* ws, double* lat00, double* lat11, int32_t* sel, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (d->is_decoder || !theta || !p4 || !ws || !lat00 || !lat11 || batch < 0) return LGAE_E_BADARG;
-    if (batch == 0) return LGAE_OK;
+    if (d->is_decoder || batch < 0) return LGAE_E_BADARG;
+    if (batch == 0) return LGAE_OK;   // empty batch: nothing to launch (the tensors' pointers may be NULL)
+    if (!theta || !p4 || !ws || !lat00 || !lat11) return LGAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
@@ -332,7 +333,7 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
                           double* ws, const int32_t* sel, const double* g_lat00, const double* g_lat11, double* gtheta,
                           double* partials, double l1_lambda, double* loss_accumulate, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (d->is_decoder || !theta || !p4 || !ws || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
+    if (d->is_decoder || !theta || !gtheta || !partials || batch < 0 || (batch > 0 && (!p4 || !ws))) return LGAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     PartPlan plan;
     plan.base = partials;
@@ -386,8 +387,9 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
 int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
                          double* gen00, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (!d->is_decoder || !theta || !lat11 || !ws || !recon || batch < 0) return LGAE_E_BADARG;
+    if (!d->is_decoder || batch < 0) return LGAE_E_BADARG;
     if (batch == 0) return LGAE_OK;
+    if (!theta || !lat11 || !ws || !recon) return LGAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
@@ -405,7 +407,8 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
                           const double* g_recon, const double* g_gen00, double* g_lat11, double* gtheta, double* partials,
                           double l1_lambda, double* loss_accumulate, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (!d->is_decoder || !theta || !lat11 || !ws || !g_recon || !g_lat11 || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
+    if (!d->is_decoder || !theta || !gtheta || !partials || batch < 0 || (batch > 0 && (!lat11 || !ws || !g_recon || !g_lat11)))
+        return LGAE_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     PartPlan plan;
     plan.base = partials;
@@ -439,7 +442,7 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
 
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,
                  const double* g_loss, double* g_recon, void* stream) {
-    if (!recon || !target || !jet_loss || batch < 0 || n < 1 || m < 1) return LGAE_E_BADARG;
+    if (batch < 0 || n < 1 || m < 1 || (batch > 0 && (!recon || !target || !jet_loss))) return LGAE_E_BADARG;
     if (batch == 0) {
         if (loss && cudaMemsetAsync(loss, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) return check_launch("memset loss");
         return LGAE_OK;
@@ -448,7 +451,7 @@ int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32
 }
 
 int lgae_normalize_p4(const double* p4, int32_t batch, int32_t n, double* out, double* factor, void* stream) {
-    if (!p4 || !out || batch < 0 || n < 1) return LGAE_E_BADARG;
+    if (batch < 0 || n < 1 || (batch > 0 && (!p4 || !out))) return LGAE_E_BADARG;
     if (batch == 0) return LGAE_OK;
     return run_normalize(p4, batch, n, out, factor, (cudaStream_t)stream);
 }
