@@ -12,8 +12,8 @@
 // column 8*tile + 2q + e), so no shuffles or shared-memory round trips are needed between layers.
 // Backward: a CTA owns a contiguous slab of rows.  Per layer, the data gradient uses the same register trick with
 // the transposed weights; the weight gradient dW = dZ^T H is a second MMA contraction over the slab's rows with dZ
-// and H staged in shared memory, its tiles dealt to the warps, and the result goes straight to the CTA's row of
-// parameter-gradient partials.
+// and H staged in shared memory, computed by dedicated warps as register-blocked tile blocks, and the result goes
+// straight to the CTA's row of parameter-gradient partials.
 #include <cstring>
 
 #include "lgae_common.cuh"
@@ -199,23 +199,32 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpArgs a
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
+// Warp-specialised: warps 0-3 ("dW warps") own the weight-gradient tiles of a layer as register-blocked (<= 3 x 3) tile
+// blocks -- each k-step loads 3 + 3 fragments for 9 MMAs instead of 2 per MMA, which is what keeps the contraction off the
+// shared-memory bandwidth limit -- plus the bias gradient and the staging of the layer inputs H_l (prefetched one layer
+// ahead); warps 4-7 ("row warps") own the slab's row groups: they carry dZ through the layer chain in registers (data
+// gradient with the transposed weights) and publish it to shared memory for the dW warps.  Both run concurrently between
+// the two barriers of a layer, one of each kind per SM sub-partition.
 template <int NTW, int NTI>
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a) {
     extern __shared__ __align__(128) double smem[];
     constexpr int WS = 8 * NTW + 4;                 // padded row stride of the staged tiles (conflict-free fragment loads)
     constexpr int WP = 8 * NTW;
-    constexpr int NWARP = MLP_THREADS / 32;
-    constexpr int TU = MLP_BWD_ROWS / 8 / NWARP;    // row groups per warp per chunk
-    constexpr int MAXT = (NTW * NTW + NWARP - 1) / NWARP;   // dW tiles per warp
+    constexpr int NWH = 4;                          // warps per role
+    constexpr int GMAX = MLP_BWD_ROWS / 8 / NWH;    // row groups per row warp per chunk (4)
+    constexpr int MB = (NTW + 1) / 2;               // tile-block edge (3 for w = 48)
+    constexpr int PERD = (MLP_BWD_ROWS * WP / 4 + 32 * NWH - 1) / (32 * NWH);   // double4 of H per dW-warp thread
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
+    const bool dw_role = warp < NWH;
+    const int wi = warp & (NWH - 1);
     const int last = a.n_lin - 1;
     double* w_s = smem;
     int wtotal = 0;
     for (int l = 0; l <= last; ++l) wtotal += mlp_layer_frag(l, a.n_lin, NTW, NTI);
     double* dz_s = w_s + wtotal;                    // MLP_BWD_ROWS * WS
     double* h_s = dz_s + MLP_BWD_ROWS * WS;         // MLP_BWD_ROWS * WS
-    double* bred = h_s + MLP_BWD_ROWS * WS;         // NWARP * WP : per-warp column sums of dZ
+    double* bred = h_s + MLP_BWD_ROWS * WS;         // NWH * WP : per-dW-warp column sums of dZ
     pdl_launch();
     pdl_wait();
     {
@@ -232,175 +241,215 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
     const int64_t slab0 = (int64_t)blockIdx.x * a.rows_per_cta;
     const int64_t slab1 = slab0 + a.rows_per_cta < a.rows ? slab0 + a.rows_per_cta : a.rows;
     bool first = true;   // first chunk of the slab: partials are stored, later chunks accumulate
-    for (int64_t r0 = slab0;; r0 += MLP_BWD_ROWS) {
-        const int crows = (int)(slab1 - r0 < MLP_BWD_ROWS ? (slab1 > r0 ? slab1 - r0 : 0) : MLP_BWD_ROWS);
-        const int ksteps = ((crows + 7) / 8) * 2;   // MMA k-steps (4 rows each) covering the chunk
-        // gradient wrt the output of the last layer, accumulator-fragment layout, for this warp's row groups
-        double dz[TU][NTW][2];
+    // The two roles run separate copies of the chunk / layer loops (disjoint register live ranges) and meet at the same
+    // two block-wide barriers per layer (bar.sync 0 from either branch).
+    auto cta_sync = [] { asm volatile("bar.sync 0;" ::: "memory"); };
+    if (dw_role) {
+        for (int64_t r0 = slab0;; r0 += MLP_BWD_ROWS) {
+            const int crows = (int)(slab1 - r0 < MLP_BWD_ROWS ? (slab1 > r0 ? slab1 - r0 : 0) : MLP_BWD_ROWS);
+            const int ksteps = ((crows + 7) / 8) * 2;   // MMA k-steps (4 rows each) covering the chunk; even
+            // the saved activations feeding layer l (its input H_l), fetched one layer ahead; the chunk's rows are one
+            // contiguous run of crows * WP doubles
+            double4 hv[PERD];
+            auto fetch_h = [&](int layer) {
+                const double4* src = reinterpret_cast<const double4*>(a.acts + ((int64_t)(layer - 1) * a.rows + r0) * WP);
 #pragma unroll
-        for (int u = 0; u < TU; ++u) {
-            const int64_t row = r0 + (warp + NWARP * u) * 8 + g;
+                for (int j = 0; j < PERD; ++j) {
+                    const int idx = wi * 32 + lane + 32 * NWH * j;
+                    hv[j] = make_double4(0.0, 0.0, 0.0, 0.0);
+                    if (idx < ksteps * 4 * (WP / 4) && r0 + idx / (WP / 4) < slab1) hv[j] = src[idx];
+                }
+            };
+            if (last > 0) fetch_h(last);
+            int nout_prev = 0, l_prev = -1;
+            for (int l = last; l >= 0; --l) {
+                const int nout = l == last ? a.nin : a.width, nink = l == 0 ? a.nin : a.width;
+                const int NOt = l == last ? NTI : NTW, KIt = l == 0 ? NTI : NTW;
+                cta_sync();   // the previous layer's readers of dz_s / h_s are done; its bias partials are complete
+                if (l_prev >= 0)
+                    for (int n = tid; n < nout_prev; n += 32 * NWH) {
+                        double s = 0.0;
 #pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) {
-                dz[u][nt][0] = dz[u][nt][1] = 0.0;
-                if (nt < NTI) {
-                    const int col = 8 * nt + 2 * q;
-                    if (row < slab1 && col < a.nin) {
-                        const double2 v = *reinterpret_cast<const double2*>(a.g_y + row * a.nin + col);
-                        dz[u][nt][0] = v.x;
-                        dz[u][nt][1] = v.y;
+                        for (int w = 0; w < NWH; ++w) s += bred[w * WP + n];
+                        double* dst = part + a.po_b[l_prev] + n;
+                        dst[0] = first ? s : dst[0] + s;
                     }
-                }
-            }
-        }
-        // the saved activations feeding layer l (its input H_l) are fetched into registers one layer ahead, so their L2 / HBM
-        // latency overlaps the MMA work of layer l + 1
-        constexpr int PER = (8 * WP / 4 + 31) / 32;
-        double4 hv[TU][PER];
-        auto fetch_h = [&](int layer) {
-#pragma unroll
-            for (int u = 0; u < TU; ++u) {
-                const int rl = (warp + NWARP * u) * 8;
-                const double4* src = reinterpret_cast<const double4*>(a.acts + ((int64_t)(layer - 1) * a.rows + r0 + rl) * WP);
-#pragma unroll
-                for (int j = 0; j < PER; ++j) {
-                    const int idx = lane + 32 * j, rr = idx / (WP / 4);
-                    hv[u][j] = make_double4(0.0, 0.0, 0.0, 0.0);
-                    if (rl < ksteps * 4 && idx < 8 * WP / 4 && r0 + rl + rr < slab1) hv[u][j] = src[idx];
-                }
-            }
-        };
-        if (last > 0) fetch_h(last);
-        const double* wl = w_s + wtotal;
-        for (int l = last; l >= 0; --l) {
-            const int nout = l == last ? a.nin : a.width, nink = l == 0 ? a.nin : a.width;
-            const int NOt = l == last ? NTI : NTW, KIt = l == 0 ? NTI : NTW;
-            wl -= mlp_layer_frag(l, a.n_lin, NTW, NTI);
-            __syncthreads();   // previous layer's readers of dz_s / h_s / bred are done (also orders the weight staging)
-            // ---- stage dZ_l and the layer input H_l of this warp's row groups ----
-#pragma unroll
-            for (int u = 0; u < TU; ++u) {
-                const int rl = (warp + NWARP * u) * 8;
-                if (rl < ksteps * 4) {
-#pragma unroll
-                    for (int nt = 0; nt < NTW; ++nt)
-                        if (nt < NOt)
-                            *reinterpret_cast<double2*>(dz_s + (rl + g) * WS + 8 * nt + 2 * q) = make_double2(dz[u][nt][0], dz[u][nt][1]);
-                    if (l > 0) {
-                        // 8 consecutive rows of the saved activations are one contiguous run of 8*WP doubles (prefetched above)
-#pragma unroll
-                        for (int j = 0; j < PER; ++j) {
-                            const int idx = lane + 32 * j, rr = idx / (WP / 4), c4 = idx % (WP / 4);
-                            if (idx < 8 * WP / 4) *reinterpret_cast<double4*>(h_s + (rl + rr) * WS + 4 * c4) = hv[u][j];
-                        }
-                    } else {
-                        for (int idx = lane; idx < 8 * 8 * NTI; idx += 32) {
-                            const int rr = idx / (8 * NTI), cc = idx % (8 * NTI);
-                            const int64_t row = r0 + rl + rr;
-                            h_s[(rl + rr) * WS + cc] = (row < slab1 && cc < a.nin) ? a.x[row * a.nin + cc] : 0.0;
-                        }
-                    }
-                }
-            }
-            if (l > 1) fetch_h(l - 1);
-            __syncthreads();
-            // ---- bias gradient: column sums of dZ (each warp sums a slice of rows, then the slices are added) ----
-            {
-                const int per = (ksteps * 4 + NWARP - 1) / NWARP;
-                const int ra = warp * per, rb = ra + per < ksteps * 4 ? ra + per : ksteps * 4;
-                for (int n = lane; n < 8 * NOt; n += 32) {
-                    double s = 0.0;
-                    for (int r = ra; r < rb; ++r) s += dz_s[r * WS + n];
-                    bred[warp * WP + n] = s;
-                }
-            }
-            // ---- weight gradient: dW[n][k] = sum_rows dZ[row][n] H[row][k]; this warp's tiles, all in flight ----
-            {
-                double cw[MAXT][2], cw2[MAXT][2];   // even / odd k-steps: twice the independent MMA chains
-                int tm[MAXT], tn[MAXT];
-#pragma unroll
-                for (int j = 0; j < MAXT; ++j) {
-                    const int t = warp + NWARP * j;
-                    const bool on = t < NOt * KIt;
-                    tm[j] = on ? t / KIt : -1;
-                    tn[j] = on ? t % KIt : 0;
-                    cw[j][0] = cw[j][1] = cw2[j][0] = cw2[j][1] = 0.0;
-                }
-                for (int ks = 0; ks < ksteps; ks += 2) {   // ksteps is even
-                    const double* dr = dz_s + (4 * ks + q) * WS + g;
-                    const double* hr = h_s + (4 * ks + q) * WS + g;
-#pragma unroll
-                    for (int j = 0; j < MAXT; ++j)
-                        if (tm[j] >= 0) {
-                            dmma(cw[j][0], cw[j][1], dr[8 * tm[j]], hr[8 * tn[j]]);
-                            dmma(cw2[j][0], cw2[j][1], dr[4 * WS + 8 * tm[j]], hr[4 * WS + 8 * tn[j]]);
-                        }
-                }
-#pragma unroll
-                for (int j = 0; j < MAXT; ++j) { cw[j][0] += cw2[j][0]; cw[j][1] += cw2[j][1]; }
-#pragma unroll
-                for (int j = 0; j < MAXT; ++j) {
-                    if (tm[j] < 0) continue;
-                    const int n = 8 * tm[j] + g, k = 8 * tn[j] + 2 * q;
-                    if (n < nout) {
-                        double* dst = part + a.po_w[l] + (int64_t)n * nink + k;
-                        if (k < nink) dst[0] = first ? cw[j][0] : dst[0] + cw[j][0];
-                        if (k + 1 < nink) dst[1] = first ? cw[j][1] : dst[1] + cw[j][1];
-                    }
-                }
-            }
-            // ---- data gradient: Gin[row][k] = sum_n dZ[row][n] W[n][k], then through the LeakyReLU of layer l-1 ----
-            double ging[TU][NTW][2];
-#pragma unroll
-            for (int u = 0; u < TU; ++u)
-#pragma unroll
-                for (int kt = 0; kt < NTW; ++kt) ging[u][kt][0] = ging[u][kt][1] = 0.0;
-#pragma unroll
-            for (int nt = 0; nt < NTW; ++nt) {
-                if (nt < NOt) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
-#pragma unroll
-                        for (int kt = 0; kt < NTW; ++kt)
-                            if (kt < KIt) {
-                                const double bv = wl[((nt * 2 + e) * KIt + kt) * 32 + q * 8 + g];
-#pragma unroll
-                                for (int u = 0; u < TU; ++u) dmma(ging[u][kt][0], ging[u][kt][1], dz[u][nt][e], bv);   // padding groups carry zeros
-                            }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < TU; ++u) {
-                const int rl = (warp + NWARP * u) * 8;
-                if (rl >= ksteps * 4) continue;
-                double (&gin)[NTW][2] = ging[u];
+                // ---- stage the layer input H_l, then start fetching H_{l-1} ----
                 if (l > 0) {
 #pragma unroll
-                    for (int kt = 0; kt < NTW; ++kt) {
-                        const double2 h = *reinterpret_cast<const double2*>(h_s + (rl + g) * WS + 8 * kt + 2 * q);
-                        dz[u][kt][0] = gin[kt][0] * (h.x > 0.0 ? 1.0 : a.slope);
-                        dz[u][kt][1] = gin[kt][1] * (h.y > 0.0 ? 1.0 : a.slope);
+                    for (int j = 0; j < PERD; ++j) {
+                        const int idx = wi * 32 + lane + 32 * NWH * j, rr = idx / (WP / 4), c4 = idx % (WP / 4);
+                        if (idx < ksteps * 4 * (WP / 4)) *reinterpret_cast<double4*>(h_s + rr * WS + 4 * c4) = hv[j];
                     }
-                } else if (a.g_x) {
-                    const int64_t row = r0 + rl + g;
+                    if (l > 1) fetch_h(l - 1);
+                } else {
+                    for (int idx = wi * 32 + lane; idx < ksteps * 4 * 8 * NTI; idx += 32 * NWH) {
+                        const int rr = idx / (8 * NTI), cc = idx % (8 * NTI);
+                        const int64_t row = r0 + rr;
+                        h_s[rr * WS + cc] = (row < slab1 && cc < a.nin) ? a.x[row * a.nin + cc] : 0.0;
+                    }
+                }
+                cta_sync();
+                __syncwarp();
+                // ---- bias gradient: column sums of dZ over this warp's slice of rows (the four slices are added after the
+                //      next barrier) ----
+                {
+                    const int per = (ksteps * 4 + NWH - 1) / NWH;
+                    const int ra = wi * per, rb = ra + per < ksteps * 4 ? ra + per : ksteps * 4;
+                    for (int n = lane; n < 8 * NOt; n += 32) {
+                        double s0 = 0.0, s1 = 0.0;
+                        int r = ra;
+                        for (; r + 1 < rb; r += 2) { s0 += dz_s[r * WS + n]; s1 += dz_s[(r + 1) * WS + n]; }
+                        if (r < rb) s0 += dz_s[r * WS + n];
+                        bred[wi * WP + n] = s0 + s1;
+                    }
+                }
+                // ---- weight gradient dW[n][k] = sum_rows dZ[row][n] H[row][k]: this warp's (<= MB x MB) tile block ----
+                const int MBo = (NOt + 1) / 2, NBo = (KIt + 1) / 2;
+                const int m0 = (wi >> 1) * MBo, n0 = (wi & 1) * NBo;
+                const int mcnt = NOt - m0 < MBo ? NOt - m0 : MBo, ncnt = KIt - n0 < NBo ? KIt - n0 : NBo;
+                if (mcnt > 0 && ncnt > 0) {
+                    double cw[2][MB][MB][2];   // even / odd k-steps: twice the independent MMA chains
 #pragma unroll
-                    for (int kt = 0; kt < NTI; ++kt) {
-                        const int col = 8 * kt + 2 * q;
-                        if (row < slab1 && col < a.nin) *reinterpret_cast<double2*>(a.g_x + row * a.nin + col) = make_double2(gin[kt][0], gin[kt][1]);
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int i = 0; i < MB; ++i)
+#pragma unroll
+                            for (int j = 0; j < MB; ++j) cw[h][i][j][0] = cw[h][i][j][1] = 0.0;
+                    for (int ks = 0; ks < ksteps; ks += 2) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const double* dr = dz_s + (4 * (ks + h) + q) * WS + 8 * m0 + g;
+                            const double* hr = h_s + (4 * (ks + h) + q) * WS + 8 * n0 + g;
+                            double af[MB], bf[MB];
+#pragma unroll
+                            for (int i = 0; i < MB; ++i) af[i] = i < mcnt ? dr[8 * i] : 0.0;
+#pragma unroll
+                            for (int j = 0; j < MB; ++j) bf[j] = j < ncnt ? hr[8 * j] : 0.0;
+#pragma unroll
+                            for (int i = 0; i < MB; ++i)
+#pragma unroll
+                                for (int j = 0; j < MB; ++j)
+                                    if (i < mcnt && j < ncnt) dmma(cw[h][i][j][0], cw[h][i][j][1], af[i], bf[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < MB; ++i)
+#pragma unroll
+                        for (int j = 0; j < MB; ++j) {
+                            if (i >= mcnt || j >= ncnt) continue;
+                            const int n = 8 * (m0 + i) + g, k = 8 * (n0 + j) + 2 * q;
+                            const double c0 = cw[0][i][j][0] + cw[1][i][j][0], c1 = cw[0][i][j][1] + cw[1][i][j][1];
+                            if (n < nout) {
+                                double* dst = part + a.po_w[l] + (int64_t)n * nink + k;
+                                if (k < nink) dst[0] = first ? c0 : dst[0] + c0;
+                                if (k + 1 < nink) dst[1] = first ? c1 : dst[1] + c1;
+                            }
+                        }
+                }
+                nout_prev = nout;
+                l_prev = l;
+            }
+            cta_sync();   // bias partials of the first layer
+            for (int n = tid; n < nout_prev; n += 32 * NWH) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWH; ++w) s += bred[w * WP + n];
+                double* dst = part + a.po_b[0] + n;
+                dst[0] = first ? s : dst[0] + s;
+            }
+            first = false;
+            if (r0 + MLP_BWD_ROWS >= slab1) break;
+        }
+    } else {
+        for (int64_t r0 = slab0;; r0 += MLP_BWD_ROWS) {
+            const int crows = (int)(slab1 - r0 < MLP_BWD_ROWS ? (slab1 > r0 ? slab1 - r0 : 0) : MLP_BWD_ROWS);
+            const int ksteps = ((crows + 7) / 8) * 2;
+            // gradient wrt the output of the last layer, accumulator-fragment layout, for the warp's row groups
+            double dz[GMAX][NTW][2];
+#pragma unroll
+            for (int u = 0; u < GMAX; ++u) {
+                const int64_t row = r0 + (wi + NWH * u) * 8 + g;
+#pragma unroll
+                for (int nt = 0; nt < NTW; ++nt) {
+                    dz[u][nt][0] = dz[u][nt][1] = 0.0;
+                    if (nt < NTI) {
+                        const int col = 8 * nt + 2 * q;
+                        if (row < slab1 && col < a.nin) {
+                            const double2 v = *reinterpret_cast<const double2*>(a.g_y + row * a.nin + col);
+                            dz[u][nt][0] = v.x;
+                            dz[u][nt][1] = v.y;
+                        }
                     }
                 }
             }
-            __syncthreads();   // bred complete
-            for (int n = tid; n < nout; n += blockDim.x) {
-                double s = 0.0;
+            const double* wl = w_s + wtotal;
+            for (int l = last; l >= 0; --l) {
+                const int NOt = l == last ? NTI : NTW, KIt = l == 0 ? NTI : NTW;
+                wl -= mlp_layer_frag(l, a.n_lin, NTW, NTI);
+                cta_sync();
+                // ---- publish dZ_l of this warp's row groups ----
 #pragma unroll
-                for (int w = 0; w < NWARP; ++w) s += bred[w * WP + n];
-                double* dst = part + a.po_b[l] + n;
-                dst[0] = first ? s : dst[0] + s;
+                for (int u = 0; u < GMAX; ++u) {
+                    const int rl = (wi + NWH * u) * 8;
+                    if (rl < ksteps * 4) {
+#pragma unroll
+                        for (int nt = 0; nt < NTW; ++nt)
+                            if (nt < NOt)
+                                *reinterpret_cast<double2*>(dz_s + (rl + g) * WS + 8 * nt + 2 * q) = make_double2(dz[u][nt][0], dz[u][nt][1]);
+                    }
+                }
+                cta_sync();
+                // ---- data gradient: Gin[row][k] = sum_n dZ[row][n] W[n][k], then through the LeakyReLU of layer l-1; two row
+                //      groups advance together (2 * KIt independent chains) ----
+#pragma unroll
+                for (int up = 0; up < GMAX; up += 2) {
+                    if ((wi + NWH * up) * 8 >= ksteps * 4) continue;   // both groups of the pair are padding
+                    double gin[2][NTW][2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int kt = 0; kt < NTW; ++kt) gin[u][kt][0] = gin[u][kt][1] = 0.0;
+#pragma unroll
+                    for (int nt = 0; nt < NTW; ++nt) {
+                        if (nt < NOt) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                                for (int kt = 0; kt < NTW; ++kt)
+                                    if (kt < KIt) {
+                                        const double bv = wl[((nt * 2 + e) * KIt + kt) * 32 + q * 8 + g];
+#pragma unroll
+                                        for (int u = 0; u < 2; ++u) dmma(gin[u][kt][0], gin[u][kt][1], dz[up + u][nt][e], bv);   // padding groups carry zeros
+                                    }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int rl = (wi + NWH * (up + u)) * 8;
+                        if (rl >= ksteps * 4) continue;
+                        if (l > 0) {
+#pragma unroll
+                            for (int kt = 0; kt < NTW; ++kt) {
+                                const double2 h = *reinterpret_cast<const double2*>(h_s + (rl + g) * WS + 8 * kt + 2 * q);
+                                dz[up + u][kt][0] = gin[u][kt][0] * (h.x > 0.0 ? 1.0 : a.slope);
+                                dz[up + u][kt][1] = gin[u][kt][1] * (h.y > 0.0 ? 1.0 : a.slope);
+                            }
+                        } else if (a.g_x) {
+                            const int64_t row = r0 + rl + g;
+#pragma unroll
+                            for (int kt = 0; kt < NTI; ++kt) {
+                                const int col = 8 * kt + 2 * q;
+                                if (row < slab1 && col < a.nin)
+                                    *reinterpret_cast<double2*>(a.g_x + row * a.nin + col) = make_double2(gin[u][kt][0], gin[u][kt][1]);
+                            }
+                        }
+                    }
+                }
             }
+            cta_sync();   // pairs with the dW warps' barrier before the last bias reduction
+            if (r0 + MLP_BWD_ROWS >= slab1) break;
         }
-        first = false;
-        if (r0 + MLP_BWD_ROWS >= slab1) break;
     }
 }
 
@@ -456,7 +505,7 @@ static int launch_mlp(MlpArgs& a, bool bwd, cudaStream_t st) {
         launch_k(kern, dim3(grid), dim3(MLP_THREADS), bytes, st, a);
         return check_launch("mlp_fwd");
     }
-    const size_t bytes = (size_t)(wtotal + 2 * MLP_BWD_ROWS * (8 * NTW + 4) + (MLP_THREADS / 32) * 8 * NTW) * sizeof(double);
+    const size_t bytes = (size_t)(wtotal + 2 * MLP_BWD_ROWS * (8 * NTW + 4) + 4 * 8 * NTW) * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
     auto kern = mlp_bwd_kernel<NTW, NTI>;
     if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
