@@ -272,6 +272,7 @@ struct SegTable {
     int32_t n;
     int32_t pad;
     Seg s[LGAE_MAX_SEGS];
+    int32_t chunk0[LGAE_MAX_SEGS + 1];   // filled by the reduce launcher: first 32-column chunk (= block index) of every segment
 };
 // Host-side allocator of blocks inside `partials`.
 struct PartPlan {

@@ -685,16 +685,21 @@ __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, cons
     pdl_launch();
     pdl_wait();
     __shared__ double sm[8][33];
-    if ((int)blockIdx.y == t.n) {
-        if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0 && loss) {
+    // blockIdx.x enumerates the 32-column chunks of all segments back to back (t.chunk0[s] = first chunk of segment s); the
+    // block after the last chunk adds the L1 term to the loss
+    if ((int)blockIdx.x == t.chunk0[t.n]) {
+        if (threadIdx.x == 0 && threadIdx.y == 0 && loss) {
             double s = 0.0;
             for (int i = 0; i < npsum; ++i) s += psum[i];
             loss[0] += lambda * s;
         }
         return;
     }
-    const Seg sg = t.s[blockIdx.y];
-    for (int x0 = blockIdx.x * 32; x0 < sg.len; x0 += gridDim.x * 32) {
+    int si = 0;
+    while (si + 1 < t.n && (int)blockIdx.x >= t.chunk0[si + 1]) ++si;
+    const Seg sg = t.s[si];
+    {
+        const int x0 = ((int)blockIdx.x - t.chunk0[si]) * 32;
         const int x = x0 + threadIdx.x;
         double acc = 0.0;
         if (x < sg.len) {
@@ -718,7 +723,6 @@ __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, cons
             for (int y = 0; y < 8; ++y) v += sm[y][threadIdx.x];
             gtheta[sg.theta_off + x] += v;
         }
-        __syncthreads();
     }
 }
 
@@ -853,12 +857,14 @@ int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const doub
         if (int rc = check_launch("grad_init")) return rc;
     }
     if (plan->table.n == 0 && !l1) return LGAE_OK;
-    int maxlen = 1;
-    for (int i = 0; i < plan->table.n; ++i) maxlen = plan->table.s[i].len > maxlen ? plan->table.s[i].len : maxlen;
-    int gx = (maxlen + 31) / 32;
-    if (gx > 1024) gx = 1024;
+    int chunks = 0;
+    for (int i = 0; i < plan->table.n; ++i) {
+        plan->table.chunk0[i] = chunks;
+        chunks += (plan->table.s[i].len + 31) / 32;
+    }
+    plan->table.chunk0[plan->table.n] = chunks;
     LaunchScope ls_("reduce_partials", st);
-    launch_k(reduce_segs_kernel, dim3(gx, plan->table.n + 1), dim3(32, 8), 0, st, plan->table, plan->base, gtheta, psum, nb, lambda, l1 ? loss : nullptr);
+    launch_k(reduce_segs_kernel, dim3(chunks + 1), dim3(32, 8), 0, st, plan->table, plan->base, gtheta, psum, nb, lambda, l1 ? loss : nullptr);
     return check_launch("reduce_partials");
 }
 int reduce_scratch_doubles() { return L1_BLOCKS_MAX; }
