@@ -97,9 +97,11 @@ class FusedTrainStep:
         self.g_lat11 = torch.empty_like(self.latent11)
         self.jet_loss = torch.empty(B, **f64)
         self.loss = torch.zeros((), **f64)
-        # flat gradient buckets; every param.grad is a view of them
-        self.g_e = torch.zeros(self.pe.n_params, **f64)
-        self.g_d = torch.zeros(self.pd.n_params, **f64)
+        # one flat gradient bucket for both models (a single all-reduce per step); every param.grad is a view of it
+        off_d = (self.pe.n_params + 3) // 4 * 4   # keep the decoder bucket 32-byte aligned
+        self.g_all = torch.zeros(off_d + self.pd.n_params, **f64)
+        self.g_e = self.g_all[:self.pe.n_params]
+        self.g_d = self.g_all[off_d:]
         self._bind_grads()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
@@ -137,8 +139,7 @@ class FusedTrainStep:
                                         ptr(self.g_lat11), ptr(self.g_e), ptr(self.part_e), self.l1, ptr(self.loss), st), "encoder_backward")
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size
-            dist.all_reduce(self.g_e, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(self.g_d, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.g_all, op=dist.ReduceOp.SUM, group=self.group)
 
     def _params_moved(self) -> bool:
         """Cheap per-step check (a few attribute reads): the flat buffers the captured kernels read are still the models'.
