@@ -59,7 +59,7 @@ class ClockSampler:
     def __init__(self, index):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.p = None
@@ -213,9 +213,9 @@ def main():
     kern = _lib.kernel_timings(eager, reps=5)
 
     # ---- value: jets resident in HBM ----
+    sampler = ClockSampler(local) if rank == 0 else None   # clocks / throttle reasons from the warm-up to the end of the e2e loop
     for _ in range(W):
         fstep.run()
-    sampler = ClockSampler(local) if rank == 0 else None
     ms_step, _ = timed(fstep.run, K)
 
     # ---- end to end: pinned host jets -> device, loss back to the host, every step ----
