@@ -217,3 +217,79 @@ class FusedTrainStep:
             self.graph_host.replay()
         torch.cuda.current_stream().synchronize()
         return float(self.host_loss)
+
+
+class FusedInference:
+    """Forward-only pass (encoder -> decoder -> per-jet chamfer score) for a fixed batch size on static buffers, replayed as one
+    CUDA graph: the inference / anomaly-scoring path (test.py:57-95, utils/jet_analysis/anomaly_detection.py chamfer score).
+    Jets are independent, so multi-GPU inference is one instance per rank on its shard of the jets, with no communication.
+    Supports any number of particles per jet the forward kernels do (blocks of 32 particles per CTA; cfg-5 has 150).
+
+    ``score(p4, labels=None)`` returns the (B,) per-jet chamfer distances between the reconstruction (re + im) and the
+    normalised input; ``recon`` (2,B,N,4), ``latent00`` / ``latent11`` and ``norm_factor`` hold the other results.
+    """
+
+    def __init__(self, encoder, decoder, batch: int, normalize: bool = True, use_labels: bool = False, use_graph: bool = True):
+        if not (getattr(encoder, "fused", False) and getattr(decoder, "fused", False)):
+            raise NotImplementedError("FusedInference needs the fused (maxdim 2) encoder and decoder")
+        self.enc, self.dec, self.B = encoder, decoder, int(batch)
+        self.pe, self.pd = encoder._plan, decoder._plan
+        self.normalize = normalize
+        self.lib = _lib.load()
+        dev = next(encoder.parameters()).device
+        f64 = dict(dtype=torch.float64, device=dev)
+        B, N = self.B, self.pe.n_particles
+        ts, tv = self.pe.latent_taus()
+        self.p4_in = torch.zeros((B, N, 4), **f64)
+        self.p4 = torch.empty((B, N, 4), **f64) if normalize else self.p4_in
+        self.norm_factor = torch.ones(B, **f64)
+        self.mask = torch.ones((B, N), dtype=torch.uint8, device=dev) if use_labels else None
+        self.ws_e, self.ws_d = self.pe.workspace(B, dev), self.pd.workspace(B, dev)
+        self.latent00 = torch.empty((2, B, 1, ts, 1), **f64)
+        self.latent11 = torch.empty((2, B, 1, tv, 4), **f64)
+        self.sel = torch.empty((4, 2, B, max(self.pe.tau_s, self.pe.tau_v)), dtype=torch.int32, device=dev)
+        self.recon = torch.empty((2, B, self.pd.n_particles, 4), **f64)
+        self.scores = torch.empty(B, **f64)
+        self.use_graph = use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._thetas = None
+
+    def _launch(self):
+        lib, pe, pd, B = self.lib, self.pe, self.pd, self.B
+        st = torch.cuda.current_stream().cuda_stream
+        th_e, _ = self.enc._flat_params()
+        th_d, _ = self.dec._flat_params()
+        self._thetas = (th_e.data_ptr(), th_d.data_ptr())
+        if self.normalize:
+            check(lib.lgae_normalize_p4(ptr(self.p4_in), B, pe.n_particles, ptr(self.p4), ptr(self.norm_factor), st), "normalize_p4")
+        check(lib.lgae_encoder_forward(C.byref(pe.desc), ptr(th_e), ptr(self.p4), ptr(self.mask), B, ptr(self.ws_e), ptr(self.latent00),
+                                       ptr(self.latent11), ptr(self.sel), st), "encoder_forward")
+        check(lib.lgae_decoder_forward(C.byref(pd.desc), ptr(th_d), ptr(self.latent11), B, ptr(self.ws_d), ptr(self.recon), None, st),
+              "decoder_forward")
+        check(lib.lgae_chamfer(ptr(self.recon), ptr(self.p4), B, pd.n_particles, pe.n_particles, None, ptr(self.scores), None, None, st),
+              "chamfer")
+
+    def run(self):
+        if not self.use_graph:
+            self._launch()
+            return self.scores
+        te, td = self.enc._theta, self.dec._theta
+        moved = te is None or td is None or self._thetas != (te.data_ptr(), td.data_ptr())
+        if self.graph is None or moved:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._launch()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+        self.graph.replay()
+        return self.scores
+
+    def score(self, p4, labels=None):
+        self.p4_in.copy_(p4, non_blocking=True)
+        if self.mask is not None and labels is not None:
+            self.mask.copy_((labels != 0).to(torch.uint8), non_blocking=True)
+        return self.run()

@@ -65,3 +65,39 @@ def test_step_host_matches_step():
     assert l_host == l_dev
     assert torch.equal(step.g_e, g_dev)
     assert abs(l_host - g["loss"].item()) < 1e-10 * abs(g["loss"].item())
+
+
+def test_fused_inference_matches_module_forward_and_oracle_at_150_particles():
+    """Forward-only scoring path at the cfg-5 particle count (150 per jet: five particle blocks per CTA in the forward kernels)
+    against the module forward and against the CPU oracle on two seeded jets."""
+    from lgn_autoencoder_b200 import fused
+    from lgn_autoencoder_b200.train import FusedInference
+    from oracle import lgae_oracle as orc
+    from tests.test_edge_cases_gpu import _build
+    dev = torch.device("cuda:0")
+    cfg = dict(seed=21, n=150, enc_channels=[3, 3, 4, 4], dec_channels=[4, 4, 3, 3], tau_s=1, tau_v=8, map_to_latent="min&max", mlp_depth=6,
+               mlp_width=6)
+    enc, dec = _build(cfg, dev)
+    data = orc.synthetic_jets(2, 150, seed=22, mass_scale=1e-6, pad=True)
+    inf = FusedInference(enc, dec, 2, normalize=True, use_labels=True)
+    for _ in range(2):
+        scores = inf.score(data["p4"], data["labels"]).clone()
+    # module path
+    p4n, _ = fused.normalize_p4(data["p4"].to(dev))
+    with torch.no_grad():
+        rec = dec(enc({"p4": p4n, "labels": data["labels"].to(dev)}))
+    assert torch.equal(rec, inf.recon)
+    assert torch.equal(fused.chamfer_per_jet(rec, p4n), scores)
+    # oracle
+    pn, _ = orc.normalize_p4_overall_max(data["p4"])
+    enc_sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+    dec_sd = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        lat = orc.encoder_forward(enc_sd, dict(num_channels=cfg["enc_channels"], maxdim=[2], max_zf=[1], map_to_latent="min&max"),
+                                  dict(data, p4=pn))
+        ref = orc.decoder_forward(dec_sd, dict(num_channels=cfg["dec_channels"], maxdim=[2], max_zf=[1]), lat)
+    assert rel_err(inf.recon, ref) < 1e-10
+    x = orc.get_real_sum(ref)
+    for b in range(2):
+        s = orc.chamfer_loss(x[b:b + 1], pn[b:b + 1]).item()
+        assert abs(scores[b].item() - s) <= 1e-10 * abs(s)
