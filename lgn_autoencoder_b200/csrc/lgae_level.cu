@@ -43,6 +43,12 @@ struct LevelArgs {
     int B, N, C, Cout, K;
 };
 
+#ifndef LGAE_BWD_UNROLL
+#define LGAE_BWD_UNROLL 1   // unroll factor of the adjoint neighbour loop
+#endif
+#ifndef LGAE_FWD_UNROLL
+#define LGAE_FWD_UNROLL 1   // ... and of the forward one
+#endif
 #ifndef LGAE_RPD_FWD
 #define LGAE_RPD_FWD 2   // partners of radial weights in flight per thread in the forward neighbour loop
 #endif
@@ -55,6 +61,7 @@ struct LevelArgs {
 #ifndef LGAE_LBWD_MINB
 #define LGAE_LBWD_MINB 3   // resident CTAs per SM the level adjoint is compiled for (register cap 168; 4 => 128 registers spills and is slower)
 #endif
+constexpr int kBwdUnroll = LGAE_BWD_UNROLL, kFwdUnroll = LGAE_FWD_UNROLL;
 constexpr int TJ = 8;  // neighbours per shared-memory tile of radial weights
 constexpr int CAT_E = 21;  // entries per (channel, particle) of the concatenation staged for the channel mix
 
@@ -292,6 +299,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
             radial_tile<NT, KS>(p_s, msk_s, N, C, i0, j0, tj, abc_s, wf, bf, Rs);
             __syncthreads();
         }
+#pragma unroll kFwdUnroll
         for (int jj = 0; jj < tj; ++jj) {
             const int j = j0 + jj;
             cplx R0 = R0c, R1 = R1c;
@@ -721,6 +729,7 @@ __global__ void __launch_bounds__(MAXT, MINB) level_bwd_kernel(const LevelArgs a
             for (int e = 0; e < 10; ++e) gAa[e] = gA_s[(c * 10 + e) * 32 + lane];
 #endif
             double4* grv = reinterpret_cast<double4*>(a.g_r) + ((int64_t)b * N * C + c) * 32 + lane;
+#pragma unroll kBwdUnroll
             for (int o = 0; o < N; ++o) {
                 cplx R0 = R0c, R1 = R1c;
                 if (ENC) {
