@@ -131,6 +131,21 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
                           double* workspace, const double* g_recon, const double* g_gen00, double* g_lat11,
                           double* gtheta, double* partials, double l1_lambda, double* loss_accumulate, void* stream);
 
+/* ---- the whole training step ---------------------------------------------------------------------- */
+/* utils/train.py:283-327 in one call: [normalize_p4] -> encoder -> decoder -> chamfer (sum over the batch, get_real 'sum') +
+ * l1_lambda (|theta_enc|_1 + |theta_dec|_1) -> decoder adjoint -> encoder adjoint.  The parameter gradients of both models
+ * land in ONE bucket `gtheta`: encoder at [0, enc->n_params), decoder at [gtheta_dec_offset, + dec->n_params) (so a single
+ * all-reduce exchanges them), produced by one gradient-init and one reduce launch for both models.  p4_in (B,N,4); when
+ * normalize != 0 the normalised jets go to p4 and the per-jet factors to norm_factor (B), otherwise p4 / norm_factor are
+ * unused.  loss (1) is overwritten; jet_loss (B) gets the per-jet chamfer distances; recon / g_recon (2,B,N,4), lat00, lat11,
+ * sel, g_lat11 as in the model entry points.  partials: lgae_train_step_partials_doubles(enc, dec, batch) doubles. */
+int64_t lgae_train_step_partials_doubles(const LgaeModelDesc* enc, const LgaeModelDesc* dec, int32_t batch);
+int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
+                    const double* p4_in, const uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4,
+                    double* norm_factor, double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel,
+                    double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss, double* gtheta,
+                    int64_t gtheta_dec_offset, double* partials, double l1_lambda, void* stream);
+
 /* ---- caller-side ops on the hot path ------------------------------------------------------------- */
 /* ChamferLoss (sum over the batch) of x = re(recon) + im(recon) against target (B,M,4).
  * loss (1 double) is overwritten.  If g_recon != NULL it receives d loss / d recon (2,B,N,4), scaled by

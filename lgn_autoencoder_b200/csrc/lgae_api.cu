@@ -48,6 +48,8 @@ int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const
                        const double* g_gen00, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
 int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const double* theta, double lambda, double* loss, cudaStream_t st);
 int reduce_scratch_doubles();
+int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta,
+                     double lambda, double* loss, cudaStream_t st);
 int64_t glue_part_doubles(const LgaeModelDesc* d, int batch);
 int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
                 double* g_recon, cudaStream_t st);
@@ -294,13 +296,11 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
     return n;
 }
 
-int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
-                         double* ws, double* lat00, double* lat11, int32_t* sel, void* stream) {
-    LGAE_TRY(check_desc(d));
-    if (d->is_decoder || batch < 0) return LGAE_E_BADARG;
-    if (batch == 0) return LGAE_OK;   // empty batch: nothing to launch (the tensors' pointers may be NULL)
-    if (!theta || !p4 || !ws || !lat00 || !lat11) return LGAE_E_BADARG;
-    cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+
+// Launch sequence of LGNEncoder.forward; `pack` = also pack the MLP weights (a caller that runs both models packs them once).
+static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
+                              double* ws, double* lat00, double* lat11, int32_t* sel, bool pack, cudaStream_t st) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
     SideStream* ss = L.rsave[0] >= 0 ? side_stream() : nullptr;
@@ -315,7 +315,7 @@ int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const doub
             LGAE_CUDA_TRY(cudaEventRecord(ss->join[l], ss->s), "join");
         }
     }
-    LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
+    if (pack) LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
     LGAE_TRY(run_enc_input(d, theta, p4, batch, ws + L.mass, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
         if (ss)
@@ -329,14 +329,10 @@ int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     return run_enc_latent(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], lat00, lat11, sel, st);
 }
 
-int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
-                          double* ws, const int32_t* sel, const double* g_lat00, const double* g_lat11, double* gtheta,
-                          double* partials, double l1_lambda, double* loss_accumulate, void* stream) {
-    LGAE_TRY(check_desc(d));
-    if (d->is_decoder || !theta || !gtheta || !partials || batch < 0 || (batch > 0 && (!p4 || !ws))) return LGAE_E_BADARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    PartPlan plan;
-    plan.base = partials;
+// Launch sequence of the encoder adjoint; appends its blocks / segments to `plan` (no reduce).
+static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
+                               double* ws, const int32_t* sel, const double* g_lat00, const double* g_lat11, PartPlan& plan,
+                               cudaStream_t st) {
     SideStream* ss = side_stream();
     std::unique_lock<std::mutex> side_lock(g_side_mu, std::defer_lock);
     if (ss) side_lock.lock();
@@ -381,19 +377,14 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
             LGAE_CUDA_TRY(cudaStreamWaitEvent(st, ss->join[0], 0), "join wait");
         }
     }
-    return run_reduce_plan(&plan, d->n_params, gtheta, theta, l1_lambda, loss_accumulate, st);
+    return LGAE_OK;
 }
 
-int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
-                         double* gen00, void* stream) {
-    LGAE_TRY(check_desc(d));
-    if (!d->is_decoder || batch < 0) return LGAE_E_BADARG;
-    if (batch == 0) return LGAE_OK;
-    if (!theta || !lat11 || !ws || !recon) return LGAE_E_BADARG;
-    cudaStream_t st = (cudaStream_t)stream;
+static int dec_forward_launch(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
+                              double* gen00, bool pack, cudaStream_t st) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
-    LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
+    if (pack) LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
     LGAE_TRY(run_dec_input(d, theta, batch, lat11, ws + L.y, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
         LGAE_TRY(run_level_fwd(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, ws + L.spre[l],
@@ -403,15 +394,8 @@ int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     return run_dec_output(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], recon, gen00, st);
 }
 
-int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws,
-                          const double* g_recon, const double* g_gen00, double* g_lat11, double* gtheta, double* partials,
-                          double l1_lambda, double* loss_accumulate, void* stream) {
-    LGAE_TRY(check_desc(d));
-    if (!d->is_decoder || !theta || !gtheta || !partials || batch < 0 || (batch > 0 && (!lat11 || !ws || !g_recon || !g_lat11)))
-        return LGAE_E_BADARG;
-    cudaStream_t st = (cudaStream_t)stream;
-    PartPlan plan;
-    plan.base = partials;
+static int dec_backward_launch(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws,
+                               const double* g_recon, const double* g_gen00, double* g_lat11, PartPlan& plan, cudaStream_t st) {
     if (batch > 0) {
         const Layout L = layout(d, batch);
         const int64_t rows = (int64_t)batch * d->n_particles;
@@ -437,7 +421,87 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
         }
         LGAE_TRY(run_dec_input_bwd(d, theta, batch, lat11, ws + L.y, ws + L.gS[cur], ws + L.gV[cur], ws + L.gy, g_lat11, &plan, st));
     }
-    return run_reduce_plan(&plan, d->n_params, gtheta, theta, l1_lambda, loss_accumulate, st);
+    return LGAE_OK;
+}
+
+extern "C" {
+
+int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
+                         double* ws, double* lat00, double* lat11, int32_t* sel, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (d->is_decoder || batch < 0) return LGAE_E_BADARG;
+    if (batch == 0) return LGAE_OK;   // empty batch: nothing to launch (the tensors' pointers may be NULL)
+    if (!theta || !p4 || !ws || !lat00 || !lat11) return LGAE_E_BADARG;
+    return enc_forward_launch(d, theta, p4, node_mask, batch, ws, lat00, lat11, sel, true, (cudaStream_t)stream);
+}
+
+int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
+                          double* ws, const int32_t* sel, const double* g_lat00, const double* g_lat11, double* gtheta,
+                          double* partials, double l1_lambda, double* loss_accumulate, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (d->is_decoder || !theta || !gtheta || !partials || batch < 0 || (batch > 0 && (!p4 || !ws))) return LGAE_E_BADARG;
+    PartPlan plan;
+    plan.base = partials;
+    LGAE_TRY(enc_backward_launch(d, theta, p4, node_mask, batch, ws, sel, g_lat00, g_lat11, plan, (cudaStream_t)stream));
+    return run_reduce_plan(&plan, d->n_params, gtheta, theta, l1_lambda, loss_accumulate, (cudaStream_t)stream);
+}
+
+int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
+                         double* gen00, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!d->is_decoder || batch < 0) return LGAE_E_BADARG;
+    if (batch == 0) return LGAE_OK;
+    if (!theta || !lat11 || !ws || !recon) return LGAE_E_BADARG;
+    return dec_forward_launch(d, theta, lat11, batch, ws, recon, gen00, true, (cudaStream_t)stream);
+}
+
+int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws,
+                          const double* g_recon, const double* g_gen00, double* g_lat11, double* gtheta, double* partials,
+                          double l1_lambda, double* loss_accumulate, void* stream) {
+    LGAE_TRY(check_desc(d));
+    if (!d->is_decoder || !theta || !gtheta || !partials || batch < 0 || (batch > 0 && (!lat11 || !ws || !g_recon || !g_lat11)))
+        return LGAE_E_BADARG;
+    PartPlan plan;
+    plan.base = partials;
+    LGAE_TRY(dec_backward_launch(d, theta, lat11, batch, ws, g_recon, g_gen00, g_lat11, plan, (cudaStream_t)stream));
+    return run_reduce_plan(&plan, d->n_params, gtheta, theta, l1_lambda, loss_accumulate, (cudaStream_t)stream);
+}
+
+int64_t lgae_train_step_partials_doubles(const LgaeModelDesc* enc, const LgaeModelDesc* dec, int32_t batch) {
+    const int64_t a = lgae_partials_doubles(enc, batch), b = lgae_partials_doubles(dec, batch);
+    return (a < 0 || b < 0) ? -1 : a + b;
+}
+
+int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
+                    const double* p4_in, const uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4, double* norm_factor,
+                    double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel, double* recon, double* g_recon,
+                    double* g_lat11, double* jet_loss, double* loss, double* gtheta, int64_t gtheta_dec_offset, double* partials,
+                    double l1_lambda, void* stream) {
+    LGAE_TRY(check_desc(enc));
+    LGAE_TRY(check_desc(dec));
+    if (enc->is_decoder || !dec->is_decoder || batch < 1 || gtheta_dec_offset < enc->n_params) return LGAE_E_BADARG;
+    if (!theta_enc || !theta_dec || !p4_in || !p4 || !ws_enc || !ws_dec || !lat00 || !lat11 || !sel || !recon || !g_recon || !g_lat11 ||
+        !jet_loss || !loss || !gtheta || !partials)
+        return LGAE_E_BADARG;
+    if (enc->n_particles > 32) return LGAE_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double* x = p4_in;
+    if (normalize) {
+        LGAE_TRY(run_normalize(p4_in, batch, enc->n_particles, p4, norm_factor, st));
+        x = p4;
+    }
+    // forward (each model packs its MLP weights at its start), loss + its gradient
+    LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, true, st));
+    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, true, st));
+    LGAE_TRY(run_chamfer(recon, x, batch, dec->n_particles, enc->n_particles, loss, jet_loss, nullptr, g_recon, st));
+    // both adjoints append to one plan; a single gradient-init + reduce pair finishes the step
+    PartPlan plan;
+    plan.base = partials;
+    plan.theta_base = gtheta_dec_offset;
+    LGAE_TRY(dec_backward_launch(dec, theta_dec, lat11, batch, ws_dec, g_recon, nullptr, g_lat11, plan, st));
+    plan.theta_base = 0;
+    LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan, st));
+    return run_reduce_plan2(&plan, theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, loss, st);
 }
 
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,

@@ -278,6 +278,7 @@ struct SegTable {
 struct PartPlan {
     double* base = nullptr;
     int64_t used = 0;
+    int64_t theta_base = 0;   // added to every segment's theta offset (two models sharing one gradient bucket)
     SegTable table;
     PartPlan() { table.n = 0; table.pad = 0; }
     // reserve rows x width doubles; returns the block's offset
@@ -289,6 +290,7 @@ struct PartPlan {
     // declare that columns [col, col+len) of the block at `off` hold the gradient of theta[theta_off ...]
     int seg(int64_t theta_off, int64_t off, int64_t stride, int64_t col, int64_t len, int rows) {
         if (len <= 0) return LGAE_OK;
+        theta_off += theta_base;
         if (table.n > 0) {   // merge with the previous segment when both ranges continue it
             Seg& p = table.s[table.n - 1];
             if (p.rows == rows && p.stride == stride && p.theta_off + p.len == theta_off && p.part_off + p.len == off + col) {

@@ -678,6 +678,27 @@ __global__ void __launch_bounds__(256) grad_init_kernel(const double* theta, int
     if (threadIdx.x == 0 && psum) psum[blockIdx.x] = s;
 }
 
+// Two-model variant of grad_init_kernel for a shared gradient bucket: model A owns [0, na), model B owns [off_b, off_b + nb).
+__global__ void __launch_bounds__(256) grad_init2_kernel(const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b,
+                                                         double lambda, double* gtheta, double* psum) {
+    pdl_launch();
+    pdl_wait();
+    __shared__ double scratch[32];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool in_a = i < na;
+        double g = 0.0;
+        if (lambda != 0.0) {
+            const double v = in_a ? theta_a[i] : theta_b[i - na];
+            s += fabs(v);
+            g = lambda * (v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0));
+        }
+        gtheta[in_a ? i : off_b + (i - na)] = g;
+    }
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0 && psum) psum[blockIdx.x] = s;
+}
+
 // gtheta[seg] += sum over the rows of the segment's block.  blockIdx.y = segment, blockDim = (32 columns, 8 row groups);
 // fixed summation order => deterministic gradients.  The extra y-block (blockIdx.y == t.n) adds the L1 term to the loss.
 __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, const double* partials, double* gtheta, const double* psum,
@@ -868,6 +889,30 @@ int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const doub
     return check_launch("reduce_partials");
 }
 int reduce_scratch_doubles() { return L1_BLOCKS_MAX; }
+
+// The same for two models whose gradients share one bucket (segments of model B were declared with plan->theta_base = off_b).
+int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta,
+                     double lambda, double* loss, cudaStream_t st) {
+    const bool l1 = lambda != 0.0;
+    int nblk = (int)((na + nb + 1023) / 1024);
+    nblk = nblk < 1 ? 1 : (nblk > L1_BLOCKS_MAX ? L1_BLOCKS_MAX : nblk);
+    double* psum = plan->base + plan->used;
+    {
+        LaunchScope ls_("grad_init", st);
+        launch_k(grad_init2_kernel, dim3(nblk), dim3(256), 0, st, theta_a, na, theta_b, nb, off_b, l1 ? lambda : 0.0, gtheta, l1 ? psum : nullptr);
+        if (int rc = check_launch("grad_init")) return rc;
+    }
+    if (plan->table.n == 0 && !l1) return LGAE_OK;
+    int chunks = 0;
+    for (int i = 0; i < plan->table.n; ++i) {
+        plan->table.chunk0[i] = chunks;
+        chunks += (plan->table.s[i].len + 31) / 32;
+    }
+    plan->table.chunk0[plan->table.n] = chunks;
+    LaunchScope ls_("reduce_partials", st);
+    launch_k(reduce_segs_kernel, dim3(chunks + 1), dim3(32, 8), 0, st, plan->table, plan->base, gtheta, psum, nblk, lambda, l1 ? loss : nullptr);
+    return check_launch("reduce_partials");
+}
 // Doubles of partial rows used by the glue adjoints of a model.
 int64_t glue_part_doubles(const LgaeModelDesc* d, int batch) {
     const int64_t g = sm_count(), gj = glue_grid(batch);

@@ -88,7 +88,8 @@ class FusedTrainStep:
         self.norm_factor = torch.ones(B, **f64)
         self.mask = torch.ones((B, N), dtype=torch.uint8, device=dev) if use_labels else None
         self.ws_e, self.ws_d = self.pe.workspace(B, dev), self.pd.workspace(B, dev)
-        self.part_e, self.part_d = self.pe.partials(B, dev), self.pd.partials(B, dev)
+        n_part = self.lib.lgae_train_step_partials_doubles(C.byref(self.pe.desc), C.byref(self.pd.desc), B)
+        self.part = torch.empty(max(int(n_part), 1), **f64)
         self.latent00 = torch.empty((2, B, 1, ts, 1), **f64)
         self.latent11 = torch.empty((2, B, 1, tv, 4), **f64)
         self.sel = torch.empty((4, 2, B, max(self.pe.tau_s, self.pe.tau_v)), dtype=torch.int32, device=dev)
@@ -99,6 +100,7 @@ class FusedTrainStep:
         self.loss = torch.zeros((), **f64)
         # one flat gradient bucket for both models (a single all-reduce per step); every param.grad is a view of it
         off_d = (self.pe.n_params + 3) // 4 * 4   # keep the decoder bucket 32-byte aligned
+        self.off_d = off_d
         self.g_all = torch.zeros(off_d + self.pd.n_params, **f64)
         self.g_e = self.g_all[:self.pe.n_params]
         self.g_d = self.g_all[off_d:]
@@ -125,18 +127,11 @@ class FusedTrainStep:
         th_e, _ = self.enc._flat_params()
         th_d, _ = self.dec._flat_params()
         self._thetas = (th_e.data_ptr(), th_d.data_ptr())
-        if self.normalize:
-            check(lib.lgae_normalize_p4(ptr(self.p4_in), B, pe.n_particles, ptr(self.p4), ptr(self.norm_factor), st), "normalize_p4")
-        check(lib.lgae_encoder_forward(C.byref(pe.desc), ptr(th_e), ptr(self.p4), ptr(self.mask), B, ptr(self.ws_e), ptr(self.latent00),
-                                       ptr(self.latent11), ptr(self.sel), st), "encoder_forward")
-        check(lib.lgae_decoder_forward(C.byref(pd.desc), ptr(th_d), ptr(self.latent11), B, ptr(self.ws_d), ptr(self.recon), None, st),
-              "decoder_forward")
-        check(lib.lgae_chamfer(ptr(self.recon), ptr(self.p4), B, pd.n_particles, pe.n_particles, ptr(self.loss), ptr(self.jet_loss), None,
-                               ptr(self.g_recon), st), "chamfer")
-        check(lib.lgae_decoder_backward(C.byref(pd.desc), ptr(th_d), ptr(self.latent11), B, ptr(self.ws_d), ptr(self.g_recon), None,
-                                        ptr(self.g_lat11), ptr(self.g_d), ptr(self.part_d), self.l1, ptr(self.loss), st), "decoder_backward")
-        check(lib.lgae_encoder_backward(C.byref(pe.desc), ptr(th_e), ptr(self.p4), ptr(self.mask), B, ptr(self.ws_e), ptr(self.sel), None,
-                                        ptr(self.g_lat11), ptr(self.g_e), ptr(self.part_e), self.l1, ptr(self.loss), st), "encoder_backward")
+        check(lib.lgae_train_step(C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(self.p4_in), ptr(self.mask), B,
+                                  1 if self.normalize else 0, ptr(self.p4), ptr(self.norm_factor), ptr(self.ws_e), ptr(self.ws_d),
+                                  ptr(self.latent00), ptr(self.latent11), ptr(self.sel), ptr(self.recon), ptr(self.g_recon),
+                                  ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss), ptr(self.g_all), self.off_d, ptr(self.part), self.l1,
+                                  st), "train_step")
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size
             dist.all_reduce(self.g_all, op=dist.ReduceOp.SUM, group=self.group)
