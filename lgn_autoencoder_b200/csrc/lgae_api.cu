@@ -48,6 +48,8 @@ int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const
                        const double* g_gen00, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
 int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const double* theta, double lambda, double* loss, cudaStream_t st);
 int reduce_scratch_doubles();
+int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, const double* V, const double* target, double* recon,
+                 double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, PartPlan* plan, cudaStream_t st);
 int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta,
                      double lambda, double* loss, cudaStream_t st);
 int64_t glue_part_doubles(const LgaeModelDesc* d, int batch);
@@ -381,7 +383,7 @@ static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, cons
 }
 
 static int dec_forward_launch(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
-                              double* gen00, bool pack, cudaStream_t st) {
+                              double* gen00, bool pack, cudaStream_t st, bool with_output = true) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
     if (pack) LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
@@ -391,18 +393,21 @@ static int dec_forward_launch(const LgaeModelDesc* d, const double* theta, const
                                ws + L.V[l + 1], st));
         if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
+    if (!with_output) return LGAE_OK;   // the caller runs the fused tail (reconstruction + loss + adjoint of the output map)
     return run_dec_output(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], recon, gen00, st);
 }
 
 static int dec_backward_launch(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws,
-                               const double* g_recon, const double* g_gen00, double* g_lat11, PartPlan& plan, cudaStream_t st) {
+                               const double* g_recon, const double* g_gen00, double* g_lat11, PartPlan& plan, cudaStream_t st,
+                               bool with_output = true) {
     if (batch > 0) {
         const Layout L = layout(d, batch);
         const int64_t rows = (int64_t)batch * d->n_particles;
         const int nl = d->n_levels;
         if (cudaMemsetAsync(ws + L.gy, 0, (size_t)rows * 8 * sizeof(double), st) != cudaSuccess) return check_launch("memset gy");
         int cur = 0;
-        LGAE_TRY(run_dec_output_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], g_recon, g_gen00, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
+        if (with_output)   // otherwise the fused tail already left dL/dV of the last level in gV[0]
+            LGAE_TRY(run_dec_output_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], g_recon, g_gen00, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
         bool gs_zero = g_gen00 == nullptr;
         for (int l = nl - 1; l >= 0; --l) {
             const double* g_spre = nullptr;
@@ -469,7 +474,9 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
 
 int64_t lgae_train_step_partials_doubles(const LgaeModelDesc* enc, const LgaeModelDesc* dec, int32_t batch) {
     const int64_t a = lgae_partials_doubles(enc, batch), b = lgae_partials_doubles(dec, batch);
-    return (a < 0 || b < 0) ? -1 : a + b;
+    if (a < 0 || b < 0) return -1;
+    // + the fused decoder tail's rows (one per jet) and one trailing double whose first 4 bytes are its completion counter
+    return a + b + (int64_t)batch * 4 * dec->channels[dec->n_levels] + 1;
 }
 
 int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
@@ -492,13 +499,19 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
     }
     // forward (each model packs its MLP weights at its start), loss + its gradient
     LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, true, st));
-    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, true, st));
-    LGAE_TRY(run_chamfer(recon, x, batch, dec->n_particles, enc->n_particles, loss, jet_loss, nullptr, g_recon, st));
+    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, true, st, false));
     // both adjoints append to one plan; a single gradient-init + reduce pair finishes the step
     PartPlan plan;
     plan.base = partials;
     plan.theta_base = gtheta_dec_offset;
-    LGAE_TRY(dec_backward_launch(dec, theta_dec, lat11, batch, ws_dec, g_recon, nullptr, g_lat11, plan, st));
+    {
+        // fused decoder tail: reconstruction, chamfer (+ batch sum), loss gradient, adjoint of the output map
+        const Layout Ld = layout(dec, batch);
+        unsigned int* counter = reinterpret_cast<unsigned int*>(partials + lgae_train_step_partials_doubles(enc, dec, batch) - 1);
+        LGAE_TRY(run_dec_tail(dec, theta_dec, batch, enc->n_particles, ws_dec + Ld.V[dec->n_levels], x, recon, g_recon, ws_dec + Ld.gV[0],
+                              jet_loss, loss, counter, &plan, st));
+    }
+    LGAE_TRY(dec_backward_launch(dec, theta_dec, lat11, batch, ws_dec, g_recon, nullptr, g_lat11, plan, st, false));
     plan.theta_base = 0;
     LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan, st));
     return run_reduce_plan2(&plan, theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, loss, st);

@@ -614,6 +614,160 @@ __global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const
     }
 }
 
+// Decoder tail of a training step, one CTA per jet: mix_to_output + rep_to_p (reconstruction), get_real('sum') + chamfer against
+// the target jet, the loss gradient, and the adjoint of the output map -- dec_output, chamfer, chamfer_sum and dec_output_bwd
+// in one launch.  The last CTA to finish adds up the per-jet losses in a fixed order (`counter` must be zero at launch; it is
+// reset for the next one).  Row of partials per CTA: [out00 (2C, zero: the output scalars do not reach the loss) | out11 (2C)].
+struct DecTailArgs {
+    const double* theta;
+    int64_t off11;
+    int B, N, M, C;
+    const double* V;        // (B,N,C,4,2) node vectors after the last level
+    const double* target;   // (B,M,4)
+    double* recon;          // (2,B,N,4)
+    double* g_recon;        // (2,B,N,4) or nullptr
+    double* gV;             // (B,N,C,4,2) gradient wrt V
+    double* jet_loss;       // (B)
+    double* loss;           // (1)
+    unsigned int* counter;
+    double* partials;
+    int64_t part_stride;
+};
+__global__ void __launch_bounds__(128) dec_tail_kernel(const DecTailArgs a) {
+    pdl_launch();
+    extern __shared__ __align__(128) double smem[];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = a.N, M = a.M, C = a.C, B = a.B;
+    cplx* V_s = reinterpret_cast<cplx*>(smem);          // N*C*4
+    cplx* gg_s = V_s + N * C * 4;                        // N*4   canonical gradient of the generated vectors
+    cplx* w_s = gg_s + N * 4;                            // C
+    double* x = reinterpret_cast<double*>(w_s + C);      // N*4
+    double* t = x + 4 * N;                               // M*4
+    double* m1 = t + 4 * M;                              // N
+    double* m2 = m1 + N;                                 // M
+    int* j1 = reinterpret_cast<int*>(m2 + M);            // N
+    int* i2 = j1 + N;                                    // M
+    __shared__ double dir_sum[2];
+    __shared__ double scratch[32];
+    __shared__ bool is_last;
+    for (int c = tid; c < C; c += blockDim.x) w_s[c] = wget(a.theta, a.off11, 1, C, 0, c);
+    pdl_wait();
+    {
+        const double2* gv = reinterpret_cast<const double2*>(a.V) + (int64_t)b * N * C * 4;
+        for (int k = tid; k < N * C * 4; k += blockDim.x) V_s[k] = gv[k];
+        for (int k = tid; k < 4 * M; k += blockDim.x) t[k] = a.target[(int64_t)b * M * 4 + k];
+    }
+    __syncthreads();
+    const int64_t plane = (int64_t)B * N * 4;
+    // ---- reconstruction (lgn_decoder.py:286-296) ----
+    for (int i = tid; i < N; i += blockDim.x) {
+        cplx gen[4] = {czero(), czero(), czero(), czero()};
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cfma(gen[mu], w_s[c], V_s[(i * C + c) * 4 + mu]);
+        cplx pc[4];
+        cart_from_canon(gen, pc);
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) {
+            a.recon[((int64_t)b * N + i) * 4 + mu] = pc[mu].x;
+            a.recon[plane + ((int64_t)b * N + i) * 4 + mu] = pc[mu].y;
+            x[4 * i + mu] = pc[mu].x + pc[mu].y;   // get_real(..., 'sum'), utils/utils.py:201-202
+        }
+    }
+    __syncthreads();
+    // ---- chamfer (chamfer_loss.py:16-31): the two directions side by side on even / odd warps ----
+    auto dist = [&](int i, int j) {
+        double s = 0.0;
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) { const double d = x[4 * i + mu] - t[4 * j + mu]; s += d * d; }
+        return s;
+    };
+    const int nw2 = (blockDim.x >> 5) >> 1;
+    if ((warp & 1) == 0) {
+        for (int i = (warp >> 1) * 32 + lane; i < N; i += nw2 * 32) {
+            double best = dist(i, 0);
+            int bj = 0;
+            for (int j = 1; j < M; ++j) { const double d = dist(i, j); if (d < best) { best = d; bj = j; } }
+            m1[i] = best; j1[i] = bj;
+        }
+    } else {
+        for (int j = (warp >> 1) * 32 + lane; j < M; j += nw2 * 32) {
+            double best = dist(0, j);
+            int bi = 0;
+            for (int i = 1; i < N; ++i) { const double d = dist(i, j); if (d < best) { best = d; bi = i; } }
+            m2[j] = best; i2[j] = bi;
+        }
+    }
+    __syncthreads();
+    if (warp < 2) {
+        const double* mm = warp == 0 ? m1 : m2;
+        const int n = warp == 0 ? N : M;
+        double acc = 0.0;
+        for (int k = lane; k < n; k += 32) acc += mm[k];
+        acc = warp_sum(acc);
+        if (lane == 0) dir_sum[warp] = acc;
+    }
+    // ---- loss gradient and the adjoint of rep_to_p / mix_to_output ----
+    for (int i = tid; i < N; i += blockDim.x) {
+        double g[4];
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) g[mu] = x[4 * i + mu] - t[4 * j1[i] + mu];
+        for (int j = 0; j < M; ++j)
+            if (i2[j] == i) {
+#pragma unroll
+                for (int mu = 0; mu < 4; ++mu) g[mu] += x[4 * i + mu] - t[4 * j + mu];
+            }
+        cplx gp[4], gg[4];
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) {
+            gp[mu] = cmake(g[mu], g[mu]);
+            if (a.g_recon) {
+                a.g_recon[((int64_t)b * N + i) * 4 + mu] = g[mu];
+                a.g_recon[plane + ((int64_t)b * N + i) * 4 + mu] = g[mu];
+            }
+        }
+        canon_from_cplx(gp, gg);   // adjoint of rep_to_p
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(a.gV)[(((int64_t)b * N + i) * C + c) * 4 + mu] = cmulc(w_s[c], gg[mu]);
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) gg_s[i * 4 + mu] = gg[mu];
+    }
+    __syncthreads();
+    if (tid == 0) a.jet_loss[b] = 0.5 * (dir_sum[0] + dir_sum[1]);
+    // ---- output-weight gradient: one warp per channel, lanes over the particles ----
+    double* part = a.partials + (int64_t)b * a.part_stride;
+    for (int c = warp; c < C; c += blockDim.x >> 5) {
+        cplx acc = czero();
+        for (int i = lane; i < N; i += 32)
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cfmac(acc, V_s[(i * C + c) * 4 + mu], gg_s[i * 4 + mu]);
+        acc.x = warp_sum(acc.x);
+        acc.y = warp_sum(acc.y);
+        if (lane == 0) {
+            part[c] = 0.0;
+            part[C + c] = 0.0;
+            part[2 * C + c] = acc.x;
+            part[3 * C + c] = acc.y;
+        }
+    }
+    // ---- the last CTA sums the per-jet losses (fixed order => deterministic) ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(a.counter, 1u) == (unsigned)(B - 1);
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int k = tid; k < B; k += blockDim.x) s += __ldcg(a.jet_loss + k);
+        s = block_sum(s, scratch);
+        if (tid == 0) {
+            a.loss[0] = s;
+            *a.counter = 0u;
+        }
+    }
+}
+
 // Deterministic single-block sum of n values: out[0] = sum (or += when accumulate).
 __global__ void __launch_bounds__(1024) sum_kernel(const double* v, int64_t n, double scale, double* out, int accumulate) {
     pdl_launch();
@@ -936,6 +1090,26 @@ int run_chamfer(const double* recon, const double* target, int B, int N, int M, 
         rc = check_launch("chamfer_sum");
     }
     return rc;
+}
+// mix_to_output + chamfer + their adjoints for a training step (see dec_tail_kernel).  `counter`: 4 bytes of device scratch.
+int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, const double* V, const double* target, double* recon,
+                 double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, PartPlan* plan, cudaStream_t st) {
+    DecTailArgs a;
+    a.theta = theta; a.off11 = d->off_out11;
+    a.B = B; a.N = d->n_particles; a.M = M; a.C = d->channels[d->n_levels];
+    a.V = V; a.target = target; a.recon = recon; a.g_recon = g_recon; a.gV = gV; a.jet_loss = jet_loss; a.loss = loss; a.counter = counter;
+    const int C = a.C, N = a.N;
+    const int64_t w = 4 * C, off = plan->block(B, w);
+    if (int rc = plan->seg(d->off_out00, off, w, 0, 2 * C, B)) return rc;
+    if (int rc = plan->seg(d->off_out11, off, w, 2 * C, 2 * C, B)) return rc;
+    a.partials = plan->base + off; a.part_stride = w;
+    const size_t bytes = ((size_t)N * C * 4 + N * 4 + C) * sizeof(cplx) + (size_t)(4 * N + 4 * M + N + M) * sizeof(double) + (size_t)(N + M) * sizeof(int);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    if (int rc = ensure_smem((const void*)dec_tail_kernel, bytes)) return rc;
+    if (cudaMemsetAsync(counter, 0, sizeof(unsigned int), st) != cudaSuccess) return check_launch("memset counter");
+    LaunchScope ls_("dec_tail", st);
+    launch_k(dec_tail_kernel, dim3(B), dim3(128), bytes, st, a);
+    return check_launch("dec_tail");
 }
 int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st) {
     LaunchScope ls_("normalize_p4", st);
