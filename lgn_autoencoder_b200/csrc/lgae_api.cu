@@ -31,7 +31,8 @@ int64_t level_part_width(const LgaeModelDesc* d, int level);
 int run_mlp(const LgaeModelDesc* d, int level, const double* theta, const double* wpack, const double* x, int64_t rows, double* acts,
             double* y, const double* g_y, double* g_x, PartPlan* plan, bool bwd, cudaStream_t st);
 int64_t mlp_pack_doubles(const LgaeModelDesc* d, int level);
-int run_mlp_pack(const LgaeModelDesc* d, const double* theta, double* out, const int64_t* out_off, cudaStream_t st);
+int run_mlp_pack(const LgaeModelDesc* d, const double* theta, double* out, const int64_t* out_off, cudaStream_t st,
+                 const LgaeModelDesc* d2 = nullptr, const double* theta2 = nullptr, double* out2 = nullptr, const int64_t* out_off2 = nullptr);
 int mlp_padded_width(const LgaeModelDesc* d, int level);
 int64_t mlp_part_width(const LgaeModelDesc* d, int level);
 int mlp_bwd_grid();
@@ -48,6 +49,8 @@ int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const
                        const double* g_gen00, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
 int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const double* theta, double lambda, double* loss, cudaStream_t st);
 int reduce_scratch_doubles();
+int run_latent_bridge(const LgaeModelDesc* de, const double* theta_e, const LgaeModelDesc* dd, const double* theta_d, int B, const double* S,
+                      const double* V, double* lat00, double* lat11, int32_t* sel, double* y, double* S0, double* V0, cudaStream_t st);
 int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, const double* V, const double* target, double* recon,
                  double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, PartPlan* plan, cudaStream_t st);
 int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta,
@@ -302,7 +305,7 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
 
 // Launch sequence of LGNEncoder.forward; `pack` = also pack the MLP weights (a caller that runs both models packs them once).
 static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
-                              double* ws, double* lat00, double* lat11, int32_t* sel, bool pack, cudaStream_t st) {
+                              double* ws, double* lat00, double* lat11, int32_t* sel, bool pack, cudaStream_t st, bool with_latent = true) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
     SideStream* ss = L.rsave[0] >= 0 ? side_stream() : nullptr;
@@ -328,6 +331,7 @@ static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const
                                L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, ws + L.spre[l], ws + L.V[l + 1], st));
         if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
+    if (!with_latent) return LGAE_OK;   // the caller runs the fused latent bridge
     return run_enc_latent(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], lat00, lat11, sel, st);
 }
 
@@ -383,11 +387,11 @@ static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, cons
 }
 
 static int dec_forward_launch(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
-                              double* gen00, bool pack, cudaStream_t st, bool with_output = true) {
+                              double* gen00, bool pack, cudaStream_t st, bool with_output = true, bool with_input = true) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
     if (pack) LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
-    LGAE_TRY(run_dec_input(d, theta, batch, lat11, ws + L.y, ws + L.S[0], ws + L.V[0], st));
+    if (with_input) LGAE_TRY(run_dec_input(d, theta, batch, lat11, ws + L.y, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
         LGAE_TRY(run_level_fwd(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, ws + L.spre[l],
                                ws + L.V[l + 1], st));
@@ -497,9 +501,19 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
         LGAE_TRY(run_normalize(p4_in, batch, enc->n_particles, p4, norm_factor, st));
         x = p4;
     }
-    // forward (each model packs its MLP weights at its start), loss + its gradient
-    LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, true, st));
-    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, true, st, false));
+    // forward: one launch packs the MLP weights of both models
+    {
+        const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
+        LGAE_TRY(run_mlp_pack(enc, theta_enc, ws_enc, Le.wpack, st, dec, theta_dec, ws_dec, Ld.wpack));
+    }
+    LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false));
+    {
+        // fused encoder latent map + decoder input map
+        const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
+        LGAE_TRY(run_latent_bridge(enc, theta_enc, dec, theta_dec, batch, ws_enc + Le.S[enc->n_levels], ws_enc + Le.V[enc->n_levels], lat00,
+                                   lat11, sel, ws_dec + Ld.y, ws_dec + Ld.S[0], ws_dec + Ld.V[0], st));
+    }
+    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, false, st, false, false));
     // both adjoints append to one plan; a single gradient-init + reduce pair finishes the step
     PartPlan plan;
     plan.base = partials;

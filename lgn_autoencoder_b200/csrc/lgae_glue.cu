@@ -117,10 +117,8 @@ LGAE_DEV double msq_of(const double* v) {   // get_msq, lgn_encoder.py:499-505 (
 }
 
 // One CTA per jet.  Shared: L00 (N*tau_s complex), L11 Cartesian (N*tau_v*4 complex).
-__global__ void __launch_bounds__(256) enc_latent_kernel(const LatentArgs a) {
-    pdl_launch();
-    pdl_wait();
-    extern __shared__ __align__(128) double smem[];
+// `lat_out` (optional, shared memory, T_v * 4 complex): the jet's latent vectors, for a fused consumer (latent_bridge_kernel).
+LGAE_DEV void enc_latent_body(const LatentArgs& a, double* smem, cplx* lat_out) {
     const int b = blockIdx.x, tid = threadIdx.x;
     const int N = a.N, C = a.C, ts = a.tau_s, tv = a.tau_v;
     const bool mix = a.mode == LGAE_LATENT_MIX;
@@ -165,6 +163,7 @@ __global__ void __launch_bounds__(256) enc_latent_kernel(const LatentArgs a) {
             for (int i = 0; i < rows; ++i) acc = cadd(acc, L11[i * tv * 4 + it]);
             a.lat11[(int64_t)(0 * B + b) * tv * 4 + it] = acc.x * scale;
             a.lat11[(int64_t)(1 * B + b) * tv * 4 + it] = acc.y * scale;
+            if (lat_out) lat_out[it] = cscale(acc, scale);
         }
         return;
     }
@@ -205,9 +204,19 @@ __global__ void __launch_bounds__(256) enc_latent_kernel(const LatentArgs a) {
         for (int mu = 0; mu < 4; ++mu) {
             const cplx z = L11[(best * tv + t) * 4 + mu];
             a.lat11[((int64_t)(part * B + b) * Tv + T) * 4 + mu] = part ? z.y : z.x;
+            if (lat_out) {   // re and im parts are selected independently: two threads fill the two halves
+                if (part) lat_out[T * 4 + mu].y = z.y; else lat_out[T * 4 + mu].x = z.x;
+            }
         }
         if (a.sel) a.sel[((int64_t)((2 + kind) * 2 + part) * B + b) * tmax + t] = best;
     }
+}
+
+__global__ void __launch_bounds__(256) enc_latent_kernel(const LatentArgs a) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(128) double smem[];
+    enc_latent_body(a, smem, nullptr);
 }
 
 // Adjoint of enc_latent.  Persistent CTAs over jets; latent-weight gradients accumulate in shared memory.
@@ -350,15 +359,9 @@ struct DecInArgs {
     int64_t part_stride, po_g11, po_in00, po_in11;
 };
 
-__global__ void __launch_bounds__(128) dec_input_kernel(const DecInArgs a) {
-    pdl_launch();
-    pdl_wait();
-    extern __shared__ __align__(128) double smem[];
-    cplx* lat = reinterpret_cast<cplx*>(smem);   // tau*4
-    const int b = blockIdx.x, tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau, B = a.B;
-    for (int t = tid; t < tau * 4; t += blockDim.x)
-        lat[t] = cmake(a.lat11[(int64_t)(0 * B + b) * tau * 4 + t], a.lat11[(int64_t)(1 * B + b) * tau * 4 + t]);
-    __syncthreads();
+// latent_to_graph + p_cplx_to_rep + input MixReps of one jet from its latent vectors `lat` (tau * 4 complex, shared memory).
+LGAE_DEV void dec_input_body(const DecInArgs& a, const cplx* lat) {
+    const int b = blockIdx.x, tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau;
     for (int i = tid; i < N; i += blockDim.x) {
         cplx P[4] = {czero(), czero(), czero(), czero()};
         for (int t = 0; t < tau; ++t) {
@@ -378,6 +381,28 @@ __global__ void __launch_bounds__(128) dec_input_kernel(const DecInArgs a) {
             for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(a.V)[(node * C + c) * 4 + mu] = cmul(w1, y[mu]);
         }
     }
+}
+__global__ void __launch_bounds__(128) dec_input_kernel(const DecInArgs a) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(128) double smem[];
+    cplx* lat = reinterpret_cast<cplx*>(smem);   // tau*4
+    const int b = blockIdx.x, tid = threadIdx.x, tau = a.tau, B = a.B;
+    for (int t = tid; t < tau * 4; t += blockDim.x)
+        lat[t] = cmake(a.lat11[(int64_t)(0 * B + b) * tau * 4 + t], a.lat11[(int64_t)(1 * B + b) * tau * 4 + t]);
+    __syncthreads();
+    dec_input_body(a, lat);
+}
+// Encoder latent map and decoder input of a jet in one launch (the latent never leaves the CTA between the two; it is still
+// written to HBM as the step's output).  Shared memory: [enc_latent scratch | latent vectors (T_v * 4 complex)].
+__global__ void __launch_bounds__(256) latent_bridge_kernel(const LatentArgs a, const DecInArgs d, int lat_off) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(128) double smem[];
+    cplx* lat = reinterpret_cast<cplx*>(smem + lat_off);
+    enc_latent_body(a, smem, lat);
+    __syncthreads();
+    dec_input_body(d, lat);
 }
 
 // Persistent over jets, one thread per particle (N <= blockDim.x required).
@@ -982,6 +1007,23 @@ int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const doub
     LaunchScope ls_("dec_input", st);
     launch_k(dec_input_kernel, dim3(B), dim3(128), bytes, st, a);
     return check_launch("dec_input");
+}
+// enc_latent + dec_input fused (training step / inference of both models back to back).
+int run_latent_bridge(const LgaeModelDesc* de, const double* theta_e, const LgaeModelDesc* dd, const double* theta_d, int B, const double* S,
+                      const double* V, double* lat00, double* lat11, int32_t* sel, double* y, double* S0, double* V0, cudaStream_t st) {
+    LatentArgs a = latent_args(de, theta_e, B, S, V);
+    a.lat00 = lat00; a.lat11 = lat11; a.sel = sel;
+    DecInArgs di = dec_in_args(dd, theta_d, B, lat11, y, S0, V0);
+    const int rows = a.mode == LGAE_LATENT_MIX ? 1 : a.N;
+    const int mult = a.mode == LGAE_LATENT_MINMAX ? 2 : 1;
+    if (di.tau != mult * a.tau_v) return LGAE_E_BADARG;   // decoder latent width must be the encoder's output width
+    const size_t scratch = (size_t)rows * (a.tau_s + 4 * a.tau_v) * sizeof(cplx);
+    const size_t bytes = scratch + (size_t)di.tau * 4 * sizeof(cplx);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    if (int rc = ensure_smem((const void*)latent_bridge_kernel, bytes)) return rc;
+    LaunchScope ls_("latent_bridge", st);
+    launch_k(latent_bridge_kernel, dim3(B), dim3(256), bytes, st, a, di, (int)(scratch / sizeof(double)));
+    return check_launch("latent_bridge");
 }
 int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, const double* gS, const double* gV,
                       const double* gy, double* g_lat11, PartPlan* plan, cudaStream_t st) {

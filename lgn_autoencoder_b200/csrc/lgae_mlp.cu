@@ -456,27 +456,29 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
 // ------------------------------------------------------------------------------------------------------------
 // Weight pre-packing: one launch per model forward writes every level's weights in both fragment orders, so the
 // MLP kernels stage them with straight vector copies.  blockIdx = (layer, direction, level).
+constexpr int PACK_SLOTS = 2 * LGAE_MAX_LEVELS;   // levels of up to two models (encoder + decoder) per launch
 struct MlpPackArgs {
-    const double* theta;
-    double* out;
-    int n_lin;
-    int nin[LGAE_MAX_LEVELS], width[LGAE_MAX_LEVELS];
-    int64_t off_w[LGAE_MAX_LEVELS][LGAE_MAX_LINEAR];
-    int64_t out_off[LGAE_MAX_LEVELS];
+    const double* theta[PACK_SLOTS];
+    double* out[PACK_SLOTS];           // where the level's packed weights go
+    int n_lin[PACK_SLOTS];
+    int nin[PACK_SLOTS], width[PACK_SLOTS];
+    int64_t off_w[PACK_SLOTS][LGAE_MAX_LINEAR];
 };
 __global__ void __launch_bounds__(256) mlp_pack_kernel(const MlpPackArgs p) {
     pdl_launch();
     pdl_wait();   // (writes the packed weights that earlier kernels of a previous pass may still be reading)
     const int l = blockIdx.x, dir = blockIdx.y, lev = blockIdx.z;
-    const int nin = p.nin[lev], width = p.width[lev], NTW = (width + 7) / 8, NTI = (nin + 7) / 8, last = p.n_lin - 1;
+    const int n_lin = p.n_lin[lev];
+    if (l >= n_lin) return;
+    const int nin = p.nin[lev], width = p.width[lev], NTW = (width + 7) / 8, NTI = (nin + 7) / 8, last = n_lin - 1;
     int off = 0, wtotal = 0;
     for (int i = 0; i <= last; ++i) {
-        if (i < l) off += mlp_layer_frag(i, p.n_lin, NTW, NTI);
-        wtotal += mlp_layer_frag(i, p.n_lin, NTW, NTI);
+        if (i < l) off += mlp_layer_frag(i, n_lin, NTW, NTI);
+        wtotal += mlp_layer_frag(i, n_lin, NTW, NTI);
     }
     const int nout = l == last ? nin : width, nink = l == 0 ? nin : width;
-    const double* w = p.theta + p.off_w[lev][l];
-    double* dst = p.out + p.out_off[lev] + (dir ? wtotal : 0) + off;
+    const double* w = p.theta[lev] + p.off_w[lev][l];
+    double* dst = p.out[lev] + (dir ? wtotal : 0) + off;
     if (dir == 0)
         stage_w_fwd(w, nout, nink, l == 0 ? NTI : NTW, l == last ? NTI : NTW, dst);
     else
@@ -523,19 +525,30 @@ int64_t mlp_pack_doubles(const LgaeModelDesc* d, int level) {
     return 2 * (int64_t)mlp_frag_total(d->mlp_hidden + 1, (d->mlp_width[level] + 7) / 8, (2 * d->channels[level + 1] + 7) / 8);
 }
 // Pack the MLP weights of every level: out + out_off[level] receives mlp_pack_doubles(d, level) doubles.
-int run_mlp_pack(const LgaeModelDesc* d, const double* theta, double* out, const int64_t* out_off, cudaStream_t st) {
-    if (!d->has_mlp) return LGAE_OK;
+static int add_pack_slots(MlpPackArgs& p, int slot, const LgaeModelDesc* d, const double* theta, double* out, const int64_t* out_off) {
+    if (!d->has_mlp) return slot;
+    for (int l = 0; l < d->n_levels; ++l, ++slot) {
+        p.theta[slot] = theta;
+        p.out[slot] = out + out_off[l];
+        p.n_lin[slot] = d->mlp_hidden + 1;
+        p.nin[slot] = 2 * d->channels[l + 1];
+        p.width[slot] = d->mlp_width[l];
+        for (int i = 0; i < p.n_lin[slot]; ++i) p.off_w[slot][i] = d->off_mlp_w[l][i];
+    }
+    return slot;
+}
+// One launch packs the weights of all levels of one model -- or of two (d2 != NULL: the training step's encoder + decoder).
+int run_mlp_pack(const LgaeModelDesc* d, const double* theta, double* out, const int64_t* out_off, cudaStream_t st,
+                 const LgaeModelDesc* d2 = nullptr, const double* theta2 = nullptr, double* out2 = nullptr, const int64_t* out_off2 = nullptr) {
     MlpPackArgs p;
     memset(&p, 0, sizeof(p));
-    p.theta = theta; p.out = out; p.n_lin = d->mlp_hidden + 1;
-    for (int l = 0; l < d->n_levels; ++l) {
-        p.nin[l] = 2 * d->channels[l + 1];
-        p.width[l] = d->mlp_width[l];
-        p.out_off[l] = out_off[l];
-        for (int i = 0; i < p.n_lin; ++i) p.off_w[l][i] = d->off_mlp_w[l][i];
-    }
+    int slots = add_pack_slots(p, 0, d, theta, out, out_off);
+    if (d2) slots = add_pack_slots(p, slots, d2, theta2, out2, out_off2);
+    if (slots == 0) return LGAE_OK;
+    int max_lin = 0;
+    for (int i = 0; i < slots; ++i) max_lin = p.n_lin[i] > max_lin ? p.n_lin[i] : max_lin;
     LaunchScope ls_("mlp_pack", st);
-    launch_k(mlp_pack_kernel, dim3(p.n_lin, 2, d->n_levels), dim3(256), 0, st, p);
+    launch_k(mlp_pack_kernel, dim3(max_lin, 2, slots), dim3(256), 0, st, p);
     return check_launch("mlp_pack");
 }
 
