@@ -47,6 +47,10 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
 int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st);
 int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const double* g_recon,
                        const double* g_gen00, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
+int run_latent_bridge_bwd(const LgaeModelDesc* dd, const double* theta_d, const LgaeModelDesc* de, const double* theta_e, int B,
+                          const double* lat11, double* y, const double* gS_d, const double* gV_d, const double* gy, double* g_lat11,
+                          const double* S, const double* V, const int32_t* sel, double* gS_e, double* gV_e, PartPlan* plan,
+                          int64_t theta_base_d, int64_t theta_base_e, cudaStream_t st);
 int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const double* theta, double lambda, double* loss, cudaStream_t st);
 int reduce_scratch_doubles();
 int run_latent_bridge(const LgaeModelDesc* de, const double* theta_e, const LgaeModelDesc* dd, const double* theta_d, int B, const double* S,
@@ -59,6 +63,8 @@ int64_t glue_part_doubles(const LgaeModelDesc* d, int batch);
 int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
                 double* g_recon, cudaStream_t st);
 int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st);
+int run_norm_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* out, double* factor, double* mass, double* S,
+                   double* V, cudaStream_t st);
 int run_l1(const double* theta, int64_t n, double lambda, double* out, double* gtheta, cudaStream_t st);
 
 // ---- bookkeeping ------------------------------------------------------------------------------------------------
@@ -305,7 +311,8 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
 
 // Launch sequence of LGNEncoder.forward; `pack` = also pack the MLP weights (a caller that runs both models packs them once).
 static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
-                              double* ws, double* lat00, double* lat11, int32_t* sel, bool pack, cudaStream_t st, bool with_latent = true) {
+                              double* ws, double* lat00, double* lat11, int32_t* sel, bool pack, cudaStream_t st, bool with_latent = true,
+                              bool with_input = true) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
     SideStream* ss = L.rsave[0] >= 0 ? side_stream() : nullptr;
@@ -321,7 +328,7 @@ static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const
         }
     }
     if (pack) LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
-    LGAE_TRY(run_enc_input(d, theta, p4, batch, ws + L.mass, ws + L.S[0], ws + L.V[0], st));
+    if (with_input) LGAE_TRY(run_enc_input(d, theta, p4, batch, ws + L.mass, ws + L.S[0], ws + L.V[0], st));
     for (int l = 0; l < d->n_levels; ++l) {
         if (ss)
             LGAE_CUDA_TRY(cudaStreamWaitEvent(st, ss->join[l], 0), "join wait");
@@ -338,7 +345,7 @@ static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const
 // Launch sequence of the encoder adjoint; appends its blocks / segments to `plan` (no reduce).
 static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
                                double* ws, const int32_t* sel, const double* g_lat00, const double* g_lat11, PartPlan& plan,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool with_latent = true) {
     SideStream* ss = side_stream();
     std::unique_lock<std::mutex> side_lock(g_side_mu, std::defer_lock);
     if (ss) side_lock.lock();
@@ -348,7 +355,8 @@ static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, cons
         const int64_t rows = (int64_t)batch * d->n_particles;
         const int nl = d->n_levels;
         int cur = 0;
-        LGAE_TRY(run_enc_latent_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], sel, g_lat00, g_lat11, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
+        if (with_latent)   // otherwise the fused bridge adjoint already left dL/dS, dL/dV of the last level in gS[0], gV[0]
+            LGAE_TRY(run_enc_latent_bwd(d, theta, batch, ws + L.S[nl], ws + L.V[nl], sel, g_lat00, g_lat11, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
         // The scalar features of the last level only reach the latent scalars: without a gradient on those the
         // whole last-level MLP is dead in the backward pass ("dead-in-training sub-paths").
         bool gs_zero = g_lat00 == nullptr;
@@ -403,7 +411,7 @@ static int dec_forward_launch(const LgaeModelDesc* d, const double* theta, const
 
 static int dec_backward_launch(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws,
                                const double* g_recon, const double* g_gen00, double* g_lat11, PartPlan& plan, cudaStream_t st,
-                               bool with_output = true) {
+                               bool with_output = true, bool with_input = true) {
     if (batch > 0) {
         const Layout L = layout(d, batch);
         const int64_t rows = (int64_t)batch * d->n_particles;
@@ -428,7 +436,8 @@ static int dec_backward_launch(const LgaeModelDesc* d, const double* theta, cons
             cur ^= 1;
             gs_zero = false;
         }
-        LGAE_TRY(run_dec_input_bwd(d, theta, batch, lat11, ws + L.y, ws + L.gS[cur], ws + L.gV[cur], ws + L.gy, g_lat11, &plan, st));
+        if (with_input)   // otherwise the caller continues from gS/gV[n_levels & 1] and gy (fused bridge adjoint)
+            LGAE_TRY(run_dec_input_bwd(d, theta, batch, lat11, ws + L.y, ws + L.gS[cur], ws + L.gV[cur], ws + L.gy, g_lat11, &plan, st));
     }
     return LGAE_OK;
 }
@@ -496,17 +505,15 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
         return LGAE_E_BADARG;
     if (enc->n_particles > 32) return LGAE_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const double* x = p4_in;
-    if (normalize) {
-        LGAE_TRY(run_normalize(p4_in, batch, enc->n_particles, p4, norm_factor, st));
-        x = p4;
-    }
+    const double* x = normalize ? p4 : p4_in;
     // forward: one launch packs the MLP weights of both models
     {
         const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
         LGAE_TRY(run_mlp_pack(enc, theta_enc, ws_enc, Le.wpack, st, dec, theta_dec, ws_dec, Ld.wpack));
+        if (normalize)   // normalisation + encoder input map, one CTA per jet
+            LGAE_TRY(run_norm_input(enc, theta_enc, p4_in, batch, p4, norm_factor, ws_enc + Le.mass, ws_enc + Le.S[0], ws_enc + Le.V[0], st));
     }
-    LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false));
+    LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false, !normalize));
     {
         // fused encoder latent map + decoder input map
         const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
@@ -525,9 +532,17 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
         LGAE_TRY(run_dec_tail(dec, theta_dec, batch, enc->n_particles, ws_dec + Ld.V[dec->n_levels], x, recon, g_recon, ws_dec + Ld.gV[0],
                               jet_loss, loss, counter, &plan, st));
     }
-    LGAE_TRY(dec_backward_launch(dec, theta_dec, lat11, batch, ws_dec, g_recon, nullptr, g_lat11, plan, st, false));
+    LGAE_TRY(dec_backward_launch(dec, theta_dec, lat11, batch, ws_dec, g_recon, nullptr, g_lat11, plan, st, false, false));
+    {
+        // fused adjoint of the bridge: decoder input map, then encoder latent map, latent gradient handed over on chip
+        const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
+        const int cur = dec->n_levels & 1;
+        LGAE_TRY(run_latent_bridge_bwd(dec, theta_dec, enc, theta_enc, batch, lat11, ws_dec + Ld.y, ws_dec + Ld.gS[cur], ws_dec + Ld.gV[cur],
+                                       ws_dec + Ld.gy, g_lat11, ws_enc + Le.S[enc->n_levels], ws_enc + Le.V[enc->n_levels], sel,
+                                       ws_enc + Le.gS[0], ws_enc + Le.gV[0], &plan, gtheta_dec_offset, 0, st));
+    }
     plan.theta_base = 0;
-    LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan, st));
+    LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan, st, false));
     return run_reduce_plan2(&plan, theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, loss, st);
 }
 

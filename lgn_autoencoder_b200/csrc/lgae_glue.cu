@@ -28,12 +28,8 @@ LGAE_DEV void pput(double* part, int64_t off, int rows, int cols, int r, int cc,
 // ------------------------------------------------------------------------------------------------------------
 // encoder input
 // ------------------------------------------------------------------------------------------------------------
-__global__ void enc_input_kernel(const double* theta, int64_t off00, int64_t off11, const double* p4, int64_t nodes, int C,
-                                 double* mass, double* S, double* V) {
-    pdl_launch();
-    pdl_wait();
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nodes) return;
+__device__ __forceinline__ void enc_input_node(const double* theta, int64_t off00, int64_t off11, const double* p4, int64_t t, int C,
+                                               double* mass, double* S, double* V) {
     const double* p = p4 + 4 * t;
     const double m = __dsqrt_rn(fabs(minkowski_sq(p[0], p[1], p[2], p[3])));   // lgn_encoder.py:376
     mass[t] = m;
@@ -45,6 +41,14 @@ __global__ void enc_input_kernel(const double* theta, int64_t off00, int64_t off
 #pragma unroll
         for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(V)[(t * C + c) * 4 + mu] = cmul(w1, y[mu]);
     }
+}
+__global__ void enc_input_kernel(const double* theta, int64_t off00, int64_t off11, const double* p4, int64_t nodes, int C,
+                                 double* mass, double* S, double* V) {
+    pdl_launch();
+    pdl_wait();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nodes) return;
+    enc_input_node(theta, off00, off11, p4, t, C, mass, S, V);
 }
 
 __global__ void __launch_bounds__(256) enc_input_bwd_kernel(int64_t off00, int64_t off11, const double* p4, const double* mass, int64_t nodes,
@@ -220,29 +224,53 @@ __global__ void __launch_bounds__(256) enc_latent_kernel(const LatentArgs a) {
 }
 
 // Adjoint of enc_latent.  Persistent CTAs over jets; latent-weight gradients accumulate in shared memory.
-__global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a) {
-    pdl_launch();
-    pdl_wait();
-    extern __shared__ __align__(128) double smem[];
+// Split into init / per-jet / flush pieces so that the training step can run it in one kernel with the decoder-input
+// adjoint (latent_bridge_bwd_kernel), which hands the latent gradient over in shared memory.
+struct EncLatBwdSm {
+    cplx *gL00, *gL11, *gw00, *gw11, *w00_s, *w11_s, *S_s, *V_s;
+    int rows, cin;
+};
+__device__ __forceinline__ EncLatBwdSm enc_latent_bwd_init(const LatentArgs& a, double* smem) {
+    const int tid = threadIdx.x, N = a.N, C = a.C, ts = a.tau_s, tv = a.tau_v;
+    const bool mix = a.mode == LGAE_LATENT_MIX;
+    EncLatBwdSm m;
+    m.rows = mix ? 1 : N; m.cin = mix ? N * C : C;
+    const int rows = m.rows, cin = m.cin;
+    m.gL00 = reinterpret_cast<cplx*>(smem);       // rows*ts
+    m.gL11 = m.gL00 + rows * ts;                  // rows*tv*4 (canonical after the basis change)
+    m.gw00 = m.gL11 + rows * tv * 4;              // ts*cin
+    m.gw11 = m.gw00 + ts * cin;                   // tv*cin
+    m.w00_s = m.gw11 + tv * cin;                  // ts*cin   latent weights, interleaved
+    m.w11_s = m.w00_s + ts * cin;                 // tv*cin
+    m.S_s = m.w11_s + tv * cin;                   // N*C      this jet's node features
+    m.V_s = m.S_s + N * C;                        // N*C*4
+    for (int t = tid; t < (ts + tv) * cin; t += blockDim.x) m.gw00[t] = czero();
+    for (int t = tid; t < ts * cin; t += blockDim.x) m.w00_s[t] = wget(a.theta, a.off00, ts, cin, t / cin, t % cin);
+    for (int t = tid; t < tv * cin; t += blockDim.x) m.w11_s[t] = wget(a.theta, a.off11, tv, cin, t / cin, t % cin);
+    return m;
+}
+__host__ __device__ inline size_t enc_latent_bwd_smem_cplx(int N, int C, int ts, int tv, int mode) {
+    const int mix = mode == LGAE_LATENT_MIX;
+    const int rows = mix ? 1 : N, cin = mix ? N * C : C;
+    return (size_t)rows * (ts + 4 * tv) + (size_t)2 * (ts + tv) * cin + (size_t)5 * N * C;
+}
+// GLAT_S: the latent-vector gradient of jet b is read from shared memory (Tv*4 interleaved complex) instead of a.g_lat11.
+template <bool GLAT_S>
+__device__ __forceinline__ void enc_latent_bwd_jet(const LatentArgs& a, const EncLatBwdSm& m, int b, const cplx* glat_s) {
     const int tid = threadIdx.x;
     const int N = a.N, C = a.C, ts = a.tau_s, tv = a.tau_v, B = a.B, mode = a.mode;
     const bool mix = mode == LGAE_LATENT_MIX;
-    const int rows = mix ? 1 : N, cin = mix ? N * C : C;
-    cplx* gL00 = reinterpret_cast<cplx*>(smem);       // rows*ts
-    cplx* gL11 = gL00 + rows * ts;                    // rows*tv*4 (canonical after the basis change)
-    cplx* gw00 = gL11 + rows * tv * 4;                // ts*cin
-    cplx* gw11 = gw00 + ts * cin;                     // tv*cin
-    cplx* w00_s = gw11 + tv * cin;                    // ts*cin   latent weights, interleaved
-    cplx* w11_s = w00_s + ts * cin;                   // tv*cin
-    cplx* S_s = w11_s + tv * cin;                     // N*C      this jet's node features
-    cplx* V_s = S_s + N * C;                          // N*C*4
-    for (int t = tid; t < (ts + tv) * cin; t += blockDim.x) gw00[t] = czero();
-    for (int t = tid; t < ts * cin; t += blockDim.x) w00_s[t] = wget(a.theta, a.off00, ts, cin, t / cin, t % cin);
-    for (int t = tid; t < tv * cin; t += blockDim.x) w11_s[t] = wget(a.theta, a.off11, tv, cin, t / cin, t % cin);
+    const int rows = m.rows, cin = m.cin;
+    cplx *gL00 = m.gL00, *gL11 = m.gL11, *gw00 = m.gw00, *gw11 = m.gw11, *w00_s = m.w00_s, *w11_s = m.w11_s, *S_s = m.S_s, *V_s = m.V_s;
     const bool both = mode == LGAE_LATENT_MINMAX;
     const int Ts = both ? 2 * ts : ts, Tv = both ? 2 * tv : tv;
     const int tmax = ts > tv ? ts : tv;
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const bool have11 = GLAT_S || a.g_lat11;
+    auto g11 = [&](int part, int width, int r) -> double {   // element r of the (width) latent-vector gradient, part re/im
+        if (GLAT_S) return part ? glat_s[r].y : glat_s[r].x;
+        return a.g_lat11[(int64_t)(part * B + b) * width + r];
+    };
+    {
         __syncthreads();
         for (int t = tid; t < rows * (ts + 4 * tv); t += blockDim.x) gL00[t] = czero();
         {   // node features of the jet -> shared memory (16-byte vector loads, all in flight)
@@ -260,7 +288,7 @@ __global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a)
             }
             for (int it = tid; it < rows * tv * 4; it += blockDim.x) {
                 const int r = it % (tv * 4);
-                if (a.g_lat11) gL11[it] = cmake(a.g_lat11[(int64_t)(0 * B + b) * tv * 4 + r] * scale, a.g_lat11[(int64_t)(1 * B + b) * tv * 4 + r] * scale);
+                if (have11) gL11[it] = cmake(g11(0, tv * 4, r) * scale, g11(1, tv * 4, r) * scale);
             }
         } else {
             // scatter: one thread per (tau) handles its 2 kinds x 2 parts sequentially => no write conflicts
@@ -277,14 +305,14 @@ __global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a)
                 }
             }
             for (int t = tid; t < tv; t += blockDim.x) {
-                if (!a.g_lat11) break;
+                if (!have11) break;
                 for (int kind = 0; kind < 2; ++kind) {
                     if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
                     const int T = (both && kind) ? tv + t : t;
                     for (int part = 0; part < 2; ++part) {
                         const int i = a.sel[((int64_t)((2 + kind) * 2 + part) * B + b) * tmax + t];
                         for (int mu = 0; mu < 4; ++mu) {
-                            const double gv = a.g_lat11[((int64_t)(part * B + b) * Tv + T) * 4 + mu];
+                            const double gv = g11(part, Tv * 4, T * 4 + mu);
                             if (part) gL11[(i * tv + t) * 4 + mu].y += gv; else gL11[(i * tv + t) * 4 + mu].x += gv;
                         }
                     }
@@ -334,10 +362,21 @@ __global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a)
             gw11[it] = cadd(gw11[it], acc);
         }
     }
-    __syncthreads();
+}
+__device__ __forceinline__ void enc_latent_bwd_flush(const LatentArgs& a, const EncLatBwdSm& m) {
+    const int tid = threadIdx.x, ts = a.tau_s, tv = a.tau_v, cin = m.cin;
     double* part = a.partials + (int64_t)blockIdx.x * a.part_stride;
-    for (int it = tid; it < ts * cin; it += blockDim.x) pput(part, a.po00, ts, cin, it / cin, it % cin, gw00[it]);
-    for (int it = tid; it < tv * cin; it += blockDim.x) pput(part, a.po11, tv, cin, it / cin, it % cin, gw11[it]);
+    for (int it = tid; it < ts * cin; it += blockDim.x) pput(part, a.po00, ts, cin, it / cin, it % cin, m.gw00[it]);
+    for (int it = tid; it < tv * cin; it += blockDim.x) pput(part, a.po11, tv, cin, it / cin, it % cin, m.gw11[it]);
+}
+__global__ void __launch_bounds__(256) enc_latent_bwd_kernel(const LatentArgs a) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(128) double smem[];
+    const EncLatBwdSm m = enc_latent_bwd_init(a, smem);
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) enc_latent_bwd_jet<false>(a, m, b, nullptr);
+    __syncthreads();
+    enc_latent_bwd_flush(a, m);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -406,17 +445,23 @@ __global__ void __launch_bounds__(256) latent_bridge_kernel(const LatentArgs a, 
 }
 
 // Persistent over jets, one thread per particle (N <= blockDim.x required).
-__global__ void __launch_bounds__(128) dec_input_bwd_kernel(const DecInArgs a) {
-    pdl_launch();
-    pdl_wait();
-    extern __shared__ __align__(128) double smem[];
+struct DecInBwdSm { cplx *lat, *gP_s, *gwg, *gin; };
+__device__ __forceinline__ DecInBwdSm dec_input_bwd_init(const DecInArgs& a, double* smem) {
+    const int tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau;
+    DecInBwdSm m;
+    m.lat = reinterpret_cast<cplx*>(smem);   // tau*4
+    m.gP_s = m.lat + tau * 4;                // N*4
+    m.gwg = m.gP_s + N * 4;                  // N*tau   accumulators
+    m.gin = m.gwg + N * tau;                 // 2*C     accumulators (in00, in11)
+    for (int t = tid; t < N * tau + 2 * C; t += blockDim.x) m.gwg[t] = czero();
+    return m;
+}
+__host__ __device__ inline size_t dec_input_bwd_smem_cplx(int N, int C, int tau) { return (size_t)tau * 4 + (size_t)N * 4 + (size_t)N * tau + 2 * C; }
+// glat_s (optional): also leaves the latent gradient of jet b in shared memory, tau*4 interleaved complex.
+__device__ __forceinline__ void dec_input_bwd_jet(const DecInArgs& a, const DecInBwdSm& m, int b, cplx* glat_s) {
     const int tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau, B = a.B;
-    cplx* lat = reinterpret_cast<cplx*>(smem);   // tau*4
-    cplx* gP_s = lat + tau * 4;                  // N*4
-    cplx* gwg = gP_s + N * 4;                    // N*tau   accumulators
-    cplx* gin = gwg + N * tau;                   // 2*C     accumulators (in00, in11)
-    for (int t = tid; t < N * tau + 2 * C; t += blockDim.x) gwg[t] = czero();
-    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    cplx *lat = m.lat, *gP_s = m.gP_s, *gwg = m.gwg, *gin = m.gin;
+    {
         __syncthreads();
         for (int t = tid; t < tau * 4; t += blockDim.x)
             lat[t] = cmake(a.lat11[(int64_t)(0 * B + b) * tau * 4 + t], a.lat11[(int64_t)(1 * B + b) * tau * 4 + t]);
@@ -472,15 +517,44 @@ __global__ void __launch_bounds__(128) dec_input_bwd_kernel(const DecInArgs a) {
             for (int i = 0; i < N; ++i) cfmac(acc, wget(a.theta, a.off_g11, N, tau, i, t), gP_s[i * 4 + mu]);
             a.g_lat11[(int64_t)(0 * B + b) * tau * 4 + it] = acc.x;
             a.g_lat11[(int64_t)(1 * B + b) * tau * 4 + it] = acc.y;
+            if (glat_s) glat_s[it] = acc;
         }
     }
-    __syncthreads();
+}
+__device__ __forceinline__ void dec_input_bwd_flush(const DecInArgs& a, const DecInBwdSm& m) {
+    const int tid = threadIdx.x, N = a.N, C = a.C, tau = a.tau;
     double* part = a.partials + (int64_t)blockIdx.x * a.part_stride;
-    for (int it = tid; it < N * tau; it += blockDim.x) pput(part, a.po_g11, N, tau, it / tau, it % tau, gwg[it]);
+    for (int it = tid; it < N * tau; it += blockDim.x) pput(part, a.po_g11, N, tau, it / tau, it % tau, m.gwg[it]);
     for (int c = tid; c < C; c += blockDim.x) {
-        pput(part, a.po_in00, C, 1, c, 0, gin[c]);
-        pput(part, a.po_in11, C, 1, c, 0, gin[C + c]);
+        pput(part, a.po_in00, C, 1, c, 0, m.gin[c]);
+        pput(part, a.po_in11, C, 1, c, 0, m.gin[C + c]);
     }
+}
+__global__ void __launch_bounds__(128) dec_input_bwd_kernel(const DecInArgs a) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(128) double smem[];
+    const DecInBwdSm m = dec_input_bwd_init(a, smem);
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) dec_input_bwd_jet(a, m, b, nullptr);
+    __syncthreads();
+    dec_input_bwd_flush(a, m);
+}
+// Training step: decoder-input adjoint and encoder-latent adjoint of the same jets in one kernel; the latent gradient
+// goes from one to the other through shared memory (and is still written to g_lat11 for the caller).
+__global__ void __launch_bounds__(256) latent_bridge_bwd_kernel(const DecInArgs d, const LatentArgs a, int off_enc, int off_glat) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(128) double smem[];
+    const DecInBwdSm md = dec_input_bwd_init(d, smem);
+    const EncLatBwdSm me = enc_latent_bwd_init(a, smem + off_enc);
+    cplx* glat_s = reinterpret_cast<cplx*>(smem + off_glat);
+    for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+        dec_input_bwd_jet(d, md, b, glat_s);
+        enc_latent_bwd_jet<true>(a, me, b, glat_s);   // starts with a barrier: glat_s is complete
+    }
+    __syncthreads();
+    dec_input_bwd_flush(d, md);
+    enc_latent_bwd_flush(a, me);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -804,11 +878,7 @@ __global__ void __launch_bounds__(1024) sum_kernel(const double* v, int64_t n, d
     if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.0) + scale * s;
 }
 
-__global__ void __launch_bounds__(128) normalize_kernel(const double* p4, int N, double* out, double* factor) {
-    pdl_launch();
-    pdl_wait();
-    __shared__ double scratch[32];
-    const int b = blockIdx.x;
+__device__ __forceinline__ void normalize_jet(const double* p4, int N, double* out, double* factor, int b, double* scratch) {
     double m = 0.0;
     for (int k = threadIdx.x; k < 4 * N; k += blockDim.x) m = fmax(m, fabs(p4[(int64_t)b * N * 4 + k]));
     // block max via the sum helper's scratch
@@ -820,6 +890,23 @@ __global__ void __launch_bounds__(128) normalize_kernel(const double* p4, int N,
     f = f + 1e-16;
     if (threadIdx.x == 0 && factor) factor[b] = f;
     for (int k = threadIdx.x; k < 4 * N; k += blockDim.x) out[(int64_t)b * N * 4 + k] = p4[(int64_t)b * N * 4 + k] / f;
+}
+__global__ void __launch_bounds__(128) normalize_kernel(const double* p4, int N, double* out, double* factor) {
+    pdl_launch();
+    pdl_wait();
+    __shared__ double scratch[32];
+    normalize_jet(p4, N, out, factor, blockIdx.x, scratch);
+}
+// Training step: normalisation and the encoder's input map of one jet per CTA (the normalised momenta are re-read by the
+// CTA that wrote them, after a barrier).
+__global__ void __launch_bounds__(128) norm_input_kernel(const double* p4, int N, double* out, double* factor, const double* theta,
+                                                         int64_t off00, int64_t off11, int C, double* mass, double* S, double* V) {
+    pdl_launch();
+    pdl_wait();
+    __shared__ double scratch[32];
+    normalize_jet(p4, N, out, factor, blockIdx.x, scratch);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) enc_input_node(theta, off00, off11, out, (int64_t)blockIdx.x * N + i, C, mass, S, V);
 }
 
 // Single block: the parameter vector has ~3e4..3e5 entries.  out[0] += lambda * sum|theta| ; gtheta += lambda * sign(theta).
@@ -1045,6 +1132,47 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
     launch_k(dec_input_bwd_kernel, dim3(grid), dim3(128), bytes, st, a);
     return check_launch("dec_input_bwd");
 }
+// dec_input_bwd + enc_latent_bwd fused (training step).  g_lat11 is still written (API output).
+int run_latent_bridge_bwd(const LgaeModelDesc* dd, const double* theta_d, const LgaeModelDesc* de, const double* theta_e, int B,
+                          const double* lat11, double* y, const double* gS_d, const double* gV_d, const double* gy, double* g_lat11,
+                          const double* S, const double* V, const int32_t* sel, double* gS_e, double* gV_e, PartPlan* plan,
+                          int64_t theta_base_d, int64_t theta_base_e, cudaStream_t st) {
+    PartPlan* plan_d = plan;
+    PartPlan* plan_e = plan;
+    DecInArgs di = dec_in_args(dd, theta_d, B, lat11, y, nullptr, nullptr);
+    di.gS = gS_d; di.gV = gV_d; di.gy = gy; di.g_lat11 = g_lat11;
+    if (di.N > 128) return LGAE_E_UNSUPPORTED;
+    LatentArgs a = latent_args(de, theta_e, B, S, V);
+    a.sel = const_cast<int32_t*>(sel); a.g_lat00 = nullptr; a.g_lat11 = nullptr; a.gS = gS_e; a.gV = gV_e;
+    const int mult = a.mode == LGAE_LATENT_MINMAX ? 2 : 1;
+    if (di.tau != mult * a.tau_v || di.N != a.N) return LGAE_E_BADARG;
+    const int mix = a.mode == LGAE_LATENT_MIX;
+    const int cin = mix ? a.N * a.C : a.C;
+    const int grid = glue_grid(B);
+    plan->theta_base = theta_base_d;
+    {
+        const int64_t ng = (int64_t)2 * di.N * di.tau, w = ng + 4 * di.C, off = plan_d->block(grid, w);
+        if (int rc = plan_d->seg(di.off_g11, off, w, 0, ng, grid)) return rc;
+        if (int rc = plan_d->seg(di.off_in00, off, w, ng, 2 * di.C, grid)) return rc;
+        if (int rc = plan_d->seg(di.off_in11, off, w, ng + 2 * di.C, 2 * di.C, grid)) return rc;
+        di.partials = plan_d->base + off; di.part_stride = w; di.po_g11 = 0; di.po_in00 = ng; di.po_in11 = ng + 2 * di.C;
+    }
+    plan->theta_base = theta_base_e;
+    {
+        const int64_t n00 = (int64_t)2 * a.tau_s * cin, n11 = (int64_t)2 * a.tau_v * cin, w = n00 + n11, off = plan_e->block(grid, w);
+        if (int rc = plan_e->seg(a.off00, off, w, 0, n00, grid)) return rc;
+        if (int rc = plan_e->seg(a.off11, off, w, n00, n11, grid)) return rc;
+        a.partials = plan_e->base + off; a.part_stride = w; a.po00 = 0; a.po11 = n00;
+    }
+    const size_t cd = (dec_input_bwd_smem_cplx(di.N, di.C, di.tau) + 7) & ~(size_t)7;
+    const size_t ce = (enc_latent_bwd_smem_cplx(a.N, a.C, a.tau_s, a.tau_v, a.mode) + 7) & ~(size_t)7;
+    const size_t bytes = (cd + ce + (size_t)di.tau * 4) * sizeof(cplx);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    if (int rc = ensure_smem((const void*)latent_bridge_bwd_kernel, bytes)) return rc;
+    LaunchScope ls_("latent_bridge_bwd", st);
+    launch_k(latent_bridge_bwd_kernel, dim3(grid), dim3(256), bytes, st, di, a, (int)(2 * cd), (int)(2 * (cd + ce)));
+    return check_launch("latent_bridge_bwd");
+}
 int run_dec_output(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* recon, double* gen00, cudaStream_t st) {
     const int64_t nodes = (int64_t)B * d->n_particles;
     LaunchScope ls_("dec_output", st);
@@ -1152,6 +1280,12 @@ int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, cons
     LaunchScope ls_("dec_tail", st);
     launch_k(dec_tail_kernel, dim3(B), dim3(128), bytes, st, a);
     return check_launch("dec_tail");
+}
+int run_norm_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* out, double* factor, double* mass, double* S,
+                   double* V, cudaStream_t st) {
+    LaunchScope ls_("norm_input", st);
+    launch_k(norm_input_kernel, dim3(B), dim3(128), 0, st, p4, d->n_particles, out, factor, theta, d->off_in00, d->off_in11, d->channels[0], mass, S, V);
+    return check_launch("norm_input");
 }
 int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st) {
     LaunchScope ls_("normalize_p4", st);
