@@ -184,6 +184,49 @@ int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta
                       const double* wpack, const double* acts, const double* g_y, double* g_x, double* gtheta,
                       double* partials, void* stream);
 
+/* ---- layer-level API of the reference, any maxdim --------------------------------------------------------------
+ * Clebsch-Gordan product of ONE pair of irreps (k1,n1) x (k2,n2), channel-wise (replaces cg_product /
+ * complex_kron_product, lgn/cg_lib/cg_ops.py:135-298, called by CGProduct.forward, cg_ops.py:113-132).
+ * z1 (2, rows1, C, d1), z2: planar complex like every GVec part.
+ *   n_nbr == 0: point-wise, z2 (2, rows, C, d2), out_o (2, rows, c_total_o, d_o);
+ *   n_nbr == N: aggregated, rows = B*N, z1 (2,B,N,C,d1) indexed by the neighbour j, z2 (2,B,N,N,C,d2) indexed (i,j),
+ *               out_o[i] = sum_j H_o (z1_j (x) z2_ij)  (cg_ops.py:265-291).
+ * The pair writes channels [c_offset, c_offset + C) of every output irrep o (the reference concatenates the pairs'
+ * results on the channel axis, cg_ops.py:210-215), so the caller passes the final concatenated tensors.
+ * The non-zero CG coefficients H_o[m, a*d2+d] are a term list on the device, given in three orders:
+ *   tab  int32: [order 0: by output component | order 1: by a | order 2: by d][n_terms][3] = (component, a, d),
+ *               then comp_start[n_comp+1], a_start[d1+1], d_start[d2+1] (first term of every group, per order);
+ *   coef fp64:  [3][n_terms] in the same orders.
+ * `component` counts over the output irreps of the pair (out_comp0[o] + m). */
+#define LGAE_CG_MAX_OUT 16
+typedef struct LgaeCgPairDesc {
+    int32_t d1, d2;      /* (k1+1)(n1+1), (k2+1)(n2+1) */
+    int32_t channels;    /* C, equal in both operands */
+    int32_t n_out;       /* output irreps of this pair */
+    int32_t n_comp;      /* sum of their dimensions */
+    int32_t n_terms;     /* non-zero CG coefficients */
+    int32_t out_d[LGAE_CG_MAX_OUT];
+    int32_t out_comp0[LGAE_CG_MAX_OUT];
+    int32_t out_ctotal[LGAE_CG_MAX_OUT];
+    int32_t out_coffset[LGAE_CG_MAX_OUT];
+} LgaeCgPairDesc;
+int lgae_cg_product_forward(const LgaeCgPairDesc* d, const int32_t* tab, const double* coef, const double* z1,
+                            const double* z2, int64_t rows, int32_t n_nbr, double* const* outs, void* stream);
+/* Adjoint (autograd of the above).  g_outs: gradients of the concatenated outputs; g_z1 / g_z2 may be NULL;
+ * accumulate_*: add to the buffer instead of overwriting it (several pairs share an operand). */
+int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const double* coef, const double* z1,
+                             const double* z2, int64_t rows, int32_t n_nbr, const double* const* g_outs, double* g_z1,
+                             double* g_z2, int32_t accumulate_z1, int32_t accumulate_z2, void* stream);
+/* Per-irrep complex channel mixing out[r, co, m] = sum_ci W[co, ci] x[r, ci, m] (replaces mix_zweight_zvec /
+ * mix_zweight_zscalar, lgn/g_lib/cplx_lib.py:7-25, called by MixReps.forward, lgn/nn/g_nn.py:95-121).
+ * w (2, c_out, c_in), x (2, rows, c_in, d), out (2, rows, c_out, d).  The adjoint needs
+ * lgae_mix_partials_doubles(rows, c_in, c_out) doubles of scratch when g_w is requested. */
+int64_t lgae_mix_partials_doubles(int64_t rows, int32_t c_in, int32_t c_out);
+int lgae_mix_forward(const double* w, const double* x, int64_t rows, int32_t c_in, int32_t c_out, int32_t d, double* out,
+                     void* stream);
+int lgae_mix_backward(const double* w, const double* x, const double* g_out, int64_t rows, int32_t c_in, int32_t c_out,
+                      int32_t d, double* g_x, double* g_w, double* partials, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

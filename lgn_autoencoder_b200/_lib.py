@@ -52,8 +52,27 @@ class LgaeModelDesc(C.Structure):
     ]
 
 
+CG_MAX_OUT = 16
+
+
+class LgaeCgPairDesc(C.Structure):
+    _fields_ = [
+        ("d1", C.c_int32),
+        ("d2", C.c_int32),
+        ("channels", C.c_int32),
+        ("n_out", C.c_int32),
+        ("n_comp", C.c_int32),
+        ("n_terms", C.c_int32),
+        ("out_d", C.c_int32 * CG_MAX_OUT),
+        ("out_comp0", C.c_int32 * CG_MAX_OUT),
+        ("out_ctotal", C.c_int32 * CG_MAX_OUT),
+        ("out_coffset", C.c_int32 * CG_MAX_OUT),
+    ]
+
+
 _P = C.c_void_p
 _D = C.POINTER(LgaeModelDesc)
+_CG = C.POINTER(LgaeCgPairDesc)
 
 _PROTOS = {
     "lgae_version": (C.c_int, []),
@@ -81,6 +100,11 @@ _PROTOS = {
     "lgae_mlp_pack_doubles": (C.c_int64, [_D, C.c_int32]),
     "lgae_mlp_forward": (C.c_int, [_D, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "lgae_mlp_backward": (C.c_int, [_D, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
+    "lgae_cg_product_forward": (C.c_int, [_CG, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "lgae_cg_product_backward": (C.c_int, [_CG, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "lgae_mix_partials_doubles": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "lgae_mix_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "lgae_mix_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

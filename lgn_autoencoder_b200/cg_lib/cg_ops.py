@@ -1,10 +1,11 @@
 """Clebsch-Gordan products of GVecs (reference: lgn/cg_lib/cg_ops.py:10-298, cg_ops_tau.py:6-44).
 
-This is the generic, layer-level composite (complex einsum on device tensors) that serves stand-alone calls and
-configurations outside the fused path (maxdim 3, 'mix' pooling).  The training hot path of the LGAE never comes
-here: at maxdim 2 the whole level is one hand-written kernel (csrc/lgae_level.cu)."""
+Layer-level API for stand-alone calls and for configurations outside the fused path (maxdim 3, 'mix' pooling):
+the product of every (irrep, irrep) pair is one launch of the generic term-list kernels in csrc/lgae_cg.cu.  The
+training hot path of the LGAE at maxdim 2 never comes here: there the whole level is one kernel (csrc/lgae_level.cu)."""
 import torch
 
+from .. import layer_ops
 from ..g_lib import GTau, GVec
 from .cg_module import CGModule
 
@@ -27,45 +28,20 @@ def cg_product_tau(tau1, tau2, maxdim=float("inf")):
     return GTau(tau)
 
 
-def _c(x):
-    return torch.complex(x[0], x[1])
-
-
 def cg_product(cg_dict, rep1, rep2, maxdim=float("inf"), aggregate=False, ignore_check=False):
     """out[(k,n)][c] = H_(k,n) . vec(z1[c] (x) z2[c]); results for the same output irrep are concatenated on the
     channel axis in loop order (rep1 outer, rep2 inner).  With aggregate=True one operand carries an extra
-    neighbour axis (2,B,N,N,C,d) and the product is summed over it: out_i = sum_j H (node_j (x) edge_ij)."""
+    neighbour axis (2,B,N,N,C,d) and the product is summed over it: out_i = sum_j H (node_j (x) edge_ij).
+
+    Runs on the term-list kernels of csrc/lgae_cg.cu (forward and adjoint); the Kronecker product the reference
+    materialises (cg_ops.py:221-298) never exists."""
     if not ignore_check and cg_dict.maxdim is not None and maxdim < float("inf") and cg_dict.maxdim < maxdim:
         raise ValueError(f"CG dictionary maxdim ({cg_dict.maxdim}) is smaller than the requested maxdim ({maxdim})")
     keys1, keys2 = list(rep1.keys()), list(rep2.keys())
     top = max(max(k for k, _ in keys1) + max(k for k, _ in keys2), max(n for _, n in keys1) + max(n for _, n in keys2)) + 1
     max_dim = int(min(top, maxdim))
-    out = {}
-    for (k1, n1) in keys1:
-        z1 = _c(rep1[(k1, n1)])
-        for (k2, n2) in keys2:
-            if max(k1, n1, k2, n2) > max_dim - 1:
-                continue
-            z2 = _c(rep2[(k2, n2)])
-            d1, d2 = z1.shape[-1], z2.shape[-1]
-            if aggregate:
-                if z2.dim() == z1.dim() + 1:          # node (B,N,C,d1) x edge (B,N,N,C,d2)
-                    prod = torch.einsum("bjca,bijcd->bicad", z1, z2)
-                elif z1.dim() == z2.dim() + 1:
-                    prod = torch.einsum("bijca,bjcd->bicad", z1, z2)
-                else:
-                    raise ValueError(f"Batch size error! {tuple(z1.shape)} {tuple(z2.shape)}")
-            else:
-                if z1.shape[:-1] != z2.shape[:-1]:
-                    raise ValueError(f"shape mismatch {tuple(z1.shape)} vs {tuple(z2.shape)}")
-                prod = z1.unsqueeze(-1) * z2.unsqueeze(-2)
-            prod = prod.reshape(prod.shape[:-2] + (d1 * d2,))
-            for k in range(abs(k1 - k2), min(max_dim, k1 + k2 + 1), 2):
-                for n in range(abs(n1 - n2), min(max_dim, n1 + n2 + 1), 2):
-                    h = cg_dict[((k1, n1), (k2, n2))][(k, n)].to(prod.real.dtype)
-                    piece = torch.matmul(prod, h.T.to(prod.dtype))
-                    out.setdefault((k, n), []).append(piece)
-    return GVec({key: torch.stack((torch.cat(v, -2).real, torch.cat(v, -2).imag), 0) for key, v in out.items()}, ignore_check=True)
+    out_keys, outs = layer_ops.cg_pairs(cg_dict, keys1, [rep1[k] for k in keys1], keys2, [rep2[k] for k in keys2], max_dim, aggregate)
+    return GVec(dict(zip(out_keys, outs)), ignore_check=True)
 
 
 class CGProduct(CGModule):

@@ -1,0 +1,545 @@
+// Layer-level kernels of the reference's generic API, for any maxdim:
+//   * Clebsch-Gordan product of one (irrep1, irrep2) pair, channel-wise, point-wise or aggregated over the neighbour
+//     axis, forward and adjoint  (lgn/cg_lib/cg_ops.py:135-298: cg_product / complex_kron_product);
+//   * per-irrep complex channel mixing W.x, forward and adjoint  (lgn/nn/g_nn.py:95-121, lgn/g_lib/cplx_lib.py:7-25).
+// The reference materialises the Kronecker product (4,B,N,N,C,d1*d2) and multiplies by the dense CG matrix; here the
+// non-zero CG coefficients are a term list (out component, a, d, coefficient) staged in shared memory, the neighbour sum
+// runs over shared-memory slabs of the jet and nothing of size N*N*d1*d2 is ever written.
+//
+// Tensors are the reference's planar complex layout: (2, ..., C, d) with the leading index re/im.
+#include <algorithm>
+
+#include "lgae_common.cuh"
+
+namespace lgae {
+
+struct CgOut {
+    double* ptr;      // forward: output part; adjoint: its gradient
+    int64_t plane;    // distance re -> im (doubles)
+    int32_t d, comp0, ctot, coff;
+};
+struct CgArgs {
+    const double *z1, *z2;
+    double *g1, *g2;
+    int64_t plane1, plane2;
+    int32_t B, N, NJ, C, d1, d2, n_comp, n_terms, n_out, JT, acc1, acc2;
+    const int32_t* tab;   // [3 orderings][n_terms][3] (comp, a, d), then comp_start[n_comp+1], a_start[d1+1], d_start[d2+1]
+    const double* coef;   // [3 orderings][n_terms]
+    CgOut out[LGAE_CG_MAX_OUT];
+};
+
+constexpr int CG_THREADS = 256;
+constexpr int CG_ITEMS = 4;   // work items per thread held in registers
+
+// Term list of one ordering (0: by output component, 1: by a, 2: by d) -> shared memory.
+struct TermsSm {
+    int32_t *comp, *a, *d, *start;
+    double* coef;
+};
+LGAE_DEV int terms_start_len(const CgArgs& p, int ord) { return (ord == 0 ? p.n_comp : ord == 1 ? p.d1 : p.d2) + 1; }
+LGAE_DEV const int32_t* terms_start_src(const CgArgs& p, int ord) {
+    const int32_t* s = p.tab + (int64_t)9 * p.n_terms;
+    if (ord >= 1) s += p.n_comp + 1;
+    if (ord >= 2) s += p.d1 + 1;
+    return s;
+}
+// carve `mem` (8-byte aligned); returns the number of doubles consumed
+LGAE_DEV int terms_load(const CgArgs& p, int ord, double* mem, TermsSm& t) {
+    const int n = p.n_terms, ns = terms_start_len(p, ord);
+    t.coef = mem;
+    t.comp = reinterpret_cast<int32_t*>(mem + n);
+    t.a = t.comp + n;
+    t.d = t.a + n;
+    t.start = t.d + n;
+    const int32_t* src = p.tab + (int64_t)ord * 3 * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        t.coef[i] = p.coef[(int64_t)ord * n + i];
+        t.comp[i] = src[3 * i];
+        t.a[i] = src[3 * i + 1];
+        t.d[i] = src[3 * i + 2];
+    }
+    const int32_t* ss = terms_start_src(p, ord);
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) t.start[i] = ss[i];
+    return n + (3 * n + ns + 1) / 2;
+}
+static size_t terms_doubles(int n_terms, int n_start) { return (size_t)n_terms + (size_t)(3 * n_terms + n_start + 1) / 2; }
+
+LGAE_DEV int out_of_comp(const CgArgs& p, int oc) {
+    int o = 0;
+    while (o + 1 < p.n_out && oc >= p.out[o + 1].comp0) ++o;
+    return o;
+}
+LGAE_DEV void stage_planar(cplx* dst, const double* src, int64_t plane, int n) {
+    for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = cmake(src[t], src[plane + t]);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// aggregated product: out_i = sum_j H (z1_j (x) z2_ij);  z1 (2,B,NJ,C,d1), z2 (2,B,N,NJ,C,d2)
+// grid (B, i-split); the neighbour axis is processed in tiles of JT particles held in shared memory.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_fwd_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, d1 = p.d1, d2 = p.d2, NJ = p.NJ, JT = p.JT;
+    cplx* z1s = reinterpret_cast<cplx*>(smem);
+    cplx* z2s = z1s + (size_t)JT * C * d1;
+    TermsSm T;
+    terms_load(p, 0, reinterpret_cast<double*>(z2s + (size_t)JT * C * d2), T);
+    pdl_wait();
+    const int b = blockIdx.x, items = C * p.n_comp;
+    const bool single = JT >= NJ;
+    if (single) stage_planar(z1s, p.z1 + (int64_t)b * NJ * C * d1, p.plane1, NJ * C * d1);
+    for (int i = blockIdx.y; i < p.N; i += gridDim.y) {
+        cplx acc[CG_ITEMS];
+#pragma unroll
+        for (int k = 0; k < CG_ITEMS; ++k) acc[k] = czero();
+        for (int j0 = 0; j0 < NJ; j0 += JT) {
+            const int jt = min(JT, NJ - j0);
+            __syncthreads();
+            if (!single) stage_planar(z1s, p.z1 + ((int64_t)b * NJ + j0) * C * d1, p.plane1, jt * C * d1);
+            stage_planar(z2s, p.z2 + (((int64_t)b * p.N + i) * NJ + j0) * C * d2, p.plane2, jt * C * d2);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < CG_ITEMS; ++k) {
+                const int it = tid + k * CG_THREADS;
+                if (it >= items) break;
+                const int c = it % C, oc = it / C;
+                for (int t = T.start[oc]; t < T.start[oc + 1]; ++t) {
+                    const cplx* x = z1s + c * d1 + T.a[t];
+                    const cplx* y = z2s + c * d2 + T.d[t];
+                    cplx s = czero();
+                    for (int j = 0; j < jt; ++j) cfma(s, x[(size_t)j * C * d1], y[(size_t)j * C * d2]);
+                    cfmar(acc[k], s, T.coef[t]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CG_ITEMS; ++k) {
+            const int it = tid + k * CG_THREADS;
+            if (it >= items) break;
+            const int c = it % C, oc = it / C;
+            const CgOut& o = p.out[out_of_comp(p, oc)];
+            const int64_t idx = (((int64_t)b * p.N + i) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+            o.ptr[idx] = acc[k].x;
+            o.ptr[o.plane + idx] = acc[k].y;
+        }
+    }
+}
+
+// Adjoint.  grid (B, neighbour tiles): the CTA owns the gradient of its z1 tile (registers) and writes the gradient of
+// the z2 entries (i, tile) for every i.  Every sum has a fixed order.
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, d1 = p.d1, d2 = p.d2, NJ = p.NJ, JT = p.JT, nc = p.n_comp;
+    cplx* z1s = reinterpret_cast<cplx*>(smem);
+    cplx* z2s = z1s + (size_t)JT * C * d1;
+    cplx* gs = z2s + (size_t)JT * C * d2;   // C * n_comp
+    double* rest = reinterpret_cast<double*>(gs + (size_t)C * nc);
+    TermsSm Ta, Td;
+    rest += terms_load(p, 1, rest, Ta);
+    terms_load(p, 2, rest, Td);
+    pdl_wait();
+    const int b = blockIdx.x, j0 = blockIdx.y * JT, jt = min(JT, NJ - j0);
+    stage_planar(z1s, p.z1 + ((int64_t)b * NJ + j0) * C * d1, p.plane1, jt * C * d1);
+    const int items1 = p.g1 ? jt * C * d1 : 0, items2 = p.g2 ? jt * C * d2 : 0;
+    cplx acc[CG_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CG_ITEMS; ++k) acc[k] = czero();
+    for (int i = 0; i < p.N; ++i) {
+        __syncthreads();
+        stage_planar(z2s, p.z2 + (((int64_t)b * p.N + i) * NJ + j0) * C * d2, p.plane2, jt * C * d2);
+        for (int t = tid; t < C * nc; t += blockDim.x) {
+            const int c = t / nc, oc = t % nc;
+            const CgOut& o = p.out[out_of_comp(p, oc)];
+            const int64_t idx = (((int64_t)b * p.N + i) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+            gs[t] = cmake(o.ptr[idx], o.ptr[o.plane + idx]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < CG_ITEMS; ++k) {
+            const int it = tid + k * CG_THREADS;
+            if (it >= items1) break;
+            const int a_ = it % d1, c = (it / d1) % C, j = it / (d1 * C);
+            cplx s = czero();
+            for (int t = Ta.start[a_]; t < Ta.start[a_ + 1]; ++t) {
+                cplx v = czero();
+                cfmac(v, z2s[((size_t)j * C + c) * d2 + Ta.d[t]], gs[c * nc + Ta.comp[t]]);
+                cfmar(s, v, Ta.coef[t]);
+            }
+            acc[k] = cadd(acc[k], s);
+        }
+        for (int it = tid; it < items2; it += blockDim.x) {
+            const int d_ = it % d2, c = (it / d2) % C, j = it / (d2 * C);
+            cplx s = czero();
+            for (int t = Td.start[d_]; t < Td.start[d_ + 1]; ++t) {
+                cplx v = czero();
+                cfmac(v, z1s[((size_t)j * C + c) * d1 + Td.a[t]], gs[c * nc + Td.comp[t]]);
+                cfmar(s, v, Td.coef[t]);
+            }
+            const int64_t idx = (((int64_t)b * p.N + i) * NJ + j0) * C * d2 + it;
+            if (p.acc2) {
+                p.g2[idx] += s.x;
+                p.g2[p.plane2 + idx] += s.y;
+            } else {
+                p.g2[idx] = s.x;
+                p.g2[p.plane2 + idx] = s.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CG_ITEMS; ++k) {
+        const int it = tid + k * CG_THREADS;
+        if (it >= items1) break;
+        const int64_t idx = ((int64_t)b * NJ + j0) * C * d1 + it;
+        if (p.acc1) {
+            p.g1[idx] += acc[k].x;
+            p.g1[p.plane1 + idx] += acc[k].y;
+        } else {
+            p.g1[idx] = acc[k].x;
+            p.g1[p.plane1 + idx] = acc[k].y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// point-wise product: out_r = H (z1_r (x) z2_r), rows r = 0..B-1 (p.B = number of rows, p.N = 1, p.NJ = 0)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CG_THREADS) cg_pt_fwd_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    TermsSm T;
+    terms_load(p, 0, smem, T);
+    pdl_wait();
+    __syncthreads();
+    const int C = p.C, d1 = p.d1, d2 = p.d2;
+    const int64_t per_row = (int64_t)C * p.n_comp, total = (int64_t)p.B * per_row;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = it / per_row;
+        const int w = (int)(it % per_row), c = w % C, oc = w / C;
+        const double* x = p.z1 + (r * C + c) * d1;
+        const double* y = p.z2 + (r * C + c) * d2;
+        cplx acc = czero();
+        for (int t = T.start[oc]; t < T.start[oc + 1]; ++t) {
+            const int a_ = T.a[t], d_ = T.d[t];
+            cfmar(acc, cmul(cmake(x[a_], x[p.plane1 + a_]), cmake(y[d_], y[p.plane2 + d_])), T.coef[t]);
+        }
+        const CgOut& o = p.out[out_of_comp(p, oc)];
+        const int64_t idx = (r * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+        o.ptr[idx] = acc.x;
+        o.ptr[o.plane + idx] = acc.y;
+    }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) cg_pt_bwd_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    TermsSm Ta, Td;
+    double* rest = smem;
+    rest += terms_load(p, 1, rest, Ta);
+    terms_load(p, 2, rest, Td);
+    pdl_wait();
+    __syncthreads();
+    const int C = p.C, d1 = p.d1, d2 = p.d2;
+    const int64_t n1 = p.g1 ? (int64_t)p.B * C * d1 : 0, n2 = p.g2 ? (int64_t)p.B * C * d2 : 0;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n1 + n2; it += (int64_t)gridDim.x * blockDim.x) {
+        const bool first = it < n1;
+        const int64_t e = first ? it : it - n1;
+        const int dd = first ? d1 : d2, od = first ? d2 : d1;
+        const int q = (int)(e % dd), c = (int)((e / dd) % C);
+        const int64_t r = e / ((int64_t)dd * C);
+        const TermsSm& T = first ? Ta : Td;
+        const double* other = (first ? p.z2 : p.z1) + (r * C + c) * od;
+        const int64_t oplane = first ? p.plane2 : p.plane1;
+        cplx s = czero();
+        for (int t = T.start[q]; t < T.start[q + 1]; ++t) {
+            const int oc = T.comp[t], k = first ? T.d[t] : T.a[t];
+            const CgOut& o = p.out[out_of_comp(p, oc)];
+            const int64_t idx = (r * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+            cplx v = czero();
+            cfmac(v, cmake(other[k], other[oplane + k]), cmake(o.ptr[idx], o.ptr[o.plane + idx]));
+            cfmar(s, v, T.coef[t]);
+        }
+        double* g = first ? p.g1 : p.g2;
+        const int64_t gplane = first ? p.plane1 : p.plane2;
+        if (first ? p.acc1 : p.acc2) {
+            g[e] += s.x;
+            g[gplane + e] += s.y;
+        } else {
+            g[e] = s.x;
+            g[gplane + e] = s.y;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// channel mixing  out[r, co, m] = sum_ci W[co, ci] x[r, ci, m]      x (2,R,Cin,d), W (2,Cout,Cin), out (2,R,Cout,d)
+// ------------------------------------------------------------------------------------------------------------
+struct MixArgs {
+    const double *x, *w, *g;
+    double *out, *gx, *gw_part;
+    int64_t R;
+    int32_t cin, cout, d, rows_per_cta;
+};
+constexpr int MIX_THREADS = 256;
+
+LGAE_DEV void mix_stage_w(const MixArgs& a, cplx* ws) {
+    const int n = a.cout * a.cin;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) ws[t] = cmake(a.w[t], a.w[n + t]);
+}
+__global__ void __launch_bounds__(MIX_THREADS) mix_fwd_kernel(const MixArgs a) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    cplx* ws = reinterpret_cast<cplx*>(smem);
+    mix_stage_w(a, ws);
+    pdl_wait();
+    __syncthreads();
+    const int64_t per_row = (int64_t)a.cout * a.d, total = a.R * per_row, xplane = a.R * a.cin * a.d;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = it / per_row;
+        const int w = (int)(it % per_row), m = w % a.d, co = w / a.d;
+        const double* x = a.x + r * a.cin * a.d + m;
+        cplx acc = czero();
+        for (int ci = 0; ci < a.cin; ++ci) cfma(acc, ws[co * a.cin + ci], cmake(x[(int64_t)ci * a.d], x[xplane + (int64_t)ci * a.d]));
+        a.out[it] = acc.x;
+        a.out[total + it] = acc.y;
+    }
+}
+// gx[r, ci, m] = sum_co conj(W[co, ci]) g[r, co, m]
+__global__ void __launch_bounds__(MIX_THREADS) mix_bwd_x_kernel(const MixArgs a) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    cplx* ws = reinterpret_cast<cplx*>(smem);
+    mix_stage_w(a, ws);
+    pdl_wait();
+    __syncthreads();
+    const int64_t per_row = (int64_t)a.cin * a.d, total = a.R * per_row, gplane = a.R * a.cout * a.d;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = it / per_row;
+        const int w = (int)(it % per_row), m = w % a.d, ci = w / a.d;
+        const double* g = a.g + r * a.cout * a.d + m;
+        cplx acc = czero();
+        for (int co = 0; co < a.cout; ++co) cfmac(acc, ws[co * a.cin + ci], cmake(g[(int64_t)co * a.d], g[gplane + (int64_t)co * a.d]));
+        a.gx[it] = acc.x;
+        a.gx[total + it] = acc.y;
+    }
+}
+// gW[co, ci] = sum_{r, m} conj(x[r, ci, m]) g[r, co, m]: one partial (2, cout*cin) per CTA over its rows, fixed order.
+__global__ void __launch_bounds__(MIX_THREADS) mix_bwd_w_kernel(const MixArgs a) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(16) double smem[];
+    cplx* xs = reinterpret_cast<cplx*>(smem);   // cin*d
+    cplx* gs = xs + (size_t)a.cin * a.d;        // cout*d
+    const int n = a.cout * a.cin;
+    const int64_t xplane = a.R * a.cin * a.d, gplane = a.R * a.cout * a.d;
+    const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta, r1 = min(a.R, r0 + a.rows_per_cta);
+    double* part = a.gw_part + (int64_t)blockIdx.x * 2 * n;
+    for (int base = 0; base < n; base += MIX_THREADS * CG_ITEMS) {
+        cplx acc[CG_ITEMS];
+#pragma unroll
+        for (int k = 0; k < CG_ITEMS; ++k) acc[k] = czero();
+        for (int64_t r = r0; r < r1; ++r) {
+            __syncthreads();
+            stage_planar(xs, a.x + r * a.cin * a.d, xplane, a.cin * a.d);
+            stage_planar(gs, a.g + r * a.cout * a.d, gplane, a.cout * a.d);
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < CG_ITEMS; ++k) {
+                const int it = base + threadIdx.x + k * MIX_THREADS;
+                if (it >= n) break;
+                const int ci = it % a.cin, co = it / a.cin;
+                for (int m = 0; m < a.d; ++m) cfmac(acc[k], xs[ci * a.d + m], gs[co * a.d + m]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CG_ITEMS; ++k) {
+            const int it = base + threadIdx.x + k * MIX_THREADS;
+            if (it >= n) break;
+            part[it] = acc[k].x;
+            part[n + it] = acc[k].y;
+        }
+    }
+}
+// out[t] = sum_rows part[row][t]   (fixed order)
+__global__ void __launch_bounds__(256) colsum_kernel(const double* part, int rows, int64_t n, double* out) {
+    pdl_launch();
+    pdl_wait();
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < rows; ++r) s += part[(int64_t)r * n + t];
+        out[t] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static int grid_for(int64_t work, int threads) {
+    const int64_t need = (work + threads - 1) / threads, cap = (int64_t)sm_count() * 8;
+    return (int)std::max<int64_t>(1, std::min(need, cap));
+}
+static int cg_fill(const LgaeCgPairDesc* d, const int32_t* tab, const double* coef, CgArgs& p, void* const* ptrs, int64_t rows) {
+    if (!d || !tab || !coef || !ptrs) return LGAE_E_BADARG;
+    if (d->d1 < 1 || d->d2 < 1 || d->channels < 1 || d->n_out < 1 || d->n_out > LGAE_CG_MAX_OUT || d->n_terms < 1 || d->n_comp < 1)
+        return LGAE_E_BADARG;
+    p.C = d->channels; p.d1 = d->d1; p.d2 = d->d2; p.n_comp = d->n_comp; p.n_terms = d->n_terms; p.n_out = d->n_out;
+    p.tab = tab; p.coef = coef;
+    int comp = 0;
+    for (int o = 0; o < d->n_out; ++o) {
+        if (!ptrs[o] || d->out_comp0[o] != comp || d->out_d[o] < 1 || d->out_coffset[o] < 0 || d->out_coffset[o] + d->channels > d->out_ctotal[o])
+            return LGAE_E_BADARG;
+        p.out[o].ptr = (double*)ptrs[o];
+        p.out[o].d = d->out_d[o]; p.out[o].comp0 = comp; p.out[o].ctot = d->out_ctotal[o]; p.out[o].coff = d->out_coffset[o];
+        p.out[o].plane = rows * d->out_ctotal[o] * d->out_d[o];
+        comp += d->out_d[o];
+    }
+    if (comp != d->n_comp) return LGAE_E_BADARG;
+    return LGAE_OK;
+}
+// neighbour tile: as many particles as fit next to the fixed part in ~160 KB, and (adjoint) CG_ITEMS*CG_THREADS z1 items
+static int cg_tile(const CgArgs& p, size_t fixed_bytes, bool bwd) {
+    const size_t per_j = (size_t)p.C * (p.d1 + p.d2) * sizeof(cplx);
+    const size_t budget = 160 * 1024;
+    if (fixed_bytes + per_j > budget) return 0;
+    int64_t jt = (int64_t)((budget - fixed_bytes) / per_j);
+    if (bwd) jt = std::min<int64_t>(jt, (CG_ITEMS * CG_THREADS) / (p.C * p.d1));
+    return (int)std::min<int64_t>(jt, p.NJ);
+}
+
+}  // namespace lgae
+
+using namespace lgae;
+
+extern "C" {
+
+int lgae_cg_product_forward(const LgaeCgPairDesc* d, const int32_t* tab, const double* coef, const double* z1, const double* z2, int64_t rows,
+                            int32_t n_nbr, double* const* outs, void* stream) {
+    CgArgs p;
+    if (rows < 0 || n_nbr < 0) return LGAE_E_BADARG;
+    if (int rc = cg_fill(d, tab, coef, p, (void* const*)outs, rows)) return rc;
+    if (rows == 0) return LGAE_OK;
+    if (!z1 || !z2) return LGAE_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    p.z1 = z1; p.z2 = z2; p.g1 = p.g2 = nullptr; p.acc1 = p.acc2 = 0;
+    if (n_nbr == 0) {
+        p.B = (int32_t)rows; p.N = 1; p.NJ = 0; p.JT = 0;
+        if (rows > INT32_MAX) return LGAE_E_UNSUPPORTED;
+        p.plane1 = rows * p.C * p.d1; p.plane2 = rows * p.C * p.d2;
+        const size_t bytes = terms_doubles(p.n_terms, p.n_comp + 1) * sizeof(double);
+        if (int rc = ensure_smem((const void*)cg_pt_fwd_kernel, bytes)) return rc;
+        LaunchScope ls_("cg_product_fwd", st);
+        launch_k(cg_pt_fwd_kernel, dim3(grid_for(rows * p.C * p.n_comp, CG_THREADS)), dim3(CG_THREADS), bytes, st, p);
+        return check_launch("cg_product_fwd");
+    }
+    if (rows % n_nbr) return LGAE_E_BADARG;
+    p.B = (int32_t)(rows / n_nbr); p.N = n_nbr; p.NJ = n_nbr;
+    p.plane1 = rows * p.C * p.d1; p.plane2 = rows * n_nbr * p.C * p.d2;
+    if (p.C * p.n_comp > CG_ITEMS * CG_THREADS) return LGAE_E_UNSUPPORTED;
+    const size_t fixed = terms_doubles(p.n_terms, p.n_comp + 1) * sizeof(double);
+    p.JT = cg_tile(p, fixed, false);
+    if (p.JT < 1) return LGAE_E_UNSUPPORTED;
+    const size_t bytes = fixed + (size_t)p.JT * p.C * (p.d1 + p.d2) * sizeof(cplx);
+    if (int rc = ensure_smem((const void*)cg_agg_fwd_kernel, bytes)) return rc;
+    int split = (2 * sm_count() + p.B - 1) / p.B;
+    split = std::max(1, std::min(split, (int)p.N));
+    LaunchScope ls_("cg_aggregate_fwd", st);
+    launch_k(cg_agg_fwd_kernel, dim3(p.B, split), dim3(CG_THREADS), bytes, st, p);
+    return check_launch("cg_aggregate_fwd");
+}
+
+int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const double* coef, const double* z1, const double* z2, int64_t rows,
+                             int32_t n_nbr, const double* const* g_outs, double* g_z1, double* g_z2, int32_t accumulate_z1,
+                             int32_t accumulate_z2, void* stream) {
+    CgArgs p;
+    if (rows < 0 || n_nbr < 0) return LGAE_E_BADARG;
+    if (int rc = cg_fill(d, tab, coef, p, (void* const*)g_outs, rows)) return rc;
+    if (rows == 0 || (!g_z1 && !g_z2)) return LGAE_OK;
+    if (!z1 || !z2) return LGAE_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    p.z1 = z1; p.z2 = z2; p.g1 = g_z1; p.g2 = g_z2; p.acc1 = accumulate_z1; p.acc2 = accumulate_z2;
+    const size_t terms = (terms_doubles(p.n_terms, p.d1 + 1) + terms_doubles(p.n_terms, p.d2 + 1)) * sizeof(double);
+    if (n_nbr == 0) {
+        if (rows > INT32_MAX) return LGAE_E_UNSUPPORTED;
+        p.B = (int32_t)rows; p.N = 1; p.NJ = 0; p.JT = 0;
+        p.plane1 = rows * p.C * p.d1; p.plane2 = rows * p.C * p.d2;
+        if (int rc = ensure_smem((const void*)cg_pt_bwd_kernel, terms)) return rc;
+        LaunchScope ls_("cg_product_bwd", st);
+        launch_k(cg_pt_bwd_kernel, dim3(grid_for(rows * p.C * (p.d1 + p.d2), CG_THREADS)), dim3(CG_THREADS), terms, st, p);
+        return check_launch("cg_product_bwd");
+    }
+    if (rows % n_nbr) return LGAE_E_BADARG;
+    p.B = (int32_t)(rows / n_nbr); p.N = n_nbr; p.NJ = n_nbr;
+    p.plane1 = rows * p.C * p.d1; p.plane2 = rows * n_nbr * p.C * p.d2;
+    if (p.C * p.d1 > CG_ITEMS * CG_THREADS) return LGAE_E_UNSUPPORTED;
+    const size_t fixed = terms + (size_t)p.C * p.n_comp * sizeof(cplx);
+    p.JT = cg_tile(p, fixed, true);
+    if (p.JT < 1) return LGAE_E_UNSUPPORTED;
+    const size_t bytes = fixed + (size_t)p.JT * p.C * (p.d1 + p.d2) * sizeof(cplx);
+    if (int rc = ensure_smem((const void*)cg_agg_bwd_kernel, bytes)) return rc;
+    LaunchScope ls_("cg_aggregate_bwd", st);
+    launch_k(cg_agg_bwd_kernel, dim3(p.B, (p.NJ + p.JT - 1) / p.JT), dim3(CG_THREADS), bytes, st, p);
+    return check_launch("cg_aggregate_bwd");
+}
+
+int64_t lgae_mix_partials_doubles(int64_t rows, int32_t c_in, int32_t c_out) {
+    if (rows < 0 || c_in < 1 || c_out < 1) return -1;
+    const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(rows, 4 * (int64_t)sm_count()));
+    return ctas * 2 * c_in * c_out;
+}
+
+int lgae_mix_forward(const double* w, const double* x, int64_t rows, int32_t c_in, int32_t c_out, int32_t d, double* out, void* stream) {
+    if (rows < 0 || c_in < 1 || c_out < 1 || d < 1) return LGAE_E_BADARG;
+    if (rows == 0) return LGAE_OK;
+    if (!w || !x || !out) return LGAE_E_BADARG;
+    MixArgs a = {};
+    a.x = x; a.w = w; a.out = out; a.R = rows; a.cin = c_in; a.cout = c_out; a.d = d;
+    const size_t bytes = (size_t)c_in * c_out * sizeof(cplx);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = ensure_smem((const void*)mix_fwd_kernel, bytes)) return rc;
+    LaunchScope ls_("mix_fwd", st);
+    launch_k(mix_fwd_kernel, dim3(grid_for(rows * c_out * d, MIX_THREADS)), dim3(MIX_THREADS), bytes, st, a);
+    return check_launch("mix_fwd");
+}
+
+int lgae_mix_backward(const double* w, const double* x, const double* g_out, int64_t rows, int32_t c_in, int32_t c_out, int32_t d, double* g_x,
+                      double* g_w, double* partials, void* stream) {
+    if (rows < 0 || c_in < 1 || c_out < 1 || d < 1) return LGAE_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) {
+        if (g_w && cudaMemsetAsync(g_w, 0, (size_t)2 * c_in * c_out * sizeof(double), st) != cudaSuccess) return check_launch("memset g_w");
+        return LGAE_OK;
+    }
+    if (!w || !x || !g_out || (g_w && !partials)) return LGAE_E_BADARG;
+    MixArgs a = {};
+    a.x = x; a.w = w; a.g = g_out; a.gx = g_x; a.gw_part = partials; a.R = rows; a.cin = c_in; a.cout = c_out; a.d = d;
+    if (g_x) {
+        const size_t bytes = (size_t)c_in * c_out * sizeof(cplx);
+        if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+        if (int rc = ensure_smem((const void*)mix_bwd_x_kernel, bytes)) return rc;
+        LaunchScope ls_("mix_bwd_x", st);
+        launch_k(mix_bwd_x_kernel, dim3(grid_for(rows * c_in * d, MIX_THREADS)), dim3(MIX_THREADS), bytes, st, a);
+        if (int rc = check_launch("mix_bwd_x")) return rc;
+    }
+    if (g_w) {
+        const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(rows, 4 * (int64_t)sm_count()));
+        a.rows_per_cta = (int32_t)((rows + ctas - 1) / ctas);
+        const int grid = (int)((rows + a.rows_per_cta - 1) / a.rows_per_cta);
+        const size_t bytes = (size_t)(c_in + c_out) * d * sizeof(cplx);
+        if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+        if (int rc = ensure_smem((const void*)mix_bwd_w_kernel, bytes)) return rc;
+        {
+            LaunchScope ls_("mix_bwd_w", st);
+            launch_k(mix_bwd_w_kernel, dim3(grid), dim3(MIX_THREADS), bytes, st, a);
+            if (int rc = check_launch("mix_bwd_w")) return rc;
+        }
+        const int64_t n = (int64_t)2 * c_in * c_out;
+        LaunchScope ls_("mix_bwd_w_sum", st);
+        launch_k(colsum_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const double*)partials, grid, n, g_w);
+        return check_launch("mix_bwd_w_sum");
+    }
+    return LGAE_OK;
+}
+
+}  // extern "C"

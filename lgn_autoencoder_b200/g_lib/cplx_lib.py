@@ -12,13 +12,15 @@ def _p(z):
 
 
 def mix_zweight_zvec(weight, part, zdim=0):
-    """(2,C',C) complex weight applied on the channel axis of a (2,...,C,d) part."""
-    return _p(torch.matmul(_c(weight), _c(part)))
+    """(2,C',C) complex weight applied on the channel axis of a (2,...,C,d) part (kernel: csrc/lgae_cg.cu)."""
+    from .. import layer_ops
+    return layer_ops.mix(weight, part)
 
 
 def mix_zweight_zscalar(weight, part, zdim=0):
     """(2,C',C) applied on the channel axis of a (2,...,C) part."""
-    return _p(torch.matmul(_c(weight), _c(part).unsqueeze(-1)).squeeze(-1))
+    from .. import layer_ops
+    return layer_ops.mix(weight, part.unsqueeze(-1)).squeeze(-1)
 
 
 def mul_zscalar_zirrep(scalar, part, zdim=0):

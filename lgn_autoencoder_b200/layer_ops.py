@@ -1,0 +1,248 @@
+"""Layer-level ops of the reference's generic API on the hand-written kernels of csrc/lgae_cg.cu:
+
+* ``cg_pairs`` — Clebsch-Gordan product of GVec parts, channel-wise, point-wise or aggregated over the neighbour axis
+  (reference lgn/cg_lib/cg_ops.py:135-298), any maxdim, with its hand-written adjoint;
+* ``mix``      — per-irrep complex channel mixing (reference lgn/g_lib/cplx_lib.py:7-25) with its adjoint.
+
+Both take and return the reference's planar complex tensors (2, ..., C, d) and are ``torch.autograd.Function``s over the
+C ABI (include/lgae_b200.h).  There is no CPU path: tensors must be fp64 CUDA tensors."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"lgn_autoencoder_b200 {what}: tensors must live on a CUDA device (there is no CPU path)")
+    if t.dtype != torch.float64:
+        raise ValueError(f"lgn_autoencoder_b200 {what}: only torch.float64 is supported (as in the reference), got {t.dtype}")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CG product
+# ------------------------------------------------------------------------------------------------------------
+class PairPlan:
+    """One (irrep1, irrep2) pair of a cg_product call: its output irreps, channel offsets and device term tables."""
+
+    def __init__(self, i1, i2, desc, tab, coef, out_slots, swap):
+        self.i1, self.i2 = i1, i2          # indices of the operand tensors (kernel order: z1 = node side, z2 = edge side)
+        self.desc, self.tab, self.coef = desc, tab, coef
+        self.out_slots = out_slots         # index of every output irrep in the call's output list
+        self.swap = swap
+
+
+def _term_tables(cg_dict, key1, key2, out_keys, swap, device):
+    """Non-zero CG coefficients H_o[m, a*d2+d] of a pair as term lists in three orders (see include/lgae_b200.h)."""
+    cache = cg_dict.__dict__.setdefault("_lgae_term_cache", {})
+    ck = (key1, key2, tuple(out_keys), bool(swap), str(device))
+    if ck in cache:
+        return cache[ck]
+    d2 = (key2[0] + 1) * (key2[1] + 1)
+    terms, comp0 = [], 0
+    for ok in out_keys:
+        h = cg_dict[(key1, key2)][ok].detach().cpu().numpy()
+        for m, idx in zip(*np.nonzero(h)):
+            a, d = divmod(int(idx), d2)
+            if swap:
+                a, d = d, a
+            terms.append((comp0 + int(m), a, d, float(h[m, idx])))
+        comp0 += h.shape[0]
+    d1k = (key1[0] + 1) * (key1[1] + 1)
+    dk1, dk2 = (d2, d1k) if swap else (d1k, d2)     # kernel-side d1, d2
+    n = len(terms)
+    tabs, coefs, starts = [], [], []
+    for col, groups in ((0, comp0), (1, dk1), (2, dk2)):
+        order = sorted(range(n), key=lambda t: (terms[t][col], t))
+        tabs.append([[terms[t][0], terms[t][1], terms[t][2]] for t in order])
+        coefs.append([terms[t][3] for t in order])
+        cnt = np.bincount([terms[t][col] for t in order], minlength=groups)
+        starts.append(np.concatenate(([0], np.cumsum(cnt))))
+    tab = np.concatenate([np.asarray(tabs, dtype=np.int32).reshape(-1)] + [s.astype(np.int32) for s in starts])
+    out = (torch.from_numpy(tab).to(device), torch.tensor(coefs, dtype=torch.float64).reshape(-1).to(device), n, comp0, dk1, dk2)
+    cache[ck] = out
+    return out
+
+
+def plan_pairs(cg_dict, keys1, keys2, chans1, chans2, max_dim, swap, device):
+    """Pairs in the reference's loop order (rep1 outer, rep2 inner, cg_ops.py:176-215) with the channel offset of every
+    result inside the concatenated output irreps.  Returns (pair plans, output keys in first-appearance order,
+    channels per output key)."""
+    out_keys, out_ch, pairs = [], {}, []
+    for i1, key1 in enumerate(keys1):
+        for i2, key2 in enumerate(keys2):
+            (k1, n1), (k2, n2) = key1, key2
+            if max(k1, n1, k2, n2) > max_dim - 1:
+                continue
+            if chans1[i1] != chans2[i2]:
+                raise ValueError(f"The number of fragments must be same for each part! {chans1[i1]} {chans2[i2]}")
+            outs = [(k, n) for k in range(abs(k1 - k2), min(max_dim, k1 + k2 + 1), 2) for n in range(abs(n1 - n2), min(max_dim, n1 + n2 + 1), 2)]
+            if not outs:
+                continue
+            if len(outs) > 16:
+                raise NotImplementedError("more than 16 output irreps per pair")
+            tab, coef, n_terms, n_comp, dk1, dk2 = _term_tables(cg_dict, key1, key2, outs, swap, device)
+            desc = _lib.LgaeCgPairDesc()
+            desc.d1, desc.d2, desc.channels, desc.n_out, desc.n_comp, desc.n_terms = dk1, dk2, chans1[i1], len(outs), n_comp, n_terms
+            comp0, slots = 0, []
+            for o, ok in enumerate(outs):
+                if ok not in out_ch:
+                    out_ch[ok] = 0
+                    out_keys.append(ok)
+                desc.out_d[o] = (ok[0] + 1) * (ok[1] + 1)
+                desc.out_comp0[o] = comp0
+                desc.out_coffset[o] = out_ch[ok]
+                comp0 += desc.out_d[o]
+                out_ch[ok] += chans1[i1]
+                slots.append(out_keys.index(ok))
+            pairs.append(PairPlan(i1, i2, desc, tab, coef, slots, swap))
+    for p in pairs:
+        for o, s in enumerate(p.out_slots):
+            p.desc.out_ctotal[o] = out_ch[out_keys[s]]
+    return pairs, out_keys, [out_ch[k] for k in out_keys]
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+class _CGPairsFn(torch.autograd.Function):
+    """All pairs of one cg_product call.  Inputs: the n1 parts of rep1 then the n2 parts of rep2."""
+
+    @staticmethod
+    def forward(ctx, pairs, out_keys, out_ch, n1, n_nbr, swap, *parts):
+        lib = _lib.load()
+        parts = [p.contiguous() for p in parts]
+        for p in parts:
+            _require_cuda(p, "cg_product")
+        # the side without the neighbour axis fixes the output batch shape
+        node_parts = parts[n1:] if swap else parts[:n1]
+        batch = tuple(node_parts[0].shape[1:-2])
+        rows = int(np.prod(batch)) if batch else 1
+        outs = [torch.empty((2,) + batch + (c, (k[0] + 1) * (k[1] + 1)), dtype=torch.float64, device=parts[0].device)
+                for k, c in zip(out_keys, out_ch)]
+        st = _stream()
+        for pp in pairs:
+            a, b = parts[pp.i1], parts[n1 + pp.i2]
+            z1, z2 = (b, a) if swap else (a, b)
+            _lib.check(lib.lgae_cg_product_forward(C.byref(pp.desc), pp.tab.data_ptr(), pp.coef.data_ptr(), z1.data_ptr(), z2.data_ptr(),
+                                                   rows, n_nbr, _ptr_array([outs[s] for s in pp.out_slots]), st), "cg_product_forward")
+        ctx.pairs, ctx.n1, ctx.n_nbr, ctx.swap, ctx.rows = pairs, n1, n_nbr, swap, rows
+        ctx.save_for_backward(*parts)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        lib = _lib.load()
+        parts = ctx.saved_tensors
+        n1, swap = ctx.n1, ctx.swap
+        need = ctx.needs_input_grad[6:]
+        g_outs = [g.contiguous() if g is not None else None for g in g_outs]
+        grads = [None] * len(parts)
+        st = _stream()
+        for pp in ctx.pairs:
+            ia, ib = pp.i1, n1 + pp.i2
+            gl = []
+            for o, s in enumerate(pp.out_slots):
+                if g_outs[s] is None:   # an output nobody used: zero gradient
+                    shape = (2,) + tuple(parts[ib if swap else ia].shape[1:-2]) + (pp.desc.out_ctotal[o], pp.desc.out_d[o])
+                    g_outs[s] = torch.zeros(shape, dtype=torch.float64, device=parts[0].device)
+                gl.append(g_outs[s])
+            acc, ptrs = {}, {}
+            for idx in (ia, ib):
+                if need[idx]:
+                    acc[idx] = 1 if grads[idx] is not None else 0
+                    if grads[idx] is None:
+                        grads[idx] = torch.empty_like(parts[idx])
+                    ptrs[idx] = grads[idx].data_ptr()
+                else:
+                    acc[idx], ptrs[idx] = 0, None
+            a, b = parts[ia], parts[ib]
+            (z1, i1), (z2, i2) = ((b, ib), (a, ia)) if swap else ((a, ia), (b, ib))
+            _lib.check(lib.lgae_cg_product_backward(C.byref(pp.desc), pp.tab.data_ptr(), pp.coef.data_ptr(), z1.data_ptr(), z2.data_ptr(),
+                                                    ctx.rows, ctx.n_nbr, _ptr_array(gl), ptrs[i1], ptrs[i2], acc[i1], acc[i2], st),
+                       "cg_product_backward")
+        for idx, p in enumerate(parts):   # parts that met no partner under the maxdim cut
+            if need[idx] and grads[idx] is None:
+                grads[idx] = torch.zeros_like(p)
+        return (None,) * 6 + tuple(grads)
+
+
+def cg_pairs(cg_dict, keys1, parts1, keys2, parts2, max_dim, aggregate):
+    """Returns (output keys, output tensors).  aggregate: one operand has the extra neighbour axis (2,B,N,N,C,d)."""
+    n_nbr, swap = 0, False
+    if aggregate:
+        if parts2[0].dim() == parts1[0].dim() + 1:
+            swap = False
+        elif parts1[0].dim() == parts2[0].dim() + 1:
+            swap = True
+        else:
+            raise ValueError(f"Batch size error! {tuple(parts1[0].shape)} {tuple(parts2[0].shape)}")
+        edge = parts1[0] if swap else parts2[0]
+        node = parts2[0] if swap else parts1[0]
+        if edge.dim() != 6 or tuple(edge.shape[1:4]) != (node.shape[1], node.shape[2], node.shape[2]):
+            raise ValueError(f"Batch size error! {tuple(parts1[0].shape)} {tuple(parts2[0].shape)}")
+        n_nbr = int(node.shape[2])
+    else:
+        for p, q in zip(parts1[:1], parts2[:1]):
+            if p.shape[1:-2] != q.shape[1:-2]:
+                raise ValueError(f"shape mismatch {tuple(p.shape)} vs {tuple(q.shape)}")
+    pairs, out_keys, out_ch = plan_pairs(cg_dict, list(keys1), list(keys2), [int(p.shape[-2]) for p in parts1],
+                                         [int(p.shape[-2]) for p in parts2], max_dim, swap, parts1[0].device)
+    if not pairs:
+        return [], []
+    outs = _CGPairsFn.apply(pairs, out_keys, out_ch, len(parts1), n_nbr, swap, *parts1, *parts2)
+    return out_keys, list(outs)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# channel mixing
+# ------------------------------------------------------------------------------------------------------------
+class _MixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weight, part):
+        lib = _lib.load()
+        _require_cuda(part, "mix")
+        _require_cuda(weight, "mix")
+        w, x = weight.contiguous(), part.contiguous()
+        c_out, c_in = int(w.shape[1]), int(w.shape[2])
+        d = int(x.shape[-1])
+        if x.shape[-2] != c_in:
+            raise ValueError(f"mix: weight {tuple(w.shape)} does not match part {tuple(x.shape)}")
+        rows = int(np.prod(x.shape[1:-2])) if x.dim() > 3 else 1
+        out = torch.empty(tuple(x.shape[:-2]) + (c_out, d), dtype=torch.float64, device=x.device)
+        _lib.check(lib.lgae_mix_forward(w.data_ptr(), x.data_ptr(), rows, c_in, c_out, d, out.data_ptr(), _stream()), "mix_forward")
+        ctx.save_for_backward(w, x)
+        ctx.dims = (rows, c_in, c_out, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        w, x = ctx.saved_tensors
+        rows, c_in, c_out, d = ctx.dims
+        g = g.contiguous()
+        gw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        gx = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+        part = None
+        if gw is not None:
+            part = torch.empty(int(lib.lgae_mix_partials_doubles(rows, c_in, c_out)), dtype=torch.float64, device=x.device)
+        _lib.check(lib.lgae_mix_backward(w.data_ptr(), x.data_ptr(), g.data_ptr(), rows, c_in, c_out, d, _lib.ptr(gx), _lib.ptr(gw),
+                                         _lib.ptr(part), _stream()), "mix_backward")
+        return gw, gx
+
+
+def mix(weight, part):
+    """(2,C',C) complex weight on the channel axis of a (2,...,C,d) part."""
+    if weight.dim() != 3 or weight.shape[0] != 2:
+        raise ValueError(f"mix: expected a complex weight of shape (2, C_out, C_in), got {tuple(weight.shape)}")
+    return _MixFn.apply(weight, part)

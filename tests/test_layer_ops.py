@@ -1,0 +1,141 @@
+"""Layer-level kernels (csrc/lgae_cg.cu) behind CGProduct / cg_product / MixReps: term tables on CPU, and on the GPU
+the product and its adjoint against the oracle's restatement of the reference (cg_ops.py:135-298, cplx_lib.py:7-25)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import rel_err
+
+TOL = 1e-12   # fp64, sums of <= a few hundred products
+
+
+def _cg(maxdim):
+    from lgn_autoencoder_b200.cg_lib import CGDict
+    return CGDict(maxdim=maxdim, transpose=True, dtype=torch.float64, device=torch.device("cpu"))
+
+
+@pytest.mark.parametrize("swap", [False, True])
+def test_term_tables_reproduce_the_cg_matrices(swap):
+    from lgn_autoencoder_b200 import layer_ops
+    cg = _cg(3)
+    irreps = [(0, 0), (1, 1), (0, 2), (2, 0), (2, 2)]
+    for key1 in irreps:
+        for key2 in irreps:
+            outs = [(k, n) for k in range(abs(key1[0] - key2[0]), min(3, key1[0] + key2[0] + 1), 2)
+                    for n in range(abs(key1[1] - key2[1]), min(3, key1[1] + key2[1] + 1), 2)]
+            tab, coef, n, n_comp, dk1, dk2 = layer_ops._term_tables(cg, key1, key2, outs, swap, torch.device("cpu"))
+            d1, d2 = (key1[0] + 1) * (key1[1] + 1), (key2[0] + 1) * (key2[1] + 1)
+            assert (dk1, dk2) == ((d2, d1) if swap else (d1, d2))
+            dense = torch.cat([cg[(key1, key2)][o] for o in outs], 0).numpy()
+            assert n == np.count_nonzero(dense) and n_comp == dense.shape[0]
+            tab, coef = tab.numpy(), coef.numpy().reshape(3, n)
+            trip = tab[:9 * n].reshape(3, n, 3)
+            starts = np.split(tab[9 * n:], [n_comp + 1, n_comp + 1 + dk1 + 1])
+            assert [len(s) for s in starts] == [n_comp + 1, dk1 + 1, dk2 + 1]
+            for order in range(3):
+                rebuilt = np.zeros_like(dense)
+                for (comp, a, d), c in zip(trip[order], coef[order]):
+                    if swap:
+                        a, d = d, a
+                    rebuilt[comp, a * d2 + d] += c
+                assert np.array_equal(rebuilt, dense)
+                col = trip[order][:, order]
+                assert np.all(np.diff(col) >= 0)
+                s = starts[order]
+                assert s[0] == 0 and s[-1] == n
+                for g in range(len(s) - 1):
+                    assert np.all(col[s[g]:s[g + 1]] == g)
+
+
+def _rand_rep(gen, batch, tau, requires_grad=True):
+    rep = {k: torch.randn((2,) + batch + (c, (k[0] + 1) * (k[1] + 1)), generator=gen, dtype=torch.float64) for k, c in tau.items()}
+    return {k: v.requires_grad_(requires_grad) for k, v in rep.items()}
+
+
+def _run_both(rep1, rep2, maxdim, aggregate):
+    """(outputs, input grads) of the oracle on CPU and of the kernels on cuda:0 for the same random cotangent."""
+    from lgn_autoencoder_b200.cg_lib import cg_product
+    from lgn_autoencoder_b200.g_lib import GVec
+    from oracle import lgae_oracle as orc
+    dev = torch.device("cuda:0")
+    cg_o = orc.cg_table(maxdim)
+    ref = orc.cg_product(cg_o, rep1, rep2, maxdim, aggregate)
+    gen = torch.Generator().manual_seed(7)
+    cot = {k: torch.randn(v.shape, generator=gen, dtype=torch.float64) for k, v in ref.items()}
+    leaves = list(rep1.values()) + [v for v in rep2.values() if all(v is not u for u in rep1.values())]
+    g_ref = torch.autograd.grad(sum((ref[k] * cot[k]).sum() for k in ref), leaves, allow_unused=True)
+    d1 = {k: v.detach().to(dev).requires_grad_(True) for k, v in rep1.items()}
+    d2 = d1 if rep2 is rep1 else {k: v.detach().to(dev).requires_grad_(True) for k, v in rep2.items()}
+    out = cg_product(_cg(maxdim).to(device=dev), GVec(d1, ignore_check=True), GVec(d2, ignore_check=True), maxdim=maxdim, aggregate=aggregate)
+    dleaves = list(d1.values()) + ([] if d2 is d1 else list(d2.values()))
+    g_out = torch.autograd.grad(sum((out[k] * cot[k].to(dev)).sum() for k in out.keys()), dleaves, allow_unused=True)
+    return ref, out, g_ref, g_out
+
+
+def _check(ref, out, g_ref, g_out):
+    assert list(out.keys()) == list(ref.keys())          # part order is part of the contract
+    for k in ref:
+        assert rel_err(out[k], ref[k]) < TOL, k
+    for a, b in zip(g_out, g_ref):
+        if b is None:
+            assert a is None or a.abs().max().item() == 0.0
+        else:
+            assert rel_err(a, b) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("maxdim,C,B,N", [(2, 3, 2, 5), (3, 3, 2, 5), (3, 8, 2, 40)])
+def test_cg_aggregate_matches_oracle(maxdim, C, B, N):
+    gen = torch.Generator().manual_seed(maxdim * 100 + C)
+    irreps = [(0, 0), (1, 1)] + ([(0, 2), (2, 0), (2, 2)] if maxdim == 3 else [])
+    node = _rand_rep(gen, (B, N), {k: C for k in irreps})
+    edge = _rand_rep(gen, (B, N, N), {(0, 0): C, (1, 1): C})
+    _check(*_run_both(node, edge, maxdim, True))
+    _check(*_run_both(edge, node, maxdim, True))        # the other orientation (edge (x) node)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("maxdim", [2, 3])
+def test_cg_pointwise_and_power_match_oracle(maxdim):
+    gen = torch.Generator().manual_seed(maxdim)
+    irreps = [(0, 0), (1, 1)] + ([(0, 2), (2, 0), (2, 2)] if maxdim == 3 else [])
+    a = _rand_rep(gen, (3, 7), {k: 4 for k in irreps})
+    b = _rand_rep(gen, (3, 7), {k: 4 for k in irreps[:3]})
+    _check(*_run_both(a, b, maxdim, False))
+    _check(*_run_both(a, a, maxdim, False))              # cg_power: both operands are the same tensors
+
+
+@pytest.mark.gpu
+def test_cg_product_rejects_cpu_tensors_and_bad_shapes():
+    from lgn_autoencoder_b200.cg_lib import cg_product
+    from lgn_autoencoder_b200.g_lib import GVec
+    gen = torch.Generator().manual_seed(0)
+    a = GVec(_rand_rep(gen, (2, 4), {(0, 0): 2, (1, 1): 2}, False), ignore_check=True)
+    with pytest.raises(RuntimeError):
+        cg_product(_cg(2), a, a, maxdim=2)
+    dev = torch.device("cuda:0")
+    a3 = GVec({k: v.to(dev) for k, v in _rand_rep(gen, (2, 4), {(0, 0): 2, (1, 1): 2}, False).items()}, ignore_check=True)
+    b3 = GVec({k: v.to(dev) for k, v in _rand_rep(gen, (2, 4), {(0, 0): 3, (1, 1): 3}, False).items()}, ignore_check=True)
+    with pytest.raises(ValueError):
+        cg_product(_cg(2).to(device=dev), a3, b3, maxdim=2)     # channel mismatch
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,cin,cout,d", [((2, 5), 15, 4, 4), ((3,), 7, 9, 1), ((2, 3, 3), 40, 8, 9), ((700,), 20, 4, 4)])
+def test_mix_matches_oracle(shape, cin, cout, d):
+    from lgn_autoencoder_b200 import layer_ops
+    from oracle import lgae_oracle as orc
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(cin)
+    w = torch.randn((2, cout, cin), generator=gen, dtype=torch.float64, requires_grad=True)
+    x = torch.randn((2,) + shape + (cin, d), generator=gen, dtype=torch.float64, requires_grad=True)
+    ref = orc.mix_zweight_zvec(w, x)
+    cot = torch.randn(ref.shape, generator=gen, dtype=torch.float64)
+    gw_ref, gx_ref = torch.autograd.grad((ref * cot).sum(), (w, x))
+    wd, xd = w.detach().to(dev).requires_grad_(True), x.detach().to(dev).requires_grad_(True)
+    out = layer_ops.mix(wd, xd)
+    gw, gx = torch.autograd.grad((out * cot.to(dev)).sum(), (wd, xd))
+    assert rel_err(out, ref) < TOL and rel_err(gx, gx_ref) < TOL and rel_err(gw, gw_ref) < TOL
+    # reproducible: fixed summation order
+    gw2, _ = torch.autograd.grad((layer_ops.mix(wd, xd) * cot.to(dev)).sum(), (wd, xd))
+    assert torch.equal(gw, gw2)
