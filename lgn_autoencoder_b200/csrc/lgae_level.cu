@@ -58,6 +58,12 @@ struct LevelArgs {
 #ifndef LGAE_LBWD_CF_MINB
 #define LGAE_LBWD_CF_MINB 3   // the same for the decoder's closed-form adjoint
 #endif
+#ifndef LGAE_LBWD_MINB_C4
+#define LGAE_LBWD_MINB_C4 3   // same, launches with 4 channels (128 threads): 3 CTAs/SM = 444 slots < 512 jets, 4 => one wave but 128 registers
+#endif
+#ifndef LGAE_LBWD_CF_MINB_C4
+#define LGAE_LBWD_CF_MINB_C4 3
+#endif
 #ifndef LGAE_LBWD_MINB
 #define LGAE_LBWD_MINB 3   // resident CTAs per SM the level adjoint is compiled for (register cap 168; 4 => 128 registers spills and is slower)
 #endif
@@ -917,8 +923,10 @@ static int launch_level_bwd(const LevelArgs& a, int grid, cudaStream_t st) {
         if (int rc = ensure_smem((const void*)kern, bytes)) return rc;        \
         launch_k(kern, dim3(grid), dim3(32 * a.C), bytes, st, a);                               \
     }
-    if (a.C <= 4) {
+    if (a.C <= 3) {
         if (cf) LGAE_LAUNCH(128, LGAE_LBWD_CF_MINB, true) else LGAE_LAUNCH(128, LGAE_LBWD_MINB, false)
+    } else if (a.C == 4) {
+        if (cf) LGAE_LAUNCH(128, LGAE_LBWD_CF_MINB_C4, true) else LGAE_LAUNCH(128, LGAE_LBWD_MINB_C4, false)
     } else {
         if (cf) LGAE_LAUNCH(256, 1, true) else LGAE_LAUNCH(256, 1, false)
     }
