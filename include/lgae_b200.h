@@ -227,6 +227,40 @@ int lgae_mix_forward(const double* w, const double* x, int64_t rows, int32_t c_i
 int lgae_mix_backward(const double* w, const double* x, const double* g_out, int64_t rows, int32_t c_in, int32_t c_out,
                       int32_t d, double* g_x, double* g_w, double* partials, void* stream);
 
+/* Complex scalar x irrep product with channel broadcast, out[e, c, m] = s[e, c] * v[e, c, m] (edge features
+ * rad (x) zonal: lgn/models/lgn_cg.py:167 -> g_torch.mul -> mul_zscalar_zirrep, lgn/g_lib/cplx_lib.py:54-72).
+ * s (2, edges, cs), v (2, edges, cv, d), out (2, edges, max(cs, cv), d); cs, cv equal or one of them 1. */
+int lgae_scalar_irrep_forward(const double* s, const double* v, int64_t edges, int32_t cs, int32_t cv, int32_t d,
+                              double* out, void* stream);
+int lgae_scalar_irrep_backward(const double* s, const double* v, const double* g_out, int64_t edges, int32_t cs,
+                               int32_t cv, int32_t d, double* g_s, double* g_v, void* stream);
+/* RadPolyTrig.forward (lgn/nn/position_levels.py:118-209), mix = 'cplx': k2 = 2*num_basis_fn Lorentzian bells
+ * b_k / (1 + (c_k x)^2 + 1e-16) + a_k of `edges` scalars x, zeroed where mask[e % n_mask] == 0, then for each of
+ * the n_l zonal degrees y_l = W_l bell + bias_l, W_l (n_out, k2).
+ *   planar != 0 (Cartesian basis, n_out = 2C): outs[l] is (2, edges, C), entry (o & 1, e, o >> 1);
+ *   planar == 0 (canonical basis: x holds the re and im slices, edges = 2*B*N*N): outs[l] is (edges, n_out).
+ * w, bias, outs: host arrays of n_l device pointers. */
+int lgae_radial_functions_forward(const double* x, const uint8_t* mask, int64_t edges, int64_t n_mask, const double* a,
+                                  const double* b, const double* c, int32_t k2, int32_t n_out, int32_t n_l,
+                                  const double* const* w, const double* const* bias, double* const* outs, int32_t planar,
+                                  void* stream);
+int64_t lgae_radial_functions_partials_doubles(int64_t edges, int32_t k2, int32_t n_out, int32_t n_l);
+/* Adjoint.  g_params receives, contiguously: dW [n_l][n_out][k2], dbias [n_l][n_out], da[k2], db[k2], dc[k2];
+ * g_x (edges) may be NULL. */
+int lgae_radial_functions_backward(const double* x, const uint8_t* mask, int64_t edges, int64_t n_mask, const double* a,
+                                   const double* b, const double* c, int32_t k2, int32_t n_out, int32_t n_l,
+                                   const double* const* w, const double* const* g_outs, int32_t planar, double* g_x,
+                                   double* g_params, double* partials, void* stream);
+/* One Linear layer on rows, y = act(x W^T + b), act = LeakyReLU(slope) when leaky_relu != 0 (the CGMLP layers,
+ * lgn/models/lgn_levels.py:191-227, for widths outside lgae_mlp_forward).  x (rows, n_in), w (n_out, n_in), b (n_out)
+ * or NULL, y (rows, n_out).  The adjoint takes the forward output y for the activation's derivative. */
+int lgae_linear_forward(const double* x, const double* w, const double* b, int64_t rows, int32_t n_in, int32_t n_out,
+                        int32_t leaky_relu, double slope, double* y, void* stream);
+int64_t lgae_linear_partials_doubles(int64_t rows, int32_t n_in, int32_t n_out);
+int lgae_linear_backward(const double* x, const double* w, const double* y, const double* g_y, int64_t rows, int32_t n_in,
+                         int32_t n_out, int32_t leaky_relu, double slope, double* g_x, double* g_w, double* g_b,
+                         double* partials, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,16 @@ _PROTOS = {
     "lgae_mix_partials_doubles": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "lgae_mix_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "lgae_mix_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "lgae_scalar_irrep_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "lgae_scalar_irrep_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "lgae_radial_functions_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32,
+                                                _P]),
+    "lgae_radial_functions_partials_doubles": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "lgae_radial_functions_backward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32,
+                                                 _P, _P, _P, _P]),
+    "lgae_linear_forward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P]),
+    "lgae_linear_partials_doubles": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "lgae_linear_backward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -24,8 +24,9 @@ def mix_zweight_zscalar(weight, part, zdim=0):
 
 
 def mul_zscalar_zirrep(scalar, part, zdim=0):
-    """(2,...,C) x (2,...,C,d) -> (2,...,C,d)."""
-    return _p(_c(scalar).unsqueeze(-1) * _c(part))
+    """(2,...,C) x (2,...,C,d) -> (2,...,C,d) (kernel: csrc/lgae_layers.cu)."""
+    from .. import layer_ops
+    return layer_ops.scalar_irrep(scalar, part)
 
 
 def mul_zscalar_zscalar(s1, s2, zdim=0):

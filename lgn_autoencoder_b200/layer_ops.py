@@ -1,10 +1,13 @@
-"""Layer-level ops of the reference's generic API on the hand-written kernels of csrc/lgae_cg.cu:
+"""Layer-level ops of the reference's generic API on the hand-written kernels of csrc/lgae_cg.cu and csrc/lgae_layers.cu:
 
 * ``cg_pairs`` — Clebsch-Gordan product of GVec parts, channel-wise, point-wise or aggregated over the neighbour axis
   (reference lgn/cg_lib/cg_ops.py:135-298), any maxdim, with its hand-written adjoint;
-* ``mix``      — per-irrep complex channel mixing (reference lgn/g_lib/cplx_lib.py:7-25) with its adjoint.
+* ``mix``      — per-irrep complex channel mixing (reference lgn/g_lib/cplx_lib.py:7-25) with its adjoint;
+* ``scalar_irrep`` — complex scalar x irrep product with channel broadcast (edge features, cplx_lib.py:54-72);
+* ``radial_functions`` — RadPolyTrig: bells + mask + one Linear per zonal degree (lgn/nn/position_levels.py:118-209);
+* ``linear``   — Linear (+ LeakyReLU) on rows, the CGMLP layers (lgn/models/lgn_levels.py:191-227).
 
-Both take and return the reference's planar complex tensors (2, ..., C, d) and are ``torch.autograd.Function``s over the
+All take and return the reference's planar complex tensors (2, ..., C, d) and are ``torch.autograd.Function``s over the
 C ABI (include/lgae_b200.h).  There is no CPU path: tensors must be fp64 CUDA tensors."""
 import ctypes as C
 
@@ -246,3 +249,150 @@ def mix(weight, part):
     if weight.dim() != 3 or weight.shape[0] != 2:
         raise ValueError(f"mix: expected a complex weight of shape (2, C_out, C_in), got {tuple(weight.shape)}")
     return _MixFn.apply(weight, part)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# complex scalar x irrep (edge features rad (x) zonal)
+# ------------------------------------------------------------------------------------------------------------
+class _ScalarIrrepFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scalar, part):
+        lib = _lib.load()
+        s, v = scalar.contiguous(), part.contiguous()
+        cs, cv, d = int(s.shape[-1]), int(v.shape[-2]), int(v.shape[-1])
+        edges = int(np.prod(s.shape[1:-1])) if s.dim() > 2 else 1
+        out = torch.empty(tuple(v.shape[:-2]) + (max(cs, cv), d), dtype=torch.float64, device=v.device)
+        _lib.check(lib.lgae_scalar_irrep_forward(s.data_ptr(), v.data_ptr(), edges, cs, cv, d, out.data_ptr(), _stream()), "scalar_irrep_forward")
+        ctx.save_for_backward(s, v)
+        ctx.dims = (edges, cs, cv, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        s, v = ctx.saved_tensors
+        edges, cs, cv, d = ctx.dims
+        gs = torch.empty_like(s) if ctx.needs_input_grad[0] else None
+        gv = torch.empty_like(v) if ctx.needs_input_grad[1] else None
+        _lib.check(lib.lgae_scalar_irrep_backward(s.data_ptr(), v.data_ptr(), g.contiguous().data_ptr(), edges, cs, cv, d, _lib.ptr(gs),
+                                                  _lib.ptr(gv), _stream()), "scalar_irrep_backward")
+        return gs, gv
+
+
+def scalar_irrep(scalar, part):
+    """(2,...,C) x (2,...,C,d) -> (2,...,C,d); either channel count may be 1 (broadcast)."""
+    _require_cuda(scalar, "scalar x irrep")
+    _require_cuda(part, "scalar x irrep")
+    bs, bv = tuple(scalar.shape[1:-1]), tuple(part.shape[1:-2])
+    if bs != bv:   # general batch broadcasting: materialise the expanded operands
+        full = torch.broadcast_shapes(bs, bv)
+        scalar = scalar.expand((2,) + full + (scalar.shape[-1],))
+        part = part.expand((2,) + full + tuple(part.shape[-2:]))
+    cs, cv = scalar.shape[-1], part.shape[-2]
+    if cs != cv and cs != 1 and cv != 1:
+        raise ValueError(f"scalar x irrep: channel counts {cs} and {cv} do not broadcast")
+    return _ScalarIrrepFn.apply(scalar, part)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# RadPolyTrig
+# ------------------------------------------------------------------------------------------------------------
+class _RadialFn(torch.autograd.Function):
+    """Inputs: norms, a, b, c, then W_0, bias_0, W_1, bias_1, ...  Outputs: one tensor per zonal degree."""
+
+    @staticmethod
+    def forward(ctx, edge_mask, planar, norms, a, b, c, *wb):
+        lib = _lib.load()
+        x = norms.contiguous()
+        _require_cuda(x, "RadPolyTrig")
+        ws = [t.contiguous() for t in wb[0::2]]
+        bs = [t.contiguous() for t in wb[1::2]]
+        a, b, c = a.contiguous(), b.contiguous(), c.contiguous()
+        mask = (edge_mask != 0).to(torch.uint8).contiguous()
+        n_l, n_out, k2 = len(ws), int(ws[0].shape[0]), int(ws[0].shape[1])
+        edges, n_mask = x.numel(), mask.numel()
+        if n_mask == 0 or edges % n_mask:
+            raise ValueError(f"RadPolyTrig: mask {tuple(edge_mask.shape)} does not broadcast over norms {tuple(norms.shape)}")
+        shape = ((2,) + tuple(x.shape) + (n_out // 2,)) if planar else (tuple(x.shape) + (n_out,))
+        outs = [torch.empty(shape, dtype=torch.float64, device=x.device) for _ in range(n_l)]
+        _lib.check(lib.lgae_radial_functions_forward(x.data_ptr(), mask.data_ptr(), edges, n_mask, a.data_ptr(), b.data_ptr(), c.data_ptr(), k2,
+                                                     n_out, n_l, _ptr_array(ws), _ptr_array(bs), _ptr_array(outs), int(planar), _stream()),
+                   "radial_functions_forward")
+        ctx.save_for_backward(x, mask, a, b, c, *ws)
+        ctx.dims = (edges, n_mask, k2, n_out, n_l, int(planar))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *g_outs):
+        lib = _lib.load()
+        x, mask, a, b, c, *ws = ctx.saved_tensors
+        edges, n_mask, k2, n_out, n_l, planar = ctx.dims
+        shape = ((2,) + tuple(x.shape) + (n_out // 2,)) if planar else (tuple(x.shape) + (n_out,))
+        gl = [g.contiguous() if g is not None else torch.zeros(shape, dtype=torch.float64, device=x.device) for g in g_outs]
+        gx = torch.empty_like(x) if ctx.needs_input_grad[2] else None
+        gp = torch.empty(n_l * n_out * (k2 + 1) + 3 * k2, dtype=torch.float64, device=x.device)
+        part = torch.empty(int(lib.lgae_radial_functions_partials_doubles(edges, k2, n_out, n_l)), dtype=torch.float64, device=x.device)
+        _lib.check(lib.lgae_radial_functions_backward(x.data_ptr(), mask.data_ptr(), edges, n_mask, a.data_ptr(), b.data_ptr(), c.data_ptr(), k2,
+                                                      n_out, n_l, _ptr_array(ws), _ptr_array(gl), planar, _lib.ptr(gx), gp.data_ptr(),
+                                                      part.data_ptr(), _stream()), "radial_functions_backward")
+        nw = n_l * n_out * k2
+        gw = gp[:nw].view(n_l, n_out, k2)
+        gb = gp[nw:nw + n_l * n_out].view(n_l, n_out)
+        rest = gp[nw + n_l * n_out:].view(3, k2)
+        wb = []
+        for l in range(n_l):
+            wb += [gw[l], gb[l]]
+        return (None, None, gx, rest[0].view(a.shape), rest[1].view(b.shape), rest[2].view(c.shape)) + tuple(wb)
+
+
+def radial_functions(norms, edge_mask, a, b, c, linears, planar):
+    """linears: list of (weight (n_out, 2K), bias (n_out)).  Returns one tensor per zonal degree:
+    planar (Cartesian basis): (2, *norms.shape, n_out/2); otherwise (canonical basis): (*norms.shape, n_out)."""
+    wb = []
+    for w, bias in linears:
+        wb += [w, bias]
+    return list(_RadialFn.apply(edge_mask, bool(planar), norms, a, b, c, *wb))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Linear (+ LeakyReLU)
+# ------------------------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, slope):
+        lib = _lib.load()
+        _require_cuda(x, "linear")
+        x2 = x.contiguous().view(-1, x.shape[-1])
+        w = weight.contiguous()
+        bvec = bias.contiguous() if bias is not None else None
+        rows, n_in, n_out = int(x2.shape[0]), int(w.shape[1]), int(w.shape[0])
+        if x2.shape[1] != n_in:
+            raise ValueError(f"linear: input features {x2.shape[1]} do not match the weight {tuple(w.shape)}")
+        y = torch.empty((rows, n_out), dtype=torch.float64, device=x.device)
+        act = slope is not None
+        _lib.check(lib.lgae_linear_forward(x2.data_ptr(), w.data_ptr(), _lib.ptr(bvec), rows, n_in, n_out, int(act), float(slope or 0.0),
+                                           y.data_ptr(), _stream()), "linear_forward")
+        ctx.save_for_backward(x2, w, y)
+        ctx.meta = (rows, n_in, n_out, act, float(slope or 0.0), tuple(x.shape), bias is not None)
+        return y.view(tuple(x.shape[:-1]) + (n_out,))
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x2, w, y = ctx.saved_tensors
+        rows, n_in, n_out, act, slope, xshape, has_bias = ctx.meta
+        g2 = g.contiguous().view(rows, n_out)
+        gx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        gb = torch.empty(n_out, dtype=torch.float64, device=w.device) if (has_bias and ctx.needs_input_grad[2]) else None
+        part = None
+        if gw is not None or gb is not None:
+            part = torch.empty(int(lib.lgae_linear_partials_doubles(rows, n_in, n_out)), dtype=torch.float64, device=w.device)
+        _lib.check(lib.lgae_linear_backward(x2.data_ptr(), w.data_ptr(), y.data_ptr(), g2.data_ptr(), rows, n_in, n_out, int(act), slope,
+                                            _lib.ptr(gx), _lib.ptr(gw), _lib.ptr(gb), _lib.ptr(part), _stream()), "linear_backward")
+        return (gx.view(xshape) if gx is not None else None), gw, gb, None
+
+
+def linear(x, weight, bias=None, leaky_slope=None):
+    """y = x W^T + b on the last axis, followed by LeakyReLU(leaky_slope) when a slope is given."""
+    return _LinearFn.apply(x, weight, bias, leaky_slope)

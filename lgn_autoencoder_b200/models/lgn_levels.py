@@ -6,6 +6,7 @@ for stand-alone calls and for configurations outside the fused path."""
 import torch
 import torch.nn as nn
 
+from .. import layer_ops
 from ..cg_lib import CGProduct
 from ..g_lib import GTau
 from ..nn import CatMixReps, get_activation_fn
@@ -63,9 +64,13 @@ class CGMLP(nn.Module):
         x = out.pop((0, 0)).squeeze(-1)
         s = x.shape
         x = x.permute(1, 2, 3, 0).contiguous().view(s[1:3] + (self.num_scalars,))
+        # every layer is one launch of the tiled fp64 GEMM kernel (csrc/lgae_layers.cu); LeakyReLU is fused into it
         for lin, act in zip(self.linear, self.activations):
-            x = act(lin(x))
-        x = self.linear[-1](x)
+            if isinstance(act, nn.LeakyReLU):
+                x = layer_ops.linear(x, lin.weight, lin.bias, leaky_slope=act.negative_slope)
+            else:
+                x = act(layer_ops.linear(x, lin.weight, lin.bias))
+        x = layer_ops.linear(x, self.linear[-1].weight, self.linear[-1].bias)
         if mask is not None:
             x = torch.where(mask, x, torch.zeros((), dtype=x.dtype, device=x.device))
         out[(0, 0)] = x.view(s[1:] + (2,)).permute(3, 0, 1, 2).unsqueeze(-1)

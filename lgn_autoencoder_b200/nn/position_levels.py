@@ -37,6 +37,12 @@ class RadPolyTrig(nn.Module):
         self.device = device
 
     def forward(self, norms, edge_mask):
+        if self.mix == "cplx" or self.mix is True:
+            # one kernel for the bells, the mask and the Linear of every zonal degree (csrc/lgae_layers.cu)
+            from .. import layer_ops
+            outs = layer_ops.radial_functions(norms, edge_mask, self.a, self.b, self.c, [(lin.weight, lin.bias) for lin in self.linear],
+                                              planar=self.input_basis != "canonical")
+            return GScalar({(l, l): o for l, o in enumerate(outs)}, ignore_check=True)
         s = tuple(norms.shape)
         mask = (edge_mask != 0).unsqueeze(-1)
         x = norms.unsqueeze(-1)

@@ -139,3 +139,74 @@ def test_mix_matches_oracle(shape, cin, cout, d):
     # reproducible: fixed summation order
     gw2, _ = torch.autograd.grad((layer_ops.mix(wd, xd) * cot.to(dev)).sum(), (wd, xd))
     assert torch.equal(gw, gw2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cs,cv", [(5, 1), (5, 5), (1, 5)])
+def test_scalar_times_irrep_matches_oracle(cs, cv):
+    from lgn_autoencoder_b200 import layer_ops
+    from oracle import lgae_oracle as orc
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(cs * 10 + cv)
+    s = torch.randn((2, 2, 6, 6, cs), generator=gen, dtype=torch.float64, requires_grad=True)
+    v = torch.randn((2, 2, 6, 6, cv, 4), generator=gen, dtype=torch.float64, requires_grad=True)
+    ref = orc.mul_zscalar_zirrep(s, v)
+    cot = torch.randn(ref.shape, generator=gen, dtype=torch.float64)
+    gs_ref, gv_ref = torch.autograd.grad((ref * cot).sum(), (s, v))
+    sd, vd = s.detach().to(dev).requires_grad_(True), v.detach().to(dev).requires_grad_(True)
+    out = layer_ops.scalar_irrep(sd, vd)
+    gs, gv = torch.autograd.grad((out * cot.to(dev)).sum(), (sd, vd))
+    assert rel_err(out, ref) < TOL and rel_err(gs, gs_ref) < TOL and rel_err(gv, gv_ref) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("basis,B,N,C", [("cartesian", 2, 7, 3), ("canonical", 2, 7, 4), ("cartesian", 3, 40, 8)])
+def test_radial_functions_match_oracle(basis, B, N, C):
+    """RadPolyTrig module (kernel) vs the oracle's restatement: outputs, d/dnorms and every parameter gradient."""
+    from lgn_autoencoder_b200.nn import RadPolyTrig
+    from oracle import lgae_oracle as orc
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(N)
+    torch.manual_seed(5)
+    mod = RadPolyTrig(1, 10, C, mix=True, input_basis=basis, device=dev, dtype=torch.float64)
+    shape = (B, N, N) if basis == "cartesian" else (2, B, N, N)
+    norms = torch.randn(shape, generator=gen, dtype=torch.float64)
+    mask = (torch.rand((B, N, N), generator=gen) > 0.3).to(torch.uint8)
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in mod.named_parameters()}
+    x_ref = norms.clone().requires_grad_(True)
+    lin = [(params[f"linear.{l}.weight"], params[f"linear.{l}.bias"]) for l in range(2)]
+    ref = orc.rad_poly_trig(x_ref, mask, params["a"], params["b"], params["c"], lin, C, basis)
+    cot = {k: torch.randn(v.shape, generator=gen, dtype=torch.float64) for k, v in ref.items()}
+    names = list(params)
+    g_ref = torch.autograd.grad(sum((ref[k] * cot[k]).sum() for k in ref), [x_ref] + [params[n] for n in names])
+    x = norms.to(dev).requires_grad_(True)
+    out = mod(x, mask.to(dev))
+    assert list(out.keys()) == list(ref.keys())
+    for k in ref:
+        assert out[k].shape == ref[k].shape and rel_err(out[k], ref[k]) < TOL
+    g = torch.autograd.grad(sum((out[k] * cot[k].to(dev)).sum() for k in ref), [x] + [dict(mod.named_parameters())[n] for n in names])
+    for a, b, n in zip(g, g_ref, ["norms"] + names):
+        assert rel_err(a, b) < 1e-11, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,nin,nout,slope", [(37, 6, 36, 0.01), (700, 96, 96, None), (1000, 72, 12, 0.01), (5, 3, 130, 0.2)])
+def test_linear_matches_torch_fp64(rows, nin, nout, slope):
+    """Floating-point GEMM kernel: reference = the same op in plain torch fp64 on the CPU; tolerance 1e-12 relative."""
+    from lgn_autoencoder_b200 import layer_ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(rows)
+    x = torch.randn((rows, nin), generator=gen, dtype=torch.float64, requires_grad=True)
+    w = torch.randn((nout, nin), generator=gen, dtype=torch.float64, requires_grad=True)
+    b = torch.randn((nout,), generator=gen, dtype=torch.float64, requires_grad=True)
+    ref = torch.nn.functional.linear(x, w, b)
+    if slope is not None:
+        ref = torch.nn.functional.leaky_relu(ref, slope)
+    cot = torch.randn(ref.shape, generator=gen, dtype=torch.float64)
+    g_ref = torch.autograd.grad((ref * cot).sum(), (x, w, b))
+    xd, wd, bd = (t.detach().to(dev).requires_grad_(True) for t in (x, w, b))
+    out = layer_ops.linear(xd, wd, bd, leaky_slope=slope)
+    g = torch.autograd.grad((out * cot.to(dev)).sum(), (xd, wd, bd))
+    assert rel_err(out, ref) < TOL
+    for a, r in zip(g, g_ref):
+        assert rel_err(a, r) < TOL
