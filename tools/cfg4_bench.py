@@ -1,0 +1,54 @@
+"""Developer: training-step throughput of BASELINE.json configs[3] (cfg-4: maxdim 3, enc 6 6 8 8 / dec 8 8 6 6, 'mix' latent map,
+bs 1024) on the layer-level kernels (csrc/lgae_cg.cu, lgae_layers.cu) through the module API + autograd, with a per-kernel table.
+Usage: python tools/cfg4_bench.py [B] [steps]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from bench import synthetic_jets
+from lgn_autoencoder_b200 import _lib
+from lgn_autoencoder_b200.flop_model import step_flops_per_jet
+from lgn_autoencoder_b200.models import LGNDecoder, LGNEncoder
+from lgn_autoencoder_b200.train import training_step
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+N, ENC, DEC = 30, [6, 6, 8, 8], [8, 8, 6, 6]
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+common = dict(maxdim=[3], num_basis_fn=10, max_zf=[1], weight_init="randn", level_gain=[1.0], activation="leakyrelu", mlp=True, mlp_depth=6,
+              mlp_width=6, device=dev, dtype=torch.float64)
+enc = LGNEncoder(num_input_particles=N, tau_input_scalars=1, tau_input_vectors=1, tau_latent_scalars=1, tau_latent_vectors=8,
+                 num_channels=ENC, jet_features=False, map_to_latent="mix", **common)
+dec = LGNDecoder(tau_latent_scalars=1, tau_latent_vectors=8, num_output_particles=N, tau_output_scalars=1, tau_output_vectors=1,
+                 num_channels=DEC, cg_dict=enc.cg_dict, **common)
+p4 = synthetic_jets(B, N, seed=2).to(dev)
+
+
+def step():
+    for m in (enc, dec):
+        for p in m.parameters():
+            p.grad = None
+    loss, _, _ = training_step(enc, dec, p4)
+    loss.backward()
+    return loss
+
+
+for _ in range(2):
+    loss = step()
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(steps):
+    loss = step()
+b.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(b) / steps
+k = _lib.kernel_timings(step, reps=2)
+tot = sum(n * t for n, t in k.values()) / 2
+for name, (n, t) in sorted(k.items(), key=lambda kv: -kv[1][0] * kv[1][1])[:12]:
+    print(f"{name:28s} {n/2:5.0f} x {t*1e3:8.1f} us  {n*t/2/tot*100:5.1f}% of library time")
+try:
+    fl = step_flops_per_jet(N, ENC, DEC)
+except Exception:
+    fl = float("nan")
+print(f"cfg-4 B={B}: {ms:.2f} ms/step -> {B / ms * 1e3:.0f} jets/s; library kernels {tot:.2f} ms/step; loss {loss.item():.6g}; "
+      f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB; maxdim-2 flop model would give {fl/1e6:.1f} MFLOP/jet (not the maxdim-3 count)")
