@@ -57,6 +57,9 @@ int run_latent_bridge(const LgaeModelDesc* de, const double* theta_e, const Lgae
                       const double* V, double* lat00, double* lat11, int32_t* sel, double* y, double* S0, double* V0, cudaStream_t st);
 int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, const double* V, const double* target, double* recon,
                  double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, PartPlan* plan, cudaStream_t st);
+int run_grad_init2(const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta, double lambda,
+                   double* psum, cudaStream_t st);
+int run_reduce_segs(PartPlan* plan, int64_t n_params, double* gtheta, const double* psum, double lambda, double* loss, cudaStream_t st);
 int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta,
                      double lambda, double* loss, cudaStream_t st);
 int64_t glue_part_doubles(const LgaeModelDesc* d, int batch);
@@ -154,6 +157,29 @@ static SideStream* side_stream() {
     per_dev[dev] = ss;
     return ss->ok ? ss : nullptr;
 }
+// Auxiliary stream of the training step for its small, independent kernels (weight packing and gradient init at the start,
+// the encoder-input adjoint next to the last radial adjoint): they become parallel branches of the step's graph instead of
+// ~10 us links of its critical path.  LGAE_NO_AUX=1 keeps everything on one stream.
+static SideStream* aux_stream() {
+    static const bool off = [] { const char* e = getenv("LGAE_NO_AUX"); return e && e[0] == '1'; }();
+    if (off) return nullptr;
+    static std::unordered_map<int, SideStream*> per_dev;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    auto it = per_dev.find(dev);
+    if (it != per_dev.end()) return it->second->ok ? it->second : nullptr;
+    SideStream* ss = new SideStream();
+    ss->ok = cudaStreamCreateWithFlags(&ss->s, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ss->ok && i <= LGAE_MAX_LEVELS; ++i)
+        ss->ok = cudaEventCreateWithFlags(&ss->fork[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ss->join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ss->ok) cudaGetLastError();
+    per_dev[dev] = ss;
+    return ss->ok ? ss : nullptr;
+}
+static std::mutex g_aux_mu;   // serialises the training steps that share the auxiliary stream's events
 #define LGAE_CUDA_TRY(expr, what)                                   \
     do {                                                            \
         if ((expr) != cudaSuccess) return check_launch(what);       \
@@ -312,7 +338,7 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
 // Launch sequence of LGNEncoder.forward; `pack` = also pack the MLP weights (a caller that runs both models packs them once).
 static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
                               double* ws, double* lat00, double* lat11, int32_t* sel, bool pack, cudaStream_t st, bool with_latent = true,
-                              bool with_input = true) {
+                              bool with_input = true, cudaEvent_t pack_done = nullptr) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
     SideStream* ss = L.rsave[0] >= 0 ? side_stream() : nullptr;
@@ -336,6 +362,7 @@ static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const
             LGAE_TRY(run_radial_fwd(d, l, theta, p4, node_mask, batch, ws + L.rsave[l], ws + L.nrm, st));
         LGAE_TRY(run_level_fwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l],
                                L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, ws + L.spre[l], ws + L.V[l + 1], st));
+        if (l == 0 && pack_done) LGAE_CUDA_TRY(cudaStreamWaitEvent(st, pack_done, 0), "pack wait");   // packed on another stream
         if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
     if (!with_latent) return LGAE_OK;   // the caller runs the fused latent bridge
@@ -345,7 +372,7 @@ static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const
 // Launch sequence of the encoder adjoint; appends its blocks / segments to `plan` (no reduce).
 static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
                                double* ws, const int32_t* sel, const double* g_lat00, const double* g_lat11, PartPlan& plan,
-                               cudaStream_t st, bool with_latent = true) {
+                               cudaStream_t st, bool with_latent = true, SideStream* aux = nullptr) {
     SideStream* ss = side_stream();
     std::unique_lock<std::mutex> side_lock(g_side_mu, std::defer_lock);
     if (ss) side_lock.lock();
@@ -380,12 +407,22 @@ static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, cons
                 LGAE_TRY(run_radial_bwd(d, l, theta, p4, node_mask, batch, ws + L.gr[l], ws + L.nrm, &plan, ss->s));
                 side_used = true;
             } else {
+                if (aux && l == 0) {
+                    // the input-map adjoint (small) runs next to the last radial adjoint; both only feed the final reduce
+                    LGAE_CUDA_TRY(cudaEventRecord(aux->fork[1], st), "aux fork");
+                    LGAE_CUDA_TRY(cudaStreamWaitEvent(aux->s, aux->fork[1], 0), "aux fork wait");
+                    LGAE_TRY(run_enc_input_bwd(d, p4, ws + L.mass, batch, ws + L.gS[cur ^ 1], ws + L.gV[cur ^ 1], &plan, aux->s));
+                    LGAE_CUDA_TRY(cudaEventRecord(aux->join[2], aux->s), "aux join");
+                }
                 LGAE_TRY(run_radial_bwd(d, l, theta, p4, node_mask, batch, ws + L.gr[l], ws + L.nrm, &plan, st));
             }
             cur ^= 1;
             gs_zero = false;
         }
-        LGAE_TRY(run_enc_input_bwd(d, p4, ws + L.mass, batch, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
+        if (aux && !ss && nl > 0)
+            LGAE_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[2], 0), "aux join wait");
+        else
+            LGAE_TRY(run_enc_input_bwd(d, p4, ws + L.mass, batch, ws + L.gS[cur], ws + L.gV[cur], &plan, st));
         if (side_used) {
             LGAE_CUDA_TRY(cudaEventRecord(ss->join[0], ss->s), "join");
             LGAE_CUDA_TRY(cudaStreamWaitEvent(st, ss->join[0], 0), "join wait");
@@ -506,14 +543,31 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
     if (enc->n_particles > 32) return LGAE_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const double* x = normalize ? p4 : p4_in;
+    SideStream* aux = aux_stream();
+    std::unique_lock<std::mutex> aux_lock(g_aux_mu, std::defer_lock);
+    if (aux) aux_lock.lock();
+    // L1 partial sums of the gradient init: the second reduce-scratch region at the end of `partials` (the first one, behind the
+    // plan's blocks, is unused by this entry point)
+    double* psum = partials + lgae_train_step_partials_doubles(enc, dec, batch) - 1 - reduce_scratch_doubles();
     // forward: one launch packs the MLP weights of both models
     {
         const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
-        LGAE_TRY(run_mlp_pack(enc, theta_enc, ws_enc, Le.wpack, st, dec, theta_dec, ws_dec, Ld.wpack));
+        if (aux) {
+            // weight packing and gradient init only need theta: a parallel branch next to normalise + radial functions
+            LGAE_CUDA_TRY(cudaEventRecord(aux->fork[0], st), "aux fork");
+            LGAE_CUDA_TRY(cudaStreamWaitEvent(aux->s, aux->fork[0], 0), "aux fork wait");
+            LGAE_TRY(run_mlp_pack(enc, theta_enc, ws_enc, Le.wpack, aux->s, dec, theta_dec, ws_dec, Ld.wpack));
+            LGAE_CUDA_TRY(cudaEventRecord(aux->join[0], aux->s), "aux join");
+            LGAE_TRY(run_grad_init2(theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, psum, aux->s));
+            LGAE_CUDA_TRY(cudaEventRecord(aux->join[1], aux->s), "aux join");
+        } else {
+            LGAE_TRY(run_mlp_pack(enc, theta_enc, ws_enc, Le.wpack, st, dec, theta_dec, ws_dec, Ld.wpack));
+        }
         if (normalize)   // normalisation + encoder input map, one CTA per jet
             LGAE_TRY(run_norm_input(enc, theta_enc, p4_in, batch, p4, norm_factor, ws_enc + Le.mass, ws_enc + Le.S[0], ws_enc + Le.V[0], st));
     }
-    LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false, !normalize));
+    LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false, !normalize,
+                                aux ? aux->join[0] : nullptr));
     {
         // fused encoder latent map + decoder input map
         const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
@@ -542,8 +596,12 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
                                        ws_enc + Le.gS[0], ws_enc + Le.gV[0], &plan, gtheta_dec_offset, 0, st));
     }
     plan.theta_base = 0;
-    LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan, st, false));
-    return run_reduce_plan2(&plan, theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, loss, st);
+    LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan, st, false, aux));
+    if (aux)
+        LGAE_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[1], 0), "aux join wait");
+    else
+        LGAE_TRY(run_grad_init2(theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, psum, st));
+    return run_reduce_segs(&plan, enc->n_params + dec->n_params, gtheta, psum, l1_lambda, loss, st);
 }
 
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,

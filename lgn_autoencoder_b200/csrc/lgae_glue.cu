@@ -1215,17 +1215,21 @@ int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const doub
 int reduce_scratch_doubles() { return L1_BLOCKS_MAX; }
 
 // The same for two models whose gradients share one bucket (segments of model B were declared with plan->theta_base = off_b).
-int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta,
-                     double lambda, double* loss, cudaStream_t st) {
+// The two halves of run_reduce_plan2, so that a caller can run the gradient init early on another stream (it only needs
+// theta): psum = L1_BLOCKS_MAX doubles of scratch that nothing else touches between the two launches.
+int run_grad_init2(const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta, double lambda,
+                   double* psum, cudaStream_t st) {
     const bool l1 = lambda != 0.0;
     int nblk = (int)((na + nb + 1023) / 1024);
     nblk = nblk < 1 ? 1 : (nblk > L1_BLOCKS_MAX ? L1_BLOCKS_MAX : nblk);
-    double* psum = plan->base + plan->used;
-    {
-        LaunchScope ls_("grad_init", st);
-        launch_k(grad_init2_kernel, dim3(nblk), dim3(256), 0, st, theta_a, na, theta_b, nb, off_b, l1 ? lambda : 0.0, gtheta, l1 ? psum : nullptr);
-        if (int rc = check_launch("grad_init")) return rc;
-    }
+    LaunchScope ls_("grad_init", st);
+    launch_k(grad_init2_kernel, dim3(nblk), dim3(256), 0, st, theta_a, na, theta_b, nb, off_b, l1 ? lambda : 0.0, gtheta, l1 ? psum : nullptr);
+    return check_launch("grad_init");
+}
+int run_reduce_segs(PartPlan* plan, int64_t n_params, double* gtheta, const double* psum, double lambda, double* loss, cudaStream_t st) {
+    const bool l1 = lambda != 0.0;
+    int nblk = (int)((n_params + 1023) / 1024);
+    nblk = nblk < 1 ? 1 : (nblk > L1_BLOCKS_MAX ? L1_BLOCKS_MAX : nblk);
     if (plan->table.n == 0 && !l1) return LGAE_OK;
     int chunks = 0;
     for (int i = 0; i < plan->table.n; ++i) {
@@ -1236,6 +1240,12 @@ int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const do
     LaunchScope ls_("reduce_partials", st);
     launch_k(reduce_segs_kernel, dim3(chunks + 1), dim3(32, 8), 0, st, plan->table, plan->base, gtheta, psum, nblk, lambda, l1 ? loss : nullptr);
     return check_launch("reduce_partials");
+}
+int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta,
+                     double lambda, double* loss, cudaStream_t st) {
+    double* psum = plan->base + plan->used;
+    if (int rc = run_grad_init2(theta_a, na, theta_b, nb, off_b, gtheta, lambda, psum, st)) return rc;
+    return run_reduce_segs(plan, na + nb, gtheta, psum, lambda, loss, st);
 }
 // Doubles of partial rows used by the glue adjoints of a model.
 int64_t glue_part_doubles(const LgaeModelDesc* d, int batch) {
