@@ -49,8 +49,8 @@ int run_dec_output_bwd(const LgaeModelDesc* d, const double* theta, int B, const
                        const double* g_gen00, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
 int run_latent_bridge_bwd(const LgaeModelDesc* dd, const double* theta_d, const LgaeModelDesc* de, const double* theta_e, int B,
                           const double* lat11, double* y, const double* gS_d, const double* gV_d, const double* gy, double* g_lat11,
-                          const double* S, const double* V, const int32_t* sel, double* gS_e, double* gV_e, PartPlan* plan,
-                          int64_t theta_base_d, int64_t theta_base_e, cudaStream_t st);
+                          const double* S, const double* V, const int32_t* sel, double* gS_e, double* gV_e, PartPlan* plan_d,
+                          PartPlan* plan_e, cudaStream_t st);
 int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const double* theta, double lambda, double* loss, cudaStream_t st);
 int reduce_scratch_doubles();
 int run_latent_bridge(const LgaeModelDesc* de, const double* theta_e, const LgaeModelDesc* dd, const double* theta_d, int B, const double* S,
@@ -575,33 +575,44 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
                                    lat11, sel, ws_dec + Ld.y, ws_dec + Ld.S[0], ws_dec + Ld.V[0], st));
     }
     LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, false, st, false, false));
-    // both adjoints append to one plan; a single gradient-init + reduce pair finishes the step
-    PartPlan plan;
-    plan.base = partials;
-    plan.theta_base = gtheta_dec_offset;
+    // one plan per model over the same partials buffer (the encoder's continues where the decoder's ends): the decoder's rows are
+    // reduced on the auxiliary stream while the encoder adjoint runs, the encoder's at the end
+    PartPlan plan_d, plan_e;
+    plan_d.base = plan_e.base = partials;
+    plan_d.theta_base = gtheta_dec_offset;
     {
         // fused decoder tail: reconstruction, chamfer (+ batch sum), loss gradient, adjoint of the output map
         const Layout Ld = layout(dec, batch);
         unsigned int* counter = reinterpret_cast<unsigned int*>(partials + lgae_train_step_partials_doubles(enc, dec, batch) - 1);
         LGAE_TRY(run_dec_tail(dec, theta_dec, batch, enc->n_particles, ws_dec + Ld.V[dec->n_levels], x, recon, g_recon, ws_dec + Ld.gV[0],
-                              jet_loss, loss, counter, &plan, st));
+                              jet_loss, loss, counter, &plan_d, st));
     }
-    LGAE_TRY(dec_backward_launch(dec, theta_dec, lat11, batch, ws_dec, g_recon, nullptr, g_lat11, plan, st, false, false));
+    LGAE_TRY(dec_backward_launch(dec, theta_dec, lat11, batch, ws_dec, g_recon, nullptr, g_lat11, plan_d, st, false, false));
     {
         // fused adjoint of the bridge: decoder input map, then encoder latent map, latent gradient handed over on chip
         const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
         const int cur = dec->n_levels & 1;
         LGAE_TRY(run_latent_bridge_bwd(dec, theta_dec, enc, theta_enc, batch, lat11, ws_dec + Ld.y, ws_dec + Ld.gS[cur], ws_dec + Ld.gV[cur],
                                        ws_dec + Ld.gy, g_lat11, ws_enc + Le.S[enc->n_levels], ws_enc + Le.V[enc->n_levels], sel,
-                                       ws_enc + Le.gS[0], ws_enc + Le.gV[0], &plan, gtheta_dec_offset, 0, st));
+                                       ws_enc + Le.gS[0], ws_enc + Le.gV[0], &plan_d, &plan_e, st));
     }
-    plan.theta_base = 0;
-    LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan, st, false, aux));
-    if (aux)
+    const int64_t n_all = enc->n_params + dec->n_params;
+    if (aux) {
+        // the decoder's gradient is complete: reduce it now, next to the encoder adjoint (the gradient init ran on this stream)
+        LGAE_CUDA_TRY(cudaEventRecord(aux->fork[2], st), "aux fork");
+        LGAE_CUDA_TRY(cudaStreamWaitEvent(aux->s, aux->fork[2], 0), "aux fork wait");
+        LGAE_TRY(run_reduce_segs(&plan_d, n_all, gtheta, psum, 0.0, nullptr, aux->s));
+        LGAE_CUDA_TRY(cudaEventRecord(aux->join[3], aux->s), "aux join");
+    }
+    LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan_e, st, false, aux));
+    if (aux) {
         LGAE_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[1], 0), "aux join wait");
-    else
+        LGAE_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[3], 0), "aux join wait");
+    } else {
         LGAE_TRY(run_grad_init2(theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, psum, st));
-    return run_reduce_segs(&plan, enc->n_params + dec->n_params, gtheta, psum, l1_lambda, loss, st);
+        LGAE_TRY(run_reduce_segs(&plan_d, n_all, gtheta, psum, 0.0, nullptr, st));
+    }
+    return run_reduce_segs(&plan_e, n_all, gtheta, psum, l1_lambda, loss, st);
 }
 
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,

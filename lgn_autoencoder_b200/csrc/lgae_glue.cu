@@ -1135,10 +1135,10 @@ int run_dec_input_bwd(const LgaeModelDesc* d, const double* theta, int B, const 
 // dec_input_bwd + enc_latent_bwd fused (training step).  g_lat11 is still written (API output).
 int run_latent_bridge_bwd(const LgaeModelDesc* dd, const double* theta_d, const LgaeModelDesc* de, const double* theta_e, int B,
                           const double* lat11, double* y, const double* gS_d, const double* gV_d, const double* gy, double* g_lat11,
-                          const double* S, const double* V, const int32_t* sel, double* gS_e, double* gV_e, PartPlan* plan,
-                          int64_t theta_base_d, int64_t theta_base_e, cudaStream_t st) {
-    PartPlan* plan_d = plan;
-    PartPlan* plan_e = plan;
+                          const double* S, const double* V, const int32_t* sel, double* gS_e, double* gV_e, PartPlan* plan_d,
+                          PartPlan* plan_e, cudaStream_t st) {
+    // plan_d / plan_e: the decoder's and the encoder's plans (they may be the same object); both allocate from one buffer,
+    // the encoder's plan continues where the decoder's ends
     DecInArgs di = dec_in_args(dd, theta_d, B, lat11, y, nullptr, nullptr);
     di.gS = gS_d; di.gV = gV_d; di.gy = gy; di.g_lat11 = g_lat11;
     if (di.N > 128) return LGAE_E_UNSUPPORTED;
@@ -1149,7 +1149,6 @@ int run_latent_bridge_bwd(const LgaeModelDesc* dd, const double* theta_d, const 
     const int mix = a.mode == LGAE_LATENT_MIX;
     const int cin = mix ? a.N * a.C : a.C;
     const int grid = glue_grid(B);
-    plan->theta_base = theta_base_d;
     {
         const int64_t ng = (int64_t)2 * di.N * di.tau, w = ng + 4 * di.C, off = plan_d->block(grid, w);
         if (int rc = plan_d->seg(di.off_g11, off, w, 0, ng, grid)) return rc;
@@ -1157,7 +1156,7 @@ int run_latent_bridge_bwd(const LgaeModelDesc* dd, const double* theta_d, const 
         if (int rc = plan_d->seg(di.off_in11, off, w, ng + 2 * di.C, 2 * di.C, grid)) return rc;
         di.partials = plan_d->base + off; di.part_stride = w; di.po_g11 = 0; di.po_in00 = ng; di.po_in11 = ng + 2 * di.C;
     }
-    plan->theta_base = theta_base_e;
+    if (plan_e != plan_d) plan_e->used = plan_d->used;
     {
         const int64_t n00 = (int64_t)2 * a.tau_s * cin, n11 = (int64_t)2 * a.tau_v * cin, w = n00 + n11, off = plan_e->block(grid, w);
         if (int rc = plan_e->seg(a.off00, off, w, 0, n00, grid)) return rc;
