@@ -88,12 +88,13 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(sample_batch, steps, warmup):
-    """jets/s of the CPU oracle (the reference's algorithm restated in torch, all host threads) on a bounded sample."""
+def cpu_oracle_rate(sample_batch, steps, warmup, threads=None):
+    """jets/s of the CPU oracle (the reference's algorithm restated in torch, all host threads unless `threads`) on a bounded
+    sample."""
     import torch
     from oracle import lgae_oracle as orc
     from lgn_autoencoder_b200.models import LGNDecoder, LGNEncoder  # only to draw reference-shaped random weights
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(threads or os.cpu_count())
     torch.manual_seed(0)
     common = dict(maxdim=[2], num_basis_fn=10, max_zf=[1], weight_init="randn", level_gain=[1.0], activation="leakyrelu", mlp=True,
                   mlp_depth=6, mlp_width=6, device=torch.device("cpu"), dtype=torch.float64)
@@ -125,7 +126,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 32
+    sample = CFG["batch"]   # the real per-GPU batch: ~3 s per step on the GPU box's 16 host threads
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     rate, sec = cpu_oracle_rate(sample, steps, warmup)
     cores = os.cpu_count()
@@ -280,9 +281,12 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec = cpu_oracle_rate(32, 3, 1)
+        rate, sec = cpu_oracle_rate(B, 2, 1)
+        rate1, sec1 = cpu_oracle_rate(32, 1, 1, threads=1)
         cpu = {"value": rate, "unit": "jets/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"3 steps of 32 jets (median {sec:.2f} s/step), fwd+bwd, torch fp64 on {os.cpu_count()} threads, oracle/lgae_oracle.py"}
+               "sample": f"2 steps of {B} jets (the full per-GPU batch, median {sec:.2f} s/step) after 1 warm-up, fwd+bwd, torch fp64 on "
+                         f"{os.cpu_count()} threads, oracle/lgae_oracle.py",
+               "one_thread": {"value": rate1, "unit": "jets/s", "sample": f"1 step of 32 jets ({sec1:.2f} s) on 1 thread"}}
 
     if rank == 0:
         jets = B * world
