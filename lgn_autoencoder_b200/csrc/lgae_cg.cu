@@ -23,6 +23,7 @@ struct CgArgs {
     double *g1, *g2;
     int64_t plane1, plane2;
     int32_t B, N, NJ, C, d1, d2, n_comp, n_terms, n_out, JT, acc1, acc2;
+    int32_t JS;           // forward: lanes that share one output item and split the neighbour sum (power of two <= 32)
     const int32_t* tab;   // [3 orderings][n_terms][3] (comp, a, d), then comp_start[n_comp+1], a_start[d1+1], d_start[d2+1]
     const double* coef;   // [3 orderings][n_terms]
     CgOut out[LGAE_CG_MAX_OUT];
@@ -72,6 +73,13 @@ LGAE_DEV int out_of_comp(const CgArgs& p, int oc) {
 LGAE_DEV void stage_planar(cplx* dst, const double* src, int64_t plane, int n) {
     for (int t = threadIdx.x; t < n; t += blockDim.x) dst[t] = cmake(src[t], src[plane + t]);
 }
+// The same with one row of `rowlen` complex numbers per neighbour, rows `stride` apart.  stride = rowlen | 1 (odd): lanes
+// that split the neighbour sum of one item read the same column of consecutive rows, 16 bytes each, from different banks.
+__host__ __device__ inline int cg_row_stride(int rowlen) { return rowlen | 1; }
+LGAE_DEV void stage_rows(cplx* dst, const double* src, int64_t plane, int rows, int rowlen) {
+    const int stride = cg_row_stride(rowlen), n = rows * rowlen;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) dst[(t / rowlen) * stride + t % rowlen] = cmake(src[t], src[plane + t]);
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // aggregated product: out_i = sum_j H (z1_j (x) z2_ij);  z1 (2,B,NJ,C,d1), z2 (2,B,N,NJ,C,d2)
@@ -81,14 +89,16 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_fwd_kernel(const CgArgs p) 
     pdl_launch();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, C = p.C, d1 = p.d1, d2 = p.d2, NJ = p.NJ, JT = p.JT;
+    const int S1 = cg_row_stride(C * d1), S2 = cg_row_stride(C * d2);
     cplx* z1s = reinterpret_cast<cplx*>(smem);
-    cplx* z2s = z1s + (size_t)JT * C * d1;
+    cplx* z2s = z1s + (size_t)JT * S1;
     TermsSm T;
-    terms_load(p, 0, reinterpret_cast<double*>(z2s + (size_t)JT * C * d2), T);
+    terms_load(p, 0, reinterpret_cast<double*>(z2s + (size_t)JT * S2), T);
     pdl_wait();
     const int b = blockIdx.x, items = C * p.n_comp;
     const bool single = JT >= NJ;
-    if (single) stage_planar(z1s, p.z1 + (int64_t)b * NJ * C * d1, p.plane1, NJ * C * d1);
+    if (single) stage_rows(z1s, p.z1 + (int64_t)b * NJ * C * d1, p.plane1, NJ, C * d1);
+    const int JS = p.JS, jl = tid % JS, per_pass = CG_THREADS / JS;
     for (int i = blockIdx.y; i < p.N; i += gridDim.y) {
         cplx acc[CG_ITEMS];
 #pragma unroll
@@ -96,32 +106,39 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_fwd_kernel(const CgArgs p) 
         for (int j0 = 0; j0 < NJ; j0 += JT) {
             const int jt = min(JT, NJ - j0);
             __syncthreads();
-            if (!single) stage_planar(z1s, p.z1 + ((int64_t)b * NJ + j0) * C * d1, p.plane1, jt * C * d1);
-            stage_planar(z2s, p.z2 + (((int64_t)b * p.N + i) * NJ + j0) * C * d2, p.plane2, jt * C * d2);
+            if (!single) stage_rows(z1s, p.z1 + ((int64_t)b * NJ + j0) * C * d1, p.plane1, jt, C * d1);
+            stage_rows(z2s, p.z2 + (((int64_t)b * p.N + i) * NJ + j0) * C * d2, p.plane2, jt, C * d2);
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < CG_ITEMS; ++k) {
-                const int it = tid + k * CG_THREADS;
-                if (it >= items) break;
-                const int c = it % C, oc = it / C;
-                for (int t = T.start[oc]; t < T.start[oc + 1]; ++t) {
-                    const cplx* x = z1s + c * d1 + T.a[t];
-                    const cplx* y = z2s + c * d2 + T.d[t];
-                    cplx s = czero();
-                    for (int j = 0; j < jt; ++j) cfma(s, x[(size_t)j * C * d1], y[(size_t)j * C * d2]);
-                    cfmar(acc[k], s, T.coef[t]);
+                const int it = tid / JS + k * per_pass;
+                if (it < items) {
+                    const int c = it % C, oc = it / C;
+                    for (int t = T.start[oc]; t < T.start[oc + 1]; ++t) {
+                        const cplx* x = z1s + c * d1 + T.a[t];
+                        const cplx* y = z2s + c * d2 + T.d[t];
+                        cplx s = czero();
+                        for (int j = jl; j < jt; j += JS) cfma(s, x[j * S1], y[j * S2]);
+                        cfmar(acc[k], s, T.coef[t]);
+                    }
                 }
             }
         }
 #pragma unroll
         for (int k = 0; k < CG_ITEMS; ++k) {
-            const int it = tid + k * CG_THREADS;
-            if (it >= items) break;
-            const int c = it % C, oc = it / C;
-            const CgOut& o = p.out[out_of_comp(p, oc)];
-            const int64_t idx = (((int64_t)b * p.N + i) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
-            o.ptr[idx] = acc[k].x;
-            o.ptr[o.plane + idx] = acc[k].y;
+            // butterfly over the JS lanes of the item (fixed order); every lane of the warp takes part in the shuffles
+            for (int o = JS >> 1; o > 0; o >>= 1) {
+                acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
+                acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+            }
+            const int it = tid / JS + k * per_pass;
+            if (it < items && jl == 0) {
+                const int c = it % C, oc = it / C;
+                const CgOut& o = p.out[out_of_comp(p, oc)];
+                const int64_t idx = (((int64_t)b * p.N + i) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+                o.ptr[idx] = acc[k].x;
+                o.ptr[o.plane + idx] = acc[k].y;
+            }
         }
     }
 }
@@ -132,24 +149,26 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_kernel(const CgArgs p) 
     pdl_launch();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, C = p.C, d1 = p.d1, d2 = p.d2, NJ = p.NJ, JT = p.JT, nc = p.n_comp;
+    const int S1 = cg_row_stride(C * d1), S2 = cg_row_stride(C * d2);
     cplx* z1s = reinterpret_cast<cplx*>(smem);
-    cplx* z2s = z1s + (size_t)JT * C * d1;
-    cplx* gs = z2s + (size_t)JT * C * d2;   // C * n_comp
+    cplx* z2s = z1s + (size_t)JT * S1;
+    cplx* gs = z2s + (size_t)JT * S2;   // C * n_comp
     double* rest = reinterpret_cast<double*>(gs + (size_t)C * nc);
     TermsSm Ta, Td;
     rest += terms_load(p, 1, rest, Ta);
     terms_load(p, 2, rest, Td);
     pdl_wait();
     const int b = blockIdx.x, j0 = blockIdx.y * JT, jt = min(JT, NJ - j0);
-    stage_planar(z1s, p.z1 + ((int64_t)b * NJ + j0) * C * d1, p.plane1, jt * C * d1);
+    stage_rows(z1s, p.z1 + ((int64_t)b * NJ + j0) * C * d1, p.plane1, jt, C * d1);
     const int items1 = p.g1 ? jt * C * d1 : 0, items2 = p.g2 ? jt * C * d2 : 0;
     cplx acc[CG_ITEMS];
 #pragma unroll
     for (int k = 0; k < CG_ITEMS; ++k) acc[k] = czero();
+    const int ng = C * nc;
     for (int i = 0; i < p.N; ++i) {
         __syncthreads();
-        stage_planar(z2s, p.z2 + (((int64_t)b * p.N + i) * NJ + j0) * C * d2, p.plane2, jt * C * d2);
-        for (int t = tid; t < C * nc; t += blockDim.x) {
+        stage_rows(z2s, p.z2 + (((int64_t)b * p.N + i) * NJ + j0) * C * d2, p.plane2, jt, C * d2);
+        for (int t = tid; t < ng; t += blockDim.x) {
             const int c = t / nc, oc = t % nc;
             const CgOut& o = p.out[out_of_comp(p, oc)];
             const int64_t idx = (((int64_t)b * p.N + i) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
@@ -164,7 +183,7 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_kernel(const CgArgs p) 
             cplx s = czero();
             for (int t = Ta.start[a_]; t < Ta.start[a_ + 1]; ++t) {
                 cplx v = czero();
-                cfmac(v, z2s[((size_t)j * C + c) * d2 + Ta.d[t]], gs[c * nc + Ta.comp[t]]);
+                cfmac(v, z2s[j * S2 + c * d2 + Ta.d[t]], gs[c * nc + Ta.comp[t]]);
                 cfmar(s, v, Ta.coef[t]);
             }
             acc[k] = cadd(acc[k], s);
@@ -174,7 +193,7 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_kernel(const CgArgs p) 
             cplx s = czero();
             for (int t = Td.start[d_]; t < Td.start[d_ + 1]; ++t) {
                 cplx v = czero();
-                cfmac(v, z1s[((size_t)j * C + c) * d1 + Td.a[t]], gs[c * nc + Td.comp[t]]);
+                cfmac(v, z1s[j * S1 + c * d1 + Td.a[t]], gs[c * nc + Td.comp[t]]);
                 cfmar(s, v, Td.coef[t]);
             }
             const int64_t idx = (((int64_t)b * p.N + i) * NJ + j0) * C * d2 + it;
@@ -384,7 +403,7 @@ static int cg_fill(const LgaeCgPairDesc* d, const int32_t* tab, const double* co
     if (d->d1 < 1 || d->d2 < 1 || d->channels < 1 || d->n_out < 1 || d->n_out > LGAE_CG_MAX_OUT || d->n_terms < 1 || d->n_comp < 1)
         return LGAE_E_BADARG;
     p.C = d->channels; p.d1 = d->d1; p.d2 = d->d2; p.n_comp = d->n_comp; p.n_terms = d->n_terms; p.n_out = d->n_out;
-    p.tab = tab; p.coef = coef;
+    p.tab = tab; p.coef = coef; p.JS = 1;
     int comp = 0;
     for (int o = 0; o < d->n_out; ++o) {
         if (!ptrs[o] || d->out_comp0[o] != comp || d->out_d[o] < 1 || d->out_coffset[o] < 0 || d->out_coffset[o] + d->channels > d->out_ctotal[o])
@@ -399,7 +418,7 @@ static int cg_fill(const LgaeCgPairDesc* d, const int32_t* tab, const double* co
 }
 // neighbour tile: as many particles as fit next to the fixed part in ~160 KB, and (adjoint) CG_ITEMS*CG_THREADS z1 items
 static int cg_tile(const CgArgs& p, size_t fixed_bytes, bool bwd) {
-    const size_t per_j = (size_t)p.C * (p.d1 + p.d2) * sizeof(cplx);
+    const size_t per_j = (size_t)(cg_row_stride(p.C * p.d1) + cg_row_stride(p.C * p.d2)) * sizeof(cplx);
     const size_t budget = 160 * 1024;
     if (fixed_bytes + per_j > budget) return 0;
     int64_t jt = (int64_t)((budget - fixed_bytes) / per_j);
@@ -436,10 +455,12 @@ int lgae_cg_product_forward(const LgaeCgPairDesc* d, const int32_t* tab, const d
     p.B = (int32_t)(rows / n_nbr); p.N = n_nbr; p.NJ = n_nbr;
     p.plane1 = rows * p.C * p.d1; p.plane2 = rows * n_nbr * p.C * p.d2;
     if (p.C * p.n_comp > CG_ITEMS * CG_THREADS) return LGAE_E_UNSUPPORTED;
+    p.JS = 1;   // few output items per (jet, i): several lanes share an item and split its neighbour sum
+    while (p.JS < 32 && 2 * p.JS * p.C * p.n_comp <= CG_THREADS && 2 * p.JS <= p.NJ) p.JS *= 2;
     const size_t fixed = terms_doubles(p.n_terms, p.n_comp + 1) * sizeof(double);
     p.JT = cg_tile(p, fixed, false);
     if (p.JT < 1) return LGAE_E_UNSUPPORTED;
-    const size_t bytes = fixed + (size_t)p.JT * p.C * (p.d1 + p.d2) * sizeof(cplx);
+    const size_t bytes = fixed + (size_t)p.JT * (cg_row_stride(p.C * p.d1) + cg_row_stride(p.C * p.d2)) * sizeof(cplx);
     if (int rc = ensure_smem((const void*)cg_agg_fwd_kernel, bytes)) return rc;
     int split = (2 * sm_count() + p.B - 1) / p.B;
     split = std::max(1, std::min(split, (int)p.N));
@@ -475,7 +496,7 @@ int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const 
     const size_t fixed = terms + (size_t)p.C * p.n_comp * sizeof(cplx);
     p.JT = cg_tile(p, fixed, true);
     if (p.JT < 1) return LGAE_E_UNSUPPORTED;
-    const size_t bytes = fixed + (size_t)p.JT * p.C * (p.d1 + p.d2) * sizeof(cplx);
+    const size_t bytes = fixed + (size_t)p.JT * (cg_row_stride(p.C * p.d1) + cg_row_stride(p.C * p.d2)) * sizeof(cplx);
     if (int rc = ensure_smem((const void*)cg_agg_bwd_kernel, bytes)) return rc;
     LaunchScope ls_("cg_aggregate_bwd", st);
     launch_k(cg_agg_bwd_kernel, dim3(p.B, (p.NJ + p.JT - 1) / p.JT), dim3(CG_THREADS), bytes, st, p);

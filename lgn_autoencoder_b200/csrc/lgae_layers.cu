@@ -88,6 +88,9 @@ struct RadArgs {
 };
 constexpr int RAD_EB = 128;   // edges per block iteration
 constexpr int RAD_T = 256;
+// Row strides of the per-edge shared-memory tables, made odd: a warp that walks the edges at a fixed column then hits 16
+// different bank pairs instead of 2-4 (K2 = 20) or one (n_l * n_out = 32).
+__host__ __device__ inline int rad_odd(int n) { return n | 1; }
 
 LGAE_DEV int64_t rad_out_index(const RadArgs& p, int64_t e, int o) {
     return p.planar ? (int64_t)(o & 1) * p.E * (p.nout / 2) + e * (p.nout / 2) + (o >> 1) : e * p.nout + o;
@@ -101,8 +104,8 @@ LGAE_DEV void rad_bells(const RadArgs& p, int64_t e0, int ne, const double* pa, 
         const double cx = pc[k] * p.x[ge];
         // same operation order as the reference: (1 + (c x)^2 + 1e-16)^-1, then b * (...) + a
         const double r = 1.0 / (__dadd_rn(__dadd_rn(1.0, __dmul_rn(cx, cx)), 1e-16));
-        bell[t] = on ? __dadd_rn(__dmul_rn(pb[k], r), pa[k]) : 0.0;
-        if (rr) rr[t] = on ? r : 0.0;
+        bell[e * rad_odd(p.K2) + k] = on ? __dadd_rn(__dmul_rn(pb[k], r), pa[k]) : 0.0;
+        if (rr) rr[e * rad_odd(p.K2) + k] = on ? r : 0.0;
     }
 }
 __global__ void __launch_bounds__(RAD_T) rad_fwd_kernel(const RadArgs p) {
@@ -114,7 +117,8 @@ __global__ void __launch_bounds__(RAD_T) rad_fwd_kernel(const RadArgs p) {
     double* pc = pb + K2;
     double* ws = pc + K2;                    // L * nout * K2
     double* bs = ws + (size_t)L * nout * K2;  // L * nout
-    double* bell = bs + (size_t)L * nout;     // RAD_EB * K2
+    double* bell = bs + (size_t)L * nout;     // RAD_EB * KS
+    const int KS = rad_odd(K2);
     for (int t = threadIdx.x; t < K2; t += blockDim.x) { pa[t] = p.a[t]; pb[t] = p.b[t]; pc[t] = p.c[t]; }
     for (int l = 0; l < L; ++l) {
         for (int t = threadIdx.x; t < nout * K2; t += blockDim.x) ws[(size_t)l * nout * K2 + t] = p.w[l][t];
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(RAD_T) rad_fwd_kernel(const RadArgs p) {
             // planar: consecutive threads walk the edges of one (l, o) => coalesced stores
             const int e = t % ne, o = (t / ne) % nout, l = t / (ne * nout);
             const double* w = ws + ((size_t)l * nout + o) * K2;
-            const double* be = bell + (size_t)e * K2;
+            const double* be = bell + (size_t)e * KS;
             double acc = 0.0;
             for (int k = 0; k < K2; ++k) acc = fma(be[k], w[k], acc);
             p.out[l][rad_out_index(p, e0 + e, o)] = acc + bs[l * nout + o];
@@ -146,11 +150,12 @@ __global__ void __launch_bounds__(RAD_T) rad_bwd_kernel(const RadArgs p) {
     double* pb = pa + K2;
     double* pc = pb + K2;
     double* ws = pc + K2;                     // LO * K2
-    double* bell = ws + (size_t)LO * K2;      // RAD_EB * K2
-    double* rr = bell + (size_t)RAD_EB * K2;  // RAD_EB * K2
-    double* gb = rr + (size_t)RAD_EB * K2;    // RAD_EB * K2: d/dbell
-    double* gy = gb + (size_t)RAD_EB * K2;    // RAD_EB * LO
-    double* accs = gy + (size_t)RAD_EB * LO;  // LO*K2 + LO + 3*K2 accumulators (one owner thread each)
+    const int KS = rad_odd(K2), GS = rad_odd(LO);
+    double* bell = ws + (size_t)LO * K2;      // RAD_EB * KS
+    double* rr = bell + (size_t)RAD_EB * KS;  // RAD_EB * KS
+    double* gb = rr + (size_t)RAD_EB * KS;    // RAD_EB * KS: d/dbell
+    double* gy = gb + (size_t)RAD_EB * KS;    // RAD_EB * GS
+    double* accs = gy + (size_t)RAD_EB * GS;  // LO*K2 + LO + 3*K2 accumulators (one owner thread each)
     const int n_w = LO * K2, n_acc = n_w + LO + 3 * K2;
     for (int t = threadIdx.x; t < K2; t += blockDim.x) { pa[t] = p.a[t]; pb[t] = p.b[t]; pc[t] = p.c[t]; }
     for (int l = 0; l < L; ++l)
@@ -163,25 +168,25 @@ __global__ void __launch_bounds__(RAD_T) rad_bwd_kernel(const RadArgs p) {
         rad_bells(p, e0, ne, pa, pb, pc, bell, rr);
         for (int t = threadIdx.x; t < ne * LO; t += blockDim.x) {
             const int e = t % ne, lo = t / ne;
-            gy[(size_t)e * LO + lo] = p.out[lo / nout][rad_out_index(p, e0 + e, lo % nout)];
+            gy[(size_t)e * GS + lo] = p.out[lo / nout][rad_out_index(p, e0 + e, lo % nout)];
         }
         __syncthreads();
         // d/dbell[e, k] = sum_lo W[lo, k] gy[e, lo]   (zero on masked edges: rr == 0 there)
         for (int t = threadIdx.x; t < ne * K2; t += blockDim.x) {
             const int e = t / K2, k = t % K2;
             double acc = 0.0;
-            for (int lo = 0; lo < LO; ++lo) acc = fma(ws[(size_t)lo * K2 + k], gy[(size_t)e * LO + lo], acc);
-            gb[t] = rr[t] != 0.0 ? acc : 0.0;
+            for (int lo = 0; lo < LO; ++lo) acc = fma(ws[(size_t)lo * K2 + k], gy[(size_t)e * GS + lo], acc);
+            gb[e * KS + k] = rr[e * KS + k] != 0.0 ? acc : 0.0;
         }
         // dW[lo, k] += sum_e gy[e, lo] bell[e, k];  dbias[lo] += sum_e gy[e, lo]
         for (int t = threadIdx.x; t < n_w + LO; t += blockDim.x) {
             double acc = 0.0;
             if (t < n_w) {
                 const int lo = t / K2, k = t % K2;
-                for (int e = 0; e < ne; ++e) acc = fma(gy[(size_t)e * LO + lo], bell[(size_t)e * K2 + k], acc);
+                for (int e = 0; e < ne; ++e) acc = fma(gy[(size_t)e * GS + lo], bell[(size_t)e * KS + k], acc);
             } else {
                 const int lo = t - n_w;
-                for (int e = 0; e < ne; ++e) acc += gy[(size_t)e * LO + lo];
+                for (int e = 0; e < ne; ++e) acc += gy[(size_t)e * GS + lo];
             }
             accs[t] += acc;
         }
@@ -191,7 +196,7 @@ __global__ void __launch_bounds__(RAD_T) rad_bwd_kernel(const RadArgs p) {
             const int which = t / K2, k = t % K2;
             double acc = 0.0;
             for (int e = 0; e < ne; ++e) {
-                const double g = gb[(size_t)e * K2 + k], r = rr[(size_t)e * K2 + k];
+                const double g = gb[(size_t)e * KS + k], r = rr[(size_t)e * KS + k];
                 if (which == 0) acc += g;
                 else if (which == 1) acc = fma(g, r, acc);
                 else { const double x = p.x[e0 + e]; acc = fma(g, -2.0 * pb[k] * r * r * pc[k] * x * x, acc); }
@@ -203,8 +208,8 @@ __global__ void __launch_bounds__(RAD_T) rad_bwd_kernel(const RadArgs p) {
                 const double x = p.x[e0 + e];
                 double acc = 0.0;
                 for (int k = 0; k < K2; ++k) {
-                    const double r = rr[(size_t)e * K2 + k];
-                    acc = fma(gb[(size_t)e * K2 + k], -2.0 * pb[k] * r * r * pc[k] * pc[k] * x, acc);
+                    const double r = rr[(size_t)e * KS + k];
+                    acc = fma(gb[(size_t)e * KS + k], -2.0 * pb[k] * r * r * pc[k] * pc[k] * x, acc);
                 }
                 p.gx[e0 + e] = acc;
             }
@@ -380,7 +385,7 @@ int lgae_radial_functions_forward(const double* x, const uint8_t* mask, int64_t 
     RadArgs p = {};
     if (edges == 0) return LGAE_OK;
     if (int rc = rad_fill(p, x, mask, edges, n_mask, a, b, c, k2, n_out, n_l, w, bias, outs, planar)) return rc;
-    const size_t bytes = ((size_t)3 * k2 + (size_t)n_l * n_out * (k2 + 1) + (size_t)RAD_EB * k2) * sizeof(double);
+    const size_t bytes = ((size_t)3 * k2 + (size_t)n_l * n_out * (k2 + 1) + (size_t)RAD_EB * rad_odd(k2)) * sizeof(double);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (int rc = ensure_smem((const void*)rad_fwd_kernel, bytes)) return rc;
@@ -408,7 +413,7 @@ int lgae_radial_functions_backward(const double* x, const uint8_t* mask, int64_t
     if (int rc = rad_fill(p, x, mask, edges, n_mask, a, b, c, k2, n_out, n_l, w, w /* bias unused */, (double* const*)g_outs, planar)) return rc;
     p.gx = g_x; p.part = partials; p.part_stride = (int32_t)width;
     const int lo = n_l * n_out;
-    const size_t bytes = ((size_t)3 * k2 + (size_t)lo * k2 + (size_t)3 * RAD_EB * k2 + (size_t)RAD_EB * lo + (size_t)width) * sizeof(double);
+    const size_t bytes = ((size_t)3 * k2 + (size_t)lo * k2 + (size_t)3 * RAD_EB * rad_odd(k2) + (size_t)RAD_EB * rad_odd(lo) + (size_t)width) * sizeof(double);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)rad_bwd_kernel, bytes)) return rc;
     const int ctas = rad_ctas(edges);

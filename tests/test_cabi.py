@@ -79,7 +79,6 @@ def test_bad_arguments_are_rejected_before_any_launch():
 
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     """No CPU fallback: without the CUDA library the product import path raises."""
-    import importlib
     from lgn_autoencoder_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
@@ -89,8 +88,7 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
         assert "no CPU fallback" in str(e)
     else:
         raise AssertionError("load() must fail when the library is missing")
-    finally:
-        importlib.reload(_lib)
+    # monkeypatch restores the handle and the path (no reload: that would re-create the ctypes classes the handle is bound to)
 
 
 def test_product_never_imports_the_oracle():
@@ -104,3 +102,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py") and re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(dirpath, f)).read(), flags=re.M):
                 bad.append(f)
     assert not bad, bad
+
+
+def test_layer_level_entry_points_check_arguments_without_gpu():
+    """lgae_cg_product_* / lgae_mix_* / lgae_scalar_irrep_* / lgae_radial_functions_* / lgae_linear_*: size queries and
+    argument validation return before any CUDA call."""
+    from lgn_autoencoder_b200 import _lib
+    lib = _lib.load()
+    BADARG = -1
+    assert lib.lgae_mix_partials_doubles(-1, 4, 4) == -1 and lib.lgae_mix_partials_doubles(100, 0, 4) == -1
+    assert lib.lgae_mix_partials_doubles(10, 3, 5) == 10 * 2 * 3 * 5
+    assert lib.lgae_linear_partials_doubles(1000, 8, 0) == -1 and lib.lgae_linear_partials_doubles(100, 8, 6) == 6 * 9
+    assert lib.lgae_radial_functions_partials_doubles(-5, 20, 8, 2) == -1
+    assert lib.lgae_radial_functions_partials_doubles(128, 20, 8, 2) == 2 * 8 * 21 + 60
+    assert lib.lgae_cg_product_forward(None, None, None, None, None, 4, 0, None, None) == BADARG
+    d = _lib.LgaeCgPairDesc()
+    d.d1, d.d2, d.channels, d.n_out, d.n_comp, d.n_terms = 4, 4, 3, 17, 1, 1          # more output irreps than LGAE_CG_MAX_OUT
+    assert lib.lgae_cg_product_forward(C.byref(d), 1, 1, None, None, 4, 0, 1, None) == BADARG
+    assert lib.lgae_mix_forward(None, None, 5, 0, 3, 4, None, None) == BADARG
+    assert lib.lgae_mix_forward(None, None, 0, 2, 3, 4, None, None) == 0                # empty input: nothing to launch
+    assert lib.lgae_scalar_irrep_forward(None, None, 7, 3, 2, 4, None, None) == BADARG  # channel counts do not broadcast
+    assert lib.lgae_scalar_irrep_forward(None, None, 0, 3, 1, 4, None, None) == 0
+    assert lib.lgae_linear_forward(None, None, None, 0, 6, 36, 1, 0.01, None, None) == 0
+    assert lib.lgae_linear_forward(None, None, None, 5, 6, 36, 1, 0.01, None, None) == BADARG
+    assert lib.lgae_radial_functions_forward(None, None, 0, 1, None, None, None, 20, 8, 2, None, None, None, 1, None) == 0
