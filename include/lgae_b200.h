@@ -261,6 +261,16 @@ int lgae_linear_backward(const double* x, const double* w, const double* y, cons
                          int32_t n_out, int32_t leaky_relu, double slope, double* g_x, double* g_w, double* g_b,
                          double* partials, void* stream);
 
+/* ---- the caller of the hot path: optimizer step ------------------------------------------------------------------
+ * torch.optim.Adam (amsgrad = False) on the flat parameter / gradient buffers of up to two models in one launch
+ * (replaces optimizer_encoder.step(); optimizer_decoder.step(), utils/train.py:342-343; optimizers built in
+ * utils/initialize.py:152-158).  exp_avg / exp_avg_sq: the caller's state buffers (zero-initialised), same sizes as
+ * theta.  step_state: TWO int64 on the device, zero-initialised by the caller: [0] = number of updates done (advanced by
+ * the kernel, so the call can be replayed inside a CUDA graph), [1] = scratch. */
+int lgae_adam_step(double* theta_a, const double* grad_a, double* exp_avg_a, double* exp_avg_sq_a, int64_t n_a,
+                   double* theta_b, const double* grad_b, double* exp_avg_b, double* exp_avg_sq_b, int64_t n_b, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int64_t* step_state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,12 @@ struct MlpArgs {
 };
 
 constexpr int MLP_THREADS = 256;
+#ifndef LGAE_MLP_FWD_MT
+#define LGAE_MLP_FWD_MT 2     // row groups (of 8 rows) a warp of the forward kernel carries through the chain at a time
+#endif
+#ifndef LGAE_MLP_FWD_CTAS
+#define LGAE_MLP_FWD_CTAS 1   // resident CTAs per SM the forward kernel is compiled and launched for
+#endif
 constexpr int MLP_BWD_ROWS = 128;   // rows of a slab processed at once by the backward kernel (16 row groups)
 
 // Doubles of fragment-ordered weights of layer l (tiles padded to 8).
@@ -90,7 +96,7 @@ LGAE_DEV void layer_mma(const double (&act)[MT][KT][2], double (&acc)[MT][NO][2]
 // forward
 // ------------------------------------------------------------------------------------------------------------
 template <int NTW, int NTI>
-__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpArgs a) {
+__global__ void __launch_bounds__(MLP_THREADS, LGAE_MLP_FWD_CTAS) mlp_fwd_kernel(const MlpArgs a) {
     extern __shared__ __align__(128) double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_fwd_kernel(const MlpArgs a
     }
     __syncthreads();
     // ---- row groups of 8: a contiguous range per CTA, each warp takes MT = 2 consecutive groups at a time ----
-    constexpr int MT = 2;
+    constexpr int MT = LGAE_MLP_FWD_MT;
     const int64_t ngroups = (a.rows + 7) / 8;
     const int64_t per_cta = (ngroups + gridDim.x - 1) / gridDim.x;
     const int64_t g_begin = (int64_t)blockIdx.x * per_cta, g_end = g_begin + per_cta < ngroups ? g_begin + per_cta : ngroups;
@@ -502,7 +508,8 @@ static int launch_mlp(MlpArgs& a, bool bwd, cudaStream_t st) {
         auto kern = mlp_fwd_kernel<NTW, NTI>;
         if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
         const int64_t ngroups = (a.rows + 7) / 8;
-        const int grid = (int)(ngroups < sm_count() ? ngroups : sm_count());
+        const int cap = LGAE_MLP_FWD_CTAS * sm_count();
+        const int grid = (int)(ngroups < cap ? ngroups : cap);
         LaunchScope ls_("mlp_fwd", st);
         launch_k(kern, dim3(grid), dim3(MLP_THREADS), bytes, st, a);
         return check_launch("mlp_fwd");

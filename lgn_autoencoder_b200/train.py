@@ -104,6 +104,8 @@ class FusedTrainStep:
         self.g_all = torch.zeros(off_d + self.pd.n_params, **f64)
         self.g_e = self.g_all[:self.pe.n_params]
         self.g_d = self.g_all[off_d:]
+        self.optimizer = None
+        self._probe = (next(encoder.parameters()), next(decoder.parameters()))
         self._bind_grads()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
@@ -135,6 +137,15 @@ class FusedTrainStep:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size
             dist.all_reduce(self.g_all, op=dist.ReduceOp.SUM, group=self.group)
+        if self.optimizer is not None:
+            self.optimizer.step()
+
+    def attach_optimizer(self, optimizer):
+        """Make ``optimizer.step()`` (a ``FlatAdam``) the last node of the step: gradients -> (all-reduce) -> parameter update in
+        one launch sequence / one CUDA graph.  ``None`` detaches."""
+        self.optimizer = optimizer
+        self.graph = None
+        self.graph_host = None
 
     def _params_moved(self) -> bool:
         """Cheap per-step check (a few attribute reads): the flat buffers the captured kernels read are still the models'.
@@ -157,8 +168,15 @@ class FusedTrainStep:
         if self.mask is not None and labels is not None:
             self.mask.copy_((labels != 0).to(torch.uint8), non_blocking=True)
 
+    def _check_grads(self):
+        """optimizer.zero_grad() (set_to_none=True is torch's default) drops ``param.grad``: point them at the bucket again,
+        otherwise optimizer.step() would silently skip every parameter.  O(1): looks at one parameter per model."""
+        if self._probe[0].grad is None or self._probe[1].grad is None:
+            self._bind_grads()
+
     def run(self):
         """Run the step on the jets already in the static input buffer."""
+        self._check_grads()
         if not self.use_graph:
             self._launch()
             return self.loss
@@ -167,7 +185,11 @@ class FusedTrainStep:
             s = torch.cuda.Stream()
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self._launch()
+                opt, self.optimizer = self.optimizer, None   # the warm-up run must not update the parameters
+                try:
+                    self._launch()
+                finally:
+                    self.optimizer = opt
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
@@ -191,6 +213,7 @@ class FusedTrainStep:
     def step_host(self, p4=None, labels=None) -> float:
         """End-to-end step from host memory: jets (B,N,4) are staged in the pinned buffer ``host_p4`` (pass ``p4=None`` if the
         data loader already wrote them there), copied to the device, the step runs, and the loss comes back as a float."""
+        self._check_grads()
         if p4 is not None and p4.data_ptr() != self.host_p4.data_ptr():
             self.host_p4.copy_(p4)
         if self.host_mask is not None and labels is not None:
@@ -202,7 +225,11 @@ class FusedTrainStep:
                 s = torch.cuda.Stream()
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
-                    self._launch_host()
+                    opt, self.optimizer = self.optimizer, None   # the warm-up run must not update the parameters
+                    try:
+                        self._launch_host()
+                    finally:
+                        self.optimizer = opt
                 torch.cuda.current_stream().wait_stream(s)
                 torch.cuda.synchronize()
                 self.graph_host = torch.cuda.CUDAGraph()
@@ -212,6 +239,49 @@ class FusedTrainStep:
             self.graph_host.replay()
         torch.cuda.current_stream().synchronize()
         return float(self.host_loss)
+
+
+class FlatAdam:
+    """``torch.optim.Adam`` (amsgrad=False) for the two models of a ``FusedTrainStep`` as ONE kernel launch per step
+    (``lgae_adam_step``) on the flat parameter buffers and the step's flat gradient bucket, instead of two optimizers looping
+    over ~130 tensors each (reference: utils/initialize.py:152-158, utils/train.py:342-343).  The step count lives on the
+    device, so ``step()`` may be captured in a CUDA graph together with the training step.
+
+    State (``exp_avg``, ``exp_avg_sq`` per model, flat) is exposed through ``state_dict()`` / ``load_state_dict()``."""
+
+    def __init__(self, step: "FusedTrainStep", lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+        if lr < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or eps < 0:
+            raise ValueError("invalid Adam hyper-parameters")
+        self.fs, self.lr, self.betas, self.eps, self.weight_decay = step, float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        dev = step.dev
+        self.exp_avg = [torch.zeros(step.pe.n_params, dtype=torch.float64, device=dev), torch.zeros(step.pd.n_params, dtype=torch.float64, device=dev)]
+        self.exp_avg_sq = [torch.zeros_like(self.exp_avg[0]), torch.zeros_like(self.exp_avg[1])]
+        self.step_state = torch.zeros(2, dtype=torch.int64, device=dev)   # [updates done, launch counter]
+        self.lib = _lib.load()
+
+    def step(self):
+        fs = self.fs
+        th_e, th_d = fs.enc._theta, fs.dec._theta
+        if th_e is None or th_d is None or fs._params_moved():   # cheap pointer check; full re-validation only when needed
+            th_e, _ = fs.enc._flat_params()
+            th_d, _ = fs.dec._flat_params()
+        check(self.lib.lgae_adam_step(ptr(th_e), ptr(fs.g_e), ptr(self.exp_avg[0]), ptr(self.exp_avg_sq[0]), fs.pe.n_params,
+                                      ptr(th_d), ptr(fs.g_d), ptr(self.exp_avg[1]), ptr(self.exp_avg_sq[1]), fs.pd.n_params,
+                                      self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, ptr(self.step_state),
+                                      torch.cuda.current_stream().cuda_stream), "adam_step")
+
+    def zero_grad(self, set_to_none: bool = False):
+        """No-op: the training step overwrites the gradient bucket."""
+
+    def state_dict(self):
+        return {"step": int(self.step_state[0].item()), "exp_avg": [t.clone() for t in self.exp_avg], "exp_avg_sq": [t.clone() for t in self.exp_avg_sq],
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay}
+
+    def load_state_dict(self, sd):
+        self.step_state[0] = int(sd["step"])
+        for dst, src in zip(self.exp_avg + self.exp_avg_sq, list(sd["exp_avg"]) + list(sd["exp_avg_sq"])):
+            dst.copy_(src)
+        self.lr, self.betas, self.eps, self.weight_decay = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
 
 
 class FusedInference:

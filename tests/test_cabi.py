@@ -126,3 +126,12 @@ def test_layer_level_entry_points_check_arguments_without_gpu():
     assert lib.lgae_linear_forward(None, None, None, 0, 6, 36, 1, 0.01, None, None) == 0
     assert lib.lgae_linear_forward(None, None, None, 5, 6, 36, 1, 0.01, None, None) == BADARG
     assert lib.lgae_radial_functions_forward(None, None, 0, 1, None, None, None, 20, 8, 2, None, None, None, 1, None) == 0
+
+
+def test_adam_entry_point_checks_arguments_without_gpu():
+    from lgn_autoencoder_b200 import _lib
+    lib = _lib.load()
+    assert lib.lgae_adam_step(None, None, None, None, 0, None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, None, None) == -1   # no step state
+    assert lib.lgae_adam_step(None, None, None, None, 0, None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 8, None) == 0      # nothing to update
+    assert lib.lgae_adam_step(None, None, None, None, 5, None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 8, None) == -1     # NULL buffers
+    assert lib.lgae_adam_step(None, None, None, None, 0, None, None, None, None, 0, 1e-3, 1.0, 0.999, 1e-8, 0.0, 8, None) == -1     # beta1 == 1

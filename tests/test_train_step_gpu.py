@@ -101,3 +101,44 @@ def test_fused_inference_matches_module_forward_and_oracle_at_150_particles():
     for b in range(2):
         s = orc.chamfer_loss(x[b:b + 1], pn[b:b + 1]).item()
         assert abs(scores[b].item() - s) <= 1e-10 * abs(s)
+
+
+@pytest.mark.parametrize("in_graph", [False, True])
+def test_flat_adam_matches_torch_adam(in_graph):
+    """FlatAdam (one launch for both models, optionally a node of the step's CUDA graph) follows torch.optim.Adam on the same
+    gradients for several steps; a caller's zero_grad(set_to_none=True) does not detach the gradient views."""
+    from lgn_autoencoder_b200.train import FlatAdam, FusedTrainStep
+    dev = torch.device("cuda:0")
+    g, enc_a, dec_a, batch = load("cfg1_b3", dev)
+    _, enc_b, dec_b, _ = load("cfg1_b3", dev)
+    b = batch["p4"].shape[0]
+    lr, wd = 3e-3, 1e-2
+    sa = FusedTrainStep(enc_a, dec_a, b, l1_lambda=1e-8, normalize=True, use_graph=True)
+    opts = [torch.optim.Adam(enc_a.parameters(), lr, weight_decay=wd), torch.optim.Adam(dec_a.parameters(), lr, weight_decay=wd)]
+    sb = FusedTrainStep(enc_b, dec_b, b, l1_lambda=1e-8, normalize=True, use_graph=True)
+    flat = FlatAdam(sb, lr=lr, weight_decay=wd)
+    if in_graph:
+        sb.attach_optimizer(flat)
+    losses_a, losses_b = [], []
+    for it in range(5):
+        for o in opts:
+            o.zero_grad()                       # set_to_none=True: FusedTrainStep must re-bind its gradient views
+        losses_a.append(sa.step(batch["p4"]).item())
+        for o in opts:
+            o.step()
+        losses_b.append(sb.step(batch["p4"]).item())
+        if not in_graph:
+            flat.step()
+    torch.cuda.synchronize()
+    assert losses_a[0] == losses_b[0] and losses_a[-1] != losses_a[0]
+    for x, y in zip(losses_a, losses_b):
+        assert abs(x - y) <= 1e-11 * abs(x)
+    assert int(flat.step_state[0].item()) == 5 and int(flat.step_state[1].item()) == 0
+    for (k, pa), (_, pb) in zip(list(enc_a.named_parameters()) + list(dec_a.named_parameters()),
+                                list(enc_b.named_parameters()) + list(dec_b.named_parameters())):
+        assert rel_err(pb, pa) < 1e-11, k
+    # optimizer state round trip
+    sd = flat.state_dict()
+    flat2 = FlatAdam(sb, lr=1.0)
+    flat2.load_state_dict(sd)
+    assert flat2.lr == lr and int(flat2.step_state[0].item()) == 5 and torch.equal(flat2.exp_avg[1], flat.exp_avg[1])

@@ -4,7 +4,7 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/.."
 objs=""
-for f in lgae_api lgae_glue lgae_level lgae_radial lgae_mlp lgae_cg lgae_layers; do
+for f in lgae_api lgae_glue lgae_level lgae_radial lgae_mlp lgae_cg lgae_layers lgae_optim; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c lgn_autoencoder_b200/csrc/$f.cu -o /tmp/var_${name}_$f.o &
   objs="$objs /tmp/var_${name}_$f.o"
 done
