@@ -270,6 +270,11 @@ int lgae_linear_backward(const double* x, const double* w, const double* y, cons
 int lgae_adam_step(double* theta_a, const double* grad_a, double* exp_avg_a, double* exp_avg_sq_a, int64_t n_a,
                    double* theta_b, const double* grad_b, double* exp_avg_b, double* exp_avg_sq_b, int64_t n_b, double lr,
                    double beta1, double beta2, double eps, double weight_decay, int64_t* step_state, void* stream);
+/* torch.optim.RMSprop (centered = False), the reference's other optimizer choice (utils/initialize.py:159-165: momentum 0.9):
+ * same flat layout; momentum_buf_* may be NULL when momentum == 0. */
+int lgae_rmsprop_step(double* theta_a, const double* grad_a, double* square_avg_a, double* momentum_buf_a, int64_t n_a,
+                      double* theta_b, const double* grad_b, double* square_avg_b, double* momentum_buf_b, int64_t n_b,
+                      double lr, double alpha, double eps, double momentum, double weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

@@ -284,6 +284,36 @@ class FlatAdam:
         self.lr, self.betas, self.eps, self.weight_decay = float(sd["lr"]), tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
 
 
+class FlatRMSprop:
+    """``torch.optim.RMSprop`` (centered=False) for both models of a ``FusedTrainStep`` as one launch per step
+    (``lgae_rmsprop_step``); the reference builds it with ``eps = get_eps(dtype)`` and ``momentum = 0.9``
+    (utils/initialize.py:159-165)."""
+
+    def __init__(self, step: "FusedTrainStep", lr: float = 1e-2, alpha: float = 0.99, eps: float = 1e-8, weight_decay: float = 0.0,
+                 momentum: float = 0.0):
+        if lr < 0 or alpha < 0 or eps < 0 or momentum < 0:
+            raise ValueError("invalid RMSprop hyper-parameters")
+        self.fs, self.lr, self.alpha, self.eps, self.weight_decay, self.momentum = step, float(lr), float(alpha), float(eps), float(weight_decay), float(momentum)
+        dev = step.dev
+        self.square_avg = [torch.zeros(step.pe.n_params, dtype=torch.float64, device=dev), torch.zeros(step.pd.n_params, dtype=torch.float64, device=dev)]
+        self.momentum_buf = [torch.zeros_like(t) for t in self.square_avg] if momentum > 0 else [None, None]
+        self.lib = _lib.load()
+
+    def step(self):
+        fs = self.fs
+        th_e, th_d = fs.enc._theta, fs.dec._theta
+        if th_e is None or th_d is None or fs._params_moved():
+            th_e, _ = fs.enc._flat_params()
+            th_d, _ = fs.dec._flat_params()
+        check(self.lib.lgae_rmsprop_step(ptr(th_e), ptr(fs.g_e), ptr(self.square_avg[0]), ptr(self.momentum_buf[0]), fs.pe.n_params,
+                                         ptr(th_d), ptr(fs.g_d), ptr(self.square_avg[1]), ptr(self.momentum_buf[1]), fs.pd.n_params,
+                                         self.lr, self.alpha, self.eps, self.momentum, self.weight_decay,
+                                         torch.cuda.current_stream().cuda_stream), "rmsprop_step")
+
+    def zero_grad(self, set_to_none: bool = False):
+        """No-op: the training step overwrites the gradient bucket."""
+
+
 class FusedInference:
     """Forward-only pass (encoder -> decoder -> per-jet chamfer score) for a fixed batch size on static buffers, replayed as one
     CUDA graph: the inference / anomaly-scoring path (test.py:57-95, utils/jet_analysis/anomaly_detection.py chamfer score).

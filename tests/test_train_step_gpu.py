@@ -142,3 +142,26 @@ def test_flat_adam_matches_torch_adam(in_graph):
     flat2 = FlatAdam(sb, lr=1.0)
     flat2.load_state_dict(sd)
     assert flat2.lr == lr and int(flat2.step_state[0].item()) == 5 and torch.equal(flat2.exp_avg[1], flat.exp_avg[1])
+
+
+def test_flat_rmsprop_matches_torch_rmsprop():
+    """The reference's other optimizer choice (momentum 0.9) on the flat buffers, one launch for both models."""
+    from lgn_autoencoder_b200.train import FlatRMSprop, FusedTrainStep
+    dev = torch.device("cuda:0")
+    g, enc_a, dec_a, batch = load("cfg1_b3", dev)
+    _, enc_b, dec_b, _ = load("cfg1_b3", dev)
+    b = batch["p4"].shape[0]
+    kw = dict(lr=2e-3, eps=1e-16, momentum=0.9)
+    sa = FusedTrainStep(enc_a, dec_a, b, l1_lambda=1e-8, use_graph=True)
+    opts = [torch.optim.RMSprop(enc_a.parameters(), **kw), torch.optim.RMSprop(dec_a.parameters(), **kw)]
+    sb = FusedTrainStep(enc_b, dec_b, b, l1_lambda=1e-8, use_graph=True)
+    sb.attach_optimizer(FlatRMSprop(sb, **kw))
+    for it in range(4):
+        la = sa.step(batch["p4"]).item()
+        for o in opts:
+            o.step()
+        lb = sb.step(batch["p4"]).item()
+        assert abs(la - lb) <= 1e-10 * abs(la)
+    for (k, pa), (_, pb) in zip(list(enc_a.named_parameters()) + list(dec_a.named_parameters()),
+                                list(enc_b.named_parameters()) + list(dec_b.named_parameters())):
+        assert rel_err(pb, pa) < 1e-10, k
