@@ -144,6 +144,8 @@ static SideStream* side_stream() {
     static const bool on = [] { const char* e = getenv("LGAE_OVERLAP"); return e && e[0] == '1'; }();
     if (!on) return nullptr;
     static std::unordered_map<int, SideStream*> per_dev;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     auto it = per_dev.find(dev);
