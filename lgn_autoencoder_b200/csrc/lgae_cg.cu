@@ -143,6 +143,41 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_fwd_kernel(const CgArgs p) 
     }
 }
 
+// Whole-jet variant (the common case: the jet's node slab and IB rows of the edge tensor fit in shared memory):
+// grid (B, ceil(N / IB)), no loop and no barrier after the single staging step; a thread owns one (i, channel, output
+// component) and runs the whole neighbour sum.  p.JT holds IB.
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_fwd_block_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, d1 = p.d1, d2 = p.d2, NJ = p.NJ, IB = p.JT;
+    cplx* z1s = reinterpret_cast<cplx*>(smem);
+    cplx* z2s = z1s + (size_t)NJ * C * d1;
+    TermsSm T;
+    terms_load(p, 0, reinterpret_cast<double*>(z2s + (size_t)IB * NJ * C * d2), T);
+    pdl_wait();
+    const int b = blockIdx.x, i0 = blockIdx.y * IB, ib = min(IB, p.N - i0), items = C * p.n_comp;
+    stage_planar(z1s, p.z1 + (int64_t)b * NJ * C * d1, p.plane1, NJ * C * d1);
+    stage_planar(z2s, p.z2 + ((int64_t)b * p.N + i0) * NJ * C * d2, p.plane2, ib * NJ * C * d2);
+    __syncthreads();
+    for (int it = tid; it < ib * items; it += CG_THREADS) {
+        const int il = it / items, w = it % items, c = w % C, oc = w / C;
+        const cplx* xb = z1s + c * d1;
+        const cplx* yb = z2s + ((size_t)il * NJ * C + c) * d2;
+        cplx acc = czero();
+        for (int t = T.start[oc]; t < T.start[oc + 1]; ++t) {
+            const cplx* x = xb + T.a[t];
+            const cplx* y = yb + T.d[t];
+            cplx s = czero();
+            for (int j = 0; j < NJ; ++j) cfma(s, x[(size_t)j * C * d1], y[(size_t)j * C * d2]);
+            cfmar(acc, s, T.coef[t]);
+        }
+        const CgOut& o = p.out[out_of_comp(p, oc)];
+        const int64_t idx = (((int64_t)b * p.N + i0 + il) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+        o.ptr[idx] = acc.x;
+        o.ptr[o.plane + idx] = acc.y;
+    }
+}
+
 // Adjoint.  grid (B, neighbour tiles): the CTA owns the gradient of its z1 tile (registers) and writes the gradient of
 // the z2 entries (i, tile) for every i.  Every sum has a fixed order.
 __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_kernel(const CgArgs p) {
@@ -217,6 +252,49 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_kernel(const CgArgs p) 
         } else {
             p.g1[idx] = acc[k].x;
             p.g1[p.plane1 + idx] = acc[k].y;
+        }
+    }
+}
+
+// Gradient of the edge operand alone: dL/dz2[i, j] = sum_terms coef conj(z1_j) g_i needs no neighbour sum and no z2, so it is
+// a fully parallel kernel over (jet, block of IB particles i): node slab + IB rows of output gradients in shared memory,
+// one thread per (i, j, c, d), stores contiguous in the edge tensor's layout.  p.JT holds IB.
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_edge_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, d1 = p.d1, d2 = p.d2, NJ = p.NJ, IB = p.JT, nc = p.n_comp;
+    cplx* z1s = reinterpret_cast<cplx*>(smem);
+    cplx* gs = z1s + (size_t)NJ * C * d1;   // IB * C * n_comp
+    TermsSm Td;
+    terms_load(p, 2, reinterpret_cast<double*>(gs + (size_t)IB * C * nc), Td);
+    pdl_wait();
+    const int b = blockIdx.x, i0 = blockIdx.y * IB, ib = min(IB, p.N - i0);
+    stage_planar(z1s, p.z1 + (int64_t)b * NJ * C * d1, p.plane1, NJ * C * d1);
+    for (int t = tid; t < ib * C * nc; t += blockDim.x) {
+        const int il = t / (C * nc), w = t % (C * nc), c = w / nc, oc = w % nc;
+        const CgOut& o = p.out[out_of_comp(p, oc)];
+        const int64_t idx = (((int64_t)b * p.N + i0 + il) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+        gs[t] = cmake(o.ptr[idx], o.ptr[o.plane + idx]);
+    }
+    __syncthreads();
+    const int per_i = NJ * C * d2;
+    double* g2 = p.g2 + ((int64_t)b * p.N + i0) * per_i;
+    for (int it = tid; it < ib * per_i; it += CG_THREADS) {
+        const int il = it / per_i, w = it % per_i, d_ = w % d2, c = (w / d2) % C, j = w / (d2 * C);
+        const cplx* gi = gs + ((size_t)il * C + c) * nc;
+        const cplx* zj = z1s + ((size_t)j * C + c) * d1;
+        cplx sum = czero();
+        for (int t = Td.start[d_]; t < Td.start[d_ + 1]; ++t) {
+            cplx v = czero();
+            cfmac(v, zj[Td.a[t]], gi[Td.comp[t]]);
+            cfmar(sum, v, Td.coef[t]);
+        }
+        if (p.acc2) {
+            g2[it] += sum.x;
+            g2[p.plane2 + it] += sum.y;
+        } else {
+            g2[it] = sum.x;
+            g2[p.plane2 + it] = sum.y;
         }
     }
 }
@@ -455,6 +533,22 @@ int lgae_cg_product_forward(const LgaeCgPairDesc* d, const int32_t* tab, const d
     p.B = (int32_t)(rows / n_nbr); p.N = n_nbr; p.NJ = n_nbr;
     p.plane1 = rows * p.C * p.d1; p.plane2 = rows * n_nbr * p.C * p.d2;
     if (p.C * p.n_comp > CG_ITEMS * CG_THREADS) return LGAE_E_UNSUPPORTED;
+    {
+        // whole-jet variant when the node slab + at least one edge row block fit next to the term table
+        const size_t fixed0 = terms_doubles(p.n_terms, p.n_comp + 1) * sizeof(double);
+        const size_t z1b = (size_t)p.NJ * p.C * p.d1 * sizeof(cplx), rowb = (size_t)p.NJ * p.C * p.d2 * sizeof(cplx), budget = 100 * 1024;
+        if (fixed0 + z1b + rowb <= budget) {
+            int ib = std::max(1, CG_THREADS / (p.C * p.n_comp));
+            ib = std::min<int>(ib, p.N);
+            while (ib > 1 && fixed0 + z1b + ib * rowb > budget) --ib;
+            p.JT = ib;
+            const size_t bytes = fixed0 + z1b + ib * rowb;
+            if (int rc = ensure_smem((const void*)cg_agg_fwd_block_kernel, bytes)) return rc;
+            LaunchScope ls_("cg_aggregate_fwd", st);
+            launch_k(cg_agg_fwd_block_kernel, dim3(p.B, (p.N + ib - 1) / ib), dim3(CG_THREADS), bytes, st, p);
+            return check_launch("cg_aggregate_fwd");
+        }
+    }
     p.JS = 1;   // few output items per (jet, i): several lanes share an item and split its neighbour sum
     while (p.JS < 32 && 2 * p.JS * p.C * p.n_comp <= CG_THREADS && 2 * p.JS <= p.NJ) p.JS *= 2;
     const size_t fixed = terms_doubles(p.n_terms, p.n_comp + 1) * sizeof(double);
@@ -493,6 +587,23 @@ int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const 
     p.B = (int32_t)(rows / n_nbr); p.N = n_nbr; p.NJ = n_nbr;
     p.plane1 = rows * p.C * p.d1; p.plane2 = rows * n_nbr * p.C * p.d2;
     if (p.C * p.d1 > CG_ITEMS * CG_THREADS) return LGAE_E_UNSUPPORTED;
+    if (p.g2) {
+        // the edge gradient as its own fully parallel launch when the jet's node slab fits in shared memory
+        const int ib = std::min<int>(8, p.N);
+        const size_t bytes = terms_doubles(p.n_terms, p.d2 + 1) * sizeof(double) + ((size_t)p.NJ * p.C * p.d1 + (size_t)ib * p.C * p.n_comp) * sizeof(cplx);
+        if (bytes <= 100 * 1024) {
+            CgArgs q = p;
+            q.JT = ib; q.g1 = nullptr;
+            if (int rc = ensure_smem((const void*)cg_agg_bwd_edge_kernel, bytes)) return rc;
+            {
+                LaunchScope ls_("cg_aggregate_bwd_edge", st);
+                launch_k(cg_agg_bwd_edge_kernel, dim3(q.B, (q.N + ib - 1) / ib), dim3(CG_THREADS), bytes, st, q);
+                if (int rc = check_launch("cg_aggregate_bwd_edge")) return rc;
+            }
+            p.g2 = nullptr;
+            if (!p.g1) return LGAE_OK;
+        }
+    }
     const size_t fixed = terms + (size_t)p.C * p.n_comp * sizeof(cplx);
     p.JT = cg_tile(p, fixed, true);
     if (p.JT < 1) return LGAE_E_UNSUPPORTED;

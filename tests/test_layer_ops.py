@@ -84,7 +84,7 @@ def _check(ref, out, g_ref, g_out):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("maxdim,C,B,N", [(2, 3, 2, 5), (3, 3, 2, 5), (3, 8, 2, 40)])
+@pytest.mark.parametrize("maxdim,C,B,N", [(2, 3, 2, 5), (3, 3, 2, 5), (3, 8, 2, 40), (3, 4, 1, 150)])   # N = 150: neighbour-tiled kernels
 def test_cg_aggregate_matches_oracle(maxdim, C, B, N):
     gen = torch.Generator().manual_seed(maxdim * 100 + C)
     irreps = [(0, 0), (1, 1)] + ([(0, 2), (2, 0), (2, 2)] if maxdim == 3 else [])
