@@ -178,6 +178,53 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_fwd_block_kernel(const CgAr
     }
 }
 
+// Kronecker-sum form of the whole-jet variant for the common edge dimensions D2 (1, 3, 4, 9): phase 1 builds
+// K[a][d] = sum_j z1_j[a] z2_ij[d] per (i, channel) with the d axis in registers (one z1 load + D2 z2 loads per D2 complex
+// FMAs instead of two loads per FMA, and d1*d2 products instead of one per CG term); phase 2 applies the CG matrix,
+// out[m] = sum_terms coef K[a][d].  Same grid, staging and p.JT = IB as cg_agg_fwd_block_kernel.
+template <int D2>
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_fwd_kron_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, d1 = p.d1, NJ = p.NJ, IB = p.JT;
+    cplx* z1s = reinterpret_cast<cplx*>(smem);
+    cplx* z2s = z1s + (size_t)NJ * C * d1;
+    cplx* ks = z2s + (size_t)IB * NJ * C * D2;   // IB * C * d1 * D2
+    TermsSm T;
+    terms_load(p, 0, reinterpret_cast<double*>(ks + (size_t)IB * C * d1 * D2), T);
+    pdl_wait();
+    const int b = blockIdx.x, i0 = blockIdx.y * IB, ib = min(IB, p.N - i0), items = C * p.n_comp;
+    stage_planar(z1s, p.z1 + (int64_t)b * NJ * C * d1, p.plane1, NJ * C * d1);
+    stage_planar(z2s, p.z2 + ((int64_t)b * p.N + i0) * NJ * C * D2, p.plane2, ib * NJ * C * D2);
+    __syncthreads();
+    for (int it = tid; it < ib * C * d1; it += CG_THREADS) {   // (il, c, a), a fastest
+        const int a_ = it % d1, c = (it / d1) % C, il = it / (d1 * C);
+        const cplx* x = z1s + c * d1 + a_;
+        const cplx* y = z2s + ((size_t)il * NJ * C + c) * D2;
+        cplx acc[D2];
+#pragma unroll
+        for (int d = 0; d < D2; ++d) acc[d] = czero();
+        for (int j = 0; j < NJ; ++j) {
+            const cplx xv = x[(size_t)j * C * d1];
+#pragma unroll
+            for (int d = 0; d < D2; ++d) cfma(acc[d], xv, y[(size_t)j * C * D2 + d]);
+        }
+#pragma unroll
+        for (int d = 0; d < D2; ++d) ks[(size_t)it * D2 + d] = acc[d];
+    }
+    __syncthreads();
+    for (int it = tid; it < ib * items; it += CG_THREADS) {
+        const int il = it / items, w = it % items, c = w % C, oc = w / C;
+        const cplx* k = ks + ((size_t)il * C + c) * d1 * D2;
+        cplx acc = czero();
+        for (int t = T.start[oc]; t < T.start[oc + 1]; ++t) cfmar(acc, k[T.a[t] * D2 + T.d[t]], T.coef[t]);
+        const CgOut& o = p.out[out_of_comp(p, oc)];
+        const int64_t idx = (((int64_t)b * p.N + i0 + il) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+        o.ptr[idx] = acc.x;
+        o.ptr[o.plane + idx] = acc.y;
+    }
+}
+
 // Adjoint.  grid (B, neighbour tiles): the CTA owns the gradient of its z1 tile (registers) and writes the gradient of
 // the z2 entries (i, tile) for every i.  Every sum has a fixed order.
 __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_kernel(const CgArgs p) {
@@ -295,6 +342,65 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_edge_kernel(const CgArg
         } else {
             g2[it] = sum.x;
             g2[p.plane2 + it] = sum.y;
+        }
+    }
+}
+
+// Kronecker form of the edge gradient: gK[a][d] = sum_terms coef g[m] (the transposed CG matrix applied to the output
+// gradient) per (i, channel), then dL/dz2[i, j][d] = sum_a conj(z1_j[a]) gK[a][d] with the d axis in registers.
+template <int D2>
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_edge_kron_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, d1 = p.d1, NJ = p.NJ, IB = p.JT, nc = p.n_comp;
+    cplx* z1s = reinterpret_cast<cplx*>(smem);
+    cplx* gs = z1s + (size_t)NJ * C * d1;        // IB * C * n_comp
+    cplx* gk = gs + (size_t)IB * C * nc;         // IB * C * d1 * D2
+    TermsSm Ta;
+    terms_load(p, 1, reinterpret_cast<double*>(gk + (size_t)IB * C * d1 * D2), Ta);
+    pdl_wait();
+    const int b = blockIdx.x, i0 = blockIdx.y * IB, ib = min(IB, p.N - i0);
+    stage_planar(z1s, p.z1 + (int64_t)b * NJ * C * d1, p.plane1, NJ * C * d1);
+    for (int t = tid; t < ib * C * nc; t += blockDim.x) {
+        const int il = t / (C * nc), w = t % (C * nc), c = w / nc, oc = w % nc;
+        const CgOut& o = p.out[out_of_comp(p, oc)];
+        const int64_t idx = (((int64_t)b * p.N + i0 + il) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+        gs[t] = cmake(o.ptr[idx], o.ptr[o.plane + idx]);
+    }
+    __syncthreads();
+    for (int it = tid; it < ib * C * d1 * D2; it += CG_THREADS) {   // (il, c, a, d)
+        const int d_ = it % D2, a_ = (it / D2) % d1, ic = it / (D2 * d1);
+        const cplx* g = gs + (size_t)ic * nc;
+        cplx acc = czero();
+        for (int t = Ta.start[a_]; t < Ta.start[a_ + 1]; ++t)
+            if (Ta.d[t] == d_) cfmar(acc, g[Ta.comp[t]], Ta.coef[t]);
+        gk[it] = acc;
+    }
+    __syncthreads();
+    const int per_i = NJ * C;
+    double* g2 = p.g2 + ((int64_t)b * p.N + i0) * per_i * D2;
+    for (int it = tid; it < ib * per_i; it += CG_THREADS) {   // (il, j, c), c fastest
+        const int il = it / per_i, w = it % per_i, c = w % C, j = w / C;
+        const cplx* zj = z1s + ((size_t)j * C + c) * d1;
+        const cplx* k = gk + ((size_t)il * C + c) * d1 * D2;
+        cplx acc[D2];
+#pragma unroll
+        for (int d = 0; d < D2; ++d) acc[d] = czero();
+        for (int a_ = 0; a_ < d1; ++a_) {
+            const cplx xv = zj[a_];
+#pragma unroll
+            for (int d = 0; d < D2; ++d) cfmac(acc[d], xv, k[a_ * D2 + d]);
+        }
+#pragma unroll
+        for (int d = 0; d < D2; ++d) {
+            const int64_t o = (int64_t)it * D2 + d;
+            if (p.acc2) {
+                g2[o] += acc[d].x;
+                g2[p.plane2 + o] += acc[d].y;
+            } else {
+                g2[o] = acc[d].x;
+                g2[p.plane2 + o] = acc[d].y;
+            }
         }
     }
 }
@@ -542,10 +648,20 @@ int lgae_cg_product_forward(const LgaeCgPairDesc* d, const int32_t* tab, const d
             ib = std::min<int>(ib, p.N);
             while (ib > 1 && fixed0 + z1b + ib * rowb > budget) --ib;
             p.JT = ib;
+            const size_t kb = (size_t)ib * p.C * p.d1 * p.d2 * sizeof(cplx);
             const size_t bytes = fixed0 + z1b + ib * rowb;
-            if (int rc = ensure_smem((const void*)cg_agg_fwd_block_kernel, bytes)) return rc;
+            const dim3 grid(p.B, (p.N + ib - 1) / ib);
             LaunchScope ls_("cg_aggregate_fwd", st);
-            launch_k(cg_agg_fwd_block_kernel, dim3(p.B, (p.N + ib - 1) / ib), dim3(CG_THREADS), bytes, st, p);
+#define LGAE_KRON(D)                                                                                  \
+    if (p.d2 == D) {                                                                                  \
+        if (int rc = ensure_smem((const void*)cg_agg_fwd_kron_kernel<D>, bytes + kb)) return rc;      \
+        launch_k(cg_agg_fwd_kron_kernel<D>, grid, dim3(CG_THREADS), bytes + kb, st, p);               \
+        return check_launch("cg_aggregate_fwd");                                                      \
+    }
+            LGAE_KRON(1) LGAE_KRON(3) LGAE_KRON(4) LGAE_KRON(9)
+#undef LGAE_KRON
+            if (int rc = ensure_smem((const void*)cg_agg_fwd_block_kernel, bytes)) return rc;
+            launch_k(cg_agg_fwd_block_kernel, grid, dim3(CG_THREADS), bytes, st, p);
             return check_launch("cg_aggregate_fwd");
         }
     }
@@ -594,10 +710,24 @@ int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const 
         if (bytes <= 100 * 1024) {
             CgArgs q = p;
             q.JT = ib; q.g1 = nullptr;
-            if (int rc = ensure_smem((const void*)cg_agg_bwd_edge_kernel, bytes)) return rc;
             {
                 LaunchScope ls_("cg_aggregate_bwd_edge", st);
-                launch_k(cg_agg_bwd_edge_kernel, dim3(q.B, (q.N + ib - 1) / ib), dim3(CG_THREADS), bytes, st, q);
+                const dim3 grid(q.B, (q.N + ib - 1) / ib);
+                const size_t kbytes = terms_doubles(p.n_terms, p.d1 + 1) * sizeof(double) +
+                                      ((size_t)p.NJ * p.C * p.d1 + (size_t)ib * p.C * p.n_comp + (size_t)ib * p.C * p.d1 * p.d2) * sizeof(cplx);
+                bool done = false;
+#define LGAE_KRON(D)                                                                                          \
+    if (!done && p.d2 == D) {                                                                                 \
+        if (int rc = ensure_smem((const void*)cg_agg_bwd_edge_kron_kernel<D>, kbytes)) return rc;             \
+        launch_k(cg_agg_bwd_edge_kron_kernel<D>, grid, dim3(CG_THREADS), kbytes, st, q);                      \
+        done = true;                                                                                          \
+    }
+                LGAE_KRON(1) LGAE_KRON(3) LGAE_KRON(4) LGAE_KRON(9)
+#undef LGAE_KRON
+                if (!done) {
+                    if (int rc = ensure_smem((const void*)cg_agg_bwd_edge_kernel, bytes)) return rc;
+                    launch_k(cg_agg_bwd_edge_kernel, grid, dim3(CG_THREADS), bytes, st, q);
+                }
                 if (int rc = check_launch("cg_aggregate_bwd_edge")) return rc;
             }
             p.g2 = nullptr;
