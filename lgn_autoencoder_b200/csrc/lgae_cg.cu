@@ -405,6 +405,85 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_edge_kron_kernel(const 
     }
 }
 
+// Kronecker form of the node gradient: dL/dz1[j][a] = sum_i sum_d conj(z2_ij[d]) gK_i[a][d].  One CTA per jet walks the
+// particles i in blocks of IB (p.JT): IB rows of the edge tensor and the IB gK matrices in shared memory, a thread owns one
+// (neighbour j, channel) and keeps its D1 accumulators in registers over the whole walk (fixed summation order).
+template <int D1, int D2>
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_node_kron_kernel(const CgArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, NJ = p.NJ, IB = p.JT, nc = p.n_comp;
+    cplx* z2s = reinterpret_cast<cplx*>(smem);          // IB * NJ * C * D2
+    cplx* gs = z2s + (size_t)IB * NJ * C * D2;            // IB * C * n_comp
+    cplx* gk = gs + (size_t)IB * C * nc;                  // IB * C * D1 * D2
+    TermsSm Ta;
+    terms_load(p, 1, reinterpret_cast<double*>(gk + (size_t)IB * C * D1 * D2), Ta);
+    pdl_wait();
+    const int b = blockIdx.x, per_i = NJ * C;
+    constexpr int PASS = 2;   // (j, c) items per thread
+    cplx acc[PASS][D1];
+#pragma unroll
+    for (int k = 0; k < PASS; ++k)
+#pragma unroll
+        for (int a_ = 0; a_ < D1; ++a_) acc[k][a_] = czero();
+    for (int i0 = 0; i0 < p.N; i0 += IB) {
+        const int ib = min(IB, p.N - i0);
+        __syncthreads();
+        stage_planar(z2s, p.z2 + ((int64_t)b * p.N + i0) * per_i * D2, p.plane2, ib * per_i * D2);
+        for (int t = tid; t < ib * C * nc; t += blockDim.x) {
+            const int il = t / (C * nc), w = t % (C * nc), c = w / nc, oc = w % nc;
+            const CgOut& o = p.out[out_of_comp(p, oc)];
+            const int64_t idx = (((int64_t)b * p.N + i0 + il) * o.ctot + o.coff + c) * o.d + (oc - o.comp0);
+            gs[t] = cmake(o.ptr[idx], o.ptr[o.plane + idx]);
+        }
+        __syncthreads();
+        for (int it = tid; it < ib * C * D1 * D2; it += CG_THREADS) {   // gK (il, c, a, d)
+            const int d_ = it % D2, a_ = (it / D2) % D1, ic = it / (D2 * D1);
+            const cplx* g = gs + (size_t)ic * nc;
+            cplx v = czero();
+            for (int t = Ta.start[a_]; t < Ta.start[a_ + 1]; ++t)
+                if (Ta.d[t] == d_) cfmar(v, g[Ta.comp[t]], Ta.coef[t]);
+            gk[it] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < PASS; ++k) {
+            const int it = tid + k * CG_THREADS;
+            if (it < per_i) {
+                const int c = it % C;
+                for (int il = 0; il < ib; ++il) {
+                    const cplx* z = z2s + ((size_t)il * per_i + it) * D2;
+                    const cplx* kk = gk + ((size_t)il * C + c) * D1 * D2;
+                    cplx zv[D2];
+#pragma unroll
+                    for (int d = 0; d < D2; ++d) zv[d] = z[d];
+#pragma unroll
+                    for (int a_ = 0; a_ < D1; ++a_)
+#pragma unroll
+                        for (int d = 0; d < D2; ++d) cfmac(acc[k][a_], zv[d], kk[a_ * D2 + d]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < PASS; ++k) {
+        const int it = tid + k * CG_THREADS;
+        if (it < per_i) {
+            double* g1 = p.g1 + ((int64_t)b * per_i + it) * D1;
+#pragma unroll
+            for (int a_ = 0; a_ < D1; ++a_) {
+                if (p.acc1) {
+                    g1[a_] += acc[k][a_].x;
+                    g1[p.plane1 + a_] += acc[k][a_].y;
+                } else {
+                    g1[a_] = acc[k][a_].x;
+                    g1[p.plane1 + a_] = acc[k][a_].y;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // point-wise product: out_r = H (z1_r (x) z2_r), rows r = 0..B-1 (p.B = number of rows, p.N = 1, p.NJ = 0)
 // ------------------------------------------------------------------------------------------------------------
@@ -732,6 +811,31 @@ int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const 
             }
             p.g2 = nullptr;
             if (!p.g1) return LGAE_OK;
+        }
+    }
+    if (!p.g2 && p.g1 && p.NJ * p.C <= 2 * CG_THREADS) {
+        // node gradient in Kronecker form, one CTA per jet, for the common (d1, d2)
+        const size_t t1 = terms_doubles(p.n_terms, p.d1 + 1) * sizeof(double);
+        const size_t rowb = (size_t)p.NJ * p.C * p.d2 * sizeof(cplx);
+        const size_t per_ib = rowb + ((size_t)p.C * p.n_comp + (size_t)p.C * p.d1 * p.d2) * sizeof(cplx);
+        int ib = std::min<int>(4, p.N);
+        while (ib > 1 && t1 + ib * per_ib > 100 * 1024) --ib;
+        const size_t nbytes = t1 + ib * per_ib;
+        if (nbytes <= 100 * 1024) {
+            CgArgs q = p;
+            q.JT = ib;
+            bool done = false;
+            LaunchScope ls_("cg_aggregate_bwd_node", st);
+#define LGAE_KRON(A, D)                                                                                           \
+    if (!done && p.d1 == A && p.d2 == D) {                                                                        \
+        if (int rc = ensure_smem((const void*)cg_agg_bwd_node_kron_kernel<A, D>, nbytes)) return rc;              \
+        launch_k(cg_agg_bwd_node_kron_kernel<A, D>, dim3(q.B), dim3(CG_THREADS), nbytes, st, q);                  \
+        done = true;                                                                                              \
+    }
+            LGAE_KRON(1, 1) LGAE_KRON(3, 1) LGAE_KRON(4, 1) LGAE_KRON(9, 1)
+            LGAE_KRON(1, 4) LGAE_KRON(3, 4) LGAE_KRON(4, 4) LGAE_KRON(9, 4)
+#undef LGAE_KRON
+            if (done) return check_launch("cg_aggregate_bwd_node");
         }
     }
     const size_t fixed = terms + (size_t)p.C * p.n_comp * sizeof(cplx);
