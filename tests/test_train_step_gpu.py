@@ -165,3 +165,41 @@ def test_flat_rmsprop_matches_torch_rmsprop():
     for (k, pa), (_, pb) in zip(list(enc_a.named_parameters()) + list(dec_a.named_parameters()),
                                 list(enc_b.named_parameters()) + list(dec_b.named_parameters())):
         assert rel_err(pb, pa) < 1e-10, k
+
+
+def test_full_size_step_properties():
+    """BASELINE configs[1] at its full size (512 jets x 30 particles per GPU), where the CPU oracle is too slow to be the
+    checker: size-independent properties of the path.  (1) Jets are independent and chamfer is a SUM over jets, so the step on
+    512 jets equals the two half-batch steps: per-jet reconstructions and losses identical, parameter gradients additive.
+    (2) The encoder's min&max pooling and every neighbour sum are permutation invariant: permuting the particles inside each
+    jet leaves latent, reconstruction and loss unchanged (up to summation order)."""
+    from bench import CFG, build_models, synthetic_jets
+    from lgn_autoencoder_b200.train import FusedTrainStep
+    dev = torch.device("cuda:0")
+    enc, dec = build_models(dev)
+    B, N = CFG["batch"], CFG["n"]
+    assert (B, N) == (512, 30)
+    p4 = synthetic_jets(B, N, seed=11).to(dev)
+    full = FusedTrainStep(enc, dec, B, l1_lambda=0.0, use_graph=True)
+    half = FusedTrainStep(enc, dec, B // 2, l1_lambda=0.0, use_graph=False)
+    loss = full.step(p4).item()
+    g_full, recon, jet_loss, lat = full.g_all.clone(), full.recon.clone(), full.jet_loss.clone(), full.latent11.clone()
+    assert torch.isfinite(g_full).all() and g_full.abs().max().item() > 0
+    g_sum, l_sum = torch.zeros_like(g_full), 0.0
+    for h in range(2):
+        sl = slice(h * B // 2, (h + 1) * B // 2)
+        l_sum += half.step(p4[sl]).item()
+        g_sum += half.g_all
+        assert torch.equal(half.recon, recon[:, sl]) and torch.equal(half.jet_loss, jet_loss[sl])   # per-jet work is batch independent
+    assert abs(l_sum - loss) <= 1e-12 * abs(loss)
+    assert (g_sum - g_full).abs().max().item() <= 1e-11 * g_full.abs().max().item()
+    assert abs(jet_loss.sum().item() - loss) <= 1e-12 * abs(loss)
+    # permutation of the particles inside every jet
+    gen = torch.Generator().manual_seed(3)
+    perm = torch.stack([torch.randperm(N, generator=gen) for _ in range(B)]).to(dev)
+    p4p = torch.gather(p4, 1, perm[:, :, None].expand(B, N, 4))
+    full._bind_grads()
+    loss_p = full.step(p4p).item()
+    assert abs(loss_p - loss) <= 1e-10 * abs(loss)
+    assert rel_err(full.latent11, lat) < 1e-10 and rel_err(full.recon, recon) < 1e-10
+    assert (full.g_all - g_full).abs().max().item() <= 1e-9 * g_full.abs().max().item()
