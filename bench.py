@@ -298,6 +298,8 @@ def main():
             "config": {"workload": WORKLOAD, "global_batch": jets, "parallelism": f"dp{world}", "l2": "flushed (256 MB write) between timed steps",
                        "step": "FusedTrainStep: one CUDA graph per step (normalize, encoder, decoder, chamfer, both adjoints, L1, grad all-reduce)"
                                if not args.no_graph else "FusedTrainStep, eager launches",
+                       "dead_code": "the decoder's last-level scalar MLP (its output reaches no result of the training step: loss, gradients, "
+                                    "reconstruction, latents) is not run, LGAE_KEEP_DEAD_MLP=1 restores it; the flop count stays the reference's",
                        "step_tflops": jets * fl / (ms_step * 1e-3) / 1e12, "step_frac_of_fp64_peak": jets * fl / (ms_step * 1e-3) / 1e12 / (FP64_PEAK_TFLOPS * world),
                        "mflop_per_jet": fl / 1e6},
             "e2e": {"value": jets / (ms_e2e * 1e-3), "unit": "jets/s", "h2d_bytes_per_step": host_p4.numel() * 8, "d2h_bytes_per_step": 8,

@@ -434,7 +434,8 @@ static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, cons
 }
 
 static int dec_forward_launch(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
-                              double* gen00, bool pack, cudaStream_t st, bool with_output = true, bool with_input = true) {
+                              double* gen00, bool pack, cudaStream_t st, bool with_output = true, bool with_input = true,
+                              bool scalars_unused = false) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
     if (pack) LGAE_TRY(run_mlp_pack(d, theta, ws, L.wpack, st));
@@ -442,7 +443,10 @@ static int dec_forward_launch(const LgaeModelDesc* d, const double* theta, const
     for (int l = 0; l < d->n_levels; ++l) {
         LGAE_TRY(run_level_fwd(d, l, theta, ws + L.y, nullptr, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l], nullptr, ws + L.spre[l],
                                ws + L.V[l + 1], st));
-        if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
+        // scalars_unused: nothing reads the output scalars of the last level (the training step's loss only sees the 4-vectors,
+        // lgn_decoder.py:305-345 + get_real; SURVEY.md section 8(a) "dead-in-training sub-paths"), so its MLP is not run
+        if (d->has_mlp && !(scalars_unused && l == d->n_levels - 1))
+            LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
     if (!with_output) return LGAE_OK;   // the caller runs the fused tail (reconstruction + loss + adjoint of the output map)
     return run_dec_output(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], recon, gen00, st);
@@ -576,7 +580,9 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
         LGAE_TRY(run_latent_bridge(enc, theta_enc, dec, theta_dec, batch, ws_enc + Le.S[enc->n_levels], ws_enc + Le.V[enc->n_levels], lat00,
                                    lat11, sel, ws_dec + Ld.y, ws_dec + Ld.S[0], ws_dec + Ld.V[0], st));
     }
-    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, false, st, false, false));
+    // LGAE_KEEP_DEAD_MLP=1 also runs the decoder's last-level scalar MLP, whose output no result of this entry point depends on
+    static const bool keep_dead = [] { const char* e = getenv("LGAE_KEEP_DEAD_MLP"); return e && e[0] == '1'; }();
+    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, false, st, false, false, !keep_dead));
     // one plan per model over the same partials buffer (the encoder's continues where the decoder's ends): the decoder's rows are
     // reduced on the auxiliary stream while the encoder adjoint runs, the encoder's at the end
     PartPlan plan_d, plan_e;
