@@ -123,7 +123,9 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
                           int32_t batch, double* workspace, const int32_t* sel, const double* g_lat00,
                           const double* g_lat11, double* gtheta, double* partials, double l1_lambda,
                           double* loss_accumulate, void* stream);
-/* LGNDecoder.forward.  lat11 (2,B,1,tau_v,4) planar complex Cartesian.  recon (2,B,N,4); gen00 (2,B,N,1,1) or NULL. */
+/* LGNDecoder.forward.  lat11 (2,B,1,tau_v,4) planar complex Cartesian.  recon (2,B,N,4); gen00 (2,B,N,1,1) or NULL
+ * (NULL: the output scalars are not wanted, the last level's scalar MLP -- which feeds only them -- is then not run;
+ * pass g_gen00 = NULL to the backward accordingly). */
 int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch,
                          double* workspace, double* recon, double* gen00, void* stream);
 /* g_recon (2,B,N,4); g_gen00 (2,B,N,1,1) or NULL.  g_lat11 (2,B,1,tau_v,4) receives the latent gradient. */

@@ -433,6 +433,11 @@ static int enc_backward_launch(const LgaeModelDesc* d, const double* theta, cons
     return LGAE_OK;
 }
 
+// LGAE_KEEP_DEAD_MLP=1 also runs the decoder's last-level scalar MLP when no result of the entry point depends on its output.
+static bool keep_dead_mlp() {
+    static const bool keep = [] { const char* e = getenv("LGAE_KEEP_DEAD_MLP"); return e && e[0] == '1'; }();
+    return keep;
+}
 static int dec_forward_launch(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws, double* recon,
                               double* gen00, bool pack, cudaStream_t st, bool with_output = true, bool with_input = true,
                               bool scalars_unused = false) {
@@ -513,7 +518,9 @@ int lgae_decoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     if (!d->is_decoder || batch < 0) return LGAE_E_BADARG;
     if (batch == 0) return LGAE_OK;
     if (!theta || !lat11 || !ws || !recon) return LGAE_E_BADARG;
-    return dec_forward_launch(d, theta, lat11, batch, ws, recon, gen00, true, (cudaStream_t)stream);
+    // gen00 == NULL: the caller does not want the output scalars, and the adjoint never reads the last level's saved
+    // activations when there is no gradient on them, so the last level's scalar MLP is not evaluated
+    return dec_forward_launch(d, theta, lat11, batch, ws, recon, gen00, true, (cudaStream_t)stream, true, true, !gen00 && !keep_dead_mlp());
 }
 
 int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const double* lat11, int32_t batch, double* ws,
@@ -580,9 +587,7 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
         LGAE_TRY(run_latent_bridge(enc, theta_enc, dec, theta_dec, batch, ws_enc + Le.S[enc->n_levels], ws_enc + Le.V[enc->n_levels], lat00,
                                    lat11, sel, ws_dec + Ld.y, ws_dec + Ld.S[0], ws_dec + Ld.V[0], st));
     }
-    // LGAE_KEEP_DEAD_MLP=1 also runs the decoder's last-level scalar MLP, whose output no result of this entry point depends on
-    static const bool keep_dead = [] { const char* e = getenv("LGAE_KEEP_DEAD_MLP"); return e && e[0] == '1'; }();
-    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, false, st, false, false, !keep_dead));
+    LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, false, st, false, false, !keep_dead_mlp()));
     // one plan per model over the same partials buffer (the encoder's continues where the decoder's ends): the decoder's rows are
     // reduced on the auxiliary stream while the encoder adjoint runs, the encoder's at the end
     PartPlan plan_d, plan_e;
