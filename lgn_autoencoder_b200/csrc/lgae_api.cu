@@ -542,11 +542,16 @@ int64_t lgae_train_step_partials_doubles(const LgaeModelDesc* enc, const LgaeMod
     return a + b + (int64_t)batch * 4 * dec->channels[dec->n_levels] + 1;
 }
 
-int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
-                    const double* p4_in, const uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4, double* norm_factor,
-                    double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel, double* recon, double* g_recon,
-                    double* g_lat11, double* jet_loss, double* loss, double* gtheta, int64_t gtheta_dec_offset, double* partials,
-                    double l1_lambda, void* stream) {
+}  // extern "C"
+
+// Body of lgae_train_step / lgae_train_step_host.  host_p4 / host_mask / host_loss (pinned host memory, may be NULL): the jets
+// are copied to p4_in (and the mask to node_mask) at the start and the loss back at the end, on the same stream -- after the
+// auxiliary branch has been forked, so that weight packing and gradient init overlap the host-to-device copy.
+static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
+                           double* p4_in, uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4, double* norm_factor,
+                           double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel, double* recon, double* g_recon,
+                           double* g_lat11, double* jet_loss, double* loss, double* gtheta, int64_t gtheta_dec_offset, double* partials,
+                           double l1_lambda, const double* host_p4, const uint8_t* host_mask, double* host_loss, void* stream) {
     LGAE_TRY(check_desc(enc));
     LGAE_TRY(check_desc(dec));
     if (enc->is_decoder || !dec->is_decoder || batch < 1 || gtheta_dec_offset < enc->n_params) return LGAE_E_BADARG;
@@ -576,6 +581,10 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
         } else {
             LGAE_TRY(run_mlp_pack(enc, theta_enc, ws_enc, Le.wpack, st, dec, theta_dec, ws_dec, Ld.wpack));
         }
+        if (host_p4)
+            LGAE_CUDA_TRY(cudaMemcpyAsync(p4_in, host_p4, (size_t)batch * enc->n_particles * 4 * sizeof(double), cudaMemcpyHostToDevice, st), "H2D jets");
+        if (host_mask && node_mask)
+            LGAE_CUDA_TRY(cudaMemcpyAsync(node_mask, host_mask, (size_t)batch * enc->n_particles, cudaMemcpyHostToDevice, st), "H2D mask");
         if (normalize)   // normalisation + encoder input map, one CTA per jet
             LGAE_TRY(run_norm_input(enc, theta_enc, p4_in, batch, p4, norm_factor, ws_enc + Le.mass, ws_enc + Le.S[0], ws_enc + Le.V[0], st));
     }
@@ -625,7 +634,32 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
         LGAE_TRY(run_grad_init2(theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, psum, st));
         LGAE_TRY(run_reduce_segs(&plan_d, n_all, gtheta, psum, 0.0, nullptr, st));
     }
-    return run_reduce_segs(&plan_e, n_all, gtheta, psum, l1_lambda, loss, st);
+    LGAE_TRY(run_reduce_segs(&plan_e, n_all, gtheta, psum, l1_lambda, loss, st));
+    if (host_loss) LGAE_CUDA_TRY(cudaMemcpyAsync(host_loss, loss, sizeof(double), cudaMemcpyDeviceToHost, st), "D2H loss");
+    return LGAE_OK;
+}
+
+extern "C" {
+
+int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
+                    const double* p4_in, const uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4, double* norm_factor,
+                    double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel, double* recon, double* g_recon,
+                    double* g_lat11, double* jet_loss, double* loss, double* gtheta, int64_t gtheta_dec_offset, double* partials,
+                    double l1_lambda, void* stream) {
+    return train_step_impl(enc, dec, theta_enc, theta_dec, const_cast<double*>(p4_in), const_cast<uint8_t*>(node_mask), batch, normalize, p4,
+                           norm_factor, ws_enc, ws_dec, lat00, lat11, sel, recon, g_recon, g_lat11, jet_loss, loss, gtheta, gtheta_dec_offset,
+                           partials, l1_lambda, nullptr, nullptr, nullptr, stream);
+}
+
+int lgae_train_step_host(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
+                         const double* host_p4, const uint8_t* host_mask, double* host_loss, double* p4_in, uint8_t* node_mask,
+                         int32_t batch, int32_t normalize, double* p4, double* norm_factor, double* ws_enc, double* ws_dec, double* lat00,
+                         double* lat11, int32_t* sel, double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss,
+                         double* gtheta, int64_t gtheta_dec_offset, double* partials, double l1_lambda, void* stream) {
+    if (!host_p4 || !host_loss) return LGAE_E_BADARG;
+    return train_step_impl(enc, dec, theta_enc, theta_dec, p4_in, node_mask, batch, normalize, p4, norm_factor, ws_enc, ws_dec, lat00, lat11, sel,
+                           recon, g_recon, g_lat11, jet_loss, loss, gtheta, gtheta_dec_offset, partials, l1_lambda, host_p4, host_mask, host_loss,
+                           stream);
 }
 
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,

@@ -134,6 +134,10 @@ class FusedTrainStep:
                                   ptr(self.latent00), ptr(self.latent11), ptr(self.sel), ptr(self.recon), ptr(self.g_recon),
                                   ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss), ptr(self.g_all), self.off_d, ptr(self.part), self.l1,
                                   st), "train_step")
+        self._launch_tail()
+
+    def _launch_tail(self):
+        """After the step's kernels: the data-parallel gradient exchange, then the attached optimizer."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size (SURVEY.md section 8(e))
             dist.all_reduce(self.g_all, op=dist.ReduceOp.SUM, group=self.group)
@@ -204,11 +208,18 @@ class FusedTrainStep:
         return self.run()
 
     def _launch_host(self):
-        self.p4_in.copy_(self.host_p4, non_blocking=True)
-        if self.mask is not None:
-            self.mask.copy_(self.host_mask, non_blocking=True)
-        self._launch()
-        self.host_loss.copy_(self.loss, non_blocking=True)
+        """One C call: H2D copy of the pinned jets (+ mask), the step, D2H copy of the loss (``lgae_train_step_host``)."""
+        lib, pe, pd, B = self.lib, self.pe, self.pd, self.B
+        st = torch.cuda.current_stream().cuda_stream
+        th_e, _ = self.enc._flat_params()
+        th_d, _ = self.dec._flat_params()
+        self._thetas = (th_e.data_ptr(), th_d.data_ptr())
+        check(lib.lgae_train_step_host(C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(self.host_p4), ptr(self.host_mask),
+                                       ptr(self.host_loss), ptr(self.p4_in), ptr(self.mask), B, 1 if self.normalize else 0, ptr(self.p4),
+                                       ptr(self.norm_factor), ptr(self.ws_e), ptr(self.ws_d), ptr(self.latent00), ptr(self.latent11),
+                                       ptr(self.sel), ptr(self.recon), ptr(self.g_recon), ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss),
+                                       ptr(self.g_all), self.off_d, ptr(self.part), self.l1, st), "train_step_host")
+        self._launch_tail()
 
     def step_host(self, p4=None, labels=None) -> float:
         """End-to-end step from host memory: jets (B,N,4) are staged in the pinned buffer ``host_p4`` (pass ``p4=None`` if the
