@@ -623,7 +623,10 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
         // the decoder's gradient is complete: reduce it now, next to the encoder adjoint (the gradient init ran on this stream)
         LGAE_CUDA_TRY(cudaEventRecord(aux->fork[2], st), "aux fork");
         LGAE_CUDA_TRY(cudaStreamWaitEvent(aux->s, aux->fork[2], 0), "aux fork wait");
-        LGAE_TRY(run_reduce_segs(&plan_d, n_all, gtheta, psum, 0.0, nullptr, aux->s));
+        // ... and the loss is final once the L1 term joins the chamfer sum (dec_tail): add it here and send it to the host now,
+        // so that the device-to-host copy overlaps the encoder adjoint instead of trailing the step
+        LGAE_TRY(run_reduce_segs(&plan_d, n_all, gtheta, psum, l1_lambda, loss, aux->s));
+        if (host_loss) LGAE_CUDA_TRY(cudaMemcpyAsync(host_loss, loss, sizeof(double), cudaMemcpyDeviceToHost, aux->s), "D2H loss");
         LGAE_CUDA_TRY(cudaEventRecord(aux->join[3], aux->s), "aux join");
     }
     LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan_e, st, false, aux));
@@ -634,8 +637,9 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
         LGAE_TRY(run_grad_init2(theta_enc, enc->n_params, theta_dec, dec->n_params, gtheta_dec_offset, gtheta, l1_lambda, psum, st));
         LGAE_TRY(run_reduce_segs(&plan_d, n_all, gtheta, psum, 0.0, nullptr, st));
     }
-    LGAE_TRY(run_reduce_segs(&plan_e, n_all, gtheta, psum, l1_lambda, loss, st));
-    if (host_loss) LGAE_CUDA_TRY(cudaMemcpyAsync(host_loss, loss, sizeof(double), cudaMemcpyDeviceToHost, st), "D2H loss");
+    // without the auxiliary branch the L1 term joins the loss in this last launch and the read-back trails it
+    LGAE_TRY(run_reduce_segs(&plan_e, n_all, gtheta, psum, aux ? 0.0 : l1_lambda, aux ? nullptr : loss, st));
+    if (host_loss && !aux) LGAE_CUDA_TRY(cudaMemcpyAsync(host_loss, loss, sizeof(double), cudaMemcpyDeviceToHost, st), "D2H loss");
     return LGAE_OK;
 }
 
