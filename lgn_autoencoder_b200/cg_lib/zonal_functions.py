@@ -1,5 +1,6 @@
 """Basis changes, Minkowski norms and zonal functions (reference: lgn/cg_lib/zonal_functions.py:10-446).
 Layer-level composites on device tensors; the fused kernels compute the same quantities in registers."""
+import functools
 import math
 
 import torch
@@ -16,7 +17,9 @@ def eps(data):
     return 1e-16 if data.dtype == torch.float64 else None
 
 
+@functools.lru_cache(maxsize=None)
 def _cartesian4(dtype, device):
+    """Constant basis-change matrix, built once per (dtype, device): no host-to-device copy per call (CUDA-graph capturable)."""
     re = [[1, 0, 0, 0], [0, R2, 0, 0], [0, 0, 0, 1], [0, -R2, 0, 0]]
     im = [[0, 0, 0, 0], [0, 0, -R2, 0], [0, 0, 0, 0], [0, 0, -R2, 0]]
     return torch.complex(torch.tensor(re, dtype=dtype, device=device), torch.tensor(im, dtype=dtype, device=device))
@@ -50,12 +53,14 @@ def rep_to_p(rep):
     return torch.stack((z.real, z.imag), 0)
 
 
+@functools.lru_cache(maxsize=None)
+def _metric_cached(dtype, device):
+    return torch.tensor([[1.0, 0, 0, 0], [0, 0, 0, 1.0], [0, 0, -1.0, 0], [0, 1.0, 0, 0]], dtype=dtype, device=device)
+
+
 def metric(dtype=torch.float64, device=None):
-    g = torch.zeros(4, 4, dtype=dtype, device=device)
-    g[0, 0] = 1.0
-    g[1, 3] = g[3, 1] = 1.0
-    g[2, 2] = -1.0
-    return g
+    """Canonical-basis metric (built once per dtype and device; callers get a copy they may modify)."""
+    return _metric_cached(dtype, device).clone()
 
 
 def repdot(rep1, rep2):

@@ -10,8 +10,9 @@ from lgn_autoencoder_b200.flop_model import step_flops_per_jet
 from lgn_autoencoder_b200.models import LGNDecoder, LGNEncoder
 from lgn_autoencoder_b200.train import training_step
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+B = int(_pos[0]) if len(_pos) > 0 else 1024
+steps = int(_pos[1]) if len(_pos) > 1 else 5
 N, ENC, DEC = 30, [6, 6, 8, 8], [8, 8, 6, 6]
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -46,6 +47,44 @@ k = _lib.kernel_timings(step, reps=2)
 tot = sum(n * t for n, t in k.values()) / 2
 for name, (n, t) in sorted(k.items(), key=lambda kv: -kv[1][0] * kv[1][1])[:12]:
     print(f"{name:28s} {n/2:5.0f} x {t*1e3:8.1f} us  {n*t/2/tot*100:5.1f}% of library time")
+# the same step (forward + autograd backward of the module path, ~700 launches) captured in one CUDA graph
+# (experimental, --graph: whole-step capture of the autograd path is not supported yet -- a call on the path invalidates the capture)
+graph_ms = float("nan")
+try:
+    if "--graph" not in sys.argv:
+        raise RuntimeError("skipped (pass --graph to try)")
+    params = [p for m in (enc, dec) for p in m.parameters()]
+    static_grads = None
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            for p in params:
+                p.grad = None
+            l, _, _ = training_step(enc, dec, p4)
+            l.backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    for p in params:
+        p.grad = None
+    with torch.cuda.graph(g):
+        static_loss, _, _ = training_step(enc, dec, p4)
+        static_loss.backward()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(steps):
+        g.replay()
+    b.record(); torch.cuda.synchronize()
+    graph_ms = a.elapsed_time(b) / steps
+    print(f"CUDA-graph replay of the same step: {graph_ms:.2f} ms/step -> {B / graph_ms * 1e3:.0f} jets/s; loss {static_loss.item():.6g}")
+except Exception as e:   # noqa: BLE001
+    if "--graph" in sys.argv:
+        import traceback
+        print("graph capture of the module path failed:", repr(e)[:300])
+        print("".join(traceback.format_exc().splitlines(True)[-14:]))
 try:
     fl = step_flops_per_jet(N, ENC, DEC)
 except Exception:
