@@ -203,3 +203,18 @@ def test_full_size_step_properties():
     assert abs(loss_p - loss) <= 1e-10 * abs(loss)
     assert rel_err(full.latent11, lat) < 1e-10 and rel_err(full.recon, recon) < 1e-10
     assert (full.g_all - g_full).abs().max().item() <= 1e-9 * g_full.abs().max().item()
+
+
+def test_step_host_with_padded_jets_matches_step():
+    """lgae_train_step_host also carries the labels mask from pinned host memory."""
+    from lgn_autoencoder_b200.train import FusedTrainStep
+    dev = torch.device("cuda:0")
+    g, enc, dec, batch = load("pad_n8", dev)
+    b = batch["p4"].shape[0]
+    step = FusedTrainStep(enc, dec, b, l1_lambda=1e-8, normalize=True, use_labels=True, use_graph=True)
+    l_dev = step.step(batch["p4"], batch["labels"]).item()
+    g_dev = step.g_all.clone()
+    step.mask.zero_()                      # make sure the host entry really re-uploads the mask
+    l_host = step.step_host(batch["p4"].cpu(), batch["labels"].cpu())
+    assert l_host == l_dev and torch.equal(step.g_all, g_dev)
+    assert l_host == step.step_host()      # replay from the staged pinned buffers
