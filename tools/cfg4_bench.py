@@ -48,13 +48,17 @@ tot = sum(n * t for n, t in k.values()) / 2
 for name, (n, t) in sorted(k.items(), key=lambda kv: -kv[1][0] * kv[1][1])[:12]:
     print(f"{name:28s} {n/2:5.0f} x {t*1e3:8.1f} us  {n*t/2/tot*100:5.1f}% of library time")
 # the same step (forward + autograd backward of the module path, ~700 launches) captured in one CUDA graph
-# (experimental, --graph: whole-step capture of the autograd path is not supported yet -- a call on the path invalidates the capture)
+# (--no-graph skips it; no reference to an autograd graph built on the default stream may be alive during the capture)
 graph_ms = float("nan")
+loss_eager = loss.item()
 try:
-    if "--graph" not in sys.argv:
-        raise RuntimeError("skipped (pass --graph to try)")
+    if "--no-graph" in sys.argv:
+        raise RuntimeError("skipped")
     params = [p for m in (enc, dec) for p in m.parameters()]
-    static_grads = None
+    loss_eager = loss.item()
+    del loss          # no reference to an autograd graph made on the default stream may survive into the capture
+    import gc
+    gc.collect()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -63,6 +67,7 @@ try:
                 p.grad = None
             l, _, _ = training_step(enc, dec, p4)
             l.backward()
+            del l
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
@@ -81,7 +86,7 @@ try:
     graph_ms = a.elapsed_time(b) / steps
     print(f"CUDA-graph replay of the same step: {graph_ms:.2f} ms/step -> {B / graph_ms * 1e3:.0f} jets/s; loss {static_loss.item():.6g}")
 except Exception as e:   # noqa: BLE001
-    if "--graph" in sys.argv:
+    if "--no-graph" not in sys.argv:
         import traceback
         print("graph capture of the module path failed:", repr(e)[:300])
         print("".join(traceback.format_exc().splitlines(True)[-14:]))
@@ -89,5 +94,5 @@ try:
     fl = step_flops_per_jet(N, ENC, DEC)
 except Exception:
     fl = float("nan")
-print(f"cfg-4 B={B}: {ms:.2f} ms/step -> {B / ms * 1e3:.0f} jets/s; library kernels {tot:.2f} ms/step; loss {loss.item():.6g}; "
+print(f"cfg-4 B={B}: {ms:.2f} ms/step -> {B / ms * 1e3:.0f} jets/s; library kernels {tot:.2f} ms/step; loss {loss_eager:.6g}; "
       f"peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB; maxdim-2 flop model would give {fl/1e6:.1f} MFLOP/jet (not the maxdim-3 count)")
