@@ -232,6 +232,21 @@ int lgae_cg_product_forward(const LgaeCgPairDesc* d, const int32_t* tab, const d
 int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const double* coef, const double* z1,
                              const double* z2, int64_t rows, int32_t n_nbr, const double* const* g_outs, double* g_z1,
                              double* g_z2, int32_t accumulate_z1, int32_t accumulate_z2, void* stream);
+/* All (node irrep, edge irrep) pairs of ONE aggregated cg_product call in one launch: every edge part is read once instead of
+ * once per node irrep.  node_parts[p] (2,B,N,C,node_d[p]), edge_parts[q] (2,B,N,N,C,edge_d[q]); the term list addresses the
+ * concatenated component axes a_all (over node parts) and d_all (over edge parts):
+ *   tab int32: [n_terms][3] = (component, a_all, d_all) sorted by component, then comp_start[n_comp+1], then for every
+ *              component (output tensor index, component m inside that irrep, first channel it writes);  coef fp64 [n_terms].
+ * Supported when the edge dimensions add up to 1, 4 or 5 (max_zf <= 1); otherwise LGAE_E_UNSUPPORTED (use the per-pair call). */
+#define LGAE_CG_MAX_PARTS 8
+typedef struct LgaeCgMultiDesc {
+    int32_t channels, n_node, n_edge, n_out, n_comp, n_terms;
+    int32_t node_d[LGAE_CG_MAX_PARTS], edge_d[LGAE_CG_MAX_PARTS];
+    int32_t out_d[LGAE_CG_MAX_OUT], out_ctotal[LGAE_CG_MAX_OUT];
+} LgaeCgMultiDesc;
+int lgae_cg_aggregate_multi_forward(const LgaeCgMultiDesc* d, const int32_t* tab, const double* coef,
+                                    const double* const* node_parts, const double* const* edge_parts, int64_t rows,
+                                    int32_t n_nbr, double* const* outs, void* stream);
 /* Per-irrep complex channel mixing out[r, co, m] = sum_ci W[co, ci] x[r, ci, m] (replaces mix_zweight_zvec /
  * mix_zweight_zscalar, lgn/g_lib/cplx_lib.py:7-25, called by MixReps.forward, lgn/nn/g_nn.py:95-121).
  * w (2, c_out, c_in), x (2, rows, c_in, d), out (2, rows, c_out, d).  The adjoint needs

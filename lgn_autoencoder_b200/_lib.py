@@ -70,6 +70,24 @@ class LgaeCgPairDesc(C.Structure):
     ]
 
 
+CG_MAX_PARTS = 8
+
+
+class LgaeCgMultiDesc(C.Structure):
+    _fields_ = [
+        ("channels", C.c_int32),
+        ("n_node", C.c_int32),
+        ("n_edge", C.c_int32),
+        ("n_out", C.c_int32),
+        ("n_comp", C.c_int32),
+        ("n_terms", C.c_int32),
+        ("node_d", C.c_int32 * CG_MAX_PARTS),
+        ("edge_d", C.c_int32 * CG_MAX_PARTS),
+        ("out_d", C.c_int32 * CG_MAX_OUT),
+        ("out_ctotal", C.c_int32 * CG_MAX_OUT),
+    ]
+
+
 _P = C.c_void_p
 _D = C.POINTER(LgaeModelDesc)
 _CG = C.POINTER(LgaeCgPairDesc)
@@ -104,6 +122,7 @@ _PROTOS = {
     "lgae_mlp_backward": (C.c_int, [_D, C.c_int32, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "lgae_cg_product_forward": (C.c_int, [_CG, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
     "lgae_cg_product_backward": (C.c_int, [_CG, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "lgae_cg_aggregate_multi_forward": (C.c_int, [C.POINTER(LgaeCgMultiDesc), _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
     "lgae_mix_partials_doubles": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "lgae_mix_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "lgae_mix_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),

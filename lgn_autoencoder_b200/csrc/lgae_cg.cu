@@ -225,6 +225,84 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_fwd_kron_kernel(const CgArg
     }
 }
 
+// All (node irrep, edge irrep) pairs of one aggregated cg_product call in ONE launch (Kronecker form): the rows of every edge
+// part are staged once, interleaved per (i, j, channel); K[a][d] is built for all node components a (the node parts are read
+// straight from global memory: every element is needed by exactly one thread per i) against all D2T edge components d in
+// registers; the CG matrices of all pairs are then applied from one term list.  grid (B, ceil(N / IB)), p.JT = IB.
+struct CgMultiArgs {
+    const double* node[LGAE_CG_MAX_PARTS];
+    const double* edge[LGAE_CG_MAX_PARTS];
+    double* out[LGAE_CG_MAX_OUT];
+    int32_t node_d[LGAE_CG_MAX_PARTS], node_off[LGAE_CG_MAX_PARTS + 1], edge_d[LGAE_CG_MAX_PARTS], edge_off[LGAE_CG_MAX_PARTS + 1];
+    int32_t out_d[LGAE_CG_MAX_OUT], out_ctot[LGAE_CG_MAX_OUT];
+    int32_t B, N, NJ, C, n_node, n_edge, n_comp, n_terms, IB;
+    const int32_t* tab;    // [n_terms][3] = (component, a_all, d_all) sorted by component, then comp_start[n_comp + 1],
+                           // then per component: output tensor, m, channel offset  ([n_comp][3])
+    const double* coef;    // [n_terms]
+};
+template <int D2T>
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_fwd_kernel(const CgMultiArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, NJ = p.NJ, IB = p.IB, nc = p.n_comp, nt = p.n_terms;
+    const int D1T = p.node_off[p.n_node];
+    cplx* z2s = reinterpret_cast<cplx*>(smem);                 // IB * NJ * C * D2T
+    cplx* ks = z2s + (size_t)IB * NJ * C * D2T;                  // IB * C * D1T * D2T
+    double* coef_s = reinterpret_cast<double*>(ks + (size_t)IB * C * D1T * D2T);
+    int32_t* ta = reinterpret_cast<int32_t*>(coef_s + nt);       // a_all
+    int32_t* td = ta + nt;                                       // d_all
+    int32_t* start = td + nt;                                    // n_comp + 1
+    int32_t* cinfo = start + nc + 1;                             // n_comp * 3
+    for (int t = tid; t < nt; t += blockDim.x) {
+        coef_s[t] = p.coef[t];
+        ta[t] = p.tab[3 * t + 1];
+        td[t] = p.tab[3 * t + 2];
+    }
+    for (int t = tid; t < nc + 1 + 3 * nc; t += blockDim.x) start[t] = p.tab[3 * nt + t];
+    pdl_wait();
+    const int b = blockIdx.x, i0 = blockIdx.y * IB, ib = min(IB, p.N - i0);
+    for (int q = 0; q < p.n_edge; ++q) {
+        const int dq = p.edge_d[q], off = p.edge_off[q];
+        const int64_t plane = (int64_t)p.B * p.N * NJ * C * dq;
+        const double* src = p.edge[q] + ((int64_t)b * p.N + i0) * NJ * C * dq;
+        for (int t = tid; t < ib * NJ * C * dq; t += blockDim.x)
+            z2s[(size_t)(t / dq) * D2T + off + t % dq] = cmake(src[t], src[plane + t]);
+    }
+    __syncthreads();
+    for (int it = tid; it < ib * C * D1T; it += CG_THREADS) {   // (il, c, a_all), a_all fastest
+        const int a_all = it % D1T, c = (it / D1T) % C, il = it / (D1T * C);
+        int pn = 0;
+        while (pn + 1 < p.n_node && a_all >= p.node_off[pn + 1]) ++pn;
+        const int dp = p.node_d[pn];
+        const int64_t plane = (int64_t)p.B * NJ * C * dp, step = (int64_t)C * dp;
+        const double* x = p.node[pn] + ((int64_t)b * NJ * C + c) * dp + (a_all - p.node_off[pn]);
+        const cplx* y = z2s + ((size_t)il * NJ * C + c) * D2T;
+        cplx acc[D2T];
+#pragma unroll
+        for (int d = 0; d < D2T; ++d) acc[d] = czero();
+#pragma unroll 2
+        for (int j = 0; j < NJ; ++j) {
+            const cplx xv = cmake(x[j * step], x[plane + j * step]);
+#pragma unroll
+            for (int d = 0; d < D2T; ++d) cfma(acc[d], xv, y[(size_t)j * C * D2T + d]);
+        }
+#pragma unroll
+        for (int d = 0; d < D2T; ++d) ks[(size_t)it * D2T + d] = acc[d];
+    }
+    __syncthreads();
+    for (int it = tid; it < ib * C * nc; it += CG_THREADS) {   // (il, oc, c), c fastest
+        const int c = it % C, oc = (it / C) % nc, il = it / (C * nc);
+        const cplx* k = ks + ((size_t)il * C + c) * D1T * D2T;
+        cplx acc = czero();
+        for (int t = start[oc]; t < start[oc + 1]; ++t) cfmar(acc, k[ta[t] * D2T + td[t]], coef_s[t]);
+        const int o = cinfo[3 * oc], m = cinfo[3 * oc + 1], coff = cinfo[3 * oc + 2];
+        const int64_t rowsz = (int64_t)p.out_ctot[o] * p.out_d[o];
+        const int64_t idx = ((int64_t)b * p.N + i0 + il) * rowsz + (int64_t)(coff + c) * p.out_d[o] + m;
+        p.out[o][idx] = acc.x;
+        p.out[o][(int64_t)p.B * p.N * rowsz + idx] = acc.y;
+    }
+}
+
 // Adjoint.  grid (B, neighbour tiles): the CTA owns the gradient of its z1 tile (registers) and writes the gradient of
 // the z2 entries (i, tile) for every i.  Every sum has a fixed order.
 __global__ void __launch_bounds__(CG_THREADS) cg_agg_bwd_kernel(const CgArgs p) {
@@ -846,6 +924,52 @@ int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const 
     LaunchScope ls_("cg_aggregate_bwd", st);
     launch_k(cg_agg_bwd_kernel, dim3(p.B, (p.NJ + p.JT - 1) / p.JT), dim3(CG_THREADS), bytes, st, p);
     return check_launch("cg_aggregate_bwd");
+}
+
+int lgae_cg_aggregate_multi_forward(const LgaeCgMultiDesc* d, const int32_t* tab, const double* coef, const double* const* node_parts,
+                                    const double* const* edge_parts, int64_t rows, int32_t n_nbr, double* const* outs, void* stream) {
+    if (!d || !tab || !coef || !node_parts || !edge_parts || !outs || rows < 0 || n_nbr < 1) return LGAE_E_BADARG;
+    if (d->n_node < 1 || d->n_node > LGAE_CG_MAX_PARTS || d->n_edge < 1 || d->n_edge > LGAE_CG_MAX_PARTS || d->n_out < 1 ||
+        d->n_out > LGAE_CG_MAX_OUT || d->channels < 1 || d->n_comp < 1 || d->n_terms < 1)
+        return LGAE_E_BADARG;
+    if (rows == 0) return LGAE_OK;
+    if (rows % n_nbr) return LGAE_E_BADARG;
+    CgMultiArgs p;
+    p.B = (int32_t)(rows / n_nbr); p.N = n_nbr; p.NJ = n_nbr; p.C = d->channels; p.n_node = d->n_node; p.n_edge = d->n_edge;
+    p.n_comp = d->n_comp; p.n_terms = d->n_terms; p.tab = tab; p.coef = coef;
+    p.node_off[0] = p.edge_off[0] = 0;
+    for (int i = 0; i < d->n_node; ++i) {
+        if (!node_parts[i] || d->node_d[i] < 1) return LGAE_E_BADARG;
+        p.node[i] = node_parts[i]; p.node_d[i] = d->node_d[i]; p.node_off[i + 1] = p.node_off[i] + d->node_d[i];
+    }
+    for (int i = 0; i < d->n_edge; ++i) {
+        if (!edge_parts[i] || d->edge_d[i] < 1) return LGAE_E_BADARG;
+        p.edge[i] = edge_parts[i]; p.edge_d[i] = d->edge_d[i]; p.edge_off[i + 1] = p.edge_off[i] + d->edge_d[i];
+    }
+    for (int i = 0; i < d->n_out; ++i) {
+        if (!outs[i] || d->out_d[i] < 1 || d->out_ctotal[i] < d->channels) return LGAE_E_BADARG;
+        p.out[i] = outs[i]; p.out_d[i] = d->out_d[i]; p.out_ctot[i] = d->out_ctotal[i];
+    }
+    const int D1T = p.node_off[d->n_node], D2T = p.edge_off[d->n_edge];
+    const size_t fixed = (size_t)p.n_terms * sizeof(double) + ((size_t)2 * p.n_terms + (size_t)4 * p.n_comp + 2) * sizeof(int32_t) + 16;
+    const size_t per_ib = ((size_t)p.NJ * p.C * D2T + (size_t)p.C * D1T * D2T) * sizeof(cplx);
+    int ib = std::min<int>(3, p.N);
+    while (ib > 1 && fixed + ib * per_ib > 100 * 1024) --ib;
+    const size_t bytes = fixed + ib * per_ib;
+    if (bytes > 160 * 1024) return LGAE_E_UNSUPPORTED;
+    p.IB = ib;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(p.B, (p.N + ib - 1) / ib);
+    LaunchScope ls_("cg_aggregate_multi_fwd", st);
+#define LGAE_MULTI(D)                                                                                 \
+    if (D2T == D) {                                                                                   \
+        if (int rc = ensure_smem((const void*)cg_agg_multi_fwd_kernel<D>, bytes)) return rc;          \
+        launch_k(cg_agg_multi_fwd_kernel<D>, grid, dim3(CG_THREADS), bytes, st, p);                   \
+        return check_launch("cg_aggregate_multi_fwd");                                                \
+    }
+    LGAE_MULTI(1) LGAE_MULTI(4) LGAE_MULTI(5)
+#undef LGAE_MULTI
+    return LGAE_E_UNSUPPORTED;
 }
 
 int64_t lgae_mix_partials_doubles(int64_t rows, int32_t c_in, int32_t c_out) {

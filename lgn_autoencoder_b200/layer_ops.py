@@ -34,11 +34,32 @@ def _require_cuda(t, what):
 class PairPlan:
     """One (irrep1, irrep2) pair of a cg_product call: its output irreps, channel offsets and device term tables."""
 
-    def __init__(self, i1, i2, desc, tab, coef, out_slots, swap):
+    def __init__(self, i1, i2, desc, tab, coef, out_slots, swap, keys=None, outs=None):
+        self.keys, self.outs = keys, outs  # ((k1,n1),(k2,n2)) and the pair's output irreps
         self.i1, self.i2 = i1, i2          # indices of the operand tensors (kernel order: z1 = node side, z2 = edge side)
         self.desc, self.tab, self.coef = desc, tab, coef
         self.out_slots = out_slots         # index of every output irrep in the call's output list
         self.swap = swap
+
+
+def _pair_terms(cg_dict, key1, key2, out_keys, swap):
+    """Host-side term list [(component, a, d, coef)] of a pair (a indexes the node-side operand of the kernels) and the number
+    of output components; cached on the CG dictionary."""
+    cache = cg_dict.__dict__.setdefault("_lgae_pair_terms", {})
+    ck = (key1, key2, tuple(out_keys), bool(swap))
+    if ck not in cache:
+        d2 = (key2[0] + 1) * (key2[1] + 1)
+        terms, comp0 = [], 0
+        for ok in out_keys:
+            h = cg_dict[(key1, key2)][ok].detach().cpu().numpy()
+            for m, idx in zip(*np.nonzero(h)):
+                a, d = divmod(int(idx), d2)
+                if swap:
+                    a, d = d, a
+                terms.append((comp0 + int(m), a, d, float(h[m, idx])))
+            comp0 += h.shape[0]
+        cache[ck] = (terms, comp0)
+    return cache[ck]
 
 
 def _term_tables(cg_dict, key1, key2, out_keys, swap, device):
@@ -48,15 +69,7 @@ def _term_tables(cg_dict, key1, key2, out_keys, swap, device):
     if ck in cache:
         return cache[ck]
     d2 = (key2[0] + 1) * (key2[1] + 1)
-    terms, comp0 = [], 0
-    for ok in out_keys:
-        h = cg_dict[(key1, key2)][ok].detach().cpu().numpy()
-        for m, idx in zip(*np.nonzero(h)):
-            a, d = divmod(int(idx), d2)
-            if swap:
-                a, d = d, a
-            terms.append((comp0 + int(m), a, d, float(h[m, idx])))
-        comp0 += h.shape[0]
+    terms, comp0 = _pair_terms(cg_dict, key1, key2, out_keys, swap)
     d1k = (key1[0] + 1) * (key1[1] + 1)
     dk1, dk2 = (d2, d1k) if swap else (d1k, d2)     # kernel-side d1, d2
     n = len(terms)
@@ -104,11 +117,63 @@ def plan_pairs(cg_dict, keys1, keys2, chans1, chans2, max_dim, swap, device):
                 comp0 += desc.out_d[o]
                 out_ch[ok] += chans1[i1]
                 slots.append(out_keys.index(ok))
-            pairs.append(PairPlan(i1, i2, desc, tab, coef, slots, swap))
+            pairs.append(PairPlan(i1, i2, desc, tab, coef, slots, swap, keys=(key1, key2), outs=outs))
     for p in pairs:
         for o, s in enumerate(p.out_slots):
             p.desc.out_ctotal[o] = out_ch[out_keys[s]]
     return pairs, out_keys, [out_ch[k] for k in out_keys]
+
+
+class MultiPlan:
+    """All pairs of an aggregated cg_product call for lgae_cg_aggregate_multi_forward (one launch)."""
+
+    def __init__(self, cg_dict, pairs, dims1, dims2, chans, out_keys, out_ch, swap, device):
+        node_d, edge_d = (dims2, dims1) if swap else (dims1, dims2)
+        node_off, edge_off = np.concatenate(([0], np.cumsum(node_d))), np.concatenate(([0], np.cumsum(edge_d)))
+        rows, coefs, starts, cinfo, ncomp = [], [], [0], [], 0
+        for pp in pairs:
+            terms, n_comp_pair = _pair_terms(cg_dict, pp.keys[0], pp.keys[1], pp.outs, swap)
+            i_node, i_edge = (pp.i2, pp.i1) if swap else (pp.i1, pp.i2)
+            by_comp = [[] for _ in range(n_comp_pair)]
+            for comp, a, d, coef in terms:
+                by_comp[comp].append((int(node_off[i_node]) + a, int(edge_off[i_edge]) + d, coef))
+            for comp in range(n_comp_pair):
+                o = max(k for k in range(pp.desc.n_out) if pp.desc.out_comp0[k] <= comp)
+                for a_all, d_all, coef in by_comp[comp]:
+                    rows.append((ncomp + comp, a_all, d_all))
+                    coefs.append(coef)
+                starts.append(len(rows))
+                cinfo.append((pp.out_slots[o], comp - pp.desc.out_comp0[o], pp.desc.out_coffset[o]))
+            ncomp += n_comp_pair
+        desc = _lib.LgaeCgMultiDesc()
+        desc.channels, desc.n_node, desc.n_edge, desc.n_out, desc.n_comp, desc.n_terms = chans, len(node_d), len(edge_d), len(out_keys), ncomp, len(rows)
+        for i, v in enumerate(node_d):
+            desc.node_d[i] = v
+        for i, v in enumerate(edge_d):
+            desc.edge_d[i] = v
+        for i, (k, c) in enumerate(zip(out_keys, out_ch)):
+            desc.out_d[i], desc.out_ctotal[i] = (k[0] + 1) * (k[1] + 1), c
+        tab = np.concatenate([np.asarray(rows, dtype=np.int32).reshape(-1), np.asarray(starts, dtype=np.int32),
+                              np.asarray(cinfo, dtype=np.int32).reshape(-1)])
+        self.desc = desc
+        self.tab = torch.from_numpy(tab).to(device)
+        self.coef = torch.tensor(coefs, dtype=torch.float64, device=device)
+
+
+def plan_multi(cg_dict, pairs, parts1, parts2, out_keys, out_ch, swap):
+    """MultiPlan for an aggregated call, or None when the one-launch kernel does not apply (mixed channel counts, too many
+    parts / irreps, edge dimensions other than 1, 4 or 5 in total)."""
+    dims1, dims2 = [int(p.shape[-1]) for p in parts1], [int(p.shape[-1]) for p in parts2]
+    chans = {int(p.shape[-2]) for p in list(parts1) + list(parts2)}
+    edge_total = sum(dims1 if swap else dims2)
+    if len(chans) != 1 or len(parts1) > _lib.CG_MAX_PARTS or len(parts2) > _lib.CG_MAX_PARTS or len(out_keys) > _lib.CG_MAX_OUT or \
+            edge_total not in (1, 4, 5):
+        return None
+    cache = cg_dict.__dict__.setdefault("_lgae_multi_cache", {})
+    ck = (tuple(pp.keys for pp in pairs), tuple(dims1), tuple(dims2), tuple(chans), tuple(out_keys), tuple(out_ch), bool(swap), str(parts1[0].device))
+    if ck not in cache:
+        cache[ck] = MultiPlan(cg_dict, pairs, dims1, dims2, chans.pop(), out_keys, out_ch, swap, parts1[0].device)
+    return cache[ck]
 
 
 def _ptr_array(tensors):
@@ -122,7 +187,7 @@ class _CGPairsFn(torch.autograd.Function):
     """All pairs of one cg_product call.  Inputs: the n1 parts of rep1 then the n2 parts of rep2."""
 
     @staticmethod
-    def forward(ctx, pairs, out_keys, out_ch, n1, n_nbr, swap, *parts):
+    def forward(ctx, cg_dict, pairs, out_keys, out_ch, n1, n_nbr, swap, *parts):
         lib = _lib.load()
         parts = [p.contiguous() for p in parts]
         for p in parts:
@@ -134,7 +199,18 @@ class _CGPairsFn(torch.autograd.Function):
         outs = [torch.empty((2,) + batch + (c, (k[0] + 1) * (k[1] + 1)), dtype=torch.float64, device=parts[0].device)
                 for k, c in zip(out_keys, out_ch)]
         st = _stream()
-        for pp in pairs:
+        multi = plan_multi(cg_dict, pairs, parts[:n1], parts[n1:], out_keys, out_ch, swap) if n_nbr > 0 else None
+        if multi is not None:
+            # one launch for all (node irrep, edge irrep) pairs: the edge tensor is read once
+            node, edge = (parts[n1:], parts[:n1]) if swap else (parts[:n1], parts[n1:])
+            rc = lib.lgae_cg_aggregate_multi_forward(C.byref(multi.desc), multi.tab.data_ptr(), multi.coef.data_ptr(), _ptr_array(node),
+                                                     _ptr_array(edge), rows, n_nbr, _ptr_array(outs), st)
+            if rc != -2:   # LGAE_E_UNSUPPORTED (e.g. shared memory): fall through to the per-pair launches
+                _lib.check(rc, "cg_aggregate_multi_forward")
+                multi = True
+            else:
+                multi = None
+        for pp in ([] if multi else pairs):
             a, b = parts[pp.i1], parts[n1 + pp.i2]
             z1, z2 = (b, a) if swap else (a, b)
             _lib.check(lib.lgae_cg_product_forward(C.byref(pp.desc), pp.tab.data_ptr(), pp.coef.data_ptr(), z1.data_ptr(), z2.data_ptr(),
@@ -148,7 +224,7 @@ class _CGPairsFn(torch.autograd.Function):
         lib = _lib.load()
         parts = ctx.saved_tensors
         n1, swap = ctx.n1, ctx.swap
-        need = ctx.needs_input_grad[6:]
+        need = ctx.needs_input_grad[7:]
         g_outs = [g.contiguous() if g is not None else None for g in g_outs]
         grads = [None] * len(parts)
         st = _stream()
@@ -177,7 +253,7 @@ class _CGPairsFn(torch.autograd.Function):
         for idx, p in enumerate(parts):   # parts that met no partner under the maxdim cut
             if need[idx] and grads[idx] is None:
                 grads[idx] = torch.zeros_like(p)
-        return (None,) * 6 + tuple(grads)
+        return (None,) * 7 + tuple(grads)
 
 
 def cg_pairs(cg_dict, keys1, parts1, keys2, parts2, max_dim, aggregate):
@@ -203,7 +279,7 @@ def cg_pairs(cg_dict, keys1, parts1, keys2, parts2, max_dim, aggregate):
                                          [int(p.shape[-2]) for p in parts2], max_dim, swap, parts1[0].device)
     if not pairs:
         return [], []
-    outs = _CGPairsFn.apply(pairs, out_keys, out_ch, len(parts1), n_nbr, swap, *parts1, *parts2)
+    outs = _CGPairsFn.apply(cg_dict, pairs, out_keys, out_ch, len(parts1), n_nbr, swap, *parts1, *parts2)
     return out_keys, list(outs)
 
 

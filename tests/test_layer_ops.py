@@ -210,3 +210,42 @@ def test_linear_matches_torch_fp64(rows, nin, nout, slope):
     assert rel_err(out, ref) < TOL
     for a, r in zip(g, g_ref):
         assert rel_err(a, r) < TOL
+
+
+@pytest.mark.parametrize("swap", [False, True])
+def test_multi_pair_plan_reproduces_every_pair(swap):
+    """The one-launch plan of an aggregated call (all node x edge irrep pairs): its global term list, component starts and
+    output map give, for random operands, exactly what the dense CG matrices of every pair give, in the reference's channel order."""
+    from lgn_autoencoder_b200 import layer_ops
+    cg = _cg(3)
+    node_keys, edge_keys = [(0, 0), (1, 1), (0, 2), (2, 0), (2, 2)], [(0, 0), (1, 1)]
+    keys1, keys2 = (edge_keys, node_keys) if swap else (node_keys, edge_keys)
+    C = 3
+    pairs, out_keys, out_ch = layer_ops.plan_pairs(cg, keys1, keys2, [C] * len(keys1), [C] * len(keys2), 3, swap, torch.device("cpu"))
+    dims1, dims2 = [(k + 1) * (n + 1) for k, n in keys1], [(k + 1) * (n + 1) for k, n in keys2]
+    mp = layer_ops.MultiPlan(cg, pairs, dims1, dims2, C, out_keys, out_ch, swap, torch.device("cpu"))
+    nt, nc = mp.desc.n_terms, mp.desc.n_comp
+    tab = mp.tab.numpy()
+    rows, start, cinfo = tab[:3 * nt].reshape(nt, 3), tab[3 * nt:3 * nt + nc + 1], tab[3 * nt + nc + 1:].reshape(nc, 3)
+    assert np.all(np.diff(rows[:, 0]) >= 0) and start[0] == 0 and start[-1] == nt
+    rng = np.random.default_rng(0)
+    node_d, edge_d = (dims2, dims1) if swap else (dims1, dims2)
+    x, y = rng.normal(size=sum(node_d)), rng.normal(size=sum(edge_d))
+    noff, eoff = np.concatenate(([0], np.cumsum(node_d))), np.concatenate(([0], np.cumsum(edge_d)))
+    got = {}
+    for oc in range(nc):
+        got[(int(cinfo[oc, 0]), int(cinfo[oc, 2]), int(cinfo[oc, 1]))] = sum(
+            mp.coef[t].item() * x[rows[t, 1]] * y[rows[t, 2]] for t in range(start[oc], start[oc + 1]))
+    ref, chan = {}, {k: 0 for k in out_keys}
+    for i1, key1 in enumerate(keys1):
+        for i2, key2 in enumerate(keys2):
+            outs = [(k, n) for k in range(abs(key1[0] - key2[0]), min(3, key1[0] + key2[0] + 1), 2)
+                    for n in range(abs(key1[1] - key2[1]), min(3, key1[1] + key2[1] + 1), 2)]
+            z1, z2 = (y[eoff[i1]:eoff[i1 + 1]], x[noff[i2]:noff[i2 + 1]]) if swap else (x[noff[i1]:noff[i1 + 1]], y[eoff[i2]:eoff[i2 + 1]])
+            kron = np.outer(z1, z2).reshape(-1)
+            for ok in outs:
+                for m, v in enumerate(cg[(key1, key2)][ok].numpy() @ kron):
+                    ref[(out_keys.index(ok), chan[ok], m)] = v
+                chan[ok] += C
+    assert set(got) == set(ref)
+    assert max(abs(got[k] - ref[k]) for k in ref) < 1e-14
