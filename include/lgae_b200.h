@@ -247,6 +247,14 @@ typedef struct LgaeCgMultiDesc {
 int lgae_cg_aggregate_multi_forward(const LgaeCgMultiDesc* d, const int32_t* tab, const double* coef,
                                     const double* const* node_parts, const double* const* edge_parts, int64_t rows,
                                     int32_t n_nbr, double* const* outs, void* stream);
+/* Adjoint of the one-launch aggregate.  tab_b int32: the component of every term with the terms sorted by cell
+ * a_all * D2T + d_all (D2T = sum of edge_d), then cell_start[D1T * D2T + 1], then the same [n_comp][3] output map; coef_b in the
+ * same order.  g_outs: gradients of the concatenated outputs; g_node[p] / g_edge[q]: gradient buffers (overwritten) or NULL.
+ * Node gradients need D1T in {5, 20} with D2T = 5 and N * C <= 256, otherwise LGAE_E_UNSUPPORTED (use the per-pair adjoint). */
+int lgae_cg_aggregate_multi_backward(const LgaeCgMultiDesc* d, const int32_t* tab_b, const double* coef_b,
+                                     const double* const* node_parts, const double* const* edge_parts, int64_t rows,
+                                     int32_t n_nbr, const double* const* g_outs, double* const* g_node,
+                                     double* const* g_edge, void* stream);
 /* Per-irrep complex channel mixing out[r, co, m] = sum_ci W[co, ci] x[r, ci, m] (replaces mix_zweight_zvec /
  * mix_zweight_zscalar, lgn/g_lib/cplx_lib.py:7-25, called by MixReps.forward, lgn/nn/g_nn.py:95-121).
  * w (2, c_out, c_in), x (2, rows, c_in, d), out (2, rows, c_out, d).  The adjoint needs

@@ -123,6 +123,7 @@ _PROTOS = {
     "lgae_cg_product_forward": (C.c_int, [_CG, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
     "lgae_cg_product_backward": (C.c_int, [_CG, _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "lgae_cg_aggregate_multi_forward": (C.c_int, [C.POINTER(LgaeCgMultiDesc), _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P]),
+    "lgae_cg_aggregate_multi_backward": (C.c_int, [C.POINTER(LgaeCgMultiDesc), _P, _P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P, _P]),
     "lgae_mix_partials_doubles": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "lgae_mix_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "lgae_mix_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),

@@ -8,6 +8,7 @@
 //
 // Tensors are the reference's planar complex layout: (2, ..., C, d) with the leading index re/im.
 #include <algorithm>
+#include <cstring>
 
 #include "lgae_common.cuh"
 
@@ -239,7 +240,52 @@ struct CgMultiArgs {
     const int32_t* tab;    // [n_terms][3] = (component, a_all, d_all) sorted by component, then comp_start[n_comp + 1],
                            // then per component: output tensor, m, channel offset  ([n_comp][3])
     const double* coef;    // [n_terms]
+    // adjoint: out[] holds the gradients of the outputs; terms sorted by cell = a_all * D2T + d_all
+    const int32_t* tab_b;  // [n_terms] component of every term, then cell_start[D1T * D2T + 1], then the [n_comp][3] output map
+    const double* coef_b;  // [n_terms]
+    double* gnode[LGAE_CG_MAX_PARTS];
+    double* gedge[LGAE_CG_MAX_PARTS];
 };
+// adjoint helpers: output gradients of IB particles -> shared memory, then gK[a_all][d_all] = sum_terms coef g[component]
+LGAE_DEV void multi_stage_g(const CgMultiArgs& p, const int32_t* cinfo, cplx* gs, int b, int i0, int ib) {
+    const int C = p.C, nc = p.n_comp;
+    for (int t = threadIdx.x; t < ib * C * nc; t += blockDim.x) {
+        const int oc = t % nc, c = (t / nc) % C, il = t / (nc * C);
+        const int o = cinfo[3 * oc], m = cinfo[3 * oc + 1], coff = cinfo[3 * oc + 2];
+        const int64_t rowsz = (int64_t)p.out_ctot[o] * p.out_d[o];
+        const int64_t idx = ((int64_t)b * p.N + i0 + il) * rowsz + (int64_t)(coff + c) * p.out_d[o] + m;
+        gs[t] = cmake(p.out[o][idx], p.out[o][(int64_t)p.B * p.N * rowsz + idx]);
+    }
+}
+LGAE_DEV void multi_gk(const CgMultiArgs& p, const int32_t* toc, const int32_t* cstart, const double* coef_s, const cplx* gs, cplx* gk, int ib,
+                       int ncell) {
+    const int C = p.C, nc = p.n_comp;
+    for (int it = threadIdx.x; it < ib * C * ncell; it += blockDim.x) {   // (il, c, cell)
+        const int cell = it % ncell, ic = it / ncell;
+        const cplx* g = gs + (size_t)ic * nc;
+        cplx v = czero();
+        for (int t = cstart[cell]; t < cstart[cell + 1]; ++t) cfmar(v, g[toc[t]], coef_s[t]);
+        gk[it] = v;
+    }
+}
+// carve the adjoint's tables out of shared memory (coef, component per term, cell starts, output map)
+struct MultiBwdTabs {
+    double* coef;
+    int32_t *toc, *cstart, *cinfo;
+};
+LGAE_DEV MultiBwdTabs multi_load_bwd_tabs(const CgMultiArgs& p, double* mem, int ncell) {
+    MultiBwdTabs T;
+    const int nt = p.n_terms, nc = p.n_comp;
+    T.coef = mem;
+    T.toc = reinterpret_cast<int32_t*>(mem + nt);
+    T.cstart = T.toc + nt;
+    T.cinfo = T.cstart + ncell + 1;
+    for (int t = threadIdx.x; t < nt; t += blockDim.x) T.coef[t] = p.coef_b[t];
+    for (int t = threadIdx.x; t < nt + ncell + 1 + 3 * nc; t += blockDim.x) T.toc[t] = p.tab_b[t];
+    return T;
+}
+static size_t multi_bwd_tab_bytes(int nt, int nc, int ncell) { return (size_t)nt * sizeof(double) + ((size_t)nt + ncell + 1 + 3 * nc) * sizeof(int32_t) + 16; }
+
 template <int D2T>
 __global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_fwd_kernel(const CgMultiArgs p) {
     pdl_launch();
@@ -300,6 +346,116 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_fwd_kernel(const CgMu
         const int64_t idx = ((int64_t)b * p.N + i0 + il) * rowsz + (int64_t)(coff + c) * p.out_d[o] + m;
         p.out[o][idx] = acc.x;
         p.out[o][(int64_t)p.B * p.N * rowsz + idx] = acc.y;
+    }
+}
+
+// Adjoint of the one-launch aggregate, edge operand: dL/dz2_q[i, j][d] = sum_{a_all} conj(z1_j[a_all]) gK_i[a_all][d_all] for every
+// edge part q at once; grid (B, ceil(N / IB)), fully parallel, node parts read from global memory.
+template <int D2T>
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_bwd_edge_kernel(const CgMultiArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, NJ = p.NJ, IB = p.IB, nc = p.n_comp;
+    const int D1T = p.node_off[p.n_node], ncell = D1T * D2T;
+    cplx* gs = reinterpret_cast<cplx*>(smem);             // IB * C * n_comp
+    cplx* gk = gs + (size_t)IB * C * nc;                    // IB * C * D1T * D2T
+    const MultiBwdTabs T = multi_load_bwd_tabs(p, reinterpret_cast<double*>(gk + (size_t)IB * C * ncell), ncell);
+    pdl_wait();
+    __syncthreads();
+    const int b = blockIdx.x, i0 = blockIdx.y * IB, ib = min(IB, p.N - i0);
+    multi_stage_g(p, T.cinfo, gs, b, i0, ib);
+    __syncthreads();
+    multi_gk(p, T.toc, T.cstart, T.coef, gs, gk, ib, ncell);
+    __syncthreads();
+    for (int it = tid; it < ib * NJ * C; it += CG_THREADS) {   // (il, j, c), c fastest
+        const int c = it % C, j = (it / C) % NJ, il = it / (C * NJ);
+        cplx acc[D2T];
+#pragma unroll
+        for (int d = 0; d < D2T; ++d) acc[d] = czero();
+        for (int pn = 0; pn < p.n_node; ++pn) {
+            const int dp = p.node_d[pn];
+            const int64_t plane = (int64_t)p.B * NJ * C * dp;
+            const double* x = p.node[pn] + (((int64_t)b * NJ + j) * C + c) * dp;
+            const cplx* kk = gk + (((size_t)il * C + c) * D1T + p.node_off[pn]) * D2T;
+            for (int a_ = 0; a_ < dp; ++a_) {
+                const cplx xv = cmake(x[a_], x[plane + a_]);
+#pragma unroll
+                for (int d = 0; d < D2T; ++d) cfmac(acc[d], xv, kk[a_ * D2T + d]);
+            }
+        }
+        for (int q = 0; q < p.n_edge; ++q) {
+            if (!p.gedge[q]) continue;
+            const int dq = p.edge_d[q];
+            const int64_t plane = (int64_t)p.B * p.N * NJ * C * dq;
+            double* g2 = p.gedge[q] + ((((int64_t)b * p.N + i0 + il) * NJ + j) * C + c) * dq;
+#pragma unroll
+            for (int d = 0; d < D2T; ++d) {
+                const int dl = d - p.edge_off[q];
+                if (dl >= 0 && dl < dq) {
+                    g2[dl] = acc[d].x;
+                    g2[plane + dl] = acc[d].y;
+                }
+            }
+        }
+    }
+}
+// Adjoint, node operands: dL/dz1_p[j][a] = sum_i sum_{d_all} conj(z2_ij[d_all]) gK_i[a_all][d_all]; one CTA per jet walks the particles
+// i in blocks of IB, a thread owns one (j, channel) and all D1T accumulators in registers (fixed summation order).
+template <int D1T, int D2T>
+__global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_bwd_node_kernel(const CgMultiArgs p) {
+    pdl_launch();
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, C = p.C, NJ = p.NJ, IB = p.IB, nc = p.n_comp;
+    constexpr int ncell = D1T * D2T;
+    cplx* z2s = reinterpret_cast<cplx*>(smem);              // IB * NJ * C * D2T
+    cplx* gs = z2s + (size_t)IB * NJ * C * D2T;               // IB * C * n_comp
+    cplx* gk = gs + (size_t)IB * C * nc;                      // IB * C * D1T * D2T
+    const MultiBwdTabs T = multi_load_bwd_tabs(p, reinterpret_cast<double*>(gk + (size_t)IB * C * ncell), ncell);
+    pdl_wait();
+    const int b = blockIdx.x, per_i = NJ * C;
+    cplx acc[D1T];
+#pragma unroll
+    for (int a_ = 0; a_ < D1T; ++a_) acc[a_] = czero();
+    for (int i0 = 0; i0 < p.N; i0 += IB) {
+        const int ib = min(IB, p.N - i0);
+        __syncthreads();
+        for (int q = 0; q < p.n_edge; ++q) {
+            const int dq = p.edge_d[q], off = p.edge_off[q];
+            const int64_t plane = (int64_t)p.B * p.N * NJ * C * dq;
+            const double* src = p.edge[q] + ((int64_t)b * p.N + i0) * NJ * C * dq;
+            for (int t = tid; t < ib * per_i * dq; t += blockDim.x) z2s[(size_t)(t / dq) * D2T + off + t % dq] = cmake(src[t], src[plane + t]);
+        }
+        multi_stage_g(p, T.cinfo, gs, b, i0, ib);
+        __syncthreads();
+        multi_gk(p, T.toc, T.cstart, T.coef, gs, gk, ib, ncell);
+        __syncthreads();
+        if (tid < per_i) {
+            const int c = tid % C;
+            for (int il = 0; il < ib; ++il) {
+                const cplx* z = z2s + ((size_t)il * per_i + tid) * D2T;
+                const cplx* kk = gk + ((size_t)il * C + c) * ncell;
+                cplx zv[D2T];
+#pragma unroll
+                for (int d = 0; d < D2T; ++d) zv[d] = z[d];
+#pragma unroll
+                for (int a_ = 0; a_ < D1T; ++a_)
+#pragma unroll
+                    for (int d = 0; d < D2T; ++d) cfmac(acc[a_], zv[d], kk[a_ * D2T + d]);
+            }
+        }
+    }
+    if (tid < per_i) {
+        int pn = 0;
+#pragma unroll
+        for (int a_ = 0; a_ < D1T; ++a_) {
+            while (pn + 1 < p.n_node && a_ >= p.node_off[pn + 1]) ++pn;
+            if (p.gnode[pn]) {
+                const int dp = p.node_d[pn];
+                const int64_t idx = ((int64_t)b * per_i + tid) * dp + (a_ - p.node_off[pn]);
+                p.gnode[pn][idx] = acc[a_].x;
+                p.gnode[pn][(int64_t)p.B * per_i * dp + idx] = acc[a_].y;
+            }
+        }
     }
 }
 
@@ -926,15 +1082,71 @@ int lgae_cg_product_backward(const LgaeCgPairDesc* d, const int32_t* tab, const 
     return check_launch("cg_aggregate_bwd");
 }
 
-int lgae_cg_aggregate_multi_forward(const LgaeCgMultiDesc* d, const int32_t* tab, const double* coef, const double* const* node_parts,
-                                    const double* const* edge_parts, int64_t rows, int32_t n_nbr, double* const* outs, void* stream) {
+static int multi_fill(CgMultiArgs& p, const LgaeCgMultiDesc* d, const int32_t* tab, const double* coef, const double* const* node_parts,
+                      const double* const* edge_parts, int64_t rows, int32_t n_nbr, double* const* outs);
+
+int lgae_cg_aggregate_multi_backward(const LgaeCgMultiDesc* d, const int32_t* tab_b, const double* coef_b, const double* const* node_parts,
+                                     const double* const* edge_parts, int64_t rows, int32_t n_nbr, const double* const* g_outs,
+                                     double* const* g_node, double* const* g_edge, void* stream) {
+    CgMultiArgs p;
+    if (!g_node || !g_edge) return LGAE_E_BADARG;
+    if (int rc = multi_fill(p, d, tab_b, coef_b, node_parts, edge_parts, rows, n_nbr, (double* const*)g_outs)) return rc;
+    if (rows == 0) return LGAE_OK;
+    p.tab_b = tab_b; p.coef_b = coef_b;
+    bool want_node = false, want_edge = false;
+    for (int i = 0; i < d->n_node; ++i) { p.gnode[i] = g_node[i]; want_node |= g_node[i] != nullptr; }
+    for (int i = 0; i < d->n_edge; ++i) { p.gedge[i] = g_edge[i]; want_edge |= g_edge[i] != nullptr; }
+    const int D1T = p.node_off[d->n_node], D2T = p.edge_off[d->n_edge], ncell = D1T * D2T;
+    const size_t tabs = multi_bwd_tab_bytes(p.n_terms, p.n_comp, ncell);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (want_node && !((D1T == 5 || D1T == 20) && D2T == 5 && p.NJ * p.C <= CG_THREADS)) return LGAE_E_UNSUPPORTED;
+    if (want_edge && !(D2T == 1 || D2T == 4 || D2T == 5)) return LGAE_E_UNSUPPORTED;
+    if (want_edge) {
+        const size_t per_ib = ((size_t)p.C * p.n_comp + (size_t)p.C * ncell) * sizeof(cplx);
+        int ib = std::min<int>(4, p.N);
+        while (ib > 1 && tabs + ib * per_ib > 100 * 1024) --ib;
+        const size_t bytes = tabs + ib * per_ib;
+        if (bytes > 160 * 1024) return LGAE_E_UNSUPPORTED;
+        p.IB = ib;
+        const dim3 grid(p.B, (p.N + ib - 1) / ib);
+        LaunchScope ls_("cg_aggregate_multi_bwd_edge", st);
+#define LGAE_MULTI(D)                                                                                      \
+    if (D2T == D) {                                                                                        \
+        if (int rc = ensure_smem((const void*)cg_agg_multi_bwd_edge_kernel<D>, bytes)) return rc;          \
+        launch_k(cg_agg_multi_bwd_edge_kernel<D>, grid, dim3(CG_THREADS), bytes, st, p);                   \
+    }
+        LGAE_MULTI(1) LGAE_MULTI(4) LGAE_MULTI(5)
+#undef LGAE_MULTI
+        if (int rc = check_launch("cg_aggregate_multi_bwd_edge")) return rc;
+    }
+    if (want_node) {
+        const size_t per_ib = ((size_t)p.NJ * p.C * D2T + (size_t)p.C * p.n_comp + (size_t)p.C * ncell) * sizeof(cplx);
+        int ib = std::min<int>(2, p.N);
+        while (ib > 1 && tabs + ib * per_ib > 100 * 1024) --ib;
+        const size_t bytes = tabs + ib * per_ib;
+        if (bytes > 160 * 1024) return LGAE_E_UNSUPPORTED;
+        p.IB = ib;
+        LaunchScope ls_("cg_aggregate_multi_bwd_node", st);
+        if (D1T == 5) {
+            if (int rc = ensure_smem((const void*)cg_agg_multi_bwd_node_kernel<5, 5>, bytes)) return rc;
+            launch_k(cg_agg_multi_bwd_node_kernel<5, 5>, dim3(p.B), dim3(CG_THREADS), bytes, st, p);
+        } else {
+            if (int rc = ensure_smem((const void*)cg_agg_multi_bwd_node_kernel<20, 5>, bytes)) return rc;
+            launch_k(cg_agg_multi_bwd_node_kernel<20, 5>, dim3(p.B), dim3(CG_THREADS), bytes, st, p);
+        }
+        if (int rc = check_launch("cg_aggregate_multi_bwd_node")) return rc;
+    }
+    return LGAE_OK;
+}
+
+static int multi_fill(CgMultiArgs& p, const LgaeCgMultiDesc* d, const int32_t* tab, const double* coef, const double* const* node_parts,
+                      const double* const* edge_parts, int64_t rows, int32_t n_nbr, double* const* outs) {
     if (!d || !tab || !coef || !node_parts || !edge_parts || !outs || rows < 0 || n_nbr < 1) return LGAE_E_BADARG;
     if (d->n_node < 1 || d->n_node > LGAE_CG_MAX_PARTS || d->n_edge < 1 || d->n_edge > LGAE_CG_MAX_PARTS || d->n_out < 1 ||
         d->n_out > LGAE_CG_MAX_OUT || d->channels < 1 || d->n_comp < 1 || d->n_terms < 1)
         return LGAE_E_BADARG;
-    if (rows == 0) return LGAE_OK;
     if (rows % n_nbr) return LGAE_E_BADARG;
-    CgMultiArgs p;
+    memset(&p, 0, sizeof(p));
     p.B = (int32_t)(rows / n_nbr); p.N = n_nbr; p.NJ = n_nbr; p.C = d->channels; p.n_node = d->n_node; p.n_edge = d->n_edge;
     p.n_comp = d->n_comp; p.n_terms = d->n_terms; p.tab = tab; p.coef = coef;
     p.node_off[0] = p.edge_off[0] = 0;
@@ -950,6 +1162,14 @@ int lgae_cg_aggregate_multi_forward(const LgaeCgMultiDesc* d, const int32_t* tab
         if (!outs[i] || d->out_d[i] < 1 || d->out_ctotal[i] < d->channels) return LGAE_E_BADARG;
         p.out[i] = outs[i]; p.out_d[i] = d->out_d[i]; p.out_ctot[i] = d->out_ctotal[i];
     }
+    return LGAE_OK;
+}
+
+int lgae_cg_aggregate_multi_forward(const LgaeCgMultiDesc* d, const int32_t* tab, const double* coef, const double* const* node_parts,
+                                    const double* const* edge_parts, int64_t rows, int32_t n_nbr, double* const* outs, void* stream) {
+    CgMultiArgs p;
+    if (int rc = multi_fill(p, d, tab, coef, node_parts, edge_parts, rows, n_nbr, outs)) return rc;
+    if (rows == 0) return LGAE_OK;
     const int D1T = p.node_off[d->n_node], D2T = p.edge_off[d->n_edge];
     const size_t fixed = (size_t)p.n_terms * sizeof(double) + ((size_t)2 * p.n_terms + (size_t)4 * p.n_comp + 2) * sizeof(int32_t) + 16;
     const size_t per_ib = ((size_t)p.NJ * p.C * D2T + (size_t)p.C * D1T * D2T) * sizeof(cplx);

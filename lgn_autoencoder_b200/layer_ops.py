@@ -158,6 +158,15 @@ class MultiPlan:
         self.desc = desc
         self.tab = torch.from_numpy(tab).to(device)
         self.coef = torch.tensor(coefs, dtype=torch.float64, device=device)
+        # adjoint order: terms sorted by cell = a_all * D2T + d_all
+        self.d1t, self.d2t = int(sum(node_d)), int(sum(edge_d))
+        cells = [r[1] * self.d2t + r[2] for r in rows]
+        order = sorted(range(len(rows)), key=lambda t: (cells[t], t))
+        cnt = np.bincount([cells[t] for t in order], minlength=self.d1t * self.d2t)
+        tab_b = np.concatenate([np.asarray([rows[t][0] for t in order], dtype=np.int32), np.concatenate(([0], np.cumsum(cnt))).astype(np.int32),
+                                np.asarray(cinfo, dtype=np.int32).reshape(-1)])
+        self.tab_b = torch.from_numpy(tab_b).to(device)
+        self.coef_b = torch.tensor([coefs[t] for t in order], dtype=torch.float64, device=device)
 
 
 def plan_multi(cg_dict, pairs, parts1, parts2, out_keys, out_ch, swap):
@@ -216,6 +225,8 @@ class _CGPairsFn(torch.autograd.Function):
             _lib.check(lib.lgae_cg_product_forward(C.byref(pp.desc), pp.tab.data_ptr(), pp.coef.data_ptr(), z1.data_ptr(), z2.data_ptr(),
                                                    rows, n_nbr, _ptr_array([outs[s] for s in pp.out_slots]), st), "cg_product_forward")
         ctx.pairs, ctx.n1, ctx.n_nbr, ctx.swap, ctx.rows = pairs, n1, n_nbr, swap, rows
+        ctx.multi = plan_multi(cg_dict, pairs, parts[:n1], parts[n1:], out_keys, out_ch, swap) if multi else None
+        ctx.out_shapes = [tuple(o.shape) for o in outs]
         ctx.save_for_backward(*parts)
         return tuple(outs)
 
@@ -228,7 +239,41 @@ class _CGPairsFn(torch.autograd.Function):
         g_outs = [g.contiguous() if g is not None else None for g in g_outs]
         grads = [None] * len(parts)
         st = _stream()
-        for pp in ctx.pairs:
+        pairs_todo = ctx.pairs
+        if ctx.multi is not None:
+            # one launch per operand side for all pairs (falls back to the per-pair adjoint when unsupported)
+            mp = ctx.multi
+            gl = [g if g is not None else torch.zeros(shp, dtype=torch.float64, device=parts[0].device) for g, shp in zip(g_outs, ctx.out_shapes)]
+            node_idx = list(range(n1, len(parts))) if swap else list(range(n1))
+            edge_idx = list(range(n1)) if swap else list(range(n1, len(parts)))
+            node_ok = mp.d2t == 5 and mp.d1t in (5, 20) and ctx.n_nbr * mp.desc.channels <= 256
+            want_node = node_ok and any(need[i] for i in node_idx)
+            want_edge = any(need[i] for i in edge_idx)
+            if want_node or want_edge:
+                gn = [torch.empty_like(parts[i]) if (want_node and need[i]) else None for i in node_idx]
+                ge = [torch.empty_like(parts[i]) if (want_edge and need[i]) else None for i in edge_idx]
+                arr_n, arr_e = (C.c_void_p * len(gn))(), (C.c_void_p * len(ge))()
+                for k, t in enumerate(gn):
+                    arr_n[k] = t.data_ptr() if t is not None else None
+                for k, t in enumerate(ge):
+                    arr_e[k] = t.data_ptr() if t is not None else None
+                rc = lib.lgae_cg_aggregate_multi_backward(C.byref(mp.desc), mp.tab_b.data_ptr(), mp.coef_b.data_ptr(),
+                                                          _ptr_array([parts[i] for i in node_idx]), _ptr_array([parts[i] for i in edge_idx]),
+                                                          ctx.rows, ctx.n_nbr, _ptr_array(gl), arr_n, arr_e, st)
+                if rc == 0:
+                    for i, t in zip(node_idx, gn):
+                        grads[i] = t
+                    for i, t in zip(edge_idx, ge):
+                        grads[i] = t
+                    need = list(need)
+                    for i in (node_idx if want_node else []) + (edge_idx if want_edge else []):
+                        need[i] = False     # done; the per-pair loop below only covers what is left
+                elif rc != -2:
+                    _lib.check(rc, "cg_aggregate_multi_backward")
+            if not any(need):
+                pairs_todo = []
+        done = [g is not None for g in grads]
+        for pp in pairs_todo:
             ia, ib = pp.i1, n1 + pp.i2
             gl = []
             for o, s in enumerate(pp.out_slots):
@@ -253,6 +298,7 @@ class _CGPairsFn(torch.autograd.Function):
         for idx, p in enumerate(parts):   # parts that met no partner under the maxdim cut
             if need[idx] and grads[idx] is None:
                 grads[idx] = torch.zeros_like(p)
+        del done
         return (None,) * 7 + tuple(grads)
 
 

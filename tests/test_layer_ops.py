@@ -249,3 +249,14 @@ def test_multi_pair_plan_reproduces_every_pair(swap):
                 chan[ok] += C
     assert set(got) == set(ref)
     assert max(abs(got[k] - ref[k]) for k in ref) < 1e-14
+    # adjoint order: the same terms sorted by cell (a_all, d_all) apply the transposed CG matrices
+    ncell = mp.d1t * mp.d2t
+    tab_b = mp.tab_b.numpy()
+    oc_b, cstart = tab_b[:nt], tab_b[nt:nt + ncell + 1]
+    assert cstart[0] == 0 and cstart[-1] == nt and np.array_equal(tab_b[nt + ncell + 1:].reshape(nc, 3), cinfo)
+    g = rng.normal(size=nc)
+    gk = np.array([sum(mp.coef_b[t].item() * g[oc_b[t]] for t in range(cstart[c], cstart[c + 1])) for c in range(ncell)])
+    gk_ref = np.zeros(ncell)
+    for t in range(nt):
+        gk_ref[rows[t, 1] * mp.d2t + rows[t, 2]] += mp.coef[t].item() * g[rows[t, 0]]
+    assert np.allclose(gk, gk_ref, atol=1e-15)
