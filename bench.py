@@ -88,55 +88,160 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(sample_batch, steps, warmup, threads=None):
-    """jets/s of the CPU oracle (the reference's algorithm restated in torch, all host threads unless `threads`) on a bounded
-    sample."""
+REF = os.path.join(ROOT, "baseline", "_ref")        # the unmodified reference, copied by tools/setup_reference.py (git-ignored, ships with gpurun)
+STUBS = os.path.join(ROOT, "baseline", "stubs")     # matplotlib / jetnet stand-ins the reference's `utils` package imports at module top
+
+
+def bench_config(world, batch):
+    """`config` of the JSON line, identical for both arms."""
+    return {"workload": WORKLOAD, "global_batch": batch * world, "parallelism": f"dp{world}", "l2": "flushed (256 MB write) between timed steps"}
+
+
+def oracle_step(enc_sd_in, dec_sd_in, p4, steps=1, warmup=0, threads=None):
+    """The CPU oracle (oracle/lgae_oracle.py: the reference's algorithm restated in plain torch, pinned to the reference's golden
+    vectors) on the given state dicts and jets: the CHECKER of the bench line's `parity` object and, when the reference copy is
+    absent, the CPU baseline.  Returns (median seconds per step, dict of results of the last step)."""
     import torch
     from oracle import lgae_oracle as orc
-    from lgn_autoencoder_b200.models import LGNDecoder, LGNEncoder  # only to draw reference-shaped random weights
     torch.set_num_threads(threads or os.cpu_count())
-    torch.manual_seed(0)
-    common = dict(maxdim=[2], num_basis_fn=10, max_zf=[1], weight_init="randn", level_gain=[1.0], activation="leakyrelu", mlp=True,
-                  mlp_depth=6, mlp_width=6, device=torch.device("cpu"), dtype=torch.float64)
-    enc = LGNEncoder(num_input_particles=30, tau_input_scalars=1, tau_input_vectors=1, tau_latent_scalars=1, tau_latent_vectors=8,
-                     num_channels=CFG["enc_channels"], jet_features=False, map_to_latent="min&max", **common)
-    dec = LGNDecoder(tau_latent_scalars=2, tau_latent_vectors=16, num_output_particles=30, tau_output_scalars=1, tau_output_vectors=1,
-                     num_channels=CFG["dec_channels"], cg_dict=enc.cg_dict, **common)
-    enc_sd = {k: v.detach().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
-    dec_sd = {k: v.detach().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
-    ecfg = dict(num_channels=CFG["enc_channels"], maxdim=[2], max_zf=[1], map_to_latent="min&max")
+    enc_sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in enc_sd_in.items()}
+    dec_sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in dec_sd_in.items()}
+    ecfg = dict(num_channels=CFG["enc_channels"], maxdim=[2], max_zf=[1], map_to_latent=CFG["map_to_latent"])
     dcfg = dict(num_channels=CFG["dec_channels"], maxdim=[2], max_zf=[1])
-    p4 = synthetic_jets(sample_batch, CFG["n"], seed=1)
-    p4, _ = orc.normalize_p4_overall_max(p4)
-    times = []
+    pn, _ = orc.normalize_p4_overall_max(p4.cpu())
+    times, res = [], None
     for it in range(warmup + steps):
         for sd in (enc_sd, dec_sd):
             for v in sd.values():
                 v.grad = None
         t0 = time.perf_counter()
-        loss, _, _ = orc.training_step(enc_sd, dec_sd, ecfg, dcfg, {"p4": p4}, l1_lambda=CFG["l1_lambda"])
+        loss, latent, recon = orc.training_step(enc_sd, dec_sd, ecfg, dcfg, {"p4": pn}, l1_lambda=CFG["l1_lambda"], get_real_method="sum")
         loss.backward()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return sample_batch / statistics.median(times), statistics.median(times)
+        res = {"loss": loss.detach(), "latent": {k: v.detach() for k, v in latent.items()}, "recon": recon.detach(),
+               "grads_enc": {k: v.grad for k, v in enc_sd.items()}, "grads_dec": {k: v.grad for k, v in dec_sd.items()}}
+    return statistics.median(times), res
+
+
+def reference_models(device):
+    """The UNMODIFIED reference's LGNEncoder / LGNDecoder (baseline/_ref/lgn), built with the constructor arguments of
+    utils/initialize.py:91-141.  This repository's own `lgn` shim must not be importable in this process."""
+    import torch
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") != ROOT]
+    sys.path.insert(0, STUBS)
+    sys.path.insert(0, REF)
+    import lgn.models   # noqa: F401  (first: the reference's import-order quirk, SURVEY.md appendix C.2)
+    from lgn.models import LGNDecoder, LGNEncoder
+    assert os.path.abspath(lgn.models.__file__).startswith(REF), lgn.models.__file__
+    assert "lgn_autoencoder_b200" not in sys.modules
+    torch.manual_seed(0)
+    common = dict(maxdim=[CFG["maxdim"]], num_basis_fn=CFG["num_basis_fn"], max_zf=[1], weight_init="randn", level_gain=[1.0],
+                  activation="leakyrelu", mlp=True, mlp_depth=CFG["mlp_depth"], mlp_width=CFG["mlp_width"], device=device, dtype=torch.float64)
+    enc = LGNEncoder(num_input_particles=CFG["n"], tau_input_scalars=1, tau_input_vectors=1, tau_latent_scalars=CFG["tau_s"],
+                     tau_latent_vectors=CFG["tau_v"], num_channels=CFG["enc_channels"], scale=1.0, jet_features=False,
+                     map_to_latent=CFG["map_to_latent"], **common)
+    dec = LGNDecoder(tau_latent_scalars=2 * CFG["tau_s"], tau_latent_vectors=2 * CFG["tau_v"], num_output_particles=CFG["n"],
+                     tau_output_scalars=1, tau_output_vectors=1, num_channels=CFG["dec_channels"], cg_dict=enc.cg_dict, **common)
+    return enc, dec
+
+
+def reference_rate(sample_batch, steps, warmup, device="cpu", threads=None):
+    """jets/s of the unmodified reference's training step (utils/train.py:283-327 minus the optimizer: normalize_p4 -> encoder ->
+    decoder -> get_real('sum') -> ChamferLoss + 1e-8 L1 -> backward) on `device`, through the reference's own modules."""
+    import torch
+    torch.set_num_threads(threads or os.cpu_count())
+    dev = torch.device(device)
+    enc, dec = reference_models(dev)
+    from utils.losses.chamfer_loss.chamfer_loss import ChamferLoss
+    from utils.normalize_p4 import normalize_p4
+    from utils.utils import get_real
+    chamfer = ChamferLoss(device=dev)
+    p4 = synthetic_jets(sample_batch, CFG["n"], seed=100)
+    times = []
+    for it in range(warmup + steps):
+        enc.zero_grad(set_to_none=True)
+        dec.zero_grad(set_to_none=True)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pn, _ = normalize_p4(p4.clone(), "overall_max")
+        recon = dec(enc({"p4": pn}, covariance_test=False), covariance_test=False)
+        loss = chamfer(get_real(recon, "sum"), pn.to(dev)) + CFG["l1_lambda"] * (enc.l1_norm() + dec.l1_norm())
+        loss.backward()
+        lv = loss.item()   # the reference's loop reads the loss every step (utils/train.py:320)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = statistics.median(times)
+    peak = torch.cuda.max_memory_allocated() / 2 ** 30 if dev.type == "cuda" else None
+    return sample_batch / sec, sec, lv, peak
 
 
 def run_reference(args):
+    """The reference arm: the reference's own implementation of the path on the box's host cores (all threads), one bounded
+    step = the full per-GPU batch of the workload.  kind = "reference" (the unmodified code from baseline/_ref) when that copy is
+    present, else "port" (the CPU oracle).  With --ref-device cuda the same unmodified code runs on the GPU through stock ATen
+    kernels (an extra, informative line: "what a user of the reference gets on this B200 today")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = CFG["batch"]   # the real per-GPU batch: ~3 s per step on the GPU box's 16 host threads
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    rate, sec = cpu_oracle_rate(sample, steps, warmup)
+    import torch
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     cores = os.cpu_count()
+    peak = None
+    have_ref = os.path.isdir(os.path.join(REF, "lgn"))
+    if not have_ref and args.ref_device != "cpu":
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is absent: the unmodified reference cannot run on cuda here"}))
+        return
+    if have_ref:
+        kind = "reference"
+        what = f"unmodified reference (baseline/_ref, torch {torch.__version__}) on {args.ref_device}"
+        run = lambda n, k, w: reference_rate(n, k, w, device=args.ref_device)[:3]
+    else:
+        kind = "port"
+        what = "CPU oracle (oracle/lgae_oracle.py)"
+        g = torch.load(os.path.join(ROOT, "tests", "golden", "cfg1_b3.pt"), weights_only=False)   # reference-made cfg-1 weights
+
+        def run(n, k, w):
+            sec = oracle_step(g["enc_state"], g["dec_state"], synthetic_jets(n, CFG["n"], seed=100), k, w)[0]
+            return n / sec, sec, None
+    # Bounded sample: every step processes `sample` jets of the workload's batch, sized from a probe step so that the
+    # whole --steps K --warmup W run ends within a few minutes (the full per-GPU batch when K is small).
+    sample = args.batch
+    if args.ref_device == "cpu" and (steps + warmup) > 4:
+        probe_rate = run(min(64, args.batch), 1, 1)[0]
+        sample = int(max(16, min(args.batch, (150.0 * probe_rate / (steps + warmup)) // 16 * 16)))
+    rate, sec, _ = run(sample, steps, warmup)
+    if args.ref_device != "cpu":
+        peak = torch.cuda.max_memory_allocated() / 2 ** 30
+    on_cpu = args.ref_device == "cpu"
     line = {"impl": "reference", "metric": "jets/sec LGAE fwd+bwd (30p, maxdim 2)", "value": rate, "unit": "jets/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{sample} jets per step on the host CPU"},
-            "cpu_baseline": {"value": rate, "unit": "jets/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} steps of {sample} jets, fwd+bwd, torch fp64 on {cores} threads (oracle/lgae_oracle.py)"},
-            "e2e": {"value": rate, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "dtype": "f64", "data": "synthetic", "config": bench_config(args.gpus, args.batch), "sample": f"{sample} jets per step, {what}",
+            "cpu_baseline": {"value": rate, "unit": "jets/s", "cores": cores if on_cpu else 0, "kind": kind,
+                             "sample": f"{steps} steps of {sample} jets after {warmup} warm-up, fwd+bwd, fp64, {what}"
+                                       + (f", {cores} threads" if on_cpu else f", peak {peak:.1f} GiB")},
+            "e2e": {"value": rate, "unit": "jets/s", "h2d_bytes_per_step": 0 if on_cpu else sample * CFG["n"] * 32, "d2h_bytes_per_step": 0 if on_cpu else 8},
+            "gpu_launches": 0, "device": args.ref_device}
     print(json.dumps(line))
+
+
+def reference_subprocess(extra, timeout=600):
+    """Run this script's reference arm in a fresh interpreter (the reference's `lgn` and this repository's `lgn` shim cannot
+    live in one process) and parse its JSON line."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference"] + extra, capture_output=True, text=True,
+                             timeout=timeout, env={k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")})
+        for ln in reversed(out.stdout.splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": (out.stderr or "no output").strip().splitlines()[-1][:300]}
+    except (subprocess.TimeoutExpired, OSError) as e:
+        return {"unavailable": repr(e)[:300]}
 
 
 def main():
@@ -147,6 +252,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"], help="jets per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", help="reference arm only: cpu (the baseline) or cuda (stock ATen kernels, informative)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -175,7 +281,7 @@ def main():
     host_p4 = synthetic_jets(B, N, seed=100 + rank).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
     # The public training-step API: static buffers + one CUDA graph per step (lgn_autoencoder_b200/train.py)
-    fstep = FusedTrainStep(enc, dec, B, l1_lambda=CFG["l1_lambda"], l1_scale=1.0 / world, normalize=True, use_graph=not args.no_graph)
+    fstep = FusedTrainStep(enc, dec, B, l1_lambda=CFG["l1_lambda"], l1_scale=1.0 / world, normalize=True, use_graph=not args.no_graph, get_real="sum")
 
     def barrier():
         if world > 1:
@@ -279,14 +385,34 @@ def main():
                     "note": "achieved = reference-faithful algorithmic flops of this kernel family per step / its measured time per step "
                             "(CUDA events around every launch, eager step, L2 flushed); `kernels` lists every kernel of the step"}
 
-    cpu = None
+    cpu, parity, ref_cuda = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, sec = cpu_oracle_rate(B, 2, 1)
-        rate1, sec1 = cpu_oracle_rate(32, 1, 1, threads=1)
-        cpu = {"value": rate, "unit": "jets/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"2 steps of {B} jets (the full per-GPU batch, median {sec:.2f} s/step) after 1 warm-up, fwd+bwd, torch fp64 on "
-                         f"{os.cpu_count()} threads, oracle/lgae_oracle.py",
-               "one_thread": {"value": rate1, "unit": "jets/s", "sample": f"1 step of 32 jets ({sec1:.2f} s) on 1 thread"}}
+        # ---- parity of THIS run's step against the CPU oracle on the same weights and the same 512 jets (the checker) ----
+        fstep._bind_grads()
+        loss_gpu = fstep.step(host_p4.to(dev)).item()
+        sec_o, ref = oracle_step(enc.state_dict(), dec.state_dict(), host_p4, steps=1, warmup=0)
+
+        def rel(a, b):
+            a, b = a.detach().double().cpu(), b.detach().double().cpu()
+            return ((a - b).abs().max() / b.abs().max()).item()
+        gmax = max(v.abs().max().item() for v in list(ref["grads_enc"].values()) + list(ref["grads_dec"].values()))
+        gerr = max((p.grad.detach().cpu() - sd[k]).abs().max().item() / gmax
+                   for m, sd in ((enc, ref["grads_enc"]), (dec, ref["grads_dec"])) for k, p in m.named_parameters())
+        parity = {"vs": "oracle/lgae_oracle.py (pinned to the reference's golden vectors) on the same weights and jets", "jets": B,
+                  "loss_rel": abs(loss_gpu - ref["loss"].item()) / abs(ref["loss"].item()), "recon_rel": rel(fstep.recon, ref["recon"]),
+                  "latent00_rel": rel(fstep.latent00, ref["latent"][(0, 0)]), "latent11_rel": rel(fstep.latent11, ref["latent"][(1, 1)]),
+                  "grads_rel_to_model_max": gerr, "tolerance": 1e-10}
+        # ---- CPU baseline: the unmodified reference (fresh interpreter), else the oracle port ----
+        r = reference_subprocess(["--batch", str(B), "--steps", "2", "--warmup", "1"])
+        if "value" in r:
+            cpu = dict(r["cpu_baseline"])
+        else:
+            cpu = {"value": B / sec_o, "unit": "jets/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"1 step of {B} jets ({sec_o:.2f} s), fwd+bwd, torch fp64 on {os.cpu_count()} threads, oracle/lgae_oracle.py",
+                   "note": r.get("unavailable")}
+        # ---- the unmodified reference on this GPU (stock ATen fp64 kernels): what a user of the reference gets today ----
+        r = reference_subprocess(["--batch", str(B), "--steps", "3", "--warmup", "1", "--ref-device", "cuda"])
+        ref_cuda = {"value": r["value"], "unit": "jets/s", "ms_per_step": r["ms_per_step"], "sample": r["cpu_baseline"]["sample"]} if "value" in r else r
 
     if rank == 0:
         jets = B * world
@@ -295,8 +421,8 @@ def main():
             "metric": "jets/sec LGAE fwd+bwd (30p, maxdim 2)", "value": jets / (ms_step * 1e-3), "unit": "jets/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": jets, "parallelism": f"dp{world}", "l2": "flushed (256 MB write) between timed steps",
-                       "step": "FusedTrainStep: one CUDA graph per step (normalize, encoder, decoder, chamfer, both adjoints, L1, grad all-reduce)"
+            "config": bench_config(world, B),
+            "detail": {"step": "FusedTrainStep: one CUDA graph per step (normalize, encoder, decoder, chamfer, both adjoints, L1, grad all-reduce)"
                                if not args.no_graph else "FusedTrainStep, eager launches",
                        "dead_code": "the decoder's last-level scalar MLP (its output reaches no result of the training step: loss, gradients, "
                                     "reconstruction, latents) is not run, LGAE_KEEP_DEAD_MLP=1 restores it; the flop count stays the reference's",
@@ -304,7 +430,8 @@ def main():
                        "mflop_per_jet": fl / 1e6},
             "e2e": {"value": jets / (ms_e2e * 1e-3), "unit": "jets/s", "h2d_bytes_per_step": host_p4.numel() * 8, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "kernels": table,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "reference_cuda": ref_cuda,
+            "kernels": table,
         }
         print(json.dumps(line))
     if world > 1:

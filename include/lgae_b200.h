@@ -50,6 +50,14 @@ extern "C" {
 #define LGAE_LATENT_SUM 4
 #define LGAE_LATENT_MIX 5    /* nodes x channels mixed by the latent MixReps; no pooling                  */
 
+/* get_real modes (utils/utils.py:194-207): how the complex reconstruction becomes the real 4-momenta the loss sees.
+ * The reference's default is 'real' (main.py:295-300); examples/main.sh and the benchmarked configuration use 'sum'. */
+#define LGAE_GET_REAL_REAL 0
+#define LGAE_GET_REAL_IMAG 1
+#define LGAE_GET_REAL_SUM 2
+#define LGAE_GET_REAL_MEAN 3
+#define LGAE_GET_REAL_NORM 4 /* sqrt(re^2 + im^2 + 1e-16) */
+
 /* Model descriptor: geometry + offsets (in doubles) of every parameter inside one flat fp64 buffer `theta`.
  * Gradients are written to a buffer `gtheta` with the same offsets.  Parameter shapes are the reference's
  * state-dict shapes; complex weights are planar (2, C_out, C_in). */
@@ -76,6 +84,7 @@ typedef struct LgaeModelDesc {
     int64_t off_lat00, off_lat11;           /* encoder mix_reps: (2, tau_s, C_L) / (2, tau_v, C_L) [x N: mix] */
     int64_t off_graph00, off_graph11;       /* decoder latent_to_graph: (2, N, tau_s) / (2, N, tau_v)        */
     int64_t off_out00, off_out11;           /* decoder mix_to_output: (2, 1, C_L)                            */
+    double input_scale;                     /* encoder: p4 is multiplied by this first (lgn_encoder.py:371); 0 means 1 */
 } LgaeModelDesc;
 
 /* ---- library / device ---------------------------------------------------------------------------- */
@@ -134,7 +143,7 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
                           double* gtheta, double* partials, double l1_lambda, double* loss_accumulate, void* stream);
 
 /* ---- the whole training step ---------------------------------------------------------------------- */
-/* utils/train.py:283-327 in one call: [normalize_p4] -> encoder -> decoder -> chamfer (sum over the batch, get_real 'sum') +
+/* utils/train.py:283-327 in one call: [normalize_p4] -> encoder -> decoder -> chamfer (sum over the batch) of get_real(recon) +
  * l1_lambda (|theta_enc|_1 + |theta_dec|_1) -> decoder adjoint -> encoder adjoint.  The parameter gradients of both models
  * land in ONE bucket `gtheta`: encoder at [0, enc->n_params), decoder at [gtheta_dec_offset, + dec->n_params) (so a single
  * all-reduce exchanges them), produced by one gradient-init and one reduce launch for both models.  p4_in (B,N,4); when
@@ -146,7 +155,7 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
                     const double* p4_in, const uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4,
                     double* norm_factor, double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel,
                     double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss, double* gtheta,
-                    int64_t gtheta_dec_offset, double* partials, double l1_lambda, void* stream);
+                    int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, void* stream);
 /* The same step from HOST memory: host_p4 (B,N,4) [and host_mask (B,N), may be NULL] in pinned memory are copied to the
  * device buffers p4_in / node_mask at the start of the step and the loss (1 double) back to host_loss at its end, all on
  * `stream` and capturable in one CUDA graph; the copies are ordered so that the step's parameter-only kernels (weight
@@ -158,15 +167,15 @@ int lgae_train_step_host(const LgaeModelDesc* enc, const LgaeModelDesc* dec, con
                          double* p4_in, uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4,
                          double* norm_factor, double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel,
                          double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss, double* gtheta,
-                         int64_t gtheta_dec_offset, double* partials, double l1_lambda, void* stream);
+                         int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, void* stream);
 
 
 /* ---- caller-side ops on the hot path ------------------------------------------------------------- */
-/* ChamferLoss (sum over the batch) of x = re(recon) + im(recon) against target (B,M,4).
+/* ChamferLoss (sum over the batch) of x = get_real(recon) (LGAE_GET_REAL_*) against target (B,M,4).
  * loss (1 double) is overwritten.  If g_recon != NULL it receives d loss / d recon (2,B,N,4), scaled by
  * *g_loss (device scalar) when g_loss != NULL.  jet_loss (B) optional per-jet loss (anomaly score). */
-int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss,
-                 double* jet_loss, const double* g_loss, double* g_recon, void* stream);
+int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, int32_t get_real,
+                 double* loss, double* jet_loss, const double* g_loss, double* g_recon, void* stream);
 /* normalize_p4(..., 'overall_max') (utils/normalize_p4.py:39-52): out = p4 / (max|p4| + 1e-16) per jet. */
 int lgae_normalize_p4(const double* p4, int32_t batch, int32_t n, double* out, double* factor, void* stream);
 /* L1 regulariser: out[0] (+)= lambda * sum |theta| ; gtheta += lambda * sign(theta)  (lgn_encoder.py:249-250). */

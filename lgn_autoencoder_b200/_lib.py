@@ -49,6 +49,7 @@ class LgaeModelDesc(C.Structure):
         ("off_graph11", C.c_int64),
         ("off_out00", C.c_int64),
         ("off_out11", C.c_int64),
+        ("input_scale", C.c_double),
     ]
 
 
@@ -109,10 +110,10 @@ _PROTOS = {
     "lgae_decoder_backward": (C.c_int, [_D, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_double, _P, _P]),
     "lgae_train_step_partials_doubles": (C.c_int64, [_D, _D, C.c_int32]),
     "lgae_train_step": (C.c_int, [_D, _D, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P,
-                                  C.c_double, _P]),
+                                  C.c_double, C.c_int32, _P]),
     "lgae_train_step_host": (C.c_int, [_D, _D, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
-                                       C.c_int64, _P, C.c_double, _P]),
-    "lgae_chamfer": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
+                                       C.c_int64, _P, C.c_double, C.c_int32, _P]),
+    "lgae_chamfer": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "lgae_normalize_p4": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     "lgae_l1": (C.c_int, [_P, C.c_int64, C.c_double, _P, _P, _P]),
     "lgae_level_forward": (C.c_int, [_D, C.c_int32, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P]),

@@ -56,7 +56,7 @@ int reduce_scratch_doubles();
 int run_latent_bridge(const LgaeModelDesc* de, const double* theta_e, const LgaeModelDesc* dd, const double* theta_d, int B, const double* S,
                       const double* V, double* lat00, double* lat11, int32_t* sel, double* y, double* S0, double* V0, cudaStream_t st);
 int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, const double* V, const double* target, double* recon,
-                 double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, PartPlan* plan, cudaStream_t st);
+                 double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, int mode, PartPlan* plan, cudaStream_t st);
 int run_grad_init2(const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta, double lambda,
                    double* psum, cudaStream_t st);
 int run_reduce_segs(PartPlan* plan, int64_t n_params, double* gtheta, const double* psum, double lambda, double* loss, cudaStream_t st);
@@ -64,16 +64,17 @@ int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const do
                      double lambda, double* loss, cudaStream_t st);
 int64_t glue_part_doubles(const LgaeModelDesc* d, int batch);
 int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
-                double* g_recon, cudaStream_t st);
+                double* g_recon, int mode, cudaStream_t st);
 int run_normalize(const double* p4, int B, int N, double* out, double* factor, cudaStream_t st);
 int run_norm_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* out, double* factor, double* mass, double* S,
                    double* V, cudaStream_t st);
 int run_l1(const double* theta, int64_t n, double lambda, double* out, double* gtheta, cudaStream_t st);
+int run_scale(const double* in, int64_t n, double s, double* out, cudaStream_t st);
 
 // ---- bookkeeping ------------------------------------------------------------------------------------------------
+#define LGAE_MAX_DEVICES 64
 static std::atomic<int64_t> g_launches{0};
-static char g_cuda_error[512] = "";
-static int g_sm_count = 0;
+static thread_local char g_cuda_error[512] = "";   // per calling thread: lgae_last_cuda_error() reports the caller's own failure
 
 void count_launch(int n) { g_launches += n; }
 bool pdl_enabled() {
@@ -109,24 +110,33 @@ int check_launch(const char* what) {
     snprintf(g_cuda_error, sizeof(g_cuda_error), "%s: %s", what, cudaGetErrorString(e));
     return LGAE_E_CUDA;
 }
+// The opt-in applies to the current device's copy of the function: the cache is keyed by (device, kernel).
 int ensure_smem(const void* kernel, size_t bytes) {
     static std::mutex mu;
-    static std::unordered_map<const void*, size_t> seen;
+    static std::unordered_map<const void*, size_t> seen[LGAE_MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return check_launch("cudaGetDevice");
+    const bool cached = dev >= 0 && dev < LGAE_MAX_DEVICES;
     std::lock_guard<std::mutex> lock(mu);
-    auto it = seen.find(kernel);
-    if (it != seen.end() && it->second >= bytes) return LGAE_OK;
+    if (cached) {
+        auto it = seen[dev].find(kernel);
+        if (it != seen[dev].end() && it->second >= bytes) return LGAE_OK;
+    }
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return check_launch("cudaFuncSetAttribute");
-    seen[kernel] = bytes;
+    if (cached) seen[dev][kernel] = bytes;
     return LGAE_OK;
 }
 int sm_count() {
-    if (g_sm_count > 0) return g_sm_count;
+    static std::atomic<int> per_dev[LGAE_MAX_DEVICES];
     int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 148; }
+    const bool cached = dev >= 0 && dev < LGAE_MAX_DEVICES;
+    if (cached && (n = per_dev[dev].load()) > 0) return n;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         return 148;
     }
-    g_sm_count = n;
+    if (cached) per_dev[dev].store(n);
     return n;
 }
 
@@ -191,8 +201,9 @@ static std::mutex g_aux_mu;   // serialises the training steps that share the au
 struct Layout {
     int64_t S[LGAE_MAX_LEVELS + 1], V[LGAE_MAX_LEVELS + 1];
     int64_t sums[LGAE_MAX_LEVELS], spre[LGAE_MAX_LEVELS], acts[LGAE_MAX_LEVELS], rsave[LGAE_MAX_LEVELS], wpack[LGAE_MAX_LEVELS];
-    int64_t y, mass, gS[2], gV[2], gSpre, gy, gr[LGAE_MAX_LEVELS], nrm, total;
+    int64_t y, mass, gS[2], gV[2], gSpre, gy, gr[LGAE_MAX_LEVELS], nrm, pscaled, total;
 };
+static bool has_input_scale(const LgaeModelDesc* d) { return !d->is_decoder && d->input_scale != 0.0 && d->input_scale != 1.0; }
 static int max_channels(const LgaeModelDesc* d) {
     int m = 1;
     for (int l = 0; l <= d->n_levels; ++l) m = d->channels[l] > m ? d->channels[l] : m;
@@ -226,6 +237,8 @@ static Layout layout(const LgaeModelDesc* d, int64_t B) {
         L.gr[l] = (!d->is_decoder && d->n_particles <= 32 && l < d->n_levels) ? take(nodes * d->channels[l] * 128) : -1;
     // encoder, N <= 32: norms of the unordered pairs (NaN = masked), written by the radial forward
     L.nrm = (!d->is_decoder && d->n_particles <= 32) ? take(B * radial_nrm_stride(d->n_particles)) : -1;
+    // encoder with an input scale: the scaled momenta every kernel of the model reads
+    L.pscaled = has_input_scale(d) ? take(nodes * 4) : -1;
     L.total = o;
     return L;
 }
@@ -237,6 +250,16 @@ static int check_desc(const LgaeModelDesc* d) {
         if (d->channels[l] < 1 || d->channels[l] > LGAE_MAX_CHANNELS) return LGAE_E_UNSUPPORTED;
     if (d->has_mlp && (d->mlp_hidden < 1 || d->mlp_hidden + 1 > LGAE_MAX_LINEAR)) return LGAE_E_UNSUPPORTED;
     return LGAE_OK;
+}
+
+// The momenta the encoder kernels read: p4 itself, or (input_scale != 1) the scaled copy kept in the workspace, written here
+// when `write` (forward) and re-used by the adjoint.
+static const double* scaled_input(const LgaeModelDesc* d, const double* p4, int64_t batch, double* ws, bool write, cudaStream_t st, int* rc) {
+    *rc = LGAE_OK;
+    if (!has_input_scale(d) || batch <= 0) return p4;
+    double* out = ws + layout(d, batch).pscaled;
+    if (write) *rc = run_scale(p4, batch * d->n_particles * 4, d->input_scale, out, st);
+    return out;
 }
 
 #define LGAE_TRY(expr)            \
@@ -498,7 +521,10 @@ int lgae_encoder_forward(const LgaeModelDesc* d, const double* theta, const doub
     if (d->is_decoder || batch < 0) return LGAE_E_BADARG;
     if (batch == 0) return LGAE_OK;   // empty batch: nothing to launch (the tensors' pointers may be NULL)
     if (!theta || !p4 || !ws || !lat00 || !lat11) return LGAE_E_BADARG;
-    return enc_forward_launch(d, theta, p4, node_mask, batch, ws, lat00, lat11, sel, true, (cudaStream_t)stream);
+    int rc = LGAE_OK;
+    const double* x = scaled_input(d, p4, batch, ws, true, (cudaStream_t)stream, &rc);
+    if (rc) return rc;
+    return enc_forward_launch(d, theta, x, node_mask, batch, ws, lat00, lat11, sel, true, (cudaStream_t)stream);
 }
 
 int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
@@ -506,8 +532,11 @@ int lgae_encoder_backward(const LgaeModelDesc* d, const double* theta, const dou
                           double* partials, double l1_lambda, double* loss_accumulate, void* stream) {
     LGAE_TRY(check_desc(d));
     if (d->is_decoder || !theta || !gtheta || !partials || batch < 0 || (batch > 0 && (!p4 || !ws))) return LGAE_E_BADARG;
+    if (d->n_particles > 32) return LGAE_E_UNSUPPORTED;   // before anything is launched: the adjoint holds one particle per lane
     PartPlan plan;
     plan.base = partials;
+    int rc = LGAE_OK;
+    p4 = scaled_input(d, p4, batch, ws, false, (cudaStream_t)stream, &rc);   // the forward left the scaled momenta in the workspace
     LGAE_TRY(enc_backward_launch(d, theta, p4, node_mask, batch, ws, sel, g_lat00, g_lat11, plan, (cudaStream_t)stream));
     return run_reduce_plan(&plan, d->n_params, gtheta, theta, l1_lambda, loss_accumulate, (cudaStream_t)stream);
 }
@@ -551,16 +580,18 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
                            double* p4_in, uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4, double* norm_factor,
                            double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel, double* recon, double* g_recon,
                            double* g_lat11, double* jet_loss, double* loss, double* gtheta, int64_t gtheta_dec_offset, double* partials,
-                           double l1_lambda, const double* host_p4, const uint8_t* host_mask, double* host_loss, void* stream) {
+                           double l1_lambda, int32_t get_real, const double* host_p4, const uint8_t* host_mask, double* host_loss, void* stream) {
     LGAE_TRY(check_desc(enc));
     LGAE_TRY(check_desc(dec));
     if (enc->is_decoder || !dec->is_decoder || batch < 1 || gtheta_dec_offset < enc->n_params) return LGAE_E_BADARG;
+    if (get_real < LGAE_GET_REAL_REAL || get_real > LGAE_GET_REAL_NORM) return LGAE_E_BADARG;
     if (!theta_enc || !theta_dec || !p4_in || !p4 || !ws_enc || !ws_dec || !lat00 || !lat11 || !sel || !recon || !g_recon || !g_lat11 ||
         !jet_loss || !loss || !gtheta || !partials)
         return LGAE_E_BADARG;
     if (enc->n_particles > 32) return LGAE_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const double* x = normalize ? p4 : p4_in;
+    const bool scaled = has_input_scale(enc);
     SideStream* aux = aux_stream();
     std::unique_lock<std::mutex> aux_lock(g_aux_mu, std::defer_lock);
     if (aux) aux_lock.lock();
@@ -585,10 +616,16 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
             LGAE_CUDA_TRY(cudaMemcpyAsync(p4_in, host_p4, (size_t)batch * enc->n_particles * 4 * sizeof(double), cudaMemcpyHostToDevice, st), "H2D jets");
         if (host_mask && node_mask)
             LGAE_CUDA_TRY(cudaMemcpyAsync(node_mask, host_mask, (size_t)batch * enc->n_particles, cudaMemcpyHostToDevice, st), "H2D mask");
-        if (normalize)   // normalisation + encoder input map, one CTA per jet
+        if (normalize && !scaled)   // normalisation + encoder input map, one CTA per jet
             LGAE_TRY(run_norm_input(enc, theta_enc, p4_in, batch, p4, norm_factor, ws_enc + Le.mass, ws_enc + Le.S[0], ws_enc + Le.V[0], st));
+        else if (normalize)
+            LGAE_TRY(run_normalize(p4_in, batch, enc->n_particles, p4, norm_factor, st));
     }
-    LGAE_TRY(enc_forward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false, !normalize,
+    // x: the (normalised) jets = the loss target; xe: what the encoder reads (x times the encoder's input scale)
+    int rc_scale = LGAE_OK;
+    const double* xe = scaled_input(enc, x, batch, ws_enc, true, st, &rc_scale);
+    LGAE_TRY(rc_scale);
+    LGAE_TRY(enc_forward_launch(enc, theta_enc, xe, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false, !normalize || scaled,
                                 aux ? aux->join[0] : nullptr));
     {
         // fused encoder latent map + decoder input map
@@ -607,7 +644,7 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
         const Layout Ld = layout(dec, batch);
         unsigned int* counter = reinterpret_cast<unsigned int*>(partials + lgae_train_step_partials_doubles(enc, dec, batch) - 1);
         LGAE_TRY(run_dec_tail(dec, theta_dec, batch, enc->n_particles, ws_dec + Ld.V[dec->n_levels], x, recon, g_recon, ws_dec + Ld.gV[0],
-                              jet_loss, loss, counter, &plan_d, st));
+                              jet_loss, loss, counter, get_real, &plan_d, st));
     }
     LGAE_TRY(dec_backward_launch(dec, theta_dec, lat11, batch, ws_dec, g_recon, nullptr, g_lat11, plan_d, st, false, false));
     {
@@ -629,7 +666,7 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
         if (host_loss) LGAE_CUDA_TRY(cudaMemcpyAsync(host_loss, loss, sizeof(double), cudaMemcpyDeviceToHost, aux->s), "D2H loss");
         LGAE_CUDA_TRY(cudaEventRecord(aux->join[3], aux->s), "aux join");
     }
-    LGAE_TRY(enc_backward_launch(enc, theta_enc, x, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan_e, st, false, aux));
+    LGAE_TRY(enc_backward_launch(enc, theta_enc, xe, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan_e, st, false, aux));
     if (aux) {
         LGAE_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[1], 0), "aux join wait");
         LGAE_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[3], 0), "aux join wait");
@@ -649,31 +686,32 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
                     const double* p4_in, const uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4, double* norm_factor,
                     double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel, double* recon, double* g_recon,
                     double* g_lat11, double* jet_loss, double* loss, double* gtheta, int64_t gtheta_dec_offset, double* partials,
-                    double l1_lambda, void* stream) {
+                    double l1_lambda, int32_t get_real, void* stream) {
     return train_step_impl(enc, dec, theta_enc, theta_dec, const_cast<double*>(p4_in), const_cast<uint8_t*>(node_mask), batch, normalize, p4,
                            norm_factor, ws_enc, ws_dec, lat00, lat11, sel, recon, g_recon, g_lat11, jet_loss, loss, gtheta, gtheta_dec_offset,
-                           partials, l1_lambda, nullptr, nullptr, nullptr, stream);
+                           partials, l1_lambda, get_real, nullptr, nullptr, nullptr, stream);
 }
 
 int lgae_train_step_host(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
                          const double* host_p4, const uint8_t* host_mask, double* host_loss, double* p4_in, uint8_t* node_mask,
                          int32_t batch, int32_t normalize, double* p4, double* norm_factor, double* ws_enc, double* ws_dec, double* lat00,
                          double* lat11, int32_t* sel, double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss,
-                         double* gtheta, int64_t gtheta_dec_offset, double* partials, double l1_lambda, void* stream) {
+                         double* gtheta, int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, void* stream) {
     if (!host_p4 || !host_loss) return LGAE_E_BADARG;
     return train_step_impl(enc, dec, theta_enc, theta_dec, p4_in, node_mask, batch, normalize, p4, norm_factor, ws_enc, ws_dec, lat00, lat11, sel,
-                           recon, g_recon, g_lat11, jet_loss, loss, gtheta, gtheta_dec_offset, partials, l1_lambda, host_p4, host_mask, host_loss,
-                           stream);
+                           recon, g_recon, g_lat11, jet_loss, loss, gtheta, gtheta_dec_offset, partials, l1_lambda, get_real, host_p4, host_mask,
+                           host_loss, stream);
 }
 
-int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, double* loss, double* jet_loss,
-                 const double* g_loss, double* g_recon, void* stream) {
+int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, int32_t get_real, double* loss,
+                 double* jet_loss, const double* g_loss, double* g_recon, void* stream) {
     if (batch < 0 || n < 1 || m < 1 || (batch > 0 && (!recon || !target || !jet_loss))) return LGAE_E_BADARG;
+    if (get_real < LGAE_GET_REAL_REAL || get_real > LGAE_GET_REAL_NORM) return LGAE_E_BADARG;
     if (batch == 0) {
         if (loss && cudaMemsetAsync(loss, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) return check_launch("memset loss");
         return LGAE_OK;
     }
-    return run_chamfer(recon, target, batch, n, m, loss, jet_loss, g_loss, g_recon, (cudaStream_t)stream);
+    return run_chamfer(recon, target, batch, n, m, loss, jet_loss, g_loss, g_recon, get_real, (cudaStream_t)stream);
 }
 
 int lgae_normalize_p4(const double* p4, int32_t batch, int32_t n, double* out, double* factor, void* stream) {
@@ -692,7 +730,7 @@ int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* thet
                        int32_t batch, const double* s_in, const double* v_in, double* sums, double* r_save, double* s_pre, double* v_out,
                        void* stream) {
     LGAE_TRY(check_desc(d));
-    if (!theta || !p_or_y || !s_in || !v_in || !sums || !s_pre || !v_out || batch < 0) return LGAE_E_BADARG;
+    if (!theta || !p_or_y || !s_in || !v_in || !sums || !s_pre || !v_out || batch < 0 || level < 0 || level >= d->n_levels) return LGAE_E_BADARG;
     if (!d->is_decoder && d->n_particles <= 32 && r_save)
         LGAE_TRY(run_radial_fwd(d, level, theta, p_or_y, node_mask, batch, r_save, nullptr, (cudaStream_t)stream));
     return run_level_fwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, s_pre, v_out, (cudaStream_t)stream);
@@ -702,7 +740,9 @@ int lgae_level_backward(const LgaeModelDesc* d, int32_t level, const double* the
                         double* g_r_scratch, const double* g_s_pre, const double* g_v_out, double* g_s_in, double* g_v_in,
                         double* g_y_accumulate, double* gtheta, double* partials, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (!theta || !p_or_y || !s_in || !v_in || !sums || !g_v_out || !g_s_in || !g_v_in || !gtheta || !partials || batch < 0) return LGAE_E_BADARG;
+    if (!theta || !p_or_y || !s_in || !v_in || !sums || !g_v_out || !g_s_in || !g_v_in || !gtheta || !partials || batch < 0 || level < 0 ||
+        level >= d->n_levels)
+        return LGAE_E_BADARG;
     if (d->is_decoder && !g_y_accumulate) return LGAE_E_BADARG;
     if (!d->is_decoder && (!r_save || !g_r_scratch)) return LGAE_E_BADARG;
     PartPlan plan;
@@ -742,7 +782,7 @@ int lgae_mlp_forward(const LgaeModelDesc* d, int32_t level, const double* theta,
 int lgae_mlp_backward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* x, int64_t rows, const double* wpack,
                       const double* acts, const double* g_y, double* g_x, double* gtheta, double* partials, void* stream) {
     LGAE_TRY(check_desc(d));
-    if (!theta || !x || !wpack || !acts || !g_y || !gtheta || !partials || rows < 0) return LGAE_E_BADARG;
+    if (!theta || !x || !wpack || !acts || !g_y || !gtheta || !partials || rows < 0 || level < 0 || level >= d->n_levels) return LGAE_E_BADARG;
     PartPlan plan;
     plan.base = partials;
     LGAE_TRY(run_mlp(d, level, theta, wpack, x, rows, const_cast<double*>(acts), nullptr, g_y, g_x, &plan, true, (cudaStream_t)stream));

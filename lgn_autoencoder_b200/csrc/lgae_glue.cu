@@ -640,9 +640,28 @@ __global__ void __launch_bounds__(256) dec_output_bwd_kernel(const double* theta
 // ------------------------------------------------------------------------------------------------------------
 // chamfer loss (+ gradient), normalisation, L1, reductions
 // ------------------------------------------------------------------------------------------------------------
-// One CTA per jet.  x_i = re(recon_i) + im(recon_i)  (get_real 'sum', utils/utils.py:201-202).
+// get_real (utils/utils.py:194-207): the real 4-momentum the loss sees, x = f(re, im), and its derivative (d_re, d_im).
+LGAE_DEV double get_real_value(int mode, double re, double im) {
+    switch (mode) {
+        case LGAE_GET_REAL_IMAG: return im;
+        case LGAE_GET_REAL_SUM: return re + im;
+        case LGAE_GET_REAL_MEAN: return (re + im) / 2;
+        case LGAE_GET_REAL_NORM: return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)), 1e-16));
+        default: return re;
+    }
+}
+LGAE_DEV void get_real_grad(int mode, double re, double im, double x, double g, double& g_re, double& g_im) {
+    switch (mode) {
+        case LGAE_GET_REAL_IMAG: g_re = 0.0; g_im = g; break;
+        case LGAE_GET_REAL_SUM: g_re = g; g_im = g; break;
+        case LGAE_GET_REAL_MEAN: g_re = 0.5 * g; g_im = 0.5 * g; break;
+        case LGAE_GET_REAL_NORM: g_re = g * (re / x); g_im = g * (im / x); break;
+        default: g_re = g; g_im = 0.0; break;
+    }
+}
+// One CTA per jet.  x_i = get_real(recon_i)  (utils/train.py:292).
 __global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const double* target, int B, int N, int M, double* jet_loss,
-                                                      const double* g_loss, double* g_recon) {
+                                                      const double* g_loss, double* g_recon, int mode) {
     pdl_launch();
     pdl_wait();
     extern __shared__ __align__(128) double smem[];
@@ -654,7 +673,7 @@ __global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const
     int* i2 = j1 + N;                            // M
     const int b = blockIdx.x, tid = threadIdx.x;
     const int64_t plane = (int64_t)B * N * 4;
-    for (int k = tid; k < 4 * N; k += blockDim.x) x[k] = recon[(int64_t)b * N * 4 + k] + recon[plane + (int64_t)b * N * 4 + k];
+    for (int k = tid; k < 4 * N; k += blockDim.x) x[k] = get_real_value(mode, recon[(int64_t)b * N * 4 + k], recon[plane + (int64_t)b * N * 4 + k]);
     for (int k = tid; k < 4 * M; k += blockDim.x) t[k] = target[(int64_t)b * M * 4 + k];
     __syncthreads();
     auto dist = [&](int i, int j) {
@@ -705,9 +724,11 @@ __global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const
                 }
 #pragma unroll
             for (int mu = 0; mu < 4; ++mu) {
-                const double v = g[mu] * scale;
-                g_recon[((int64_t)b * N + i) * 4 + mu] = v;
-                g_recon[plane + ((int64_t)b * N + i) * 4 + mu] = v;
+                const int64_t k = ((int64_t)b * N + i) * 4 + mu;
+                double g_re, g_im;
+                get_real_grad(mode, recon[k], recon[plane + k], x[4 * i + mu], g[mu] * scale, g_re, g_im);
+                g_recon[k] = g_re;
+                g_recon[plane + k] = g_im;
             }
         }
     }
@@ -721,6 +742,7 @@ struct DecTailArgs {
     const double* theta;
     int64_t off11;
     int B, N, M, C;
+    int mode;               // LGAE_GET_REAL_*
     const double* V;        // (B,N,C,4,2) node vectors after the last level
     const double* target;   // (B,M,4)
     double* recon;          // (2,B,N,4)
@@ -770,7 +792,7 @@ __global__ void __launch_bounds__(128) dec_tail_kernel(const DecTailArgs a) {
         for (int mu = 0; mu < 4; ++mu) {
             a.recon[((int64_t)b * N + i) * 4 + mu] = pc[mu].x;
             a.recon[plane + ((int64_t)b * N + i) * 4 + mu] = pc[mu].y;
-            x[4 * i + mu] = pc[mu].x + pc[mu].y;   // get_real(..., 'sum'), utils/utils.py:201-202
+            x[4 * i + mu] = get_real_value(a.mode, pc[mu].x, pc[mu].y);   // get_real, utils/utils.py:194-207
         }
     }
     __syncthreads();
@@ -819,10 +841,13 @@ __global__ void __launch_bounds__(128) dec_tail_kernel(const DecTailArgs a) {
         cplx gp[4], gg[4];
 #pragma unroll
         for (int mu = 0; mu < 4; ++mu) {
-            gp[mu] = cmake(g[mu], g[mu]);
+            const int64_t k = ((int64_t)b * N + i) * 4 + mu;
+            double re = 0.0, im = 0.0;
+            if (a.mode == LGAE_GET_REAL_NORM) { re = a.recon[k]; im = a.recon[plane + k]; }   // written by this thread above
+            get_real_grad(a.mode, re, im, x[4 * i + mu], g[mu], gp[mu].x, gp[mu].y);
             if (a.g_recon) {
-                a.g_recon[((int64_t)b * N + i) * 4 + mu] = g[mu];
-                a.g_recon[plane + ((int64_t)b * N + i) * 4 + mu] = g[mu];
+                a.g_recon[k] = gp[mu].x;
+                a.g_recon[plane + k] = gp[mu].y;
             }
         }
         canon_from_cplx(gp, gg);   // adjoint of rep_to_p
@@ -907,6 +932,13 @@ __global__ void __launch_bounds__(128) norm_input_kernel(const double* p4, int N
     normalize_jet(p4, N, out, factor, blockIdx.x, scratch);
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) enc_input_node(theta, off00, off11, out, (int64_t)blockIdx.x * N + i, C, mass, S, V);
+}
+
+// out = s * in (the encoder's input scale, lgn_encoder.py:371)
+__global__ void __launch_bounds__(256) scale_kernel(const double* in, int64_t n, double s, double* out) {
+    pdl_launch();
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i] * s;
 }
 
 // Single block: the parameter vector has ~3e4..3e5 entries.  out[0] += lambda * sum|theta| ; gtheta += lambda * sign(theta).
@@ -1255,12 +1287,12 @@ int64_t glue_part_doubles(const LgaeModelDesc* d, int batch) {
     return g * 4 * d->channels[0] + gj * 2 * (d->tau_s + d->tau_v) * cin;
 }
 int run_chamfer(const double* recon, const double* target, int B, int N, int M, double* loss, double* jet_loss, const double* g_loss,
-                double* g_recon, cudaStream_t st) {
+                double* g_recon, int mode, cudaStream_t st) {
     const size_t bytes = (size_t)(4 * N + 4 * M + N + M) * sizeof(double) + (size_t)(N + M) * sizeof(int);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     if (int rc = ensure_smem((const void*)chamfer_kernel, bytes)) return rc;
     LaunchScope ls_("chamfer", st);
-    launch_k(chamfer_kernel, dim3(B), dim3(128), bytes, st, recon, target, B, N, M, jet_loss, g_loss, g_recon);
+    launch_k(chamfer_kernel, dim3(B), dim3(128), bytes, st, recon, target, B, N, M, jet_loss, g_loss, g_recon, mode);
     int rc = check_launch("chamfer");
     if (rc) return rc;
     if (loss) {
@@ -1272,8 +1304,9 @@ int run_chamfer(const double* recon, const double* target, int B, int N, int M, 
 }
 // mix_to_output + chamfer + their adjoints for a training step (see dec_tail_kernel).  `counter`: 4 bytes of device scratch.
 int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, const double* V, const double* target, double* recon,
-                 double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, PartPlan* plan, cudaStream_t st) {
+                 double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, int mode, PartPlan* plan, cudaStream_t st) {
     DecTailArgs a;
+    a.mode = mode;
     a.theta = theta; a.off11 = d->off_out11;
     a.B = B; a.N = d->n_particles; a.M = M; a.C = d->channels[d->n_levels];
     a.V = V; a.target = target; a.recon = recon; a.g_recon = g_recon; a.gV = gV; a.jet_loss = jet_loss; a.loss = loss; a.counter = counter;
@@ -1300,6 +1333,12 @@ int run_normalize(const double* p4, int B, int N, double* out, double* factor, c
     LaunchScope ls_("normalize_p4", st);
     launch_k(normalize_kernel, dim3(B), dim3(128), 0, st, p4, N, out, factor);
     return check_launch("normalize_p4");
+}
+int run_scale(const double* in, int64_t n, double s, double* out, cudaStream_t st) {
+    LaunchScope ls_("scale_input", st);
+    const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    launch_k(scale_kernel, dim3(grid), dim3(256), 0, st, in, n, s, out);
+    return check_launch("scale_input");
 }
 int run_l1(const double* theta, int64_t n, double lambda, double* out, double* gtheta, cudaStream_t st) {
     LaunchScope ls_("l1", st);

@@ -22,7 +22,7 @@ struct AdamArgs {
 // exp_avg <- exp_avg + (g - exp_avg)(1 - beta1), exp_avg_sq <- beta2 exp_avg_sq + (1 - beta2) g^2,
 // theta <- theta - (lr / (1 - beta1^t)) exp_avg / (sqrt(exp_avg_sq) / sqrt(1 - beta2^t) + eps).
 __global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
-    pdl_launch();
+    // no early launch_dependents: the next step's kernels read theta in their prologues, which must not overlap this update
     pdl_wait();
     const double t = (double)(a.step[0] + 1);
     const double bc1 = 1.0 - pow(a.beta1, t), bc2 = 1.0 - pow(a.beta2, t);
@@ -63,7 +63,7 @@ struct RmsArgs {
     double lr, alpha, eps, momentum, weight_decay;
 };
 __global__ void __launch_bounds__(256) rmsprop_kernel(const RmsArgs a) {
-    pdl_launch();
+    // no early launch_dependents: the next step's kernels read theta in their prologues, which must not overlap this update
     pdl_wait();
     const int64_t total = a.n[0] + a.n[1];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {

@@ -16,6 +16,18 @@ import torch
 from . import _lib
 from ._lib import LATENT_MODES, LgaeModelDesc, check, ptr
 
+GET_REAL_MODES = {"real": 0, "imag": 1, "sum": 2, "mean": 3, "norm": 4}
+
+
+def get_real_mode(method: str) -> int:
+    """utils/utils.py:194-207: an unknown method logs a warning and means 'real'."""
+    m = str(method).lower()
+    if m not in GET_REAL_MODES:
+        import logging
+        logging.warning(f"Invalid method of get_real: {method}. Using 'real' instead.")
+        return 0
+    return GET_REAL_MODES[m]
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -26,7 +38,7 @@ class FusedPlan:
 
     def __init__(self, kind: str, shapes: "OrderedDict[str, Tuple[int, ...]]", *, n_particles: int, channels: Sequence[int],
                  num_basis_fn: int = 10, mlp: bool = True, mlp_depth: int = 6, mlp_width: int = 6, latent_mode: str = "mean",
-                 tau_s: int = 1, tau_v: int = 1):
+                 tau_s: int = 1, tau_v: int = 1, input_scale: float = 1.0):
         assert kind in ("encoder", "decoder")
         self.kind = kind
         self.names: List[str] = list(shapes)
@@ -55,6 +67,7 @@ class FusedPlan:
         d.mlp_hidden = int(mlp_depth)
         d.tau_s, d.tau_v = self.tau_s, self.tau_v
         d.n_params = self.n_params
+        d.input_scale = float(input_scale)   # encoder: p4 * scale (lgn_encoder.py:371), applied inside the library
         mode = latent_mode.lower()
         if kind == "encoder":
             if mode not in LATENT_MODES:
@@ -234,10 +247,10 @@ class _DecoderFn(torch.autograd.Function):
 
 class _ChamferFn(torch.autograd.Function):
     """ChamferLoss.forward (utils/losses/chamfer_loss/chamfer_loss.py:16-31) on the complex reconstruction with
-    get_real(..., 'sum') folded in; the gradient is produced by the same launch."""
+    get_real(..., method) (utils/train.py:292) folded in; the gradient is produced by the same launch."""
 
     @staticmethod
-    def forward(ctx, recon, target):
+    def forward(ctx, recon, target, mode):
         lib = _lib.load()
         recon = recon.contiguous()
         target = target.contiguous()
@@ -246,28 +259,29 @@ class _ChamferFn(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float64, device=dev)
         jet = torch.empty(b, dtype=torch.float64, device=dev)
         g = torch.empty_like(recon)
-        check(lib.lgae_chamfer(ptr(recon), ptr(target), b, n, m, ptr(loss), ptr(jet), None, ptr(g), _stream()), "chamfer")
+        check(lib.lgae_chamfer(ptr(recon), ptr(target), b, n, m, mode, ptr(loss), ptr(jet), None, ptr(g), _stream()), "chamfer")
         ctx.save_for_backward(g)
         return loss
 
     @staticmethod
     def backward(ctx, g_loss):
         (g,) = ctx.saved_tensors
-        return g * g_loss, None
+        return g * g_loss, None, None
 
 
-def chamfer_loss(recon: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-    """Chamfer loss (summed over the batch) between re+im of ``recon`` (2,B,N,4) and ``target`` (B,M,4)."""
-    return _ChamferFn.apply(recon, target)
+def chamfer_loss(recon: torch.Tensor, target: torch.Tensor, get_real: str = "real") -> torch.Tensor:
+    """Chamfer loss (summed over the batch) between ``get_real(recon, method)`` of the complex reconstruction (2,B,N,4) and
+    ``target`` (B,M,4).  ``get_real``: 'real' (the reference's default, main.py:295-300), 'imag', 'sum', 'mean', 'norm'."""
+    return _ChamferFn.apply(recon, target, get_real_mode(get_real))
 
 
-def chamfer_per_jet(recon: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+def chamfer_per_jet(recon: torch.Tensor, target: torch.Tensor, get_real: str = "real") -> torch.Tensor:
     """Per-jet chamfer distance (anomaly score), no gradient."""
     lib = _lib.load()
     recon, target = recon.contiguous(), target.contiguous()
     b, n, m = recon.shape[1], recon.shape[2], target.shape[1]
     jet = torch.empty(b, dtype=torch.float64, device=recon.device)
-    check(lib.lgae_chamfer(ptr(recon), ptr(target), b, n, m, None, ptr(jet), None, None, _stream()), "chamfer")
+    check(lib.lgae_chamfer(ptr(recon), ptr(target), b, n, m, get_real_mode(get_real), None, ptr(jet), None, None, _stream()), "chamfer")
     return jet
 
 

@@ -76,7 +76,7 @@ class LGNEncoder(FusedParamsMixin, CGModule):
         if self._fused_reason is None:
             self._build_plan("encoder", n_particles=self.num_input_particles, channels=list(num_channels), num_basis_fn=num_basis_fn,
                              mlp=mlp, mlp_depth=mlp_depth if mlp else 0, mlp_width=mlp_width if mlp else 0,
-                             latent_mode=map_to_latent, tau_s=tau_latent_scalars, tau_v=tau_latent_vectors)
+                             latent_mode=map_to_latent, tau_s=tau_latent_scalars, tau_v=tau_latent_vectors, input_scale=scale)
 
     # ---------------------------------------------------------------------------------------------------------
     def _why_not_fused(self):
@@ -116,15 +116,27 @@ class LGNEncoder(FusedParamsMixin, CGModule):
         p4 = torch.as_tensor(data["p4"]).to(self.device, self.dtype)
         if p4.device.type != "cuda":
             raise RuntimeError("lgn_autoencoder_b200 runs on CUDA devices only (no CPU fallback); construct the model with device='cuda'")
-        if self.fused and "scalars" not in data:
+        # the fused adjoint holds one particle per lane (N <= 32): larger jets train through the layer-level composite,
+        # whose autograd covers any N; forward-only calls keep the fused kernels (blocks of 32 particles)
+        needs_grad = torch.is_grad_enabled() and (p4.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.fused and "scalars" not in data and not (needs_grad and p4.shape[1] > 32):
             return self._forward_fused(data, p4, covariance_test)
         return self._forward_generic(data, p4, covariance_test)
 
+    @staticmethod
+    def _mask_from(data):
+        """The node mask the reference takes from the batch (lgn_encoder.py:387-398): 'labels', else 'masks', else 'mask';
+        None means p4[..., 0] != 0."""
+        for key in ("labels", "masks", "mask"):
+            if key in data:
+                return torch.as_tensor(data[key])
+        return None
+
     def _forward_fused(self, data, p4, covariance_test):
-        p4 = (p4 * self.scale if self.scale != 1.0 else p4).contiguous()
-        mask = None
-        if "labels" in data:
-            mask = (torch.as_tensor(data["labels"]).to(self.device) != 0).to(torch.uint8).contiguous()
+        p4 = p4.contiguous()   # the input scale is applied inside the library (LgaeModelDesc.input_scale)
+        mask = self._mask_from(data)
+        if mask is not None:
+            mask = (mask.to(self.device) != 0).to(torch.uint8).contiguous()
         theta, params = self._flat_params()
         holder = {} if covariance_test else None
         lat00, lat11 = fused._EncoderFn.apply(self._plan, theta, p4, mask, holder, *params)
@@ -164,8 +176,9 @@ class LGNEncoder(FusedParamsMixin, CGModule):
             jet = node_ps.sum(1, keepdim=True)
             node_ps = torch.cat([node_ps, jet], 1)
             scalars = torch.cat([scalars, normsq4(jet).abs().sqrt().unsqueeze(-1).expand(-1, -1, scalars.shape[-1])], 1)
-        if "labels" in data:
-            node_mask = torch.as_tensor(data["labels"]).to(self.device).to(torch.uint8)
+        given = self._mask_from(data)
+        if given is not None:
+            node_mask = given.to(self.device).to(torch.uint8)
             if self.jet_features:
                 node_mask = torch.cat([node_mask, torch.ones_like(node_mask[:, :1])], 1)
         else:

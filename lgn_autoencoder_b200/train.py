@@ -23,8 +23,9 @@ from . import _lib, fused
 from ._lib import check, ptr
 
 
-def training_step(encoder, decoder, p4, labels=None, l1_lambda: float = 1e-8, normalize: bool = True, l1_scale: float = 1.0):
-    """normalize_p4('overall_max') -> encoder -> decoder -> get_real('sum') + ChamferLoss (sum over the batch)
+def training_step(encoder, decoder, p4, labels=None, l1_lambda: float = 1e-8, normalize: bool = True, l1_scale: float = 1.0,
+                  get_real: str = "real"):
+    """normalize_p4('overall_max') -> encoder -> decoder -> get_real(method) + ChamferLoss (sum over the batch)
     + l1_lambda * (|theta_enc|_1 + |theta_dec|_1).  Returns (loss, reconstruction (2,B,N,4), normalised input)."""
     if normalize:
         p4, _ = fused.normalize_p4(p4)
@@ -33,7 +34,7 @@ def training_step(encoder, decoder, p4, labels=None, l1_lambda: float = 1e-8, no
         batch["labels"] = labels
     latent = encoder(batch, covariance_test=False)
     recon = decoder(latent, covariance_test=False)
-    loss = fused.chamfer_loss(recon, p4)
+    loss = fused.chamfer_loss(recon, p4, get_real)
     if l1_lambda:
         loss = loss + (l1_lambda * l1_scale) * (encoder.l1_norm() + decoder.l1_norm())
     return loss, recon, p4
@@ -67,7 +68,7 @@ class FusedTrainStep:
     """
 
     def __init__(self, encoder, decoder, batch: int, l1_lambda: float = 1e-8, l1_scale: float = 1.0, normalize: bool = True,
-                 use_labels: bool = False, use_graph: bool = True, group=None):
+                 use_labels: bool = False, use_graph: bool = True, group=None, get_real: str = "real"):
         if not (getattr(encoder, "fused", False) and getattr(decoder, "fused", False)):
             raise NotImplementedError("FusedTrainStep needs the fused (maxdim 2) encoder and decoder")
         self.enc, self.dec, self.B = encoder, decoder, int(batch)
@@ -76,6 +77,7 @@ class FusedTrainStep:
             raise NotImplementedError("the adjoint kernels hold one particle per lane: at most 32 particles per jet")
         self.l1 = float(l1_lambda) * float(l1_scale)
         self.normalize = normalize
+        self.get_real = fused.get_real_mode(get_real)
         self.group = group
         self.lib = _lib.load()
         dev = next(encoder.parameters()).device
@@ -133,7 +135,7 @@ class FusedTrainStep:
                                   1 if self.normalize else 0, ptr(self.p4), ptr(self.norm_factor), ptr(self.ws_e), ptr(self.ws_d),
                                   ptr(self.latent00), ptr(self.latent11), ptr(self.sel), ptr(self.recon), ptr(self.g_recon),
                                   ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss), ptr(self.g_all), self.off_d, ptr(self.part), self.l1,
-                                  st), "train_step")
+                                  self.get_real, st), "train_step")
         self._launch_tail()
 
     def _launch_tail(self):
@@ -169,8 +171,10 @@ class FusedTrainStep:
     def load(self, p4, labels=None):
         """Copy one batch of jets (host or device tensor, (B,N,4)) into the static input buffer."""
         self.p4_in.copy_(p4, non_blocking=True)
-        if self.mask is not None and labels is not None:
-            self.mask.copy_((labels != 0).to(torch.uint8), non_blocking=True)
+        if self.mask is not None:
+            # without labels the reference masks on p4[..., 0] != 0 (lgn_encoder.py:396-398)
+            src = labels if labels is not None else p4[..., 0]
+            self.mask.copy_((src != 0).to(torch.uint8), non_blocking=True)
 
     def _check_grads(self):
         """optimizer.zero_grad() (set_to_none=True is torch's default) drops ``param.grad``: point them at the bucket again,
@@ -218,7 +222,7 @@ class FusedTrainStep:
                                        ptr(self.host_loss), ptr(self.p4_in), ptr(self.mask), B, 1 if self.normalize else 0, ptr(self.p4),
                                        ptr(self.norm_factor), ptr(self.ws_e), ptr(self.ws_d), ptr(self.latent00), ptr(self.latent11),
                                        ptr(self.sel), ptr(self.recon), ptr(self.g_recon), ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss),
-                                       ptr(self.g_all), self.off_d, ptr(self.part), self.l1, st), "train_step_host")
+                                       ptr(self.g_all), self.off_d, ptr(self.part), self.l1, self.get_real, st), "train_step_host")
         self._launch_tail()
 
     def step_host(self, p4=None, labels=None) -> float:
@@ -227,8 +231,8 @@ class FusedTrainStep:
         self._check_grads()
         if p4 is not None and p4.data_ptr() != self.host_p4.data_ptr():
             self.host_p4.copy_(p4)
-        if self.host_mask is not None and labels is not None:
-            self.host_mask.copy_((labels != 0).to(torch.uint8))
+        if self.host_mask is not None and (labels is not None or p4 is not None):
+            self.host_mask.copy_(((labels if labels is not None else p4[..., 0]) != 0).to(torch.uint8))
         if not self.use_graph:
             self._launch_host()
         else:
@@ -335,9 +339,11 @@ class FusedInference:
     normalised input; ``recon`` (2,B,N,4), ``latent00`` / ``latent11`` and ``norm_factor`` hold the other results.
     """
 
-    def __init__(self, encoder, decoder, batch: int, normalize: bool = True, use_labels: bool = False, use_graph: bool = True):
+    def __init__(self, encoder, decoder, batch: int, normalize: bool = True, use_labels: bool = False, use_graph: bool = True,
+                 get_real: str = "real"):
         if not (getattr(encoder, "fused", False) and getattr(decoder, "fused", False)):
             raise NotImplementedError("FusedInference needs the fused (maxdim 2) encoder and decoder")
+        self.get_real = fused.get_real_mode(get_real)
         self.enc, self.dec, self.B = encoder, decoder, int(batch)
         self.pe, self.pd = encoder._plan, decoder._plan
         self.normalize = normalize
@@ -372,7 +378,7 @@ class FusedInference:
                                        ptr(self.latent11), ptr(self.sel), st), "encoder_forward")
         check(lib.lgae_decoder_forward(C.byref(pd.desc), ptr(th_d), ptr(self.latent11), B, ptr(self.ws_d), ptr(self.recon), None, st),
               "decoder_forward")
-        check(lib.lgae_chamfer(ptr(self.recon), ptr(self.p4), B, pd.n_particles, pe.n_particles, None, ptr(self.scores), None, None, st),
+        check(lib.lgae_chamfer(ptr(self.recon), ptr(self.p4), B, pd.n_particles, pe.n_particles, self.get_real, None, ptr(self.scores), None, None, st),
               "chamfer")
 
     def run(self):
@@ -396,6 +402,7 @@ class FusedInference:
 
     def score(self, p4, labels=None):
         self.p4_in.copy_(p4, non_blocking=True)
-        if self.mask is not None and labels is not None:
-            self.mask.copy_((labels != 0).to(torch.uint8), non_blocking=True)
+        if self.mask is not None:
+            src = labels if labels is not None else p4[..., 0]
+            self.mask.copy_((src != 0).to(torch.uint8), non_blocking=True)
         return self.run()

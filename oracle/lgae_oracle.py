@@ -504,8 +504,10 @@ def encoder_forward(sd: dict, cfg: dict, data, covariance_test: bool = False):
     cg = cg_table(max(maxdim + max_zf))
     p = data["p4"].to(torch.float64) * cfg.get("scale", 1.0)
     scalars = normsq4(p).abs().sqrt().unsqueeze(-1)                       # lgn_encoder.py:376
-    if "labels" in data:
-        node_mask = data["labels"].to(torch.uint8)
+    for key in ("labels", "masks", "mask"):                                # lgn_encoder.py:387-395
+        if key in data:
+            node_mask = data[key].to(torch.uint8)
+            break
     else:
         node_mask = (data["p4"][..., 0] != 0).to(torch.uint8)
     edge_mask = node_mask.unsqueeze(1) * node_mask.unsqueeze(2)           # :403
@@ -567,6 +569,20 @@ def get_real_sum(x: torch.Tensor) -> torch.Tensor:
     return x[0] + x[1]                                                      # utils/utils.py:201-202
 
 
+def get_real(x: torch.Tensor, method: str = "real", eps: float = 1e-16) -> torch.Tensor:
+    """utils/utils.py:194-207 (an unknown method means 'real')."""
+    m = method.lower()
+    if m == "imag":
+        return x[1]
+    if m == "norm":
+        return torch.sqrt(torch.pow(x[0], 2) + torch.pow(x[1], 2) + eps)
+    if m == "sum":
+        return x[0] + x[1]
+    if m == "mean":
+        return (x[0] + x[1]) / 2
+    return x[0]
+
+
 def chamfer_loss(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """chamfer_loss.py:16-31 over distance_sq.py:263-304 (p=2): squared Euclidean distance on all
     four components, **summed** over the batch."""
@@ -579,11 +595,11 @@ def l1_norm(sd: dict) -> torch.Tensor:
     return sum(p.abs().sum() for p in sd.values())                         # lgn_encoder.py:249-250
 
 
-def training_step(enc_sd, dec_sd, enc_cfg, dec_cfg, data, l1_lambda: float = 1e-8):
+def training_step(enc_sd, dec_sd, enc_cfg, dec_cfg, data, l1_lambda: float = 1e-8, get_real_method: str = "sum"):
     """utils/train.py:283-327 minus optimizer: returns (loss, latent, recons)."""
     latent = encoder_forward(enc_sd, enc_cfg, data)
     recons_c = decoder_forward(dec_sd, dec_cfg, latent)
-    recons = get_real_sum(recons_c)
+    recons = get_real(recons_c, get_real_method)
     p4 = data["p4"] if isinstance(data, dict) else data
     loss = chamfer_loss(recons, p4.to(torch.float64))
     if l1_lambda:

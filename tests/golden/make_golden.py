@@ -66,6 +66,8 @@ def build(cfg):
                      tau_latent_scalars=cfg["tau_s"], tau_latent_vectors=cfg["tau_v"], num_channels=cfg["enc_channels"],
                      jet_features=False, map_to_latent=cfg["map_to_latent"], **common)
     mult = len(cfg["map_to_latent"].split("&")) if "&" in cfg["map_to_latent"] else 1
+    if cfg["map_to_latent"] == "mix":
+        mult = 1
     dec = LGNDecoder(tau_latent_scalars=cfg["tau_s"] * mult, tau_latent_vectors=cfg["tau_v"] * mult,
                      num_output_particles=cfg["n"], tau_output_scalars=1, tau_output_vectors=1,
                      num_channels=cfg["dec_channels"], cg_dict=enc.cg_dict, **common)
@@ -84,8 +86,19 @@ def run(cfg):
     batch["p4"] = p4n
 
     latent = enc(batch, covariance_test=False)
+    if cfg.get("encoder_only"):
+        # the reference's own decoder cannot consume a 'sum' latent (its spurious extra axis breaks RadPolyTrig.forward,
+        # position_levels.py:171-207): pin the encoder alone, with the gradient of a fixed quadratic form of the latent
+        loss = sum((v * v).sum() * (0.5 + i) for i, v in enumerate(latent.values()))
+        loss.backward()
+        return {"cfg": cfg, "batch": {k: v.clone() for k, v in batch.items()},
+                "enc_state": {k: v.detach().clone() for k, v in enc.state_dict().items()},
+                "dec_state": {k: v.detach().clone() for k, v in dec.state_dict().items()},
+                "latent": gvec_to_dict(latent), "loss": loss.detach().clone(),
+                "grads_enc": {k: (None if p.grad is None else p.grad.clone()) for k, p in enc.named_parameters()},
+                "torch_version": torch.__version__}
     recons = dec(latent, covariance_test=False)
-    p4_recons = get_real(recons, "sum")
+    p4_recons = get_real(recons, cfg.get("get_real", "sum"))
     loss = ChamferLoss(device=torch.device("cpu"))(p4_recons, p4n) + 1e-8 * (enc.l1_norm() + dec.l1_norm())
     loss.backward()
     grads_enc = {k: (None if p.grad is None else p.grad.clone()) for k, p in enc.named_parameters()}
@@ -128,6 +141,19 @@ CONFIGS = {
     # more than 32 particles per jet (two particle blocks per CTA in the forward kernels; cfg-5 has 150): forward parity
     "n40_b2": dict(seed=9, batch=2, n=40, maxdim=2, enc_channels=[2, 2, 3, 3], dec_channels=[3, 3, 2, 2], tau_s=1, tau_v=4,
                    map_to_latent="min&max", mass_scale=1e-6, pad=True, mlp_depth=2, mlp_width=2),
+    # cfg-4 of BASELINE.json at its real shape (30 particles, maxdim 3, 6-6-8-8 / 8-8-6-6, 'mix' latent map, MLP 6 x 6), two jets
+    "cfg4_b2": dict(seed=11, batch=2, n=30, maxdim=3, enc_channels=[6, 6, 8, 8], dec_channels=[8, 8, 6, 6], tau_s=1, tau_v=8,
+                    map_to_latent="mix", mass_scale=1e-6, pad=False),
+    # the remaining pooling modes (lgn_encoder.py:419-476): 'sum' (keeps a spurious axis) and a '+' combination
+    "sum_n6": dict(seed=13, batch=2, n=6, maxdim=2, enc_channels=[2, 2, 3], dec_channels=[3, 2, 2], tau_s=1, tau_v=2,
+                   map_to_latent="sum", mass_scale=0.1, pad=False, mlp_depth=2, mlp_width=2, encoder_only=True),
+    "minplusmax_n6": dict(seed=15, batch=2, n=6, maxdim=2, enc_channels=[2, 2, 3], dec_channels=[3, 2, 2], tau_s=1, tau_v=2,
+                          map_to_latent="min+max", mass_scale=0.1, pad=True, mlp_depth=2, mlp_width=2),
+    # get_real 'real' (the reference's default, main.py:295-300) and 'norm'
+    "real_n6": dict(seed=17, batch=3, n=6, maxdim=2, enc_channels=[2, 2, 3], dec_channels=[3, 2, 2], tau_s=1, tau_v=2,
+                    map_to_latent="min&max", mass_scale=0.1, pad=False, mlp_depth=2, mlp_width=2, get_real="real"),
+    "norm_n6": dict(seed=17, batch=3, n=6, maxdim=2, enc_channels=[2, 2, 3], dec_channels=[3, 2, 2], tau_s=1, tau_v=2,
+                    map_to_latent="min&max", mass_scale=0.1, pad=False, mlp_depth=2, mlp_width=2, get_real="norm"),
 }
 
 

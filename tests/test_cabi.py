@@ -70,7 +70,8 @@ def test_bad_arguments_are_rejected_before_any_launch():
     # null pointers -> LGAE_E_BADARG, never a crash; an encoder descriptor is refused by the decoder entry point
     assert lib.lgae_encoder_forward(d, None, None, None, 4, None, None, None, None, None) == -1
     assert lib.lgae_decoder_forward(d, None, None, 4, None, None, None, None) == -1
-    assert lib.lgae_chamfer(None, None, 4, 30, 30, None, None, None, None, None) == -1
+    assert lib.lgae_chamfer(None, None, 4, 30, 30, 2, None, None, None, None, None) == -1
+    assert lib.lgae_chamfer(None, None, 0, 30, 30, 7, None, None, None, None, None) == -1   # unknown get_real mode
     assert lib.lgae_normalize_p4(None, 4, 30, None, None, None) == -1
     assert lib.lgae_encoder_forward(None, None, None, None, 4, None, None, None, None, None) == -1
     bad = _lib.LgaeModelDesc()

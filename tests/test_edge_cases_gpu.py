@@ -62,7 +62,7 @@ def test_forward_backward_match_oracle(name):
     # product path: module API + autograd
     latent = enc(batch)
     recon = dec(latent)
-    loss = fused.chamfer_loss(recon, batch["p4"]) + 1e-8 * (enc.l1_norm() + dec.l1_norm())
+    loss = fused.chamfer_loss(recon, batch["p4"], "sum") + 1e-8 * (enc.l1_norm() + dec.l1_norm())
     loss.backward()
     # oracle on the same weights
     enc_sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
@@ -96,7 +96,7 @@ def test_empty_batch_is_a_no_op():
     th_d, _ = dec._flat_params()
     recon, _, ws_d = fused.decoder_forward_raw(dec._plan, th_d, lat11)
     assert recon.shape == (2, 0, 6, 4)
-    assert fused.chamfer_loss(recon, p4).item() == 0.0
+    assert fused.chamfer_loss(recon, p4, "sum").item() == 0.0
     g = fused.encoder_backward_raw(enc._plan, theta, p4, None, ws, sel, None, lat11)
     assert torch.count_nonzero(g).item() == 0
 
@@ -108,7 +108,7 @@ def test_unsupported_configurations_fail_loudly():
     cfg = dict(CASES["min_pool"], n=40)
     enc, dec = _build(cfg, dev)
     with pytest.raises(NotImplementedError):
-        FusedTrainStep(enc, dec, 2)
+        FusedTrainStep(enc, dec, 2, get_real="sum")
     p4 = torch.rand((2, 40, 4), dtype=torch.float64, device=dev) + 0.1
     rec = dec(enc({"p4": p4}))
     with pytest.raises((NotImplementedError, RuntimeError)):

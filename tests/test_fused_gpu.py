@@ -70,7 +70,7 @@ def test_loss_and_gradients_match_reference(name):
     g = load_golden(name)
     r = _run(g, dev)
     recon = r["recon"].clone().requires_grad_(True)
-    loss = fused.chamfer_loss(recon, r["p4"])
+    loss = fused.chamfer_loss(recon, r["p4"], "sum")
     l1 = 1e-8 * (r["th_e"].abs().sum() + r["th_d"].abs().sum())
     assert abs((loss + l1).item() - g["loss"].item()) < 1e-11 * abs(g["loss"].item())
     loss.backward()

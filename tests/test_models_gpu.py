@@ -31,7 +31,7 @@ def load(name, dev):
     return g, enc, dec, batch
 
 
-@pytest.mark.parametrize("name", ["cfg1_b3", "pad_n8", "mean_n6", "md3_mix_n5"])
+@pytest.mark.parametrize("name", ["cfg1_b3", "pad_n8", "mean_n6", "md3_mix_n5", "cfg4_b2", "minplusmax_n6", "real_n6", "norm_n6"])
 def test_module_forward_backward_matches_reference(name):
     from lgn_autoencoder_b200 import fused
     dev = torch.device("cuda:0")
@@ -42,7 +42,7 @@ def test_module_forward_backward_matches_reference(name):
     for key, val in g["latent"].items():
         assert rel_err(latent[eval(key)], val) < 1e-10, ("latent", key, rel_err(latent[eval(key)], val))
     assert rel_err(recon, g["recons"]) < 1e-10
-    loss = fused.chamfer_loss(recon, batch["p4"]) + 1e-8 * (enc.l1_norm() + dec.l1_norm())
+    loss = fused.chamfer_loss(recon, batch["p4"], g["cfg"].get("get_real", "sum")) + 1e-8 * (enc.l1_norm() + dec.l1_norm())
     assert abs(loss.item() - g["loss"].item()) < 1e-10 * abs(g["loss"].item())
     loss.backward()
     mine_e = {k: p.grad for k, p in enc.named_parameters()}
@@ -61,6 +61,71 @@ def test_module_forward_backward_matches_reference(name):
         assert [str(k) for k in mine.keys()] == list(ref.keys()), (i, list(mine.keys()), list(ref.keys()))
         for key, val in ref.items():
             assert rel_err(mine[eval(key)], val) < 1e-10, (i, key, rel_err(mine[eval(key)], val))
+
+
+def test_sum_pooling_encoder_matches_reference():
+    """map_to_latent='sum' (lgn_encoder.py:421-427): latent with the reference's spurious extra axis, and the encoder's
+    gradients of a fixed quadratic form of it (the reference's decoder cannot consume this latent; encoder only)."""
+    from tests.test_oracle_golden import sum_latent_loss
+    dev = torch.device("cuda:0")
+    g, enc, dec, batch = load("sum_n6", dev)
+    assert enc.fused
+    latent = enc(batch)
+    for key, val in g["latent"].items():
+        assert latent[eval(key)].shape == val.shape
+        assert rel_err(latent[eval(key)], val) < 1e-10, ("latent", key)
+    loss = sum_latent_loss(latent)
+    assert abs(loss.item() - g["loss"].item()) < 1e-10 * abs(g["loss"].item())
+    loss.backward()
+    ref = {k: v for k, v in g["grads_enc"].items() if v is not None}
+    assert_grads_close({k: p.grad for k, p in enc.named_parameters()}, ref)
+    for k, p in enc.named_parameters():
+        if g["grads_enc"][k] is None:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, k
+
+
+def test_input_scale_and_mask_keys():
+    """encoder.scale multiplies p4 inside the library (lgn_encoder.py:371), on the module path and in FusedTrainStep; the node
+    mask may come as 'labels', 'masks' or 'mask' (lgn_encoder.py:387-395)."""
+    from lgn_autoencoder_b200 import fused
+    from lgn_autoencoder_b200.train import FusedTrainStep
+    from oracle import lgae_oracle as orc
+    dev = torch.device("cuda:0")
+    g, enc, dec, batch = load("pad_n8", dev)
+    cfg = g["cfg"]
+    scale = 1.7
+    from lgn_autoencoder_b200.models import LGNEncoder
+    enc_s = LGNEncoder(num_input_particles=cfg["n"], tau_input_scalars=1, tau_input_vectors=1, tau_latent_scalars=cfg["tau_s"],
+                       tau_latent_vectors=cfg["tau_v"], num_channels=cfg["enc_channels"], jet_features=False, map_to_latent=cfg["map_to_latent"],
+                       maxdim=[2], num_basis_fn=10, max_zf=[1], weight_init="randn", level_gain=[1.0], activation="leakyrelu", mlp=True,
+                       mlp_depth=cfg["mlp_depth"], mlp_width=cfg["mlp_width"], scale=scale, device=dev, dtype=torch.float64)
+    enc_s.load_state_dict(g["enc_state"])
+    assert enc_s.fused
+    enc_sd = {k: v.clone().requires_grad_(True) for k, v in g["enc_state"].items()}
+    dec_sd = {k: v.clone().requires_grad_(True) for k, v in g["dec_state"].items()}
+    ecfg = dict(num_channels=cfg["enc_channels"], maxdim=[2], max_zf=[1], map_to_latent=cfg["map_to_latent"], scale=scale)
+    dcfg = dict(num_channels=cfg["dec_channels"], maxdim=[2], max_zf=[1])
+    cpu_batch = {k: v.cpu() for k, v in batch.items()}
+    ref_loss, ref_lat, ref_recon = orc.training_step(enc_sd, dec_sd, ecfg, dcfg, cpu_batch, l1_lambda=1e-8, get_real_method="real")
+    ref_loss.backward()
+    for key in ("labels", "masks", "mask"):
+        data = {"p4": batch["p4"], key: batch["labels"]}
+        lat = enc_s(data)
+        assert rel_err(lat[(1, 1)], ref_lat[(1, 1)]) < 1e-10 and rel_err(lat[(0, 0)], ref_lat[(0, 0)]) < 1e-10, key
+    recon = dec(lat)
+    loss = fused.chamfer_loss(recon, batch["p4"], "real") + 1e-8 * (enc_s.l1_norm() + dec.l1_norm())
+    assert abs(loss.item() - ref_loss.item()) < 1e-10 * abs(ref_loss.item())
+    loss.backward()
+    assert_grads_close({k: p.grad for k, p in enc_s.named_parameters()}, {k: v.grad for k, v in enc_sd.items()})
+    assert_grads_close({k: p.grad for k, p in dec.named_parameters()}, {k: v.grad for k, v in dec_sd.items()})
+    step = FusedTrainStep(enc_s, dec, batch["p4"].shape[0], l1_lambda=1e-8, normalize=False, use_labels=True, get_real="real")
+    l_step = step.step(batch["p4"], batch["labels"]).item()
+    assert abs(l_step - ref_loss.item()) < 1e-10 * abs(ref_loss.item())
+    assert_grads_close({k: p.grad for k, p in enc_s.named_parameters()}, {k: v.grad for k, v in enc_sd.items()})
+    assert_grads_close({k: p.grad for k, p in dec.named_parameters()}, {k: v.grad for k, v in dec_sd.items()})
+    # without labels the mask falls back to p4[..., 0] != 0 (lgn_encoder.py:396-398): identical here, the padded rows are zero
+    l_nolabels = step.step(batch["p4"]).item()
+    assert l_nolabels == l_step
 
 
 def test_state_dict_roundtrip_and_optimizer_step():
@@ -114,3 +179,67 @@ def test_equivariance_no_worse_than_reference():
         for i, (ml, rl) in enumerate(zip(mine, ref)):
             for j, (m, r) in enumerate(zip(ml, rl)):
                 assert m[(1, 1)] <= max(3 * r["(1, 1)"], 1e-10), (kind, i, j, m, r)
+
+
+def test_batched_equivariance_harness_matches_sequential():
+    """(f2) The 26 transforms of a covariance test run as ONE batch of 26 B jets; the deviation tables equal those of the
+    transform-by-transform evaluation (per-jet results do not depend on the batch they are in)."""
+    from lgn_autoencoder_b200.models.autotest import covariance_test, lgn_tests as harness
+    from lgn_autoencoder_b200.models.autotest import lgn_tests as lgn_tests_fn, permutation_invariance_test
+    import lgn_autoencoder_b200.models.autotest.lgn_tests as mod
+    dev = torch.device("cuda:0")
+    g = load_golden("equivariance_cfg1")
+    enc, dec = build(g["cfg"], dev)
+    enc.load_state_dict(g["enc_state"])
+    dec.load_state_dict(g["dec_state"])
+    data = {"p4": g["p4"].clone()}
+    batched = covariance_test(enc, dec, dict(data), "boost", axis="z", unit="TeV")
+    old = mod.MAX_JETS_PER_PASS
+    mod.MAX_JETS_PER_PASS = 1          # one transform per model evaluation, as the reference does
+    try:
+        seq = covariance_test(enc, dec, dict(data), "boost", axis="z", unit="TeV")
+    finally:
+        mod.MAX_JETS_PER_PASS = old
+    assert batched["gammas"] == seq["gammas"]
+    for a, b in zip(batched["boost_dev_output"], seq["boost_dev_output"]):
+        assert a == b
+    for la, lb in zip(batched["boost_dev_internal"], seq["boost_dev_internal"]):
+        assert la == lb
+    # permutation test: reference semantics (per-jet permutation of the real particles, 'max'-mode deviations per irrep)
+    inv, equi = permutation_invariance_test(enc, dec, dict(data))
+    assert set(inv) == {(0, 0), (1, 1)} and set(equi) == {(0, 0), (1, 1)}
+    assert equi[(1, 1)] < 1e-8 and equi[(0, 0)] < 1e-8
+    # the reference's positional signature (args, encoder, decoder, dataloader, axis, alpha_max, theta_max, cg_dict, unit) and num_test_batch
+    import types
+    res = lgn_tests_fn(types.SimpleNamespace(num_test_batch=1), enc, dec, [dict(data), dict(data)], "z", 10.0, None, enc.cg_dict, "TeV")
+    assert len(res["gammas"]) == 26 and len(res["boost_dev_output"]) == 26
+    for a, b in zip(res["boost_dev_output"], batched["boost_dev_output"]):
+        assert a == b
+
+
+def test_reference_cli_runs_unchanged_through_the_shim(tmp_path):
+    """The reference's own main.py -> test.py -> covariance_test.py (baseline/_ref, unmodified) against this repository's `lgn`
+    package on the GPU: 1 epoch of training on synthetic jets in the reference's .pt format, inference, equivariance test."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "baseline", "_ref", "lgn")):
+        pytest.skip("baseline/_ref (copy of the unmodified reference, tools/setup_reference.py) is not present")
+    out = str(tmp_path / "refcli")
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "run_reference_cli.py"), "--out", out, "--device", "cuda", "--jets", "256",
+                        "--batch", "64", "--epochs", "1", "--test-jets", "32"], capture_output=True, text=True, timeout=1500)
+    logs = ""
+    for name in ("main.log", "test.log", "covariance_test.log"):
+        f = os.path.join(out, name)
+        if os.path.exists(f):
+            logs += f"\n==== {name} ====\n" + open(f).read()[-3000:]
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:] + logs
+    summary = json.load(open(os.path.join(out, "summary.json")))
+    assert summary["main"]["rc"] == 0 and summary["test"]["rc"] == 0 and summary["covariance_test"]["rc"] == 0
+    main_log = open(os.path.join(out, "main.log")).read()
+    assert "lgn_autoencoder_b200" in main_log or "Training completed" in main_log
+    assert "Boost equivariance test result" in main_log
+    exp = summary["model_path"]
+    assert os.path.exists(os.path.join(exp, "weights_encoder")) and os.path.exists(os.path.join(exp, "weights_decoder"))

@@ -7,7 +7,7 @@ from oracle import lgae_oracle as orc
 from tests.helpers import dec_cfg, enc_cfg, load_golden, rel_err
 
 TOL = 1e-12  # fp64, identical operation order up to BLAS/summation details
-CASES = ["cfg1_b3", "pad_n8", "mean_n6", "md3_mix_n5", "n40_b2"]
+CASES = ["cfg1_b3", "pad_n8", "mean_n6", "md3_mix_n5", "n40_b2", "cfg4_b2", "minplusmax_n6", "real_n6", "norm_n6"]
 
 
 def test_cg_coefficients_match_reference():
@@ -62,7 +62,8 @@ def test_loss_and_gradients_match_reference(name):
     cfg = g["cfg"]
     enc_sd = {k: v.clone().requires_grad_(True) for k, v in g["enc_state"].items()}
     dec_sd = {k: v.clone().requires_grad_(True) for k, v in g["dec_state"].items()}
-    loss, _, _ = orc.training_step(enc_sd, dec_sd, enc_cfg(cfg), dec_cfg(cfg), g["batch"], l1_lambda=1e-8)
+    loss, _, _ = orc.training_step(enc_sd, dec_sd, enc_cfg(cfg), dec_cfg(cfg), g["batch"], l1_lambda=1e-8,
+                                   get_real_method=cfg.get("get_real", "sum"))
     assert abs(loss.item() - g["loss"].item()) < 1e-12 * abs(g["loss"].item())
     loss.backward()
     for sd, grads in ((enc_sd, g["grads_enc"]), (dec_sd, g["grads_dec"])):
@@ -74,3 +75,27 @@ def test_loss_and_gradients_match_reference(name):
                 continue
             assert mine is not None, k
             assert rel_err(mine, ref) < 1e-10, (k, rel_err(mine, ref))
+
+
+def sum_latent_loss(latent):
+    """The fixed quadratic form tests/golden/make_golden.py differentiates for the encoder-only 'sum' fixture."""
+    return sum((v * v).sum() * (0.5 + i) for i, v in enumerate(latent.values()))
+
+
+def test_sum_pooling_encoder_matches_reference():
+    """'sum' pooling (lgn_encoder.py:421-427) keeps a spurious axis the reference's decoder cannot consume: encoder only."""
+    g = load_golden("sum_n6")
+    cfg = g["cfg"]
+    enc_sd = {k: v.clone().requires_grad_(True) for k, v in g["enc_state"].items()}
+    latent = orc.encoder_forward(enc_sd, enc_cfg(cfg), g["batch"])
+    for key, val in g["latent"].items():
+        assert latent[eval(key)].shape == val.shape
+        assert rel_err(latent[eval(key)], val) < TOL, ("latent", key)
+    loss = sum_latent_loss(latent)
+    assert abs(loss.item() - g["loss"].item()) < 1e-12 * abs(g["loss"].item())
+    loss.backward()
+    for k, ref in g["grads_enc"].items():
+        if ref is None:
+            assert enc_sd[k].grad is None or enc_sd[k].grad.abs().max().item() == 0.0, k
+        else:
+            assert rel_err(enc_sd[k].grad, ref) < 1e-10, k

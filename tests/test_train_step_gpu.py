@@ -13,7 +13,7 @@ def test_fused_train_step_matches_reference(use_graph):
     from lgn_autoencoder_b200.train import FusedTrainStep
     dev = torch.device("cuda:0")
     g, enc, dec, batch = load("cfg1_b3", dev)
-    step = FusedTrainStep(enc, dec, batch["p4"].shape[0], l1_lambda=1e-8, normalize=False, use_graph=use_graph)
+    step = FusedTrainStep(enc, dec, batch["p4"].shape[0], l1_lambda=1e-8, normalize=False, use_graph=use_graph, get_real="sum")
     for _ in range(3):   # replays must be idempotent
         loss = step.step(batch["p4"])
     torch.cuda.synchronize()
@@ -30,14 +30,14 @@ def test_fused_train_step_padded_jets_and_optimizer():
     dev = torch.device("cuda:0")
     g, enc, dec, batch = load("pad_n8", dev)
     b = batch["p4"].shape[0]
-    step = FusedTrainStep(enc, dec, b, l1_lambda=1e-8, normalize=True, use_labels=True, use_graph=True)
+    step = FusedTrainStep(enc, dec, b, l1_lambda=1e-8, normalize=True, use_labels=True, use_graph=True, get_real="sum")
     opt = torch.optim.SGD(list(enc.parameters()) + list(dec.parameters()), lr=1e-4)
     l0 = step.step(batch["p4"], batch["labels"]).item()
     # the same step through the module API + autograd
     g_fused = {k: p.grad.clone() for k, p in list(enc.named_parameters()) + list(dec.named_parameters())}
     for p in list(enc.parameters()) + list(dec.parameters()):
         p.grad = None
-    loss, _, _ = training_step(enc, dec, batch["p4"], labels=batch["labels"], l1_lambda=1e-8)
+    loss, _, _ = training_step(enc, dec, batch["p4"], labels=batch["labels"], l1_lambda=1e-8, get_real="sum")
     loss.backward()
     assert abs(loss.item() - l0) < 1e-12 * abs(l0)
     g_mod = {k: p.grad.clone() for k, p in list(enc.named_parameters()) + list(dec.named_parameters())}
@@ -57,7 +57,7 @@ def test_step_host_matches_step():
     from lgn_autoencoder_b200.train import FusedTrainStep
     dev = torch.device("cuda:0")
     g, enc, dec, batch = load("cfg1_b3", dev)
-    step = FusedTrainStep(enc, dec, batch["p4"].shape[0], l1_lambda=1e-8, normalize=False, use_graph=True)
+    step = FusedTrainStep(enc, dec, batch["p4"].shape[0], l1_lambda=1e-8, normalize=False, use_graph=True, get_real="sum")
     l_dev = step.step(batch["p4"]).item()
     g_dev = step.g_e.clone()
     for _ in range(2):
@@ -79,7 +79,7 @@ def test_fused_inference_matches_module_forward_and_oracle_at_150_particles():
                mlp_width=6)
     enc, dec = _build(cfg, dev)
     data = orc.synthetic_jets(2, 150, seed=22, mass_scale=1e-6, pad=True)
-    inf = FusedInference(enc, dec, 2, normalize=True, use_labels=True)
+    inf = FusedInference(enc, dec, 2, normalize=True, use_labels=True, get_real="sum")
     for _ in range(2):
         scores = inf.score(data["p4"], data["labels"]).clone()
     # module path
@@ -87,7 +87,7 @@ def test_fused_inference_matches_module_forward_and_oracle_at_150_particles():
     with torch.no_grad():
         rec = dec(enc({"p4": p4n, "labels": data["labels"].to(dev)}))
     assert torch.equal(rec, inf.recon)
-    assert torch.equal(fused.chamfer_per_jet(rec, p4n), scores)
+    assert torch.equal(fused.chamfer_per_jet(rec, p4n, "sum"), scores)
     # oracle
     pn, _ = orc.normalize_p4_overall_max(data["p4"])
     enc_sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
@@ -113,9 +113,9 @@ def test_flat_adam_matches_torch_adam(in_graph):
     _, enc_b, dec_b, _ = load("cfg1_b3", dev)
     b = batch["p4"].shape[0]
     lr, wd = 3e-3, 1e-2
-    sa = FusedTrainStep(enc_a, dec_a, b, l1_lambda=1e-8, normalize=True, use_graph=True)
+    sa = FusedTrainStep(enc_a, dec_a, b, l1_lambda=1e-8, normalize=True, use_graph=True, get_real="sum")
     opts = [torch.optim.Adam(enc_a.parameters(), lr, weight_decay=wd), torch.optim.Adam(dec_a.parameters(), lr, weight_decay=wd)]
-    sb = FusedTrainStep(enc_b, dec_b, b, l1_lambda=1e-8, normalize=True, use_graph=True)
+    sb = FusedTrainStep(enc_b, dec_b, b, l1_lambda=1e-8, normalize=True, use_graph=True, get_real="sum")
     flat = FlatAdam(sb, lr=lr, weight_decay=wd)
     if in_graph:
         sb.attach_optimizer(flat)
@@ -152,9 +152,9 @@ def test_flat_rmsprop_matches_torch_rmsprop():
     _, enc_b, dec_b, _ = load("cfg1_b3", dev)
     b = batch["p4"].shape[0]
     kw = dict(lr=2e-3, eps=1e-16, momentum=0.9)
-    sa = FusedTrainStep(enc_a, dec_a, b, l1_lambda=1e-8, use_graph=True)
+    sa = FusedTrainStep(enc_a, dec_a, b, l1_lambda=1e-8, use_graph=True, get_real="sum")
     opts = [torch.optim.RMSprop(enc_a.parameters(), **kw), torch.optim.RMSprop(dec_a.parameters(), **kw)]
-    sb = FusedTrainStep(enc_b, dec_b, b, l1_lambda=1e-8, use_graph=True)
+    sb = FusedTrainStep(enc_b, dec_b, b, l1_lambda=1e-8, use_graph=True, get_real="sum")
     sb.attach_optimizer(FlatRMSprop(sb, **kw))
     for it in range(4):
         la = sa.step(batch["p4"]).item()
@@ -180,8 +180,8 @@ def test_full_size_step_properties():
     B, N = CFG["batch"], CFG["n"]
     assert (B, N) == (512, 30)
     p4 = synthetic_jets(B, N, seed=11).to(dev)
-    full = FusedTrainStep(enc, dec, B, l1_lambda=0.0, use_graph=True)
-    half = FusedTrainStep(enc, dec, B // 2, l1_lambda=0.0, use_graph=False)
+    full = FusedTrainStep(enc, dec, B, l1_lambda=0.0, use_graph=True, get_real="sum")
+    half = FusedTrainStep(enc, dec, B // 2, l1_lambda=0.0, use_graph=False, get_real="sum")
     loss = full.step(p4).item()
     g_full, recon, jet_loss, lat = full.g_all.clone(), full.recon.clone(), full.jet_loss.clone(), full.latent11.clone()
     assert torch.isfinite(g_full).all() and g_full.abs().max().item() > 0
@@ -211,10 +211,70 @@ def test_step_host_with_padded_jets_matches_step():
     dev = torch.device("cuda:0")
     g, enc, dec, batch = load("pad_n8", dev)
     b = batch["p4"].shape[0]
-    step = FusedTrainStep(enc, dec, b, l1_lambda=1e-8, normalize=True, use_labels=True, use_graph=True)
+    step = FusedTrainStep(enc, dec, b, l1_lambda=1e-8, normalize=True, use_labels=True, use_graph=True, get_real="sum")
     l_dev = step.step(batch["p4"], batch["labels"]).item()
     g_dev = step.g_all.clone()
     step.mask.zero_()                      # make sure the host entry really re-uploads the mask
     l_host = step.step_host(batch["p4"].cpu(), batch["labels"].cpu())
     assert l_host == l_dev and torch.equal(step.g_all, g_dev)
     assert l_host == step.step_host()      # replay from the staged pinned buffers
+
+
+@pytest.mark.parametrize("variant", ["near_massless", "padded_labels"])
+def test_cfg1_full_batch_matches_oracle(variant):
+    """BASELINE configs[1] at its REAL batch (512 jets x 30 particles) against the CPU oracle on the same weights and jets
+    (about 3 s of CPU work per variant): FusedTrainStep (CUDA graph, the benchmarked path) and the module/autograd path --
+    latent (0,0) / (1,1), reconstruction, loss and every parameter gradient within 1e-10.  The persistent kernels take a
+    different trip count at 15 360 rows than in the 3-jet fixtures."""
+    from bench import CFG, build_models
+    from lgn_autoencoder_b200.train import FusedTrainStep, training_step
+    from oracle import lgae_oracle as orc
+    dev = torch.device("cuda:0")
+    enc, dec = build_models(dev)
+    B, N = CFG["batch"], CFG["n"]
+    data = orc.synthetic_jets(B, N, seed=21, mass_scale=1e-6, pad=(variant == "padded_labels"))
+    labels = data.get("labels")
+    pn, _ = orc.normalize_p4_overall_max(data["p4"])
+    enc_sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in enc.state_dict().items()}
+    dec_sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    ecfg = dict(num_channels=CFG["enc_channels"], maxdim=[2], max_zf=[1], map_to_latent=CFG["map_to_latent"])
+    dcfg = dict(num_channels=CFG["dec_channels"], maxdim=[2], max_zf=[1])
+    batch = {"p4": pn} if labels is None else {"p4": pn, "labels": labels}
+    ref_loss, ref_lat, ref_recon = orc.training_step(enc_sd, dec_sd, ecfg, dcfg, batch, l1_lambda=CFG["l1_lambda"])
+    ref_loss.backward()
+    ref_ge, ref_gd = {k: v.grad for k, v in enc_sd.items()}, {k: v.grad for k, v in dec_sd.items()}
+
+    step = FusedTrainStep(enc, dec, B, l1_lambda=CFG["l1_lambda"], normalize=True, use_labels=labels is not None, use_graph=True,
+                          get_real="sum")
+    for _ in range(2):
+        loss = step.step(data["p4"].to(dev), None if labels is None else labels.to(dev)).item()
+    errs = {"loss": abs(loss - ref_loss.item()) / abs(ref_loss.item()), "recon": rel_err(step.recon, ref_recon),
+            "lat00": rel_err(step.latent00, ref_lat[(0, 0)]), "lat11": rel_err(step.latent11, ref_lat[(1, 1)])}
+    print(variant, "fused step", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert all(v < 1e-10 for v in errs.values()), errs
+    assert_grads_close({k: p.grad for k, p in enc.named_parameters()}, ref_ge)
+    assert_grads_close({k: p.grad for k, p in dec.named_parameters()}, ref_gd)
+    # the module API + autograd on the same jets
+    for p in list(enc.parameters()) + list(dec.parameters()):
+        p.grad = None
+    loss_m, recon_m, _ = training_step(enc, dec, data["p4"].to(dev), labels=None if labels is None else labels.to(dev),
+                                       l1_lambda=CFG["l1_lambda"], get_real="sum")
+    loss_m.backward()
+    assert abs(loss_m.item() - ref_loss.item()) < 1e-10 * abs(ref_loss.item())
+    assert rel_err(recon_m, ref_recon) < 1e-10
+    assert_grads_close({k: p.grad for k, p in enc.named_parameters()}, ref_ge)
+    assert_grads_close({k: p.grad for k, p in dec.named_parameters()}, ref_gd)
+
+
+@pytest.mark.parametrize("name", ["real_n6", "norm_n6"])
+def test_fused_train_step_get_real_modes(name):
+    """get_real 'real' (the reference's default, main.py:295-300) and 'norm' through the fused step, against the reference."""
+    from lgn_autoencoder_b200.train import FusedTrainStep
+    dev = torch.device("cuda:0")
+    g, enc, dec, batch = load(name, dev)
+    step = FusedTrainStep(enc, dec, batch["p4"].shape[0], l1_lambda=1e-8, normalize=False, get_real=g["cfg"]["get_real"])
+    loss = step.step(batch["p4"]).item()
+    assert abs(loss - g["loss"].item()) < 1e-10 * abs(g["loss"].item())
+    assert rel_err(step.recon, g["recons"]) < 1e-10
+    assert_grads_close({k: p.grad for k, p in enc.named_parameters()}, g["grads_enc"])
+    assert_grads_close({k: p.grad for k, p in dec.named_parameters()}, g["grads_dec"])

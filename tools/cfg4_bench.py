@@ -29,7 +29,7 @@ def step():
     for m in (enc, dec):
         for p in m.parameters():
             p.grad = None
-    loss, _, _ = training_step(enc, dec, p4)
+    loss, _, _ = training_step(enc, dec, p4, get_real="sum")
     loss.backward()
     return loss
 
@@ -65,7 +65,7 @@ try:
         for _ in range(2):
             for p in params:
                 p.grad = None
-            l, _, _ = training_step(enc, dec, p4)
+            l, _, _ = training_step(enc, dec, p4, get_real="sum")
             l.backward()
             del l
     torch.cuda.current_stream().wait_stream(side)
@@ -74,7 +74,7 @@ try:
     for p in params:
         p.grad = None
     with torch.cuda.graph(g):
-        static_loss, _, _ = training_step(enc, dec, p4)
+        static_loss, _, _ = training_step(enc, dec, p4, get_real="sum")
         static_loss.backward()
     for _ in range(2):
         g.replay()

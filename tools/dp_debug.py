@@ -12,7 +12,7 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 say("pg up")
 enc, dec = build_models(dev)
-st = FusedTrainStep(enc, dec, 512, l1_lambda=1e-8, l1_scale=1.0 / world, use_graph=(os.environ.get("GRAPH", "1") == "1"))
+st = FusedTrainStep(enc, dec, 512, l1_lambda=1e-8, l1_scale=1.0 / world, use_graph=(os.environ.get("GRAPH", "1") == "1"), get_real="sum")
 st.load(synthetic_jets(512, 30, seed=100 + rank))
 say("built")
 st._launch(); torch.cuda.synchronize(); say("eager 1", st.loss.item())

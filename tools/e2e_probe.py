@@ -6,7 +6,7 @@ from bench import CFG, build_models, synthetic_jets
 from lgn_autoencoder_b200.train import FusedTrainStep
 dev = torch.device("cuda:0")
 enc, dec = build_models(dev)
-st = FusedTrainStep(enc, dec, 512, l1_lambda=1e-8, use_graph=True)
+st = FusedTrainStep(enc, dec, 512, l1_lambda=1e-8, use_graph=True, get_real="sum")
 hp = synthetic_jets(512, 30, seed=3).pin_memory()
 st.host_p4.copy_(hp)
 st.load(hp)
@@ -22,7 +22,7 @@ print("graph replay + sync each step      %.0f us" % wall(run_sync))
 print("step_host (in-graph H2D/D2H, sync) %.0f us" % wall(st.step_host))
 def item_step(): return st.step(hp).item()
 print("step(load)+item()                   %.0f us" % wall(item_step))
-st2 = FusedTrainStep(enc, dec, 512, l1_lambda=1e-8, use_graph=False)
+st2 = FusedTrainStep(enc, dec, 512, l1_lambda=1e-8, use_graph=False, get_real="sum")
 st2.host_p4.copy_(hp)
 for _ in range(3): st2.step_host()
 print("step_host EAGER (C launches, sync)  %.0f us" % wall(st2.step_host))

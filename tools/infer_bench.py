@@ -19,7 +19,7 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 enc, dec = bench.build_models(dev)
-inf = FusedInference(enc, dec, B)
+inf = FusedInference(enc, dec, B, get_real="sum")
 p4 = synthetic_jets(B, N, seed=1 + rank).to(dev)     # this rank's shard of the global batch
 for _ in range(3):
     s = inf.score(p4)

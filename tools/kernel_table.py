@@ -8,7 +8,7 @@ from lgn_autoencoder_b200.train import FusedTrainStep
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 dev = torch.device("cuda:0")
 enc, dec = build_models(dev)
-st = FusedTrainStep(enc, dec, B, l1_lambda=1e-8, use_graph=True)
+st = FusedTrainStep(enc, dec, B, l1_lambda=1e-8, use_graph=True, get_real="sum")
 st.load(synthetic_jets(B, 30, seed=3))
 flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 def eager():

@@ -9,7 +9,7 @@ from lgn_autoencoder_b200.train import FlatAdam, FusedTrainStep
 B = 512
 dev = torch.device("cuda:0")
 enc, dec = build_models(dev)
-fs = FusedTrainStep(enc, dec, B, l1_lambda=1e-8, use_graph=True)
+fs = FusedTrainStep(enc, dec, B, l1_lambda=1e-8, use_graph=True, get_real="sum")
 fs.load(synthetic_jets(B, 30, seed=3))
 fs.run()
 

@@ -28,7 +28,7 @@ for it in range(3 + steps):
     lat00, lat11, ws_e, sel = phase("enc_fwd", lambda: fused.encoder_forward_raw(enc, th_e, p4, None))
     recon, _, ws_d = phase("dec_fwd", lambda: fused.decoder_forward_raw(dec, th_d, lat11))
     def ch():
-        rg = recon.clone().requires_grad_(True); loss = fused.chamfer_loss(rg, p4); loss.backward(); return rg.grad
+        rg = recon.clone().requires_grad_(True); loss = fused.chamfer_loss(rg, p4, "sum"); loss.backward(); return rg.grad
     gr = phase("chamfer", ch)
     g_lat11, gd = phase("dec_bwd", lambda: fused.decoder_backward_raw(dec, th_d, lat11, ws_d, gr, None))
     ge = phase("enc_bwd", lambda: fused.encoder_backward_raw(enc, th_e, p4, None, ws_e, sel, None, g_lat11))

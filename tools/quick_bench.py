@@ -20,7 +20,7 @@ def step():
     lat00, lat11, ws_e, sel = fused.encoder_forward_raw(enc, th_e, p4, None)
     recon, _, ws_d = fused.decoder_forward_raw(dec, th_d, lat11)
     rg = recon.clone().requires_grad_(True)
-    loss = fused.chamfer_loss(rg, p4)
+    loss = fused.chamfer_loss(rg, p4, "sum")
     loss.backward()
     g_lat11, gd = fused.decoder_backward_raw(dec, th_d, lat11, ws_d, rg.grad, None)
     ge = fused.encoder_backward_raw(enc, th_e, p4, None, ws_e, sel, None, g_lat11)
