@@ -4,6 +4,9 @@ import sys
 import types
 
 
+_PAIR_RETURNING = ("subplots", "get_legend_handles_labels")   # call sites unpack two values
+
+
 class _Noop:
     """Callable, iterable, indexable, context-managing nothing."""
 
@@ -16,10 +19,12 @@ class _Noop:
     def __getattr__(self, name):
         if name.startswith("__") and name.endswith("__"):
             raise AttributeError(name)
+        if name in _PAIR_RETURNING:
+            return lambda *a, **k: (_Noop(), _Noop())
         return _Noop()
 
     def __iter__(self):
-        return iter(())
+        return iter([_Noop() for _ in range(16)])   # `for ax, x in zip(axs, data)` must bind its loop variables
 
     def __getitem__(self, k):
         return _Noop()
@@ -33,11 +38,35 @@ class _Noop:
     def __exit__(self, *a):
         return False
 
+    def __bool__(self):
+        return False
+
     def __len__(self):
         return 0
 
-    def __bool__(self):
-        return False
+    def __float__(self):
+        return 0.0
+
+    def __int__(self):
+        return 0
+
+    def __index__(self):
+        return 0
+
+    def __array__(self, dtype=None, copy=None):
+        import numpy
+        return numpy.zeros(1, dtype=dtype or float)
+
+
+def _arith(self, *a, **k):
+    return _Noop()
+
+
+for _ARITH in ("add", "radd", "sub", "rsub", "mul", "rmul", "truediv", "rtruediv", "pow", "rpow", "neg", "pos", "abs", "matmul", "rmatmul",
+               "floordiv", "rfloordiv", "mod", "rmod"):
+    setattr(_Noop, f"__{_ARITH}__", _arith)
+for _CMP in ("lt", "le", "gt", "ge"):
+    setattr(_Noop, f"__{_CMP}__", lambda self, other: False)
 
 
 class _StubModule(types.ModuleType):
@@ -49,6 +78,8 @@ class _StubModule(types.ModuleType):
         full = self.__name__ + "." + name
         if full in sys.modules:
             return sys.modules[full]
+        if name in _PAIR_RETURNING:
+            return lambda *a, **k: (_Noop(), _Noop())
         return _Noop()
 
 

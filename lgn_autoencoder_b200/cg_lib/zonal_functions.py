@@ -27,8 +27,11 @@ def _cartesian4(dtype, device):
 
 def normsq4(p):
     """Minkowski square of real Cartesian 4-vectors (reference zonal_functions.py:201-218)."""
-    psq = torch.pow(p, 2)
-    return 2 * psq[..., 0] - psq.sum(dim=-1)
+    # Near-massless particles make this a cancellation (p^2 ~ 1e-10 E^2), so the reference's CPU rounding sequence is kept
+    # explicitly: squares, then the four terms added left to right (no device-side reduction, no FMA contraction).
+    psq = p * p
+    s = ((psq[..., 0] + psq[..., 1]) + psq[..., 2]) + psq[..., 3]
+    return 2 * psq[..., 0] - s
 
 
 def p_to_rep(p):

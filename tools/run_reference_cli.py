@@ -63,7 +63,8 @@ def main():
     save = os.path.join(out, "exp")
     model = ["-j", "QCD", "--maxdim", "2", "--tau-latent-vectors", "8", "--tau-latent-scalars", "1", "--map-to-latent", "min&max",
              "--mlp-width", "6", "--mlp-depth", "6", "--encoder-num-channels", "3", "3", "4", "4", "--decoder-num-channels", "4", "4", "3", "3",
-             "--device", args.device, "--test-device", args.device]
+             "--device", args.device]
+    test_dev = ["--test-device", args.device]
     skip = set(args.skip.split(","))
     summary = {"impl": args.impl, "device": args.device}
     py = [sys.executable, "-u"]
@@ -71,7 +72,7 @@ def main():
         cmd = py + ["main.py", "--data-paths", data, "--test-data-paths", test_data, "-e", str(args.epochs), "-bs", str(args.batch),
                     "--train-fraction", "0.75", "--lr", "0.0005", "--loss-choice", "chamfer", "--get-real-method", "sum", "--l1-lambda", "1e-8",
                     "--l2-lambda", "0", "--patience", "1000", "--plot-freq", "1000", "--save-freq", "1", "--plot-start-epoch", "1000",
-                    "--equivariance-test", "--num-test-batch", "1", "--test-batch-size", "16", "--save-dir", save, "--seed", "0"] + model
+                    "--equivariance-test", "--num-test-batch", "1", "--test-batch-size", "16", "--save-dir", save, "--seed", "0"] + model + test_dev
         rc, dt = run(cmd, env, REF, os.path.join(out, "main.log"))
         summary["main"] = {"rc": rc, "seconds": dt}
     # the folder main.py created
@@ -82,7 +83,7 @@ def main():
     summary["model_path"] = exp
     if "test" not in skip and exp:
         cmd = py + ["test.py", "--test-data-paths", test_data, "--model-path", exp, "--test-batch-size", "32", "--get-real-method", "sum",
-                    "--loss-choice", "chamfer", "--plot-freq", "1000"] + model
+                    "--loss-choice", "chamfer", "--plot-freq", "1000"] + model + test_dev
         rc, dt = run(cmd, env, REF, os.path.join(out, "test.log"))
         summary["test"] = {"rc": rc, "seconds": dt}
     if "cov" not in skip and exp:
