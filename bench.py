@@ -244,14 +244,109 @@ def reference_subprocess(extra, timeout=600):
         return {"unavailable": repr(e)[:300]}
 
 
+def extra_cfg3_strong(enc, dec, world, rank, dev, timed, W, K):
+    """BASELINE configs[2] as written: GLOBAL batch 4096 sharded over the ranks (strong scaling: 4096 / world jets per GPU)."""
+    import torch
+    from lgn_autoencoder_b200.train import FusedTrainStep
+    G = 4096
+    b = G // world
+    step = FusedTrainStep(enc, dec, b, l1_lambda=CFG["l1_lambda"], l1_scale=1.0 / world, normalize=True, get_real="sum")
+    step.load(synthetic_jets(b, CFG["n"], seed=300 + rank).to(dev))
+    for _ in range(W):
+        step.run()
+    ms, _ = timed(step.run, K)
+    step.graph = None
+    return {"workload": "cfg3: the cfg1 step data-parallel at GLOBAL batch 4096 (strong scaling)", "global_batch": G, "jets_per_gpu": b,
+            "n_gpus": world, "ms_per_step": ms, "value": G / (ms * 1e-3), "unit": "jets/s", "scaling": "strong"}
+
+
+def extra_cfg4(dev, rank, world, timed, K):
+    """BASELINE configs[3]: the wide maxdim-3 model (enc 6 6 8 8 / dec 8 8 6 6, 'mix' latent map), training step at bs 1024 per GPU
+    through the module API (forward + autograd adjoint on this library's kernels), replayed as one CUDA graph."""
+    import gc
+    import torch
+    from lgn_autoencoder_b200.models import LGNDecoder, LGNEncoder
+    from lgn_autoencoder_b200.train import training_step
+    B, N, ENC, DEC = 1024, 30, [6, 6, 8, 8], [8, 8, 6, 6]
+    torch.manual_seed(0)
+    common = dict(maxdim=[3], num_basis_fn=10, max_zf=[1], weight_init="randn", level_gain=[1.0], activation="leakyrelu", mlp=True, mlp_depth=6,
+                  mlp_width=6, device=dev, dtype=torch.float64)
+    enc = LGNEncoder(num_input_particles=N, tau_input_scalars=1, tau_input_vectors=1, tau_latent_scalars=1, tau_latent_vectors=8,
+                     num_channels=ENC, jet_features=False, map_to_latent="mix", **common)
+    dec = LGNDecoder(tau_latent_scalars=1, tau_latent_vectors=8, num_output_particles=N, tau_output_scalars=1, tau_output_vectors=1,
+                     num_channels=DEC, cg_dict=enc.cg_dict, **common)
+    p4 = synthetic_jets(B, N, seed=2 + rank).to(dev)
+    params = [p for m in (enc, dec) for p in m.parameters()]
+
+    def eager():
+        for p in params:
+            p.grad = None
+        loss, _, _ = training_step(enc, dec, p4, get_real="sum")
+        loss.backward()
+        return loss.detach()
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            eager()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gc.collect()
+    graph = torch.cuda.CUDAGraph()
+    for p in params:
+        p.grad = None
+    with torch.cuda.graph(graph):
+        static_loss, _, _ = training_step(enc, dec, p4, get_real="sum")
+        static_loss.backward()
+    for _ in range(2):
+        graph.replay()
+    ms, _ = timed(graph.replay, max(3, min(K, 10)))
+    mflop = 198.0   # SURVEY.md 8(d): reference-faithful count of cfg-4, fwd + bwd, per jet
+    tf = B * mflop * 1e6 / (ms * 1e-3) / 1e12
+    out = {"workload": "cfg4: maxdim 3, enc 6-6-8-8 / dec 8-8-6-6, 'mix' latent, bs 1024/GPU, train step (module API + autograd, CUDA graph)",
+           "jets_per_gpu": B, "ms_per_step": ms, "value": B * world / (ms * 1e-3), "unit": "jets/s", "mflop_per_jet": mflop, "tflops_per_gpu": tf,
+           "frac_of_fp64_peak": tf / FP64_PEAK_TFLOPS, "loss": static_loss.item(), "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30,
+           "parity": "tests/test_models_gpu.py::test_module_forward_backward_matches_reference[cfg4_b2] (same shapes, 2 jets, vs the unmodified reference)"}
+    del graph
+    return out
+
+
+def extra_cfg5(dev, rank, world, timed, K):
+    """BASELINE configs[4]: forward-only anomaly scoring, 150-particle jets, 8192 jets sharded over the ranks (no communication)."""
+    import torch
+    from lgn_autoencoder_b200.flop_model import step_flops_per_jet
+    from lgn_autoencoder_b200.train import FusedInference
+    n0 = CFG["n"]
+    CFG["n"] = 150
+    try:
+        enc, dec = build_models(dev)
+        G = 8192
+        b = G // world
+        inf = FusedInference(enc, dec, b, get_real="sum")
+        inf.score(synthetic_jets(b, 150, seed=500 + rank).to(dev))
+        for _ in range(2):
+            inf.run()
+        ms, _ = timed(inf.run, max(3, min(K, 10)))
+        fl = step_flops_per_jet(150, CFG["enc_channels"], CFG["dec_channels"], backward=False)
+        tf = G * fl / (ms * 1e-3) / 1e12
+        return {"workload": "cfg5: encoder + decoder forward + per-jet scores, 150-particle jets, 8192 jets sharded over the GPUs", "global_batch": G,
+                "jets_per_gpu": b, "n_gpus": world, "ms_per_pass": ms, "value": G / (ms * 1e-3), "unit": "jets/s", "mflop_per_jet": fl / 1e6,
+                "tflops": tf, "frac_of_fp64_peak": tf / (FP64_PEAK_TFLOPS * world), "mean_score": inf.scores.mean().item(),
+                "parity": "tests/test_train_step_gpu.py::test_fused_inference_matches_module_forward_and_oracle_at_150_particles"}
+    finally:
+        CFG["n"] = n0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=CFG["batch"], help="jets per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg3 (global batch 4096) / cfg4 / cfg5 objects of the line")
     ap.add_argument("--ref-device", default="cpu", help="reference arm only: cpu (the baseline) or cuda (stock ATen kernels, informative)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -348,6 +443,14 @@ def main():
         # algorithmic flops per step of each kernel family (reference-faithful counts; adjoint = 2 x forward;
         # the last level's MLP is dead in the backward pass)
         fam = {k: 0.0 for k in ("level_fwd", "level_bwd", "radial_fwd", "radial_bwd", "mlp_fwd", "mlp_bwd")}
+        executed = {"mlp_fwd": 0.0, "mlp_bwd": 0.0}
+        # which fp64 pipe bounds each family, and its busy fraction from this round's `ncu --set full` captures (profiles/)
+        pipe = {"level_fwd": "fp64 DFMA", "level_bwd": "fp64 DFMA", "radial_fwd": "fp64 DMMA", "radial_bwd": "fp64 DMMA", "mlp_fwd": "fp64 DMMA",
+                "mlp_bwd": "fp64 DMMA"}
+        try:
+            ncu_pipe = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_pipe.json")))
+        except (OSError, ValueError):
+            ncu_pipe = {}
         for chs, enc_side in ((ech, True), (dch, False)):
             for l in range(len(chs) - 1):
                 f = lvl(chs, enc_side, l)
@@ -356,9 +459,20 @@ def main():
                 fam["level_bwd"] += 2 * B * cg
                 fam["radial_fwd"] += B * f["radial"]
                 fam["radial_bwd"] += 2 * B * f["radial"]
-                fam["mlp_fwd"] += B * f["mlp"]
+                # the decoder's last-level MLP forward is not run (dead: see `detail.dead_code`) -- its flops are not credited to the
+                # mlp_fwd family either (the whole-step figure keeps the reference's full count)
+                if enc_side or l < len(chs) - 2:
+                    fam["mlp_fwd"] += B * f["mlp"]
                 if l < len(chs) - 2:
                     fam["mlp_bwd"] += 2 * B * f["mlp"]
+                    # flops the DMMA pipe actually executes: tiles padded to multiples of 8 (widths 36 -> 40, inputs 6 -> 8)
+                pad8 = lambda v: 8 * ((v + 7) // 8)
+                w_, ni_ = pad8(CFG["mlp_width"] * 2 * chs[l + 1]), pad8(2 * chs[l + 1])
+                ex = N * 2 * (ni_ * w_ + (CFG["mlp_depth"] - 1) * w_ * w_ + w_ * ni_)
+                if enc_side or l < len(chs) - 2:
+                    executed["mlp_fwd"] += B * ex
+                if l < len(chs) - 2:
+                    executed["mlp_bwd"] += 2 * B * ex
         total_ms = sum(n * ms for n, ms in kern.values()) / 5.0
         table = {}
         for name, (n, ms) in sorted(kern.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
@@ -367,17 +481,23 @@ def main():
             if name in fam:
                 ent["tflops"] = fam[name] / (per_step * ms * 1e-3) / 1e12
                 ent["frac_of_fp64_peak"] = ent["tflops"] / FP64_PEAK_TFLOPS
+                ent["bound"] = pipe[name]
+                if name in executed:   # flops the kernel really issues (padded MMA tiles) / peak
+                    ent["executed_frac"] = executed[name] / (per_step * ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS
+                if name in ncu_pipe:   # ncu: busy fraction of that pipe over the kernel's duration
+                    ent["ncu_pipe_busy"] = ncu_pipe[name]
             table[name] = ent
         top = max((k for k in table if k in fam), key=lambda k: table[k]["share"])
         t = table[top]
         # DRAM bytes per launch of that kernel from this round's `ncu --set full` capture (profiles/r01_traffic.json)
         traffic = None
         try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"][top]
+            tf_ = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+            tr = json.load(open(os.path.join(ROOT, "profiles", tf_)))["kernels"][top]
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         except (OSError, KeyError, ValueError):
             pass
-        roofline = {"bound": "tensor", "kernel": top, "achieved": t["tflops"], "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+        roofline = {"bound": pipe[top], "executed_frac": t.get("executed_frac"), "ncu_pipe_busy": t.get("ncu_pipe_busy"), "kernel": top, "achieved": t["tflops"], "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                     "frac": t["frac_of_fp64_peak"], "traffic": traffic, "kernel_ms": t["ms_per_launch"], "launches_per_step": t["launches_per_step"],
                     "flops_per_launch": fam[top] / t["launches_per_step"],
                     "peak_source": "fp64 pipe: DMMA m8n8k4 37.1 TFLOP/s / DFMA 33.7 TFLOP/s measured with tools/fp64_peak.cu on this pool "
@@ -414,6 +534,19 @@ def main():
         r = reference_subprocess(["--batch", str(B), "--steps", "3", "--warmup", "1", "--ref-device", "cuda"])
         ref_cuda = {"value": r["value"], "unit": "jets/s", "ms_per_step": r["ms_per_step"], "sample": r["cpu_baseline"]["sample"]} if "value" in r else r
 
+    # ---- the other configurations of BASELINE.json, as extra objects of the same line (every rank runs them) ----
+    extras = {}
+    if not args.no_extras:
+        fstep.graph = None
+        fstep.graph_host = None
+        for name, fn in (("cfg3_global4096", lambda: extra_cfg3_strong(enc, dec, world, rank, dev, timed, W, min(K, 30))),
+                         ("cfg5", lambda: extra_cfg5(dev, rank, world, timed, K)), ("cfg4", lambda: extra_cfg4(dev, rank, world, timed, K))):
+            try:
+                extras[name] = fn()
+            except Exception as e:   # noqa: BLE001  (an extra must never take the headline line down)
+                extras[name] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+
     if rank == 0:
         jets = B * world
         fl = step_flops_per_jet(N, CFG["enc_channels"], CFG["dec_channels"])
@@ -431,7 +564,7 @@ def main():
             "e2e": {"value": jets / (ms_e2e * 1e-3), "unit": "jets/s", "h2d_bytes_per_step": host_p4.numel() * 8, "d2h_bytes_per_step": 8,
                     "ms_per_step": ms_e2e},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "reference_cuda": ref_cuda,
-            "kernels": table,
+            "kernels": table, **extras,
         }
         print(json.dumps(line))
     if world > 1:

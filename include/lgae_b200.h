@@ -155,7 +155,7 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
                     const double* p4_in, const uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4,
                     double* norm_factor, double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel,
                     double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss, double* gtheta,
-                    int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, void* stream);
+                    int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, int32_t phase, void* stream);
 /* The same step from HOST memory: host_p4 (B,N,4) [and host_mask (B,N), may be NULL] in pinned memory are copied to the
  * device buffers p4_in / node_mask at the start of the step and the loss (1 double) back to host_loss at its end, all on
  * `stream` and capturable in one CUDA graph; the copies are ordered so that the step's parameter-only kernels (weight
@@ -167,7 +167,7 @@ int lgae_train_step_host(const LgaeModelDesc* enc, const LgaeModelDesc* dec, con
                          double* p4_in, uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4,
                          double* norm_factor, double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel,
                          double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss, double* gtheta,
-                         int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, void* stream);
+                         int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, int32_t phase, void* stream);
 
 
 /* ---- caller-side ops on the hot path ------------------------------------------------------------- */

@@ -564,6 +564,11 @@ int lgae_decoder_backward(const LgaeModelDesc* d, const double* theta, const dou
     return run_reduce_plan(&plan, d->n_params, gtheta, theta, l1_lambda, loss_accumulate, (cudaStream_t)stream);
 }
 
+void* lgae_aux_stream(void) {
+    SideStream* aux = aux_stream();
+    return aux ? (void*)aux->s : nullptr;
+}
+
 int64_t lgae_train_step_partials_doubles(const LgaeModelDesc* enc, const LgaeModelDesc* dec, int32_t batch) {
     const int64_t a = lgae_partials_doubles(enc, batch), b = lgae_partials_doubles(dec, batch);
     if (a < 0 || b < 0) return -1;
@@ -573,18 +578,26 @@ int64_t lgae_train_step_partials_doubles(const LgaeModelDesc* enc, const LgaeMod
 
 }  // extern "C"
 
-// Body of lgae_train_step / lgae_train_step_host.  host_p4 / host_mask / host_loss (pinned host memory, may be NULL): the jets
+// Plan of the encoder's partial rows handed from phase 1 to phase 2 of a split step (same thread, back to back).
+static thread_local PartPlan tl_plan_e;
+static thread_local bool tl_phase1 = false;
+
+// Body of lgae_train_step / lgae_train_step_host.  phase: 0 = the whole step; 1 = everything up to the point where the
+// decoder's gradient bucket is final (its reduce is enqueued on the auxiliary stream, lgae_aux_stream()); 2 = the rest (encoder
+// adjoint + encoder reduce).  Between phases 1 and 2 the caller may enqueue work on the auxiliary stream -- the data-parallel
+// all-reduce of the decoder bucket -- which then overlaps the encoder adjoint; phase 2 joins the auxiliary stream back.  host_p4 / host_mask / host_loss (pinned host memory, may be NULL): the jets
 // are copied to p4_in (and the mask to node_mask) at the start and the loss back at the end, on the same stream -- after the
 // auxiliary branch has been forked, so that weight packing and gradient init overlap the host-to-device copy.
 static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
                            double* p4_in, uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4, double* norm_factor,
                            double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel, double* recon, double* g_recon,
                            double* g_lat11, double* jet_loss, double* loss, double* gtheta, int64_t gtheta_dec_offset, double* partials,
-                           double l1_lambda, int32_t get_real, const double* host_p4, const uint8_t* host_mask, double* host_loss, void* stream) {
+                           double l1_lambda, int32_t get_real, const double* host_p4, const uint8_t* host_mask, double* host_loss, int32_t phase,
+                           void* stream) {
     LGAE_TRY(check_desc(enc));
     LGAE_TRY(check_desc(dec));
     if (enc->is_decoder || !dec->is_decoder || batch < 1 || gtheta_dec_offset < enc->n_params) return LGAE_E_BADARG;
-    if (get_real < LGAE_GET_REAL_REAL || get_real > LGAE_GET_REAL_NORM) return LGAE_E_BADARG;
+    if (get_real < LGAE_GET_REAL_REAL || get_real > LGAE_GET_REAL_NORM || phase < 0 || phase > 2) return LGAE_E_BADARG;
     if (!theta_enc || !theta_dec || !p4_in || !p4 || !ws_enc || !ws_dec || !lat00 || !lat11 || !sel || !recon || !g_recon || !g_lat11 ||
         !jet_loss || !loss || !gtheta || !partials)
         return LGAE_E_BADARG;
@@ -593,11 +606,18 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
     const double* x = normalize ? p4 : p4_in;
     const bool scaled = has_input_scale(enc);
     SideStream* aux = aux_stream();
+    if (phase != 0 && !aux) return LGAE_E_UNSUPPORTED;   // the split step needs the auxiliary stream
+    if (phase == 2 && !tl_phase1) return LGAE_E_BADARG;
     std::unique_lock<std::mutex> aux_lock(g_aux_mu, std::defer_lock);
     if (aux) aux_lock.lock();
     // L1 partial sums of the gradient init: the second reduce-scratch region at the end of `partials` (the first one, behind the
     // plan's blocks, is unused by this entry point)
     double* psum = partials + lgae_train_step_partials_doubles(enc, dec, batch) - 1 - reduce_scratch_doubles();
+    const int64_t n_all = enc->n_params + dec->n_params;
+    PartPlan plan_d, plan_e;
+    int rc_scale = LGAE_OK;
+    const double* xe = x;
+    if (phase != 2) {
     // forward: one launch packs the MLP weights of both models
     {
         const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
@@ -622,8 +642,7 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
             LGAE_TRY(run_normalize(p4_in, batch, enc->n_particles, p4, norm_factor, st));
     }
     // x: the (normalised) jets = the loss target; xe: what the encoder reads (x times the encoder's input scale)
-    int rc_scale = LGAE_OK;
-    const double* xe = scaled_input(enc, x, batch, ws_enc, true, st, &rc_scale);
+    xe = scaled_input(enc, x, batch, ws_enc, true, st, &rc_scale);
     LGAE_TRY(rc_scale);
     LGAE_TRY(enc_forward_launch(enc, theta_enc, xe, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false, !normalize || scaled,
                                 aux ? aux->join[0] : nullptr));
@@ -636,7 +655,6 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
     LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, false, st, false, false, !keep_dead_mlp()));
     // one plan per model over the same partials buffer (the encoder's continues where the decoder's ends): the decoder's rows are
     // reduced on the auxiliary stream while the encoder adjoint runs, the encoder's at the end
-    PartPlan plan_d, plan_e;
     plan_d.base = plan_e.base = partials;
     plan_d.theta_base = gtheta_dec_offset;
     {
@@ -655,7 +673,6 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
                                        ws_dec + Ld.gy, g_lat11, ws_enc + Le.S[enc->n_levels], ws_enc + Le.V[enc->n_levels], sel,
                                        ws_enc + Le.gS[0], ws_enc + Le.gV[0], &plan_d, &plan_e, st));
     }
-    const int64_t n_all = enc->n_params + dec->n_params;
     if (aux) {
         // the decoder's gradient is complete: reduce it now, next to the encoder adjoint (the gradient init ran on this stream)
         LGAE_CUDA_TRY(cudaEventRecord(aux->fork[2], st), "aux fork");
@@ -664,8 +681,19 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
         // so that the device-to-host copy overlaps the encoder adjoint instead of trailing the step
         LGAE_TRY(run_reduce_segs(&plan_d, n_all, gtheta, psum, l1_lambda, loss, aux->s));
         if (host_loss) LGAE_CUDA_TRY(cudaMemcpyAsync(host_loss, loss, sizeof(double), cudaMemcpyDeviceToHost, aux->s), "D2H loss");
-        LGAE_CUDA_TRY(cudaEventRecord(aux->join[3], aux->s), "aux join");
     }
+    if (phase == 1) {
+        tl_plan_e = plan_e;
+        tl_phase1 = true;
+        return LGAE_OK;
+    }
+    } else {
+        plan_e = tl_plan_e;
+        tl_phase1 = false;
+        xe = scaled_input(enc, x, batch, ws_enc, false, st, &rc_scale);
+    }
+    // (split step: whatever the caller enqueued on the auxiliary stream between the phases is joined here too)
+    if (aux) LGAE_CUDA_TRY(cudaEventRecord(aux->join[3], aux->s), "aux join");
     LGAE_TRY(enc_backward_launch(enc, theta_enc, xe, node_mask, batch, ws_enc, sel, nullptr, g_lat11, plan_e, st, false, aux));
     if (aux) {
         LGAE_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[1], 0), "aux join wait");
@@ -686,21 +714,22 @@ int lgae_train_step(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const do
                     const double* p4_in, const uint8_t* node_mask, int32_t batch, int32_t normalize, double* p4, double* norm_factor,
                     double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel, double* recon, double* g_recon,
                     double* g_lat11, double* jet_loss, double* loss, double* gtheta, int64_t gtheta_dec_offset, double* partials,
-                    double l1_lambda, int32_t get_real, void* stream) {
+                    double l1_lambda, int32_t get_real, int32_t phase, void* stream) {
     return train_step_impl(enc, dec, theta_enc, theta_dec, const_cast<double*>(p4_in), const_cast<uint8_t*>(node_mask), batch, normalize, p4,
                            norm_factor, ws_enc, ws_dec, lat00, lat11, sel, recon, g_recon, g_lat11, jet_loss, loss, gtheta, gtheta_dec_offset,
-                           partials, l1_lambda, get_real, nullptr, nullptr, nullptr, stream);
+                           partials, l1_lambda, get_real, nullptr, nullptr, nullptr, phase, stream);
 }
 
 int lgae_train_step_host(const LgaeModelDesc* enc, const LgaeModelDesc* dec, const double* theta_enc, const double* theta_dec,
                          const double* host_p4, const uint8_t* host_mask, double* host_loss, double* p4_in, uint8_t* node_mask,
                          int32_t batch, int32_t normalize, double* p4, double* norm_factor, double* ws_enc, double* ws_dec, double* lat00,
                          double* lat11, int32_t* sel, double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss,
-                         double* gtheta, int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, void* stream) {
+                         double* gtheta, int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, int32_t phase,
+                         void* stream) {
     if (!host_p4 || !host_loss) return LGAE_E_BADARG;
     return train_step_impl(enc, dec, theta_enc, theta_dec, p4_in, node_mask, batch, normalize, p4, norm_factor, ws_enc, ws_dec, lat00, lat11, sel,
                            recon, g_recon, g_lat11, jet_loss, loss, gtheta, gtheta_dec_offset, partials, l1_lambda, get_real, host_p4, host_mask,
-                           host_loss, stream);
+                           host_loss, phase, stream);
 }
 
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, int32_t get_real, double* loss,

@@ -202,11 +202,28 @@ def _contig(t):
     return None if t is None else t.contiguous()
 
 
-class _EncoderFn(torch.autograd.Function):
-    """LGNEncoder.forward (lgn/models/lgn_encoder.py:255-336) as one autograd node."""
+class _FlatParamsFn(torch.autograd.Function):
+    """The flat parameter buffer as ONE differentiable tensor: forward returns the buffer every ``nn.Parameter`` of the model
+    aliases; backward hands each parameter its slice of the flat gradient as a view (no kernel).  The model-level Functions
+    below and the L1 / L2 norms take this tensor, so their gradients meet in a single flat add instead of one add per
+    parameter tensor (~130 per model), and ``param.grad`` ends up as views of one flat bucket."""
 
     @staticmethod
-    def forward(ctx, plan, theta, p4, node_mask, holder, *params):
+    def forward(ctx, plan, theta, *params):
+        ctx.plan = plan
+        return theta.view(-1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None) + tuple(ctx.plan.views(g.contiguous()).values())
+
+
+class _EncoderFn(torch.autograd.Function):
+    """LGNEncoder.forward (lgn/models/lgn_encoder.py:255-336) as one autograd node; theta: the flat parameters
+    (``_FlatParamsFn``), whose gradient comes back as one flat tensor."""
+
+    @staticmethod
+    def forward(ctx, plan, theta, p4, node_mask, holder):
         lat00, lat11, ws, sel = encoder_forward_raw(plan, theta, p4, node_mask)
         ctx.plan, ctx.theta, ctx.p4, ctx.node_mask, ctx.ws, ctx.sel = plan, theta, p4, node_mask, ws, sel
         if holder is not None:
@@ -217,15 +234,14 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, g00, g11):
         plan = ctx.plan
         gtheta = encoder_backward_raw(plan, ctx.theta, ctx.p4, ctx.node_mask, ctx.ws, ctx.sel, _contig(g00), _contig(g11))
-        grads = tuple(plan.views(gtheta).values())
-        return (None, None, None, None, None) + grads
+        return None, gtheta, None, None, None
 
 
 class _DecoderFn(torch.autograd.Function):
     """LGNDecoder.forward (lgn/models/lgn_decoder.py:218-303) as one autograd node."""
 
     @staticmethod
-    def forward(ctx, plan, theta, lat11, want_gen00, holder, *params):
+    def forward(ctx, plan, theta, lat11, want_gen00, holder):
         lat11 = lat11.contiguous()
         recon, gen00, ws = decoder_forward_raw(plan, theta, lat11, want_gen00)
         ctx.plan, ctx.theta, ctx.lat11, ctx.ws = plan, theta, lat11, ws
@@ -241,8 +257,7 @@ class _DecoderFn(torch.autograd.Function):
         if g_recon is None:
             g_recon = torch.zeros((2, ctx.lat11.shape[1], plan.n_particles, 4), dtype=torch.float64, device=ctx.lat11.device)
         g_lat11, gtheta = decoder_backward_raw(plan, ctx.theta, ctx.lat11, ctx.ws, g_recon.contiguous(), _contig(g_gen00))
-        grads = tuple(plan.views(gtheta).values())
-        return (None, None, g_lat11, None, None) + grads
+        return None, gtheta, g_lat11, None, None
 
 
 class _ChamferFn(torch.autograd.Function):

@@ -38,32 +38,34 @@ class FusedParamsMixin:
             self._theta = theta
         return theta, list(params.values())
 
+    def _theta_node(self):
+        """The flat parameter buffer as one autograd tensor (``fused._FlatParamsFn``)."""
+        theta, params = self._flat_params()
+        return fused._FlatParamsFn.apply(self._plan, theta, *params)
+
     def l1_norm(self):
         """sum |p| over all parameters (lgn_encoder.py:249-250), evaluated on the flat buffer in one reduction."""
         if self._plan is None:
             return sum(p.abs().sum() for p in self.parameters())
-        theta, params = self._flat_params()
-        return _FlatNormFn.apply(self._plan, theta, 1, *params)
+        return _FlatNormFn.apply(self._theta_node(), 1)
 
     def l2_norm(self):
         """sum p^2 over all parameters (lgn_encoder.py:252-253)."""
         if self._plan is None:
             return sum(torch.pow(p, 2).sum() for p in self.parameters())
-        theta, params = self._flat_params()
-        return _FlatNormFn.apply(self._plan, theta, 2, *params)
+        return _FlatNormFn.apply(self._theta_node(), 2)
 
 
 class _FlatNormFn(torch.autograd.Function):
     """L1 / squared-L2 norm of all parameters through the flat buffer they alias: two launches instead of two per tensor."""
 
     @staticmethod
-    def forward(ctx, plan, theta, order, *params):
-        ctx.plan, ctx.order = plan, order
+    def forward(ctx, theta, order):
+        ctx.order = order
         ctx.save_for_backward(theta)
         return theta.abs().sum() if order == 1 else (theta * theta).sum()
 
     @staticmethod
     def backward(ctx, g):
         (theta,) = ctx.saved_tensors
-        flat = torch.sign(theta) * g if ctx.order == 1 else 2.0 * theta * g
-        return (None, None, None) + tuple(ctx.plan.views(flat).values())
+        return (torch.sign(theta) * g if ctx.order == 1 else 2.0 * theta * g), None

@@ -99,9 +99,8 @@ class LGNDecoder(FusedParamsMixin, CGModule):
     def _forward_fused(self, lat11, covariance_test, nodes_all):
         b = lat11.shape[1]
         lat11 = lat11.to(self.device, self.dtype).reshape(2, b, 1, self.tau_latent_vectors, 4)
-        theta, params = self._flat_params()
         holder = {} if covariance_test else None
-        out = fused._DecoderFn.apply(self._plan, theta, lat11, covariance_test, holder, *params)
+        out = fused._DecoderFn.apply(self._plan, self._theta_node(), lat11, covariance_test, holder)
         if not covariance_test:
             return out
         recon, gen00 = out

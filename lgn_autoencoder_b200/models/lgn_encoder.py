@@ -137,9 +137,8 @@ class LGNEncoder(FusedParamsMixin, CGModule):
         mask = self._mask_from(data)
         if mask is not None:
             mask = (mask.to(self.device) != 0).to(torch.uint8).contiguous()
-        theta, params = self._flat_params()
         holder = {} if covariance_test else None
-        lat00, lat11 = fused._EncoderFn.apply(self._plan, theta, p4, mask, holder, *params)
+        lat00, lat11 = fused._EncoderFn.apply(self._plan, self._theta_node(), p4, mask, holder)
         if self.map_to_latent.lower() == "sum":      # the reference's sum keeps a spurious extra axis (lgn_encoder.py:424)
             lat00, lat11 = lat00.unsqueeze(-3), lat11.unsqueeze(-3)
         latent = GVec({(0, 0): lat00, (1, 1): lat11}, ignore_check=True)

@@ -68,7 +68,7 @@ class FusedTrainStep:
     """
 
     def __init__(self, encoder, decoder, batch: int, l1_lambda: float = 1e-8, l1_scale: float = 1.0, normalize: bool = True,
-                 use_labels: bool = False, use_graph: bool = True, group=None, get_real: str = "real"):
+                 use_labels: bool = False, use_graph: bool = True, group=None, get_real: str = "real", overlap_allreduce: bool = True):
         if not (getattr(encoder, "fused", False) and getattr(decoder, "fused", False)):
             raise NotImplementedError("FusedTrainStep needs the fused (maxdim 2) encoder and decoder")
         self.enc, self.dec, self.B = encoder, decoder, int(batch)
@@ -78,6 +78,7 @@ class FusedTrainStep:
         self.l1 = float(l1_lambda) * float(l1_scale)
         self.normalize = normalize
         self.get_real = fused.get_real_mode(get_real)
+        self.overlap_allreduce = overlap_allreduce
         self.group = group
         self.lib = _lib.load()
         dev = next(encoder.parameters()).device
@@ -125,24 +126,44 @@ class FusedTrainStep:
             for name, p in model.named_parameters():
                 p.grad = views[name]
 
+    def _distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _split(self) -> bool:
+        """Two gradient buckets: the decoder's is all-reduced on the library's auxiliary stream while the encoder adjoint runs."""
+        return self._distributed() and self.overlap_allreduce and bool(self.lib.lgae_aux_stream())
+
+    def _phases(self, call):
+        """Run ``call(phase)`` as one step (phase 0) or -- data parallel -- as two phases with the all-reduce of the decoder's
+        bucket enqueued between them on the auxiliary stream (include/lgae_b200.h: lgae_aux_stream)."""
+        if not self._split():
+            call(0)
+            return
+        call(1)
+        aux = torch.cuda.ExternalStream(int(self.lib.lgae_aux_stream()), device=self.dev)
+        with torch.cuda.stream(aux):
+            dist.all_reduce(self.g_d, op=dist.ReduceOp.SUM, group=self.group)
+        call(2)
+
     def _launch(self):
         lib, pe, pd, B = self.lib, self.pe, self.pd, self.B
         st = torch.cuda.current_stream().cuda_stream
         th_e, _ = self.enc._flat_params()
         th_d, _ = self.dec._flat_params()
         self._thetas = (th_e.data_ptr(), th_d.data_ptr())
-        check(lib.lgae_train_step(C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(self.p4_in), ptr(self.mask), B,
-                                  1 if self.normalize else 0, ptr(self.p4), ptr(self.norm_factor), ptr(self.ws_e), ptr(self.ws_d),
-                                  ptr(self.latent00), ptr(self.latent11), ptr(self.sel), ptr(self.recon), ptr(self.g_recon),
-                                  ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss), ptr(self.g_all), self.off_d, ptr(self.part), self.l1,
-                                  self.get_real, st), "train_step")
+        self._phases(lambda phase: check(lib.lgae_train_step(
+            C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(self.p4_in), ptr(self.mask), B, 1 if self.normalize else 0,
+            ptr(self.p4), ptr(self.norm_factor), ptr(self.ws_e), ptr(self.ws_d), ptr(self.latent00), ptr(self.latent11), ptr(self.sel),
+            ptr(self.recon), ptr(self.g_recon), ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss), ptr(self.g_all), self.off_d,
+            ptr(self.part), self.l1, self.get_real, phase, st), "train_step"))
         self._launch_tail()
 
     def _launch_tail(self):
         """After the step's kernels: the data-parallel gradient exchange, then the attached optimizer."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size (SURVEY.md section 8(e))
-            dist.all_reduce(self.g_all, op=dist.ReduceOp.SUM, group=self.group)
+        if self._distributed():
+            # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size (SURVEY.md section 8(e)); in the
+            # split step the decoder's bucket is already being exchanged next to the encoder adjoint
+            dist.all_reduce(self.g_e if self._split() else self.g_all, op=dist.ReduceOp.SUM, group=self.group)
         if self.optimizer is not None:
             self.optimizer.step()
 
@@ -218,11 +239,12 @@ class FusedTrainStep:
         th_e, _ = self.enc._flat_params()
         th_d, _ = self.dec._flat_params()
         self._thetas = (th_e.data_ptr(), th_d.data_ptr())
-        check(lib.lgae_train_step_host(C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(self.host_p4), ptr(self.host_mask),
-                                       ptr(self.host_loss), ptr(self.p4_in), ptr(self.mask), B, 1 if self.normalize else 0, ptr(self.p4),
-                                       ptr(self.norm_factor), ptr(self.ws_e), ptr(self.ws_d), ptr(self.latent00), ptr(self.latent11),
-                                       ptr(self.sel), ptr(self.recon), ptr(self.g_recon), ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss),
-                                       ptr(self.g_all), self.off_d, ptr(self.part), self.l1, self.get_real, st), "train_step_host")
+        self._phases(lambda phase: check(lib.lgae_train_step_host(
+            C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(self.host_p4), ptr(self.host_mask), ptr(self.host_loss),
+            ptr(self.p4_in), ptr(self.mask), B, 1 if self.normalize else 0, ptr(self.p4), ptr(self.norm_factor), ptr(self.ws_e),
+            ptr(self.ws_d), ptr(self.latent00), ptr(self.latent11), ptr(self.sel), ptr(self.recon), ptr(self.g_recon), ptr(self.g_lat11),
+            ptr(self.jet_loss), ptr(self.loss), ptr(self.g_all), self.off_d, ptr(self.part), self.l1, self.get_real, phase, st),
+            "train_step_host"))
         self._launch_tail()
 
     def step_host(self, p4=None, labels=None) -> float:
