@@ -168,6 +168,13 @@ int lgae_train_step_host(const LgaeModelDesc* enc, const LgaeModelDesc* dec, con
                          double* norm_factor, double* ws_enc, double* ws_dec, double* lat00, double* lat11, int32_t* sel,
                          double* recon, double* g_recon, double* g_lat11, double* jet_loss, double* loss, double* gtheta,
                          int64_t gtheta_dec_offset, double* partials, double l1_lambda, int32_t get_real, int32_t phase, void* stream);
+/* Split step for data-parallel training (`phase` above): phase 0 runs the whole step.  phase 1 runs it up to the point where the
+ * DECODER's gradient bucket gtheta[gtheta_dec_offset, ...) is final -- its reduce is the last thing enqueued on the library's
+ * auxiliary stream of the current device, which this function returns (NULL when LGAE_NO_AUX=1) -- and phase 2 (same thread, same
+ * arguments, directly afterwards) runs the encoder adjoint and the encoder bucket's reduce on `stream` and joins the auxiliary
+ * stream back.  A caller enqueues the all-reduce of the decoder bucket on the auxiliary stream between the two calls: it then
+ * overlaps the encoder adjoint (SURVEY.md section 8(e) describes the exchange; the reference itself is single-process). */
+void* lgae_aux_stream(void);
 
 
 /* ---- caller-side ops on the hot path ------------------------------------------------------------- */
@@ -176,6 +183,14 @@ int lgae_train_step_host(const LgaeModelDesc* enc, const LgaeModelDesc* dec, con
  * *g_loss (device scalar) when g_loss != NULL.  jet_loss (B) optional per-jet loss (anomaly score). */
 int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32_t n, int32_t m, int32_t get_real,
                  double* loss, double* jet_loss, const double* g_loss, double* g_recon, void* stream);
+/* Per-jet anomaly scores of the Cartesian family (utils/jet_analysis/anomaly_detection.py:251-419) of x = f * get_real(recon)
+ * against f * target, both (B,N,4) (recon complex (2,B,N,4)); f = factor[b], or 1 when factor == NULL (the reference scores the
+ * un-normalised and the normalised jets).  scores (B,6): [0] chamfer with the Euclidean norm (:498-503), [1] MSE (:473),
+ * [2] chamfer with the Minkowski square (:523-527), [3] MSE with the Minkowski metric (:428-437), each averaged over the
+ * particles; [4] MSE of the jet momenta (sum over particles, :405), [5] its Minkowski version (:419).  The Hungarian and
+ * EMD scores (scipy / energyflow, per jet on the host) are outside the path. */
+int lgae_anomaly_scores(const double* recon, const double* target, const double* factor, int32_t batch, int32_t n, int32_t get_real,
+                        double* scores, void* stream);
 /* normalize_p4(..., 'overall_max') (utils/normalize_p4.py:39-52): out = p4 / (max|p4| + 1e-16) per jet. */
 int lgae_normalize_p4(const double* p4, int32_t batch, int32_t n, double* out, double* factor, void* stream);
 /* L1 regulariser: out[0] (+)= lambda * sum |theta| ; gtheta += lambda * sign(theta)  (lgn_encoder.py:249-250). */

@@ -70,6 +70,7 @@ int run_norm_input(const LgaeModelDesc* d, const double* theta, const double* p4
                    double* V, cudaStream_t st);
 int run_l1(const double* theta, int64_t n, double lambda, double* out, double* gtheta, cudaStream_t st);
 int run_scale(const double* in, int64_t n, double s, double* out, cudaStream_t st);
+int run_scores(const double* recon, const double* target, const double* factor, int B, int N, int mode, double* out, cudaStream_t st);
 
 // ---- bookkeeping ------------------------------------------------------------------------------------------------
 #define LGAE_MAX_DEVICES 64
@@ -741,6 +742,14 @@ int lgae_chamfer(const double* recon, const double* target, int32_t batch, int32
         return LGAE_OK;
     }
     return run_chamfer(recon, target, batch, n, m, loss, jet_loss, g_loss, g_recon, get_real, (cudaStream_t)stream);
+}
+
+int lgae_anomaly_scores(const double* recon, const double* target, const double* factor, int32_t batch, int32_t n, int32_t get_real,
+                        double* scores, void* stream) {
+    if (batch < 0 || n < 1 || (batch > 0 && (!recon || !target || !scores))) return LGAE_E_BADARG;
+    if (get_real < LGAE_GET_REAL_REAL || get_real > LGAE_GET_REAL_NORM) return LGAE_E_BADARG;
+    if (batch == 0) return LGAE_OK;
+    return run_scores(recon, target, factor, batch, n, get_real, scores, (cudaStream_t)stream);
 }
 
 int lgae_normalize_p4(const double* p4, int32_t batch, int32_t n, double* out, double* factor, void* stream) {

@@ -734,6 +734,67 @@ __global__ void __launch_bounds__(128) chamfer_kernel(const double* recon, const
     }
 }
 
+// Per-jet anomaly scores of the Cartesian family (utils/jet_analysis/anomaly_detection.py:251-419), one CTA per jet:
+//   x = scale * get_real(recon), t = scale * target (scale = factor[b] or 1: the reference scores both the un-normalised and the
+//   normalised jets), N == M.  out[b] = [chamfer (Euclidean norm, :498-503: mean_i (min_j |x_i - t_j| + min_j |x_j - t_i|)),
+//   mse (:473: mean_i |x_i - t_i|^2), chamfer_lorentz (:523-527, Minkowski square instead of the norm), mse_lorentz (:428-437),
+//   jet mse (:405: |sum_i x_i - sum_i t_i|^2), jet mse_lorentz (:419)].
+__global__ void __launch_bounds__(128) scores_kernel(const double* recon, const double* target, const double* factor, int B, int N, int mode,
+                                                     double* out) {
+    pdl_launch();
+    pdl_wait();
+    extern __shared__ __align__(128) double smem[];
+    double* x = smem;          // N*4
+    double* t = x + 4 * N;     // N*4
+    double* red = t + 4 * N;   // 4 * N : per-particle terms
+    __shared__ double scratch[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int64_t plane = (int64_t)B * N * 4;
+    const double sc = factor ? factor[b] : 1.0;
+    for (int k = tid; k < 4 * N; k += blockDim.x) {
+        x[k] = sc * get_real_value(mode, recon[(int64_t)b * N * 4 + k], recon[plane + (int64_t)b * N * 4 + k]);
+        t[k] = sc * target[(int64_t)b * N * 4 + k];
+    }
+    __syncthreads();
+    auto lor = [](double d0, double d1, double d2, double d3) { return d0 * d0 - d1 * d1 - d2 * d2 - d3 * d3; };
+    for (int i = tid; i < N; i += blockDim.x) {
+        double e_pq = INFINITY, e_qp = INFINITY, l_pq = INFINITY, l_qp = INFINITY;
+        for (int j = 0; j < N; ++j) {
+            // dist[i][j] = d(x_i, t_j): min over j (dim -1) and, for the other direction, min over the first index of dist[j][i]
+            const double a0 = x[4 * i] - t[4 * j], a1 = x[4 * i + 1] - t[4 * j + 1], a2 = x[4 * i + 2] - t[4 * j + 2], a3 = x[4 * i + 3] - t[4 * j + 3];
+            const double c0 = x[4 * j] - t[4 * i], c1 = x[4 * j + 1] - t[4 * i + 1], c2 = x[4 * j + 2] - t[4 * i + 2], c3 = x[4 * j + 3] - t[4 * i + 3];
+            e_pq = fmin(e_pq, sqrt(a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3));
+            e_qp = fmin(e_qp, sqrt(c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3));
+            l_pq = fmin(l_pq, lor(a0, a1, a2, a3));
+            l_qp = fmin(l_qp, lor(c0, c1, c2, c3));
+        }
+        const double d0 = x[4 * i] - t[4 * i], d1 = x[4 * i + 1] - t[4 * i + 1], d2 = x[4 * i + 2] - t[4 * i + 2], d3 = x[4 * i + 3] - t[4 * i + 3];
+        red[i] = e_pq + e_qp;
+        red[N + i] = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        red[2 * N + i] = l_pq + l_qp;
+        red[3 * N + i] = lor(d0, d1, d2, d3);
+    }
+    __syncthreads();
+    double res[4];
+    for (int s = 0; s < 4; ++s) {
+        double acc = 0.0;
+        for (int i = tid; i < N; i += blockDim.x) acc += red[s * N + i];
+        res[s] = block_sum(acc, scratch);
+    }
+    double jd[4];
+    for (int mu = 0; mu < 4; ++mu) {
+        double acc = 0.0;
+        for (int i = tid; i < N; i += blockDim.x) acc += x[4 * i + mu] - t[4 * i + mu];
+        jd[mu] = block_sum(acc, scratch);
+    }
+    if (tid == 0) {
+        double* o = out + (int64_t)b * 6;
+        o[0] = res[0] / N; o[1] = res[1] / N; o[2] = res[2] / N; o[3] = res[3] / N;
+        o[4] = jd[0] * jd[0] + jd[1] * jd[1] + jd[2] * jd[2] + jd[3] * jd[3];
+        o[5] = lor(jd[0], jd[1], jd[2], jd[3]);
+    }
+}
+
 // Decoder tail of a training step, one CTA per jet: mix_to_output + rep_to_p (reconstruction), get_real('sum') + chamfer against
 // the target jet, the loss gradient, and the adjoint of the output map -- dec_output, chamfer, chamfer_sum and dec_output_bwd
 // in one launch.  The last CTA to finish adds up the per-jet losses in a fixed order (`counter` must be zero at launch; it is
@@ -1301,6 +1362,14 @@ int run_chamfer(const double* recon, const double* target, int B, int N, int M, 
         rc = check_launch("chamfer_sum");
     }
     return rc;
+}
+int run_scores(const double* recon, const double* target, const double* factor, int B, int N, int mode, double* out, cudaStream_t st) {
+    const size_t bytes = (size_t)12 * N * sizeof(double);
+    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+    if (int rc = ensure_smem((const void*)scores_kernel, bytes)) return rc;
+    LaunchScope ls_("anomaly_scores", st);
+    launch_k(scores_kernel, dim3(B), dim3(128), bytes, st, recon, target, factor, B, N, mode, out);
+    return check_launch("anomaly_scores");
 }
 // mix_to_output + chamfer + their adjoints for a training step (see dec_tail_kernel).  `counter`: 4 bytes of device scratch.
 int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, const double* V, const double* target, double* recon,

@@ -300,6 +300,25 @@ def chamfer_per_jet(recon: torch.Tensor, target: torch.Tensor, get_real: str = "
     return jet
 
 
+SCORE_NAMES = ("chamfer_particle_cartesian", "mse_particle_cartesian", "chamfer_particle_lorentz", "mse_particle_lorentz", "jet_cartesian",
+               "jet_lorentz")
+
+
+def anomaly_scores(recon: torch.Tensor, target: torch.Tensor, get_real: str = "real", factor: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Per-jet anomaly scores of the Cartesian family (utils/jet_analysis/anomaly_detection.py:251-419) in one launch:
+    ``recon`` (2,B,N,4) complex reconstruction, ``target`` (B,N,4); ``factor`` (B,) optionally rescales both (the reference scores the
+    un-normalised jets ``recons * norm_factor`` and the normalised ones).  Returns {name: (B,)} for SCORE_NAMES."""
+    lib = _lib.load()
+    recon, target = recon.contiguous(), target.contiguous()
+    b, n = recon.shape[1], recon.shape[2]
+    if target.shape[1] != n:
+        raise ValueError("anomaly scores compare jets with the same number of particles")
+    out = torch.empty((b, len(SCORE_NAMES)), dtype=torch.float64, device=recon.device)
+    f = None if factor is None else factor.reshape(-1).to(torch.float64).contiguous()
+    check(lib.lgae_anomaly_scores(ptr(recon), ptr(target), ptr(f), b, n, get_real_mode(get_real), ptr(out), _stream()), "anomaly_scores")
+    return {name: out[:, i] for i, name in enumerate(SCORE_NAMES)}
+
+
 def normalize_p4(p4: torch.Tensor):
     """normalize_p4(p4, 'overall_max') (utils/normalize_p4.py:39-52) -> (normalised, factor (B,1,1))."""
     lib = _lib.load()

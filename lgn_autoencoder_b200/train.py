@@ -403,6 +403,13 @@ class FusedInference:
         check(lib.lgae_chamfer(ptr(self.recon), ptr(self.p4), B, pd.n_particles, pe.n_particles, self.get_real, None, ptr(self.scores), None, None, st),
               "chamfer")
 
+    def all_scores(self, unnormalized: bool = False):
+        """After ``score`` / ``run``: every per-jet score of the Cartesian family (``fused.SCORE_NAMES``: chamfer / MSE with the
+        Euclidean and the Minkowski metric, jet-level MSEs; utils/jet_analysis/anomaly_detection.py:251-419) of the last batch,
+        on the normalised jets or -- ``unnormalized`` -- rescaled by the per-jet normalisation factors as test.py does."""
+        return fused.anomaly_scores(self.recon, self.p4, ("real", "imag", "sum", "mean", "norm")[self.get_real],
+                                    self.norm_factor if unnormalized else None)
+
     def run(self):
         if not self.use_graph:
             self._launch()

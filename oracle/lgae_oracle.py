@@ -591,6 +591,26 @@ def chamfer_loss(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return torch.sum((dist.min(dim=-1).values + dist.min(dim=-2).values) / 2)
 
 
+def anomaly_scores_cartesian(recons: torch.Tensor, target: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """The Cartesian-family scores of utils/jet_analysis/anomaly_detection.py:251-419 on real (B,N,4) jets: chamfer (:498-503,
+    Euclidean norm, both directions added per particle index, mean over particles), mse (:473), their Minkowski versions
+    (:523-527, :428-437) and the jet-level scores (:405, :419; jet = sum over particles, :653-654)."""
+    def lorentz(x):
+        return x[..., 0] ** 2 - x[..., 1] ** 2 - x[..., 2] ** 2 - x[..., 3] ** 2
+    diffs = recons.unsqueeze(-2) - target.unsqueeze(-3)
+    dist = torch.norm(diffs, dim=-1)
+    dl = lorentz(diffs)
+    jr, jt = recons.sum(-2), target.sum(-2)
+    return {
+        "chamfer_particle_cartesian": (dist.min(-1).values + dist.min(-2).values).mean(-1),
+        "mse_particle_cartesian": ((recons - target) ** 2).sum(-1).mean(-1),
+        "chamfer_particle_lorentz": (dl.min(-1).values + dl.min(-2).values).mean(-1),
+        "mse_particle_lorentz": lorentz(recons - target).mean(-1),
+        "jet_cartesian": ((jr - jt) ** 2).sum(-1),
+        "jet_lorentz": lorentz(jr - jt),
+    }
+
+
 def l1_norm(sd: dict) -> torch.Tensor:
     return sum(p.abs().sum() for p in sd.values())                         # lgn_encoder.py:249-250
 

@@ -99,3 +99,13 @@ def test_sum_pooling_encoder_matches_reference():
             assert enc_sd[k].grad is None or enc_sd[k].grad.abs().max().item() == 0.0, k
         else:
             assert rel_err(enc_sd[k].grad, ref) < 1e-10, k
+
+
+def test_anomaly_scores_match_reference():
+    """The Cartesian-family anomaly scores against the unmodified reference's functions (tests/golden/make_scores_golden.py)."""
+    g = load_golden("anomaly_scores")
+    mine = orc.anomaly_scores_cartesian(g["recons"], g["target"])
+    for short, name in (("chamfer_cartesian", "chamfer_particle_cartesian"), ("mse_cartesian", "mse_particle_cartesian"),
+                        ("chamfer_lorentz", "chamfer_particle_lorentz"), ("mse_lorentz", "mse_particle_lorentz"),
+                        ("jet_cartesian", "jet_cartesian"), ("jet_lorentz", "jet_lorentz")):
+        assert rel_err(mine[name], g[short]) < TOL, name

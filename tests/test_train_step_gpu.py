@@ -278,3 +278,31 @@ def test_fused_train_step_get_real_modes(name):
     assert rel_err(step.recon, g["recons"]) < 1e-10
     assert_grads_close({k: p.grad for k, p in enc.named_parameters()}, g["grads_enc"])
     assert_grads_close({k: p.grad for k, p in dec.named_parameters()}, g["grads_dec"])
+
+
+def test_anomaly_scores_match_reference_and_oracle():
+    """(f3) lgae_anomaly_scores: chamfer / MSE with the Euclidean and the Minkowski metric and the jet-level scores
+    (utils/jet_analysis/anomaly_detection.py:251-419) against the reference's golden values, and through FusedInference against the
+    oracle on the model's own reconstruction (normalised and rescaled by the per-jet factors)."""
+    from lgn_autoencoder_b200 import fused
+    from lgn_autoencoder_b200.train import FusedInference
+    from oracle import lgae_oracle as orc
+    dev = torch.device("cuda:0")
+    g = load_golden("anomaly_scores")
+    recon_c = torch.stack([g["recons"], 0.3 * g["recons"]]).to(dev)     # complex (2,B,N,4); 'real' picks the first plane
+    mine = fused.anomaly_scores(recon_c, g["target"].to(dev), "real")
+    for short, name in (("chamfer_cartesian", "chamfer_particle_cartesian"), ("mse_cartesian", "mse_particle_cartesian"),
+                        ("chamfer_lorentz", "chamfer_particle_lorentz"), ("mse_lorentz", "mse_particle_lorentz"),
+                        ("jet_cartesian", "jet_cartesian"), ("jet_lorentz", "jet_lorentz")):
+        assert rel_err(mine[name], g[short]) < 1e-10, name
+    _, enc, dec, batch = load("cfg1_b3", dev)
+    inf = FusedInference(enc, dec, batch["p4"].shape[0], normalize=True, get_real="sum")
+    p4 = batch["p4"] * 3.7
+    inf.score(p4)
+    x = (inf.recon[0] + inf.recon[1]).cpu()
+    for unnorm in (False, True):
+        f = inf.norm_factor.cpu().view(-1, 1, 1) if unnorm else 1.0
+        ref = orc.anomaly_scores_cartesian(x * f, inf.p4.cpu() * f)
+        got = inf.all_scores(unnormalized=unnorm)
+        for name in fused.SCORE_NAMES:
+            assert rel_err(got[name], ref[name]) < 1e-10, (name, unnorm)
