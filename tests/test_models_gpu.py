@@ -36,7 +36,8 @@ def test_module_forward_backward_matches_reference(name):
     from lgn_autoencoder_b200 import fused
     dev = torch.device("cuda:0")
     g, enc, dec, batch = load(name, dev)
-    assert enc.fused == (g["cfg"]["maxdim"] == 2) and dec.fused == (g["cfg"]["maxdim"] == 2)
+    assert dec.fused == (g["cfg"]["maxdim"] == 2)
+    assert enc.fused == (g["cfg"]["maxdim"] == 2 and g["cfg"]["map_to_latent"].lower() in fused.LATENT_MODES)   # 'min+max' pools in the generic composite
     latent = enc(batch, covariance_test=False)
     recon = dec(latent, covariance_test=False)
     for key, val in g["latent"].items():
@@ -184,9 +185,10 @@ def test_equivariance_no_worse_than_reference():
 def test_batched_equivariance_harness_matches_sequential():
     """(f2) The 26 transforms of a covariance test run as ONE batch of 26 B jets; the deviation tables equal those of the
     transform-by-transform evaluation (per-jet results do not depend on the batch they are in)."""
-    from lgn_autoencoder_b200.models.autotest import covariance_test, lgn_tests as harness
-    from lgn_autoencoder_b200.models.autotest import lgn_tests as lgn_tests_fn, permutation_invariance_test
-    import lgn_autoencoder_b200.models.autotest.lgn_tests as mod
+    import importlib
+    from lgn_autoencoder_b200.models.autotest import covariance_test, permutation_invariance_test
+    from lgn_autoencoder_b200.models.autotest import lgn_tests as lgn_tests_fn
+    mod = importlib.import_module("lgn_autoencoder_b200.models.autotest.lgn_tests")   # (the package re-exports a function of that name)
     dev = torch.device("cuda:0")
     g = load_golden("equivariance_cfg1")
     enc, dec = build(g["cfg"], dev)
@@ -201,10 +203,15 @@ def test_batched_equivariance_harness_matches_sequential():
     finally:
         mod.MAX_JETS_PER_PASS = old
     assert batched["gammas"] == seq["gammas"]
+
+    def same(a, b):
+        # the per-jet features are identical; the deviation is a mean over a (strided) slice of the batched tensors, whose
+        # summation order differs from that of a stand-alone tensor
+        return all(abs(a[w] - b[w]) <= 1e-6 * max(abs(a[w]), abs(b[w])) + 1e-18 for w in a)
     for a, b in zip(batched["boost_dev_output"], seq["boost_dev_output"]):
-        assert a == b
+        assert same(a, b), (a, b)
     for la, lb in zip(batched["boost_dev_internal"], seq["boost_dev_internal"]):
-        assert la == lb
+        assert all(same(a, b) for a, b in zip(la, lb))
     # permutation test: reference semantics (per-jet permutation of the real particles, 'max'-mode deviations per irrep)
     inv, equi = permutation_invariance_test(enc, dec, dict(data))
     assert set(inv) == {(0, 0), (1, 1)} and set(equi) == {(0, 0), (1, 1)}
@@ -214,12 +221,13 @@ def test_batched_equivariance_harness_matches_sequential():
     res = lgn_tests_fn(types.SimpleNamespace(num_test_batch=1), enc, dec, [dict(data), dict(data)], "z", 10.0, None, enc.cg_dict, "TeV")
     assert len(res["gammas"]) == 26 and len(res["boost_dev_output"]) == 26
     for a, b in zip(res["boost_dev_output"], batched["boost_dev_output"]):
-        assert a == b
+        assert same(a, b), (a, b)
 
 
 def test_reference_cli_runs_unchanged_through_the_shim(tmp_path):
     """The reference's own main.py -> test.py -> covariance_test.py (baseline/_ref, unmodified) against this repository's `lgn`
-    package on the GPU: 1 epoch of training on synthetic jets in the reference's .pt format, inference, equivariance test."""
+    package on the GPU: 2 epochs of training (test.py resolves the best epoch 0-based, utils/train.py:117,127 -- with one epoch it
+    looks for a file the reference never writes) on synthetic jets in the reference's .pt format, inference, equivariance test."""
     import json
     import os
     import subprocess
@@ -229,7 +237,7 @@ def test_reference_cli_runs_unchanged_through_the_shim(tmp_path):
         pytest.skip("baseline/_ref (copy of the unmodified reference, tools/setup_reference.py) is not present")
     out = str(tmp_path / "refcli")
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "run_reference_cli.py"), "--out", out, "--device", "cuda", "--jets", "256",
-                        "--batch", "64", "--epochs", "1", "--test-jets", "32"], capture_output=True, text=True, timeout=1500)
+                        "--batch", "64", "--epochs", "2", "--test-jets", "32"], capture_output=True, text=True, timeout=1500)
     logs = ""
     for name in ("main.log", "test.log", "covariance_test.log"):
         f = os.path.join(out, name)

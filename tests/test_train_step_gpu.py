@@ -305,4 +305,7 @@ def test_anomaly_scores_match_reference_and_oracle():
         ref = orc.anomaly_scores_cartesian(x * f, inf.p4.cpu() * f)
         got = inf.all_scores(unnormalized=unnorm)
         for name in fused.SCORE_NAMES:
-            assert rel_err(got[name], ref[name]) < 1e-10, (name, unnorm)
+            # the Minkowski scores are differences of squares (near-cancelling for a good reconstruction): their error is
+            # measured against the Euclidean counterpart's scale
+            scale = ref[name.replace("lorentz", "cartesian")].abs().max().item()
+            assert (got[name].cpu() - ref[name]).abs().max().item() < 1e-10 * scale, (name, unnorm)
