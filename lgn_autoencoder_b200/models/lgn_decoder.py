@@ -4,11 +4,12 @@ Reference behaviours kept on purpose: the decoder's nod
 radial functions reduce to their Linear biases; the zonal (0,0) function is 1+1j; the latent scalars never reach
 the output."""
 import logging
+import os
 
 import torch
 
 from .. import fused
-from ..cg_lib import CGDict, CGModule, ZonalFunctions, ZonalFunctionsRel, p_cplx_to_rep, rep_to_p
+from ..cg_lib import CGDict, CGModule, ZonalFunctions, ZonalFunctionsRel, cg_product, p_cplx_to_rep, rep_to_p
 from ..g_lib import GTau, GVec
 from ..nn import MixReps, RadialFilters
 from .fused_module import FusedParamsMixin
@@ -115,14 +116,22 @@ class LGNDecoder(FusedParamsMixin, CGModule):
         graph = self.latent_to_graph(latent_features)
         graph = GVec({k: v.squeeze(-3) for k, v in graph.items()}, ignore_check=True)
         node_ps = p_cplx_to_rep(graph[(1, 1)])[(1, 1)]
-        b, n = node_ps.shape[1], node_ps.shape[2]
-        edge_mask = torch.zeros(2, b, n, n, dtype=torch.float32, device=node_ps.device)     # lgn_decoder.py:335-340
-        node_mask = torch.zeros(2, b, n, dtype=torch.float32, device=node_ps.device)
         zf_in, _, _ = self.zonal_fns_in(node_ps)
-        zonal, norms, _ = self.zonal_fns(node_ps, node_ps)
-        rad = self.rad_funcs(norms, edge_mask * (norms != 0).byte())
         node = self.input_func_node(zf_in)
-        dec_nodes = self.lgn_cg(node, node_mask, rad, zonal)
+        dec_nodes = [node]
+        if os.environ.get("LGAE_DEC_PAIRLOOP") == "1" or any(z != 1 for z in self.max_zf):
+            # the reference's O(N^2) form: pairwise zonal functions, (masked-out) radial functions, edge features, aggregation
+            b, n = node_ps.shape[1], node_ps.shape[2]
+            node_mask = torch.zeros(2, b, n, dtype=torch.float32, device=node_ps.device)     # lgn_decoder.py:335-340
+            zonal, norms, _ = self.zonal_fns(node_ps, node_ps)
+            rad = self.rad_funcs.forward_masked_out(norms.shape)
+            dec_nodes = self.lgn_cg(node, node_mask, rad, zonal)
+        else:
+            for idx, lvl in enumerate(self.lgn_cg.node_levels):
+                node = self._level_closed_form(lvl, self.rad_funcs.rad_funcs[idx], node, zf_in[(1, 1)])
+                if self.lgn_cg.mlp:
+                    node = self.lgn_cg.mlp_levels[idx](node)
+                dec_nodes.append(node)
         gen = self.mix_to_output(dec_nodes[-1])
         gen = GVec({w: gen[w] for w in [(0, 0), (1, 1)]}, ignore_check=True)
         if not covariance_test:
@@ -131,3 +140,28 @@ class LGNDecoder(FusedParamsMixin, CGModule):
             nodes_all.append(node)
         nodes_all.append(gen)
         return gen, nodes_all
+
+    def _level_closed_form(self, lvl, rad, node, y):
+        """One LGN level of the decoder (lgn_levels.py:96-121) in O(N).  The decoder's edge mask is identically zero
+        (lgn_decoder.py:335-340), so the radial weights are the constants R^l[c] = bias_l[c] (1+i) and the edge features are
+        e^(0,0)_ij = R^0 (1+i), e^(1,1)_ij = R^1 (y_i - y_j).  The CG product is bilinear, hence
+            sum_j CG(node_j (x) e_ij) = CG(M (x) E_i) - sum_j CG(node_j (x) E'_j),
+        M = sum_j node_j,  E_i = {(0,0): R^0 (1+i), (1,1): R^1 y_i},  E'_j = {(0,0): 0, (1,1): R^1 y_j}:
+        two point-wise products over the N particles instead of one over the N^2 edges; no (2,B,N,N,C,d) tensor exists.
+        y: (2,B,N,1,4) canonical momenta of the nodes.  Same pair order / channel layout as the aggregated product."""
+        b0, b1 = rad.linear[0].bias, rad.linear[1].bias          # (C,)
+        some = next(iter(node.values()))
+        B, N = some.shape[1], some.shape[2]
+        zero = torch.zeros_like(b0)
+        e00 = torch.stack((zero, 2.0 * b0)).view(2, 1, 1, -1, 1).expand(2, B, N, -1, 1)          # b0 (1+i)(1+i) = 2i b0
+        yr, yi = y[0], y[1]                                                                       # (B,N,1,4)
+        b1v = b1.view(1, 1, -1, 1)
+        e11 = torch.stack((b1v * yr - b1v * yi, b1v * yi + b1v * yr))                             # b1 (1+i) y
+        mom = GVec({k: v.sum(dim=2, keepdim=True).expand(-1, -1, N, -1, -1) for k, v in node.items()}, ignore_check=True)
+        edge = GVec({(0, 0): e00, (1, 1): e11}, ignore_check=True)
+        edge1 = GVec({(0, 0): torch.zeros_like(e00), (1, 1): e11}, ignore_check=True)
+        a = cg_product(self.cg_dict, mom, edge, maxdim=lvl.maxdim)
+        bj = cg_product(self.cg_dict, node, edge1, maxdim=lvl.maxdim)
+        reps_ag = GVec({k: a[k] - bj[k].sum(dim=2, keepdim=True) for k in a.keys()}, ignore_check=True)
+        reps_sq = lvl.cg_power(node, node)
+        return lvl.cat_mix([reps_ag, node, reps_sq])

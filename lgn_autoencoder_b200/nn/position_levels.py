@@ -5,6 +5,28 @@ import torch.nn as nn
 from ..g_lib import GScalar
 
 
+class _MaskedOutRadialFn(torch.autograd.Function):
+    """RadPolyTrig.forward with an all-zero edge mask (the decoder, lgn_decoder.py:335-340): every bell is replaced by 0, so
+    each output is exactly its Linear's bias, broadcast over the edges.  Same values and gradients as the general kernel (the
+    bias gradient is the sum over the edges; a, b, c and the Linear weights get exact zeros) without
+    evaluating 2K reciprocals per edge in either direction."""
+
+    @staticmethod
+    def forward(ctx, shape, n_l, a, b, c, *wb):
+        ctx.meta = (tuple(a.shape), [tuple(wb[2 * l].shape) for l in range(n_l)], n_l)
+        return tuple(wb[2 * l + 1].detach().expand(*shape, -1).contiguous() for l in range(n_l))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        ashape, wshapes, n_l = ctx.meta
+        g0 = gs[0]
+        zeros = lambda shp: torch.zeros(shp, dtype=g0.dtype, device=g0.device)
+        out = [None, None, zeros(ashape), zeros(ashape), zeros(ashape)]
+        for l in range(n_l):
+            out += [zeros(wshapes[l]), gs[l].reshape(-1, gs[l].shape[-1]).sum(0)]
+        return tuple(out)
+
+
 class RadPolyTrig(nn.Module):
     """phi_k(n) = b_k / (1 + (c_k n)^2 + 1e-16) + a_k for 2*num_basis_fn bells, zeroed on masked edges, followed by
     one Linear per zonal degree l.  Cartesian input: Linear(2K' -> 2C), outputs (2c, 2c+1) = (re, im) of channel c.
@@ -35,6 +57,16 @@ class RadPolyTrig(nn.Module):
         else:
             raise ValueError(f"Can only specify mix = real, cplx, or none: {mix}")
         self.device = device
+
+    def forward_masked_out(self, shape):
+        """The radial functions of ``norms`` of the given shape when EVERY edge is masked out (canonical basis, mix 'cplx')."""
+        if not (self.mix == "cplx" or self.mix is True) or self.input_basis != "canonical":
+            raise NotImplementedError("forward_masked_out covers the decoder's configuration (canonical basis, complex mixing)")
+        wb = []
+        for lin in self.linear:
+            wb += [lin.weight, lin.bias]
+        outs = _MaskedOutRadialFn.apply(tuple(shape), len(self.linear), self.a, self.b, self.c, *wb)
+        return GScalar({(l, l): o for l, o in enumerate(outs)}, ignore_check=True)
 
     def forward(self, norms, edge_mask):
         if self.mix == "cplx" or self.mix is True:
@@ -79,3 +111,6 @@ class RadialFilters(nn.Module):
 
     def forward(self, norms, base_mask, basis="cartesian"):
         return [rf(norms, base_mask) for rf in self.rad_funcs]
+
+    def forward_masked_out(self, shape):
+        return [rf.forward_masked_out(shape) for rf in self.rad_funcs]

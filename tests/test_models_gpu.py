@@ -215,7 +215,9 @@ def test_batched_equivariance_harness_matches_sequential():
     # permutation test: reference semantics (per-jet permutation of the real particles, 'max'-mode deviations per irrep)
     inv, equi = permutation_invariance_test(enc, dec, dict(data))
     assert set(inv) == {(0, 0), (1, 1)} and set(equi) == {(0, 0), (1, 1)}
-    assert equi[(1, 1)] < 1e-8 and equi[(0, 0)] < 1e-8
+    # the autoencoder is permutation INVARIANT (min&max pooling; the decoder orders its output by latent_to_graph), so the
+    # invariance deviation is rounding noise while the "equivariance" one is O(1) by construction, in the reference as well
+    assert inv[(1, 1)] < 1e-9 and inv[(0, 0)] < 1e-9
     # the reference's positional signature (args, encoder, decoder, dataloader, axis, alpha_max, theta_max, cg_dict, unit) and num_test_batch
     import types
     res = lgn_tests_fn(types.SimpleNamespace(num_test_batch=1), enc, dec, [dict(data), dict(data)], "z", 10.0, None, enc.cg_dict, "TeV")
