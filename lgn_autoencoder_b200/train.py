@@ -68,7 +68,8 @@ class FusedTrainStep:
     """
 
     def __init__(self, encoder, decoder, batch: int, l1_lambda: float = 1e-8, l1_scale: float = 1.0, normalize: bool = True,
-                 use_labels: bool = False, use_graph: bool = True, group=None, get_real: str = "real", overlap_allreduce: bool = True):
+                 use_labels: bool = False, use_graph: bool = True, group=None, get_real: str = "real", overlap_allreduce: bool = True,
+                 peer_allreduce: bool = True):
         if not (getattr(encoder, "fused", False) and getattr(decoder, "fused", False)):
             raise NotImplementedError("FusedTrainStep needs the fused (maxdim 2) encoder and decoder")
         self.enc, self.dec, self.B = encoder, decoder, int(batch)
@@ -107,6 +108,13 @@ class FusedTrainStep:
         self.g_all = torch.zeros(off_d + self.pd.n_params, **f64)
         self.g_e = self.g_all[:self.pe.n_params]
         self.g_d = self.g_all[off_d:]
+        # data parallel: the step's reduce kernels write the local gradient into a bucket that is mapped into every rank of the
+        # node (symmetric memory), and one kernel of the library pulls and adds all ranks' buckets into g_all over NVLink
+        # (lgae_peer_allreduce); NCCL's all-reduce is the fallback (LGAE_PEER_ALLREDUCE=0, or no peer mapping available)
+        self.g_step = self.g_all
+        self._peer = None
+        if peer_allreduce and self._distributed():
+            self._setup_peer()
         self.optimizer = None
         self._probe = (next(encoder.parameters()), next(decoder.parameters()))
         self._bind_grads()
@@ -126,12 +134,44 @@ class FusedTrainStep:
             for name, p in model.named_parameters():
                 p.grad = views[name]
 
+    def _setup_peer(self):
+        """Collective over the group: allocate the symmetric gradient bucket and exchange the peer mappings."""
+        import os
+        ok = 0
+        state = None
+        if os.environ.get("LGAE_PEER_ALLREDUCE", "1") != "0":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                need = int(self.lib.lgae_peer_signal_bytes())
+                if symm_mem.get_signal_pad_size() < need:
+                    symm_mem.set_signal_pad_size(need)
+                g_sym = symm_mem.empty(self.g_all.numel(), dtype=torch.float64, device=self.dev)
+                g_sym.zero_()
+                hdl = symm_mem.rendezvous(g_sym, self.group if self.group is not None else dist.group.WORLD)
+                world = int(hdl.world_size)
+                bufs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+                sigs = (C.c_void_p * world)(*[int(p) for p in hdl.signal_pad_ptrs])
+                state = (g_sym, hdl, bufs, sigs, int(hdl.rank), world, torch.zeros(1, dtype=torch.int32, device=self.dev))
+                ok = 1 if world <= 16 else 0
+            except Exception as e:   # noqa: BLE001  (no NVLink peer access, older torch, ...): NCCL carries the exchange
+                import logging
+                logging.warning(f"lgn_autoencoder_b200: peer-memory all-reduce unavailable ({e!r}); using NCCL")
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)     # every rank takes the same path
+        if int(flag.item()) == 1:
+            self._peer = state
+            self.g_step = state[0]
+
+    def peer_error(self) -> bool:
+        """True if a hand-shake of the peer all-reduce ever timed out on this rank (results are then invalid)."""
+        return self._peer is not None and bool(self._peer[6].item())
+
     def _distributed(self) -> bool:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def _split(self) -> bool:
         """Two gradient buckets: the decoder's is all-reduced on the library's auxiliary stream while the encoder adjoint runs."""
-        return self._distributed() and self.overlap_allreduce and bool(self.lib.lgae_aux_stream())
+        return self._distributed() and self._peer is None and self.overlap_allreduce and bool(self.lib.lgae_aux_stream())
 
     def _phases(self, call):
         """Run ``call(phase)`` as one step (phase 0) or -- data parallel -- as two phases with the all-reduce of the decoder's
@@ -154,13 +194,18 @@ class FusedTrainStep:
         self._phases(lambda phase: check(lib.lgae_train_step(
             C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(self.p4_in), ptr(self.mask), B, 1 if self.normalize else 0,
             ptr(self.p4), ptr(self.norm_factor), ptr(self.ws_e), ptr(self.ws_d), ptr(self.latent00), ptr(self.latent11), ptr(self.sel),
-            ptr(self.recon), ptr(self.g_recon), ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss), ptr(self.g_all), self.off_d,
+            ptr(self.recon), ptr(self.g_recon), ptr(self.g_lat11), ptr(self.jet_loss), ptr(self.loss), ptr(self.g_step), self.off_d,
             ptr(self.part), self.l1, self.get_real, phase, st), "train_step"))
         self._launch_tail()
 
     def _launch_tail(self):
         """After the step's kernels: the data-parallel gradient exchange, then the attached optimizer."""
-        if self._distributed():
+        if self._peer is not None:
+            # one kernel: hand-shake with the peers, pull every rank's bucket over NVLink, add in rank order into g_all
+            g_sym, _, bufs, sigs, rank, world, err = self._peer
+            check(self.lib.lgae_peer_allreduce(bufs, sigs, rank, world, self.g_all.numel(), ptr(self.g_all), ptr(err),
+                                               torch.cuda.current_stream().cuda_stream), "peer_allreduce")
+        elif self._distributed():
             # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size (SURVEY.md section 8(e)); in the
             # split step the decoder's bucket is already being exchanged next to the encoder adjoint
             dist.all_reduce(self.g_e if self._split() else self.g_all, op=dist.ReduceOp.SUM, group=self.group)
@@ -243,7 +288,7 @@ class FusedTrainStep:
             C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(self.host_p4), ptr(self.host_mask), ptr(self.host_loss),
             ptr(self.p4_in), ptr(self.mask), B, 1 if self.normalize else 0, ptr(self.p4), ptr(self.norm_factor), ptr(self.ws_e),
             ptr(self.ws_d), ptr(self.latent00), ptr(self.latent11), ptr(self.sel), ptr(self.recon), ptr(self.g_recon), ptr(self.g_lat11),
-            ptr(self.jet_loss), ptr(self.loss), ptr(self.g_all), self.off_d, ptr(self.part), self.l1, self.get_real, phase, st),
+            ptr(self.jet_loss), ptr(self.loss), ptr(self.g_step), self.off_d, ptr(self.part), self.l1, self.get_real, phase, st),
             "train_step_host"))
         self._launch_tail()
 
