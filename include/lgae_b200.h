@@ -329,11 +329,14 @@ int lgae_linear_backward(const double* x, const double* w, const double* y, cons
  * >= lgae_peer_signal_bytes() bytes), both mapped into this process (symmetric memory; HOST arrays of `world` device pointers).
  * out (n, local) receives sum_r bufs[r] added in rank order, i.e. bit-identical on every rank.  Every rank must make the same
  * call in the same order on its stream; the kernel hand-shakes with the peers before reading and after, so the buckets may be
- * overwritten as soon as it has completed.  err_flag (device int32, zero-initialised) is set if a hand-shake timed out.
+ * overwritten as soon as it has completed.  multicast != NULL: the address of the buckets' NVSwitch multicast mapping (NVLS);
+ * the exchange then runs in place through the switch (multimem.ld_reduce / multimem.st, every rank reduces and broadcasts its
+ * 1/world slice) and `out` must be this rank's own bucket bufs[rank].  err_flag (device int32, zero-initialised) is set if a
+ * hand-shake timed out.
  * Replaces the ncclAllReduce of the bucket (the reference is single-process: utils/train.py has no exchange at all). */
 int64_t lgae_peer_signal_bytes(void);
 int lgae_peer_allreduce(const double* const* bufs, uint32_t* const* signals, int32_t rank, int32_t world, int64_t n, double* out,
-                        int32_t* err_flag, void* stream);
+                        double* multicast, int32_t* err_flag, void* stream);
 
 /* ---- the caller of the hot path: optimizer step ------------------------------------------------------------------
  * torch.optim.Adam (amsgrad = False) on the flat parameter / gradient buffers of up to two models in one launch

@@ -141,7 +141,7 @@ _PROTOS = {
     "lgae_linear_partials_doubles": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
     "lgae_linear_backward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P, _P, _P, _P, _P]),
     "lgae_peer_signal_bytes": (C.c_int64, []),
-    "lgae_peer_allreduce": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
+    "lgae_peer_allreduce": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "lgae_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                  _P, _P]),
     "lgae_rmsprop_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,

@@ -10,8 +10,10 @@
 namespace lgae {
 
 constexpr int PEER_MAX = 16;
-constexpr int PEER_BLOCKS = 32;      // co-resident on every GPU of the node (the barrier needs all blocks running)
-constexpr int PEER_THREADS = 512;
+constexpr int PEER_BLOCKS = 32;      // slots per phase in the signal pad = the largest grid; all blocks are co-resident on every GPU
+constexpr int PEER_THREADS = 1024;
+constexpr int PEER_PULL_THREADS = 512;   // the pull kernel keeps 16 double2 in flight per thread
+constexpr int PEER_MC_BLOCKS = 8;    // the multicast path moves n / W doubles per rank: few blocks, few flags on the wire
 struct PeerArgs {
     const double* buf[PEER_MAX];   // bucket of every rank (peer-mapped)
     uint32_t* sig[PEER_MAX];       // signal pad of every rank: [phase 0/1][block][sender rank] uint32 flags, zero when idle
@@ -21,21 +23,25 @@ struct PeerArgs {
     int rank, world;
 };
 
-// Flag hand-shake (the CAS protocol of PyTorch's symmetric-memory barrier): the sender flips the receiver's slot 0 -> 1, the
-// receiver flips it back 1 -> 0, so the slots are reusable launch after launch (CUDA-graph replay included) without epochs.
-LGAE_DEV bool put_signal(uint32_t* addr) {
-    for (long long spin = 0; spin < (1LL << 28); ++spin) {
-        unsigned old;
-        asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
-        if (old == 0u) return true;
-    }
-    return false;
+// Flag hand-shake.  Slot [phase][block][sender] of the RECEIVER's signal pad: the sender stores 1 (release, system scope), the
+// receiver spins on relaxed loads until it reads 1, stores 0 back and fences (acquire).  A slot is always 0 again before its
+// sender's next store: the sender only gets past the phase-1 hand-shake of a launch after the receiver has consumed (and
+// reset) the phase-0 flag of that launch, and it only reaches the phase-1 store of the next launch after the receiver has
+// entered that launch, i.e. finished the previous one including its phase-1 reset.  So the flags are reusable launch after
+// launch (CUDA-graph replay included) without epochs or compare-and-swap round trips over NVLink.
+LGAE_DEV void put_signal(uint32_t* addr) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(1u) : "memory");
 }
 LGAE_DEV bool wait_signal(uint32_t* addr) {
-    for (long long spin = 0; spin < (1LL << 28); ++spin) {
-        unsigned old;
-        asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
-        if (old == 1u) return true;
+    for (long long spin = 0; spin < (1LL << 30); ++spin) {
+        unsigned v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+        if (v == 1u) {
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(0u) : "memory");
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            return true;
+        }
     }
     return false;
 }
@@ -45,20 +51,19 @@ LGAE_DEV void peer_barrier(const PeerArgs& a, int phase) {
     const int t = threadIdx.x;
     if (t < a.world && t != a.rank) {
         const size_t slot = ((size_t)phase * PEER_BLOCKS + blockIdx.x) * PEER_MAX;
-        bool ok = put_signal(a.sig[t] + slot + a.rank);
-        ok = wait_signal(a.sig[a.rank] + slot + t) && ok;
-        if (!ok) *a.err = 1;
+        put_signal(a.sig[t] + slot + a.rank);
+        if (!wait_signal(a.sig[a.rank] + slot + t)) *a.err = 1;
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const PeerArgs a) {
+__global__ void __launch_bounds__(PEER_PULL_THREADS) peer_allreduce_kernel(const PeerArgs a) {
+    const int nblk = gridDim.x;
     // every rank's bucket is final in its own stream order before this kernel starts there; after the hand-shake it is final on
     // all ranks (the release / acquire pair orders the peers' earlier writes before the reads below)
-    __threadfence_system();
     peer_barrier(a, 0);
     const int64_t n2 = a.n >> 1;
-    for (int64_t i = (int64_t)blockIdx.x * PEER_THREADS + threadIdx.x; i < n2; i += (int64_t)PEER_BLOCKS * PEER_THREADS) {
+    for (int64_t i = (int64_t)blockIdx.x * PEER_PULL_THREADS + threadIdx.x; i < n2; i += (int64_t)nblk * PEER_PULL_THREADS) {
         double2 v[PEER_MAX];
 #pragma unroll
         for (int r = 0; r < PEER_MAX; ++r)
@@ -78,6 +83,23 @@ __global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_kernel(const Peer
     peer_barrier(a, 1);
 }
 
+// The same exchange through the NVSwitch's multicast object (NVLS): rank r owns the r-th slice of the bucket, loads it with
+// multimem.ld_reduce -- the switch adds the slices of all ranks and returns one value -- and stores the sum with multimem.st,
+// which the switch writes into every rank's bucket.  In place; every rank moves n / W doubles each way instead of pulling
+// (W - 1) n.  The reduction order is the switch's (fixed for a topology) and every rank receives the same broadcast bits.
+__global__ void __launch_bounds__(PEER_THREADS) peer_allreduce_mc_kernel(const PeerArgs a, double* mc) {
+    peer_barrier(a, 0);
+    const int64_t per = (a.n + a.world - 1) / a.world;
+    const int64_t lo = per * a.rank, hi = lo + per < a.n ? lo + per : a.n;
+    for (int64_t i = lo + (int64_t)blockIdx.x * PEER_THREADS + threadIdx.x; i < hi; i += (int64_t)gridDim.x * PEER_THREADS) {
+        double v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc + i) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
+    }
+    // every rank's slice has landed everywhere before anyone reads its bucket (or starts the next step's gradient init)
+    peer_barrier(a, 1);
+}
+
 }  // namespace lgae
 
 using namespace lgae;
@@ -87,7 +109,7 @@ extern "C" {
 int64_t lgae_peer_signal_bytes(void) { return (int64_t)2 * PEER_BLOCKS * PEER_MAX * sizeof(uint32_t); }
 
 int lgae_peer_allreduce(const double* const* bufs, uint32_t* const* signals, int32_t rank, int32_t world, int64_t n, double* out,
-                        int32_t* err_flag, void* stream) {
+                        double* multicast, int32_t* err_flag, void* stream) {
     if (!bufs || !signals || !out || !err_flag || world < 1 || world > PEER_MAX || rank < 0 || rank >= world || n < 0) return LGAE_E_BADARG;
     if (n == 0) return LGAE_OK;
     PeerArgs a = {};
@@ -101,7 +123,12 @@ int lgae_peer_allreduce(const double* const* bufs, uint32_t* const* signals, int
     cudaStream_t st = (cudaStream_t)stream;
     LaunchScope ls_("peer_allreduce", st);
     // launched WITHOUT the programmatic-serialisation attribute: the kernel must not start before the bucket is complete
-    peer_allreduce_kernel<<<PEER_BLOCKS, PEER_THREADS, 0, st>>>(a);
+    if (multicast) {
+        if (out != bufs[rank] || ((uintptr_t)multicast & 7)) return LGAE_E_BADARG;   // the multicast path works in place
+        peer_allreduce_mc_kernel<<<PEER_MC_BLOCKS, PEER_THREADS, 0, st>>>(a, multicast);
+    } else {
+        peer_allreduce_kernel<<<PEER_BLOCKS, PEER_PULL_THREADS, 0, st>>>(a);
+    }
     return check_launch("peer_allreduce");
 }
 

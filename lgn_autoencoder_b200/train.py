@@ -68,8 +68,8 @@ class FusedTrainStep:
     """
 
     def __init__(self, encoder, decoder, batch: int, l1_lambda: float = 1e-8, l1_scale: float = 1.0, normalize: bool = True,
-                 use_labels: bool = False, use_graph: bool = True, group=None, get_real: str = "real", overlap_allreduce: bool = True,
-                 peer_allreduce: bool = True):
+                 use_labels: bool = False, use_graph: bool = True, group=None, get_real: str = "real", overlap_allreduce: bool = False,
+                 peer_allreduce: bool = False):
         if not (getattr(encoder, "fused", False) and getattr(decoder, "fused", False)):
             raise NotImplementedError("FusedTrainStep needs the fused (maxdim 2) encoder and decoder")
         self.enc, self.dec, self.B = encoder, decoder, int(batch)
@@ -106,15 +106,18 @@ class FusedTrainStep:
         off_d = (self.pe.n_params + 3) // 4 * 4   # keep the decoder bucket 32-byte aligned
         self.off_d = off_d
         self.g_all = torch.zeros(off_d + self.pd.n_params, **f64)
-        self.g_e = self.g_all[:self.pe.n_params]
-        self.g_d = self.g_all[off_d:]
-        # data parallel: the step's reduce kernels write the local gradient into a bucket that is mapped into every rank of the
-        # node (symmetric memory), and one kernel of the library pulls and adds all ranks' buckets into g_all over NVLink
-        # (lgae_peer_allreduce); NCCL's all-reduce is the fallback (LGAE_PEER_ALLREDUCE=0, or no peer mapping available)
+        # data parallel, opt-in (peer_allreduce=True or LGAE_PEER_ALLREDUCE=1; NCCL's all-reduce is the default, see DESIGN.md
+        # section 5 for the measurements): the step's reduce kernels write the local gradient into a bucket that is mapped into
+        # every rank of the node (symmetric memory) and one kernel of the library exchanges it over NVLink / NVSwitch
+        # (lgae_peer_allreduce: through the switch's multicast object when there is one -- then in place, g_all IS the
+        # symmetric bucket --, else by pulling all peers' buckets into g_all)
         self.g_step = self.g_all
         self._peer = None
-        if peer_allreduce and self._distributed():
+        import os
+        if (peer_allreduce or os.environ.get("LGAE_PEER_ALLREDUCE") == "1") and self._distributed():
             self._setup_peer()
+        self.g_e = self.g_all[:self.pe.n_params]
+        self.g_d = self.g_all[off_d:]
         self.optimizer = None
         self._probe = (next(encoder.parameters()), next(decoder.parameters()))
         self._bind_grads()
@@ -139,7 +142,7 @@ class FusedTrainStep:
         import os
         ok = 0
         state = None
-        if os.environ.get("LGAE_PEER_ALLREDUCE", "1") != "0":
+        if True:
             try:
                 import torch.distributed._symmetric_memory as symm_mem
                 need = int(self.lib.lgae_peer_signal_bytes())
@@ -151,16 +154,23 @@ class FusedTrainStep:
                 world = int(hdl.world_size)
                 bufs = (C.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
                 sigs = (C.c_void_p * world)(*[int(p) for p in hdl.signal_pad_ptrs])
-                state = (g_sym, hdl, bufs, sigs, int(hdl.rank), world, torch.zeros(1, dtype=torch.int32, device=self.dev))
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if os.environ.get("LGAE_PEER_MULTICAST", "1") != "0" else 0
+                state = (g_sym, hdl, bufs, sigs, int(hdl.rank), world, torch.zeros(1, dtype=torch.int32, device=self.dev), mc)
                 ok = 1 if world <= 16 else 0
             except Exception as e:   # noqa: BLE001  (no NVLink peer access, older torch, ...): NCCL carries the exchange
                 import logging
                 logging.warning(f"lgn_autoencoder_b200: peer-memory all-reduce unavailable ({e!r}); using NCCL")
         flag = torch.tensor([ok], dtype=torch.int32, device=self.dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)     # every rank takes the same path
+        has_mc = torch.tensor([1 if (state is not None and state[7]) else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(has_mc, op=dist.ReduceOp.MIN, group=self.group)
         if int(flag.item()) == 1:
+            if not int(has_mc.item()):
+                state = state[:7] + (0,)
             self._peer = state
             self.g_step = state[0]
+            if state[7]:
+                self.g_all = state[0]     # multicast path: the exchange is in place
 
     def peer_error(self) -> bool:
         """True if a hand-shake of the peer all-reduce ever timed out on this rank (results are then invalid)."""
@@ -202,8 +212,8 @@ class FusedTrainStep:
         """After the step's kernels: the data-parallel gradient exchange, then the attached optimizer."""
         if self._peer is not None:
             # one kernel: hand-shake with the peers, pull every rank's bucket over NVLink, add in rank order into g_all
-            g_sym, _, bufs, sigs, rank, world, err = self._peer
-            check(self.lib.lgae_peer_allreduce(bufs, sigs, rank, world, self.g_all.numel(), ptr(self.g_all), ptr(err),
+            g_sym, _, bufs, sigs, rank, world, err, mc = self._peer
+            check(self.lib.lgae_peer_allreduce(bufs, sigs, rank, world, self.g_all.numel(), ptr(self.g_all), mc or None, ptr(err),
                                                torch.cuda.current_stream().cuda_stream), "peer_allreduce")
         elif self._distributed():
             # chamfer is a SUM over jets: all-reduce with SUM, no division by the world size (SURVEY.md section 8(e)); in the
