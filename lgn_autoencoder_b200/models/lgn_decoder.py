@@ -93,7 +93,9 @@ class LGNDecoder(FusedParamsMixin, CGModule):
         lat11 = latent_features[(1, 1)]
         if lat11.device.type != "cuda":
             raise RuntimeError("lgn_autoencoder_b200 runs on CUDA devices only (no CPU fallback)")
-        if self.fused:
+        # the fused adjoint holds one particle per lane (N <= 32): larger jets train through the layer-level composite
+        needs_grad = torch.is_grad_enabled() and (lat11.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if self.fused and not (needs_grad and self.num_output_particles > 32):
             return self._forward_fused(lat11, covariance_test, nodes_all)
         return self._forward_generic(latent_features, covariance_test, nodes_all)
 

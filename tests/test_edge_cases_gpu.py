@@ -101,8 +101,11 @@ def test_empty_batch_is_a_no_op():
     assert torch.count_nonzero(g).item() == 0
 
 
-def test_unsupported_configurations_fail_loudly():
-    """No silent fallback inside the fused path: the adjoint holds one particle per lane."""
+def test_more_than_32_particles():
+    """The fused adjoint holds one particle per lane: the one-call step refuses N > 32 loudly, the raw C entry point returns
+    LGAE_E_UNSUPPORTED before launching anything, and the module API trains such models through the layer-level composite
+    (as the reference can, lgn_encoder.py:255-336 has no particle limit) -- never through a silent CPU path."""
+    from lgn_autoencoder_b200 import fused
     from lgn_autoencoder_b200.train import FusedTrainStep
     dev = torch.device("cuda:0")
     cfg = dict(CASES["min_pool"], n=40)
@@ -110,6 +113,14 @@ def test_unsupported_configurations_fail_loudly():
     with pytest.raises(NotImplementedError):
         FusedTrainStep(enc, dec, 2, get_real="sum")
     p4 = torch.rand((2, 40, 4), dtype=torch.float64, device=dev) + 0.1
-    rec = dec(enc({"p4": p4}))
-    with pytest.raises((NotImplementedError, RuntimeError)):
-        rec.sum().backward()
+    theta, _ = enc._flat_params()
+    lat00, lat11, ws, sel = fused.encoder_forward_raw(enc._plan, theta, p4, None)
+    with pytest.raises(NotImplementedError):
+        fused.encoder_backward_raw(enc._plan, theta, p4, None, ws, sel, None, torch.ones_like(lat11))
+    with torch.no_grad():
+        rec_fused = dec(enc({"p4": p4}))            # forward only: the fused kernels (blocks of 32 particles)
+    rec = dec(enc({"p4": p4}))                      # with autograd: the layer-level composite
+    assert (rec - rec_fused).abs().max().item() <= 1e-10 * rec_fused.abs().max().item()
+    rec.sum().backward()
+    grads = [p.grad for p in list(enc.parameters()) + list(dec.parameters()) if p.grad is not None]
+    assert grads and all(torch.isfinite(g).all() for g in grads) and any(g.abs().max().item() > 0 for g in grads)
