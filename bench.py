@@ -260,6 +260,33 @@ def extra_cfg3_strong(enc, dec, world, rank, dev, timed, W, K):
             "n_gpus": world, "ms_per_step": ms, "value": G / (ms * 1e-3), "unit": "jets/s", "scaling": "strong"}
 
 
+def extra_module_path(enc, dec, host_p4, dev, world, timed, K):
+    """The step as an UNCHANGED caller of the reference's module API gets it (utils/train.py:283-327 through LGNEncoder /
+    LGNDecoder forward + torch autograd, no FusedTrainStep): eager launches, one autograd node per model."""
+    import torch
+    from lgn_autoencoder_b200 import _lib
+    from lgn_autoencoder_b200.train import training_step
+    p4 = host_p4.to(dev)
+    params = [p for m in (enc, dec) for p in m.parameters()]
+
+    def step():
+        for p in params:
+            p.grad = None
+        loss, _, _ = training_step(enc, dec, p4, l1_lambda=CFG["l1_lambda"], l1_scale=1.0 / world, get_real="sum")
+        loss.backward()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    step()
+    torch.cuda.synchronize()
+    lib_launches = _lib.launch_count() - n0
+    ms, _ = timed(step, max(3, min(K, 50)))
+    B = host_p4.shape[0]
+    return {"what": "module API + autograd (what the reference's unchanged utils/train.py loop runs), eager", "ms_per_step": ms,
+            "value": B * world / (ms * 1e-3), "unit": "jets/s", "library_launches": lib_launches}
+
+
 def extra_cfg4(dev, rank, world, timed, K):
     """BASELINE configs[3]: the wide maxdim-3 model (enc 6 6 8 8 / dec 8 8 6 6, 'mix' latent map), training step at bs 1024 per GPU
     through the module API (forward + autograd adjoint on this library's kernels), replayed as one CUDA graph."""
@@ -539,7 +566,7 @@ def main():
     if not args.no_extras:
         fstep.graph = None
         fstep.graph_host = None
-        for name, fn in (("cfg3_global4096", lambda: extra_cfg3_strong(enc, dec, world, rank, dev, timed, W, min(K, 30))),
+        for name, fn in (("module_path", lambda: extra_module_path(enc, dec, host_p4, dev, world, timed, K)), ("cfg3_global4096", lambda: extra_cfg3_strong(enc, dec, world, rank, dev, timed, W, min(K, 30))),
                          ("cfg5", lambda: extra_cfg5(dev, rank, world, timed, K)), ("cfg4", lambda: extra_cfg4(dev, rank, world, timed, K))):
             try:
                 extras[name] = fn()
