@@ -10,6 +10,9 @@ from .. import fused
 class FusedParamsMixin:
     _plan = None
     _theta = None
+    _param_list = None
+    _probes = None
+    _theta_nodes = None
 
     def _build_plan(self, kind, **geometry):
         shapes = OrderedDict((name, tuple(p.shape)) for name, p in self.named_parameters())
@@ -19,29 +22,42 @@ class FusedParamsMixin:
 
     def _flat_params(self):
         """The flat buffer, rebuilt (and the parameters re-pointed into it) whenever a parameter no longer aliases
-        it, e.g. after ``.to(device)``; ``load_state_dict`` and optimizer steps write in place and keep the aliasing."""
-        params = OrderedDict(self.named_parameters())
+        it, e.g. after ``.to(device)``; ``load_state_dict`` and optimizer steps write in place and keep the aliasing.
+        The aliasing of every parameter is verified when the buffer is built; afterwards each call probes the first, a middle
+        and the last parameter (module-wide moves such as ``.to()`` / ``.double()`` re-create all of them)."""
         theta = self._theta
-        ok = theta is not None
-        if ok:
-            base = theta.data_ptr()
-            for name, (off, n, _) in self._plan.offsets.items():
-                p = params[name]
-                if p.data_ptr() != base + 8 * off or p.device != theta.device or not p.is_contiguous():
+        if theta is not None:
+            base, ok = theta.data_ptr(), True
+            for p, off in self._probes:
+                if p.data_ptr() != base + 8 * off or p.device != theta.device:
                     ok = False
                     break
-        if not ok:
-            device = next(iter(params.values())).device
-            theta = self._plan.flatten({k: v.data for k, v in params.items()}, device)
-            for name, view in self._plan.views(theta).items():
-                params[name].data = view
-            self._theta = theta
-        return theta, list(params.values())
+            if ok:
+                return theta, self._param_list
+        params = OrderedDict(self.named_parameters())
+        device = next(iter(params.values())).device
+        theta = self._plan.flatten({k: v.data for k, v in params.items()}, device)
+        for name, view in self._plan.views(theta).items():
+            params[name].data = view
+        self._theta = theta
+        self._param_list = list(params.values())
+        names = list(self._plan.offsets)
+        self._probes = [(params[n], self._plan.offsets[n][0]) for n in (names[0], names[len(names) // 2], names[-1])]
+        self._theta_nodes = {}
+        return theta, self._param_list
 
     def _theta_node(self):
-        """The flat parameter buffer as one autograd tensor (``fused._FlatParamsFn``)."""
+        """The flat parameter buffer as one autograd tensor (``fused._FlatParamsFn``).  One node per flat buffer and grad mode,
+        shared by the model's forward and its L1 / L2 norms: their gradients meet in a single flat add and every ``param.grad``
+        becomes a view of one flat tensor, instead of one accumulation per parameter and use.  (The node saves nothing, so it
+        survives ``backward()``; it is dropped when the buffer is rebuilt.)"""
         theta, params = self._flat_params()
-        return fused._FlatParamsFn.apply(self._plan, theta, *params)
+        key = (torch.is_grad_enabled(), tuple(p.requires_grad for p in params))   # (freezing / unfreezing parameters makes a new node)
+        node = self._theta_nodes.get(key)
+        if node is None:
+            node = fused._FlatParamsFn.apply(self._plan, theta, *params)
+            self._theta_nodes[key] = node
+        return node
 
     def l1_norm(self):
         """sum |p| over all parameters (lgn_encoder.py:249-250), evaluated on the flat buffer in one reduction."""
