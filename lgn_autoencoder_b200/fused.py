@@ -51,6 +51,8 @@ class FusedPlan:
             self.offsets[name] = (off, n, tuple(int(s) for s in shape))
             off += n
         self.n_params = off
+        self._sizes = [n for (_, n, _) in self.offsets.values()]
+        self._shapes = [shp for (_, _, shp) in self.offsets.values()]
         self.n_particles = int(n_particles)
         self.channels = [int(c) for c in channels]
         self.n_levels = len(self.channels) - 1
@@ -215,7 +217,9 @@ class _FlatParamsFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return (None, None) + tuple(ctx.plan.views(g.contiguous()).values())
+        plan = ctx.plan
+        parts = torch.split(g.contiguous(), plan._sizes)     # one call: views of the flat gradient
+        return (None, None) + tuple(p.view(shp) for p, shp in zip(parts, plan._shapes))
 
 
 class _EncoderFn(torch.autograd.Function):
