@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
     for (int l = 0; l <= last; ++l) wtotal += mlp_layer_frag(l, a.n_lin, NTW, NTI);
     double* dz_s = w_s + wtotal;                    // MLP_BWD_ROWS * WS
     double* h_s = dz_s + MLP_BWD_ROWS * WS;         // MLP_BWD_ROWS * WS
-    double* bred = h_s + MLP_BWD_ROWS * WS;         // NWH * WP : per-dW-warp column sums of dZ
+    double* bred = h_s + MLP_BWD_ROWS * WS;         // 2 * NWH * WP : per-row-warp column sums of dZ, double-buffered by layer parity
     pdl_launch();
     pdl_wait();
     {
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
                     for (int n = tid; n < nout_prev; n += 32 * NWH) {
                         double s = 0.0;
 #pragma unroll
-                        for (int w = 0; w < NWH; ++w) s += bred[w * WP + n];
+                        for (int w = 0; w < NWH; ++w) s += bred[((l_prev & 1) * NWH + w) * WP + n];
                         double* dst = part + a.po_b[l_prev] + n;
                         dst[0] = first ? s : dst[0] + s;
                     }
@@ -297,19 +297,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
                 }
                 cta_sync();
                 __syncwarp();
-                // ---- bias gradient: column sums of dZ over this warp's slice of rows (the four slices are added after the
-                //      next barrier) ----
-                {
-                    const int per = (ksteps * 4 + NWH - 1) / NWH;
-                    const int ra = wi * per, rb = ra + per < ksteps * 4 ? ra + per : ksteps * 4;
-                    for (int n = lane; n < 8 * NOt; n += 32) {
-                        double s0 = 0.0, s1 = 0.0;
-                        int r = ra;
-                        for (; r + 1 < rb; r += 2) { s0 += dz_s[r * WS + n]; s1 += dz_s[(r + 1) * WS + n]; }
-                        if (r < rb) s0 += dz_s[r * WS + n];
-                        bred[wi * WP + n] = s0 + s1;
-                    }
-                }
+                // (the bias gradient -- column sums of dZ -- comes from the row warps, which hold dZ in registers: bred[l & 1])
                 // ---- weight gradient dW[n][k] = sum_rows dZ[row][n] H[row][k]: this warp's (<= MB x MB) tile block ----
                 const int MBo = (NOt + 1) / 2, NBo = (KIt + 1) / 2;
                 const int m0 = (wi >> 1) * MBo, n0 = (wi & 1) * NBo;
@@ -360,7 +348,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
             for (int n = tid; n < nout_prev; n += 32 * NWH) {
                 double s = 0.0;
 #pragma unroll
-                for (int w = 0; w < NWH; ++w) s += bred[w * WP + n];
+                for (int w = 0; w < NWH; ++w) s += bred[w * WP + n];   // layer 0: parity 0
                 double* dst = part + a.po_b[0] + n;
                 dst[0] = first ? s : dst[0] + s;
             }
@@ -403,6 +391,25 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
                         for (int nt = 0; nt < NTW; ++nt)
                             if (nt < NOt)
                                 *reinterpret_cast<double2*>(dz_s + (rl + g) * WS + 8 * nt + 2 * q) = make_double2(dz[u][nt][0], dz[u][nt][1]);
+                    }
+                }
+                // ---- bias gradient of layer l: column sums of this warp's rows of dZ_l, straight from the registers (padding rows
+                //      carry zeros): add the warp's row groups, then a butterfly over the 8 rows of the fragment ----
+                {
+                    double* bl = bred + ((l & 1) * NWH + wi) * WP;
+#pragma unroll
+                    for (int nt = 0; nt < NTW; ++nt) {
+                        if (nt < NOt) {
+                            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                            for (int u = 0; u < GMAX; ++u) { c0 += dz[u][nt][0]; c1 += dz[u][nt][1]; }
+#pragma unroll
+                            for (int o = 4; o < 32; o <<= 1) {
+                                c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+                                c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                            }
+                            if (g == 0) *reinterpret_cast<double2*>(bl + 8 * nt + 2 * q) = make_double2(c0, c1);
+                        }
                     }
                 }
                 cta_sync();
@@ -514,7 +521,7 @@ static int launch_mlp(MlpArgs& a, bool bwd, cudaStream_t st) {
         launch_k(kern, dim3(grid), dim3(MLP_THREADS), bytes, st, a);
         return check_launch("mlp_fwd");
     }
-    const size_t bytes = (size_t)(wtotal + 2 * MLP_BWD_ROWS * (8 * NTW + 4) + 4 * 8 * NTW) * sizeof(double);
+    const size_t bytes = (size_t)(wtotal + 2 * MLP_BWD_ROWS * (8 * NTW + 4) + 2 * 4 * 8 * NTW) * sizeof(double);
     if (bytes > 227 * 1024) return LGAE_E_UNSUPPORTED;
     auto kern = mlp_bwd_kernel<NTW, NTI>;
     if (int rc = ensure_smem((const void*)kern, bytes)) return rc;
