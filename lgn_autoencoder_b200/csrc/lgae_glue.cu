@@ -1060,11 +1060,12 @@ __global__ void __launch_bounds__(256) grad_init2_kernel(const double* theta_a, 
 
 // gtheta[seg] += sum over the rows of the segment's block.  blockIdx.y = segment, blockDim = (32 columns, 8 row groups);
 // fixed summation order => deterministic gradients.  The extra y-block (blockIdx.y == t.n) adds the L1 term to the loss.
-__global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, const double* partials, double* gtheta, const double* psum,
+constexpr int RED_Y = 16;   // row lanes per 32-column chunk: a 512-row block of partials is 8 dependent rounds of 4 loads per thread
+__global__ void __launch_bounds__(32 * RED_Y) reduce_segs_kernel(const SegTable t, const double* partials, double* gtheta, const double* psum,
                                                           int npsum, double lambda, double* loss) {
     pdl_launch();
     pdl_wait();
-    __shared__ double sm[8][33];
+    __shared__ double sm[RED_Y][33];
     // blockIdx.x enumerates the 32-column chunks of all segments back to back (t.chunk0[s] = first chunk of segment s); the
     // block after the last chunk adds the L1 term to the loss
     if ((int)blockIdx.x == t.chunk0[t.n]) {
@@ -1086,13 +1087,13 @@ __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, cons
             const double* src = partials + sg.part_off + x;
             int r = threadIdx.y;
             double a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (; r + 24 < sg.rows; r += 32) {   // four independent loads in flight
+            for (; r + 3 * RED_Y < sg.rows; r += 4 * RED_Y) {   // four independent loads in flight
                 acc += src[(int64_t)r * sg.stride];
-                a1 += src[(int64_t)(r + 8) * sg.stride];
-                a2 += src[(int64_t)(r + 16) * sg.stride];
-                a3 += src[(int64_t)(r + 24) * sg.stride];
+                a1 += src[(int64_t)(r + RED_Y) * sg.stride];
+                a2 += src[(int64_t)(r + 2 * RED_Y) * sg.stride];
+                a3 += src[(int64_t)(r + 3 * RED_Y) * sg.stride];
             }
-            for (; r < sg.rows; r += 8) acc += src[(int64_t)r * sg.stride];
+            for (; r < sg.rows; r += RED_Y) acc += src[(int64_t)r * sg.stride];
             acc = (acc + a1) + (a2 + a3);
         }
         sm[threadIdx.y][threadIdx.x] = acc;
@@ -1100,7 +1101,7 @@ __global__ void __launch_bounds__(256) reduce_segs_kernel(const SegTable t, cons
         if (threadIdx.y == 0 && x < sg.len) {
             double v = 0.0;
 #pragma unroll
-            for (int y = 0; y < 8; ++y) v += sm[y][threadIdx.x];
+            for (int y = 0; y < RED_Y; ++y) v += sm[y][threadIdx.x];
             gtheta[sg.theta_off + x] += v;
         }
     }
@@ -1301,7 +1302,7 @@ int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const doub
     }
     plan->table.chunk0[plan->table.n] = chunks;
     LaunchScope ls_("reduce_partials", st);
-    launch_k(reduce_segs_kernel, dim3(chunks + 1), dim3(32, 8), 0, st, plan->table, plan->base, gtheta, psum, nb, lambda, l1 ? loss : nullptr);
+    launch_k(reduce_segs_kernel, dim3(chunks + 1), dim3(32, RED_Y), 0, st, plan->table, plan->base, gtheta, psum, nb, lambda, l1 ? loss : nullptr);
     return check_launch("reduce_partials");
 }
 int reduce_scratch_doubles() { return L1_BLOCKS_MAX; }
@@ -1330,7 +1331,7 @@ int run_reduce_segs(PartPlan* plan, int64_t n_params, double* gtheta, const doub
     }
     plan->table.chunk0[plan->table.n] = chunks;
     LaunchScope ls_("reduce_partials", st);
-    launch_k(reduce_segs_kernel, dim3(chunks + 1), dim3(32, 8), 0, st, plan->table, plan->base, gtheta, psum, nblk, lambda, l1 ? loss : nullptr);
+    launch_k(reduce_segs_kernel, dim3(chunks + 1), dim3(32, RED_Y), 0, st, plan->table, plan->base, gtheta, psum, nblk, lambda, l1 ? loss : nullptr);
     return check_launch("reduce_partials");
 }
 int run_reduce_plan2(PartPlan* plan, const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta,
