@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(MLP_THREADS, LGAE_MLP_FWD_CTAS) mlp_fwd_kernel
             wtotal += mlp_layer_frag(l, a.n_lin, NTW, NTI);
             for (int t = tid; t < WP; t += blockDim.x) bias_s[l * WP + t] = t < nout ? a.theta[a.off_b[l] + t] : 0.0;
         }
-        pdl_wait();   // the packed weights and the rows come from earlier kernels of the step
-        // one TMA bulk copy brings all layers' fragments (<= 98 KB) into shared memory
+        // one TMA bulk copy brings all layers' fragments (<= 98 KB) into shared memory.  It is issued BEFORE the dependency
+        // wait: the packed weights are written by mlp_pack_kernel, which never releases its dependents early, so they are
+        // complete before any later kernel of the stream can start -- the copy overlaps the predecessor's tail
         __shared__ uint64_t mbar;
         if (tid == 0) mbar_init(&mbar, 1);
         __syncthreads();
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(MLP_THREADS, LGAE_MLP_FWD_CTAS) mlp_fwd_kernel
             mbar_expect_tx(&mbar, (unsigned)(wtotal * sizeof(double)));
             bulk_g2s(w_s, a.wpack, (unsigned)(wtotal * sizeof(double)), &mbar);
         }
+        pdl_wait();   // the rows come from the previous kernel of the step
         mbar_wait(&mbar, 0);
     }
     __syncthreads();
@@ -232,8 +234,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
     double* h_s = dz_s + MLP_BWD_ROWS * WS;         // MLP_BWD_ROWS * WS
     double* bred = h_s + MLP_BWD_ROWS * WS;         // 2 * NWH * WP : per-row-warp column sums of dZ, double-buffered by layer parity
     pdl_launch();
-    pdl_wait();
     {
+        // (weights staged before the dependency wait: see mlp_fwd_kernel)
         __shared__ uint64_t mbar;
         if (tid == 0) mbar_init(&mbar, 1);
         __syncthreads();
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_bwd_kernel(const MlpArgs a
             mbar_expect_tx(&mbar, (unsigned)(wtotal * sizeof(double)));
             bulk_g2s(w_s, a.wpack + wtotal, (unsigned)(wtotal * sizeof(double)), &mbar);
         }
+        pdl_wait();
         mbar_wait(&mbar, 0);
     }
     double* part = a.part + (int64_t)blockIdx.x * a.part_stride;
@@ -478,7 +481,8 @@ struct MlpPackArgs {
     int64_t off_w[PACK_SLOTS][LGAE_MAX_LINEAR];
 };
 __global__ void __launch_bounds__(256) mlp_pack_kernel(const MlpPackArgs p) {
-    pdl_launch();
+    // no early launch_dependents: the MLP kernels stage the packed weights in their prologues, before their own dependency
+    // wait, so nothing later in the stream may start before this kernel has completed
     pdl_wait();   // (writes the packed weights that earlier kernels of a previous pass may still be reading)
     const int l = blockIdx.x, dir = blockIdx.y, lev = blockIdx.z;
     const int n_lin = p.n_lin[lev];

@@ -309,3 +309,52 @@ def test_anomaly_scores_match_reference_and_oracle():
             # measured against the Euclidean counterpart's scale
             scale = ref[name.replace("lorentz", "cartesian")].abs().max().item()
             assert (got[name].cpu() - ref[name]).abs().max().item() < 1e-10 * scale, (name, unnorm)
+
+
+def test_peer_allreduce_single_rank_and_split_step():
+    """lgae_peer_allreduce with world = 1 (the hand-shakes have no peer, the pull is the identity; the multi-rank behaviour is
+    checked by tools/dp_check.py under torchrun) and the two-phase form of lgae_train_step (decoder bucket final after phase 1,
+    the rest in phase 2 with the auxiliary stream joined back) against the single call."""
+    import ctypes as C
+    from lgn_autoencoder_b200 import _lib
+    from lgn_autoencoder_b200._lib import check, ptr
+    from lgn_autoencoder_b200.train import FusedTrainStep
+    lib = _lib.load()
+    dev = torch.device("cuda:0")
+    n = 1001
+    buf = torch.randn(n + 1, dtype=torch.float64, device=dev)[:n]          # odd length, 16-byte aligned start
+    out = torch.empty(n + 1, dtype=torch.float64, device=dev)[:n]
+    sig = torch.zeros(int(lib.lgae_peer_signal_bytes()) // 4, dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    bufs, sigs = (C.c_void_p * 1)(buf.data_ptr()), (C.c_void_p * 1)(sig.data_ptr())
+    st = torch.cuda.current_stream().cuda_stream
+    check(lib.lgae_peer_allreduce(bufs, sigs, 0, 1, n, ptr(out), None, ptr(err), st), "peer_allreduce")
+    torch.cuda.synchronize()
+    assert torch.equal(out, buf) and int(err.item()) == 0 and int(sig.abs().sum().item()) == 0
+    assert lib.lgae_peer_allreduce(bufs, sigs, 1, 1, n, ptr(out), None, ptr(err), st) == -1      # rank out of range
+    # split step == single call
+    g, enc, dec, batch = load("cfg1_b3", dev)
+    step = FusedTrainStep(enc, dec, batch["p4"].shape[0], l1_lambda=1e-8, normalize=False, use_graph=False, get_real="sum")
+    l0 = step.step(batch["p4"]).item()
+    g0 = step.g_all.clone()
+    step.g_all.zero_()
+    if lib.lgae_aux_stream():
+        pe, pd = step.pe, step.pd
+        th_e, _ = enc._flat_params()
+        th_d, _ = dec._flat_params()
+        for phase in (1, 2):
+            check(lib.lgae_train_step(C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(step.p4_in), ptr(step.mask), step.B, 0,
+                                      ptr(step.p4), ptr(step.norm_factor), ptr(step.ws_e), ptr(step.ws_d), ptr(step.latent00), ptr(step.latent11),
+                                      ptr(step.sel), ptr(step.recon), ptr(step.g_recon), ptr(step.g_lat11), ptr(step.jet_loss), ptr(step.loss),
+                                      ptr(step.g_all), step.off_d, ptr(step.part), step.l1, step.get_real, phase, st), "train_step phase")
+            if phase == 1:   # the decoder's bucket is final on the auxiliary stream
+                aux = torch.cuda.ExternalStream(int(lib.lgae_aux_stream()), device=dev)
+                aux.synchronize()
+                assert torch.equal(step.g_d, g0[step.off_d:])
+        torch.cuda.synchronize()
+        assert step.loss.item() == l0 and torch.equal(step.g_all, g0)
+        # phase 2 without phase 1 is refused
+        assert lib.lgae_train_step(C.byref(pe.desc), C.byref(pd.desc), ptr(th_e), ptr(th_d), ptr(step.p4_in), ptr(step.mask), step.B, 0,
+                                   ptr(step.p4), ptr(step.norm_factor), ptr(step.ws_e), ptr(step.ws_d), ptr(step.latent00), ptr(step.latent11),
+                                   ptr(step.sel), ptr(step.recon), ptr(step.g_recon), ptr(step.g_lat11), ptr(step.jet_loss), ptr(step.loss),
+                                   ptr(step.g_all), step.off_d, ptr(step.part), step.l1, step.get_real, 2, st) == -1
