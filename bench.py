@@ -470,7 +470,7 @@ def main():
         # algorithmic flops per step of each kernel family (reference-faithful counts; adjoint = 2 x forward;
         # the last level's MLP is dead in the backward pass)
         fam = {k: 0.0 for k in ("level_fwd", "level_bwd", "radial_fwd", "radial_bwd", "mlp_fwd", "mlp_bwd")}
-        executed = {"mlp_fwd": 0.0, "mlp_bwd": 0.0}
+        executed = {"mlp_fwd": 0.0, "mlp_bwd": 0.0, "level_fwd": 0.0, "level_bwd": 0.0}
         # which fp64 pipe bounds each family, and its busy fraction from this round's `ncu --set full` captures (profiles/)
         pipe = {"level_fwd": "fp64 DFMA", "level_bwd": "fp64 DFMA", "radial_fwd": "fp64 DMMA", "radial_bwd": "fp64 DMMA", "mlp_fwd": "fp64 DMMA",
                 "mlp_bwd": "fp64 DMMA"}
@@ -500,6 +500,19 @@ def main():
                     executed["mlp_fwd"] += B * ex
                 if l < len(chs) - 2:
                     executed["mlp_bwd"] += 2 * B * ex
+                # flops the level kernels issue (counted from the kernels' inner loops, csrc/lgae_level.cu): the encoder's
+                # neighbour loop is 52 DFMA per (i, j, channel) forward and 96 in the adjoint (the structured Y and the shared
+                # R_ij = R_ji save ~40 % of the reference's count); the decoder runs the O(N) closed form (~300 / ~700 DFMA per
+                # (particle, channel)); the channel mix and its adjoint are executed as counted.  The decoder launches are the
+                # ones whose reference-faithful credit (O(N^2)) exceeds what they execute.
+                c_in = chs[l]
+                mix_ex = f["mix"]
+                if enc_side:
+                    executed["level_fwd"] += B * (N * N * c_in * 2 * 52 + mix_ex + f["power"])
+                    executed["level_bwd"] += B * (N * N * c_in * 2 * 96 + 3 * mix_ex + 2 * f["power"])
+                else:
+                    executed["level_fwd"] += B * (N * c_in * 2 * 300 + mix_ex + f["power"])
+                    executed["level_bwd"] += B * (N * c_in * 2 * 700 + 3 * mix_ex + 2 * f["power"])
         total_ms = sum(n * ms for n, ms in kern.values()) / 5.0
         table = {}
         for name, (n, ms) in sorted(kern.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
