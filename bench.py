@@ -181,6 +181,36 @@ def reference_rate(sample_batch, steps, warmup, device="cpu", threads=None):
     return sample_batch / sec, sec, lv, peak
 
 
+def reference_noise_floor(n_jets=64):
+    """Max-norm relative difference between the unmodified reference on the CPU and on CUDA (stock ATen kernels) for the same
+    weights and jets: reconstruction, loss and gradients.  This is the floor any 'matches the reference' tolerance sits on for
+    near-massless jets."""
+    import torch
+    from utils.losses.chamfer_loss.chamfer_loss import ChamferLoss
+    from utils.normalize_p4 import normalize_p4
+    from utils.utils import get_real
+    cpu_models = reference_models(torch.device("cpu"))
+    p4 = synthetic_jets(n_jets, CFG["n"], seed=100)
+    out = {}
+    for dev in ("cpu", "cuda"):
+        d = torch.device(dev)
+        e, dd = cpu_models if dev == "cpu" else reference_models(d)
+        if dev == "cuda":   # same weights: the generator streams differ between devices
+            with torch.no_grad():
+                for src, dst in zip(cpu_models, (e, dd)):
+                    for ps, pd in zip(src.parameters(), dst.parameters(), strict=True):
+                        pd.copy_(ps)
+        pn, _ = normalize_p4(p4.clone(), "overall_max")
+        recon = dd(e({"p4": pn}, covariance_test=False), covariance_test=False)
+        loss = ChamferLoss(device=d)(get_real(recon, "sum"), pn.to(d)) + CFG["l1_lambda"] * (e.l1_norm() + dd.l1_norm())
+        loss.backward()
+        out[dev] = (recon.detach().cpu(), loss.item(), [p.grad.detach().cpu() for m in (e, dd) for p in m.parameters() if p.grad is not None])
+    rc, rg = out["cpu"], out["cuda"]
+    gmax = max(g.abs().max().item() for g in rc[2])
+    return {"jets": n_jets, "recon_rel": ((rc[0] - rg[0]).abs().max() / rc[0].abs().max()).item(), "loss_rel": abs(rc[1] - rg[1]) / abs(rc[1]),
+            "grads_rel_to_model_max": max((a - b).abs().max().item() for a, b in zip(rc[2], rg[2])) / gmax}
+
+
 def run_reference(args):
     """The reference arm: the reference's own implementation of the path on the box's host cores (all threads), one bounded
     step = the full per-GPU batch of the workload.  kind = "reference" (the unmodified code from baseline/_ref) when that copy is
@@ -216,8 +246,13 @@ def run_reference(args):
         probe_rate = run(min(64, args.batch), 1, 1)[0]
         sample = int(max(16, min(args.batch, (150.0 * probe_rate / (steps + warmup)) // 16 * 16)))
     rate, sec, _ = run(sample, steps, warmup)
+    noise = None
     if args.ref_device != "cpu":
         peak = torch.cuda.max_memory_allocated() / 2 ** 30
+        try:
+            noise = reference_noise_floor()
+        except Exception as e:   # noqa: BLE001  (informative only)
+            noise = {"error": repr(e)[:200]}
     on_cpu = args.ref_device == "cpu"
     line = {"impl": "reference", "metric": "jets/sec LGAE fwd+bwd (30p, maxdim 2)", "value": rate, "unit": "jets/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -227,6 +262,8 @@ def run_reference(args):
                                        + (f", {cores} threads" if on_cpu else f", peak {peak:.1f} GiB")},
             "e2e": {"value": rate, "unit": "jets/s", "h2d_bytes_per_step": 0 if on_cpu else sample * CFG["n"] * 32, "d2h_bytes_per_step": 0 if on_cpu else 8},
             "gpu_launches": 0, "device": args.ref_device}
+    if noise is not None:
+        line["cpu_vs_cuda_noise_floor"] = noise
     print(json.dumps(line))
 
 
@@ -572,7 +609,8 @@ def main():
                    "note": r.get("unavailable")}
         # ---- the unmodified reference on this GPU (stock ATen fp64 kernels): what a user of the reference gets today ----
         r = reference_subprocess(["--batch", str(B), "--steps", "3", "--warmup", "1", "--ref-device", "cuda"])
-        ref_cuda = {"value": r["value"], "unit": "jets/s", "ms_per_step": r["ms_per_step"], "sample": r["cpu_baseline"]["sample"]} if "value" in r else r
+        ref_cuda = {"value": r["value"], "unit": "jets/s", "ms_per_step": r["ms_per_step"], "sample": r["cpu_baseline"]["sample"],
+                    "cpu_vs_cuda_noise_floor": r.get("cpu_vs_cuda_noise_floor")} if "value" in r else r
 
     # ---- the other configurations of BASELINE.json, as extra objects of the same line (every rank runs them) ----
     extras = {}

@@ -67,7 +67,14 @@ struct LevelArgs {
 #ifndef LGAE_LBWD_MINB
 #define LGAE_LBWD_MINB 3   // resident CTAs per SM the level adjoint is compiled for (register cap 168; 4 => 128 registers spills and is slower)
 #endif
+#ifndef LGAE_FWD_RING
+#define LGAE_FWD_RING 1   // forward (PRE): radial weights arrive through a shared-memory ring of TMA bulk copies instead of per-thread loads
+#endif
+#ifndef LGAE_RING_PS
+#define LGAE_RING_PS 3    // partners per ring stage
+#endif
 constexpr int kBwdUnroll = LGAE_BWD_UNROLL, kFwdUnroll = LGAE_FWD_UNROLL;
+constexpr int kRingPS = LGAE_RING_PS, kRingMaxStages = 4;
 constexpr int TJ = 8;  // neighbours per shared-memory tile of radial weights
 constexpr int CAT_E = 21;  // entries per (channel, particle) of the concatenation staged for the channel mix
 
@@ -203,7 +210,23 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
     // ---- stage the jet: momenta and node features by TMA bulk copies, weights by the threads meanwhile ----
     pdl_launch();
     __shared__ uint64_t mbar;
-    if (tid == 0) mbar_init(&mbar, 1);
+    __shared__ uint64_t rbar[kRingMaxStages];
+    // PRE: the radial weights of this jet, (N_j, C, 32, 4) = pd doubles per partner, stream through a ring of `nst` stages of
+    // kRingPS partners in the (still dead) cat buffer: one TMA bulk copy per stage, issued nst stages ahead of their use
+    const int pd = C * 128;
+    const int nst = (ENC && PRE && LGAE_FWD_RING) ? min((2 * CAT_E * C * NS) / pd / kRingPS, kRingMaxStages) : 0;
+    const bool ring = nst >= 2;
+    const int ngr = (N + kRingPS - 1) / kRingPS;
+    auto ring_issue = [&](int g) {   // one thread
+        const int s = g % nst, j0 = g * kRingPS, tj = min(kRingPS, N - j0);
+        const unsigned bytes = (unsigned)(tj * pd * sizeof(double));
+        mbar_expect_tx(&rbar[s], bytes);
+        bulk_g2s(Rs + (size_t)s * kRingPS * pd, a.r_save + ((int64_t)b * N + j0) * pd, bytes, &rbar[s]);
+    };
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        for (int s = 0; s < kRingMaxStages; ++s) mbar_init(&rbar[s], 1);
+    }
     pdl_wait();   // everything below reads what earlier kernels of the step produced
     __syncthreads();
     {
@@ -214,6 +237,8 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
             bulk_g2s(p_s, src, np * sizeof(double), &mbar);
             bulk_g2s(smem + L.S, a.s_in + (int64_t)b * N * C * 2, 2 * N * C * sizeof(double), &mbar);
             bulk_g2s(smem + L.V, a.v_in + (int64_t)b * N * C * 8, 8 * N * C * sizeof(double), &mbar);
+            if (ring)
+                for (int g = 0; g < nst && g < ngr; ++g) ring_issue(g);
         }
         if (ENC && !PRE)
             for (int t = tid; t < N; t += blockDim.x)
@@ -291,6 +316,62 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
             A1Y[mu] = cmul(R1c, csub(cmul(yi[mu], SS), SSY[mu]));
         }
     } else {
+    // one neighbour j with its radial weights: the four neighbour sums of this (particle, channel)
+    auto pair = [&](int j, cplx R0, cplx R1) {
+        const cplx Sj = S_s[j * C + c];
+        cplx Vj[4];
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) Vj[mu] = V_s[(j * C + c) * 4 + mu];
+        cplx Y[4];
+        if (ENC) {
+            double d[4];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) d[mu] = pi[mu] - p_s[4 * j + mu];
+            canon_from_real(d, Y);
+        } else {
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) Y[mu] = csub(yi[mu], reinterpret_cast<const cplx*>(p_s)[4 * j + mu]);
+        }
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) cfma(A0V[mu], R0, Vj[mu]);
+        cfma(A0S, R0, Sj);
+        const cplx t = cmul(R1, Sj);
+        cplx e;
+        if (ENC) {
+            // Y0, Y2 are real, Y3 = -conj... structured: saves a third of the multiplies
+            cfmar(A1Y[0], t, Y[0].x);
+            cfma(A1Y[1], t, Y[1]);
+            cfmar(A1Y[2], t, Y[2].x);
+            cfma(A1Y[3], t, Y[3]);
+            e = cscale(Vj[0], Y[0].x);
+            cfma(e, Vj[1], Y[3]);
+            cfmar(e, Vj[2], -Y[2].x);
+            cfma(e, Vj[3], Y[1]);
+        } else {
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) cfma(A1Y[mu], t, Y[mu]);
+            e = ceta(Vj, Y);
+        }
+        cfma(A1E, R1, e);
+    };
+    if (ring) {
+        for (int g = 0; g < ngr; ++g) {
+            const int s = g % nst, j0 = g * kRingPS, tj = min(kRingPS, N - j0);
+            mbar_wait(&rbar[s], (unsigned)((g / nst) & 1));
+            const double* rs = Rs + (size_t)s * kRingPS * pd + (c * 32 + lane) * 4;
+#pragma unroll
+            for (int jj = 0; jj < kRingPS; ++jj) {
+                if (jj < tj) {
+                    const double4 r = *reinterpret_cast<const double4*>(rs + (size_t)jj * pd);
+                    pair(j0 + jj, cmake(r.x, r.y), cmake(r.z, r.w));
+                }
+            }
+            if (g + nst < ngr) {   // every warp is done with stage s: refill it
+                __syncthreads();
+                if (tid == 0) ring_issue(g + nst);
+            }
+        }
+    } else {
     const double4* rsv = reinterpret_cast<const double4*>(a.r_save) + ((int64_t)b * N * C + c) * 32 + lane;
     constexpr int PDF = LGAE_RPD_FWD;
     double4 rq[PDF];
@@ -320,43 +401,10 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
                 R0 = cmake(r.x, r.y);
                 R1 = cmake(r.z, r.w);
             }
-            const cplx Sj = S_s[j * C + c];
-            cplx Vj[4];
-#pragma unroll
-            for (int mu = 0; mu < 4; ++mu) Vj[mu] = V_s[(j * C + c) * 4 + mu];
-            cplx Y[4];
-            if (ENC) {
-                double d[4];
-#pragma unroll
-                for (int mu = 0; mu < 4; ++mu) d[mu] = pi[mu] - p_s[4 * j + mu];
-                canon_from_real(d, Y);
-            } else {
-#pragma unroll
-                for (int mu = 0; mu < 4; ++mu) Y[mu] = csub(yi[mu], reinterpret_cast<const cplx*>(p_s)[4 * j + mu]);
-            }
-#pragma unroll
-            for (int mu = 0; mu < 4; ++mu) cfma(A0V[mu], R0, Vj[mu]);
-            cfma(A0S, R0, Sj);
-            const cplx t = cmul(R1, Sj);
-            cplx e;
-            if (ENC) {
-                // Y0, Y2 are real, Y3 = -conj... structured: saves a third of the multiplies
-                cfmar(A1Y[0], t, Y[0].x);
-                cfma(A1Y[1], t, Y[1]);
-                cfmar(A1Y[2], t, Y[2].x);
-                cfma(A1Y[3], t, Y[3]);
-                e = cscale(Vj[0], Y[0].x);
-                cfma(e, Vj[1], Y[3]);
-                cfmar(e, Vj[2], -Y[2].x);
-                cfma(e, Vj[3], Y[1]);
-            } else {
-#pragma unroll
-                for (int mu = 0; mu < 4; ++mu) cfma(A1Y[mu], t, Y[mu]);
-                e = ceta(Vj, Y);
-            }
-            cfma(A1E, R1, e);
+            pair(j, R0, R1);
         }
         if (ENC && !PRE) __syncthreads();
+    }
     }
     }
 
