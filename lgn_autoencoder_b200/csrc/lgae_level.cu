@@ -62,7 +62,7 @@ struct LevelArgs {
 #define LGAE_LBWD_MINB_C4 3   // same, launches with 4 channels (128 threads): 3 CTAs/SM = 444 slots < 512 jets, 4 => one wave but 128 registers
 #endif
 #ifndef LGAE_LBWD_CF_MINB_C4
-#define LGAE_LBWD_CF_MINB_C4 3
+#define LGAE_LBWD_CF_MINB_C4 3   // 4 = 128 registers (228 B of spills), one wave for 512 jets: 40.3 vs 40.5 us alone, but the step is 6 us slower
 #endif
 #ifndef LGAE_LBWD_MINB
 #define LGAE_LBWD_MINB 3   // resident CTAs per SM the level adjoint is compiled for (register cap 168; 4 => 128 registers spills and is slower)
@@ -484,10 +484,14 @@ __host__ __device__ inline LevelBwdSmem level_bwd_smem(bool enc, int N, int C, i
     s.m11 = o; o += 2 * Cout * 5 * C;
     s.gm = o; o += 2 * 2 * Cout * 5 * C;     // [irrep][c'][k] complex accumulators, live for the whole CTA
     s.gA = o; o += 2 * C * 10 * 32;          // [(c*10+e)][32] complex: adjoints of the neighbour sums
-    s.gy = o; o += enc ? 0 : 2 * 4 * 32 * C;   // decoder: per-channel dL/dy, summed over channels in a fixed order
     o = (o + 3) & ~3;
     s.gout = o; o += 2 * Cout * 5 * 32;      // incoming gradients [(c'*5+comp)][32] complex
     s.graw = o; o += 2 * N * Cout * 5;       // the same as they lie in HBM: g_s_pre (N,C') | g_v_out (N,C',4), bulk-copied
+    // decoder: per-channel dL/dy, summed over channels in a fixed order; written after the neighbour loop, when the two gradient
+    // buffers are dead, so it lies on top of them
+    s.gy = s.gout;
+    const int gy = enc ? 0 : 2 * 4 * 32 * C;
+    if (o - s.gout < gy) o = s.gout + gy;
     s.total = o;
     return s;
 }
