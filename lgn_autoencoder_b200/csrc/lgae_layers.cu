@@ -305,6 +305,190 @@ __global__ void __launch_bounds__(256) lin_bwd_w_kernel(const LinArgs a) {
               [&](int64_t k, int n) { return n < a.nin ? a.x[k * a.nin + n] : 1.0; },
               [&](int64_t m, int n, double v) { part[m * (a.nin + 1) + n] = v; });
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Linear on the fp64 tensor-core MMA (DMMA m8n8k4) for layer widths <= 128 (the scalar MLPs of the generic path are
+// (B N) x w x w GEMMs with w <= 96): the small operand lives in shared memory in fragment order, the row operand is
+// streamed from global memory with a register prefetch, the accumulators never leave registers.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int LMMA_MAX = 128;      // largest n_in / n_out of this path
+constexpr int LMMA_THREADS = 256;
+constexpr int LMMA_MT = 2;         // row groups (of 8 rows) a warp advances together
+constexpr int LMMA_KC = 4;         // k-steps per prefetch chunk
+
+// y = act(x W^T + b)  (BWDX = false: K = n_in, N = n_out)     gx = dZ W  (BWDX = true: K = n_out, N = n_in)
+template <int NT, bool BWDX>
+__global__ void __launch_bounds__(LMMA_THREADS, 1) lin_mma_kernel(const LinArgs a) {
+    extern __shared__ __align__(16) double lin_smem[];
+    double* Bs = lin_smem;   // Bs[(ks*NT + nt)*32 + lane] = B[4ks + q][8nt + g]
+    const int K = BWDX ? a.nout : a.nin, N = BWDX ? a.nin : a.nout;
+    const int KS = (K + 3) / 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    constexpr int MT = LMMA_MT, KC = LMMA_KC;
+    pdl_launch();
+    pdl_wait();
+    // coalesced read of W (n_out x n_in, row-major), scattered into fragment order; padding entries are zero
+    for (int t = threadIdx.x; t < KS * NT * 32; t += blockDim.x) Bs[t] = 0.0;
+    __syncthreads();
+    {
+        const int total = a.nout * a.nin;
+#pragma unroll 4
+        for (int t = threadIdx.x; t < total; t += blockDim.x) {
+            const int o = t / a.nin, i = t - o * a.nin;
+            const int k = BWDX ? o : i, n = BWDX ? i : o;
+            Bs[(((k >> 2) * NT + (n >> 3)) * 32) + ((n & 7) << 2) + (k & 3)] = a.w[t];
+        }
+    }
+    __syncthreads();
+    const bool pair_store = (N & 1) == 0;
+    const int64_t units = (a.rows + 8 * MT - 1) / (8 * MT);
+    for (int64_t u = (int64_t)blockIdx.x * (LMMA_THREADS / 32) + warp; u < units; u += (int64_t)gridDim.x * (LMMA_THREADS / 32)) {
+        const int64_t r0 = u * 8 * MT;
+        double acc[MT][NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int col = 8 * nt + 2 * q;
+            const double b0 = (!BWDX && a.b && col < N) ? a.b[col] : 0.0, b1 = (!BWDX && a.b && col + 1 < N) ? a.b[col + 1] : 0.0;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) { acc[mt][nt][0] = b0; acc[mt][nt][1] = b1; }
+        }
+        // raw operands only (no arithmetic on them here, so that the prefetch really stays in flight); BWDX: A = dZ = gy * act'(y)
+        auto load_a = [&](int mt, int ks, double& v, double& yv) {
+            const int64_t row = r0 + 8 * mt + g;
+            const int k = 4 * ks + q;
+            v = 0.0;
+            yv = 1.0;
+            if (row < a.rows && k < K) {
+                const int64_t idx = row * K + k;
+                v = BWDX ? a.gy[idx] : a.x[idx];
+                if (BWDX && a.act) yv = a.y[idx];
+            }
+        };
+        double cur[MT][KC], nxt[MT][KC], cy[MT][KC], ny[MT][KC];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) { load_a(mt, kc, cur[mt][kc], cy[mt][kc]); nxt[mt][kc] = 0.0; ny[mt][kc] = 1.0; }
+        for (int ks0 = 0; ks0 < KS; ks0 += KC) {
+            if (ks0 + KC < KS) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int kc = 0; kc < KC; ++kc) load_a(mt, ks0 + KC + kc, nxt[mt][kc], ny[mt][kc]);
+            }
+#pragma unroll
+            for (int kc = 0; kc < KC; ++kc) {
+                const int ks = ks0 + kc;
+                if (ks < KS) {
+                    double av[MT];
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) av[mt] = (BWDX && !(cy[mt][kc] > 0.0)) ? cur[mt][kc] * a.slope : cur[mt][kc];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const double bv = Bs[(ks * NT + nt) * 32 + lane];
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) dmma(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv);
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc) { cur[mt][kc] = nxt[mt][kc]; cy[mt][kc] = ny[mt][kc]; }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int64_t row = r0 + 8 * mt + g;
+            if (row >= a.rows) continue;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = 8 * nt + 2 * q;
+                if (col >= N) continue;
+                double v0 = acc[mt][nt][0], v1 = acc[mt][nt][1];
+                if (!BWDX && a.act) { v0 = leaky(v0, a.slope); v1 = leaky(v1, a.slope); }
+                double* dst = a.out + row * N + col;
+                if (pair_store) {
+                    *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                } else {
+                    dst[0] = v0;
+                    if (col + 1 < N) dst[1] = v1;
+                }
+            }
+        }
+    }
+}
+
+// partial[z][o][i] = sum_{r in split z} dZ[r, o] x[r, i]  (column i == nin: the bias gradient) as an MMA contraction over
+// the rows of the split: A[o][r] = dZ[r][o], B[r][i] = x[r][i].  Warp (wm, wn) owns the output tiles (mt = wm + 4 i, nt = wn + 2 j)
+// -- strided, so that the four schedulers of the SM carry the same number of tiles -- and fetches its operand fragments
+// (L1-resident rows shared by the 8 warps) one k-step ahead.
+constexpr int LW_TM = 4, LW_TN = 8;
+__global__ void __launch_bounds__(LMMA_THREADS, 1) lin_bwd_w_mma_kernel(const LinArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int MTt = (a.nout + 7) / 8, NTt = (a.nin + 1 + 7) / 8;
+    pdl_launch();
+    pdl_wait();
+    const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_split, r1 = min(a.rows, r0 + a.rows_per_split);
+    double acc[LW_TM][LW_TN][2];
+#pragma unroll
+    for (int i = 0; i < LW_TM; ++i)
+#pragma unroll
+        for (int j = 0; j < LW_TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // raw operands of one k-step (4 rows); the activation derivative is applied when they are used, so that the loads of
+    // the next k-step stay in flight during this one's MMAs
+    auto fetch = [&](int64_t r, double (&av)[LW_TM], double (&yv)[LW_TM], double (&bv)[LW_TN]) {
+        const int64_t rr = r + q;
+        const bool ok = rr < r1;
+#pragma unroll
+        for (int i = 0; i < LW_TM; ++i) {
+            const int o = 8 * (wm + 4 * i) + g;
+            const bool in = ok && o < a.nout;
+            av[i] = in ? a.gy[rr * a.nout + o] : 0.0;
+            yv[i] = (in && a.act) ? a.y[rr * a.nout + o] : 1.0;
+        }
+#pragma unroll
+        for (int j = 0; j < LW_TN; ++j) {
+            const int c = 8 * (wn + 2 * j) + g;
+            bv[j] = ok ? (c < a.nin ? a.x[rr * a.nin + c] : (c == a.nin ? 1.0 : 0.0)) : 0.0;
+        }
+    };
+    double av[LW_TM], yv[LW_TM], bv[LW_TN], an[LW_TM], yn[LW_TM], bn[LW_TN];
+#pragma unroll
+    for (int i = 0; i < LW_TM; ++i) { av[i] = an[i] = 0.0; yv[i] = yn[i] = 1.0; }
+#pragma unroll
+    for (int j = 0; j < LW_TN; ++j) bv[j] = bn[j] = 0.0;
+    if (r0 < r1) fetch(r0, av, yv, bv);
+    for (int64_t r = r0; r < r1; r += 4) {
+        if (r + 4 < r1) fetch(r + 4, an, yn, bn);
+#pragma unroll
+        for (int i = 0; i < LW_TM; ++i) {
+            if (wm + 4 * i < MTt) {
+                const double ai = yv[i] > 0.0 ? av[i] : av[i] * a.slope;
+#pragma unroll
+                for (int j = 0; j < LW_TN; ++j)
+                    if (wn + 2 * j < NTt) dmma(acc[i][j][0], acc[i][j][1], ai, bv[j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < LW_TM; ++i) { av[i] = an[i]; yv[i] = yn[i]; }
+#pragma unroll
+        for (int j = 0; j < LW_TN; ++j) bv[j] = bn[j];
+    }
+    double* part = a.part + (int64_t)blockIdx.x * a.nout * (a.nin + 1);
+#pragma unroll
+    for (int i = 0; i < LW_TM; ++i) {
+        const int o = 8 * (wm + 4 * i) + g;
+        if (o >= a.nout) continue;
+#pragma unroll
+        for (int j = 0; j < LW_TN; ++j) {
+            const int c = 8 * (wn + 2 * j) + 2 * q;
+            if (c <= a.nin) part[(int64_t)o * (a.nin + 1) + c] = acc[i][j][0];
+            if (c + 1 <= a.nin) part[(int64_t)o * (a.nin + 1) + c + 1] = acc[i][j][1];
+        }
+    }
+}
+
 // gw[o, i] / gb[o] = sum_z partial[z][o][i]
 __global__ void __launch_bounds__(256) lin_reduce_kernel(const double* part, int splits, int nout, int nin, double* gw, double* gb) {
     pdl_launch();
@@ -329,8 +513,30 @@ __global__ void __launch_bounds__(256) rows_sum_kernel(const double* part, int r
 }
 
 static int lin_splits(int64_t rows) {
-    const int64_t s = std::min<int64_t>((rows + 255) / 256, 2 * (int64_t)sm_count());
+    const int64_t s = std::min<int64_t>((rows + 127) / 128, (int64_t)sm_count());
     return (int)std::max<int64_t>(1, s);
+}
+// LGAE_LINEAR_FMA=1 keeps the plain tiled-FMA kernels (A/B checks); widths above LMMA_MAX always use them.
+static bool lin_use_mma(int n_in, int n_out) {
+    static const bool off = [] { const char* e = getenv("LGAE_LINEAR_FMA"); return e && e[0] == '1'; }();
+    return !off && n_in <= LMMA_MAX && n_out <= LMMA_MAX;
+}
+template <bool BWDX>
+static int launch_lin_mma(const LinArgs& a, cudaStream_t st) {
+    const int K = BWDX ? a.nout : a.nin, N = BWDX ? a.nin : a.nout;
+    const int KS = (K + 3) / 4, nt = (N + 7) / 8;
+    const int64_t units = (a.rows + 8 * LMMA_MT - 1) / (8 * LMMA_MT);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + LMMA_THREADS / 32 - 1) / (LMMA_THREADS / 32), sm_count()));
+#define LGAE_LIN(NTV)                                                                      \
+    {                                                                                      \
+        auto kern = lin_mma_kernel<NTV, BWDX>;                                             \
+        const size_t bytes = (size_t)KS * NTV * 32 * sizeof(double);                       \
+        if (int rc = ensure_smem((const void*)kern, bytes)) return rc;                     \
+        launch_k(kern, dim3(grid), dim3(LMMA_THREADS), bytes, st, a);                      \
+    }
+    if (nt <= 2) LGAE_LIN(2) else if (nt <= 4) LGAE_LIN(4) else if (nt <= 8) LGAE_LIN(8) else if (nt <= 12) LGAE_LIN(12) else LGAE_LIN(16)
+#undef LGAE_LIN
+    return LGAE_OK;
 }
 static int rad_ctas(int64_t E) {
     return (int)std::max<int64_t>(1, std::min<int64_t>((E + RAD_EB - 1) / RAD_EB, 2 * (int64_t)sm_count()));
@@ -436,7 +642,11 @@ int lgae_linear_forward(const double* x, const double* w, const double* b, int64
     a.x = x; a.w = w; a.b = b; a.out = y; a.rows = rows; a.nin = n_in; a.nout = n_out; a.act = leaky_relu; a.slope = slope;
     cudaStream_t st = (cudaStream_t)stream;
     LaunchScope ls_("linear_fwd", st);
-    launch_k(lin_fwd_kernel, dim3((unsigned)((rows + GT - 1) / GT), (n_out + GT - 1) / GT), dim3(256), 0, st, a);
+    if (lin_use_mma(n_in, n_out)) {
+        if (int rc = launch_lin_mma<false>(a, st)) return rc;
+    } else {
+        launch_k(lin_fwd_kernel, dim3((unsigned)((rows + GT - 1) / GT), (n_out + GT - 1) / GT), dim3(256), 0, st, a);
+    }
     return check_launch("linear_fwd");
 }
 int64_t lgae_linear_partials_doubles(int64_t rows, int32_t n_in, int32_t n_out) {
@@ -459,7 +669,11 @@ int lgae_linear_backward(const double* x, const double* w, const double* y, cons
     if (g_x) {
         a.out = g_x;
         LaunchScope ls_("linear_bwd_x", st);
-        launch_k(lin_bwd_x_kernel, dim3((unsigned)((rows + GT - 1) / GT), (n_in + GT - 1) / GT), dim3(256), 0, st, a);
+        if (lin_use_mma(n_in, n_out)) {
+            if (int rc = launch_lin_mma<true>(a, st)) return rc;
+        } else {
+            launch_k(lin_bwd_x_kernel, dim3((unsigned)((rows + GT - 1) / GT), (n_in + GT - 1) / GT), dim3(256), 0, st, a);
+        }
         if (int rc = check_launch("linear_bwd_x")) return rc;
     }
     if (g_w || g_b) {
@@ -468,7 +682,10 @@ int lgae_linear_backward(const double* x, const double* w, const double* y, cons
         a.rows_per_split = (rows + splits - 1) / splits;
         {
             LaunchScope ls_("linear_bwd_w", st);
-            launch_k(lin_bwd_w_kernel, dim3((n_out + GT - 1) / GT, (n_in + 1 + GT - 1) / GT, splits), dim3(256), 0, st, a);
+            if (lin_use_mma(n_in + 1, n_out))
+                launch_k(lin_bwd_w_mma_kernel, dim3(splits), dim3(LMMA_THREADS), 0, st, a);
+            else
+                launch_k(lin_bwd_w_kernel, dim3((n_out + GT - 1) / GT, (n_in + 1 + GT - 1) / GT, splits), dim3(256), 0, st, a);
             if (int rc = check_launch("linear_bwd_w")) return rc;
         }
         LaunchScope ls_("linear_bwd_w_sum", st);

@@ -75,7 +75,10 @@ struct LevelArgs {
 #endif
 constexpr int kBwdUnroll = LGAE_BWD_UNROLL, kFwdUnroll = LGAE_FWD_UNROLL;
 constexpr int kRingPS = LGAE_RING_PS, kRingMaxStages = 4;
-constexpr int TJ = 8;  // neighbours per shared-memory tile of radial weights
+#ifndef LGAE_TJ
+#define LGAE_TJ 8
+#endif
+constexpr int TJ = LGAE_TJ;  // neighbours per shared-memory tile of radial weights
 constexpr int CAT_E = 21;  // entries per (channel, particle) of the concatenation staged for the channel mix
 
 // Pair norm n_ij = s / sqrt|s|, s = (p_i - p_j)^2 + 1e-16, with the reference's rounding sequence

@@ -190,7 +190,8 @@ def test_radial_functions_match_oracle(basis, B, N, C):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("rows,nin,nout,slope", [(37, 6, 36, 0.01), (700, 96, 96, None), (1000, 72, 12, 0.01), (5, 3, 130, 0.2)])
+@pytest.mark.parametrize("rows,nin,nout,slope", [(37, 6, 36, 0.01), (700, 96, 96, None), (1000, 72, 12, 0.01), (5, 3, 130, 0.2),
+                                                 (1003, 128, 128, 0.01), (19, 5, 7, None), (4100, 16, 96, 0.01), (333, 97, 33, 0.3)])
 def test_linear_matches_torch_fp64(rows, nin, nout, slope):
     """Floating-point GEMM kernel: reference = the same op in plain torch fp64 on the CPU; tolerance 1e-12 relative."""
     from lgn_autoencoder_b200 import layer_ops
