@@ -796,6 +796,8 @@ struct MixArgs {
     double *out, *gx, *gw_part;
     int64_t R;
     int32_t cin, cout, d, rows_per_cta;
+    int32_t co0;   // forward: first output channel of this launch (blocks of CO channels); weight gradient: rows per stage
+    int32_t nsub;  // weight gradient: row lanes
 };
 constexpr int MIX_THREADS = 256;
 
@@ -803,22 +805,43 @@ LGAE_DEV void mix_stage_w(const MixArgs& a, cplx* ws) {
     const int n = a.cout * a.cin;
     for (int t = threadIdx.x; t < n; t += blockDim.x) ws[t] = cmake(a.w[t], a.w[n + t]);
 }
+// thread = one (row, component m): it reads x[r, :, m] once and keeps the accumulators of all CO output channels in registers
+// (2 global loads + CO broadcast shared-memory loads per 4 CO multiply-adds)
+template <int CO>
 __global__ void __launch_bounds__(MIX_THREADS) mix_fwd_kernel(const MixArgs a) {
     pdl_launch();
     extern __shared__ __align__(16) double smem[];
-    cplx* ws = reinterpret_cast<cplx*>(smem);
-    mix_stage_w(a, ws);
+    cplx* ws = reinterpret_cast<cplx*>(smem);   // [ci][CO], zero beyond cout
+    {
+        const int n = a.cout * a.cin;
+        for (int t = threadIdx.x; t < a.cin * CO; t += blockDim.x) {
+            const int ci = t / CO, co = a.co0 + t % CO;
+            ws[t] = co < a.cout ? cmake(a.w[co * a.cin + ci], a.w[n + co * a.cin + ci]) : czero();
+        }
+    }
     pdl_wait();
     __syncthreads();
-    const int64_t per_row = (int64_t)a.cout * a.d, total = a.R * per_row, xplane = a.R * a.cin * a.d;
-    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = it / per_row;
-        const int w = (int)(it % per_row), m = w % a.d, co = w / a.d;
+    const int64_t items = a.R * a.d, xplane = a.R * a.cin * a.d, oplane = a.R * a.cout * a.d;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = it / a.d;
+        const int m = (int)(it - r * a.d);
         const double* x = a.x + r * a.cin * a.d + m;
-        cplx acc = czero();
-        for (int ci = 0; ci < a.cin; ++ci) cfma(acc, ws[co * a.cin + ci], cmake(x[(int64_t)ci * a.d], x[xplane + (int64_t)ci * a.d]));
-        a.out[it] = acc.x;
-        a.out[total + it] = acc.y;
+        cplx acc[CO];
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[co] = czero();
+#pragma unroll 2
+        for (int ci = 0; ci < a.cin; ++ci) {
+            const cplx xv = cmake(x[(int64_t)ci * a.d], x[xplane + (int64_t)ci * a.d]);
+#pragma unroll
+            for (int co = 0; co < CO; ++co) cfma(acc[co], ws[ci * CO + co], xv);
+        }
+        double* o = a.out + (r * a.cout + a.co0) * a.d + m;
+#pragma unroll
+        for (int co = 0; co < CO; ++co)
+            if (a.co0 + co < a.cout) {
+                o[(int64_t)co * a.d] = acc[co].x;
+                o[oplane + (int64_t)co * a.d] = acc[co].y;
+            }
     }
 }
 // gx[r, ci, m] = sum_co conj(W[co, ci]) g[r, co, m]
@@ -841,50 +864,85 @@ __global__ void __launch_bounds__(MIX_THREADS) mix_bwd_x_kernel(const MixArgs a)
     }
 }
 // gW[co, ci] = sum_{r, m} conj(x[r, ci, m]) g[r, co, m]: one partial (2, cout*cin) per CTA over its rows, fixed order.
+// Rows are staged `rows_per_stage` at a time; thread = (input channel ci, row lane): it reads its x entries once and keeps the
+// accumulators of CO output channels in registers (the g entries are warp-wide broadcasts); the row lanes are then added
+// in order through shared memory.
+template <int CO>
 __global__ void __launch_bounds__(MIX_THREADS) mix_bwd_w_kernel(const MixArgs a) {
     pdl_launch();
     pdl_wait();
     extern __shared__ __align__(16) double smem[];
-    cplx* xs = reinterpret_cast<cplx*>(smem);   // cin*d
-    cplx* gs = xs + (size_t)a.cin * a.d;        // cout*d
-    const int n = a.cout * a.cin;
-    const int64_t xplane = a.R * a.cin * a.d, gplane = a.R * a.cout * a.d;
+    const int cin = a.cin, cout = a.cout, d = a.d, RB = a.co0;   // co0 carries the rows per stage here
+    cplx* xs = reinterpret_cast<cplx*>(smem);            // RB * cin * d
+    cplx* gs = xs + (size_t)RB * cin * d;                // RB * cout * d
+    cplx* red = reinterpret_cast<cplx*>(smem);           // nsub * cb * CO, aliases the staging area after the row loop
+    const int n = cout * cin;
+    const int64_t xplane = a.R * cin * d, gplane = a.R * cout * d;
     const int64_t r0 = (int64_t)blockIdx.x * a.rows_per_cta, r1 = min(a.R, r0 + a.rows_per_cta);
     double* part = a.gw_part + (int64_t)blockIdx.x * 2 * n;
-    for (int base = 0; base < n; base += MIX_THREADS * CG_ITEMS) {
-        cplx acc[CG_ITEMS];
+    const int cb = min(cin, MIX_THREADS);                // input channels per pass
+    const int nsub = a.nsub;                             // row lanes (<= MIX_THREADS / cb)
+    const int cl = threadIdx.x % cb, sub = threadIdx.x / cb;
+    for (int ci0 = 0; ci0 < cin; ci0 += cb)
+        for (int co0 = 0; co0 < cout; co0 += CO) {
+            const int ci = ci0 + cl;
+            const bool active = sub < nsub && ci < cin;
+            cplx acc[CO];
 #pragma unroll
-        for (int k = 0; k < CG_ITEMS; ++k) acc[k] = czero();
-        for (int64_t r = r0; r < r1; ++r) {
-            __syncthreads();
-            stage_planar(xs, a.x + r * a.cin * a.d, xplane, a.cin * a.d);
-            stage_planar(gs, a.g + r * a.cout * a.d, gplane, a.cout * a.d);
-            __syncthreads();
+            for (int co = 0; co < CO; ++co) acc[co] = czero();
+            for (int64_t rb = r0; rb < r1; rb += RB) {
+                const int nr = (int)min((int64_t)RB, r1 - rb);
+                __syncthreads();
+                stage_planar(xs, a.x + rb * cin * d, xplane, nr * cin * d);
+                stage_planar(gs, a.g + rb * cout * d, gplane, nr * cout * d);
+                __syncthreads();
+                if (active)
+                    for (int rr = sub; rr < nr; rr += nsub) {
+                        const cplx* xr = xs + ((size_t)rr * cin + ci) * d;
+                        const cplx* gr = gs + ((size_t)rr * cout + co0) * d;
+                        for (int m = 0; m < d; ++m) {
+                            const cplx xv = xr[m];
 #pragma unroll
-            for (int k = 0; k < CG_ITEMS; ++k) {
-                const int it = base + threadIdx.x + k * MIX_THREADS;
-                if (it >= n) break;
-                const int ci = it % a.cin, co = it / a.cin;
-                for (int m = 0; m < a.d; ++m) cfmac(acc[k], xs[ci * a.d + m], gs[co * a.d + m]);
+                            for (int co = 0; co < CO; ++co)
+                                if (co0 + co < cout) cfmac(acc[co], xv, gr[co * d + m]);
+                        }
+                    }
+            }
+            __syncthreads();
+            if (active) {
+#pragma unroll
+                for (int co = 0; co < CO; ++co) red[((size_t)sub * cb + cl) * CO + co] = acc[co];
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < cb * CO; t += blockDim.x) {
+                const int c2 = t / CO, co = t % CO;
+                if (ci0 + c2 >= cin || co0 + co >= cout) continue;
+                cplx v = red[t];
+                for (int sl = 1; sl < nsub; ++sl) v = cadd(v, red[(size_t)sl * cb * CO + t]);
+                const int it = (co0 + co) * cin + ci0 + c2;
+                part[it] = v.x;
+                part[n + it] = v.y;
             }
         }
-#pragma unroll
-        for (int k = 0; k < CG_ITEMS; ++k) {
-            const int it = base + threadIdx.x + k * MIX_THREADS;
-            if (it >= n) break;
-            part[it] = acc[k].x;
-            part[n + it] = acc[k].y;
-        }
-    }
 }
-// out[t] = sum_rows part[row][t]   (fixed order)
-__global__ void __launch_bounds__(256) colsum_kernel(const double* part, int rows, int64_t n, double* out) {
+// out[t] = sum_rows part[row][t]: 32 columns x 8 row lanes per CTA, every lane walks its rows in order, then the lanes are
+// added in order (fixed summation order: deterministic)
+constexpr int COLSUM_Y = 8;
+__global__ void __launch_bounds__(32 * COLSUM_Y) colsum_kernel(const double* part, int rows, int64_t n, double* out) {
     pdl_launch();
     pdl_wait();
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < rows; ++r) s += part[(int64_t)r * n + t];
-        out[t] = s;
+    __shared__ double red[COLSUM_Y][33];
+    const int64_t t = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    if (t < n)
+        for (int r = threadIdx.y; r < rows; r += COLSUM_Y) s += part[(int64_t)r * n + t];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && t < n) {
+        double acc = red[0][threadIdx.x];
+#pragma unroll
+        for (int y = 1; y < COLSUM_Y; ++y) acc += red[y][threadIdx.x];
+        out[t] = acc;
     }
 }
 
@@ -1204,12 +1262,18 @@ int lgae_mix_forward(const double* w, const double* x, int64_t rows, int32_t c_i
     if (!w || !x || !out) return LGAE_E_BADARG;
     MixArgs a = {};
     a.x = x; a.w = w; a.out = out; a.R = rows; a.cin = c_in; a.cout = c_out; a.d = d;
-    const size_t bytes = (size_t)c_in * c_out * sizeof(cplx);
-    if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    if (int rc = ensure_smem((const void*)mix_fwd_kernel, bytes)) return rc;
     LaunchScope ls_("mix_fwd", st);
-    launch_k(mix_fwd_kernel, dim3(grid_for(rows * c_out * d, MIX_THREADS)), dim3(MIX_THREADS), bytes, st, a);
+#define LGAE_MIXF(COV)                                                                                              \
+    {                                                                                                               \
+        const size_t bytes = (size_t)c_in * COV * sizeof(cplx);                                                     \
+        if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;                                                          \
+        if (int rc = ensure_smem((const void*)mix_fwd_kernel<COV>, bytes)) return rc;                               \
+        launch_k(mix_fwd_kernel<COV>, dim3(grid_for(rows * d, MIX_THREADS)), dim3(MIX_THREADS), bytes, st, a);      \
+    }
+    if (c_out <= 4) LGAE_MIXF(4) else if (c_out <= 8) LGAE_MIXF(8) else
+        for (a.co0 = 0; a.co0 < c_out; a.co0 += 16) LGAE_MIXF(16)
+#undef LGAE_MIXF
     return check_launch("mix_fwd");
 }
 
@@ -1236,17 +1300,34 @@ int lgae_mix_backward(const double* w, const double* x, const double* g_out, int
         const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(rows, 4 * (int64_t)sm_count()));
         a.rows_per_cta = (int32_t)((rows + ctas - 1) / ctas);
         const int grid = (int)((rows + a.rows_per_cta - 1) / a.rows_per_cta);
-        const size_t bytes = (size_t)(c_in + c_out) * d * sizeof(cplx);
+        const size_t row_bytes = (size_t)(c_in + c_out) * d * sizeof(cplx);
+        if (row_bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
+        const int co_blk = c_out <= 4 ? 4 : 8;
+        const int cb = std::min<int>(c_in, MIX_THREADS);
+        // rows per stage: about 64 KB of staging, a multiple of the row lanes
+        int rb = (int)std::max<size_t>(1, (64 * 1024) / row_bytes);
+        const int nsub = std::max(1, std::min(MIX_THREADS / cb, rb));
+        rb = std::max(nsub, rb / nsub * nsub);
+        rb = std::min<int>(rb, std::max<int>(nsub, (a.rows_per_cta + nsub - 1) / nsub * nsub));
+        const size_t red_bytes = (size_t)nsub * cb * co_blk * sizeof(cplx);
+        const size_t bytes = std::max(row_bytes * rb, red_bytes);
         if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
-        if (int rc = ensure_smem((const void*)mix_bwd_w_kernel, bytes)) return rc;
+        a.co0 = rb;
+        a.nsub = nsub;
         {
             LaunchScope ls_("mix_bwd_w", st);
-            launch_k(mix_bwd_w_kernel, dim3(grid), dim3(MIX_THREADS), bytes, st, a);
+            if (co_blk == 4) {
+                if (int rc = ensure_smem((const void*)mix_bwd_w_kernel<4>, bytes)) return rc;
+                launch_k(mix_bwd_w_kernel<4>, dim3(grid), dim3(MIX_THREADS), bytes, st, a);
+            } else {
+                if (int rc = ensure_smem((const void*)mix_bwd_w_kernel<8>, bytes)) return rc;
+                launch_k(mix_bwd_w_kernel<8>, dim3(grid), dim3(MIX_THREADS), bytes, st, a);
+            }
             if (int rc = check_launch("mix_bwd_w")) return rc;
         }
         const int64_t n = (int64_t)2 * c_in * c_out;
         LaunchScope ls_("mix_bwd_w_sum", st);
-        launch_k(colsum_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, (const double*)partials, grid, n, g_w);
+        launch_k(colsum_kernel, dim3((unsigned)((n + 31) / 32)), dim3(32, COLSUM_Y), 0, st, (const double*)partials, grid, n, g_w);
         return check_launch("mix_bwd_w_sum");
     }
     return LGAE_OK;
