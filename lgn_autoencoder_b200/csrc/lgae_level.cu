@@ -76,7 +76,7 @@ struct LevelArgs {
 constexpr int kBwdUnroll = LGAE_BWD_UNROLL, kFwdUnroll = LGAE_FWD_UNROLL;
 constexpr int kRingPS = LGAE_RING_PS, kRingMaxStages = 4;
 #ifndef LGAE_TJ
-#define LGAE_TJ 8
+#define LGAE_TJ 8   // with the component-wise mix and tile-wise partner features a 150-particle jet needs 43 KB per CTA (4: 8.74 vs 8.48 ms per 1024 jets)
 #endif
 constexpr int TJ = LGAE_TJ;  // neighbours per shared-memory tile of radial weights
 constexpr int CAT_E = 21;  // entries per (channel, particle) of the concatenation staged for the channel mix
@@ -172,14 +172,18 @@ __host__ __device__ inline LevelSmem level_smem(bool enc, bool tiles, int N, int
     int o = 0;
     s.p = o; o += enc ? 4 * N : 8 * N;
     s.msk = o; o += ((N + 7) / 8 + 2) & ~1;
-    s.S = o; o += 2 * N * C;
-    s.V = o; o += 8 * N * C;
+    // node features: the whole jet, or (radial weights evaluated in the kernel) only the partners of the current tile -- the
+    // 10 N C doubles of a long jet would otherwise decide how many CTAs fit on an SM
+    s.S = o; o += 2 * (tiles ? TJ : N) * C;
+    s.V = o; o += 8 * (tiles ? TJ : N) * C;
     s.abc = o; o += (3 * 4 * KS + 1) & ~1;
     s.m00 = o; o += 2 * Cout * 5 * C;
     s.m11 = o; o += 2 * Cout * 5 * C;
     o = (o + 3) & ~3;
     s.big = o;
-    const int cat = 2 * CAT_E * C * (N < 32 ? N : 32);   // cat: [(c*21+e)][min(N,32)] complex
+    // cat: [(c*21+e)][min(N,32)] complex; jets of more than 32 particles (several CTAs per jet, shared memory is what limits
+    // their occupancy) mix component by component through a [(c*5+j)][32] buffer instead
+    const int cat = N > 32 ? 2 * 5 * C * 32 : 2 * CAT_E * C * (N < 32 ? N : 32);
     const int tile = tiles ? TJ * C * 32 * 4 : 0;   // Rs (radial weights evaluated in the kernel)
     o += cat > tile ? cat : tile;
     s.total = o;
@@ -236,10 +240,13 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
         const int np = ENC ? 4 * N : 8 * N;
         const double* src = a.p + (int64_t)b * np;
         if (tid == 0) {
-            mbar_expect_tx(&mbar, (unsigned)((np + 10 * N * C) * sizeof(double)));
+            constexpr bool kTiles = ENC && !PRE;   // node features of the partners arrive tile by tile
+            mbar_expect_tx(&mbar, (unsigned)((np + (kTiles ? 0 : 10 * N * C)) * sizeof(double)));
             bulk_g2s(p_s, src, np * sizeof(double), &mbar);
-            bulk_g2s(smem + L.S, a.s_in + (int64_t)b * N * C * 2, 2 * N * C * sizeof(double), &mbar);
-            bulk_g2s(smem + L.V, a.v_in + (int64_t)b * N * C * 8, 8 * N * C * sizeof(double), &mbar);
+            if (!kTiles) {
+                bulk_g2s(smem + L.S, a.s_in + (int64_t)b * N * C * 2, 2 * N * C * sizeof(double), &mbar);
+                bulk_g2s(smem + L.V, a.v_in + (int64_t)b * N * C * 8, 8 * N * C * sizeof(double), &mbar);
+            }
             if (ring)
                 for (int g = 0; g < nst && g < ngr; ++g) ring_issue(g);
         }
@@ -320,11 +327,11 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
         }
     } else {
     // one neighbour j with its radial weights: the four neighbour sums of this (particle, channel)
-    auto pair = [&](int j, cplx R0, cplx R1) {
-        const cplx Sj = S_s[j * C + c];
+    auto pair = [&](int j, int js, cplx R0, cplx R1) {   // js: where partner j's features lie in S_s / V_s
+        const cplx Sj = S_s[js * C + c];
         cplx Vj[4];
 #pragma unroll
-        for (int mu = 0; mu < 4; ++mu) Vj[mu] = V_s[(j * C + c) * 4 + mu];
+        for (int mu = 0; mu < 4; ++mu) Vj[mu] = V_s[(js * C + c) * 4 + mu];
         cplx Y[4];
         if (ENC) {
             double d[4];
@@ -366,7 +373,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
             for (int jj = 0; jj < kRingPS; ++jj) {
                 if (jj < tj) {
                     const double4 r = *reinterpret_cast<const double4*>(rs + (size_t)jj * pd);
-                    pair(j0 + jj, cmake(r.x, r.y), cmake(r.z, r.w));
+                    pair(j0 + jj, j0 + jj, cmake(r.x, r.y), cmake(r.z, r.w));
                 }
             }
             if (g + nst < ngr) {   // every warp is done with stage s: refill it
@@ -386,7 +393,24 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
     for (int j0 = 0; j0 < N; j0 += TJ) {
         const int tj = min(TJ, N - j0);
         if (ENC && !PRE) {
+            // the tile's partner features: global loads in flight during the radial tile, then into shared memory
+            constexpr int NPF = (TJ * 5 + 31) / 32;
+            cplx pf[NPF];
+            const int nsv = tj * C * 5;
+            const cplx* sg = reinterpret_cast<const cplx*>(a.s_in) + ((int64_t)b * N + j0) * C;
+            const cplx* vg = reinterpret_cast<const cplx*>(a.v_in) + ((int64_t)b * N + j0) * C * 4;
+#pragma unroll
+            for (int k = 0; k < NPF; ++k) {
+                const int t = tid + k * blockDim.x;
+                pf[k] = czero();
+                if (t < nsv) pf[k] = t < tj * C ? sg[t] : vg[t - tj * C];
+            }
             radial_tile<NT, KS>(p_s, msk_s, N, C, i0, j0, tj, abc_s, wf, bf, Rs);
+#pragma unroll
+            for (int k = 0; k < NPF; ++k) {
+                const int t = tid + k * blockDim.x;
+                if (t < nsv) { if (t < tj * C) S_s[t] = pf[k]; else V_s[t - tj * C] = pf[k]; }
+            }
             __syncthreads();
         }
 #pragma unroll kFwdUnroll
@@ -404,7 +428,7 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
                 R0 = cmake(r.x, r.y);
                 R1 = cmake(r.z, r.w);
             }
-            pair(j, R0, R1);
+            pair(j, (ENC && !PRE) ? jj : j, R0, R1);
         }
         if (ENC && !PRE) __syncthreads();
     }
@@ -420,11 +444,63 @@ __global__ void __launch_bounds__(256) level_fwd_kernel(const LevelArgs a) {
         dst[4] = A0S;
         dst[9] = A1E;
     }
-    {
-        const cplx Si = live ? S_s[i * C + c] : czero();
-        cplx Vi[4];
+    cplx Si = czero(), Vi[4] = {czero(), czero(), czero(), czero()};
+    if (live) {
+        if (ENC && !PRE) {   // only the current tile's partners are in shared memory
+            Si = reinterpret_cast<const cplx*>(a.s_in)[((int64_t)b * N + i) * C + c];
 #pragma unroll
-        for (int mu = 0; mu < 4; ++mu) Vi[mu] = live ? V_s[(i * C + c) * 4 + mu] : czero();
+            for (int mu = 0; mu < 4; ++mu) Vi[mu] = reinterpret_cast<const cplx*>(a.v_in)[(((int64_t)b * N + i) * C + c) * 4 + mu];
+        } else {
+            Si = S_s[i * C + c];
+#pragma unroll
+            for (int mu = 0; mu < 4; ++mu) Vi[mu] = V_s[(i * C + c) * 4 + mu];
+        }
+    }
+    if (N > 32) {
+        // ---- component by component: the 5 (0,0) entries, then the 4 entries of each (1,1) component, through a small buffer
+        // (same entries, weights and summation order as the one-shot form below) ----
+#pragma unroll
+        for (int comp = 0; comp < 5; ++comp) {
+            if (comp) __syncthreads();   // the previous component's entries are consumed
+            if (comp == 0) {
+                cat_s[(c * 5 + 0) * 32 + lane] = cscale(A1E, 0.5);
+                cat_s[(c * 5 + 1) * 32 + lane] = cmul_1pi(A0S);
+                cat_s[(c * 5 + 2) * 32 + lane] = Si;
+                cat_s[(c * 5 + 3) * 32 + lane] = cscale(ceta(Vi, Vi), 0.5);
+                cat_s[(c * 5 + 4) * 32 + lane] = cmul(Si, Si);
+            } else {
+                const int mu = comp > 0 ? comp - 1 : 0;   // compile-time after unrolling
+                const cplx a0 = A0V[mu], a1 = A1Y[mu], vi = Vi[mu];
+                cat_s[(c * 5 + 0) * 32 + lane] = cmul_1pi(a0);
+                cat_s[(c * 5 + 1) * 32 + lane] = a1;
+                cat_s[(c * 5 + 2) * 32 + lane] = vi;
+                cat_s[(c * 5 + 3) * 32 + lane] = cmul(vi, Si);
+            }
+            __syncthreads();
+            for (int it = tid; it < 32 * Cout; it += blockDim.x) {
+                const int il = it & 31, co = it >> 5, ii = i0 + il;
+                if (ii >= N) continue;
+                cplx acc = czero();
+                if (comp == 0) {
+                    const cplx* w = m00_s + co * 5 * C;
+                    for (int cc = 0; cc < C; ++cc)
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) cfma(acc, w[j * C + cc], cat_s[(cc * 5 + j) * 32 + il]);
+                    reinterpret_cast<cplx*>(a.s_pre)[(int64_t)(b * N + ii) * Cout + co] = acc;
+                } else {
+                    const cplx* w = m11_s + co * 5 * C;
+                    for (int cc = 0; cc < C; ++cc) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) cfma(acc, w[j * C + cc], cat_s[(cc * 5 + j) * 32 + il]);
+                        cfma(acc, cadd(w[3 * C + cc], w[4 * C + cc]), cat_s[(cc * 5 + 3) * 32 + il]);
+                    }
+                    reinterpret_cast<cplx*>(a.v_out)[((int64_t)(b * N + ii) * Cout + co) * 4 + comp - 1] = acc;
+                }
+            }
+                    }
+        return;
+    }
+    {
         // 21 entries per (channel, particle): the five (0,0) blocks [ag_a, ag_b, node, sq_a, sq_b], then the (1,1) components
         // of [ag_a, ag_b, node, sq]; the two self-product blocks share their (1,1) part V S, so it is stored once and
         // mixed with the sum of their weights.
