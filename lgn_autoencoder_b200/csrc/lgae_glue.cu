@@ -175,60 +175,44 @@ LGAE_DEV void enc_latent_body(const LatentArgs& a, double* smem, cplx* lat_out) 
     const bool both = mode == LGAE_LATENT_MINMAX;
     const int Ts = both ? 2 * ts : ts, Tv = both ? 2 * tv : tv;
     const int tmax = ts > tv ? ts : tv;
-    // One warp per selection, lanes over the particles: every lane keeps the first optimum of its particles, the butterfly keeps
-    // the better key and, on ties, the lower particle index -- the same choice as a serial scan in particle order.
-    const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    auto warp_select = [&](bool kind, double& bv, int& best) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ok = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const bool take = ob >= 0 && (best < 0 || (kind ? ok > bv : ok < bv) || (ok == bv && ob < best));
-            if (take) { bv = ok; best = ob; }
-        }
-    };
-    for (int it = warp; it < 2 * 2 * ts; it += nwarps) {          // scalars: [kind][part][t]
+    for (int it = tid; it < 2 * 2 * ts; it += blockDim.x) {          // scalars: [kind][part][t]
         const int t = it % ts, part = (it / ts) & 1, kind = it / (2 * ts);   // kind 0 = min, 1 = max
         if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
-        int best = -1;
+        int best = 0;
         double bv = 0.0;
-        for (int i = lane; i < N; i += 32) {
+        for (int i = 0; i < N; ++i) {
             const cplx z = L00[i * ts + t];
             const double s = part ? z.y : z.x;
             const double key = kind ? s * s : s;                     // max selects on s^2 (get_msq of a scalar)
-            if (best < 0 || (kind ? key > bv : key < bv)) { bv = key; best = i; }
+            if (i == 0 || (kind ? key > bv : key < bv)) { bv = key; best = i; }
         }
-        warp_select(kind != 0, bv, best);
-        if (lane == 0) {
-            const cplx z = L00[best * ts + t];
-            const int T = (both && kind) ? ts + t : t;
-            a.lat00[(int64_t)(part * B + b) * Ts + T] = part ? z.y : z.x;
-            if (a.sel) a.sel[((int64_t)((kind)*2 + part) * B + b) * tmax + t] = best;
-        }
+        const cplx z = L00[best * ts + t];
+        const int T = (both && kind) ? ts + t : t;
+        a.lat00[(int64_t)(part * B + b) * Ts + T] = part ? z.y : z.x;
+        if (a.sel) a.sel[((int64_t)((kind)*2 + part) * B + b) * tmax + t] = best;
     }
-    for (int it = warp; it < 2 * 2 * tv; it += nwarps) {          // vectors
+    for (int it = tid; it < 2 * 2 * tv; it += blockDim.x) {          // vectors
         const int t = it % tv, part = (it / tv) & 1, kind = it / (2 * tv);
         if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
-        int best = -1;
+        int best = 0;
         double bv = 0.0;
-        for (int i = lane; i < N; i += 32) {
+        for (int i = 0; i < N; ++i) {
             double v[4];
 #pragma unroll
             for (int mu = 0; mu < 4; ++mu) { const cplx z = L11[(i * tv + t) * 4 + mu]; v[mu] = part ? z.y : z.x; }
             const double key = msq_of(v);
-            if (best < 0 || (kind ? key > bv : key < bv)) { bv = key; best = i; }
+            if (i == 0 || (kind ? key > bv : key < bv)) { bv = key; best = i; }
         }
-        warp_select(kind != 0, bv, best);
         const int T = (both && kind) ? tv + t : t;
-        if (lane < 4) {
-            const int mu = lane;
+#pragma unroll
+        for (int mu = 0; mu < 4; ++mu) {
             const cplx z = L11[(best * tv + t) * 4 + mu];
             a.lat11[((int64_t)(part * B + b) * Tv + T) * 4 + mu] = part ? z.y : z.x;
-            if (lat_out) {   // re and im parts are selected independently: two warps fill the two halves
+            if (lat_out) {   // re and im parts are selected independently: two threads fill the two halves
                 if (part) lat_out[T * 4 + mu].y = z.y; else lat_out[T * 4 + mu].x = z.x;
             }
         }
-        if (lane == 0 && a.sel) a.sel[((int64_t)((2 + kind) * 2 + part) * B + b) * tmax + t] = best;
+        if (a.sel) a.sel[((int64_t)((2 + kind) * 2 + part) * B + b) * tmax + t] = best;
     }
 }
 
@@ -362,40 +346,20 @@ __device__ __forceinline__ void enc_latent_bwd_jet(const LatentArgs& a, const En
 #pragma unroll
             for (int mu = 0; mu < 4; ++mu) reinterpret_cast<cplx*>(a.gV)[((int64_t)b * N * C + it) * 4 + mu] = gv[mu];
         }
-        // weight gradients.  Several rows (per-particle latent maps): one warp per (t, k), lanes over the particles, butterfly
-        // sum (fixed order); a single row ('mix'): one thread per (t, k)
-        if (rows > 1) {
-            const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-            for (int it = warp; it < (ts + tv) * cin; it += nwarps) {
-                cplx acc = czero();
-                if (it < ts * cin) {
-                    const int t = it / cin, k = it % cin;
-                    for (int i = lane; i < rows; i += 32) cfmac(acc, S[i * cin + k], gL00[i * ts + t]);
-                } else {
-                    const int t = (it - ts * cin) / cin, k = (it - ts * cin) % cin;
-                    for (int i = lane; i < rows; i += 32)
+        // weight gradients: one thread per (t, k)
+        for (int it = tid; it < ts * cin; it += blockDim.x) {
+            const int t = it / cin, k = it % cin;
+            cplx acc = czero();
+            for (int i = 0; i < rows; ++i) cfmac(acc, S[i * cin + k], gL00[i * ts + t]);
+            gw00[it] = cadd(gw00[it], acc);
+        }
+        for (int it = tid; it < tv * cin; it += blockDim.x) {
+            const int t = it / cin, k = it % cin;
+            cplx acc = czero();
+            for (int i = 0; i < rows; ++i)
 #pragma unroll
-                        for (int mu = 0; mu < 4; ++mu) cfmac(acc, V[(i * cin + k) * 4 + mu], gL11[(i * tv + t) * 4 + mu]);
-                }
-                acc.x = warp_sum(acc.x);
-                acc.y = warp_sum(acc.y);
-                if (lane == 0) gw00[it] = cadd(gw00[it], acc);   // gw11 follows gw00 in shared memory
-            }
-        } else {
-            for (int it = tid; it < ts * cin; it += blockDim.x) {
-                const int t = it / cin, k = it % cin;
-                cplx acc = czero();
-                for (int i = 0; i < rows; ++i) cfmac(acc, S[i * cin + k], gL00[i * ts + t]);
-                gw00[it] = cadd(gw00[it], acc);
-            }
-            for (int it = tid; it < tv * cin; it += blockDim.x) {
-                const int t = it / cin, k = it % cin;
-                cplx acc = czero();
-                for (int i = 0; i < rows; ++i)
-#pragma unroll
-                    for (int mu = 0; mu < 4; ++mu) cfmac(acc, V[(i * cin + k) * 4 + mu], gL11[(i * tv + t) * 4 + mu]);
-                gw11[it] = cadd(gw11[it], acc);
-            }
+                for (int mu = 0; mu < 4; ++mu) cfmac(acc, V[(i * cin + k) * 4 + mu], gL11[(i * tv + t) * 4 + mu]);
+            gw11[it] = cadd(gw11[it], acc);
         }
     }
 }
@@ -547,17 +511,13 @@ __device__ __forceinline__ void dec_input_bwd_jet(const DecInArgs& a, const DecI
             for (int mu = 0; mu < 4; ++mu) cfmac(acc, lat[t * 4 + mu], gP_s[i * 4 + mu]);
             gwg[it] = cadd(gwg[it], acc);
         }
-        for (int it = tid >> 5; it < tau * 4; it += blockDim.x >> 5) {   // one warp per (t, mu), lanes over the particles
-            const int t = it / 4, mu = it % 4, lane = tid & 31;
+        for (int it = tid; it < tau * 4; it += blockDim.x) {
+            const int t = it / 4, mu = it % 4;
             cplx acc = czero();
-            for (int i = lane; i < N; i += 32) cfmac(acc, wget(a.theta, a.off_g11, N, tau, i, t), gP_s[i * 4 + mu]);
-            acc.x = warp_sum(acc.x);
-            acc.y = warp_sum(acc.y);
-            if (lane == 0) {
-                a.g_lat11[(int64_t)(0 * B + b) * tau * 4 + it] = acc.x;
-                a.g_lat11[(int64_t)(1 * B + b) * tau * 4 + it] = acc.y;
-                if (glat_s) glat_s[it] = acc;
-            }
+            for (int i = 0; i < N; ++i) cfmac(acc, wget(a.theta, a.off_g11, N, tau, i, t), gP_s[i * 4 + mu]);
+            a.g_lat11[(int64_t)(0 * B + b) * tau * 4 + it] = acc.x;
+            a.g_lat11[(int64_t)(1 * B + b) * tau * 4 + it] = acc.y;
+            if (glat_s) glat_s[it] = acc;
         }
     }
 }
