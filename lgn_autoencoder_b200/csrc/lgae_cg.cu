@@ -401,8 +401,11 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_bwd_edge_kernel(const
 }
 // Adjoint, node operands: dL/dz1_p[j][a] = sum_i sum_{d_all} conj(z2_ij[d_all]) gK_i[a_all][d_all]; one CTA per jet walks the particles
 // i in blocks of IB, a thread owns one (j, channel) and all D1T accumulators in registers (fixed summation order).
+#ifndef LGAE_AGG_NODE_MINB
+#define LGAE_AGG_NODE_MINB 2   // 128 registers, no spills: 2 CTAs per SM (1.45 -> 1.13 ms per launch at cfg-4)
+#endif
 template <int D1T, int D2T>
-__global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_bwd_node_kernel(const CgMultiArgs p) {
+__global__ void __launch_bounds__(CG_THREADS, LGAE_AGG_NODE_MINB) cg_agg_multi_bwd_node_kernel(const CgMultiArgs p) {
     pdl_launch();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, C = p.C, NJ = p.NJ, IB = p.IB, nc = p.n_comp;

@@ -86,7 +86,13 @@ struct RadArgs {
     int64_t E, n_mask;
     int32_t K2, nout, L, planar, part_stride;
 };
-constexpr int RAD_EB = 128;   // edges per block iteration
+#ifndef LGAE_RAD_EB
+#define LGAE_RAD_EB 64
+#endif
+#ifndef LGAE_RAD_CTAS
+#define LGAE_RAD_CTAS 4
+#endif
+constexpr int RAD_EB = LGAE_RAD_EB;   // edges per block iteration
 constexpr int RAD_T = 256;
 // Row strides of the per-edge shared-memory tables, made odd: a warp that walks the edges at a fixed column then hits 16
 // different bank pairs instead of 2-4 (K2 = 20) or one (n_l * n_out = 32).
@@ -539,7 +545,7 @@ static int launch_lin_mma(const LinArgs& a, cudaStream_t st) {
     return LGAE_OK;
 }
 static int rad_ctas(int64_t E) {
-    return (int)std::max<int64_t>(1, std::min<int64_t>((E + RAD_EB - 1) / RAD_EB, 2 * (int64_t)sm_count()));
+    return (int)std::max<int64_t>(1, std::min<int64_t>((E + RAD_EB - 1) / RAD_EB, LGAE_RAD_CTAS * (int64_t)sm_count()));
 }
 
 }  // namespace lgae
