@@ -286,8 +286,20 @@ LGAE_DEV MultiBwdTabs multi_load_bwd_tabs(const CgMultiArgs& p, double* mem, int
 }
 static size_t multi_bwd_tab_bytes(int nt, int nc, int ncell) { return (size_t)nt * sizeof(double) + ((size_t)nt + ncell + 1 + 3 * nc) * sizeof(int32_t) + 16; }
 
+#ifndef LGAE_AGG_FWD_MINB
+#define LGAE_AGG_FWD_MINB 1
+#endif
+#ifndef LGAE_AGG_FWD_IB
+#define LGAE_AGG_FWD_IB 3
+#endif
+#ifndef LGAE_AGG_EDGE_MINB
+#define LGAE_AGG_EDGE_MINB 1
+#endif
+#ifndef LGAE_AGG_EDGE_IB
+#define LGAE_AGG_EDGE_IB 4
+#endif
 template <int D2T>
-__global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_fwd_kernel(const CgMultiArgs p) {
+__global__ void __launch_bounds__(CG_THREADS, LGAE_AGG_FWD_MINB) cg_agg_multi_fwd_kernel(const CgMultiArgs p) {
     pdl_launch();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, C = p.C, NJ = p.NJ, IB = p.IB, nc = p.n_comp, nt = p.n_terms;
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_fwd_kernel(const CgMu
 // Adjoint of the one-launch aggregate, edge operand: dL/dz2_q[i, j][d] = sum_{a_all} conj(z1_j[a_all]) gK_i[a_all][d_all] for every
 // edge part q at once; grid (B, ceil(N / IB)), fully parallel, node parts read from global memory.
 template <int D2T>
-__global__ void __launch_bounds__(CG_THREADS) cg_agg_multi_bwd_edge_kernel(const CgMultiArgs p) {
+__global__ void __launch_bounds__(CG_THREADS, LGAE_AGG_EDGE_MINB) cg_agg_multi_bwd_edge_kernel(const CgMultiArgs p) {
     pdl_launch();
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x, C = p.C, NJ = p.NJ, IB = p.IB, nc = p.n_comp;
@@ -1164,7 +1176,7 @@ int lgae_cg_aggregate_multi_backward(const LgaeCgMultiDesc* d, const int32_t* ta
     if (want_edge && !(D2T == 1 || D2T == 4 || D2T == 5)) return LGAE_E_UNSUPPORTED;
     if (want_edge) {
         const size_t per_ib = ((size_t)p.C * p.n_comp + (size_t)p.C * ncell) * sizeof(cplx);
-        int ib = std::min<int>(4, p.N);
+        int ib = std::min<int>(LGAE_AGG_EDGE_IB, p.N);
         while (ib > 1 && tabs + ib * per_ib > 100 * 1024) --ib;
         const size_t bytes = tabs + ib * per_ib;
         if (bytes > 160 * 1024) return LGAE_E_UNSUPPORTED;
@@ -1234,7 +1246,7 @@ int lgae_cg_aggregate_multi_forward(const LgaeCgMultiDesc* d, const int32_t* tab
     const int D1T = p.node_off[d->n_node], D2T = p.edge_off[d->n_edge];
     const size_t fixed = (size_t)p.n_terms * sizeof(double) + ((size_t)2 * p.n_terms + (size_t)4 * p.n_comp + 2) * sizeof(int32_t) + 16;
     const size_t per_ib = ((size_t)p.NJ * p.C * D2T + (size_t)p.C * D1T * D2T) * sizeof(cplx);
-    int ib = std::min<int>(3, p.N);
+    int ib = std::min<int>(LGAE_AGG_FWD_IB, p.N);
     while (ib > 1 && fixed + ib * per_ib > 100 * 1024) --ib;
     const size_t bytes = fixed + ib * per_ib;
     if (bytes > 160 * 1024) return LGAE_E_UNSUPPORTED;
