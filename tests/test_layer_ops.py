@@ -121,7 +121,8 @@ def test_cg_product_rejects_cpu_tensors_and_bad_shapes():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape,cin,cout,d", [((2, 5), 15, 4, 4), ((3,), 7, 9, 1), ((2, 3, 3), 40, 8, 9), ((700,), 20, 4, 4)])
+@pytest.mark.parametrize("shape,cin,cout,d", [((2, 5), 15, 4, 4), ((3,), 7, 9, 1), ((2, 3, 3), 40, 8, 9), ((700,), 20, 4, 4),
+                                                ((5,), 6, 20, 3), ((4,), 300, 3, 1), ((1,), 1, 1, 1)])
 def test_mix_matches_oracle(shape, cin, cout, d):
     from lgn_autoencoder_b200 import layer_ops
     from oracle import lgae_oracle as orc
@@ -191,7 +192,7 @@ def test_radial_functions_match_oracle(basis, B, N, C):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("rows,nin,nout,slope", [(37, 6, 36, 0.01), (700, 96, 96, None), (1000, 72, 12, 0.01), (5, 3, 130, 0.2),
-                                                 (1003, 128, 128, 0.01), (19, 5, 7, None), (4100, 16, 96, 0.01), (333, 97, 33, 0.3)])
+                                                 (1003, 128, 128, 0.01), (19, 5, 7, None), (4100, 16, 96, 0.01), (333, 97, 33, 0.3), (1, 1, 1, None), (9, 2, 129, 0.01)])
 def test_linear_matches_torch_fp64(rows, nin, nout, slope):
     """Floating-point GEMM kernel: reference = the same op in plain torch fp64 on the CPU; tolerance 1e-12 relative."""
     from lgn_autoencoder_b200 import layer_ops
