@@ -86,7 +86,7 @@ constexpr int RAD_UNIT = 16;   // pairs per work unit (two MMA groups of 8)
 // MMA groups of the unit pick theirs up by shuffle.  Also writes nrm (B, NPS): n_ij, or NaN where the edge is masked,
 // which is all the adjoint needs to re-evaluate the basis functions.
 template <int NT, int KS>
-__global__ void __launch_bounds__(128, LGAE_RFWD_CTAS) radial_fwd_kernel(const RadialArgs a) {
+LGAE_DEV void radial_fwd_body(const RadialArgs& a) {
     constexpr int KP = 4 * KS;
     __shared__ unsigned char ti[RAD_MAXP + RAD_UNIT], tj[RAD_MAXP + RAD_UNIT];
     __shared__ double abc_s[3 * KP];
@@ -176,6 +176,20 @@ __global__ void __launch_bounds__(128, LGAE_RFWD_CTAS) radial_fwd_kernel(const R
     }
 }
 
+template <int NT, int KS>
+__global__ void __launch_bounds__(128, LGAE_RFWD_CTAS) radial_fwd_kernel(const RadialArgs a) {
+    radial_fwd_body<NT, KS>(a);
+}
+// All encoder levels in one launch (blockIdx.y = level): the radial weights depend only on the momenta and on the level's own
+// parameters, so the levels' launches need not be links of the step's dependency chain.
+struct RadialMultiArgs {
+    RadialArgs lv[LGAE_MAX_LEVELS];
+};
+template <int NT, int KS>
+__global__ void __launch_bounds__(128, LGAE_RFWD_CTAS) radial_fwd_multi_kernel(const RadialMultiArgs m) {
+    radial_fwd_body<NT, KS>(m.lv[blockIdx.y]);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // adjoint
 // ------------------------------------------------------------------------------------------------------------
@@ -222,7 +236,7 @@ LGAE_DEV void rad_fetch(const RadialArgs& a, const unsigned char* ti, const unsi
 }
 
 template <int NT, int KS>
-__global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_kernel(const RadialArgs a) {
+LGAE_DEV void radial_bwd_body(const RadialArgs& a) {
     constexpr int KP = 4 * KS;
     constexpr int NT2 = KS / 2 + 1;
     constexpr int NK = 8 * NT2, NCOL = 8 * NT;
@@ -344,6 +358,15 @@ __global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_kernel(const R
     }
 }
 
+template <int NT, int KS>
+__global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_kernel(const RadialArgs a) {
+    radial_bwd_body<NT, KS>(a);
+}
+template <int NT, int KS>
+__global__ void __launch_bounds__(128, LGAE_RBWD_CTAS) radial_bwd_multi_kernel(const RadialMultiArgs m) {
+    radial_bwd_body<NT, KS>(m.lv[blockIdx.y]);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -399,14 +422,40 @@ int run_radial_fwd(const LgaeModelDesc* d, int level, const double* theta, const
     return dispatch_radial(a, false, st);
 }
 
+// R of ALL encoder levels in one launch; needs the same MMA tiling (ceil(4C/8), K) on every level, else LGAE_E_UNSUPPORTED
+// (the caller then launches level by level).
+int run_radial_fwd_all(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
+                       double* const* r, double* nrm, cudaStream_t st) {
+    if (!d || d->is_decoder || !r) return LGAE_E_BADARG;
+    if (batch <= 0) return LGAE_OK;
+    RadialMultiArgs m;
+    int nt = -1;
+    for (int l = 0; l < d->n_levels; ++l) {
+        fill(m.lv[l], d, l, theta, p4, node_mask, batch);
+        m.lv[l].r = r[l];
+        m.lv[l].nrm = l == 0 ? nrm : nullptr;
+        const int t = (4 * m.lv[l].C + 7) / 8;
+        if (nt >= 0 && t != nt) return LGAE_E_UNSUPPORTED;
+        nt = t;
+        if (m.lv[l].N > RAD_MAXN || m.lv[l].C < 1 || m.lv[l].C > LGAE_MAX_CHANNELS) return LGAE_E_UNSUPPORTED;
+    }
+    const int ks = pick_ks(d->n_basis);
+    if (ks < 0) return LGAE_E_UNSUPPORTED;
+    LaunchScope ls_("radial_fwd", st);
+#define LGAE_CASE(NTV, KSV) \
+    if (nt == NTV && ks == KSV) { launch_k(radial_fwd_multi_kernel<NTV, KSV>, dim3(radial_fwd_grid(), d->n_levels), dim3(128), 0, st, m); return check_launch("radial_fwd"); }
+    LGAE_CASE(1, 3) LGAE_CASE(2, 3) LGAE_CASE(3, 3) LGAE_CASE(4, 3)
+    LGAE_CASE(1, 5) LGAE_CASE(2, 5) LGAE_CASE(3, 5) LGAE_CASE(4, 5)
+    LGAE_CASE(1, 8) LGAE_CASE(2, 8) LGAE_CASE(3, 8) LGAE_CASE(4, 8)
+#undef LGAE_CASE
+    return LGAE_E_UNSUPPORTED;
+}
+
 int64_t radial_part_width(const LgaeModelDesc* d, int level) { return (int64_t)4 * d->channels[level] * (d->n_basis + 1) + 3 * d->n_basis; }
 
 // Adjoint: g_r (B,N,C,32,4) -> partial rows for a, b, c, linear.{0,1}.{weight,bias} of the level.
-int run_radial_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
-                   const double* g_r, const double* nrm, PartPlan* plan, cudaStream_t st) {
-    if (!d || d->is_decoder || level < 0 || level >= d->n_levels || !g_r || !nrm || !plan) return LGAE_E_BADARG;
-    if (batch <= 0) return LGAE_OK;
-    RadialArgs a;
+static int prep_radial_bwd(RadialArgs& a, const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask,
+                           int batch, const double* g_r, const double* nrm, PartPlan* plan) {
     fill(a, d, level, theta, p4, node_mask, batch);
     a.g_r = g_r;
     a.nrm = const_cast<double*>(nrm);
@@ -427,8 +476,42 @@ int run_radial_bwd(const LgaeModelDesc* d, int level, const double* theta, const
     seg(a.off_w0, a.po_w0, (int64_t)2 * C * K); seg(a.off_b0, a.po_b0, 2 * C);
     seg(a.off_w1, a.po_w1, (int64_t)2 * C * K); seg(a.off_b1, a.po_b1, 2 * C);
     seg(a.off_a, a.po_a, K); seg(a.off_b, a.po_b, K); seg(a.off_c, a.po_c, K);
-    if (rc != LGAE_OK) return rc;
+    return rc;
+}
+int run_radial_bwd(const LgaeModelDesc* d, int level, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
+                   const double* g_r, const double* nrm, PartPlan* plan, cudaStream_t st) {
+    if (!d || d->is_decoder || level < 0 || level >= d->n_levels || !g_r || !nrm || !plan) return LGAE_E_BADARG;
+    if (batch <= 0) return LGAE_OK;
+    RadialArgs a;
+    if (int rc = prep_radial_bwd(a, d, level, theta, p4, node_mask, batch, g_r, nrm, plan)) return rc;
     return dispatch_radial(a, true, st);
+}
+// Whether run_radial_fwd_all / run_radial_bwd_all can serve this model (same MMA tiling on every level).
+bool radial_all_supported(const LgaeModelDesc* d) {
+    if (!d || d->is_decoder || d->n_particles > RAD_MAXN || pick_ks(d->n_basis) < 0) return false;
+    for (int l = 0; l < d->n_levels; ++l) {
+        if (d->channels[l] < 1 || d->channels[l] > LGAE_MAX_CHANNELS) return false;
+        if ((4 * d->channels[l] + 7) / 8 != (4 * d->channels[0] + 7) / 8) return false;
+    }
+    return true;
+}
+// The adjoints of all levels in one launch, after the last level adjoint has written its dL/dR.
+int run_radial_bwd_all(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int batch,
+                       const double* const* g_r, const double* nrm, PartPlan* plan, cudaStream_t st) {
+    if (!radial_all_supported(d) || !g_r || !nrm || !plan) return LGAE_E_UNSUPPORTED;
+    if (batch <= 0) return LGAE_OK;
+    RadialMultiArgs m;
+    for (int l = 0; l < d->n_levels; ++l)
+        if (int rc = prep_radial_bwd(m.lv[l], d, l, theta, p4, node_mask, batch, g_r[l], nrm, plan)) return rc;
+    const int nt = (4 * d->channels[0] + 7) / 8, ks = pick_ks(d->n_basis);
+    LaunchScope ls_("radial_bwd", st);
+#define LGAE_CASE(NTV, KSV) \
+    if (nt == NTV && ks == KSV) { launch_k(radial_bwd_multi_kernel<NTV, KSV>, dim3(radial_grid(), d->n_levels), dim3(128), 0, st, m); return check_launch("radial_bwd"); }
+    LGAE_CASE(1, 3) LGAE_CASE(2, 3) LGAE_CASE(3, 3) LGAE_CASE(4, 3)
+    LGAE_CASE(1, 5) LGAE_CASE(2, 5) LGAE_CASE(3, 5) LGAE_CASE(4, 5)
+    LGAE_CASE(1, 8) LGAE_CASE(2, 8) LGAE_CASE(3, 8) LGAE_CASE(4, 8)
+#undef LGAE_CASE
+    return LGAE_E_UNSUPPORTED;
 }
 
 }  // namespace lgae
