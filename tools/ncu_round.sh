@@ -7,7 +7,7 @@ $CMD > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gp
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches_bench.csv $CMD > gpurun_out/${tag}_ncu_launch.log 2>&1
 python tools/summarize_launches.py gpurun_out/${tag}_launches_bench.csv gpurun_out/${tag}_launches_bench.txt | tail -40
 # (kernel regex, launches of that family to skip so that the C = 4 / width-48 instance is captured)
-for spec in "level_bwd:3" "mlp_bwd:1" "level_fwd:2" "mlp_fwd:1" "radial_bwd:0" "radial_fwd:2" "reduce_segs:0"; do
+for spec in "level_bwd:3" "mlp_bwd:1" "level_fwd:2" "mlp_fwd:1" "radial_bwd:0" "radial_fwd_multi:0" "reduce_segs:0"; do
   k=${spec%%:*}; s=${spec##*:}
   ncu --set full --clock-control none --import-source on -k regex:${k}_kernel -s $s -c 1 -f -o gpurun_out/${tag}_ncu_${k} $CMD > gpurun_out/${tag}_ncu_${k}.log 2>&1
   python tools/ncu_summary.py gpurun_out/${tag}_ncu_${k}.ncu-rep > gpurun_out/${tag}_ncu_${k}.txt 2>&1
