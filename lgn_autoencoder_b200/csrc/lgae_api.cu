@@ -43,7 +43,7 @@ int64_t mlp_part_width(const LgaeModelDesc* d, int level);
 int mlp_bwd_grid();
 int run_enc_input(const LgaeModelDesc* d, const double* theta, const double* p4, int B, double* mass, double* S, double* V, cudaStream_t st);
 int run_enc_input_bwd(const LgaeModelDesc* d, const double* p4, const double* mass, int B, const double* gS, const double* gV, PartPlan* plan, cudaStream_t st);
-int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* lat00, double* lat11, int32_t* sel, cudaStream_t st);
+int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* lat00, double* lat11, int32_t* sel, cudaStream_t st, int parts = 3);
 int run_enc_latent_bwd(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, const int32_t* sel,
                        const double* g_lat00, const double* g_lat11, double* gS, double* gV, PartPlan* plan, cudaStream_t st);
 int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const double* lat11, double* y, double* S, double* V, cudaStream_t st);
@@ -59,7 +59,7 @@ int run_latent_bridge_bwd(const LgaeModelDesc* dd, const double* theta_d, const 
 int run_reduce_plan(PartPlan* plan, int64_t n_params, double* gtheta, const double* theta, double lambda, double* loss, cudaStream_t st);
 int reduce_scratch_doubles();
 int run_latent_bridge(const LgaeModelDesc* de, const double* theta_e, const LgaeModelDesc* dd, const double* theta_d, int B, const double* S,
-                      const double* V, double* lat00, double* lat11, int32_t* sel, double* y, double* S0, double* V0, cudaStream_t st);
+                      const double* V, double* lat00, double* lat11, int32_t* sel, double* y, double* S0, double* V0, cudaStream_t st, int parts = 3);
 int run_dec_tail(const LgaeModelDesc* d, const double* theta, int B, int M, const double* V, const double* target, double* recon,
                  double* g_recon, double* gV, double* jet_loss, double* loss, unsigned int* counter, int mode, PartPlan* plan, cudaStream_t st);
 int run_grad_init2(const double* theta_a, int64_t na, const double* theta_b, int64_t nb, int64_t off_b, double* gtheta, double lambda,
@@ -368,6 +368,10 @@ int64_t lgae_partials_doubles(const LgaeModelDesc* d, int32_t batch) {
 
 // The same for the radial adjoints (one launch after the last level adjoint) loses: 0.8478 vs 0.8413 ms per step, the dL/dR
 // of the upper levels is no longer in L2 when it is read.  Kept behind LGAE_RADIAL_MERGE_BWD=1 for A/B.
+static bool defer_last_mlp() {
+    static const bool on = [] { const char* e = getenv("LGAE_NO_DEFER"); return !(e && e[0] == '1'); }();
+    return on;
+}
 static bool radial_merge_bwd() {
     static const bool on = [] { const char* e = getenv("LGAE_RADIAL_MERGE_BWD"); return e && e[0] == '1'; }();
     return on;
@@ -380,7 +384,7 @@ static bool radial_merge() {
 // Launch sequence of LGNEncoder.forward; `pack` = also pack the MLP weights (a caller that runs both models packs them once).
 static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const double* p4, const uint8_t* node_mask, int32_t batch,
                               double* ws, double* lat00, double* lat11, int32_t* sel, bool pack, cudaStream_t st, bool with_latent = true,
-                              bool with_input = true, cudaEvent_t pack_done = nullptr) {
+                              bool with_input = true, cudaEvent_t pack_done = nullptr, bool skip_last_mlp = false) {
     const Layout L = layout(d, batch);
     const int64_t rows = (int64_t)batch * d->n_particles;
     SideStream* ss = L.rsave[0] >= 0 ? side_stream() : nullptr;
@@ -414,7 +418,8 @@ static int enc_forward_launch(const LgaeModelDesc* d, const double* theta, const
         LGAE_TRY(run_level_fwd(d, l, theta, p4, node_mask, batch, ws + L.S[l], ws + L.V[l], ws + L.sums[l],
                                L.rsave[l] >= 0 ? ws + L.rsave[l] : nullptr, ws + L.spre[l], ws + L.V[l + 1], st));
         if (l == 0 && pack_done) LGAE_CUDA_TRY(cudaStreamWaitEvent(st, pack_done, 0), "pack wait");   // packed on another stream
-        if (d->has_mlp) LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
+        if (d->has_mlp && !(skip_last_mlp && l == d->n_levels - 1))
+            LGAE_TRY(run_mlp(d, l, theta, ws + L.wpack[l], ws + L.spre[l], rows, ws + L.acts[l], ws + L.S[l + 1], nullptr, nullptr, nullptr, false, st));
     }
     if (!with_latent) return LGAE_OK;   // the caller runs the fused latent bridge
     return run_enc_latent(d, theta, batch, ws + L.S[d->n_levels], ws + L.V[d->n_levels], lat00, lat11, sel, st);
@@ -679,13 +684,25 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
     // x: the (normalised) jets = the loss target; xe: what the encoder reads (x times the encoder's input scale)
     xe = scaled_input(enc, x, batch, ws_enc, true, st, &rc_scale);
     LGAE_TRY(rc_scale);
+    // The scalar MLP of the encoder's last level only feeds the latent scalars, an output of the step that neither the decoder nor
+    // the loss reads: it runs, with the scalar half of the latent map, as a branch on the auxiliary stream (LGAE_NO_DEFER=1: in line)
+    const bool defer = aux && phase == 0 && enc->has_mlp && defer_last_mlp();
     LGAE_TRY(enc_forward_launch(enc, theta_enc, xe, node_mask, batch, ws_enc, lat00, lat11, sel, false, st, false, !normalize || scaled,
-                                aux ? aux->join[0] : nullptr));
+                                aux ? aux->join[0] : nullptr, defer));
     {
         // fused encoder latent map + decoder input map
         const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
-        LGAE_TRY(run_latent_bridge(enc, theta_enc, dec, theta_dec, batch, ws_enc + Le.S[enc->n_levels], ws_enc + Le.V[enc->n_levels], lat00,
-                                   lat11, sel, ws_dec + Ld.y, ws_dec + Ld.S[0], ws_dec + Ld.V[0], st));
+        const int nl = enc->n_levels;
+        if (defer) {
+            LGAE_CUDA_TRY(cudaEventRecord(aux->fork[3], st), "aux fork");
+            LGAE_CUDA_TRY(cudaStreamWaitEvent(aux->s, aux->fork[3], 0), "aux fork wait");
+            LGAE_TRY(run_mlp(enc, nl - 1, theta_enc, ws_enc + Le.wpack[nl - 1], ws_enc + Le.spre[nl - 1], (int64_t)batch * enc->n_particles,
+                             ws_enc + Le.acts[nl - 1], ws_enc + Le.S[nl], nullptr, nullptr, nullptr, false, aux->s));
+            LGAE_TRY(run_enc_latent(enc, theta_enc, batch, ws_enc + Le.S[nl], ws_enc + Le.V[nl], lat00, lat11, sel, aux->s, 1));
+            LGAE_CUDA_TRY(cudaEventRecord(aux->join[4], aux->s), "aux join");
+        }
+        LGAE_TRY(run_latent_bridge(enc, theta_enc, dec, theta_dec, batch, ws_enc + Le.S[nl], ws_enc + Le.V[nl], lat00,
+                                   lat11, sel, ws_dec + Ld.y, ws_dec + Ld.S[0], ws_dec + Ld.V[0], st, defer ? 2 : 3));
     }
     LGAE_TRY(dec_forward_launch(dec, theta_dec, lat11, batch, ws_dec, recon, nullptr, false, st, false, false, !keep_dead_mlp()));
     // one plan per model over the same partials buffer (the encoder's continues where the decoder's ends): the decoder's rows are
@@ -704,6 +721,7 @@ static int train_step_impl(const LgaeModelDesc* enc, const LgaeModelDesc* dec, c
         // fused adjoint of the bridge: decoder input map, then encoder latent map, latent gradient handed over on chip
         const Layout Le = layout(enc, batch), Ld = layout(dec, batch);
         const int cur = dec->n_levels & 1;
+        if (defer) LGAE_CUDA_TRY(cudaStreamWaitEvent(st, aux->join[4], 0), "aux join wait");   // S of the last level, latent scalars, sel
         LGAE_TRY(run_latent_bridge_bwd(dec, theta_dec, enc, theta_enc, batch, lat11, ws_dec + Ld.y, ws_dec + Ld.gS[cur], ws_dec + Ld.gV[cur],
                                        ws_dec + Ld.gy, g_lat11, ws_enc + Le.S[enc->n_levels], ws_enc + Le.V[enc->n_levels], sel,
                                        ws_enc + Le.gS[0], ws_enc + Le.gV[0], &plan_d, &plan_e, st));

@@ -102,6 +102,7 @@ struct LatentArgs {
     const double* theta;
     int64_t off00, off11;
     int B, N, C, tau_s, tau_v, mode;
+    int parts;         // forward: 1 = latent scalars only, 2 = latent vectors only, 3 = both
     const double* S;   // (B,N,C,2)
     const double* V;   // (B,N,C,4,2)
     double* lat00;     // (2,B,1,Ts,1)
@@ -132,13 +133,14 @@ LGAE_DEV void enc_latent_body(const LatentArgs& a, double* smem, cplx* lat_out) 
     cplx* L11 = L00 + rows * ts;
     const cplx* S = reinterpret_cast<const cplx*>(a.S) + (int64_t)b * N * C;
     const cplx* V = reinterpret_cast<const cplx*>(a.V) + (int64_t)b * N * C * 4;
-    for (int it = tid; it < rows * ts; it += blockDim.x) {
+    const bool do_s = (a.parts & 1) != 0, do_v = (a.parts & 2) != 0;
+    for (int it = tid; do_s && it < rows * ts; it += blockDim.x) {
         const int i = it / ts, t = it % ts;
         cplx acc = czero();
         for (int k = 0; k < cin; ++k) cfma(acc, wget(a.theta, a.off00, ts, cin, t, k), S[i * cin + k]);
         L00[it] = acc;
     }
-    for (int it = tid; it < rows * tv; it += blockDim.x) {
+    for (int it = tid; do_v && it < rows * tv; it += blockDim.x) {
         const int i = it / tv, t = it % tv;
         cplx acc[4] = {czero(), czero(), czero(), czero()};
         for (int k = 0; k < cin; ++k) {
@@ -156,13 +158,13 @@ LGAE_DEV void enc_latent_body(const LatentArgs& a, double* smem, cplx* lat_out) 
     const int mode = a.mode;
     if (mode == LGAE_LATENT_MEAN || mode == LGAE_LATENT_SUM || mix) {
         const double scale = mode == LGAE_LATENT_MEAN ? 1.0 / N : 1.0;
-        for (int it = tid; it < ts; it += blockDim.x) {
+        for (int it = tid; do_s && it < ts; it += blockDim.x) {
             cplx acc = czero();
             for (int i = 0; i < rows; ++i) acc = cadd(acc, L00[i * ts + it]);
             a.lat00[(int64_t)(0 * B + b) * ts + it] = acc.x * scale;
             a.lat00[(int64_t)(1 * B + b) * ts + it] = acc.y * scale;
         }
-        for (int it = tid; it < tv * 4; it += blockDim.x) {
+        for (int it = tid; do_v && it < tv * 4; it += blockDim.x) {
             cplx acc = czero();
             for (int i = 0; i < rows; ++i) acc = cadd(acc, L11[i * tv * 4 + it]);
             a.lat11[(int64_t)(0 * B + b) * tv * 4 + it] = acc.x * scale;
@@ -175,7 +177,7 @@ LGAE_DEV void enc_latent_body(const LatentArgs& a, double* smem, cplx* lat_out) 
     const bool both = mode == LGAE_LATENT_MINMAX;
     const int Ts = both ? 2 * ts : ts, Tv = both ? 2 * tv : tv;
     const int tmax = ts > tv ? ts : tv;
-    for (int it = tid; it < 2 * 2 * ts; it += blockDim.x) {          // scalars: [kind][part][t]
+    for (int it = tid; do_s && it < 2 * 2 * ts; it += blockDim.x) {          // scalars: [kind][part][t]
         const int t = it % ts, part = (it / ts) & 1, kind = it / (2 * ts);   // kind 0 = min, 1 = max
         if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
         int best = 0;
@@ -191,7 +193,7 @@ LGAE_DEV void enc_latent_body(const LatentArgs& a, double* smem, cplx* lat_out) 
         a.lat00[(int64_t)(part * B + b) * Ts + T] = part ? z.y : z.x;
         if (a.sel) a.sel[((int64_t)((kind)*2 + part) * B + b) * tmax + t] = best;
     }
-    for (int it = tid; it < 2 * 2 * tv; it += blockDim.x) {          // vectors
+    for (int it = tid; do_v && it < 2 * 2 * tv; it += blockDim.x) {          // vectors
         const int t = it % tv, part = (it / tv) & 1, kind = it / (2 * tv);
         if (!both && kind != (mode == LGAE_LATENT_MAX ? 1 : 0)) continue;
         int best = 0;
@@ -1138,14 +1140,15 @@ static LatentArgs latent_args(const LgaeModelDesc* d, const double* theta, int B
     LatentArgs a;
     a.theta = theta; a.off00 = d->off_lat00; a.off11 = d->off_lat11;
     a.B = B; a.N = d->n_particles; a.C = d->channels[d->n_levels]; a.tau_s = d->tau_s; a.tau_v = d->tau_v; a.mode = d->latent_mode;
+    a.parts = 3;
     a.S = S; a.V = V; a.lat00 = nullptr; a.lat11 = nullptr; a.sel = nullptr; a.g_lat00 = nullptr; a.g_lat11 = nullptr;
     a.gS = nullptr; a.gV = nullptr; a.partials = nullptr; a.part_stride = 0; a.po00 = 0; a.po11 = 0;
     return a;
 }
 int run_enc_latent(const LgaeModelDesc* d, const double* theta, int B, const double* S, const double* V, double* lat00, double* lat11,
-                   int32_t* sel, cudaStream_t st) {
+                   int32_t* sel, cudaStream_t st, int parts) {
     LatentArgs a = latent_args(d, theta, B, S, V);
-    a.lat00 = lat00; a.lat11 = lat11; a.sel = sel;
+    a.lat00 = lat00; a.lat11 = lat11; a.sel = sel; a.parts = parts;
     const int rows = a.mode == LGAE_LATENT_MIX ? 1 : a.N;
     const size_t bytes = (size_t)rows * (a.tau_s + 4 * a.tau_v) * sizeof(cplx);
     if (bytes > 200 * 1024) return LGAE_E_UNSUPPORTED;
@@ -1191,9 +1194,9 @@ int run_dec_input(const LgaeModelDesc* d, const double* theta, int B, const doub
 }
 // enc_latent + dec_input fused (training step / inference of both models back to back).
 int run_latent_bridge(const LgaeModelDesc* de, const double* theta_e, const LgaeModelDesc* dd, const double* theta_d, int B, const double* S,
-                      const double* V, double* lat00, double* lat11, int32_t* sel, double* y, double* S0, double* V0, cudaStream_t st) {
+                      const double* V, double* lat00, double* lat11, int32_t* sel, double* y, double* S0, double* V0, cudaStream_t st, int parts) {
     LatentArgs a = latent_args(de, theta_e, B, S, V);
-    a.lat00 = lat00; a.lat11 = lat11; a.sel = sel;
+    a.lat00 = lat00; a.lat11 = lat11; a.sel = sel; a.parts = parts;
     DecInArgs di = dec_in_args(dd, theta_d, B, lat11, y, S0, V0);
     const int rows = a.mode == LGAE_LATENT_MIX ? 1 : a.N;
     const int mult = a.mode == LGAE_LATENT_MINMAX ? 2 : 1;
