@@ -202,7 +202,9 @@ int lgae_l1(const double* theta, int64_t n, double lambda, double* out_accumulat
  * concat -> complex channel mix.  Encoder flavour: p (B,N,4) real Cartesian + node_mask, radial parameters
  * from theta at level `level`.  Decoder flavour: y (B,N,4,2) complex canonical, constant radial weights.
  * s_in (B,N,C,2), v_in (B,N,C,4,2) -> s_pre (B,N,C',2), v_out (B,N,C',4,2), sums (B,N,C,10,2).
- * r_save (encoder, N <= 32, may be NULL): (B,N,C,32,4) copy of the radial weights, required by the adjoint. */
+ * r_save (encoder, N <= 32, may be NULL): (B,N,C,32,4) copy of the radial weights, required by the adjoint; with more than 32
+ * particles pass NULL (the level kernel then evaluates the radial weights tile by tile), a non-NULL r_save returns
+ * LGAE_E_UNSUPPORTED. */
 int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* theta, const double* p_or_y,
                        const uint8_t* node_mask, int32_t batch, const double* s_in, const double* v_in,
                        double* sums, double* r_save, double* s_pre, double* v_out, void* stream);

@@ -821,6 +821,7 @@ int lgae_level_forward(const LgaeModelDesc* d, int32_t level, const double* thet
                        void* stream) {
     LGAE_TRY(check_desc(d));
     if (!theta || !p_or_y || !s_in || !v_in || !sums || !s_pre || !v_out || batch < 0 || level < 0 || level >= d->n_levels) return LGAE_E_BADARG;
+    if (!d->is_decoder && r_save && d->n_particles > 32) return LGAE_E_UNSUPPORTED;   // the saved radial weights are a 32-particle layout
     if (!d->is_decoder && d->n_particles <= 32 && r_save)
         LGAE_TRY(run_radial_fwd(d, level, theta, p_or_y, node_mask, batch, r_save, nullptr, (cudaStream_t)stream));
     return run_level_fwd(d, level, theta, p_or_y, node_mask, batch, s_in, v_in, sums, r_save, s_pre, v_out, (cudaStream_t)stream);
