@@ -76,6 +76,12 @@ def test_bad_arguments_are_rejected_before_any_launch():
     assert lib.lgae_encoder_forward(None, None, None, None, 4, None, None, None, None, None) == -1
     bad = _lib.LgaeModelDesc()
     assert lib.lgae_workspace_doubles(C.byref(bad), 4) == -1
+    # the saved-radial-weights buffer of the level entry point is a 32-particle layout: refused (LGAE_E_UNSUPPORTED) for longer
+    # jets before anything is launched (the pointers are never dereferenced on the host)
+    plan40, _ = _plan(40)
+    fake = C.c_void_p(0x1000)
+    assert lib.lgae_level_forward(C.byref(plan40.desc), 0, fake, fake, None, 2, fake, fake, fake, fake, fake, fake, None) == -2
+    assert lib.lgae_level_forward(C.byref(plan40.desc), 9, fake, fake, None, 2, fake, fake, fake, fake, fake, fake, None) == -1
 
 
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
